@@ -1,0 +1,202 @@
+/*
+ * rvs_cuda.h — C ABI of the B200-native collision-and-distance engine that sits behind
+ * RPMPLv2's `base::RealVectorSpace` (librvs_cuda.so).
+ *
+ * Every entry point below replaces one piece of the reference's single-threaded CPU hot path.
+ * Citations are `path:line` inside the reference tree (robotics-ETF/RPMPLv2 @ 481d3ffb):
+ *
+ *   rvs_create / rvs_destroy          <- scenario::Scenario ctor, the `robot.space` switch
+ *                                        (src/scenario/Scenario.cpp:105-112) + robot ctors
+ *                                        (src/robots/xArm6.cpp:7-78, src/robots/Planar2DOF.cpp:7-64)
+ *   rvs_set_obstacles                 <- env::Environment ctor / addObject
+ *                                        (src/environments/Environment.cpp:13-62,116-131),
+ *                                        env::Box ctor (src/environments/objects/Box.cpp:3-15)
+ *   rvs_update_obstacle_aabbs         <- env::Object::setPosition + Environment::updateEnvironment
+ *                                        (src/environments/Object.cpp:21-26, Environment.cpp:194-377)
+ *   rvs_is_valid                      <- RealVectorSpace::isValid(q)
+ *                                        (src/state_spaces/real_vector_space/RealVectorSpace.cpp:277-309)
+ *   rvs_is_valid_edges                <- RealVectorSpace::isValid(q1,q2)        (RealVectorSpace.cpp:261-275)
+ *   rvs_distance                      <- RealVectorSpace::computeDistance       (RealVectorSpace.cpp:318-392)
+ *   rvs_underestimation               <- RealVectorSpace::computeDistanceUnderestimation (RealVectorSpace.cpp:402-446)
+ *   rvs_skeleton                      <- AbstractRobot::computeSkeleton         (src/robots/xArm6.cpp:209-235,
+ *                                        src/robots/Planar2DOF.cpp:117-130)
+ *   rvs_enclosing_radii               <- AbstractRobot::computeEnclosingRadii   (src/robots/xArm6.cpp:237-275,
+ *                                        Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30)
+ *   rvs_self_collision_capsules       <- xArm6::checkSelfCollision(q) capsule pre-filter
+ *                                        (src/robots/xArm6.cpp:374-424; FCL mesh stage is NOT covered)
+ *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
+ *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
+ *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no C++ / torch types; all functions return an rvs_status (0 = ok);
+ *    no exception crosses the boundary; a collision is data (`d_c == 0`, verdict byte 0), never an error.
+ *  - configurations `q` are row-major  N x num_dofs  float32 (the reference's Eigen::VectorXf coord).
+ *  - one handle = one device + one CUDA stream; calls on one handle must be serialised by the caller.
+ *  - functions without suffix take HOST pointers and are synchronous (H2D, kernel, D2H inside).
+ *    `_dev` functions take DEVICE pointers, enqueue on the handle's stream and return immediately;
+ *    use rvs_sync() or your own event on rvs_get_stream().
+ *  - there is no CPU fallback: without a usable CUDA device rvs_create fails with RVS_ERR_NO_DEVICE.
+ */
+#ifndef RVS_CUDA_H
+#define RVS_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVS_MAX_DOFS 32
+#define RVS_ABI_VERSION 1
+
+typedef enum {
+    RVS_OK = 0,
+    RVS_ERR_INVALID_ARGUMENT = 1,
+    RVS_ERR_CUDA = 2,
+    RVS_ERR_OUT_OF_MEMORY = 3,
+    RVS_ERR_NO_DEVICE = 4,
+    RVS_ERR_UNSUPPORTED = 5
+} rvs_status;
+
+/* Which reference robot class the chain stands for. It selects the skeleton recipe and the
+ * enclosing-radii recurrence only; FK always comes from the joint chain in the descriptor. */
+typedef enum {
+    RVS_ROBOT_XARM6 = 0,   /* robots::xArm6      (src/robots/xArm6.cpp)        */
+    RVS_ROBOT_PLANAR = 1,  /* robots::Planar2DOF / Planar10DOF (Planar2DOF.cpp) */
+    RVS_ROBOT_SPATIAL = 2  /* robots::Spatial10/14/18/22DOF (Spatial10DOF.cpp)  */
+} rvs_robot_kind;
+
+/* Arithmetic variant of the hot path.
+ *  REF32  : reference-faithful. FK in FP64 (as orocos-KDL does), skeleton narrowed to FP32, all capsule/box
+ *           geometry in FP32 with NO fused multiply-add (the reference is an x86-64 -O3 build without FMA)
+ *           and IEEE division / sqrt.  Verdicts and distances are bit-comparable with the oracle<float>.
+ *  FAST32 : FP32 throughout (FK included), FMA contraction allowed. Stated tolerance 1e-4 m.
+ *  F64    : everything in FP64, outputs through the *_f64 entry points. Tolerance 1e-9 m vs oracle<double>. */
+typedef enum {
+    RVS_PREC_REF32 = 0,
+    RVS_PREC_FAST32 = 1,
+    RVS_PREC_F64 = 2
+} rvs_precision;
+
+typedef enum {
+    RVS_DIST_MIN = 0,      /* d_c only                                         (4 B / configuration)          */
+    RVS_DIST_PROFILE = 1,  /* d_c + per-link profile d_c_profile[L]            (4(1+L) B)                     */
+    RVS_DIST_FULL = 2      /* + nearest points [M][L][6] = (Rx,Ry,Rz,Ox,Oy,Oz) (+24 L M B), State::nearest_points */
+} rvs_distance_mode;
+
+/* Serial revolute chain as parsed from the robot's URDF (kdl_parser semantics):
+ *   T_k = T_{k-1} * Trans(joint_xyz[k]) * RPY(joint_rpy[k]) * Rot(joint_axis[k], q_k),   k = 0 .. num_dofs-1
+ * followed by one fixed tip transform at index num_dofs (xarm6: joint_eef; chains: the `tool` joint). */
+typedef struct {
+    int32_t kind;                               /* rvs_robot_kind */
+    int32_t num_dofs;                           /* n == number of links L (AbstractRobot::getNumLinks) */
+    int32_t ground_included;                    /* AbstractRobot::getGroundIncluded */
+    float   gripper_length;                     /* xArm6 only (src/robots/xArm6.cpp:130,231) */
+    double  joint_xyz[RVS_MAX_DOFS + 1][3];
+    double  joint_rpy[RVS_MAX_DOFS + 1][3];
+    double  joint_axis[RVS_MAX_DOFS][3];
+    float   capsule_radius[RVS_MAX_DOFS];       /* AbstractRobot::getCapsuleRadius(i) */
+    float   limit_lo[RVS_MAX_DOFS];             /* AbstractRobot::getLimits() */
+    float   limit_hi[RVS_MAX_DOFS];
+} rvs_robot_desc;
+
+/* RealVectorSpaceConfig (src/configurations/RealVectorSpaceConfig.cpp:3-5 and
+ * data/configurations/configuration_realvectorspace.yaml) made explicit. */
+typedef struct {
+    float   equality_threshold;                 /* EQUALITY_THRESHOLD (1e-6 compiled, 1e-4 shipped YAML) */
+    float   max_distance;                       /* MAX_DISTANCE (1000) */
+    int32_t num_interpolation_validity_checks;  /* NUM_INTERPOLATION_VALIDITY_CHECKS (15 compiled, 10 YAML) */
+    int32_t precision;                          /* rvs_precision */
+} rvs_params;
+
+/* Parameters of the batched generalized-bur spine primitive (RBTConnectConfig / RGBTConnectConfig,
+ * data/configurations/configuration_rbtconnect.yaml:4-8, configuration_rgbtconnect.yaml:4). */
+typedef struct {
+    int32_t num_layers;            /* RGBTConnectConfig::NUM_LAYERS (5) */
+    int32_t num_iter_spine;        /* RBTConnectConfig::NUM_ITER_SPINE (1) */
+    int32_t use_expanded_bubble;   /* RBTConnectConfig::USE_EXPANDED_BUBBLE (1) */
+    float   d_crit;                /* RBTConnectConfig::D_CRIT (0.05) */
+} rvs_spine_params;
+
+typedef struct rvs_engine *rvs_handle;
+
+/* ---- life cycle ---------------------------------------------------------------------------- */
+int  rvs_abi_version(void);
+int  rvs_device_count(void);
+int  rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device, rvs_handle *out);
+int  rvs_destroy(rvs_handle h);
+const char *rvs_last_error(rvs_handle h);      /* h may be NULL: last error of a failed rvs_create */
+int  rvs_set_params(rvs_handle h, const rvs_params *params);
+int  rvs_set_stream(rvs_handle h, void *cuda_stream);  /* adopt an external cudaStream_t (e.g. torch's) */
+void *rvs_get_stream(rvs_handle h);
+int  rvs_sync(rvs_handle h);
+/* kernels launched by this handle since creation (each counts one grid launch) */
+int64_t rvs_launch_count(rvs_handle h);
+
+/* ---- obstacle table (resident in HBM as SoA) -------------------------------------------------- */
+/* aabb_min / aabb_max: M x 3 float (x,y,z); is_ground: M bytes (label == "ground"); min_dist_tol: M float
+ * or NULL (= max_distance for all). Host pointers. */
+int  rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max,
+                       const uint8_t *is_ground, const float *min_dist_tol, int32_t M);
+int  rvs_update_obstacle_aabbs(rvs_handle h, const float *aabb_min, const float *aabb_max, int32_t M);
+int  rvs_num_obstacles(rvs_handle h);
+
+/* ---- hot path, host pointers, synchronous ------------------------------------------------------ */
+/* valid[i] = 1 iff RealVectorSpace::isValid(q_i) */
+int  rvs_is_valid(rvs_handle h, const float *q, int64_t N, uint8_t *valid);
+/* valid[e] = 1 iff RealVectorSpace::isValid(q1_e, q2_e) (discretised edge, far end first) */
+int  rvs_is_valid_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *valid);
+/* d_c[N]; profile[N x L] (mode >= PROFILE, else may be NULL); nearest[N x M x L x 6] (mode == FULL).
+ * After a collision (d_c == 0) the profile follows the reference's early-exit fill
+ * (RealVectorSpace.cpp:370-378) and the nearest-point block of that configuration is unspecified. */
+int  rvs_distance(rvs_handle h, const float *q, int64_t N, int32_t mode,
+                  float *d_c, float *profile, float *nearest);
+/* planes: R x M x L x 6 nearest-point sets of R root configurations; plane_idx[N] selects the root
+ * per configuration (NULL = root 0 for all). status[i] = 1 when the reference would have returned 0
+ * WITHOUT touching the state (a plane distance < 0, RealVectorSpace.cpp:428-429); d_c[i] is 0 then. */
+int  rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *planes,
+                         const int32_t *plane_idx, int32_t R, float *d_c, float *profile, uint8_t *status);
+/* skeleton[N x (L+1) x 3] */
+int  rvs_skeleton(rvs_handle h, const float *q, int64_t N, float *skeleton);
+/* radii[N x L x (L+1)] row-major (row = start skeleton point, column = end point) */
+int  rvs_enclosing_radii(rvs_handle h, const float *q, int64_t N, float *radii);
+/* xArm6 capsule pre-filter of checkSelfCollision(q): bit0 = pair 0-5, bit1 = 1-5, bit2 = 0-4, bit3 = 1-4 set
+ * when computeCapsulesDistance < 0 ("maybe": the reference then runs an FCL mesh test, which is out of scope).
+ * For every other robot kind the reference's answer is the constant `false` -> all zero. */
+int  rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_t *mask);
+/* Generalized-bur spines from ONE root towards S targets (RGBTConnect::extendGenSpine with
+ * underestimation). q_root[L dofs], root profile/planes come from a FULL distance query of the root.
+ * q_reached[S x n]; d_c_reached[S]; status[S] (base::State::Status: 1 Advanced, 2 Trapped, 3 Reached). */
+int  rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profile, float root_d_c,
+                       const float *root_planes, const float *q_targets, int32_t S,
+                       const rvs_spine_params *sp, float *q_reached, float *d_c_reached, uint8_t *status);
+
+/* ---- FP64 variants (handle must have been created with RVS_PREC_F64) ---------------------------- */
+int  rvs_distance_f64(rvs_handle h, const float *q, int64_t N, int32_t mode,
+                      double *d_c, double *profile, double *nearest);
+int  rvs_is_valid_f64(rvs_handle h, const float *q, int64_t N, uint8_t *valid);
+
+/* ---- device-pointer, stream-ordered variants ---------------------------------------------------- */
+int  rvs_is_valid_dev(rvs_handle h, const float *d_q, int64_t N, uint8_t *d_valid);
+int  rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid);
+int  rvs_distance_dev(rvs_handle h, const float *d_q, int64_t N, int32_t mode,
+                      float *d_d_c, float *d_profile, float *d_nearest);
+int  rvs_distance_f64_dev(rvs_handle h, const float *d_q, int64_t N, int32_t mode,
+                          double *d_d_c, double *d_profile, double *d_nearest);
+int  rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const float *d_planes,
+                             const int32_t *d_plane_idx, int32_t R, float *d_d_c, float *d_profile,
+                             uint8_t *d_status);
+/* Stateless synthetic configurations: q[i][j] = lo_j + (hi_j-lo_j) * u24(splitmix64(seed ^ (i*32+j)))
+ * generated on the device for i in [first, first+N). */
+int  rvs_generate_configs_dev(rvs_handle h, uint64_t seed, int64_t first, int64_t N, float *d_q);
+
+/* ---- tuning knobs (do not change results) ------------------------------------------------------- */
+/* cull != 0 enables the conservative bounding-box pre-test in MIN/PROFILE distance queries: a pair whose
+ * lower bound cannot beat the running per-link minimum skips the exact narrow phase. Results are identical. */
+int  rvs_set_culling(rvs_handle h, int32_t cull);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RVS_CUDA_H */

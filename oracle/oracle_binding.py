@@ -1,0 +1,196 @@
+"""ctypes binding of the CPU oracle (oracle/_build/librvs_oracle.so).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs. No product module may import this file.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional
+
+import numpy as np
+
+from rpmplv2_b200.robots import DIST_FULL, DIST_MIN, DIST_PROFILE, Robot, RvsParams, RvsRobotDesc, default_params
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "_build", "librvs_oracle.so")
+_lib = None
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with g++ (no FMA contraction, like the reference's x86-64 Release build)."""
+    srcs = [os.path.join(_HERE, f) for f in ("rvs_oracle_capi.cpp", "rvs_oracle.hpp")]
+    if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return _LIB_PATH
+    subprocess.run(["make", "-C", _HERE, "-s", "oracle"], check=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = ctypes.CDLL(_LIB_PATH)
+        _lib.orc_create.restype = ctypes.c_void_p
+        _lib.orc_create.argtypes = [ctypes.POINTER(RvsRobotDesc), ctypes.POINTER(RvsParams)]
+        _lib.orc_destroy.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+def _p(a: Optional[np.ndarray], typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Oracle:
+    """CPU oracle with the same call surface as rpmplv2_b200.engine.Engine (host arrays)."""
+
+    def __init__(self, robot: Robot, params: Optional[RvsParams] = None):
+        self.robot = robot
+        self.params = params or default_params()
+        self.n = robot.num_dofs
+        self.M = 0
+        self._desc = robot.to_desc()
+        self._h = ctypes.c_void_p(lib().orc_create(ctypes.byref(self._desc), ctypes.byref(self.params)))
+        if not self._h:
+            raise RuntimeError("orc_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def set_obstacles(self, aabb_min, aabb_max, is_ground=None, min_dist_tol=None):
+        mn, mx = _f32(aabb_min, (-1, 3)), _f32(aabb_max, (-1, 3))
+        self.M = mn.shape[0]
+        g = None if is_ground is None else np.ascontiguousarray(is_ground, np.uint8)
+        t = None if min_dist_tol is None else _f32(min_dist_tol)
+        lib().orc_set_obstacles(self._h, _p(mn, c_f32p), _p(mx, c_f32p), _p(g, c_u8p), _p(t, c_f32p), ctypes.c_int32(self.M))
+
+    def skeleton(self, q, f64=False):
+        q = _f32(q, (-1, self.n))
+        N = q.shape[0]
+        if f64:
+            sk = np.empty((N, self.n + 1, 3), np.float64)
+            lib().orc_skeleton_f64(self._h, _p(q, c_f32p), ctypes.c_int64(N), _p(sk, c_f64p))
+        else:
+            sk = np.empty((N, self.n + 1, 3), np.float32)
+            lib().orc_skeleton_f32(self._h, _p(q, c_f32p), ctypes.c_int64(N), _p(sk, c_f32p))
+        return sk
+
+    def is_valid(self, q, f64=False, threads=1):
+        q = _f32(q, (-1, self.n))
+        out = np.empty(q.shape[0], np.uint8)
+        fn = lib().orc_is_valid_f64 if f64 else lib().orc_is_valid_f32
+        fn(self._h, _p(q, c_f32p), ctypes.c_int64(q.shape[0]), _p(out, c_u8p), ctypes.c_int(threads))
+        return out
+
+    def is_valid_edges(self, q1, q2, threads=1):
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        out = np.empty(q1.shape[0], np.uint8)
+        lib().orc_is_valid_edges_f32(self._h, _p(q1, c_f32p), _p(q2, c_f32p), ctypes.c_int64(q1.shape[0]), _p(out, c_u8p),
+                                     ctypes.c_int(threads))
+        return out
+
+    def distance(self, q, mode=DIST_PROFILE, f64=False, threads=1):
+        q = _f32(q, (-1, self.n))
+        N = q.shape[0]
+        dt, pt, fn = (np.float64, c_f64p, lib().orc_distance_f64) if f64 else (np.float32, c_f32p, lib().orc_distance_f32)
+        d_c = np.empty(N, dt)
+        profile = np.zeros((N, self.n), dt) if mode >= DIST_PROFILE else None
+        nearest = np.zeros((N, self.M, self.n, 6), dt) if mode == DIST_FULL else None
+        fn(self._h, _p(q, c_f32p), ctypes.c_int64(N), ctypes.c_int32(mode), _p(d_c, pt), _p(profile, pt), _p(nearest, pt),
+           ctypes.c_int(threads))
+        return d_c, profile, nearest
+
+    def underestimation(self, q, planes, plane_idx=None):
+        q = _f32(q, (-1, self.n))
+        N = q.shape[0]
+        planes = _f32(planes, (-1, self.M, self.n, 6))
+        idx = None if plane_idx is None else np.ascontiguousarray(plane_idx, np.int32)
+        d_c, profile, status = np.empty(N, np.float32), np.empty((N, self.n), np.float32), np.empty(N, np.uint8)
+        rc = lib().orc_underestimation_f32(self._h, _p(q, c_f32p), ctypes.c_int64(N), _p(planes, c_f32p), _p(idx, c_i32p),
+                                           ctypes.c_int32(planes.shape[0]), _p(d_c, c_f32p), _p(profile, c_f32p), _p(status, c_u8p))
+        if rc:
+            raise ValueError("plane_idx out of range")
+        return d_c, profile, status
+
+    def enclosing_radii(self, q):
+        q = _f32(q, (-1, self.n))
+        out = np.empty((q.shape[0], self.n, self.n + 1), np.float32)
+        lib().orc_enclosing_radii_f32(self._h, _p(q, c_f32p), ctypes.c_int64(q.shape[0]), _p(out, c_f32p))
+        return out
+
+    def self_collision_capsules(self, q):
+        q = _f32(q, (-1, self.n))
+        out = np.empty(q.shape[0], np.uint8)
+        lib().orc_self_collision_capsules_f32(self._h, _p(q, c_f32p), ctypes.c_int64(q.shape[0]), _p(out, c_u8p))
+        return out
+
+    def generate_configs(self, seed: int, first: int, N: int):
+        q = np.empty((N, self.n), np.float32)
+        lib().orc_generate_configs(self._h, ctypes.c_uint64(seed), ctypes.c_int64(first), ctypes.c_int64(N), _p(q, c_f32p))
+        return q
+
+
+# --- primitives -------------------------------------------------------------------------------------------------
+
+def seg_seg(ABCD, thr=1e-4, maxd=1000.0, f64=False):
+    dt, pt = (np.float64, c_f64p) if f64 else (np.float32, c_f32p)
+    a = np.ascontiguousarray(ABCD, dt).reshape(-1, 12)
+    out = np.empty((a.shape[0], 8), dt)
+    ct = ctypes.c_double if f64 else ctypes.c_float
+    (lib().orc_seg_seg_f64 if f64 else lib().orc_seg_seg_f32)(ctypes.c_int64(a.shape[0]), _p(a, pt), ct(thr), ct(maxd), _p(out, pt))
+    return out
+
+
+def seg_point(ABC, thr=1e-4, maxd=1000.0):
+    a = _f32(ABC, (-1, 9))
+    out = np.empty((a.shape[0], 8), np.float32)
+    lib().orc_seg_point_f32(ctypes.c_int64(a.shape[0]), _p(a, c_f32p), ctypes.c_float(thr), ctypes.c_float(maxd), _p(out, c_f32p))
+    return out
+
+
+def capsule_box_distance(AB, radius, obs, thr=1e-4, maxd=1000.0, f64=False):
+    dt, pt = (np.float64, c_f64p) if f64 else (np.float32, c_f32p)
+    ct = ctypes.c_double if f64 else ctypes.c_float
+    a = np.ascontiguousarray(AB, dt).reshape(-1, 6)
+    o = np.ascontiguousarray(obs, dt).reshape(-1, 6)
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, dt), (a.shape[0],)))
+    out = np.empty((a.shape[0], 8), dt)
+    fn = lib().orc_capsule_box_distance_f64 if f64 else lib().orc_capsule_box_distance_f32
+    fn(ctypes.c_int64(a.shape[0]), _p(a, pt), _p(r, pt), _p(o, pt), ct(thr), ct(maxd), _p(out, pt))
+    return out
+
+
+def capsule_box_collision(AB, radius, obs, thr=1e-4, maxd=1000.0):
+    a, o = _f32(AB, (-1, 6)), _f32(obs, (-1, 6))
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (a.shape[0],)))
+    out = np.empty(a.shape[0], np.uint8)
+    lib().orc_capsule_box_collision_f32(ctypes.c_int64(a.shape[0]), _p(a, c_f32p), _p(r, c_f32p), _p(o, c_f32p),
+                                        ctypes.c_float(thr), ctypes.c_float(maxd), _p(out, c_u8p))
+    return out
+
+
+def capsule_rect_collision(AB, radius, obs, face, thr=1e-4, maxd=1000.0):
+    a, o = _f32(AB, (-1, 6)), _f32(obs, (-1, 6))
+    r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (a.shape[0],)))
+    f = np.ascontiguousarray(np.broadcast_to(np.asarray(face, np.int32), (a.shape[0],)))
+    out = np.empty(a.shape[0], np.uint8)
+    lib().orc_capsule_rect_collision_f32(ctypes.c_int64(a.shape[0]), _p(a, c_f32p), _p(r, c_f32p), _p(o, c_f32p), _p(f, c_i32p),
+                                         ctypes.c_float(thr), ctypes.c_float(maxd), _p(out, c_u8p))
+    return out

@@ -1,0 +1,259 @@
+// rvs_oracle_capi.cpp — C entry points of the CPU oracle for ctypes (TEST INFRASTRUCTURE ONLY; see rvs_oracle.hpp).
+// Mirrors the argument layout of include/rvs_cuda.h so the parity tests can feed both sides the same arrays.
+#include <thread>
+
+#include "../include/rvs_cuda.h"
+#include "rvs_oracle.hpp"
+
+namespace {
+
+struct Engine {
+    orc::Robot robot;
+    std::vector<float> lo, hi;
+    rvs_params prm;
+    orc::Scene<float> sc32;
+    orc::Scene<double> sc64;
+};
+
+template <class T> struct Pick;
+template <> struct Pick<float> { static const orc::Scene<float> &scene(const Engine &e) { return e.sc32; } };
+template <> struct Pick<double> { static const orc::Scene<double> &scene(const Engine &e) { return e.sc64; } };
+
+template <class T>
+orc::Config<T> config_of(const rvs_params &p) {
+    return {T(p.equality_threshold), T(p.max_distance), int(p.num_interpolation_validity_checks)};
+}
+
+// static split of [0, N) over `threads` std::threads (the reference itself is single-threaded)
+template <class F>
+void parallel_for(int64_t N, int threads, F &&body) {
+    if (threads <= 1 || N < 2) { body(int64_t(0), N); return; }
+    std::vector<std::thread> pool;
+    const int64_t chunk = (N + threads - 1) / threads;
+    for (int t = 0; t < threads; t++) {
+        const int64_t b = t * chunk, e = std::min<int64_t>(N, b + chunk);
+        if (b >= e) break;
+        pool.emplace_back([=, &body] { body(b, e); });
+    }
+    for (auto &th : pool) th.join();
+}
+
+template <class T>
+int distance_impl(const Engine &e, const float *q, int64_t N, int mode, T *d_c, T *profile, T *nearest, int threads) {
+    const auto cfg = config_of<T>(e.prm);
+    const auto &sc = Pick<T>::scene(e);
+    const int n = e.robot.n;
+    const size_t M = sc.boxes.size();
+    parallel_for(N, threads, [&](int64_t b, int64_t en) {
+        std::vector<orc::V3<T>> sk(n + 1);
+        std::vector<T> prof(n);
+        for (int64_t i = b; i < en; i++) {
+            orc::skeleton(e.robot, q + i * n, sk.data());
+            bool hit;
+            T *np = (mode == RVS_DIST_FULL && nearest) ? nearest + size_t(i) * M * n * 6 : nullptr;
+            d_c[i] = orc::distance(e.robot, sc, sk.data(), cfg, prof.data(), np, &hit);
+            if (mode >= RVS_DIST_PROFILE && profile)
+                for (int k = 0; k < n; k++) profile[i * n + k] = prof[k];
+        }
+    });
+    return 0;
+}
+
+template <class T>
+int is_valid_impl(const Engine &e, const float *q, int64_t N, uint8_t *out, int threads) {
+    const auto cfg = config_of<T>(e.prm);
+    const auto &sc = Pick<T>::scene(e);
+    const int n = e.robot.n;
+    parallel_for(N, threads, [&](int64_t b, int64_t en) {
+        std::vector<orc::V3<T>> sk(n + 1);
+        for (int64_t i = b; i < en; i++) {
+            orc::skeleton(e.robot, q + i * n, sk.data());
+            out[i] = orc::is_valid(e.robot, sc, sk.data(), cfg) ? 1 : 0;
+        }
+    });
+    return 0;
+}
+
+template <class T> orc::V3<T> v3(const T *p) { return {p[0], p[1], p[2]}; }
+template <class T> orc::Box6<T> box6(const T *p) { orc::Box6<T> b; for (int i = 0; i < 6; i++) b.o[i] = p[i]; return b; }
+template <class T> void put_near(const orc::Near<T> &r, T *out) {
+    out[0] = r.d; out[1] = r.has ? T(1) : T(0);
+    out[2] = r.P1.x; out[3] = r.P1.y; out[4] = r.P1.z; out[5] = r.P2.x; out[6] = r.P2.y; out[7] = r.P2.z;
+}
+
+}  // namespace
+
+extern "C" {
+
+void *orc_create(const rvs_robot_desc *rd, const rvs_params *prm) {
+    if (!rd || !prm || rd->num_dofs < 1 || rd->num_dofs > RVS_MAX_DOFS) return nullptr;
+    auto *e = new Engine();
+    e->prm = *prm;
+    orc::Robot &rb = e->robot;
+    rb.kind = rd->kind;
+    rb.n = rd->num_dofs;
+    rb.ground_included = rd->ground_included;
+    rb.gripper_length = rd->gripper_length;
+    for (int k = 0; k <= rb.n; k++) {
+        rb.fixed_rot.push_back(orc::rpy_matrix(rd->joint_rpy[k][0], rd->joint_rpy[k][1], rd->joint_rpy[k][2]));
+        rb.xyz.push_back({rd->joint_xyz[k][0], rd->joint_xyz[k][1], rd->joint_xyz[k][2]});
+    }
+    for (int k = 0; k < rb.n; k++) {
+        const double *a = rd->joint_axis[k];
+        const double len = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);   // KDL::Joint normalises the axis
+        rb.axis.push_back({a[0] / len, a[1] / len, a[2] / len});
+        rb.radius.push_back(rd->capsule_radius[k]);
+        e->lo.push_back(rd->limit_lo[k]);
+        e->hi.push_back(rd->limit_hi[k]);
+    }
+    return e;
+}
+
+void orc_destroy(void *h) { delete static_cast<Engine *>(h); }
+
+int orc_set_params(void *h, const rvs_params *prm) { static_cast<Engine *>(h)->prm = *prm; return 0; }
+
+int orc_set_obstacles(void *h, const float *mn, const float *mx, const uint8_t *ground, const float *tol, int32_t M) {
+    auto *e = static_cast<Engine *>(h);
+    e->sc32 = {};
+    e->sc64 = {};
+    for (int j = 0; j < M; j++) {
+        orc::Box6<float> b{{mn[3 * j], mn[3 * j + 1], mn[3 * j + 2], mx[3 * j], mx[3 * j + 1], mx[3 * j + 2]}};
+        orc::Box6<double> bd;
+        for (int k = 0; k < 6; k++) bd.o[k] = double(b.o[k]);
+        const float t = tol ? tol[j] : e->prm.max_distance;
+        e->sc32.boxes.push_back(b); e->sc32.is_ground.push_back(ground ? ground[j] : 0); e->sc32.min_dist_tol.push_back(t);
+        e->sc64.boxes.push_back(bd); e->sc64.is_ground.push_back(ground ? ground[j] : 0); e->sc64.min_dist_tol.push_back(double(t));
+    }
+    return 0;
+}
+
+int orc_skeleton_f32(void *h, const float *q, int64_t N, float *sk) {
+    auto *e = static_cast<Engine *>(h);
+    const int n = e->robot.n;
+    std::vector<orc::V3<float>> s(n + 1);
+    for (int64_t i = 0; i < N; i++) {
+        orc::skeleton(e->robot, q + i * n, s.data());
+        for (int k = 0; k <= n; k++) { float *d = sk + (i * (n + 1) + k) * 3; d[0] = s[k].x; d[1] = s[k].y; d[2] = s[k].z; }
+    }
+    return 0;
+}
+int orc_skeleton_f64(void *h, const float *q, int64_t N, double *sk) {
+    auto *e = static_cast<Engine *>(h);
+    const int n = e->robot.n;
+    std::vector<orc::V3<double>> s(n + 1);
+    for (int64_t i = 0; i < N; i++) {
+        orc::skeleton(e->robot, q + i * n, s.data());
+        for (int k = 0; k <= n; k++) { double *d = sk + (i * (n + 1) + k) * 3; d[0] = s[k].x; d[1] = s[k].y; d[2] = s[k].z; }
+    }
+    return 0;
+}
+
+int orc_is_valid_f32(void *h, const float *q, int64_t N, uint8_t *out, int threads) { return is_valid_impl<float>(*static_cast<Engine *>(h), q, N, out, threads); }
+int orc_is_valid_f64(void *h, const float *q, int64_t N, uint8_t *out, int threads) { return is_valid_impl<double>(*static_cast<Engine *>(h), q, N, out, threads); }
+
+int orc_is_valid_edges_f32(void *h, const float *q1, const float *q2, int64_t E, uint8_t *out, int threads) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    parallel_for(E, threads, [&](int64_t b, int64_t en) {
+        for (int64_t i = b; i < en; i++) out[i] = orc::is_valid_edge(e->robot, e->sc32, q1 + i * n, q2 + i * n, cfg) ? 1 : 0;
+    });
+    return 0;
+}
+
+int orc_distance_f32(void *h, const float *q, int64_t N, int32_t mode, float *d_c, float *profile, float *nearest, int threads) {
+    return distance_impl<float>(*static_cast<Engine *>(h), q, N, mode, d_c, profile, nearest, threads);
+}
+int orc_distance_f64(void *h, const float *q, int64_t N, int32_t mode, double *d_c, double *profile, double *nearest, int threads) {
+    return distance_impl<double>(*static_cast<Engine *>(h), q, N, mode, d_c, profile, nearest, threads);
+}
+
+int orc_underestimation_f32(void *h, const float *q, int64_t N, const float *planes, const int32_t *plane_idx, int32_t R,
+                            float *d_c, float *profile, uint8_t *status) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    const size_t M = e->sc32.boxes.size();
+    std::vector<orc::V3<float>> sk(n + 1);
+    std::vector<float> prof(n);
+    for (int64_t i = 0; i < N; i++) {
+        const int r = plane_idx ? plane_idx[i] : 0;
+        if (r < 0 || r >= R) return 1;
+        orc::skeleton(e->robot, q + i * n, sk.data());
+        bool rej;
+        d_c[i] = orc::underestimation(e->robot, M, sk.data(), planes + size_t(r) * M * n * 6, cfg, prof.data(), &rej);
+        if (status) status[i] = rej ? 1 : 0;
+        if (profile) for (int k = 0; k < n; k++) profile[i * n + k] = rej ? 0.f : prof[k];
+    }
+    return 0;
+}
+
+int orc_enclosing_radii_f32(void *h, const float *q, int64_t N, float *radii) {
+    auto *e = static_cast<Engine *>(h);
+    const int n = e->robot.n;
+    std::vector<orc::V3<float>> sk(n + 1);
+    for (int64_t i = 0; i < N; i++) {
+        orc::skeleton(e->robot, q + i * n, sk.data());
+        orc::enclosing_radii(e->robot, sk.data(), radii + i * n * (n + 1));
+    }
+    return 0;
+}
+
+int orc_self_collision_capsules_f32(void *h, const float *q, int64_t N, uint8_t *mask) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    std::vector<orc::V3<float>> sk(n + 1);
+    for (int64_t i = 0; i < N; i++) {
+        orc::skeleton(e->robot, q + i * n, sk.data());
+        mask[i] = orc::self_collision_mask(e->robot, sk.data(), cfg);
+    }
+    return 0;
+}
+
+int orc_generate_configs(void *h, uint64_t seed, int64_t first, int64_t N, float *q) {
+    auto *e = static_cast<Engine *>(h);
+    const int n = e->robot.n;
+    for (int64_t i = 0; i < N; i++) orc::generate_config(seed, first + i, n, e->lo.data(), e->hi.data(), q + i * n);
+    return 0;
+}
+
+// ---- geometric primitives, batched over K cases. out rows: (d, has_points, P1xyz, P2xyz) ------------------
+int orc_seg_seg_f32(int64_t K, const float *ABCD /*K x 12*/, float thr, float maxd, float *out /*K x 8*/) {
+    const orc::Config<float> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) { const float *p = ABCD + 12 * i; put_near(orc::seg_seg(v3(p), v3(p + 3), v3(p + 6), v3(p + 9), cfg), out + 8 * i); }
+    return 0;
+}
+int orc_seg_seg_f64(int64_t K, const double *ABCD, double thr, double maxd, double *out) {
+    const orc::Config<double> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) { const double *p = ABCD + 12 * i; put_near(orc::seg_seg(v3(p), v3(p + 3), v3(p + 6), v3(p + 9), cfg), out + 8 * i); }
+    return 0;
+}
+int orc_seg_point_f32(int64_t K, const float *ABC /*K x 9*/, float thr, float maxd, float *out) {
+    const orc::Config<float> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) { const float *p = ABC + 9 * i; put_near(orc::seg_point(v3(p), v3(p + 3), v3(p + 6), cfg), out + 8 * i); }
+    return 0;
+}
+int orc_capsule_box_distance_f32(int64_t K, const float *AB /*K x 6*/, const float *radius, const float *obs /*K x 6*/, float thr, float maxd, float *out) {
+    const orc::Config<float> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) put_near(orc::capsule_box_distance(v3(AB + 6 * i), v3(AB + 6 * i + 3), radius[i], box6(obs + 6 * i), cfg), out + 8 * i);
+    return 0;
+}
+int orc_capsule_box_distance_f64(int64_t K, const double *AB, const double *radius, const double *obs, double thr, double maxd, double *out) {
+    const orc::Config<double> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) put_near(orc::capsule_box_distance(v3(AB + 6 * i), v3(AB + 6 * i + 3), radius[i], box6(obs + 6 * i), cfg), out + 8 * i);
+    return 0;
+}
+int orc_capsule_box_collision_f32(int64_t K, const float *AB, const float *radius, const float *obs, float thr, float maxd, uint8_t *out) {
+    const orc::Config<float> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) out[i] = orc::capsule_hits_box(v3(AB + 6 * i), v3(AB + 6 * i + 3), radius[i], box6(obs + 6 * i), cfg) ? 1 : 0;
+    return 0;
+}
+int orc_capsule_rect_collision_f32(int64_t K, const float *AB, const float *radius, const float *obs, const int32_t *face, float thr, float maxd, uint8_t *out) {
+    const orc::Config<float> cfg{thr, maxd, 0};
+    for (int64_t i = 0; i < K; i++) out[i] = orc::capsule_hits_rectangle(v3(AB + 6 * i), v3(AB + 6 * i + 3), radius[i], box6(obs + 6 * i), face[i], cfg) ? 1 : 0;
+    return 0;
+}
+
+}  // extern "C"
