@@ -24,6 +24,8 @@
  *                                        Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30)
  *   rvs_self_collision_capsules       <- xArm6::checkSelfCollision(q) capsule pre-filter
  *                                        (src/robots/xArm6.cpp:374-424; FCL mesh stage is NOT covered)
+ *   rvs_capsule_box_distance /        <- the public static primitives CollisionAndDistance::distanceCapsuleToBox /
+ *   rvs_capsule_box_collision            collisionCapsuleToBox (CollisionAndDistance.cpp:4-42, 208-214), batched
  *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
  *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
  *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
@@ -134,6 +136,15 @@ int  rvs_sync(rvs_handle h);
 /* kernels launched by this handle since creation (each counts one grid launch) */
 int64_t rvs_launch_count(rvs_handle h);
 
+/* Work accounting: pair queries (distanceCapsuleToBox calls) that RealVectorSpace::computeDistance's own loop order
+ * (link-major, stop at the first collision, ground pairs skipped) would have made for all configurations passed to
+ * rvs_distance* since the last reset. Synchronises the stream. */
+int  rvs_pair_count(rvs_handle h, int32_t reset, uint64_t *out);
+
+/* Roofline denominator: achieved FFMA (fp64 = 0) or DFMA (fp64 = 1) throughput of this device in TFLOP/s, measured with a
+ * register-only unrolled FMA kernel (best of 4 timed launches, CUDA events). */
+int  rvs_measure_fma_peak(rvs_handle h, int32_t fp64, double *tflops);
+
 /* ---- obstacle table (resident in HBM as SoA) -------------------------------------------------- */
 /* aabb_min / aabb_max: M x 3 float (x,y,z); is_ground: M bytes (label == "ground"); min_dist_tol: M float
  * or NULL (= max_distance for all). Host pointers. */
@@ -171,6 +182,13 @@ int  rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_
 int  rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profile, float root_d_c,
                        const float *root_planes, const float *q_targets, int32_t S,
                        const rvs_spine_params *sp, float *q_reached, float *d_c_reached, uint8_t *status);
+
+/* Batched geometric primitives on K independent (capsule, box) pairs, host pointers.
+ * AB: K x 6 (A xyz, B xyz); radius: K; obs: K x 6 (x_min,y_min,z_min,x_max,y_max,z_max).
+ * distance -> out: K x 8 rows (d, has_points, P1 xyz, P2 xyz), has_points = 0 where the reference returns nullptr;
+ * collision -> hit: K bytes. Uses the handle's precision (REF32 / FAST32 only) and thresholds. */
+int  rvs_capsule_box_distance(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, float *out);
+int  rvs_capsule_box_collision(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, uint8_t *hit);
 
 /* ---- FP64 variants (handle must have been created with RVS_PREC_F64) ---------------------------- */
 int  rvs_distance_f64(rvs_handle h, const float *q, int64_t N, int32_t mode,

@@ -42,6 +42,8 @@ def lib():
         _lib.orc_create.restype = ctypes.c_void_p
         _lib.orc_create.argtypes = [ctypes.POINTER(RvsRobotDesc), ctypes.POINTER(RvsParams)]
         _lib.orc_destroy.argtypes = [ctypes.c_void_p]
+        _lib.orc_pair_count.restype = ctypes.c_uint64
+        _lib.orc_pair_count.argtypes = [ctypes.c_void_p, ctypes.c_int]
     return _lib
 
 
@@ -73,6 +75,9 @@ class Oracle:
             self._h = None
 
     __del__ = close
+
+    def pair_count(self, reset: bool = False) -> int:
+        return int(lib().orc_pair_count(self._h, 1 if reset else 0))
 
     def set_obstacles(self, aabb_min, aabb_max, is_ground=None, min_dist_tol=None):
         mn, mx = _f32(aabb_min, (-1, 3)), _f32(aabb_max, (-1, 3))

@@ -599,7 +599,8 @@ bool is_valid_edge(const Robot &rb, const Scene<T> &sc, const float *q1, const f
 // profile[L]; nearest (optional) [M][L][6] = (R, O). Returns d_c. `collided` reports the early exit, after
 // which `nearest` is unspecified and profile follows the reference fill (later links stay 0).
 template <class T>
-T distance(const Robot &rb, const Scene<T> &sc, const V3<T> *sk, const Config<T> &cfg, T *profile, T *nearest, bool *collided) {
+T distance(const Robot &rb, const Scene<T> &sc, const V3<T> *sk, const Config<T> &cfg, T *profile, T *nearest, bool *collided,
+           uint64_t *visited = nullptr) {
     const int L = rb.n;
     const size_t M = sc.boxes.size();
     T d_c = cfg.max_dist;
@@ -616,6 +617,7 @@ T distance(const Robot &rb, const Scene<T> &sc, const V3<T> *sk, const Config<T>
             } else {
                 Near<T> r = capsule_box_distance(sk[i], sk[i + 1], T(rb.radius[i]), sc.boxes[j], cfg);
                 d = r.d; Rp = r.P1; Op = r.P2;
+                if (visited) ++*visited;                              // one distanceCapsuleToBox call
             }
             if (d > sc.min_dist_tol[j]) d = cfg.max_dist;            // (:367-368)
             profile[i] = std::min(profile[i], d);

@@ -1,5 +1,6 @@
 // rvs_oracle_capi.cpp — C entry points of the CPU oracle for ctypes (TEST INFRASTRUCTURE ONLY; see rvs_oracle.hpp).
 // Mirrors the argument layout of include/rvs_cuda.h so the parity tests can feed both sides the same arrays.
+#include <atomic>
 #include <thread>
 
 #include "../include/rvs_cuda.h"
@@ -13,6 +14,7 @@ struct Engine {
     rvs_params prm;
     orc::Scene<float> sc32;
     orc::Scene<double> sc64;
+    std::atomic<uint64_t> pair_count{0};
 };
 
 template <class T> struct Pick;
@@ -39,7 +41,7 @@ void parallel_for(int64_t N, int threads, F &&body) {
 }
 
 template <class T>
-int distance_impl(const Engine &e, const float *q, int64_t N, int mode, T *d_c, T *profile, T *nearest, int threads) {
+int distance_impl(Engine &e, const float *q, int64_t N, int mode, T *d_c, T *profile, T *nearest, int threads) {
     const auto cfg = config_of<T>(e.prm);
     const auto &sc = Pick<T>::scene(e);
     const int n = e.robot.n;
@@ -47,14 +49,16 @@ int distance_impl(const Engine &e, const float *q, int64_t N, int mode, T *d_c, 
     parallel_for(N, threads, [&](int64_t b, int64_t en) {
         std::vector<orc::V3<T>> sk(n + 1);
         std::vector<T> prof(n);
+        uint64_t visited = 0;
         for (int64_t i = b; i < en; i++) {
             orc::skeleton(e.robot, q + i * n, sk.data());
             bool hit;
             T *np = (mode == RVS_DIST_FULL && nearest) ? nearest + size_t(i) * M * n * 6 : nullptr;
-            d_c[i] = orc::distance(e.robot, sc, sk.data(), cfg, prof.data(), np, &hit);
+            d_c[i] = orc::distance(e.robot, sc, sk.data(), cfg, prof.data(), np, &hit, &visited);
             if (mode >= RVS_DIST_PROFILE && profile)
                 for (int k = 0; k < n; k++) profile[i * n + k] = prof[k];
         }
+        e.pair_count += visited;
     });
     return 0;
 }
@@ -110,6 +114,13 @@ void *orc_create(const rvs_robot_desc *rd, const rvs_params *prm) {
 }
 
 void orc_destroy(void *h) { delete static_cast<Engine *>(h); }
+
+uint64_t orc_pair_count(void *h, int reset) {
+    auto *e = static_cast<Engine *>(h);
+    const uint64_t v = e->pair_count.load();
+    if (reset) e->pair_count = 0;
+    return v;
+}
 
 int orc_set_params(void *h, const rvs_params *prm) { static_cast<Engine *>(h)->prm = *prm; return 0; }
 

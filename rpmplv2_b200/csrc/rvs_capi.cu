@@ -1,0 +1,510 @@
+// rvs_capi.cu — C ABI of librvs_cuda.so (include/rvs_cuda.h): handle, HBM-resident robot + obstacle tables,
+// staging buffers and kernel dispatch. Host code only; the kernels live in rvs_variant.cu.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rvs_launch.h"
+#include "rvs_robot_host.h"
+#include "rvs_types.h"
+
+using namespace rvs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct rvs_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    rvs_params prm{};
+    RobotDev h_robot{};
+    RobotDev *d_robot = nullptr;
+    ObstacleRec *d_obs = nullptr;
+    int M = 0, obs_cap = 0;
+    std::vector<ObstacleRec> h_obs;
+    LaunchTable lt{};
+    DevBuf buf[8];            // grow-only device staging for the host-pointer entry points
+    int64_t launches = 0;
+    int cull = 0;
+    int num_ground = 0;
+    unsigned long long *d_pair_count = nullptr;
+    std::string err;
+};
+
+namespace {
+
+enum { B_Q = 0, B_Q2, B_DC, B_PROF, B_NEAR, B_VERD, B_PLANES, B_IDX };
+
+int fail(rvs_engine *h, int code, const std::string &msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(rvs_engine *h, cudaError_t e, const char *what) {
+    const int code = (e == cudaErrorMemoryAllocation) ? RVS_ERR_OUT_OF_MEMORY : RVS_ERR_CUDA;
+    return fail(h, code, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define RVS_CUDA(h, call)                                                   \
+    do {                                                                    \
+        cudaError_t e__ = (call);                                           \
+        if (e__ != cudaSuccess) return cuda_fail((h), e__, #call);          \
+    } while (0)
+#define RVS_TRY(expr)                       \
+    do {                                    \
+        const int rc__ = (expr);            \
+        if (rc__ != RVS_OK) return rc__;    \
+    } while (0)
+
+int reserve(rvs_engine *h, int which, size_t bytes) {
+    DevBuf &b = h->buf[which];
+    if (bytes <= b.cap) return RVS_OK;
+    if (b.p) RVS_CUDA(h, cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    const size_t cap = bytes + bytes / 4 + 256;
+    RVS_CUDA(h, cudaMalloc(&b.p, cap));
+    b.cap = cap;
+    return RVS_OK;
+}
+
+int build_robot(rvs_engine *h, const rvs_robot_desc *rd) {
+    const char *why = fill_robot_dev(rd, &h->h_robot);
+    return why ? fail(h, RVS_ERR_INVALID_ARGUMENT, why) : RVS_OK;
+}
+
+int select_table(rvs_engine *h) {
+    switch (h->prm.precision) {
+        case RVS_PREC_REF32: h->lt = launch_table_ref32(); return RVS_OK;
+        case RVS_PREC_FAST32: h->lt = launch_table_fast32(); return RVS_OK;
+        case RVS_PREC_F64: h->lt = launch_table_f64(); return RVS_OK;
+        default: return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown precision");
+    }
+}
+
+int check_params(rvs_engine *h, const rvs_params *p) {
+    if (!p) return fail(h, RVS_ERR_INVALID_ARGUMENT, "params is NULL");
+    if (!(p->max_distance > 0) || p->num_interpolation_validity_checks < 1 || !(p->equality_threshold >= 0))
+        return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad RealVectorSpaceConfig values");
+    return RVS_OK;
+}
+
+KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
+    KArgs a{};
+    a.robot = h->d_robot; a.obstacles = h->d_obs; a.M = h->M; a.N = N; a.q = d_q;
+    a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
+    a.num_checks = h->prm.num_interpolation_validity_checks; a.cull = h->cull;
+    a.robot_n_hint = h->h_robot.n;
+    a.num_ground = h->num_ground;
+    a.pair_count = h->d_pair_count;
+    return a;
+}
+
+int enter(rvs_engine *h) {
+    if (!h) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "handle is NULL");
+    RVS_CUDA(h, cudaSetDevice(h->device));
+    return RVS_OK;
+}
+
+size_t real_size(rvs_engine *h) { return h->prm.precision == RVS_PREC_F64 ? sizeof(double) : sizeof(float); }
+
+int launched(rvs_engine *h, cudaError_t e, const char *what) {
+    if (e != cudaSuccess) return cuda_fail(h, e, what);
+    h->launches++;
+    return RVS_OK;
+}
+
+int h2d(rvs_engine *h, int which, const void *src, size_t bytes) {
+    RVS_TRY(reserve(h, which, bytes));
+    if (bytes) RVS_CUDA(h, cudaMemcpyAsync(h->buf[which].p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return RVS_OK;
+}
+int d2h(rvs_engine *h, void *dst, int which, size_t bytes) {
+    if (bytes && dst) RVS_CUDA(h, cudaMemcpyAsync(dst, h->buf[which].p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    return RVS_OK;
+}
+
+int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, void *d_dc, void *d_prof, void *d_near, bool want_f64) {
+    if ((h->prm.precision == RVS_PREC_F64) != want_f64)
+        return fail(h, RVS_ERR_INVALID_ARGUMENT, want_f64 ? "handle was not created with RVS_PREC_F64" : "RVS_PREC_F64 handles use the *_f64 entry points");
+    if (N < 0 || mode < RVS_DIST_MIN || mode > RVS_DIST_FULL) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or mode");
+    if (N == 0) return RVS_OK;
+    if (!d_q || !d_dc || (mode >= RVS_DIST_PROFILE && !d_prof) || (mode == RVS_DIST_FULL && !d_near && h->M > 0))
+        return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer for the requested distance mode");
+    KArgs a = base_args(h, d_q, N);
+    a.mode = mode; a.d_c = d_dc; a.profile = d_prof; a.nearest = d_near;
+    return launched(h, h->lt.distance(a, h->stream), "distance kernel launch");
+}
+
+int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, void *d_c, void *profile, void *nearest, bool want_f64) {
+    RVS_TRY(enter(h));
+    if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
+    if (N == 0) return RVS_OK;
+    if (!q || !d_c) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL q or d_c");
+    const size_t rs = want_f64 ? sizeof(double) : sizeof(float);
+    const size_t n = size_t(h->h_robot.n), L = n;
+    const size_t near_bytes = mode == RVS_DIST_FULL ? size_t(N) * size_t(h->M) * L * 6 * rs : 0;
+    RVS_TRY(h2d(h, B_Q, q, size_t(N) * n * sizeof(float)));
+    RVS_TRY(reserve(h, B_DC, size_t(N) * rs));
+    RVS_TRY(reserve(h, B_PROF, size_t(N) * L * rs));
+    RVS_TRY(reserve(h, B_NEAR, near_bytes));
+    RVS_TRY(distance_dev_impl(h, static_cast<const float *>(h->buf[B_Q].p), N, mode, h->buf[B_DC].p, h->buf[B_PROF].p, h->buf[B_NEAR].p, want_f64));
+    RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * rs));
+    if (mode >= RVS_DIST_PROFILE) RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * L * rs));
+    if (mode == RVS_DIST_FULL) RVS_TRY(d2h(h, nearest, B_NEAR, near_bytes));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+// simple device-to-host pattern for kernels with one output array living in buffer `which`
+int run_simple(rvs_engine *h, const float *q, int64_t N, LaunchFn fn, void *out, size_t out_bytes, bool verdict_out, const char *what) {
+    RVS_TRY(enter(h));
+    if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
+    if (N == 0) return RVS_OK;
+    if (!q || !out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(h2d(h, B_Q, q, size_t(N) * size_t(h->h_robot.n) * sizeof(float)));
+    const int which = verdict_out ? B_VERD : B_DC;
+    RVS_TRY(reserve(h, which, out_bytes));
+    KArgs a = base_args(h, static_cast<const float *>(h->buf[B_Q].p), N);
+    if (verdict_out) a.verdict = static_cast<uint8_t *>(h->buf[which].p); else a.d_c = h->buf[which].p;
+    RVS_TRY(launched(h, fn(a, h->stream), what));
+    RVS_TRY(d2h(h, out, which, out_bytes));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rvs_abi_version(void) { return RVS_ABI_VERSION; }
+
+int rvs_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *rvs_last_error(rvs_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device, rvs_handle *out) {
+    if (!out) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!robot) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "robot is NULL");
+    RVS_TRY(check_params(nullptr, params));
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return fail(nullptr, RVS_ERR_NO_DEVICE, "no CUDA device available: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= count) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "device index out of range");
+    rvs_engine *h = new rvs_engine();
+    h->device = device;
+    h->prm = *params;
+    int rc = build_robot(h, robot);
+    if (rc == RVS_OK) rc = select_table(h);
+    if (rc != RVS_OK) { g_create_error = h->err; delete h; return rc; }
+    auto bail = [&](cudaError_t ce, const char *what) {
+        const int code = cuda_fail(nullptr, ce, what);
+        if (h->d_robot) cudaFree(h->d_robot);
+        if (h->d_pair_count) cudaFree(h->d_pair_count);
+        if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+        delete h;
+        return code;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    h->own_stream = true;
+    if ((e = cudaMalloc(&h->d_robot, sizeof(RobotDev))) != cudaSuccess) return bail(e, "cudaMalloc(robot)");
+    if ((e = cudaMemcpy(h->d_robot, &h->h_robot, sizeof(RobotDev), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(robot)");
+    if ((e = cudaMalloc(&h->d_pair_count, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
+    if ((e = cudaMemset(h->d_pair_count, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
+    *out = h;
+    return RVS_OK;
+}
+
+int rvs_destroy(rvs_handle h) {
+    if (!h) return RVS_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (auto &b : h->buf) if (b.p) cudaFree(b.p);
+    if (h->d_obs) cudaFree(h->d_obs);
+    if (h->d_robot) cudaFree(h->d_robot);
+    if (h->d_pair_count) cudaFree(h->d_pair_count);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return RVS_OK;
+}
+
+int rvs_set_params(rvs_handle h, const rvs_params *params) {
+    RVS_TRY(enter(h));
+    RVS_TRY(check_params(h, params));
+    h->prm = *params;
+    return select_table(h);
+}
+
+int rvs_set_stream(rvs_handle h, void *cuda_stream) {
+    RVS_TRY(enter(h));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream) { RVS_CUDA(h, cudaStreamDestroy(h->stream)); h->own_stream = false; }
+    h->stream = static_cast<cudaStream_t>(cuda_stream);
+    return RVS_OK;
+}
+
+void *rvs_get_stream(rvs_handle h) { return h ? static_cast<void *>(h->stream) : nullptr; }
+
+int rvs_sync(rvs_handle h) {
+    RVS_TRY(enter(h));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+int64_t rvs_launch_count(rvs_handle h) { return h ? h->launches : 0; }
+
+int rvs_set_culling(rvs_handle h, int32_t cull) {
+    if (!h) return RVS_ERR_INVALID_ARGUMENT;
+    h->cull = cull ? 1 : 0;
+    return RVS_OK;
+}
+
+int rvs_num_obstacles(rvs_handle h) { return h ? h->M : 0; }
+
+int rvs_measure_fma_peak(rvs_handle h, int32_t fp64, double *tflops) {
+    RVS_TRY(enter(h));
+    if (!tflops) return fail(h, RVS_ERR_INVALID_ARGUMENT, "tflops is NULL");
+    cudaDeviceProp prop;
+    RVS_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    const int blocks = prop.multiProcessorCount * 8, iters = 8192;
+    RVS_TRY(reserve(h, B_DC, 64));
+    cudaEvent_t e0, e1;
+    RVS_CUDA(h, cudaEventCreate(&e0));
+    RVS_CUDA(h, cudaEventCreate(&e1));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {        // first repetition is the warm-up
+        RVS_CUDA(h, cudaEventRecord(e0, h->stream));
+        RVS_TRY(launched(h, launch_fma_peak(fp64, h->buf[B_DC].p, blocks, iters, h->stream), "fma peak kernel launch"));
+        RVS_CUDA(h, cudaEventRecord(e1, h->stream));
+        RVS_CUDA(h, cudaEventSynchronize(e1));
+        float ms = 0;
+        RVS_CUDA(h, cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = double(blocks) * 256.0 * 16.0 * double(iters) * 2.0;
+        if (rep > 0 && ms > 0) best = std::fmax(best, flops / (double(ms) * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return RVS_OK;
+}
+
+int rvs_pair_count(rvs_handle h, int32_t reset, uint64_t *out) {
+    RVS_TRY(enter(h));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    unsigned long long v = 0;
+    RVS_CUDA(h, cudaMemcpy(&v, h->d_pair_count, sizeof(v), cudaMemcpyDeviceToHost));
+    if (out) *out = uint64_t(v);
+    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, sizeof(v)));
+    return RVS_OK;
+}
+
+int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max, const uint8_t *is_ground, const float *min_dist_tol, int32_t M) {
+    RVS_TRY(enter(h));
+    if (M < 0 || (M > 0 && (!aabb_min || !aabb_max))) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad obstacle arrays");
+    h->h_obs.resize(size_t(M));
+    for (int j = 0; j < M; j++) {
+        ObstacleRec &o = h->h_obs[size_t(j)];
+        for (int c = 0; c < 3; c++) { o.lo[c] = aabb_min[3 * j + c]; o.hi[c] = aabb_max[3 * j + c]; }
+        o.tol = min_dist_tol ? min_dist_tol[j] : h->prm.max_distance;          // Box.cpp:13
+        o.flags = (is_ground && is_ground[j]) ? 1u : 0u;
+    }
+    h->num_ground = 0;
+    for (int j = 0; j < M; j++) h->num_ground += int(h->h_obs[size_t(j)].flags & 1u);
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (M > h->obs_cap) {
+        if (h->d_obs) RVS_CUDA(h, cudaFree(h->d_obs));
+        h->d_obs = nullptr; h->obs_cap = 0;
+        const int cap = M + M / 2 + 16;
+        RVS_CUDA(h, cudaMalloc(&h->d_obs, size_t(cap) * sizeof(ObstacleRec)));
+        h->obs_cap = cap;
+    }
+    h->M = M;
+    if (M) RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+int rvs_update_obstacle_aabbs(rvs_handle h, const float *aabb_min, const float *aabb_max, int32_t M) {
+    RVS_TRY(enter(h));
+    if (M != h->M) return fail(h, RVS_ERR_INVALID_ARGUMENT, "M differs from the resident obstacle table");
+    if (M > 0 && (!aabb_min || !aabb_max)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL AABB arrays");
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));       // the pinned-less host mirror is reused: wait for the last copy
+    for (int j = 0; j < M; j++)
+        for (int c = 0; c < 3; c++) { h->h_obs[size_t(j)].lo[c] = aabb_min[3 * j + c]; h->h_obs[size_t(j)].hi[c] = aabb_max[3 * j + c]; }
+    if (M) RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+// ---- device-pointer entry points ---------------------------------------------------------------------------------
+int rvs_distance_dev(rvs_handle h, const float *d_q, int64_t N, int32_t mode, float *d_d_c, float *d_profile, float *d_nearest) {
+    RVS_TRY(enter(h));
+    return distance_dev_impl(h, d_q, N, mode, d_d_c, d_profile, d_nearest, false);
+}
+int rvs_distance_f64_dev(rvs_handle h, const float *d_q, int64_t N, int32_t mode, double *d_d_c, double *d_profile, double *d_nearest) {
+    RVS_TRY(enter(h));
+    return distance_dev_impl(h, d_q, N, mode, d_d_c, d_profile, d_nearest, true);
+}
+int rvs_is_valid_dev(rvs_handle h, const float *d_q, int64_t N, uint8_t *d_valid) {
+    RVS_TRY(enter(h));
+    if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
+    if (N == 0) return RVS_OK;
+    if (!d_q || !d_valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    KArgs a = base_args(h, d_q, N);
+    a.verdict = d_valid;
+    return launched(h, h->lt.is_valid(a, h->stream), "is_valid kernel launch");
+}
+int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid) {
+    RVS_TRY(enter(h));
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!d_q1 || !d_q2 || !d_valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(E), h->stream));
+    KArgs a = base_args(h, d_q1, E);
+    a.q2 = d_q2; a.verdict = d_valid;
+    return launched(h, h->lt.edge_valid(a, h->stream), "edge kernel launch");
+}
+int rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,
+                            float *d_d_c, float *d_profile, uint8_t *d_status) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "underestimation has no FP64 entry point");
+    if (N < 0 || R < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or R");
+    if (N == 0) return RVS_OK;
+    if (!d_q || !d_d_c || (!d_planes && h->M > 0)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    KArgs a = base_args(h, d_q, N);
+    a.planes = d_planes; a.plane_idx = d_plane_idx; a.R = R; a.d_c = d_d_c; a.profile = d_profile; a.status = d_status;
+    return launched(h, h->lt.underestimation(a, h->stream), "underestimation kernel launch");
+}
+int rvs_generate_configs_dev(rvs_handle h, uint64_t seed, int64_t first, int64_t N, float *d_q) {
+    RVS_TRY(enter(h));
+    if (N < 0 || first < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad range");
+    if (N == 0) return RVS_OK;
+    if (!d_q) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    KArgs a = base_args(h, nullptr, N);
+    a.seed = seed; a.first = first;
+    return launched(h, launch_generate_configs(a, d_q, h->stream), "generate kernel launch");
+}
+
+// ---- host-pointer entry points -------------------------------------------------------------------------------------
+int rvs_distance(rvs_handle h, const float *q, int64_t N, int32_t mode, float *d_c, float *profile, float *nearest) {
+    return distance_host_impl(h, q, N, mode, d_c, profile, nearest, false);
+}
+int rvs_distance_f64(rvs_handle h, const float *q, int64_t N, int32_t mode, double *d_c, double *profile, double *nearest) {
+    return distance_host_impl(h, q, N, mode, d_c, profile, nearest, true);
+}
+int rvs_is_valid(rvs_handle h, const float *q, int64_t N, uint8_t *valid) {
+    if (h && h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_INVALID_ARGUMENT, "RVS_PREC_F64 handles use rvs_is_valid_f64");
+    return run_simple(h, q, N, h ? h->lt.is_valid : nullptr, valid, size_t(N > 0 ? N : 0), true, "is_valid kernel launch");
+}
+int rvs_is_valid_f64(rvs_handle h, const float *q, int64_t N, uint8_t *valid) {
+    if (h && h->prm.precision != RVS_PREC_F64) return fail(h, RVS_ERR_INVALID_ARGUMENT, "handle was not created with RVS_PREC_F64");
+    return run_simple(h, q, N, h ? h->lt.is_valid : nullptr, valid, size_t(N > 0 ? N : 0), true, "is_valid kernel launch");
+}
+int rvs_is_valid_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *valid) {
+    RVS_TRY(enter(h));
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!q1 || !q2 || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    RVS_TRY(h2d(h, B_Q, q1, bytes));
+    RVS_TRY(h2d(h, B_Q2, q2, bytes));
+    RVS_TRY(reserve(h, B_VERD, size_t(E)));
+    RVS_TRY(rvs_is_valid_edges_dev(h, static_cast<const float *>(h->buf[B_Q].p), static_cast<const float *>(h->buf[B_Q2].p), E,
+                                   static_cast<uint8_t *>(h->buf[B_VERD].p)));
+    RVS_TRY(d2h(h, valid, B_VERD, size_t(E)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+int rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *planes, const int32_t *plane_idx, int32_t R,
+                        float *d_c, float *profile, uint8_t *status) {
+    RVS_TRY(enter(h));
+    if (N < 0 || R < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or R");
+    if (N == 0) return RVS_OK;
+    if (!q || !d_c || (!planes && h->M > 0)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (plane_idx)
+        for (int64_t i = 0; i < N; i++)
+            if (plane_idx[i] < 0 || plane_idx[i] >= R) return fail(h, RVS_ERR_INVALID_ARGUMENT, "plane_idx out of range");
+    const size_t n = size_t(h->h_robot.n);
+    RVS_TRY(h2d(h, B_Q, q, size_t(N) * n * sizeof(float)));
+    RVS_TRY(h2d(h, B_PLANES, planes, size_t(R) * size_t(h->M) * n * 6 * sizeof(float)));
+    if (plane_idx) RVS_TRY(h2d(h, B_IDX, plane_idx, size_t(N) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_DC, size_t(N) * sizeof(float)));
+    RVS_TRY(reserve(h, B_PROF, size_t(N) * n * sizeof(float)));
+    RVS_TRY(reserve(h, B_VERD, size_t(N)));
+    RVS_TRY(rvs_underestimation_dev(h, static_cast<const float *>(h->buf[B_Q].p), N, static_cast<const float *>(h->buf[B_PLANES].p),
+                                    plane_idx ? static_cast<const int32_t *>(h->buf[B_IDX].p) : nullptr, R,
+                                    static_cast<float *>(h->buf[B_DC].p), static_cast<float *>(h->buf[B_PROF].p),
+                                    static_cast<uint8_t *>(h->buf[B_VERD].p)));
+    RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * sizeof(float)));
+    RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * n * sizeof(float)));
+    RVS_TRY(d2h(h, status, B_VERD, size_t(N)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+int rvs_skeleton(rvs_handle h, const float *q, int64_t N, float *skeleton) {
+    if (h && h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "skeleton output is FP32: use a REF32/FAST32 handle");
+    const size_t n = h ? size_t(h->h_robot.n) : 0;
+    return run_simple(h, q, N, h ? h->lt.skeleton : nullptr, skeleton, size_t(N > 0 ? N : 0) * (n + 1) * 3 * sizeof(float), false, "skeleton kernel launch");
+}
+int rvs_enclosing_radii(rvs_handle h, const float *q, int64_t N, float *radii) {
+    if (h && h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "enclosing radii output is FP32: use a REF32/FAST32 handle");
+    const size_t n = h ? size_t(h->h_robot.n) : 0;
+    return run_simple(h, q, N, h ? h->lt.enclosing_radii : nullptr, radii, size_t(N > 0 ? N : 0) * n * (n + 1) * sizeof(float), false, "enclosing radii kernel launch");
+}
+int rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_t *mask) {
+    return run_simple(h, q, N, h ? h->lt.self_collision : nullptr, mask, size_t(N > 0 ? N : 0), true, "self collision kernel launch");
+}
+
+
+static int primitive_impl(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, float *out, uint8_t *hit) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "primitives run on REF32 / FAST32 handles");
+    if (K < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "K < 0");
+    if (K == 0) return RVS_OK;
+    if (!AB || !radius || !obs || (!out && !hit)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(h2d(h, B_Q, AB, size_t(K) * 6 * sizeof(float)));
+    RVS_TRY(h2d(h, B_Q2, radius, size_t(K) * sizeof(float)));
+    RVS_TRY(h2d(h, B_PLANES, obs, size_t(K) * 6 * sizeof(float)));
+    RVS_TRY(reserve(h, B_DC, size_t(K) * 8 * sizeof(float)));
+    RVS_TRY(reserve(h, B_VERD, size_t(K)));
+    KArgs a = base_args(h, static_cast<const float *>(h->buf[B_Q].p), K);
+    a.q2 = static_cast<const float *>(h->buf[B_Q2].p);
+    a.planes = static_cast<const float *>(h->buf[B_PLANES].p);
+    if (hit) a.verdict = static_cast<uint8_t *>(h->buf[B_VERD].p); else a.d_c = h->buf[B_DC].p;
+    RVS_TRY(launched(h, h->lt.primitive(a, h->stream), "primitive kernel launch"));
+    if (hit) RVS_TRY(d2h(h, hit, B_VERD, size_t(K))); else RVS_TRY(d2h(h, out, B_DC, size_t(K) * 8 * sizeof(float)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+int rvs_capsule_box_distance(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, float *out) {
+    return primitive_impl(h, AB, radius, obs, K, out, nullptr);
+}
+int rvs_capsule_box_collision(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, uint8_t *hit) {
+    return primitive_impl(h, AB, radius, obs, K, nullptr, hit);
+}
+
+int rvs_extend_spines(rvs_handle h, const float *, const float *, float, const float *, const float *, int32_t, const rvs_spine_params *,
+                      float *, float *, uint8_t *) {
+    return fail(h, RVS_ERR_UNSUPPORTED, "rvs_extend_spines is not implemented yet");
+}
+
+}  // extern "C"

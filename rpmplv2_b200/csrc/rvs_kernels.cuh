@@ -1,0 +1,450 @@
+// rvs_kernels.cuh — sm_100a kernels of the RealVectorSpaceCUDA engine (included by rvs_variant.cu, which is
+// compiled once per arithmetic variant: -fmad=false for REF32/F64, -fmad=true for FAST32).
+//
+// Execution model of the batch kernels: ONE THREAD PER CONFIGURATION.
+//   1. forward kinematics of the serial chain in registers (FP64 for REF32/F64, FP32 for FAST32), streamed joint
+//      by joint into the capsule skeleton (per-thread local array, touched once per link per obstacle tile);
+//   2. the obstacle table is staged tile by tile (512 records of 32 B) into shared memory with coalesced 16-byte
+//      loads; inside a tile the loop is link-major / obstacle-minor so the per-link capsule constants stay in
+//      registers and every obstacle read is a warp-wide broadcast LDS.128;
+//   3. the narrow phase is rvs_geom.cuh.
+// Results are written straight to HBM (4..28 B per configuration in MIN/PROFILE mode).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "rvs_fk.cuh"
+#include "rvs_geom.cuh"
+#include "rvs_types.h"
+
+namespace rvs {
+
+constexpr int kBlock = 128;
+
+template <class R> __device__ __forceinline__ Box<R> load_box(const ObstacleRec &o) {
+    return {{R(o.lo[0]), R(o.lo[1]), R(o.lo[2])}, {R(o.hi[0]), R(o.hi[1]), R(o.hi[2])}};
+}
+
+// cooperative, coalesced 16-byte staging of one obstacle tile
+__device__ __forceinline__ void stage_tile(ObstacleRec *tile, const ObstacleRec *__restrict__ src, int count) {
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    float4 *d4 = reinterpret_cast<float4 *>(tile);
+    for (int k = threadIdx.x; k < 2 * count; k += blockDim.x) d4[k] = __ldg(s4 + k);
+}
+
+template <class R> struct RobotScalars;
+template <> struct RobotScalars<float> {
+    static __device__ __forceinline__ float radius(const RobotDev *rb, int i) { return rb->radius[i]; }
+    static __device__ __forceinline__ float radius_in(const RobotDev *rb, int i) { return rb->radius_in[i]; }
+};
+template <> struct RobotScalars<double> {
+    static __device__ __forceinline__ double radius(const RobotDev *rb, int i) { return rb->radius_d[i]; }
+    static __device__ __forceinline__ double radius_in(const RobotDev *rb, int i) { return rb->radius_in_d[i]; }
+};
+
+// ---- computeDistance (RealVectorSpace.cpp:318-392) ----------------------------------------------------------------
+// MODE: 0 MIN, 1 PROFILE, 2 FULL.  F = FK scalar, R = geometry scalar.
+template <class F, class R, int MODE>
+__global__ void __launch_bounds__(kBlock) distance_kernel(const KArgs a) {
+    __shared__ ObstacleRec tile[kTileObstacles];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    const bool live = cfg < a.N;
+    const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
+
+    R sk[3 * (kMaxDofs + 1)];
+    R prof[kMaxDofs];
+    if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, sk);
+    for (int i = 0; i < L; i++) prof[i] = max_dist;
+    int limit = live ? L : 0;      // links >= limit are no longer evaluated (first collision semantics, :371-378)
+    R hit_d = 0;
+    int hit_j = 0;
+    R *nearest = (MODE == RVS_DIST_FULL && live) ? static_cast<R *>(a.nearest) + size_t(cfg) * size_t(a.M) * size_t(L) * 6 : nullptr;
+    const int ground_included = rb->ground_included;
+
+    for (int base = 0; base < a.M; base += kTileObstacles) {
+        const int count = min(kTileObstacles, a.M - base);
+        __syncthreads();
+        stage_tile(tile, a.obstacles + base, count);
+        __syncthreads();
+#pragma unroll 1
+        for (int i = 0; i < limit; i++) {
+            Capsule<R> cp;
+            cp.set({sk[3 * i], sk[3 * i + 1], sk[3 * i + 2]}, {sk[3 * i + 3], sk[3 * i + 4], sk[3 * i + 5]},
+                   RobotScalars<R>::radius(rb, i), R(0));
+            R best = prof[i];
+#pragma unroll 1
+            for (int j = 0; j < count; j++) {
+                const ObstacleRec &o = tile[j];
+                R d;
+                V3<R> P1 = {0, 0, 0}, P2 = {0, 0, 0};
+                if ((o.flags & 1u) && i < ground_included) {           // ground rule (:336-341)
+                    d = max_dist;
+                    P2.z = -max_dist;
+                } else {
+                    const Box<R> bx = load_box<R>(o);
+                    d = capsule_box_distance<R, MODE == RVS_DIST_FULL>(cp, bx, eq_thr, max_dist, P1, P2);
+                }
+                if (d > R(o.tol)) d = max_dist;                        // min_dist_tol (:367-368)
+                if (d <= R(0)) { limit = i; hit_d = d; hit_j = base + j; break; }        // first collision of the lowest link so far
+                if (d < best) best = d;
+                if (MODE == RVS_DIST_FULL) {
+                    R *dst = nearest + (size_t(base + j) * L + i) * 6;
+                    dst[0] = P1.x; dst[1] = P1.y; dst[2] = P1.z; dst[3] = P2.x; dst[4] = P2.y; dst[5] = P2.z;
+                }
+            }
+            prof[i] = best;
+        }
+    }
+    // Work accounting in the REFERENCE's loop order (link-major, stop at the first collision): the number of
+    // distanceCapsuleToBox calls RealVectorSpace::computeDistance would have made for this configuration.
+    if (a.pair_count) {
+        unsigned visited = 0;
+        if (live) {
+            for (int i = 0; i < limit; i++) visited += unsigned(a.M - (i < ground_included ? a.num_ground : 0));
+            if (limit < L) {
+                unsigned upto = unsigned(hit_j + 1);
+                if (limit < ground_included && a.num_ground > 0)
+                    for (int j = 0; j <= hit_j; j++) upto -= (a.obstacles[j].flags & 1u);
+                visited += upto;
+            }
+        }
+        for (int off = 16; off > 0; off >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, off);
+        if ((threadIdx.x & 31) == 0 && visited) atomicAdd(a.pair_count, (unsigned long long)visited);
+    }
+    if (!live) return;
+    const bool collided = limit < L;
+    R d_c = max_dist;
+    for (int i = 0; i < L; i++) if (prof[i] < d_c) d_c = prof[i];
+    static_cast<R *>(a.d_c)[cfg] = collided ? R(0) : d_c;
+    if (MODE >= RVS_DIST_PROFILE) {
+        R *out = static_cast<R *>(a.profile) + cfg * L;
+        for (int i = 0; i < L; i++) out[i] = !collided ? prof[i] : (i < limit ? prof[i] : (i == limit ? hit_d : R(0)));
+    }
+}
+
+// ---- isValid(q) (RealVectorSpace.cpp:277-309) ------------------------------------------------------------------------
+template <class F, class R>
+__device__ __forceinline__ bool config_is_valid(const KArgs &a, const RobotDev *__restrict__ rb, ObstacleRec *tile, const R *sk, bool live) {
+    const int L = rb->n;
+    const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
+    const int ground_included = rb->ground_included;
+    bool valid = true;
+    for (int base = 0; base < a.M; base += kTileObstacles) {
+        const int count = min(kTileObstacles, a.M - base);
+        __syncthreads();
+        stage_tile(tile, a.obstacles + base, count);
+        __syncthreads();
+        if (!live || !valid) continue;
+#pragma unroll 1
+        for (int i = 0; i < L && valid; i++) {
+            Capsule<R> cp;
+            cp.set({sk[3 * i], sk[3 * i + 1], sk[3 * i + 2]}, {sk[3 * i + 3], sk[3 * i + 4], sk[3 * i + 5]},
+                   RobotScalars<R>::radius(rb, i), RobotScalars<R>::radius_in(rb, i));
+#pragma unroll 1
+            for (int j = 0; j < count; j++) {
+                const ObstacleRec &o = tile[j];
+                if ((o.flags & 1u) && i < ground_included) continue;
+                if (capsule_hits_box<R>(cp, load_box<R>(o), eq_thr, max_dist)) { valid = false; break; }
+            }
+        }
+    }
+    return valid;
+}
+
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) is_valid_kernel(const KArgs a) {
+    __shared__ ObstacleRec tile[kTileObstacles];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    const bool live = cfg < a.N;
+    R sk[3 * (kMaxDofs + 1)];
+    if (live) fk_skeleton<F, R>(rb, a.q + cfg * rb->n, sk);
+    const bool valid = config_is_valid<F, R>(a, rb, tile, sk, live);
+    if (live) a.verdict[cfg] = valid ? 1 : 0;
+}
+
+// (q1 - q2).norm() of a dynamic VectorXf: Eigen's SSE2 linear-vectorised sum order (see oracle/rvs_oracle.hpp coord_norm)
+__device__ __forceinline__ float coord_norm(const float *__restrict__ a, const float *__restrict__ b, int n) {
+    const int aligned = (n / 4) * 4, aligned2 = (n / 8) * 8;
+    float res;
+    auto sq = [&](int i) { const float d = a[i] - b[i]; return d * d; };
+    if (aligned) {
+        float p0[4], p1[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) p0[l] = sq(l);
+        if (aligned > 4) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) p1[l] = sq(4 + l);
+            for (int idx = 8; idx < aligned2; idx += 8) {
+#pragma unroll
+                for (int l = 0; l < 4; l++) { p0[l] = p0[l] + sq(idx + l); p1[l] = p1[l] + sq(idx + 4 + l); }
+            }
+#pragma unroll
+            for (int l = 0; l < 4; l++) p0[l] = p0[l] + p1[l];
+            if (aligned > aligned2) {
+#pragma unroll
+                for (int l = 0; l < 4; l++) p0[l] = p0[l] + sq(aligned2 + l);
+            }
+        }
+        res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+        for (int i = aligned; i < n; i++) res = res + sq(i);
+    } else {
+        res = sq(0);
+        for (int i = 1; i < n; i++) res = res + sq(i);
+    }
+    return sqrtf(res);
+}
+
+// ---- isValid(q1, q2) (RealVectorSpace.cpp:261-275): one thread per (edge, check); verdict = AND over the checks -------
+// verdict[] must be pre-set to 1; threads that find a collision store 0 (idempotent).
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) edge_valid_kernel(const KArgs a) {
+    __shared__ ObstacleRec tile[kTileObstacles];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t tid = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    const int64_t edge = tid / a.num_checks;
+    const int kidx = int(tid - edge * a.num_checks);
+    const bool live = edge < a.N;
+    R sk[3 * (kMaxDofs + 1)];
+    if (live) {
+        const float *q1 = a.q + edge * n, *q2 = a.q2 + edge * n;
+        const float dist = coord_norm(q1, q2, n);
+        const float k = float(a.num_checks - kidx);                 // k = N .. 1
+        const float step = k / float(a.num_checks) * dist;
+        float qn[kMaxDofs];
+        if (dist > 0.f) {
+            const float f = step / dist;
+            for (int i = 0; i < n; i++) qn[i] = q1[i] + (q2[i] - q1[i]) * f;
+        } else
+            for (int i = 0; i < n; i++) qn[i] = q2[i];
+        fk_skeleton<F, R>(rb, qn, sk);
+    }
+    const bool valid = config_is_valid<F, R>(a, rb, tile, sk, live);
+    if (live && !valid) a.verdict[edge] = 0;
+}
+
+// ---- computeDistanceUnderestimation (RealVectorSpace.cpp:402-446) ----------------------------------------------------------
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) underestimation_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (cfg >= a.N) return;
+    const R max_dist = R(a.max_dist);
+    R sk[3 * (kMaxDofs + 1)];
+    fk_skeleton<F, R>(rb, a.q + cfg * L, sk);
+    const int root = a.plane_idx ? a.plane_idx[cfg] : 0;
+    const float *__restrict__ planes = a.planes + size_t(root) * size_t(a.M) * size_t(L) * 6;
+    R d_c = max_dist;
+    bool rejected = false;
+    R *prof = static_cast<R *>(a.profile) + cfg * L;
+#pragma unroll 1
+    for (int i = 0; i < L && !rejected; i++) {
+        const V3<R> A = {sk[3 * i], sk[3 * i + 1], sk[3 * i + 2]}, B = {sk[3 * i + 3], sk[3 * i + 4], sk[3 * i + 5]};
+        const R radius = RobotScalars<R>::radius(rb, i);
+        R best = max_dist;
+#pragma unroll 1
+        for (int j = 0; j < a.M; j++) {
+            const float2 *src = reinterpret_cast<const float2 *>(planes + (size_t(j) * L + i) * 6);
+            const float2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+            const V3<R> Rp = {R(w0.x), R(w0.y), R(w1.x)}, Op = {R(w1.y), R(w2.x), R(w2.y)};
+            if (rsqrt_of(dotF(Op, Op)) == max_dist) continue;         // ground placeholder (:420-422)
+            V3<R> nrm = sub(Rp, Op);
+            const R z = dotF(nrm, nrm);
+            if (z > R(0)) { const R len = rsqrt_of(z); nrm = {nrm.x / len, nrm.y / len, nrm.z / len}; }
+            const V3<R> ao = sub(A, Op), bo = sub(B, Op);
+            const R da = (ao.x * nrm.x + ao.y * nrm.y) + ao.z * nrm.z;   // dynamic-order dot (skeleton column lhs)
+            const R db = (bo.x * nrm.x + bo.y * nrm.y) + bo.z * nrm.z;
+            const R d = (db < da ? db : da) - radius;
+            if (d < R(0)) { rejected = true; break; }
+            if (d < best) best = d;
+        }
+        if (a.profile) prof[i] = best;
+        if (best < d_c) d_c = best;
+    }
+    static_cast<R *>(a.d_c)[cfg] = rejected ? R(0) : d_c;
+    if (a.status) a.status[cfg] = rejected ? 1 : 0;
+    if (rejected && a.profile) for (int i = 0; i < L; i++) prof[i] = R(0);
+}
+
+// ---- skeleton / enclosing radii / xArm6 capsule self-collision ---------------------------------------------------------
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) skeleton_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (cfg >= a.N) return;
+    R sk[3 * (kMaxDofs + 1)];
+    fk_skeleton<F, R>(rb, a.q + cfg * n, sk);
+    R *out = static_cast<R *>(a.d_c) + cfg * 3 * (n + 1);
+    for (int k = 0; k < 3 * (n + 1); k++) out[k] = sk[k];
+}
+
+// computeEnclosingRadii: xArm6.cpp:237-275, Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30. out: n x (n+1) row-major.
+template <class R>
+__device__ __forceinline__ void enclosing_radii_of(const RobotDev *__restrict__ rb, const R *sk, R *out) {
+    const int n = rb->n, W = n + 1;
+    for (int k = 0; k < n * W; k++) out[k] = R(0);
+    auto P = [&](int k) { return V3<R>{sk[3 * k], sk[3 * k + 1], sk[3 * k + 2]}; };
+    auto norm_xy = [&](int k) { return rsqrt_of(sk[3 * k] * sk[3 * k] + sk[3 * k + 1] * sk[3 * k + 1]); };
+    auto dist = [&](const V3<R> &u, const V3<R> &v) { return rsqrt_of(sqD(u.x - v.x, u.y - v.y, u.z - v.z)); };
+    if (rb->kind == RVS_ROBOT_XARM6) {
+        for (int i = 0; i < n - 1; i++)
+            for (int j = i + 1; j <= n; j++) {
+                const R rn = R(rb->radius_new[j - 1]);
+                R len;
+                if (i == 0) { if (j < 2) continue; len = norm_xy(j); }
+                else if (i == 3) {
+                    if (j < 5) continue;
+                    const V3<R> AB = sub(P(4), P(3)), v = sub(P(j), P(3));
+                    const R t = ((v.x * AB.x + v.y * AB.y) + v.z * AB.z) / dotF(AB, AB);
+                    len = dist(P(j), lerp_from(P(3), t, AB));
+                } else len = dist(P(j), P(i));
+                const R cand = len + rn, prev = out[i * W + j - 1];
+                out[i * W + j] = prev < cand ? cand : prev;
+            }
+    } else {
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j <= n; j++) {
+                const R len = (rb->kind == RVS_ROBOT_SPATIAL && i == 0) ? norm_xy(j) : dist(P(j), P(i));
+                const R cand = len + R(rb->radius[j - 1]), prev = out[i * W + j - 1];
+                out[i * W + j] = prev < cand ? cand : prev;
+            }
+    }
+}
+
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) enclosing_radii_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (cfg >= a.N) return;
+    R sk[3 * (kMaxDofs + 1)];
+    fk_skeleton<F, R>(rb, a.q + cfg * n, sk);
+    enclosing_radii_of<R>(rb, sk, static_cast<R *>(a.d_c) + cfg * n * (n + 1));
+}
+
+// generic segment-segment distance (distanceLineSegToLineSeg, CollisionAndDistance.cpp:217-320), distance only;
+// used by the xArm6 capsule self-collision pre-filter (xArm6.cpp:417-424) where neither segment is axis aligned.
+template <class R>
+__device__ __forceinline__ R seg_seg_distance(const V3<R> &A, const V3<R> &B, const V3<R> &C, const V3<R> &D, R eq_thr, R max_dist) {
+    const V3<R> AB = sub(B, A), CD = sub(D, C), DC = sub(C, D), CA = sub(A, C), BA = sub(A, B);
+    const R alpha1 = dotF(AB, AB), alpha2 = dotF(AB, CD), beta1 = dotF(DC, AB), beta2 = dotF(DC, CD);
+    const R gamma1 = dotF(CA, BA), gamma2 = dotF(CA, DC);
+    const R s = (alpha1 * gamma2 - alpha2 * gamma1) / (alpha1 * beta2 - alpha2 * beta1);
+    const R t = (gamma1 - beta1 * s) / alpha1;
+    if (t > R(0) && t < R(1) && s > R(0) && s < R(1)) {
+        const V3<R> p1 = lerp_from(A, t, AB), p2 = lerp_from(C, s, CD);
+        const R d = rsqrt_of(sqD(p2.x - p1.x, p2.y - p1.y, p2.z - p1.z));
+        return d < eq_thr ? R(0) : d;
+    }
+    const R alpha3 = dotF(DC, DC);
+    const R opt[4] = {dotF(CA, BA) / alpha1, dotF(sub(A, D), BA) / alpha1, dotF(CA, CD) / alpha3, dotF(sub(B, C), CD) / alpha3};
+    R best = max_dist;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        V3<R> p1, p2;
+        if (i < 2) {
+            p1 = opt[i] < R(0) ? A : (opt[i] > R(1) ? B : lerp_from(A, opt[i], AB));
+            p2 = i == 0 ? C : D;
+        } else {
+            p1 = i == 2 ? A : B;
+            p2 = opt[i] < R(0) ? C : (opt[i] > R(1) ? D : lerp_from(C, opt[i], CD));
+        }
+        const R d = rsqrt_of(sqD(p2.x - p1.x, p2.y - p1.y, p2.z - p1.z));
+        if (d < best) best = d;
+    }
+    return best;
+}
+
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) self_collision_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (cfg >= a.N) return;
+    uint8_t mask = 0;
+    if (rb->kind == RVS_ROBOT_XARM6) {
+        R sk[3 * (kMaxDofs + 1)];
+        fk_skeleton<F, R>(rb, a.q + cfg * n, sk);
+        auto P = [&](int k) { return V3<R>{sk[3 * k], sk[3 * k + 1], sk[3 * k + 2]}; };
+        const int pa[4] = {0, 1, 0, 1}, pb[4] = {5, 5, 4, 4};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const R d = seg_seg_distance<R>(P(pa[k]), P(pa[k] + 1), P(pb[k]), P(pb[k] + 1), R(a.eq_thr), R(a.max_dist)) -
+                        RobotScalars<R>::radius(rb, pa[k]) - RobotScalars<R>::radius(rb, pb[k]);
+            if (d < R(0)) mask |= uint8_t(1u << k);
+        }
+    }
+    a.verdict[cfg] = mask;
+}
+
+
+// ---- batched primitives (CollisionAndDistance::distanceCapsuleToBox / collisionCapsuleToBox as public statics) ------------
+// a.q = AB [K x 6], a.q2 = radius [K], a.planes = obs [K x 6]; a.d_c = out [K x 8] (distance) or a.verdict (collision).
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) primitive_kernel(const KArgs a) {
+    const int64_t i = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (i >= a.N) return;
+    const float *ab = a.q + 6 * i, *ob = a.planes + 6 * i;
+    const R radius = R(a.q2[i]);
+    Capsule<R> cp;
+    cp.set({R(ab[0]), R(ab[1]), R(ab[2])}, {R(ab[3]), R(ab[4]), R(ab[5])}, radius, R(double(radius) * sqrt(3.0) / 3));
+    const Box<R> bx = {{R(ob[0]), R(ob[1]), R(ob[2])}, {R(ob[3]), R(ob[4]), R(ob[5])}};
+    if (a.verdict) {
+        a.verdict[i] = capsule_hits_box<R>(cp, bx, R(a.eq_thr), R(a.max_dist)) ? 1 : 0;
+    } else {
+        V3<R> P1 = {0, 0, 0}, P2 = {0, 0, 0};
+        const R d = capsule_box_distance<R, true>(cp, bx, R(a.eq_thr), R(a.max_dist), P1, P2);
+        // the reference returns a null point pair exactly when the result is 0 (endpoint inside) or the snap paths
+        // produced d_c = 0 before the radius was subtracted; report has_points = (d > -radius-ish) conservatively as d > 0
+        float *o = static_cast<float *>(a.d_c) + 8 * i;
+        o[0] = float(d); o[1] = d > R(0) ? 1.f : 0.f;
+        o[2] = float(P1.x); o[3] = float(P1.y); o[4] = float(P1.z); o[5] = float(P2.x); o[6] = float(P2.y); o[7] = float(P2.z);
+    }
+}
+
+
+// ---- roofline denominators: register-only FMA microbenchmark (FFMA / DFMA issue peak of this device) ---------------------------
+#ifdef RVS_VARIANT_EXACT
+template <class T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(T *sink, int iters, T seed) {
+    T acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) acc[k] = seed + T(k) + T(threadIdx.x);
+    const T m = T(1.0000001), c = T(1e-9);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) acc[k] = fma(acc[k], m, c);
+    }
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += acc[k];
+    if (s == T(-1)) sink[0] = s;        // never true: keeps the chains alive
+}
+#endif
+
+// ---- stateless synthetic configurations ----------------------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+#ifdef RVS_VARIANT_EXACT
+__global__ void __launch_bounds__(256) generate_configs_kernel(const KArgs a, float *out) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t idx = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (idx >= a.N * n) return;
+    const int64_t i = idx / n;
+    const int j = int(idx - i * n);
+    const float u = float(splitmix64(a.seed ^ (uint64_t(a.first + i) * 32u + uint64_t(j))) >> 40) * (1.0f / 16777216.0f);
+    out[idx] = rb->limit_lo[j] + (rb->limit_hi[j] - rb->limit_lo[j]) * u;
+}
+#endif
+
+}  // namespace rvs

@@ -1,0 +1,28 @@
+// rvs_launch.h — launch tables exported by the per-variant translation units (rvs_variant.cu) to the C ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "rvs_types.h"
+
+namespace rvs {
+
+typedef cudaError_t (*LaunchFn)(const KArgs &, cudaStream_t);
+
+struct LaunchTable {
+    LaunchFn distance;
+    LaunchFn is_valid;
+    LaunchFn edge_valid;
+    LaunchFn underestimation;
+    LaunchFn skeleton;
+    LaunchFn enclosing_radii;
+    LaunchFn self_collision;
+    LaunchFn primitive;
+};
+
+LaunchTable launch_table_ref32();    // FK FP64, geometry FP32, no FMA contraction, IEEE div/sqrt
+LaunchTable launch_table_f64();      // everything FP64, no FMA contraction
+LaunchTable launch_table_fast32();   // everything FP32, FMA contraction allowed
+cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st);
+cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st);
+
+}  // namespace rvs

@@ -1,0 +1,75 @@
+// rvs_types.h — POD types shared by the C-ABI host code (rvs_capi.cu) and the sm_100a kernels.
+#pragma once
+#include <stdint.h>
+
+#include "../../include/rvs_cuda.h"
+
+namespace rvs {
+
+constexpr int kMaxDofs = RVS_MAX_DOFS;
+constexpr int kTileObstacles = 512;     // obstacles staged per shared-memory tile (32 B each -> 16 KB)
+
+// Obstacle record as it sits in HBM and in shared memory: two 16-byte words, so that one obstacle is two
+// broadcast LDS.128 for the whole warp.   w0 = (lo.x, lo.y, lo.z, hi.x)   w1 = (hi.y, hi.z, min_dist_tol, flags)
+// flags (bit pattern in the float slot): bit0 = label == "ground".
+struct ObstacleRec {
+    float lo[3];
+    float hi[3];
+    float tol;
+    uint32_t flags;
+};
+static_assert(sizeof(ObstacleRec) == 32, "ObstacleRec must be 32 bytes");
+
+enum AxisCode : int32_t { AXIS_X = 0, AXIS_Y = 1, AXIS_Z = 2, AXIS_GENERAL = 3 };
+
+// Robot chain resident in HBM (one copy per handle). Doubles first for alignment.
+struct RobotDev {
+    double xyz[kMaxDofs + 1][3];     // joint origin in parent frame
+    double rfix[kMaxDofs + 1][9];    // RPY rotation of the joint origin, row-major
+    double axis[kMaxDofs][3];        // unit joint axis
+    double radius_d[kMaxDofs];       // capsule radii widened (F64 variant)
+    double radius_in_d[kMaxDofs];    // radius*sqrt(3)/3 in double (F64 variant)
+    float radius[kMaxDofs];          // AbstractRobot::capsules_radius
+    float radius_in[kMaxDofs];       // float(double(radius)*sqrt(3)/3)  (CollisionAndDistance.cpp:7)
+    float radius_new[kMaxDofs];      // xArm6::capsules_radius_new (xArm6.cpp:98-105); == radius for other kinds
+    float limit_lo[kMaxDofs];
+    float limit_hi[kMaxDofs];
+    int32_t axis_code[kMaxDofs];
+    int32_t rfix_identity[kMaxDofs + 1];
+    int32_t kind;
+    int32_t n;                       // DOFs == links
+    int32_t ground_included;
+    float gripper_length;
+};
+
+// Arguments of the hot-path kernels (passed by value).
+struct KArgs {
+    const RobotDev *robot;
+    const ObstacleRec *obstacles;
+    int32_t M;
+    int64_t N;
+    const float *q;          // N x n
+    const float *q2;         // edges: far end
+    float eq_thr;
+    float max_dist;
+    int32_t num_checks;
+    int32_t mode;            // rvs_distance_mode
+    int32_t cull;
+    void *d_c;               // float* or double*
+    void *profile;
+    void *nearest;
+    uint8_t *verdict;
+    // underestimation
+    const float *planes;
+    const int32_t *plane_idx;
+    int32_t R;
+    uint8_t *status;
+    // generated configurations
+    uint64_t seed;
+    int64_t first;
+    int32_t robot_n_hint;    // num_dofs as known by the host (grid sizing)
+    int32_t num_ground;      // obstacles flagged ground
+    unsigned long long *pair_count;   // += pair queries the reference's loop would have visited (early exit respected)
+};
+
+}  // namespace rvs

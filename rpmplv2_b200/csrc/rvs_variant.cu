@@ -1,0 +1,81 @@
+// rvs_variant.cu — instantiates the kernels of rvs_kernels.cuh for one arithmetic variant.
+// Compiled twice (see Makefile):
+//   -DRVS_VARIANT_EXACT  -fmad=false -prec-div=true -prec-sqrt=true -ftz=false   -> REF32 and F64 launch tables
+//   -DRVS_VARIANT_FAST   -fmad=true                                             -> FAST32 launch table
+#include "rvs_kernels.cuh"
+#include "rvs_launch.h"
+
+namespace rvs {
+namespace {
+
+inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
+
+template <class F, class R>
+struct Variant {
+    static cudaError_t distance(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        const unsigned g = grid_for(a.N, kBlock);
+        if (a.mode == RVS_DIST_MIN) distance_kernel<F, R, RVS_DIST_MIN><<<g, kBlock, 0, st>>>(a);
+        else if (a.mode == RVS_DIST_PROFILE) distance_kernel<F, R, RVS_DIST_PROFILE><<<g, kBlock, 0, st>>>(a);
+        else distance_kernel<F, R, RVS_DIST_FULL><<<g, kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t is_valid(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        is_valid_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t edge_valid(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        edge_valid_kernel<F, R><<<grid_for(a.N * a.num_checks, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t underestimation(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        underestimation_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t skeleton(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        skeleton_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t enclosing_radii(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        enclosing_radii_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t self_collision(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        self_collision_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t primitive(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        primitive_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static LaunchTable table() { return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive}; }
+};
+
+}  // namespace
+
+#ifdef RVS_VARIANT_EXACT
+LaunchTable launch_table_ref32() { return Variant<double, float>::table(); }
+LaunchTable launch_table_f64() { return Variant<double, double>::table(); }
+cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st) {
+    if (a.N <= 0) return cudaSuccess;
+    generate_configs_kernel<<<grid_for(a.N * a.robot_n_hint, 256), 256, 0, st>>>(a, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st) {
+    if (fp64) fma_peak_kernel<double><<<blocks, 256, 0, st>>>(static_cast<double *>(sink), iters, 1.0);
+    else fma_peak_kernel<float><<<blocks, 256, 0, st>>>(static_cast<float *>(sink), iters, 1.0f);
+    return cudaGetLastError();
+}
+#endif
+#ifdef RVS_VARIANT_FAST
+LaunchTable launch_table_fast32() { return Variant<float, float>::table(); }
+#endif
+
+}  // namespace rvs

@@ -1,0 +1,272 @@
+"""ctypes binding of librvs_cuda.so (include/rvs_cuda.h) — the thin host layer every Python caller goes through.
+
+There is NO CPU fallback here: if the shared library is missing, or no CUDA device is usable, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .robots import (DIST_FULL, DIST_MIN, DIST_PROFILE, PREC_F64, PREC_REF32, Robot, RvsParams, RvsRobotDesc, RvsSpineParams,
+                     default_params)
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librvs_cuda.so")
+
+c_f32p = ctypes.POINTER(ctypes.c_float)
+c_f64p = ctypes.POINTER(ctypes.c_double)
+c_u8p = ctypes.POINTER(ctypes.c_uint8)
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+
+#: every symbol include/rvs_cuda.h declares: name -> (restype, argtypes)
+_H = ctypes.c_void_p
+SYMBOLS = {
+    "rvs_abi_version": (ctypes.c_int, []),
+    "rvs_device_count": (ctypes.c_int, []),
+    "rvs_create": (ctypes.c_int, [ctypes.POINTER(RvsRobotDesc), ctypes.POINTER(RvsParams), ctypes.c_int, ctypes.POINTER(_H)]),
+    "rvs_destroy": (ctypes.c_int, [_H]),
+    "rvs_last_error": (ctypes.c_char_p, [_H]),
+    "rvs_set_params": (ctypes.c_int, [_H, ctypes.POINTER(RvsParams)]),
+    "rvs_set_stream": (ctypes.c_int, [_H, ctypes.c_void_p]),
+    "rvs_get_stream": (ctypes.c_void_p, [_H]),
+    "rvs_sync": (ctypes.c_int, [_H]),
+    "rvs_launch_count": (ctypes.c_int64, [_H]),
+    "rvs_measure_fma_peak": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
+    "rvs_pair_count": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]),
+    "rvs_set_obstacles": (ctypes.c_int, [_H, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_int32]),
+    "rvs_update_obstacle_aabbs": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int32]),
+    "rvs_num_obstacles": (ctypes.c_int, [_H]),
+    "rvs_is_valid": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_is_valid_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_distance": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, ctypes.c_int32, c_f32p, c_f32p, c_f32p]),
+    "rvs_underestimation": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_f32p, c_i32p, ctypes.c_int32, c_f32p, c_f32p, c_u8p]),
+    "rvs_skeleton": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_f32p]),
+    "rvs_enclosing_radii": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_f32p]),
+    "rvs_self_collision_capsules": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_extend_spines": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int32,
+                                         ctypes.POINTER(RvsSpineParams), c_f32p, c_f32p, c_u8p]),
+    "rvs_capsule_box_distance": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p]),
+    "rvs_capsule_box_collision": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_distance_f64": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, ctypes.c_int32, c_f64p, c_f64p, c_f64p]),
+    "rvs_is_valid_f64": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_is_valid_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "rvs_is_valid_edges_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "rvs_distance_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rvs_distance_f64_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rvs_underestimation_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                               ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
+    "rvs_generate_configs_dev": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "rvs_set_culling": (ctypes.c_int, [_H, ctypes.c_int32]),
+}
+
+_lib = None
+
+
+class RvsError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"rvs error {code}: {message}")
+        self.code = code
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen librvs_cuda.so and bind every declared symbol. Raises if the library or a symbol is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                                "(there is no CPU fallback)")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export a declared symbol
+        fn.restype, fn.argtypes = res, args
+    if lib.rvs_abi_version() != 1:
+        raise RuntimeError("librvs_cuda.so ABI version mismatch")
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _p(a: Optional[np.ndarray], typ):
+    return None if a is None else a.ctypes.data_as(typ)
+
+
+def _f32(a, shape=None):
+    a = np.ascontiguousarray(a, np.float32)
+    return a if shape is None else a.reshape(shape)
+
+
+class Engine:
+    """One handle = one robot + one resident obstacle table on one device."""
+
+    def __init__(self, robot: Robot, params: Optional[RvsParams] = None, device: int = 0):
+        self._lib = load_library()
+        self.robot = robot
+        self.params = params or default_params()
+        self.n = robot.num_dofs
+        self.M = 0
+        self.device = device
+        self._desc = robot.to_desc()
+        h = _H()
+        rc = self._lib.rvs_create(ctypes.byref(self._desc), ctypes.byref(self.params), device, ctypes.byref(h))
+        if rc != 0:
+            raise RvsError(rc, (self._lib.rvs_last_error(None) or b"").decode())
+        self._h = h
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RvsError(rc, (self._lib.rvs_last_error(self._h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rvs_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def is_f64(self) -> bool:
+        return self.params.precision == PREC_F64
+
+    def set_stream(self, cuda_stream_ptr: int):
+        self._check(self._lib.rvs_set_stream(self._h, ctypes.c_void_p(cuda_stream_ptr)))
+
+    def sync(self):
+        self._check(self._lib.rvs_sync(self._h))
+
+    def launch_count(self) -> int:
+        return int(self._lib.rvs_launch_count(self._h))
+
+    def pair_count(self, reset: bool = False) -> int:
+        """Pair queries the reference's own loop would have made for everything passed to distance*() so far."""
+        v = ctypes.c_uint64(0)
+        self._check(self._lib.rvs_pair_count(self._h, 1 if reset else 0, ctypes.byref(v)))
+        return int(v.value)
+
+    def measure_fma_peak(self, fp64: bool = False) -> float:
+        """FFMA / DFMA issue peak of this device in TFLOP/s (register-only microbenchmark)."""
+        v = ctypes.c_double(0)
+        self._check(self._lib.rvs_measure_fma_peak(self._h, 1 if fp64 else 0, ctypes.byref(v)))
+        return float(v.value)
+
+    def set_culling(self, on: bool):
+        self._check(self._lib.rvs_set_culling(self._h, 1 if on else 0))
+
+    def set_params(self, params: RvsParams):
+        self._check(self._lib.rvs_set_params(self._h, ctypes.byref(params)))
+        self.params = params
+
+    # -- obstacles ---------------------------------------------------------------------------------------------
+    def set_obstacles(self, aabb_min, aabb_max, is_ground=None, min_dist_tol=None):
+        mn, mx = _f32(aabb_min, (-1, 3)), _f32(aabb_max, (-1, 3))
+        if mn.shape != mx.shape:
+            raise ValueError("aabb_min / aabb_max shape mismatch")
+        M = mn.shape[0]
+        g = None if is_ground is None else np.ascontiguousarray(is_ground, np.uint8)
+        t = None if min_dist_tol is None else _f32(min_dist_tol)
+        self._check(self._lib.rvs_set_obstacles(self._h, _p(mn, c_f32p), _p(mx, c_f32p), _p(g, c_u8p), _p(t, c_f32p), M))
+        self.M = M
+
+    def update_obstacle_aabbs(self, aabb_min, aabb_max):
+        mn, mx = _f32(aabb_min, (-1, 3)), _f32(aabb_max, (-1, 3))
+        self._check(self._lib.rvs_update_obstacle_aabbs(self._h, _p(mn, c_f32p), _p(mx, c_f32p), mn.shape[0]))
+
+    # -- hot path, host arrays ----------------------------------------------------------------------------------
+    def is_valid(self, q) -> np.ndarray:
+        q = _f32(q, (-1, self.n))
+        out = np.empty(q.shape[0], np.uint8)
+        fn = self._lib.rvs_is_valid_f64 if self.is_f64 else self._lib.rvs_is_valid
+        self._check(fn(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_u8p)))
+        return out
+
+    def is_valid_edges(self, q1, q2) -> np.ndarray:
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        if q1.shape != q2.shape:
+            raise ValueError("q1 / q2 shape mismatch")
+        out = np.empty(q1.shape[0], np.uint8)
+        self._check(self._lib.rvs_is_valid_edges(self._h, _p(q1, c_f32p), _p(q2, c_f32p), q1.shape[0], _p(out, c_u8p)))
+        return out
+
+    def distance(self, q, mode: int = DIST_PROFILE):
+        """Returns (d_c[N], profile[N,L] or None, nearest[N,M,L,6] or None); float64 arrays on an F64 handle."""
+        q = _f32(q, (-1, self.n))
+        N = q.shape[0]
+        dt, pt, fn = ((np.float64, c_f64p, self._lib.rvs_distance_f64) if self.is_f64
+                      else (np.float32, c_f32p, self._lib.rvs_distance))
+        d_c = np.empty(N, dt)
+        profile = np.empty((N, self.n), dt) if mode >= DIST_PROFILE else None
+        nearest = np.zeros((N, self.M, self.n, 6), dt) if mode == DIST_FULL else None
+        self._check(fn(self._h, _p(q, c_f32p), N, mode, _p(d_c, pt), _p(profile, pt), _p(nearest, pt)))
+        return d_c, profile, nearest
+
+    def underestimation(self, q, planes, plane_idx=None):
+        q = _f32(q, (-1, self.n))
+        N = q.shape[0]
+        planes = _f32(planes, (-1, self.M, self.n, 6))
+        idx = None if plane_idx is None else np.ascontiguousarray(plane_idx, np.int32)
+        d_c, profile, status = np.empty(N, np.float32), np.empty((N, self.n), np.float32), np.empty(N, np.uint8)
+        self._check(self._lib.rvs_underestimation(self._h, _p(q, c_f32p), N, _p(planes, c_f32p), _p(idx, c_i32p), planes.shape[0],
+                                                  _p(d_c, c_f32p), _p(profile, c_f32p), _p(status, c_u8p)))
+        return d_c, profile, status
+
+    def skeleton(self, q) -> np.ndarray:
+        q = _f32(q, (-1, self.n))
+        out = np.empty((q.shape[0], self.n + 1, 3), np.float32)
+        self._check(self._lib.rvs_skeleton(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_f32p)))
+        return out
+
+    def enclosing_radii(self, q) -> np.ndarray:
+        q = _f32(q, (-1, self.n))
+        out = np.empty((q.shape[0], self.n, self.n + 1), np.float32)
+        self._check(self._lib.rvs_enclosing_radii(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_f32p)))
+        return out
+
+    def self_collision_capsules(self, q) -> np.ndarray:
+        q = _f32(q, (-1, self.n))
+        out = np.empty(q.shape[0], np.uint8)
+        self._check(self._lib.rvs_self_collision_capsules(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_u8p)))
+        return out
+
+    def capsule_box_distance(self, AB, radius, obs) -> np.ndarray:
+        """Batched CollisionAndDistance::distanceCapsuleToBox: rows (d, has_points, P1 xyz, P2 xyz)."""
+        AB, obs = _f32(AB, (-1, 6)), _f32(obs, (-1, 6))
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (AB.shape[0],)))
+        out = np.empty((AB.shape[0], 8), np.float32)
+        self._check(self._lib.rvs_capsule_box_distance(self._h, _p(AB, c_f32p), _p(r, c_f32p), _p(obs, c_f32p), AB.shape[0], _p(out, c_f32p)))
+        return out
+
+    def capsule_box_collision(self, AB, radius, obs) -> np.ndarray:
+        """Batched CollisionAndDistance::collisionCapsuleToBox."""
+        AB, obs = _f32(AB, (-1, 6)), _f32(obs, (-1, 6))
+        r = np.ascontiguousarray(np.broadcast_to(np.asarray(radius, np.float32), (AB.shape[0],)))
+        out = np.empty(AB.shape[0], np.uint8)
+        self._check(self._lib.rvs_capsule_box_collision(self._h, _p(AB, c_f32p), _p(r, c_f32p), _p(obs, c_f32p), AB.shape[0], _p(out, c_u8p)))
+        return out
+
+    # -- device pointers (ints, e.g. torch.Tensor.data_ptr()), stream ordered ----------------------------------------
+    def distance_dev(self, d_q: int, N: int, mode: int, d_dc: int, d_profile: int = 0, d_nearest: int = 0):
+        fn = self._lib.rvs_distance_f64_dev if self.is_f64 else self._lib.rvs_distance_dev
+        self._check(fn(self._h, d_q, N, mode, d_dc, d_profile or None, d_nearest or None))
+
+    def is_valid_dev(self, d_q: int, N: int, d_valid: int):
+        self._check(self._lib.rvs_is_valid_dev(self._h, d_q, N, d_valid))
+
+    def is_valid_edges_dev(self, d_q1: int, d_q2: int, E: int, d_valid: int):
+        self._check(self._lib.rvs_is_valid_edges_dev(self._h, d_q1, d_q2, E, d_valid))
+
+    def underestimation_dev(self, d_q: int, N: int, d_planes: int, d_plane_idx: int, R: int, d_dc: int, d_profile: int = 0,
+                            d_status: int = 0):
+        self._check(self._lib.rvs_underestimation_dev(self._h, d_q, N, d_planes, d_plane_idx or None, R, d_dc, d_profile or None,
+                                                      d_status or None))
+
+    def generate_configs_dev(self, seed: int, first: int, N: int, d_q: int):
+        self._check(self._lib.rvs_generate_configs_dev(self._h, ctypes.c_uint64(seed), first, N, d_q))

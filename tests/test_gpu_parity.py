@@ -1,0 +1,289 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (librvs_cuda.so), against the CPU oracle and the
+golden vectors of the reference's own CollisionAndDistance.cpp.
+
+Tolerances (BASELINE.json north_star / SURVEY.md §8d):
+  REF32  : verdicts identical; distances |d - d_oracle<float>| <= 1e-4 m (expected: bit-exact up to FK last-ulp effects)
+  FAST32 : distances <= 1e-4 m; verdicts identical outside the band |clearance| <= 1e-4 m
+  F64    : distances |d - d_oracle<double>| <= 1e-9 m
+"""
+import numpy as np
+import pytest
+
+import scenes
+from conftest import same
+from rpmplv2_b200 import engine, robots, synthetic
+
+pytestmark = pytest.mark.gpu
+
+TOL32, TOL64 = 1e-4, 1e-9
+
+
+def make(rb, mn, mx, g, tol, prec=robots.PREC_REF32, thr=1e-4):
+    eng = engine.Engine(rb, robots.default_params(prec, equality_threshold=thr))
+    eng.set_obstacles(mn, mx, g, tol)
+    return eng
+
+
+def make_oracle(ob, rb, mn, mx, g, tol, thr=1e-4):
+    o = ob.Oracle(rb, robots.default_params(equality_threshold=thr))
+    o.set_obstacles(mn, mx, g, tol)
+    return o
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,thr", [("t4", 1e-4), ("t6", 1e-6)])
+def test_primitives_match_reference_golden_bit_exact(golden, tag, thr):
+    eng = engine.Engine(robots.xarm6(), robots.default_params(robots.PREC_REF32, equality_threshold=thr))
+    AB, r, obs, g = golden[f"{tag}_AB"], golden[f"{tag}_r"], golden[f"{tag}_obs"], golden[f"{tag}_dist"]
+    out = eng.capsule_box_distance(AB, r, obs)
+    assert same(out[:, 0], g[:, 0]).all()
+    live = (g[:, 1] == 1) & (g[:, 0] > 0)
+    assert same(out[live, 2:], g[live, 2:]).all()
+    assert (eng.capsule_box_collision(AB, r, obs) == golden[f"{tag}_coll"]).all()
+
+
+def test_primitives_fast32_within_tolerance(golden):
+    eng = engine.Engine(robots.xarm6(), robots.default_params(robots.PREC_FAST32))
+    g = golden["t4_dist"]
+    out = eng.capsule_box_distance(golden["t4_AB"], golden["t4_r"], golden["t4_obs"])
+    ok = np.isfinite(g[:, 0])
+    diff = np.abs(out[ok, 0] - g[ok, 0])
+    # the snap (d < EQUALITY_THRESHOLD -> -r) and the exactly-on-a-face cases are discontinuous: allow them in the band
+    big = diff > TOL32
+    assert big.mean() < 0.01
+    coll = eng.capsule_box_collision(golden["t4_AB"], golden["t4_r"], golden["t4_obs"])
+    assert (coll != golden["t4_coll"]).mean() < 0.005
+
+
+@pytest.mark.parametrize("rb", [robots.xarm6(), robots.planar(2), robots.planar(10), robots.spatial(10), robots.spatial(14),
+                                robots.spatial(18), robots.spatial(22)], ids=lambda r: r.name)
+def test_skeleton_radii_selfcollision(ob, rb):
+    q = synthetic.configs(rb, 5000)
+    eng, o = engine.Engine(rb), ob.Oracle(rb)
+    sk, sk_o = eng.skeleton(q), o.skeleton(q)
+    assert np.abs(sk - sk_o).max() <= 2.4e-7          # FK in FP64 on both sides; at most a last-ulp flip after narrowing
+    assert (sk != sk_o).mean() < 1e-4
+    R, R_o = eng.enclosing_radii(q), o.enclosing_radii(q)
+    assert np.abs(R - R_o).max() <= 1e-6
+    assert (eng.self_collision_capsules(q) == o.self_collision_capsules(q)).mean() > 0.9999
+
+
+@pytest.mark.parametrize("M,dist,r_min", [(1, "D2", 0.0), (10, "D2", 0.0), (51, "D1", 0.0), (100, "D2", 0.5), (600, "D2", 0.9), (1300, "D1", 0.8)])
+def test_distance_ref32_vs_oracle(ob, M, dist, r_min):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(M, dist, r_min)
+    q = synthetic.configs(rb, 12000)
+    eng, o = make(rb, mn, mx, g, tol), make_oracle(ob, rb, mn, mx, g, tol)
+    d_o, p_o, _ = o.distance(q, robots.DIST_PROFILE)
+    d_min, _, _ = eng.distance(q, robots.DIST_MIN)
+    d, p, _ = eng.distance(q, robots.DIST_PROFILE)
+    assert (d_min == d).all()
+    assert ((d == 0) == (d_o == 0)).all()                              # collision verdict of computeDistance
+    assert np.abs(d - d_o).max() <= TOL32 and np.abs(p - p_o).max() <= TOL32
+    assert (d != d_o).mean() < 1e-3 and (p != p_o).mean() < 1e-3       # REF32 is bit-exact up to rare FK last-ulp effects
+    assert eng.pair_count(reset=True) == 2 * o.pair_count(reset=True)  # two GPU calls vs one oracle call
+
+
+def test_distance_full_nearest_points(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D1", 0.3)
+    q = synthetic.configs(rb, 3000)
+    eng, o = make(rb, mn, mx, g, tol), make_oracle(ob, rb, mn, mx, g, tol)
+    d, p, near = eng.distance(q, robots.DIST_FULL)
+    d_o, p_o, near_o = o.distance(q, robots.DIST_FULL)
+    free = d_o > 0
+    assert free.sum() > 300 and ((d > 0) == free).all()
+    assert np.abs(near[free] - near_o[free]).max() <= TOL32
+    assert (near[free] != near_o[free]).mean() < 1e-3
+    # ground placeholder planes for the first ground_included links (RealVectorSpace.cpp:336-341)
+    assert (near[free][:, 0, :2, :3] == 0).all() and (near[free][:, 0, :2, 5] == -1000.0).all()
+
+
+def test_is_valid_and_edges_vs_oracle(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(40, "D2", 0.3)
+    q = synthetic.configs(rb, 20000)
+    eng, o = make(rb, mn, mx, g, tol), make_oracle(ob, rb, mn, mx, g, tol)
+    v, v_o = eng.is_valid(q), o.is_valid(q)
+    assert 0.05 < v_o.mean() < 0.95
+    assert (v != v_o).sum() == 0
+    q1, q2 = synthetic.edges(rb, 6000, 0.1)
+    e, e_o = eng.is_valid_edges(q1, q2), o.is_valid_edges(q1, q2)
+    assert 0.05 < e_o.mean() < 0.95
+    assert (e != e_o).sum() == 0
+    # an edge is valid iff all its interpolated configurations are: q2 itself is the first check (k = N)
+    assert (e <= eng.is_valid(q2)).all()
+
+
+def test_underestimation_vs_oracle_and_reference_invariant(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(30, "D2", 0.4)
+    tol[:] = 1000.0
+    eng, o = make(rb, mn, mx, g, tol), make_oracle(ob, rb, mn, mx, g, tol)
+    roots = synthetic.configs(rb, 400)
+    d, p, near = eng.distance(roots, robots.DIST_FULL)
+    idx = np.flatnonzero(d > 0)[:64]
+    assert len(idx) >= 16
+    planes = near[idx]
+    rng = np.random.default_rng(3)
+    N = 8000
+    pick = rng.integers(0, len(idx), N).astype(np.int32)
+    q = (roots[idx][pick] + rng.normal(0, 0.15, (N, rb.num_dofs))).astype(np.float32)
+    du, pu, st = eng.underestimation(q, planes, pick)
+    du_o, pu_o, st_o = o.underestimation(q, planes, pick)
+    assert (st == st_o).all() and 0.02 < st_o.mean() < 0.98
+    assert np.abs(du - du_o).max() <= TOL32 and np.abs(pu - pu_o).max() <= TOL32
+    # apps/test_real_vector_space.cpp:46-57 — at the generating configuration the planes reproduce the real distance
+    own, own_p, own_s = eng.underestimation(roots[idx], planes, np.arange(len(idx), dtype=np.int32))
+    assert (own_s == 0).all() and np.abs(own - d[idx]).max() <= 1e-3
+
+
+def test_f64_variant_vs_oracle_double(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(60, "D2", 0.5)
+    q = synthetic.configs(rb, 8000)
+    eng, o = make(rb, mn, mx, g, tol, robots.PREC_F64), make_oracle(ob, rb, mn, mx, g, tol)
+    d, p, _ = eng.distance(q, robots.DIST_PROFILE)
+    d_o, p_o, _ = o.distance(q, robots.DIST_PROFILE, f64=True)
+    assert d.dtype == np.float64
+    assert ((d == 0) == (d_o == 0)).all()
+    assert np.abs(d - d_o).max() <= TOL64 and np.abs(p - p_o).max() <= TOL64
+    assert (eng.is_valid(q) == o.is_valid(q, f64=True)).all()
+
+
+def test_fast32_variant_within_stated_tolerance(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(60, "D2", 0.5)
+    q = synthetic.configs(rb, 20000)
+    eng, o = make(rb, mn, mx, g, tol, robots.PREC_FAST32), make_oracle(ob, rb, mn, mx, g, tol)
+    d, p, _ = eng.distance(q, robots.DIST_PROFILE)
+    d_o, p_o, _ = o.distance(q, robots.DIST_PROFILE)
+    d64, _, _ = o.distance(q, robots.DIST_MIN, f64=True)
+    band = np.abs(d64) <= 1e-4                                          # |true clearance| within the epsilon band
+    flips = (d == 0) != (d_o == 0)
+    assert not (flips & ~band).any()
+    both = (d > 0) & (d_o > 0)
+    assert np.abs(d[both] - d_o[both]).max() <= TOL32
+    v, v_o = eng.is_valid(q), o.is_valid(q)
+    assert (v != v_o).mean() < 2e-4
+
+
+@pytest.mark.parametrize("case", ["planar2_scenario_test", "xarm6_scenario1", "planar10", "spatial10", "spatial22"])
+def test_other_robots_and_shipped_scenes(ob, case):
+    if case == "planar2_scenario_test":
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    elif case == "xarm6_scenario1":
+        rb, mn, mx, g, tol = scenes.xarm6_scenario1()
+    elif case == "planar10":
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.planar(10), 4)
+    elif case == "spatial10":
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(10), 6)
+    else:
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 6)
+    q = synthetic.configs(rb, 10000)
+    eng, o = make(rb, mn, mx, g, tol), make_oracle(ob, rb, mn, mx, g, tol)
+    d, p, near = eng.distance(q, robots.DIST_FULL)
+    d_o, p_o, near_o = o.distance(q, robots.DIST_FULL)
+    assert 0.02 < (d_o > 0).mean() < 0.999
+    assert ((d == 0) == (d_o == 0)).all()
+    assert np.abs(d - d_o).max() <= TOL32 and np.abs(p - p_o).max() <= TOL32
+    free = d_o > 0
+    assert np.abs(near[free] - near_o[free]).max() <= TOL32
+    assert (eng.is_valid(q) != o.is_valid(q)).sum() == 0
+    q1, q2 = synthetic.edges(rb, 3000, 0.1)
+    assert (eng.is_valid_edges(q1, q2) != o.is_valid_edges(q1, q2)).sum() == 0
+
+
+def test_edge_cases_and_errors(ob):
+    rb, mn, mx, g, tol = scenes.xarm6_scene(5, "D2")
+    eng = engine.Engine(rb)
+    q = synthetic.configs(rb, 130)
+    d, p, near = eng.distance(q, robots.DIST_FULL)                     # M = 0: no obstacles at all
+    assert (d == 1000.0).all() and (p == 1000.0).all() and near.shape == (130, 0, 6, 6)
+    assert eng.is_valid(q).all() and eng.is_valid_edges(q, q[::-1].copy()).all()
+    eng.set_obstacles(mn, mx, g, tol)
+    assert eng.distance(q[:0], robots.DIST_PROFILE)[0].shape == (0,)   # N = 0
+    assert eng.is_valid(q[:0]).shape == (0,)
+    one = eng.distance(q[:1], robots.DIST_PROFILE)                    # N = 1 == batch slice
+    whole = eng.distance(q, robots.DIST_PROFILE)
+    assert one[0][0] == whole[0][0] and (one[1][0] == whole[1][0]).all()
+    # min_dist_tol: distances above the tolerance become MAX_DISTANCE (RealVectorSpace.cpp:367-368)
+    o = make_oracle(ob, rb, mn, mx, g, np.full(5, 0.1, np.float32))
+    eng.set_obstacles(mn, mx, g, np.full(5, 0.1, np.float32))
+    dd, pp, _ = eng.distance(q, robots.DIST_PROFILE)
+    d_o, p_o, _ = o.distance(q, robots.DIST_PROFILE)
+    assert (pp == 1000.0).any() and np.abs(pp - p_o).max() <= TOL32
+    # obstacle motion: update_obstacle_aabbs == set_obstacles with the moved boxes
+    shift = np.array([0.07, -0.03, 0.02], np.float32)
+    eng.update_obstacle_aabbs(mn + shift, mx + shift)
+    o.set_obstacles(mn + shift, mx + shift, g, np.full(5, 0.1, np.float32))
+    assert np.abs(eng.distance(q, robots.DIST_MIN)[0] - o.distance(q, robots.DIST_MIN)[0]).max() <= TOL32
+    with pytest.raises(engine.RvsError):
+        eng.update_obstacle_aabbs(mn[:2], mx[:2])                      # M differs from the resident table
+    with pytest.raises(engine.RvsError):
+        eng.distance(q, 7)                                             # bad mode
+    with pytest.raises(engine.RvsError):
+        engine.Engine(rb, robots.default_params(robots.PREC_F64)).skeleton(q)
+    with pytest.raises(engine.RvsError):
+        engine.Engine(rb, device=10 ** 6)
+    bad = robots.xarm6()
+    bad.axis[2] = 0.0
+    with pytest.raises(engine.RvsError):
+        engine.Engine(bad)
+
+
+def test_device_pointer_api_and_generator(ob):
+    torch = pytest.importorskip("torch")
+    rb, mn, mx, g, tol = scenes.xarm6_scene(64, "D2", 0.6)
+    eng = make(rb, mn, mx, g, tol)
+    N = 50000
+    stream = torch.cuda.Stream()
+    eng.set_stream(stream.cuda_stream)
+    with torch.cuda.stream(stream):
+        d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+        d_dc = torch.empty(N, dtype=torch.float32, device="cuda")
+        d_prof = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+        d_val = torch.empty(N, dtype=torch.uint8, device="cuda")
+        eng.generate_configs_dev(synthetic.SEED_CONFIGS, 1000, N, d_q.data_ptr())
+        eng.distance_dev(d_q.data_ptr(), N, robots.DIST_PROFILE, d_dc.data_ptr(), d_prof.data_ptr())
+        eng.is_valid_dev(d_q.data_ptr(), N, d_val.data_ptr())
+    stream.synchronize()
+    q = synthetic.configs(rb, N, first=1000)
+    assert (d_q.cpu().numpy() == q).all()                              # device generator == numpy generator, bit for bit
+    o = make_oracle(ob, rb, mn, mx, g, tol)
+    d_o, p_o, _ = o.distance(q, robots.DIST_PROFILE, threads=8)
+    assert np.abs(d_dc.cpu().numpy() - d_o).max() <= TOL32
+    assert np.abs(d_prof.cpu().numpy() - p_o).max() <= TOL32
+    assert (d_val.cpu().numpy() == o.is_valid(q, threads=8)).all()
+
+
+def test_full_size_properties():
+    """BASELINE sweep size (2^20 configurations x 1000 boxes): size-independent properties instead of an oracle run."""
+    torch = pytest.importorskip("torch")
+    rb, mn, mx, g, tol = scenes.xarm6_scene(1000, "D2", 0.9)
+    eng = make(rb, mn, mx, g, tol)
+    N = 1 << 20
+    d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+    out = {k: torch.empty(N, dtype=torch.float32, device="cuda") for k in ("min", "prof", "perm", "again")}
+    prof = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+    prof2 = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.generate_configs_dev(synthetic.SEED_CONFIGS, 0, N, d_q.data_ptr())
+    eng.distance_dev(d_q.data_ptr(), N, robots.DIST_MIN, out["min"].data_ptr())
+    eng.distance_dev(d_q.data_ptr(), N, robots.DIST_PROFILE, out["prof"].data_ptr(), prof.data_ptr())
+    eng.distance_dev(d_q.data_ptr(), N, robots.DIST_MIN, out["again"].data_ptr())
+    perm = np.random.default_rng(0).permutation(1000)
+    eng.set_obstacles(mn[perm], mx[perm], g[perm], tol[perm])
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    eng.distance_dev(d_q.data_ptr(), N, robots.DIST_PROFILE, out["perm"].data_ptr(), prof2.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out["min"], out["prof"]) and torch.equal(out["min"], out["again"])      # modes agree, idempotent
+    free = out["min"] > 0
+    assert 0.4 < free.float().mean().item() < 0.9
+    assert torch.equal(prof[free].min(dim=1).values, out["min"][free])                        # d_c = min of the profile
+    hit = ~free
+    first = (prof[hit] <= 0).float().argmax(dim=1)
+    cols = torch.arange(6, device="cuda")[None, :]
+    assert (prof[hit][cols > first[:, None]] == 0).all()                                       # early-exit fill
+    # the minimum over obstacles does not depend on their order (collision-free configurations)
+    assert torch.equal(free, out["perm"] > 0)
+    assert torch.equal(prof[free], prof2[free])
+    # verdicts: a configuration whose distance query collides is (outside measure-zero cases) invalid, and vice versa
+    val = torch.empty(N, dtype=torch.uint8, device="cuda")
+    eng.is_valid_dev(d_q.data_ptr(), N, val.data_ptr())
+    torch.cuda.synchronize()
+    assert ((val == 1) != free).float().mean().item() < 1e-3

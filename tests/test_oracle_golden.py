@@ -1,0 +1,133 @@
+"""The CPU oracle against (i) golden vectors produced by the reference's own CollisionAndDistance.cpp, (ii) analytic
+known answers, (iii) an independent brute-force distance, (iv) the reference-authored invariant of
+apps/test_real_vector_space.cpp:46-57."""
+import numpy as np
+import pytest
+
+from conftest import same
+from rpmplv2_b200 import robots, synthetic
+
+
+@pytest.mark.parametrize("tag,thr", [("t4", 1e-4), ("t6", 1e-6)])
+def test_capsule_box_distance_matches_reference_golden(golden, ob, tag, thr):
+    g = golden[f"{tag}_dist"]
+    o = ob.capsule_box_distance(golden[f"{tag}_AB"], golden[f"{tag}_r"], golden[f"{tag}_obs"], thr=thr)
+    assert same(o[:, 0], g[:, 0]).all()                      # distances: bit exact
+    assert (o[:, 1] == g[:, 1]).all()                        # nullptr-ness of the nearest points
+    live = (g[:, 1] == 1) & (g[:, 0] > 0)
+    assert same(o[live, 2:], g[live, 2:]).all()              # nearest points: bit exact where defined
+
+
+@pytest.mark.parametrize("tag,thr", [("t4", 1e-4), ("t6", 1e-6)])
+def test_collision_predicates_match_reference_golden(golden, ob, tag, thr):
+    AB, r, obs = golden[f"{tag}_AB"], golden[f"{tag}_r"], golden[f"{tag}_obs"]
+    assert (ob.capsule_box_collision(AB, r, obs, thr=thr) == golden[f"{tag}_coll"]).all()
+    assert (ob.capsule_rect_collision(AB, r, obs, golden[f"{tag}_face"], thr=thr) == golden[f"{tag}_rect"]).all()
+
+
+def test_segment_primitives_match_reference_golden(golden, ob):
+    assert same(ob.seg_seg(golden["ss_ABCD"]), golden["ss_out"]).all()
+    assert same(ob.seg_point(golden["sp_ABC"]), golden["sp_out"]).all()
+
+
+def test_hand_checkable_capsule_box_kats(ob):
+    """Unit box, r = 0.1."""
+    AB = np.array([[-1, .5, .5, -.5, .5, .5], [-1, -1, .5, -1, -1, .6], [-1, -1, -1, -2, -2, -2], [.5, .5, .5, 2, 2, 2]], np.float32)
+    out = ob.capsule_box_distance(AB, 0.1, np.tile(np.array([[0, 0, 0, 1, 1, 1]], np.float32), (4, 1)))
+    np.testing.assert_allclose(out[:3, 0], [0.4, np.sqrt(2) - 0.1, np.sqrt(3) - 0.1], rtol=0, atol=2e-7)
+    assert out[3, 0] == 0.0 and out[3, 1] == 0.0             # endpoint inside -> exactly 0, null points (Q11)
+    np.testing.assert_allclose(out[0, 2:], [-.5, .5, .5, 0, .5, .5], atol=1e-7)
+
+
+def test_brute_force_distance_bound(ob):
+    """Oracle distance vs dense sampling of the segment against the closed-form point-AABB distance."""
+    rng = np.random.default_rng(5)
+    K = 400
+    c = rng.uniform(-1, 1, (K, 3)); h = rng.uniform(0.05, 0.6, (K, 3)) / 2
+    obs = np.concatenate([c - h, c + h], 1).astype(np.float32)
+    A = rng.uniform(-1.5, 1.5, (K, 3)); B = A + rng.normal(size=(K, 3)) * 0.4
+    AB = np.concatenate([A, B], 1).astype(np.float32)
+    d = ob.capsule_box_distance(AB, 0.0, obs)[:, 0].astype(np.float64)
+    t = np.linspace(0, 1, 4001)[None, :, None]
+    P = AB[:, None, :3] + t * (AB[:, None, 3:] - AB[:, None, :3])
+    gap = np.maximum(np.maximum(obs[:, None, :3] - P, P - obs[:, None, 3:]), 0.0)
+    brute = np.sqrt((gap ** 2).sum(-1)).min(1)
+    free = brute > 1e-3
+    assert free.sum() > 100
+    # sampling can only over-estimate by <= |AB| / 8000; the oracle must never be larger than the sampled distance
+    seglen = np.linalg.norm(AB[:, 3:] - AB[:, :3], axis=1)
+    assert (d[free] <= brute[free] + 1e-5).all()
+    assert (d[free] >= brute[free] - seglen[free] / 8000 - 1e-5).all()
+    assert (d[~free & (brute == 0)] <= 0).all()
+
+
+def test_forward_kinematics_known_answers(ob):
+    x = ob.Oracle(robots.xarm6())
+    sk = x.skeleton(np.zeros((1, 6), np.float32))[0]
+    expect = np.array([[0, 0, 0], [0, 0, .267], [.0535, 0, .5515], [.131, 0, .459], [.131, 0, .209], [.207, 0, .209], [.207, 0, -.007]])
+    np.testing.assert_allclose(sk, expect, atol=5e-6)        # 1.5708 != pi/2 -> ~4e-6
+    phi = 0.7
+    sk2 = x.skeleton(np.array([[phi, 0, 0, 0, 0, 0]], np.float32))[0]
+    rot = np.array([[np.cos(phi), -np.sin(phi), 0], [np.sin(phi), np.cos(phi), 0], [0, 0, 1]])
+    np.testing.assert_allclose(sk2, sk @ rot.T, atol=1e-6)   # joint 1 rotates everything about z
+    p = ob.Oracle(robots.planar(2))
+    q1, q2 = 0.3, -1.1
+    sp = p.skeleton(np.array([[q1, q2]], np.float32))[0]
+    np.testing.assert_allclose(sp, [[0, 0, 0], [np.cos(q1), np.sin(q1), 0], [np.cos(q1) + np.cos(q1 + q2), np.sin(q1) + np.sin(q1 + q2), 0]], atol=2e-7)
+    s = ob.Oracle(robots.spatial(10))
+    ss = s.skeleton(np.zeros((1, 10), np.float32))[0]
+    np.testing.assert_allclose(ss[:, 2], np.arange(11) * 0.1, atol=1e-7)
+
+
+def test_fk_matches_scipy(ob):
+    from scipy.spatial.transform import Rotation as Rot
+    rb = robots.xarm6()
+    q = synthetic.configs(rb, 50)
+    sk = ob.Oracle(rb).skeleton(q, f64=True)
+    for i in range(len(q)):
+        R, p, frames = np.eye(3), np.zeros(3), []
+        for k in range(6):
+            p = p + R @ rb.xyz[k]
+            R = R @ Rot.from_euler("xyz", rb.rpy[k]).as_matrix() @ Rot.from_rotvec(rb.axis[k] * float(q[i, k])).as_matrix()
+            frames.append((R.copy(), p.copy()))
+        g = rb.gripper_length
+        expect = [np.zeros(3), frames[1][1], frames[2][1], frames[3][1] - 0.25 * frames[3][0][:, 2], frames[4][1],
+                  frames[4][1] + 0.076 * frames[4][0][:, 0], frames[5][1] + g * frames[5][0][:, 2] - 0.3 * g * frames[5][0][:, 2]]
+        np.testing.assert_allclose(sk[i], np.array(expect), atol=2e-8)
+
+
+def test_underestimation_equals_distance_at_the_generating_configuration(ob):
+    """apps/test_real_vector_space.cpp:46-57: |d_c - d_c_under(own planes)| <= 1e-3 for collision-free q."""
+    rb = robots.xarm6()
+    o = ob.Oracle(rb)
+    mn, mx, g, tol = synthetic.sweep_obstacles(12, "D2")
+    tol[:] = 1000.0                                           # no min_dist_tol clipping in this check
+    o.set_obstacles(mn, mx, g, tol)
+    q = synthetic.configs(rb, 300)
+    d, prof, near = o.distance(q, robots.DIST_FULL)
+    free = d > 0
+    assert free.sum() > 20
+    idx = np.flatnonzero(free)
+    du, pu, st = o.underestimation(q[idx], near[idx], np.arange(len(idx), dtype=np.int32))
+    assert (st == 0).all()
+    assert np.abs(du - d[idx]).max() <= 1e-3
+    assert np.abs(pu - prof[idx]).max() <= 1e-3
+
+
+def test_distance_early_exit_fill_and_ground_rule(ob):
+    rb = robots.xarm6()
+    o = ob.Oracle(rb)
+    mn, mx, g, tol = synthetic.sweep_obstacles(30, "D2")
+    o.set_obstacles(mn, mx, g, tol)
+    q = synthetic.configs(rb, 500)
+    d, prof, _ = o.distance(q, robots.DIST_PROFILE)
+    hit = d == 0
+    assert hit.any() and (~hit).any()
+    for i in np.flatnonzero(hit)[:50]:
+        first = np.flatnonzero(prof[i] <= 0)[0]
+        assert (prof[i, first + 1:] == 0).all() and (prof[i, :first] > 0).all()
+    assert np.allclose(d[~hit], prof[~hit].min(1))
+    # links 0 and 1 never see the ground (ground_included = 2): with only the ground present their profile is MAX_DISTANCE
+    o.set_obstacles(mn[:1], mx[:1], g[:1], tol[:1])
+    _, p2, _ = o.distance(q[:20], robots.DIST_PROFILE)
+    assert (p2[:, :2] == 1000.0).all()
