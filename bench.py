@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="ref32", choices=["ref32", "fast32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cull", action="store_true", help="sequential one-thread-per-configuration kernel (no broad phase)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -165,6 +166,7 @@ def main():
     rb, mn, mx, g, tol = scene()
     eng = engine.Engine(rb, robots.default_params(prec), device=local)
     eng.set_obstacles(mn, mx, g, tol)
+    eng.set_culling(not args.no_cull)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     n, L = rb.num_dofs, rb.num_links

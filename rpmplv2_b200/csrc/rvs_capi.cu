@@ -38,7 +38,7 @@ struct rvs_engine {
     LaunchTable lt{};
     DevBuf buf[8];            // grow-only device staging for the host-pointer entry points
     int64_t launches = 0;
-    int cull = 0;
+    int cull = 1;
     int num_ground = 0;
     unsigned long long *d_pair_count = nullptr;
     std::string err;

@@ -12,11 +12,16 @@ namespace rvs {
 __device__ __forceinline__ void sincos_of(double a, double *s, double *c) { sincos(a, s, c); }
 __device__ __forceinline__ void sincos_of(float a, float *s, float *c) { sincosf(a, s, c); }
 
-// Streams the chain and writes the skeleton (n+1 points) as R.  F is the FK scalar.
+// Streams the chain and writes the skeleton (n+1 points) as R.  F is the FK scalar.  Component c of point k goes to
+// sk[(3k + c) * stride] (stride 1: a private array; stride = block size: a shared-memory column per thread).
 // Reference semantics: KDL tree FK (T_k = T_{k-1} Trans(xyz_k) RPY(rpy_k) Rot(axis_k, q_k)) and
 // computeSkeleton (xArm6.cpp:209-235, Planar2DOF.cpp:117-130).
 template <class F, class R>
-__device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, const float *__restrict__ q, R *sk) {
+__device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, const float *__restrict__ q, R *sk_base, const int stride = 1) {
+    struct Strided {
+        R *p; int s;
+        __device__ __forceinline__ R &operator[](int k) const { return p[k * s]; }
+    } sk = {sk_base, stride};
     const int n = rb->n;
     const bool xarm = rb->kind == RVS_ROBOT_XARM6;
     F r00 = 1, r01 = 0, r02 = 0, r10 = 0, r11 = 1, r12 = 0, r20 = 0, r21 = 0, r22 = 1;

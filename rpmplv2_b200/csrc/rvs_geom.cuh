@@ -165,12 +165,41 @@ __device__ __forceinline__ unsigned ring_codes(int c, int side) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// CapsuleToBox::compute (CollisionAndDistance.cpp:409-755): distance from the capsule to the box, radius already
-// subtracted; exactly 0 when an endpoint lies inside the box (Q11); -radius on the snap/crossing paths (Q14).
+// CapsuleToBox::compute (CollisionAndDistance.cpp:409-755), split in two so that the work-queue kernel can run the
+// two halves in separately compacted phases:
+//   classify_pair()  stage 1 (endpoint projections) + the case selection of stage 2: everything except the
+//                    segment-edge evaluations.  It either finishes the pair (`done`, `d` = final distance) or
+//                    leaves `d` = the best candidate so far (face distance or max_dist, radius NOT yet subtracted)
+//                    plus the list of box edges the reference would feed to distanceLineSegToLineSeg;
+//   seg_edge()       one such evaluation.
+// capsule_box_distance() below is the sequential composition (used by FULL mode, the primitives and the replay of
+// a colliding pair).
 // ---------------------------------------------------------------------------------------------------------------
+template <class R>
+struct PairPlan {
+    R d;              // done: final pair distance (radius subtracted; exactly 0 when an endpoint is inside, Q11)
+    unsigned list;    // up to 4 edge codes, 6 bits each (ignored when twelve)
+    int count;        // edges to evaluate
+    bool twelve;      // all 12 edges in the reference's order (:746-751)
+    bool done;
+};
+
+// k-th edge code of a plan
+template <class R>
+__device__ __forceinline__ unsigned plan_edge(const PairPlan<R> &pl, int k) {
+    if (!pl.twelve) return (pl.list >> (6 * k)) & 63u;
+    // z_min ring, z_max ring, then the four vertical edges (:746-751)
+    unsigned code = k < 4 ? (ring_codes(2, 0) >> (6 * k)) : (k < 8 ? (ring_codes(2, 1) >> (6 * (k - 4)))
+                    : edge_code(((0x6u >> (k - 8)) & 1u) | (((0xCu >> (k - 8)) & 1u) << 1), 0));
+    if (k >= 8) code |= ((code & 7u) | 4u) << 3;
+    return code & 63u;
+}
+
 template <class R, bool PTS>
-__device__ __forceinline__ R capsule_box_distance(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist, V3<R> &P1, V3<R> &P2) {
+__device__ __forceinline__ PairPlan<R> classify_pair(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist, V3<R> &P1, V3<R> &P2) {
     const V3<R> &A = cp.A, &B = cp.B;
+    PairPlan<R> pl;
+    pl.list = 0; pl.count = 0; pl.twelve = false; pl.done = true; pl.d = R(0);
     // --- stage 1: endpoint classification (projectionLineSegOnSide x3, :451-475)
     const bool ainx = A.x >= bx.lo.x && A.x <= bx.hi.x, ainy = A.y >= bx.lo.y && A.y <= bx.hi.y, ainz = A.z >= bx.lo.z && A.z <= bx.hi.z;
     const bool binx = B.x >= bx.lo.x && B.x <= bx.hi.x, biny = B.y >= bx.lo.y && B.y <= bx.hi.y, binz = B.z >= bx.lo.z && B.z <= bx.hi.z;
@@ -192,17 +221,12 @@ __device__ __forceinline__ R capsule_box_distance(const Capsule<R> &cp, const Bo
     RVS_PROJECT(1, ainx && ainz, binx && binz, bx.lo.y, bx.hi.y, A.y, B.y)
     RVS_PROJECT(2, ainx && ainy, binx && biny, bx.lo.z, bx.hi.z, A.z, B.z)
 #undef RVS_PROJECT
-    if (inside) return R(0);
-
-    R d = max_dist;
-    unsigned list = 0;        // up to 4 edge codes, 6 bits each
-    int count = 0;
-    bool twelve = false;
+    if (inside) return pl;                                              // exactly 0 (Q11)
 
     if ((mA | mB) != 0u) {
         // --- stage 2a: some endpoint projects onto a face (:420-443)
         const bool useB = !(dA < dB);
-        d = dB < dA ? dB : dA;
+        pl.d = dB < dA ? dB : dA;
         const unsigned m = useB ? mB : mA;
         const V3<R> &Pn = useB ? B : A;
         if (PTS) {
@@ -214,58 +238,69 @@ __device__ __forceinline__ R capsule_box_distance(const Capsule<R> &cp, const Bo
         if ((mA & mB) == 0u) {
             // checkEdges (:477-574): first face in the order x_min, x_max, y_min, y_max, z_min, z_max
             const int f = (m & 1u) ? 0 : (m & 8u) ? 3 : (m & 2u) ? 1 : (m & 16u) ? 4 : (m & 4u) ? 2 : 5;
-            if (segment_crosses_face(cp, bx, f, max_dist)) return R(0) - cp.radius;
+            if (segment_crosses_face(cp, bx, f, max_dist)) { pl.d = R(0) - cp.radius; return pl; }
             const int c = f > 2 ? f - 3 : f, a = axis_a(c), b = axis_b(c);
             const V3<R> &Po = useB ? A : B;                         // the endpoint without projection
             const R oa = sel3(Po, a), ob = sel3(Po, b);
             const unsigned s = unsigned(f > 2) << c, ua = 1u << a, ub = 1u << b;
-            if (oa < sel3(bx.lo, a)) { list = edge_code(s, s | ub); count = 1; }
-            else if (oa > sel3(bx.hi, a)) { list = edge_code(s | ua, s | ua | ub); count = 1; }
-            if (ob < sel3(bx.lo, b)) { list |= edge_code(s, s | ua) << (6 * count); count++; }
-            else if (ob > sel3(bx.hi, b)) { list |= edge_code(s | ub, s | ub | ua) << (6 * count); count++; }
+            if (oa < sel3(bx.lo, a)) { pl.list = edge_code(s, s | ub); pl.count = 1; }
+            else if (oa > sel3(bx.hi, a)) { pl.list = edge_code(s | ua, s | ua | ub); pl.count = 1; }
+            if (ob < sel3(bx.lo, b)) { pl.list |= edge_code(s, s | ua) << (6 * pl.count); pl.count++; }
+            else if (ob > sel3(bx.hi, b)) { pl.list |= edge_code(s | ub, s | ub | ua) << (6 * pl.count); pl.count++; }
         }
-    } else {
-        // --- stage 2b: no projection (checkOtherCases, :597-755)
-        const int cx = (A.x < bx.lo.x && B.x < bx.lo.x) ? 0 : ((A.x > bx.hi.x && B.x > bx.hi.x) ? 1 : 2);
-        const int cy = (A.y < bx.lo.y && B.y < bx.lo.y) ? 0 : ((A.y > bx.hi.y && B.y > bx.hi.y) ? 1 : 2);
-        const int cz = (A.z < bx.lo.z && B.z < bx.lo.z) ? 0 : ((A.z > bx.hi.z && B.z > bx.hi.z) ? 1 : 2);
-        const int mixed = (cx == 2) + (cy == 2) + (cz == 2);
-        const unsigned base = unsigned(cx == 1) | (unsigned(cy == 1) << 1) | (unsigned(cz == 1) << 2);
-        if (mixed == 0) {
-            d = seg_point<R, PTS>(cp, bx.corner(int(base)), eq_thr, P1, P2);
-            return d - cp.radius;
-        } else if (mixed == 1) {
-            const unsigned um = cx == 2 ? 1u : (cy == 2 ? 2u : 4u);
-            list = edge_code(base, base | um); count = 1;
-        } else if (mixed == 2) {
-            const int c = cx != 2 ? 0 : (cy != 2 ? 1 : 2);
-            list = ring_codes(c, int((base >> c) & 1u)); count = 4;
-        } else {
-            bool crossing = false;
-#pragma unroll 1
-            for (int f = 0; f < 6; f++) crossing = crossing || segment_crosses_face(cp, bx, f, max_dist);
-            if (crossing) return R(0) - cp.radius;
-            twelve = true; count = 12;
-        }
+        if (pl.count == 0) { pl.d = pl.d - cp.radius; return pl; }
+        pl.done = false;
+        return pl;
     }
+    // --- stage 2b: no projection (checkOtherCases, :597-755)
+    const int cx = (A.x < bx.lo.x && B.x < bx.lo.x) ? 0 : ((A.x > bx.hi.x && B.x > bx.hi.x) ? 1 : 2);
+    const int cy = (A.y < bx.lo.y && B.y < bx.lo.y) ? 0 : ((A.y > bx.hi.y && B.y > bx.hi.y) ? 1 : 2);
+    const int cz = (A.z < bx.lo.z && B.z < bx.lo.z) ? 0 : ((A.z > bx.hi.z && B.z > bx.hi.z) ? 1 : 2);
+    const int mixed = (cx == 2) + (cy == 2) + (cz == 2);
+    const unsigned base = unsigned(cx == 1) | (unsigned(cy == 1) << 1) | (unsigned(cz == 1) << 2);
+    pl.d = max_dist;
+    if (mixed == 0) {
+        pl.d = seg_point<R, PTS>(cp, bx.corner(int(base)), eq_thr, P1, P2) - cp.radius;
+        return pl;
+    } else if (mixed == 1) {
+        const unsigned um = cx == 2 ? 1u : (cy == 2 ? 2u : 4u);
+        pl.list = edge_code(base, base | um); pl.count = 1;
+    } else if (mixed == 2) {
+        const int c = cx != 2 ? 0 : (cy != 2 ? 1 : 2);
+        pl.list = ring_codes(c, int((base >> c) & 1u)); pl.count = 4;
+    } else {
+        bool crossing = false;
+#pragma unroll 1
+        for (int f = 0; f < 6; f++) crossing = crossing || segment_crosses_face(cp, bx, f, max_dist);
+        if (crossing) { pl.d = R(0) - cp.radius; return pl; }
+        pl.twelve = true; pl.count = 12;
+    }
+    pl.done = false;
+    return pl;
+}
 
+// one planned edge: decode the 6-bit code and evaluate distanceLineSegToLineSeg against it
+template <class R, bool PTS>
+__device__ __forceinline__ R plan_edge_distance(const Capsule<R> &cp, const Box<R> &bx, unsigned code, R eq_thr, R max_dist, V3<R> &q1, V3<R> &q2) {
+    const unsigned cc = code & 7u, dc = (code >> 3) & 7u;
+    const int e = __ffs(int(cc ^ dc)) - 1;
+    const V3<R> C = bx.corner(int(cc));
+    const R De = ((dc >> e) & 1u) ? sel3(bx.hi, e) : sel3(bx.lo, e);
+    return seg_edge<R, PTS>(cp, C, e, De, eq_thr, max_dist, q1, q2);
+}
+
+// distance from the capsule to the box, radius already subtracted; exactly 0 when an endpoint lies inside the box
+// (Q11); -radius on the snap/crossing paths (Q14).
+template <class R, bool PTS>
+__device__ __forceinline__ R capsule_box_distance(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist, V3<R> &P1, V3<R> &P2) {
+    const PairPlan<R> pl = classify_pair<R, PTS>(cp, bx, eq_thr, max_dist, P1, P2);
+    if (pl.done) return pl.d;
+    R d = pl.d;
     // --- uniform edge loop (distanceToMoreLineSegments, :576-595)
 #pragma unroll 1
-    for (int k = 0; k < count; k++) {
-        unsigned code;
-        if (twelve) {
-            // z_min ring, z_max ring, then the four vertical edges (:746-751)
-            code = k < 4 ? (ring_codes(2, 0) >> (6 * k)) : (k < 8 ? (ring_codes(2, 1) >> (6 * (k - 4)))
-                   : edge_code(((0x6u >> (k - 8)) & 1u) | (((0xCu >> (k - 8)) & 1u) << 1), 0));
-            if (k >= 8) code |= ((code & 7u) | 4u) << 3;
-        } else
-            code = list >> (6 * k);
-        const unsigned cc = code & 7u, dc = (code >> 3) & 7u;
-        const int e = __ffs(int(cc ^ dc)) - 1;
-        const V3<R> C = bx.corner(int(cc));
-        const R De = ((dc >> e) & 1u) ? sel3(bx.hi, e) : sel3(bx.lo, e);
+    for (int k = 0; k < pl.count; k++) {
         V3<R> q1, q2;
-        const R de = seg_edge<R, PTS>(cp, C, e, De, eq_thr, max_dist, q1, q2);
+        const R de = plan_edge_distance<R, PTS>(cp, bx, plan_edge(pl, k), eq_thr, max_dist, q1, q2);
         if (de <= R(0)) return R(0) - cp.radius;
         if (de < d) { d = de; if (PTS) { P1 = q1; P2 = q2; } }
     }

@@ -3,6 +3,7 @@
 //   -DRVS_VARIANT_EXACT  -fmad=false -prec-div=true -prec-sqrt=true -ftz=false   -> REF32 and F64 launch tables
 //   -DRVS_VARIANT_FAST   -fmad=true                                             -> FAST32 launch table
 #include "rvs_kernels.cuh"
+#include "rvs_distance_wq.cuh"
 #include "rvs_launch.h"
 
 namespace rvs {
@@ -12,8 +13,27 @@ inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1)
 
 template <class F, class R>
 struct Variant {
+    template <int MODE, int G>
+    static cudaError_t distance_wq(const KArgs &a, cudaStream_t st) {
+        const int tile_cap = a.M < kWqTile ? (a.M > 0 ? a.M : 1) : kWqTile;
+        const size_t smem = wq_smem_bytes<R, G>(a.robot_n_hint, tile_cap);
+        static size_t configured = 0;                     // per instantiation: raise the dynamic shared-memory limit once
+        if (smem > configured) {
+            const cudaError_t e = cudaFuncSetAttribute(distance_wq_kernel<F, R, MODE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        distance_wq_kernel<F, R, MODE, G><<<grid_for(a.N, kWqBlock), kWqBlock, smem, st>>>(a, tile_cap);
+        return cudaGetLastError();
+    }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (a.cull && a.mode != RVS_DIST_FULL && a.M > 0) {
+            // work-queue kernel (rvs_distance_wq.cuh): results identical to the sequential kernel below
+            const bool narrow = a.robot_n_hint <= 2;
+            if (a.mode == RVS_DIST_MIN) return narrow ? distance_wq<RVS_DIST_MIN, 2>(a, st) : distance_wq<RVS_DIST_MIN, 6>(a, st);
+            return narrow ? distance_wq<RVS_DIST_PROFILE, 2>(a, st) : distance_wq<RVS_DIST_PROFILE, 6>(a, st);
+        }
         const unsigned g = grid_for(a.N, kBlock);
         if (a.mode == RVS_DIST_MIN) distance_kernel<F, R, RVS_DIST_MIN><<<g, kBlock, 0, st>>>(a);
         else if (a.mode == RVS_DIST_PROFILE) distance_kernel<F, R, RVS_DIST_PROFILE><<<g, kBlock, 0, st>>>(a);

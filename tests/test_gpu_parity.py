@@ -83,6 +83,44 @@ def test_distance_ref32_vs_oracle(ob, M, dist, r_min):
     assert eng.pair_count(reset=True) == 2 * o.pair_count(reset=True)  # two GPU calls vs one oracle call
 
 
+@pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32, robots.PREC_F64])
+@pytest.mark.parametrize("case", ["xarm6_1000", "xarm6_2500_two_tiles", "xarm6_dense", "spatial22", "planar2", "tol_and_thr"])
+def test_work_queue_kernel_is_bit_identical_to_sequential_kernel(case, prec):
+    """The scan -> work-queue -> compacted-phase kernel (rvs_distance_wq.cuh, the default for MIN/PROFILE) against the
+    one-thread-per-configuration kernel (rvs_set_culling(0)): d_c, the whole profile (including the early-exit fill after a
+    collision) and the reference-order pair count must be identical BIT FOR BIT, whatever order the queues were served in."""
+    thr = 1e-4
+    if case == "xarm6_1000":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(1000, "D2", 0.9)
+    elif case == "xarm6_2500_two_tiles":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(2500, "D1", 0.6)
+    elif case == "xarm6_dense":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(300, "D2", 0.0)           # most configurations collide
+    elif case == "spatial22":
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 40)
+    elif case == "planar2":
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    else:
+        rb, mn, mx, g, tol = scenes.xarm6_scene(200, "D2", 0.5)
+        tol = np.random.default_rng(5).choice(np.array([0.02, 0.1, 0.4, 1000.0], np.float32), len(tol)).astype(np.float32)
+        thr = 0.05                                                         # a large EQUALITY_THRESHOLD: snaps far from contact
+    q = synthetic.configs(rb, 40000 if prec != robots.PREC_F64 else 15000)
+    eng = make(rb, mn, mx, g, tol, prec, thr)
+    for mode in (robots.DIST_PROFILE, robots.DIST_MIN):
+        eng.set_culling(True)
+        eng.pair_count(reset=True)
+        d1, p1, _ = eng.distance(q, mode)
+        n1 = eng.pair_count(reset=True)
+        eng.set_culling(False)
+        d0, p0, _ = eng.distance(q, mode)
+        n0 = eng.pair_count(reset=True)
+        assert case in ("planar2", "xarm6_dense") or 0.0 < (d0 > 0).mean() < 1.0
+        assert (d1.view(np.uint8) == d0.view(np.uint8)).all()
+        if mode == robots.DIST_PROFILE:
+            assert (p1.view(np.uint8) == p0.view(np.uint8)).all()
+        assert n1 == n0
+
+
 def test_distance_full_nearest_points(ob):
     rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D1", 0.3)
     q = synthetic.configs(rb, 3000)
