@@ -1,5 +1,5 @@
 set -u
-OUT=gpurun_out/r1b; mkdir -p $OUT
+OUT=gpurun_out/${1:-quick}; mkdir -p $OUT
 timeout 1200 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -25 $OUT/pytest_gpu.log
 timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $OUT/bench_ref32.json 2> $OUT/bench_ref32.err; echo "bench rc=$?"; tail -c 600 $OUT/bench_ref32.err
 python -c "

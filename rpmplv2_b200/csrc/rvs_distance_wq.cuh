@@ -40,6 +40,8 @@ namespace rvs {
 
 constexpr int kWqBlock = 128;
 constexpr int kWqWarps = kWqBlock / 32;
+constexpr int kWqStride = kWqBlock + 1;           // row pitch of the per-thread shared arrays: row r of thread t sits in bank (r + t) % 32, so
+                                                  // popped work items of ONE configuration (same t, different links) do not collide
 constexpr int kWqTile = 1024;                     // obstacles per shared-memory tile (32 B each)
 constexpr int kWqChunk = 32;                      // obstacles scanned between two refreshes of the inflated link boxes
 constexpr unsigned kNoHit = 0xFFFFFFFFu;
@@ -66,8 +68,8 @@ template <> struct WqBits<double> {
 template <class R, int G>
 __host__ __device__ inline size_t wq_smem_bytes(int L, int T) {
     size_t b = size_t(T) * sizeof(ObstacleRec);
-    b += size_t(3 * (L + 1)) * kWqBlock * sizeof(R);                       // skeleton
-    b += size_t(L) * kWqBlock * sizeof(typename WqBits<R>::type);         // per-link minima
+    b += size_t(3 * (L + 1)) * kWqStride * sizeof(R);                       // skeleton
+    b += size_t(L) * kWqStride * sizeof(typename WqBits<R>::type);         // per-link minima
     b += size_t(L) * sizeof(R);                                           // radii
     b = (b + 15) & ~size_t(15);
     b += size_t(kWqBlock) * sizeof(unsigned);                             // first-collision keys
@@ -78,8 +80,8 @@ __host__ __device__ inline size_t wq_smem_bytes(int L, int T) {
 template <class R>
 struct WqShared {
     ObstacleRec *tile;
-    R *skel;                                  // [3*(L+1)][kWqBlock]
-    typename WqBits<R>::type *best;           // [L][kWqBlock]
+    R *skel;                                  // [3*(L+1)][kWqStride]
+    typename WqBits<R>::type *best;           // [L][kWqStride]
     R *radius;                                // [L]
     unsigned *hit;                            // [kWqBlock]
     volatile unsigned *tails;                 // this warp: [0] = Q1 tail, [1] = Q2 tail
@@ -105,13 +107,13 @@ template <class R>
 __device__ __forceinline__ void wq_merge(const WqCtx<R> &c, int t, int link, unsigned key, R d, R tol) {
     if (d > tol) return;                                                   // min_dist_tol: contributes MAX_DISTANCE (:367-368)
     if (d <= R(0)) atomicMin(&c.s.hit[t], key);                            // a collision of this pair (:370)
-    else if (d > R(0)) atomicMin(&c.s.best[link * kWqBlock + t], WqBits<R>::to(d));
+    else if (d > R(0)) atomicMin(&c.s.best[link * kWqStride + t], WqBits<R>::to(d));
 }
 
 template <class R>
 __device__ __forceinline__ void wq_load_pair(const WqCtx<R> &c, int t, int link, int jt, Capsule<R> &cp, Box<R> &bx, R &tol) {
-    const R *sk = c.s.skel + (3 * link) * kWqBlock + t;
-    const V3<R> A = {sk[0], sk[kWqBlock], sk[2 * kWqBlock]}, B = {sk[3 * kWqBlock], sk[4 * kWqBlock], sk[5 * kWqBlock]};
+    const R *sk = c.s.skel + (3 * link) * kWqStride + t;
+    const V3<R> A = {sk[0], sk[kWqStride], sk[2 * kWqStride]}, B = {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]};
     cp.set(A, B, c.s.radius[link], R(0));
     const float4 *t4 = reinterpret_cast<const float4 *>(c.s.tile) + 2 * jt;
     const float4 w0 = t4[0], w1 = t4[1];
@@ -128,7 +130,7 @@ __device__ __forceinline__ void wq_classify(const WqCtx<R> &c, unsigned e) {
     Capsule<R> cp; Box<R> bx; R tol;
     wq_load_pair(c, t, link, jt, cp, bx, tol);
     // Euclidean gap between the segment's bounding box and the obstacle, against the current minimum
-    const R thr = wq_threshold(WqBits<R>::from(c.s.best[link * kWqBlock + t]), cp.radius, c.eq_thr);
+    const R thr = wq_threshold(WqBits<R>::from(c.s.best[link * kWqStride + t]), cp.radius, c.eq_thr);
     const R lox = cp.A.x < cp.B.x ? cp.A.x : cp.B.x, hix = cp.A.x < cp.B.x ? cp.B.x : cp.A.x;
     const R loy = cp.A.y < cp.B.y ? cp.A.y : cp.B.y, hiy = cp.A.y < cp.B.y ? cp.B.y : cp.A.y;
     const R loz = cp.A.z < cp.B.z ? cp.A.z : cp.B.z, hiz = cp.A.z < cp.B.z ? cp.B.z : cp.A.z;
@@ -196,8 +198,8 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     {
         unsigned char *p = wq_smem;
         c.s.tile = reinterpret_cast<ObstacleRec *>(p); p += size_t(tile_cap) * sizeof(ObstacleRec);
-        c.s.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqBlock * sizeof(R);
-        c.s.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqBlock * sizeof(Bits);
+        c.s.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
+        c.s.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqStride * sizeof(Bits);
         c.s.radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
         p = wq_smem + ((size_t(p - wq_smem) + 15) & ~size_t(15));
         c.s.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
@@ -210,9 +212,9 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     const int64_t cfg = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
     const bool live = cfg < a.N;
     const int t = threadIdx.x;
-    if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.s.skel + t, kWqBlock);
-    else for (int k = 0; k < 3 * (L + 1); k++) c.s.skel[k * kWqBlock + t] = R(0);
-    for (int i = 0; i < L; i++) c.s.best[i * kWqBlock + t] = WqBits<R>::to(c.max_dist);
+    if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.s.skel + t, kWqStride);
+    else for (int k = 0; k < 3 * (L + 1); k++) c.s.skel[k * kWqStride + t] = R(0);
+    for (int i = 0; i < L; i++) c.s.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
     c.s.hit[t] = kNoHit;
     if (t < L) c.s.radius[t] = RobotScalars<R>::radius(rb, t);
     if (lane == 0) { c.s.tails[0] = 0; c.s.tails[1] = 0; }
@@ -239,11 +241,11 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
                 for (int l = 0; l < G; l++) {
                     const int i = g0 + l;
                     if (i < limit && i < L) {
-                        const R *sk = c.s.skel + (3 * i) * kWqBlock + t;
-                        const R thr = wq_threshold(WqBits<R>::from(c.s.best[i * kWqBlock + t]), c.s.radius[i], c.eq_thr);
+                        const R *sk = c.s.skel + (3 * i) * kWqStride + t;
+                        const R thr = wq_threshold(WqBits<R>::from(c.s.best[i * kWqStride + t]), c.s.radius[i], c.eq_thr);
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
-                            const R p = sk[k * kWqBlock], q = sk[(3 + k) * kWqBlock];
+                            const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
                             lo[l][k] = (p < q ? p : q) - thr;
                             hi[l][k] = (p < q ? q : p) + thr;
                         }
@@ -290,8 +292,8 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     if (collided) {
         // the value the reference stores for the colliding link: replay exactly that pair sequentially
         Capsule<R> cp;
-        const R *sk = c.s.skel + (3 * limit) * kWqBlock + t;
-        cp.set({sk[0], sk[kWqBlock], sk[2 * kWqBlock]}, {sk[3 * kWqBlock], sk[4 * kWqBlock], sk[5 * kWqBlock]}, c.s.radius[limit], R(0));
+        const R *sk = c.s.skel + (3 * limit) * kWqStride + t;
+        cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, c.s.radius[limit], R(0));
         V3<R> u, v;
         hit_d = capsule_box_distance<R, false>(cp, load_box<R>(a.obstacles[hit_j]), c.eq_thr, c.max_dist, u, v);
     }
@@ -312,12 +314,12 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     }
     if (!live) return;
     R d_c = c.max_dist;
-    for (int i = 0; i < L; i++) { const R b = WqBits<R>::from(c.s.best[i * kWqBlock + t]); if (b < d_c) d_c = b; }
+    for (int i = 0; i < L; i++) { const R b = WqBits<R>::from(c.s.best[i * kWqStride + t]); if (b < d_c) d_c = b; }
     static_cast<R *>(a.d_c)[cfg] = collided ? R(0) : d_c;
     if (MODE >= RVS_DIST_PROFILE) {
         R *out = static_cast<R *>(a.profile) + cfg * L;
         for (int i = 0; i < L; i++) {
-            const R b = WqBits<R>::from(c.s.best[i * kWqBlock + t]);
+            const R b = WqBits<R>::from(c.s.best[i * kWqStride + t]);
             out[i] = !collided ? b : (i < limit ? b : (i == limit ? hit_d : R(0)));
         }
     }
