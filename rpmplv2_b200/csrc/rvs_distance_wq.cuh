@@ -6,17 +6,17 @@
 // (link, obstacle) pair although ~97 % of the pairs cannot change the per-link minimum.
 //
 // How (one warp = 32 configurations, lane = configuration during the scan, lane = work item afterwards):
-//   phase A  scan      each lane tests every obstacle of the shared-memory tile against its links' axis-aligned
-//                      bounding boxes inflated by (running minimum + radius): 6 compares per pair, no divergence.
-//                      Survivors are appended to the warp's pair queue Q1 in shared memory.
-//   phase B  classify  whenever Q1 holds >= 32 pairs, every lane pops ONE pair (of any configuration of the warp),
-//                      re-tests it against the now tighter minimum with the Euclidean box gap, and runs the
-//                      reference's endpoint-projection / region classification (classify_pair).  Immediate results
-//                      are merged; the box edges the reference would hand to distanceLineSegToLineSeg are appended
-//                      to the edge queue Q2.
-//   phase C  edges     whenever Q2 holds >= 32 edges, every lane pops ONE edge and evaluates seg_edge().
-// All three phases run with (nearly) full warps.  Results are merged with shared-memory atomicMin on the IEEE bit
-// pattern (distances that reach the minimum are > 0, so integer order == float order).
+//   phase A  scan      each lane tests every obstacle (warp-uniform 16-byte loads of the HBM-resident table, served by
+//                      L1) against its links' axis-aligned bounding boxes inflated by (running minimum + radius):
+//                      6 predicate-chained compares per pair, no divergence.  Survivors go to the pair queue Q1.
+//   phase B1 re-cull   Q1 >= 32: every lane pops ONE pair (of any configuration of the warp) and re-tests it with the
+//                      Euclidean box gap against the now tighter minimum; survivors are ballot-compacted into Q1b.
+//   phase B2 classify  Q1b >= 32: every lane runs the reference's endpoint-projection / region classification
+//                      (classify_pair) for ONE pair.  Immediate results are merged; the box edges the reference would
+//                      hand to distanceLineSegToLineSeg are appended to the edge queue Q2.
+//   phase C  edges     Q2 >= 32: every lane pops ONE edge and evaluates seg_edge().
+// All phases run with (nearly) full warps.  Results are merged with shared-memory atomicMin on the IEEE bit pattern
+// (distances that reach the minimum are > 0, so integer order == float order).
 //
 // Exactness (bit-identical outputs to the sequential kernel / the reference loop, in any processing order):
 //   * culling is conservative: a pair is skipped only if a lower bound of ANY candidate distance the reference
@@ -42,14 +42,17 @@ constexpr int kWqBlock = 128;
 constexpr int kWqWarps = kWqBlock / 32;
 constexpr int kWqStride = kWqBlock + 1;           // row pitch of the per-thread shared arrays: row r of thread t sits in bank (r + t) % 32, so
                                                   // popped work items of ONE configuration (same t, different links) do not collide
-constexpr int kWqTile = 1024;                     // obstacles per shared-memory tile (32 B each)
-constexpr int kWqChunk = 32;                      // obstacles scanned between two refreshes of the inflated link boxes
+constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bit obstacle index: the table is walked in segments of 65536
+constexpr int kWqUnroll = 2;                      // obstacles tested per scan iteration
 constexpr unsigned kNoHit = 0xFFFFFFFFu;
 constexpr unsigned kNoEntry = 0xFFFFFFFFu;
 
+// queue entry: lane (5) | link (5) << 5 | obstacle-in-segment (16) << 10 | edge code (6) << 26
 template <int G> struct WqCaps {
-    static constexpr int q1 = 32 * G + 32;        // one scan iteration can push 32*G pairs on top of a leftover < 32
-    static constexpr int q2 = 32 * 12 + 32;       // one classify round can push 32*12 edges on top of a leftover < 32
+    static constexpr int q1 = 32 * G * kWqUnroll + 32;   // one scan iteration can push 32*G*unroll pairs on top of a leftover < 32
+    static constexpr int q1b = 64;                        // one re-cull round pushes <= 32 on top of a leftover < 32
+    static constexpr int q2 = 32 * 12 + 32;               // one classify round pushes <= 32*12 edges on top of a leftover < 32
+    static constexpr int words = 4 + q1 + q1b + q2;       // 4 tail words first
 };
 
 template <class R> struct WqBits;
@@ -64,34 +67,28 @@ template <> struct WqBits<double> {
     static __device__ __forceinline__ double from(long long b) { return __longlong_as_double(b); }
 };
 
-// bytes of dynamic shared memory for L links, a tile of T obstacles and scan group width G
+// bytes of dynamic shared memory for L links and scan group width G
 template <class R, int G>
-__host__ __device__ inline size_t wq_smem_bytes(int L, int T) {
-    size_t b = size_t(T) * sizeof(ObstacleRec);
-    b += size_t(3 * (L + 1)) * kWqStride * sizeof(R);                       // skeleton
-    b += size_t(L) * kWqStride * sizeof(typename WqBits<R>::type);         // per-link minima
+__host__ __device__ inline size_t wq_smem_bytes(int L) {
+    size_t b = size_t(3 * (L + 1)) * kWqStride * sizeof(R);               // skeleton
+    b += size_t(L) * kWqStride * sizeof(typename WqBits<R>::type);        // per-link minima
     b += size_t(L) * sizeof(R);                                           // radii
     b = (b + 15) & ~size_t(15);
     b += size_t(kWqBlock) * sizeof(unsigned);                             // first-collision keys
-    b += size_t(kWqWarps) * (4 + WqCaps<G>::q1 + WqCaps<G>::q2) * sizeof(unsigned);
+    b += size_t(kWqWarps) * WqCaps<G>::words * sizeof(unsigned);
     return b;
 }
 
 template <class R>
-struct WqShared {
-    ObstacleRec *tile;
+struct WqCtx {
+    const float4 *obs4;                       // obstacle table in HBM as pairs of 16-byte words (read through L1)
     R *skel;                                  // [3*(L+1)][kWqStride]
     typename WqBits<R>::type *best;           // [L][kWqStride]
     R *radius;                                // [L]
     unsigned *hit;                            // [kWqBlock]
-    volatile unsigned *tails;                 // this warp: [0] = Q1 tail, [1] = Q2 tail
-    unsigned *q1, *q2;                        // this warp's queues
-};
-
-template <class R>
-struct WqCtx {
-    WqShared<R> s;
-    int L, M, tile_base, wbase;               // wbase = first thread of this warp in the block
+    volatile unsigned *tails;                 // this warp: [0] Q1, [1] Q1b, [2] Q2
+    unsigned *q1, *q1b, *q2;                  // this warp's queues
+    int M, seg_base, wbase;                   // wbase = first thread of this warp in the block
     R eq_thr, max_dist;
 };
 
@@ -102,84 +99,125 @@ template <class R> __device__ __forceinline__ R wq_threshold(R best, R radius, R
     return (t > eq_thr ? t : eq_thr) * R(1.001) + R(1e-4);
 }
 
+// mask |= bit  iff the obstacle box [o, p] overlaps the inflated link box [lo, hi] (all comparisons false on NaN)
+template <class R>
+__device__ __forceinline__ void wq_overlap(unsigned &mask, unsigned bit, R ox, R oy, R oz, R px, R py, R pz, const R (&lo)[3], const R (&hi)[3]) {
+    const bool ov = ox <= hi[0] && px >= lo[0] && oy <= hi[1] && py >= lo[1] && oz <= hi[2] && pz >= lo[2];
+    mask |= ov ? bit : 0u;
+}
+// FP32: one predicate chain (6 FSETP feeding each other) and a predicated OR — 7 issue slots per pair
+template <>
+__device__ __forceinline__ void wq_overlap<float>(unsigned &mask, unsigned bit, float ox, float oy, float oz, float px, float py, float pz,
+                                                  const float (&lo)[3], const float (&hi)[3]) {
+    asm("{\n\t.reg .pred p;\n\t"
+        "setp.le.f32 p, %1, %7;\n\t"
+        "setp.ge.and.f32 p, %4, %10, p;\n\t"
+        "setp.le.and.f32 p, %2, %8, p;\n\t"
+        "setp.ge.and.f32 p, %5, %11, p;\n\t"
+        "setp.le.and.f32 p, %3, %9, p;\n\t"
+        "setp.ge.and.f32 p, %6, %12, p;\n\t"
+        "@p or.b32 %0, %0, %13;\n\t}"
+        : "+r"(mask)
+        : "f"(ox), "f"(oy), "f"(oz), "f"(px), "f"(py), "f"(pz), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "r"(bit));
+}
+
 // merge one finished candidate distance (radius already subtracted) of pair `key` into configuration slot `t`
 template <class R>
 __device__ __forceinline__ void wq_merge(const WqCtx<R> &c, int t, int link, unsigned key, R d, R tol) {
     if (d > tol) return;                                                   // min_dist_tol: contributes MAX_DISTANCE (:367-368)
-    if (d <= R(0)) atomicMin(&c.s.hit[t], key);                            // a collision of this pair (:370)
-    else if (d > R(0)) atomicMin(&c.s.best[link * kWqStride + t], WqBits<R>::to(d));
+    if (d <= R(0)) atomicMin(&c.hit[t], key);                              // a collision of this pair (:370)
+    else if (d > R(0)) atomicMin(&c.best[link * kWqStride + t], WqBits<R>::to(d));
 }
 
 template <class R>
-__device__ __forceinline__ void wq_load_pair(const WqCtx<R> &c, int t, int link, int jt, Capsule<R> &cp, Box<R> &bx, R &tol) {
-    const R *sk = c.s.skel + (3 * link) * kWqStride + t;
-    const V3<R> A = {sk[0], sk[kWqStride], sk[2 * kWqStride]}, B = {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]};
-    cp.set(A, B, c.s.radius[link], R(0));
-    const float4 *t4 = reinterpret_cast<const float4 *>(c.s.tile) + 2 * jt;
-    const float4 w0 = t4[0], w1 = t4[1];
+__device__ __forceinline__ void wq_load_pair(const WqCtx<R> &c, int t, int link, int j, V3<R> &A, V3<R> &B, Box<R> &bx, R &tol) {
+    const R *sk = c.skel + (3 * link) * kWqStride + t;
+    A = {sk[0], sk[kWqStride], sk[2 * kWqStride]};
+    B = {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]};
+    const float4 w0 = __ldg(c.obs4 + 2 * j), w1 = __ldg(c.obs4 + 2 * j + 1);
     bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
     tol = R(w1.z);
 }
 
-// phase B: one surviving pair
-template <class R, int G>
+#define RVS_WQ_DECODE(e)                                                                                  \
+    const int t = c.wbase + int((e) & 31u), link = int(((e) >> 5) & 31u), j = c.seg_base + int(((e) >> 10) & 0xFFFFu); \
+    const unsigned key = unsigned(link) * unsigned(c.M) + unsigned(j)
+
+// phase B1: does this pair still matter?  Euclidean gap between the segment's bounding box and the obstacle against the
+// CURRENT minimum of its link (the scan used the Chebyshev gap and a possibly older minimum).
+template <class R>
+__device__ __forceinline__ bool wq_recull(const WqCtx<R> &c, unsigned e) {
+    RVS_WQ_DECODE(e);
+    if (key > c.hit[t]) return false;                                      // an earlier pair (reference order) already collides
+    V3<R> A, B; Box<R> bx; R tol;
+    wq_load_pair(c, t, link, j, A, B, bx, tol);
+    const R thr = wq_threshold(WqBits<R>::from(c.best[link * kWqStride + t]), c.radius[link], c.eq_thr);
+    const R gx = fmax(fmax(bx.lo.x - fmax(A.x, B.x), fmin(A.x, B.x) - bx.hi.x), R(0));
+    const R gy = fmax(fmax(bx.lo.y - fmax(A.y, B.y), fmin(A.y, B.y) - bx.hi.y), R(0));
+    const R gz = fmax(fmax(bx.lo.z - fmax(A.z, B.z), fmin(A.z, B.z) - bx.hi.z), R(0));
+    return !(gx * gx + gy * gy + gz * gz > thr * thr);
+}
+
+// phase B2: one surviving pair through the reference's classification
+template <class R>
 __device__ __forceinline__ void wq_classify(const WqCtx<R> &c, unsigned e) {
-    const int t = c.wbase + int(e & 31u), link = int((e >> 5) & 31u), jt = int(e >> 10);
-    const unsigned key = unsigned(link) * unsigned(c.M) + unsigned(c.tile_base + jt);
-    if (key > c.s.hit[t]) return;                                          // an earlier pair (reference order) already collides
-    Capsule<R> cp; Box<R> bx; R tol;
-    wq_load_pair(c, t, link, jt, cp, bx, tol);
-    // Euclidean gap between the segment's bounding box and the obstacle, against the current minimum
-    const R thr = wq_threshold(WqBits<R>::from(c.s.best[link * kWqStride + t]), cp.radius, c.eq_thr);
-    const R lox = cp.A.x < cp.B.x ? cp.A.x : cp.B.x, hix = cp.A.x < cp.B.x ? cp.B.x : cp.A.x;
-    const R loy = cp.A.y < cp.B.y ? cp.A.y : cp.B.y, hiy = cp.A.y < cp.B.y ? cp.B.y : cp.A.y;
-    const R loz = cp.A.z < cp.B.z ? cp.A.z : cp.B.z, hiz = cp.A.z < cp.B.z ? cp.B.z : cp.A.z;
-    const R gx = fmax(fmax(bx.lo.x - hix, lox - bx.hi.x), R(0)), gy = fmax(fmax(bx.lo.y - hiy, loy - bx.hi.y), R(0)),
-            gz = fmax(fmax(bx.lo.z - hiz, loz - bx.hi.z), R(0));
-    if (gx * gx + gy * gy + gz * gz > thr * thr) return;
+    RVS_WQ_DECODE(e);
+    if (key > c.hit[t]) return;
+    V3<R> A, B; Box<R> bx; R tol;
+    wq_load_pair(c, t, link, j, A, B, bx, tol);
+    Capsule<R> cp;
+    cp.set(A, B, c.radius[link], R(0));
     V3<R> u, v;
     const PairPlan<R> pl = classify_pair<R, false>(cp, bx, c.eq_thr, c.max_dist, u, v);
     if (pl.done) { wq_merge(c, t, link, key, pl.d, tol); return; }
     wq_merge(c, t, link, key, pl.d - cp.radius, tol);                      // face distance (2a) or MAX_DISTANCE (2b)
-    const unsigned pos = atomicAdd(const_cast<unsigned *>(&c.s.tails[1]), unsigned(pl.count));
+    const unsigned pos = atomicAdd(const_cast<unsigned *>(&c.tails[2]), unsigned(pl.count));
 #pragma unroll 1
-    for (int k = 0; k < pl.count; k++) c.s.q2[pos + k] = (e & 0xFFFFFu) | (plan_edge(pl, k) << 20);
+    for (int k = 0; k < pl.count; k++) c.q2[pos + k] = (e & 0x3FFFFFFu) | (plan_edge(pl, k) << 26);
 }
 
 // phase C: one box edge of one pair
 template <class R>
 __device__ __forceinline__ void wq_edge(const WqCtx<R> &c, unsigned e) {
-    const int t = c.wbase + int(e & 31u), link = int((e >> 5) & 31u), jt = int((e >> 10) & 1023u);
-    const unsigned key = unsigned(link) * unsigned(c.M) + unsigned(c.tile_base + jt);
-    if (key > c.s.hit[t]) return;
-    Capsule<R> cp; Box<R> bx; R tol;
-    wq_load_pair(c, t, link, jt, cp, bx, tol);
+    RVS_WQ_DECODE(e);
+    if (key > c.hit[t]) return;
+    V3<R> A, B; Box<R> bx; R tol;
+    wq_load_pair(c, t, link, j, A, B, bx, tol);
+    Capsule<R> cp;
+    cp.set(A, B, c.radius[link], R(0));
     V3<R> u, v;
-    const R de = plan_edge_distance<R, false>(cp, bx, e >> 20, c.eq_thr, c.max_dist, u, v);
+    const R de = plan_edge_distance<R, false>(cp, bx, e >> 26, c.eq_thr, c.max_dist, u, v);
     wq_merge(c, t, link, key, de <= R(0) ? R(0) - cp.radius : de - cp.radius, tol);     // Q14: a touching edge gives -radius
 }
 
+// pop up to 32 entries from the top of a queue (warp-uniform); lanes beyond the count get kNoEntry
+__device__ __forceinline__ unsigned wq_pop(volatile unsigned *tail, const unsigned *q, unsigned have, int lane) {
+    const unsigned n = have < 32u ? have : 32u, base = have - n;
+    const unsigned e = unsigned(lane) < n ? q[base + lane] : kNoEntry;
+    __syncwarp();
+    if (lane == 0) *tail = base;
+    return e;
+}
+
 // run compacted phases while a queue holds a full warp of work (or anything at all when flushing)
-template <class R, int G>
+template <class R>
 __device__ __forceinline__ void wq_drain(const WqCtx<R> &c, bool flush) {
     const int lane = threadIdx.x & 31;
     for (;;) {
         __syncwarp();
-        const unsigned t2 = c.s.tails[1], t1 = c.s.tails[0];
-        if (t2 >= 32u || (flush && t2 > 0u && t1 == 0u)) {
-            const unsigned n = t2 < 32u ? t2 : 32u, base = t2 - n;
-            const unsigned e = unsigned(lane) < n ? c.s.q2[base + lane] : kNoEntry;
-            __syncwarp();
-            if (lane == 0) c.s.tails[1] = base;
-            __syncwarp();
+        const unsigned t1 = c.tails[0], t1b = c.tails[1], t2 = c.tails[2];
+        if (t2 >= 32u || (flush && t2 > 0u && t1 == 0u && t1b == 0u)) {
+            const unsigned e = wq_pop(&c.tails[2], c.q2, t2, lane);
             if (e != kNoEntry) wq_edge<R>(c, e);
+        } else if (t1b >= 32u || (flush && t1b > 0u && t1 == 0u)) {
+            const unsigned e = wq_pop(&c.tails[1], c.q1b, t1b, lane);
+            if (e != kNoEntry) wq_classify<R>(c, e);
         } else if (t1 >= 32u || (flush && t1 > 0u)) {
-            const unsigned n = t1 < 32u ? t1 : 32u, base = t1 - n;
-            const unsigned e = unsigned(lane) < n ? c.s.q1[base + lane] : kNoEntry;
-            __syncwarp();
-            if (lane == 0) c.s.tails[0] = base;
-            __syncwarp();
-            if (e != kNoEntry) wq_classify<R, G>(c, e);
+            const unsigned e = wq_pop(&c.tails[0], c.q1, t1, lane);
+            const bool keep = e != kNoEntry && wq_recull<R>(c, e);
+            const unsigned b = __ballot_sync(0xffffffffu, keep);
+            if (keep) c.q1b[t1b + __popc(b & ((1u << lane) - 1u))] = e;
+            if (lane == 0) c.tails[1] = t1b + __popc(b);
         } else
             break;
     }
@@ -187,7 +225,7 @@ __device__ __forceinline__ void wq_drain(const WqCtx<R> &c, bool flush) {
 
 // F = FK scalar, R = geometry scalar, MODE = RVS_DIST_MIN | RVS_DIST_PROFILE, G = links scanned per obstacle pass.
 template <class F, class R, int MODE, int G>
-__global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, const int tile_cap) {
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char wq_smem[];
     typedef typename WqBits<R>::type Bits;
     const RobotDev *__restrict__ rb = a.robot;
@@ -197,94 +235,100 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     WqCtx<R> c;
     {
         unsigned char *p = wq_smem;
-        c.s.tile = reinterpret_cast<ObstacleRec *>(p); p += size_t(tile_cap) * sizeof(ObstacleRec);
-        c.s.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
-        c.s.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqStride * sizeof(Bits);
-        c.s.radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
+        c.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
+        c.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqStride * sizeof(Bits);
+        c.radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
         p = wq_smem + ((size_t(p - wq_smem) + 15) & ~size_t(15));
-        c.s.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
-        unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * (4 + WqCaps<G>::q1 + WqCaps<G>::q2);
-        c.s.tails = wq; c.s.q1 = wq + 4; c.s.q2 = wq + 4 + WqCaps<G>::q1;
+        c.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
+        unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * WqCaps<G>::words;
+        c.tails = wq; c.q1 = wq + 4; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
     }
-    c.L = L; c.M = a.M; c.wbase = warp * 32; c.tile_base = 0;
+    c.obs4 = reinterpret_cast<const float4 *>(a.obstacles);
+    c.M = a.M; c.wbase = warp * 32; c.seg_base = 0;
     c.eq_thr = R(a.eq_thr); c.max_dist = R(a.max_dist);
 
     const int64_t cfg = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
     const bool live = cfg < a.N;
     const int t = threadIdx.x;
-    if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.s.skel + t, kWqStride);
-    else for (int k = 0; k < 3 * (L + 1); k++) c.s.skel[k * kWqStride + t] = R(0);
-    for (int i = 0; i < L; i++) c.s.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
-    c.s.hit[t] = kNoHit;
-    if (t < L) c.s.radius[t] = RobotScalars<R>::radius(rb, t);
-    if (lane == 0) { c.s.tails[0] = 0; c.s.tails[1] = 0; }
+    if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.skel + t, kWqStride);
+    else for (int k = 0; k < 3 * (L + 1); k++) c.skel[k * kWqStride + t] = R(0);
+    for (int i = 0; i < L; i++) c.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
+    c.hit[t] = kNoHit;
+    if (t < L) c.radius[t] = RobotScalars<R>::radius(rb, t);
+    if (lane == 0) { c.tails[0] = 0; c.tails[1] = 0; c.tails[2] = 0; }
     const int ground_included = rb->ground_included;
+    __syncthreads();                                                       // radius[] is shared by the block; everything else is per warp
 
-    for (int base = 0; base < a.M; base += tile_cap) {
-        const int count = min(tile_cap, a.M - base);
-        __syncthreads();
-        stage_tile(c.s.tile, a.obstacles + base, count);
-        __syncthreads();
-        c.tile_base = base;
-        const float4 *t4 = reinterpret_cast<const float4 *>(c.s.tile);
+    for (int base = 0; base < a.M; base += kWqSegment) {
+        const int count = min(kWqSegment, a.M - base);
+        c.seg_base = base;
+        const float4 *o4 = c.obs4 + 2 * size_t(base);
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
             const int gskip = ground_included - g0;                       // links g0 .. g0+gskip-1 ignore ground objects (:336)
-            const unsigned ground_keep = gskip <= 0 ? ~0u : (gskip >= G ? 0u : ~((1u << gskip) - 1u));
+            const unsigned ground_keep1 = gskip <= 0 ? ~0u : (gskip >= G ? 0u : ~((1u << gskip) - 1u));
+            const unsigned ground_keep = (ground_keep1 & ((1u << G) - 1u)) * ((1u << G) + 1u);     // replicated for both unrolled obstacles
 #pragma unroll 1
-            for (int j0 = 0; j0 < count; j0 += kWqChunk) {
+            for (int j0 = 0; j0 < count;) {
                 // inflated link boxes from the current minima; links at or above a known collision are dead
                 R lo[G][3], hi[G][3];
-                const unsigned hk = c.s.hit[t];
+                const unsigned hk = c.hit[t];
                 const int limit = !live ? 0 : (hk == kNoHit ? L : int(hk / unsigned(a.M)) + 1);
 #pragma unroll
                 for (int l = 0; l < G; l++) {
                     const int i = g0 + l;
                     if (i < limit && i < L) {
-                        const R *sk = c.s.skel + (3 * i) * kWqStride + t;
-                        const R thr = wq_threshold(WqBits<R>::from(c.s.best[i * kWqStride + t]), c.s.radius[i], c.eq_thr);
+                        const R *sk = c.skel + (3 * i) * kWqStride + t;
+                        const R thr = wq_threshold(WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
 #pragma unroll
                         for (int k = 0; k < 3; k++) {
                             const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
-                            lo[l][k] = (p < q ? p : q) - thr;
-                            hi[l][k] = (p < q ? q : p) + thr;
+                            lo[l][k] = fmin(p, q) - thr;
+                            hi[l][k] = fmax(p, q) + thr;
                         }
                     } else {
 #pragma unroll
                         for (int k = 0; k < 3; k++) { lo[l][k] = wq_inf<R>(); hi[l][k] = -wq_inf<R>(); }          // overlaps nothing
                     }
                 }
-                const int jend = min(j0 + kWqChunk, count);
+                // the minima settle quickly: refresh after 32, 64, 128, ... obstacles
+                const int jend = min(j0 + (j0 < 32 ? 32 : j0), count);
 #pragma unroll 1
-                for (int j = j0; j < jend; j++) {
-                    const float4 w0 = t4[2 * j], w1 = t4[2 * j + 1];      // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags): warp-wide broadcast
-                    const R ox = R(w0.x), oy = R(w0.y), oz = R(w0.z), px = R(w0.w), py = R(w1.x), pz = R(w1.y);
+                for (int j = j0; j < jend; j += kWqUnroll) {
+                    // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags) of two obstacles: warp-uniform 16-byte loads
+                    const int j1 = j + 1 < jend ? j + 1 : j;
+                    const float4 w0 = __ldg(o4 + 2 * j), w1 = __ldg(o4 + 2 * j + 1), v0 = __ldg(o4 + 2 * j1), v1 = __ldg(o4 + 2 * j1 + 1);
                     unsigned mask = 0;
 #pragma unroll
                     for (int l = 0; l < G; l++) {
-                        const bool ov = ox <= hi[l][0] && px >= lo[l][0] && oy <= hi[l][1] && py >= lo[l][1] && oz <= hi[l][2] && pz >= lo[l][2];
-                        mask |= ov ? (1u << l) : 0u;
+                        wq_overlap<R>(mask, 1u << l, R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[l], hi[l]);
+                        wq_overlap<R>(mask, 1u << (G + l), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[l], hi[l]);
                     }
-                    if (__float_as_uint(w1.w) & 1u) mask &= ground_keep;
+                    if (j1 == j) mask &= (1u << G) - 1u;                                    // odd tail: the second slot is a duplicate
+                    if ((__float_as_uint(w1.w) | __float_as_uint(v1.w)) & 1u)
+                        mask &= ((__float_as_uint(w1.w) & 1u) ? (ground_keep | ~((1u << G) - 1u)) : ~0u) &
+                                ((__float_as_uint(v1.w) & 1u) ? (ground_keep | ((1u << G) - 1u)) : ~0u);
                     if (mask) {
-                        unsigned pos = atomicAdd(const_cast<unsigned *>(&c.s.tails[0]), unsigned(__popc(mask)));
+                        unsigned pos = atomicAdd(const_cast<unsigned *>(&c.tails[0]), unsigned(__popc(mask)));
                         do {
-                            const int l = __ffs(int(mask)) - 1;
+                            const int b = __ffs(int(mask)) - 1;
                             mask &= mask - 1u;
-                            c.s.q1[pos++] = unsigned(lane) | (unsigned(g0 + l) << 5) | (unsigned(j) << 10);
+                            const int l = b >= G ? b - G : b, jj = b >= G ? j1 : j;
+                            c.q1[pos++] = unsigned(lane) | (unsigned(g0 + l) << 5) | (unsigned(jj) << 10);
                         } while (mask);
                     }
                     __syncwarp();
-                    if (c.s.tails[0] >= 32u) wq_drain<R, G>(c, false);
+                    if (c.tails[0] >= 32u) wq_drain<R>(c, false);
                 }
+                j0 = jend;
             }
         }
-        wq_drain<R, G>(c, true);                                            // queue entries index this tile: empty them before it is replaced
+        wq_drain<R>(c, true);                                              // queue entries index this segment: empty them before moving on
     }
     __syncwarp();
 
     // ---- per-configuration epilogue (lane = configuration again) ---------------------------------------------------
-    const unsigned hk = c.s.hit[t];
+    const unsigned hk = c.hit[t];
     const bool collided = live && hk != kNoHit;
     const int limit = collided ? int(hk / unsigned(a.M)) : L;
     const int hit_j = collided ? int(hk % unsigned(a.M)) : 0;
@@ -292,8 +336,8 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     if (collided) {
         // the value the reference stores for the colliding link: replay exactly that pair sequentially
         Capsule<R> cp;
-        const R *sk = c.s.skel + (3 * limit) * kWqStride + t;
-        cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, c.s.radius[limit], R(0));
+        const R *sk = c.skel + (3 * limit) * kWqStride + t;
+        cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, c.radius[limit], R(0));
         V3<R> u, v;
         hit_d = capsule_box_distance<R, false>(cp, load_box<R>(a.obstacles[hit_j]), c.eq_thr, c.max_dist, u, v);
     }
@@ -314,12 +358,12 @@ __global__ void __launch_bounds__(kWqBlock) distance_wq_kernel(const KArgs a, co
     }
     if (!live) return;
     R d_c = c.max_dist;
-    for (int i = 0; i < L; i++) { const R b = WqBits<R>::from(c.s.best[i * kWqStride + t]); if (b < d_c) d_c = b; }
+    for (int i = 0; i < L; i++) { const R b = WqBits<R>::from(c.best[i * kWqStride + t]); if (b < d_c) d_c = b; }
     static_cast<R *>(a.d_c)[cfg] = collided ? R(0) : d_c;
     if (MODE >= RVS_DIST_PROFILE) {
         R *out = static_cast<R *>(a.profile) + cfg * L;
         for (int i = 0; i < L; i++) {
-            const R b = WqBits<R>::from(c.s.best[i * kWqStride + t]);
+            const R b = WqBits<R>::from(c.best[i * kWqStride + t]);
             out[i] = !collided ? b : (i < limit ? b : (i == limit ? hit_d : R(0)));
         }
     }

@@ -15,15 +15,14 @@ template <class F, class R>
 struct Variant {
     template <int MODE, int G>
     static cudaError_t distance_wq(const KArgs &a, cudaStream_t st) {
-        const int tile_cap = a.M < kWqTile ? (a.M > 0 ? a.M : 1) : kWqTile;
-        const size_t smem = wq_smem_bytes<R, G>(a.robot_n_hint, tile_cap);
+        const size_t smem = wq_smem_bytes<R, G>(a.robot_n_hint);
         static size_t configured = 0;                     // per instantiation: raise the dynamic shared-memory limit once
         if (smem > configured) {
             const cudaError_t e = cudaFuncSetAttribute(distance_wq_kernel<F, R, MODE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        distance_wq_kernel<F, R, MODE, G><<<grid_for(a.N, kWqBlock), kWqBlock, smem, st>>>(a, tile_cap);
+        distance_wq_kernel<F, R, MODE, G><<<grid_for(a.N, kWqBlock), kWqBlock, smem, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
