@@ -129,7 +129,7 @@ int  rvs_device_count(void);
 int  rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device, rvs_handle *out);
 int  rvs_destroy(rvs_handle h);
 const char *rvs_last_error(rvs_handle h);      /* h may be NULL: last error of a failed rvs_create */
-int  rvs_set_params(rvs_handle h, const rvs_params *params);
+int  rvs_set_params(rvs_handle h, const rvs_params *params);   /* precision < 0: keep the handle's variant */
 int  rvs_set_stream(rvs_handle h, void *cuda_stream);  /* adopt an external cudaStream_t (e.g. torch's) */
 void *rvs_get_stream(rvs_handle h);
 int  rvs_sync(rvs_handle h);

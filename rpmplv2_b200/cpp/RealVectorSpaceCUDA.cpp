@@ -1,0 +1,294 @@
+// RealVectorSpaceCUDA.cpp — see RealVectorSpaceCUDA.h. Host-side glue only: gathers base::State coordinates into flat
+// arrays, calls the C ABI, scatters results back into the State caches exactly as RealVectorSpace.cpp does.
+#include "RealVectorSpaceCUDA.h"
+
+#include <cstring>
+#include <stdexcept>
+
+#include "RealVectorSpaceConfig.h"
+#include "rvs_urdf.h"
+
+namespace
+{
+	rvs_params currentParams(rvs_precision precision)
+	{
+		rvs_params p;
+		p.equality_threshold = RealVectorSpaceConfig::EQUALITY_THRESHOLD;
+		p.max_distance = RealVectorSpaceConfig::MAX_DISTANCE;
+		p.num_interpolation_validity_checks = int32_t(RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS);
+		p.precision = int32_t(precision);
+		return p;
+	}
+}
+
+base::RealVectorSpaceCUDA::RealVectorSpaceCUDA(size_t num_dimensions_, const std::shared_ptr<robots::AbstractRobot> robot_,
+	const std::shared_ptr<env::Environment> env_, const std::string &urdf_path, int device, rvs_precision precision)
+	: RealVectorSpace(num_dimensions_, robot_, env_)
+{
+	rvs_robot_desc chain;
+	std::string error;
+	if (!rvs::chain_from_urdf_file(urdf_path, robot->getType(), &chain, &error))
+		throw std::runtime_error("RealVectorSpaceCUDA: " + error);
+	create(chain, device, precision);
+}
+
+base::RealVectorSpaceCUDA::RealVectorSpaceCUDA(size_t num_dimensions_, const std::shared_ptr<robots::AbstractRobot> robot_,
+	const std::shared_ptr<env::Environment> env_, const rvs_robot_desc &chain, int device, rvs_precision precision)
+	: RealVectorSpace(num_dimensions_, robot_, env_)
+{
+	create(chain, device, precision);
+}
+
+void base::RealVectorSpaceCUDA::create(const rvs_robot_desc &chain, int device, rvs_precision precision)
+{
+	setStateSpaceType(base::StateSpaceType::RealVectorSpaceCUDA);
+	if (precision == RVS_PREC_F64)
+		throw std::runtime_error("RealVectorSpaceCUDA: base::State stores float distances; use RVS_PREC_REF32 or RVS_PREC_FAST32");
+	if (size_t(chain.num_dofs) != robot->getNumDOFs() || size_t(chain.num_dofs) != num_dimensions)
+		throw std::runtime_error("RealVectorSpaceCUDA: URDF chain and robot disagree on the number of DOFs");
+	num_links = robot->getNumLinks();
+	if (num_links != size_t(chain.num_dofs))
+		throw std::runtime_error("RealVectorSpaceCUDA: the engine expects one capsule per joint (getNumLinks() == getNumDOFs())");
+
+	// scenario-level fields come from the robot object the scenario configured (Scenario.cpp:36-75)
+	rvs_robot_desc desc = chain;
+	desc.ground_included = int32_t(robot->getGroundIncluded());
+	desc.gripper_length = robot->getGripperLength();
+	for (size_t i = 0; i < num_links; i++)
+	{
+		desc.capsule_radius[i] = robot->getCapsuleRadius(i);
+		desc.limit_lo[i] = robot->getLimits()[i].first;
+		desc.limit_hi[i] = robot->getLimits()[i].second;
+	}
+
+	const rvs_params params = currentParams(precision);
+	const int status = rvs_create(&desc, &params, device, &engine);
+	if (status != RVS_OK)
+		throw std::runtime_error(std::string("RealVectorSpaceCUDA: cannot create the engine: ") + rvs_last_error(nullptr));
+	refreshObstacles();
+}
+
+base::RealVectorSpaceCUDA::~RealVectorSpaceCUDA()
+{
+	if (engine != nullptr)
+		rvs_destroy(engine);
+}
+
+void base::RealVectorSpaceCUDA::check(int status, const char *what) const
+{
+	if (status != RVS_OK)
+		throw std::runtime_error(std::string("RealVectorSpaceCUDA::") + what + ": " + rvs_last_error(engine));
+}
+
+void base::RealVectorSpaceCUDA::refreshConfig()
+{
+	rvs_params params = currentParams(RVS_PREC_REF32);
+	params.precision = -1;		// keep the precision the handle was created with
+	check(rvs_set_params(engine, &params), "refreshConfig");
+}
+
+/// Obstacle table = what RealVectorSpace.cpp:293-295,344-346 reads per pair: the AABB of every collision object,
+/// whether its label is "ground" (:285,336) and its min_dist_tol (:367).
+void base::RealVectorSpaceCUDA::refreshObstacles()
+{
+	num_objects = env->getNumObjects();
+	std::vector<float> aabb_min(3 * num_objects), aabb_max(3 * num_objects), tol(num_objects);
+	std::vector<uint8_t> is_ground(num_objects);
+	for (size_t j = 0; j < num_objects; j++)
+	{
+		if (env->getCollObject(j)->getNodeType() != fcl::GEOM_BOX)
+			throw std::runtime_error("RealVectorSpaceCUDA: only box obstacles are supported (the reference's sphere branch is a TODO stub)");
+		const fcl::AABB &AABB { env->getCollObject(j)->getAABB() };
+		for (int k = 0; k < 3; k++)
+		{
+			aabb_min[3 * j + k] = AABB.min_[k];
+			aabb_max[3 * j + k] = AABB.max_[k];
+		}
+		is_ground[j] = env->getObject(j)->getLabel() == "ground" ? 1 : 0;
+		tol[j] = env->getObject(j)->getMinDistTol();
+	}
+	check(rvs_set_obstacles(engine, aabb_min.data(), aabb_max.data(), is_ground.data(), tol.data(), int32_t(num_objects)), "refreshObstacles");
+}
+
+void base::RealVectorSpaceCUDA::gather(const std::vector<std::shared_ptr<base::State>> &states, std::vector<float> &q) const
+{
+	q.resize(states.size() * num_dimensions);
+	for (size_t i = 0; i < states.size(); i++)
+		std::memcpy(&q[i * num_dimensions], states[i]->getCoord().data(), num_dimensions * sizeof(float));
+}
+
+/// nearest_points: one 6 x L matrix per obstacle, column i = (R, O) of link i (RealVectorSpace.cpp:381) -> [M][L][6]
+void base::RealVectorSpaceCUDA::packPlanes(const std::vector<Eigen::MatrixXf> &nearest_points, std::vector<float> &planes) const
+{
+	planes.resize(nearest_points.size() * num_links * 6);
+	for (size_t j = 0; j < nearest_points.size(); j++)
+		for (size_t i = 0; i < num_links; i++)
+			for (size_t k = 0; k < 6; k++)
+				planes[(j * num_links + i) * 6 + k] = nearest_points[j](Eigen::Index(k), Eigen::Index(i));
+}
+
+/// The State side effects of RealVectorSpace::computeDistance (RealVectorSpace.cpp:371-376, 386-389).
+void base::RealVectorSpaceCUDA::storeDistance(const std::shared_ptr<base::State> &q, float d_c, const float *profile, const float *nearest) const
+{
+	q->setDistance(d_c);
+	q->setDistanceProfile(std::vector<float>(profile, profile + num_links));
+	q->setIsRealDistance(true);
+	if (d_c <= 0)
+	{
+		q->setNearestPoints(nullptr);
+		return;
+	}
+	if (nearest == nullptr)
+		return;
+	std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points { std::make_shared<std::vector<Eigen::MatrixXf>>
+		(num_objects, Eigen::MatrixXf(6, num_links)) };
+	for (size_t j = 0; j < num_objects; j++)
+		for (size_t i = 0; i < num_links; i++)
+			for (size_t k = 0; k < 6; k++)
+				nearest_points->at(j)(Eigen::Index(k), Eigen::Index(i)) = nearest[(j * num_links + i) * 6 + k];
+	q->setNearestPoints(nearest_points);
+}
+
+bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q)
+{
+	uint8_t valid = 0;
+	check(rvs_is_valid(engine, q->getCoord().data(), 1, &valid), "isValid");
+	return valid != 0;
+}
+
+bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q1, const std::shared_ptr<base::State> q2)
+{
+	uint8_t valid = 0;
+	check(rvs_is_valid_edges(engine, q1->getCoord().data(), q2->getCoord().data(), 1, &valid), "isValid(q1, q2)");
+	return valid != 0;
+}
+
+float base::RealVectorSpaceCUDA::computeDistance(const std::shared_ptr<base::State> q, bool compute_again)
+{
+	if (!compute_again && q->getDistance() > 0 && q->getIsRealDistance())
+		return q->getDistance();
+
+	float d_c = 0;
+	std::vector<float> profile(num_links), nearest(num_objects * num_links * 6);
+	check(rvs_distance(engine, q->getCoord().data(), 1, RVS_DIST_FULL, &d_c, profile.data(), nearest.data()), "computeDistance");
+	storeDistance(q, d_c, profile.data(), nearest.data());
+	return d_c;
+}
+
+float base::RealVectorSpaceCUDA::computeDistanceUnderestimation(const std::shared_ptr<base::State> q,
+	const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points)
+{
+	if (q->getDistance() > 0 && q->getIsRealDistance()) 	// Real distance was already computed
+		return q->getDistance();
+
+	std::vector<float> planes;
+	packPlanes(*nearest_points, planes);
+	float d_c = 0;
+	uint8_t rejected = 0;
+	std::vector<float> profile(num_links);
+	check(rvs_underestimation(engine, q->getCoord().data(), 1, planes.data(), nullptr, 1, &d_c, profile.data(), &rejected), "computeDistanceUnderestimation");
+	if (rejected)
+		return 0;			// a plane distance < 0: the reference returns 0 without touching the state (:428-429)
+
+	q->setDistance(d_c);
+	q->setDistanceProfile(profile);
+	q->setIsRealDistance(false);
+	return d_c;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::isValidBatch(const std::vector<std::shared_ptr<base::State>> &states)
+{
+	std::vector<float> q;
+	gather(states, q);
+	std::vector<uint8_t> valid(states.size());
+	check(rvs_is_valid(engine, q.data(), int64_t(states.size()), valid.data()), "isValidBatch");
+	return valid;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::isValidEdges
+	(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges)
+{
+	std::vector<float> q1(edges.size() * num_dimensions), q2(edges.size() * num_dimensions);
+	for (size_t e = 0; e < edges.size(); e++)
+	{
+		std::memcpy(&q1[e * num_dimensions], edges[e].first->getCoord().data(), num_dimensions * sizeof(float));
+		std::memcpy(&q2[e * num_dimensions], edges[e].second->getCoord().data(), num_dimensions * sizeof(float));
+	}
+	std::vector<uint8_t> valid(edges.size());
+	check(rvs_is_valid_edges(engine, q1.data(), q2.data(), int64_t(edges.size()), valid.data()), "isValidEdges");
+	return valid;
+}
+
+std::vector<float> base::RealVectorSpaceCUDA::computeDistanceBatch(const std::vector<std::shared_ptr<base::State>> &states,
+	bool compute_again, bool with_nearest_points)
+{
+	std::vector<float> result(states.size());
+	std::vector<std::shared_ptr<base::State>> todo;
+	std::vector<size_t> where;
+	for (size_t i = 0; i < states.size(); i++)
+	{
+		if (!compute_again && states[i]->getDistance() > 0 && states[i]->getIsRealDistance())
+			result[i] = states[i]->getDistance();		// cached (RealVectorSpace.cpp:320-321)
+		else
+		{
+			todo.emplace_back(states[i]);
+			where.emplace_back(i);
+		}
+	}
+	if (todo.empty())
+		return result;
+
+	std::vector<float> q;
+	gather(todo, q);
+	const size_t per_state = num_objects * num_links * 6;
+	std::vector<float> d_c(todo.size()), profile(todo.size() * num_links), nearest(with_nearest_points ? todo.size() * per_state : 0);
+	check(rvs_distance(engine, q.data(), int64_t(todo.size()), with_nearest_points ? RVS_DIST_FULL : RVS_DIST_PROFILE,
+					   d_c.data(), profile.data(), with_nearest_points ? nearest.data() : nullptr), "computeDistanceBatch");
+	for (size_t k = 0; k < todo.size(); k++)
+	{
+		storeDistance(todo[k], d_c[k], &profile[k * num_links], with_nearest_points ? &nearest[k * per_state] : nullptr);
+		result[where[k]] = d_c[k];
+	}
+	return result;
+}
+
+std::vector<float> base::RealVectorSpaceCUDA::computeDistanceUnderestimationBatch(const std::vector<std::shared_ptr<base::State>> &states,
+	const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points)
+{
+	std::vector<float> result(states.size());
+	std::vector<std::shared_ptr<base::State>> todo;
+	std::vector<size_t> where;
+	for (size_t i = 0; i < states.size(); i++)
+	{
+		if (states[i]->getDistance() > 0 && states[i]->getIsRealDistance())
+			result[i] = states[i]->getDistance();
+		else
+		{
+			todo.emplace_back(states[i]);
+			where.emplace_back(i);
+		}
+	}
+	if (todo.empty())
+		return result;
+
+	std::vector<float> q, planes;
+	gather(todo, q);
+	packPlanes(*nearest_points, planes);
+	std::vector<float> d_c(todo.size()), profile(todo.size() * num_links);
+	std::vector<uint8_t> rejected(todo.size());
+	check(rvs_underestimation(engine, q.data(), int64_t(todo.size()), planes.data(), nullptr, 1, d_c.data(), profile.data(), rejected.data()),
+		  "computeDistanceUnderestimationBatch");
+	for (size_t k = 0; k < todo.size(); k++)
+	{
+		if (rejected[k])
+		{
+			result[where[k]] = 0;
+			continue;
+		}
+		todo[k]->setDistance(d_c[k]);
+		todo[k]->setDistanceProfile(std::vector<float>(&profile[k * num_links], &profile[(k + 1) * num_links]));
+		todo[k]->setIsRealDistance(false);
+		result[where[k]] = d_c[k];
+	}
+	return result;
+}

@@ -1,0 +1,88 @@
+// RealVectorSpaceCUDA.h — the `space: "RealVectorSpaceCUDA"` state space: RPMPLv2's base::RealVectorSpace with its
+// collision / distance hot path served by the B200 engine (librvs_cuda.so, include/rvs_cuda.h).
+//
+// Drop-in contract (reference paths are relative to the RPMPLv2 tree):
+//   * derives from base::RealVectorSpace (include/state_spaces/real_vector_space/RealVectorSpace.h:17-52) and overrides
+//     exactly the four hot methods of base::StateSpace (include/state_spaces/StateSpace.h:50-55):
+//         bool  isValid(q)                        RealVectorSpace.cpp:277-309
+//         bool  isValid(q1, q2)                   RealVectorSpace.cpp:261-275
+//         float computeDistance(q, compute_again) RealVectorSpace.cpp:318-392
+//         float computeDistanceUnderestimation(q, nearest_points)   RealVectorSpace.cpp:402-446
+//     with the same return values, the same side effects on base::State (setDistance / setDistanceProfile /
+//     setIsRealDistance / setNearestPoints) and the same caching rules (Q20 of SURVEY.md §8.1). Everything else
+//     (sampling, interpolation, pruning, path preprocessing) is inherited unchanged.
+//   * adds the batched overloads the bur planners call for whole spine sets / edge batches:
+//         isValidBatch, isValidEdges, computeDistanceBatch, computeDistanceUnderestimationBatch.
+//   * robot chain: taken from the robot's URDF with rvs::chain_from_urdf_file (rvs_urdf.h) — the same chain the
+//     reference's robot classes hand to KDL; radii, gripper length, ground_included and limits are read from the
+//     robots::AbstractRobot the scenario built. Obstacles are read from env::Environment (AABB of every
+//     fcl::CollisionObject, label == "ground", min_dist_tol); call refreshObstacles() after the environment changed
+//     (Environment::addObject / removeObject / updateEnvironment).
+//   * there is NO CPU fallback: the constructor throws std::runtime_error when the engine cannot be created.
+#ifndef RPMPL_REALVECTORSPACECUDA_H
+#define RPMPL_REALVECTORSPACECUDA_H
+
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "RealVectorSpace.h"
+#include "rvs_cuda.h"
+
+namespace base
+{
+	class RealVectorSpaceCUDA : public base::RealVectorSpace
+	{
+	public:
+		RealVectorSpaceCUDA(size_t num_dimensions_, const std::shared_ptr<robots::AbstractRobot> robot_,
+							const std::shared_ptr<env::Environment> env_, const std::string &urdf_path,
+							int device = 0, rvs_precision precision = RVS_PREC_REF32);
+		RealVectorSpaceCUDA(size_t num_dimensions_, const std::shared_ptr<robots::AbstractRobot> robot_,
+							const std::shared_ptr<env::Environment> env_, const rvs_robot_desc &chain,
+							int device = 0, rvs_precision precision = RVS_PREC_REF32);
+		~RealVectorSpaceCUDA() override;
+		RealVectorSpaceCUDA(const RealVectorSpaceCUDA &) = delete;
+		RealVectorSpaceCUDA &operator=(const RealVectorSpaceCUDA &) = delete;
+
+		bool isValid(const std::shared_ptr<base::State> q1, const std::shared_ptr<base::State> q2) override;
+		bool isValid(const std::shared_ptr<base::State> q) override;
+		float computeDistance(const std::shared_ptr<base::State> q, bool compute_again = false) override;
+		float computeDistanceUnderestimation(const std::shared_ptr<base::State> q,
+			const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points) override;
+
+		// ---- batched overloads (new call sites for RGBT / RGBMT* / DRGBT / RRTx) ----
+		// valid[i] = isValid(states[i])
+		std::vector<uint8_t> isValidBatch(const std::vector<std::shared_ptr<base::State>> &states);
+		// valid[e] = isValid(edges[e].first, edges[e].second)
+		std::vector<uint8_t> isValidEdges(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges);
+		// computeDistance for every state (same caching rule and the same State side effects as the single call).
+		// with_nearest_points = false skips the per-(obstacle, link) nearest points (RVS_DIST_PROFILE): the states
+		// then get d_c, the profile and is_real_d_c, and their nearest_points are left untouched.
+		std::vector<float> computeDistanceBatch(const std::vector<std::shared_ptr<base::State>> &states,
+												bool compute_again = false, bool with_nearest_points = true);
+		// computeDistanceUnderestimation of every state w.r.t. ONE root's planes (the spine set of a bur)
+		std::vector<float> computeDistanceUnderestimationBatch(const std::vector<std::shared_ptr<base::State>> &states,
+			const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points);
+
+		// re-read env->getObjects() into the device obstacle table (24 B per object)
+		void refreshObstacles();
+		// push the current RealVectorSpaceConfig globals to the engine (they are mutable statics in the reference)
+		void refreshConfig();
+		rvs_handle handle() const { return engine; }
+
+	private:
+		void create(const rvs_robot_desc &chain, int device, rvs_precision precision);
+		void check(int status, const char *what) const;
+		void gather(const std::vector<std::shared_ptr<base::State>> &states, std::vector<float> &q) const;
+		void packPlanes(const std::vector<Eigen::MatrixXf> &nearest_points, std::vector<float> &planes) const;
+		void storeDistance(const std::shared_ptr<base::State> &q, float d_c, const float *profile, const float *nearest) const;
+
+		rvs_handle engine = nullptr;
+		size_t num_links = 0;
+		size_t num_objects = 0;
+	};
+}
+
+#endif //RPMPL_REALVECTORSPACECUDA_H

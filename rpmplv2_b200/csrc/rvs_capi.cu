@@ -250,7 +250,9 @@ int rvs_destroy(rvs_handle h) {
 int rvs_set_params(rvs_handle h, const rvs_params *params) {
     RVS_TRY(enter(h));
     RVS_TRY(check_params(h, params));
+    const int32_t keep = h->prm.precision;
     h->prm = *params;
+    if (params->precision < 0) h->prm.precision = keep;      // "leave the arithmetic variant as it is"
     return select_table(h);
 }
 

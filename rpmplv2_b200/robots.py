@@ -240,3 +240,26 @@ def rpy_matrix(roll: float, pitch: float, yaw: float) -> np.ndarray:
     return np.array([[ca * cb, ca * sb * sc - sa * cc, ca * sb * cc + sa * sc],
                      [sa * cb, sa * sb * sc + ca * cc, sa * sb * cc - ca * sc],
                      [-sb, cb * sc, cb * cc]], np.float64)
+
+
+def to_urdf(robot: Robot) -> str:
+    """URDF text of a chain (inverse of from_urdf): lets the tests exercise the URDF readers without /root/reference."""
+    base, tip = ("link_base", "link_eef") if robot.kind == ROBOT_XARM6 else ("base_link", "tool")
+    n = robot.num_dofs
+    links = [base] + [f"link{k + 1}" for k in range(n)] + [tip]
+    out = ['<?xml version="1.0"?>', f'<robot name="{robot.name}">', '  <!-- generated by rpmplv2_b200.robots.to_urdf -->']
+    out += [f'  <link name="{name}"/>' for name in links]
+    for k in range(n + 1):
+        xyz = " ".join(repr(float(v)) for v in robot.xyz[k])
+        rpy = " ".join(repr(float(v)) for v in robot.rpy[k])
+        if k < n:
+            axis = " ".join(repr(float(v)) for v in robot.axis[k])
+            lo, hi = (repr(float(np.float64(v))) for v in robot.limits[k])
+            out += [f'  <joint name="joint{k + 1}" type="revolute">', f'    <parent link="{links[k]}"/>', f'    <child link="{links[k + 1]}"/>',
+                    f'    <origin xyz="{xyz}" rpy="{rpy}"/>', f'    <axis xyz="{axis}"/>',
+                    f'    <limit lower="{lo}" upper="{hi}" effort="50" velocity="3.14"/>', '  </joint>']
+        else:
+            out += [f'  <joint name="joint_tip" type="fixed">', f'    <parent link="{links[k]}"/>', f'    <child link="{links[k + 1]}"/>',
+                    f'    <origin xyz="{xyz}" rpy="{rpy}"/>', '  </joint>']
+    out += ['  <transmission name="t1"><joint name="joint1"/></transmission>', '</robot>']
+    return "\n".join(out) + "\n"

@@ -1,0 +1,118 @@
+"""The C++ host layer above the C ABI: base::RealVectorSpaceCUDA (rpmplv2_b200/cpp) and the URDF chain reader.
+
+Eigen / FCL / KDL are not installed here, so the class is compiled against rpmplv2_b200/cpp/stubs (same names and
+signatures as the RPMPLv2 headers it touches) and driven by tests/cpp/class_driver.cpp through ctypes.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import scenes
+from conftest import REFERENCE_DATA, ROOT
+from rpmplv2_b200 import robots, synthetic
+
+CPP = os.path.join(ROOT, "rpmplv2_b200", "cpp")
+f32p, u8p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint8)
+
+
+@pytest.fixture(scope="session")
+def driver():
+    out = os.path.join(ROOT, "tests", "cpp", "_build", "libclass_driver.so")
+    srcs = [os.path.join(ROOT, "tests", "cpp", "class_driver.cpp"), os.path.join(CPP, "RealVectorSpaceCUDA.cpp"), os.path.join(CPP, "rvs_urdf.cpp")]
+    deps = srcs + [os.path.join(CPP, "RealVectorSpaceCUDA.h"), os.path.join(CPP, "rvs_urdf.h"), os.path.join(ROOT, "include", "rvs_cuda.h")]
+    deps += [os.path.join(CPP, "stubs", f) for f in os.listdir(os.path.join(CPP, "stubs")) if f.endswith(".h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        pkg = os.path.join(ROOT, "rpmplv2_b200")
+        subprocess.run(["g++", "-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-shared", f"-I{CPP}", f"-I{CPP}/stubs", f"-I{ROOT}/include",
+                        *srcs, "-o", out, f"-L{pkg}", "-lrvs_cuda", f"-Wl,-rpath,{pkg}"], check=True)
+    return ctypes.CDLL(out)
+
+
+def _write_urdf(tmp_path, rb):
+    p = tmp_path / f"{rb.name}.urdf"
+    p.write_text(robots.to_urdf(rb))
+    return str(p)
+
+
+def _desc_equal(a, b, n):
+    assert a.kind == b.kind and a.num_dofs == b.num_dofs
+    for k in range(n + 1):
+        assert list(a.joint_xyz[k]) == list(b.joint_xyz[k]) and list(a.joint_rpy[k]) == list(b.joint_rpy[k])
+    for k in range(n):
+        assert list(a.joint_axis[k]) == list(b.joint_axis[k])
+        assert a.limit_lo[k] == b.limit_lo[k] and a.limit_hi[k] == b.limit_hi[k]
+
+
+@pytest.mark.parametrize("rb", [robots.xarm6(), robots.planar(2), robots.planar(10), robots.spatial(22)], ids=lambda r: r.name)
+def test_cpp_urdf_reader_round_trip(driver, tmp_path, rb):
+    """class builds (compile check of RealVectorSpaceCUDA against the reference's API surface) and the C++ URDF reader agrees with
+    the built-in chain tables and with the Python reader."""
+    path = _write_urdf(tmp_path, rb)
+    got = robots.RvsRobotDesc()
+    assert driver.drv_parse_urdf(path.encode(), rb.name.encode(), ctypes.byref(got)) == 0, ctypes.c_char_p.in_dll(driver, "drv_last_error")
+    _desc_equal(got, rb.to_desc(), rb.num_dofs)
+    py = robots.from_urdf(path, rb.name)
+    assert np.array_equal(py.xyz, rb.xyz) and np.array_equal(py.rpy, rb.rpy) and np.array_equal(py.axis, rb.axis) and np.array_equal(py.limits, rb.limits)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_DATA), reason="reference data only exists in the build container")
+def test_cpp_urdf_reader_on_the_reference_urdfs(driver):
+    for rtype, rel in [("xarm6", "xarm6/xarm6.urdf"), ("planar_2dof", "planar_2dof/planar_2dof.urdf"), ("planar_10dof", "planar_10dof/planar_10dof.urdf"),
+                       ("spatial_10dof", "spatial_10dof/spatial_10dof.urdf"), ("spatial_22dof", "spatial_22dof/spatial_22dof.urdf")]:
+        got = robots.RvsRobotDesc()
+        assert driver.drv_parse_urdf(os.path.join(REFERENCE_DATA, rel).encode(), rtype.encode(), ctypes.byref(got)) == 0
+        _desc_equal(got, robots.by_type(rtype).to_desc(), got.num_dofs)
+
+
+def test_cpp_urdf_reader_rejects_malformed_input(driver, tmp_path):
+    p = tmp_path / "bad.urdf"
+    p.write_text('<robot name="x"><joint name="j" type="revolute"><parent link="base_link"/><child link="l1"/></joint></robot>')
+    got = robots.RvsRobotDesc()
+    assert driver.drv_parse_urdf(str(p).encode(), b"planar_2dof", ctypes.byref(got)) == 1
+    assert driver.drv_parse_urdf(b"/nonexistent.urdf", b"xarm6", ctypes.byref(got)) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["xarm6", "planar2", "spatial10"])
+def test_cpp_class_matches_oracle_and_keeps_reference_state_semantics(driver, ob, tmp_path, case):
+    if case == "xarm6":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(30, "D2", 0.45)
+    elif case == "planar2":
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    else:
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(10), 6)
+    n, M, N = rb.num_dofs, len(g), 300
+    q = synthetic.configs(rb, N)
+    o = ob.Oracle(rb, robots.default_params())
+    o.set_obstacles(mn, mx, g, tol)
+    d_o, p_o, near_o = o.distance(q, robots.DIST_FULL)
+    root = int(np.flatnonzero(d_o > 0)[0])
+    q[0], q[root] = q[root].copy(), q[0].copy()                     # make configuration 0 the (collision-free) root
+    d_o, p_o, near_o = o.distance(q, robots.DIST_FULL)
+    valid = np.zeros(N, np.uint8); valid_b = np.zeros(N, np.uint8); has_near = np.zeros(N, np.uint8); is_real = np.zeros(N, np.uint8)
+    d = np.zeros(N, np.float32); d_b = np.zeros(N, np.float32); prof = np.zeros((N, n), np.float32); near = np.zeros((N, M, n, 6), np.float32)
+    ev = np.zeros(N - 1, np.uint8); ev_b = np.zeros(N - 1, np.uint8); un = np.zeros(N, np.float32); un_b = np.zeros(N, np.float32)
+    limits = np.ascontiguousarray(rb.limits, np.float32)
+    P = lambda a, t: a.ctypes.data_as(t)
+    rc = driver.drv_run(_write_urdf(tmp_path, rb).encode(), rb.name.encode(), n, P(rb.radius, f32p), ctypes.c_float(rb.gripper_length), rb.ground_included,
+                        P(limits, f32p), P(mn, f32p), P(mx, f32p), P(g, u8p), P(tol, f32p), M, ctypes.c_float(1e-4), 10, P(q, f32p), N, 0,
+                        P(valid, u8p), P(d, f32p), P(prof, f32p), P(near, f32p), P(has_near, u8p), P(d_b, f32p), P(valid_b, u8p), P(ev, u8p), P(ev_b, u8p),
+                        P(un, f32p), P(un_b, f32p), P(is_real, u8p))
+    driver.drv_last_error.restype = ctypes.c_char_p
+    assert rc == 0, driver.drv_last_error()
+    assert (valid == o.is_valid(q)).all() and (valid_b == valid).all()
+    assert ((d == 0) == (d_o == 0)).all() and np.abs(d - d_o).max() <= 1e-4 and (d_b == d).all()
+    assert np.abs(prof - p_o).max() <= 1e-4
+    free = d_o > 0
+    assert (has_near == free).all()                                   # nearest_points == nullptr exactly after a collision
+    assert np.abs(near[free] - near_o[free]).max() <= 1e-4
+    e_o = o.is_valid_edges(q[:-1], q[1:])
+    assert (ev == e_o).all() and (ev_b == e_o).all()
+    du_o, _, st_o = o.underestimation(q, near_o[0:1], np.zeros(N, np.int32))
+    assert np.abs(un - du_o).max() <= 1e-4 and (un_b == un).all()
+    assert ((un == 0) == (st_o == 1)).all()
+    assert (is_real[st_o == 0] == 0).all() and (is_real[st_o == 1] == 1).all()      # accepted: is_real_d_c = false; rejected: untouched
