@@ -140,6 +140,11 @@ int64_t rvs_launch_count(rvs_handle h);
  * (link-major, stop at the first collision, ground pairs skipped) would have made for all configurations passed to
  * rvs_distance* since the last reset. Synchronises the stream. */
 int  rvs_pair_count(rvs_handle h, int32_t reset, uint64_t *out);
+/* The same counter plus what the work-queue distance kernel actually executed since the last reset:
+ * out4[0] = reference-order pair queries (as rvs_pair_count), out4[1] = pairs that survived the broad-phase scan,
+ * out4[2] = pairs that went through the reference's case classification, out4[3] = segment-edge evaluations.
+ * (The sequential kernel evaluates every visited pair: it only advances out4[0].) Synchronises the stream. */
+int  rvs_work_stats(rvs_handle h, int32_t reset, uint64_t *out4);
 
 /* Roofline denominator: achieved FFMA (fp64 = 0) or DFMA (fp64 = 1) throughput of this device in TFLOP/s, measured with a
  * register-only unrolled FMA kernel (best of 4 timed launches, CUDA events). */

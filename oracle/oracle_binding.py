@@ -140,6 +140,17 @@ class Oracle:
         lib().orc_enclosing_radii_f32(self._h, _p(q, c_f32p), ctypes.c_int64(q.shape[0]), _p(out, c_f32p))
         return out
 
+    def extend_spines(self, q_root, root_profile, root_d_c, root_planes, q_targets, spine_params):
+        """RGBTConnect::extendGenSpine (distance-to-planes variant) from one root towards every target."""
+        q_root, root_profile = _f32(q_root, (self.n,)), _f32(root_profile, (self.n,))
+        q_targets, root_planes = _f32(q_targets, (-1, self.n)), _f32(root_planes)
+        S = q_targets.shape[0]
+        q_out, d_out, status = np.empty((S, self.n), np.float32), np.empty(S, np.float32), np.empty(S, np.uint8)
+        lib().orc_extend_spines_f32(self._h, _p(q_root, c_f32p), _p(root_profile, c_f32p), ctypes.c_float(root_d_c), _p(root_planes, c_f32p),
+                                    _p(q_targets, c_f32p), ctypes.c_int32(S), ctypes.byref(spine_params), _p(q_out, c_f32p), _p(d_out, c_f32p),
+                                    _p(status, ctypes.POINTER(ctypes.c_uint8)))
+        return q_out, d_out, status
+
     def self_collision_capsules(self, q):
         q = _f32(q, (-1, self.n))
         out = np.empty(q.shape[0], np.uint8)

@@ -662,6 +662,106 @@ T underestimation(const Robot &rb, size_t M, const V3<T> *sk, const T *planes, c
     return d_c;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Generalized-bur spines (row f-1): RBTConnect::extendSpine (src/planners/rbt/RBTConnect.cpp:85-150) and
+// RGBTConnect::extendGenSpine with use_real_dist = false (src/planners/rbt/RGBTConnect.cpp:73-92).
+// Self-collision truncation (RBTConnect.cpp:129-131) is not restated: it is `false` for every robot but
+// xArm6, whose check ends in an FCL mesh test.
+// ------------------------------------------------------------------------------------------------
+struct SpineConfig {      // RBTConnectConfig / RGBTConnectConfig
+    int num_layers = 5, num_iter_spine = 1;
+    bool use_expanded_bubble = true;
+    float d_crit = 0.05f;
+};
+
+// R.col(c).dot(delta) on dynamic Eigen objects: same SSE2 linear-vectorised order as coord_norm (assumption Q24).
+inline float dot_dyn(const float *a, int stride, const float *b, int n) {
+    float pr[64];
+    for (int i = 0; i < n; i++) pr[i] = a[i * stride] * b[i];
+    const int aligned = (n / 4) * 4, aligned2 = (n / 8) * 8;
+    float res;
+    if (aligned) {
+        float p0[4], p1[4];
+        for (int l = 0; l < 4; l++) p0[l] = pr[l];
+        if (aligned > 4) {
+            for (int l = 0; l < 4; l++) p1[l] = pr[4 + l];
+            for (int idx = 8; idx < aligned2; idx += 8)
+                for (int l = 0; l < 4; l++) { p0[l] = p0[l] + pr[idx + l]; p1[l] = p1[l] + pr[idx + 4 + l]; }
+            for (int l = 0; l < 4; l++) p0[l] = p0[l] + p1[l];
+            if (aligned > aligned2)
+                for (int l = 0; l < 4; l++) p0[l] = p0[l] + pr[aligned2 + l];
+        }
+        res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+        for (int i = aligned; i < n; i++) res = res + pr[i];
+    } else {
+        res = pr[0];
+        for (int i = 1; i < n; i++) res = res + pr[i];
+    }
+    return res;
+}
+
+// One extendSpine call from state (q, profile, d_c) towards q_e. Returns base::State::Status (1 Advanced, 3 Reached).
+inline int extend_spine(const Robot &rb, const float *q, const float *profile, float d_c, const float *q_e, const SpineConfig &sp, float *q_new) {
+    const int n = rb.n, W = n + 1;
+    std::vector<V3<float>> sk(n + 1), sk_new(n + 1);
+    std::vector<float> R(size_t(n) * W), delta(n), rho_profile(n, 0.f), q_temp(q, q + n);
+    float rho = 0.f;
+    int status = 1;
+    skeleton(rb, q, sk.data());
+    for (int counter = 1;; counter++) {
+        skeleton(rb, q_temp.data(), sk_new.data());
+        enclosing_radii(rb, sk_new.data(), R.data());
+        for (int i = 0; i < n; i++) delta[i] = std::fabs(q_e[i] - q_temp[i]);
+        float step;
+        if (sp.use_expanded_bubble) {
+            step = INFINITY;
+            for (int i = 0; i < n; i++) step = std::min(step, (profile[i] - rho_profile[i]) / dot_dyn(R.data() + (i + 1), W, delta.data(), n));
+        } else
+            step = (d_c - rho) / dot_dyn(R.data() + n, W, delta.data(), n);
+        if (step > 1) {
+            for (int i = 0; i < n; i++) q_new[i] = q_e[i];
+            status = 3;
+        } else
+            for (int i = 0; i < n; i++) q_new[i] = q_temp[i] + step * (q_e[i] - q_temp[i]);
+        if (counter == sp.num_iter_spine || status != 1) return status;
+        skeleton(rb, q_new, sk_new.data());
+        std::fill(rho_profile.begin(), rho_profile.end(), 0.f);
+        float rho_k_prev = 0.f;
+        for (int k = 1; k <= n; k++) {
+            const float rho_k = normD(sk[k] - sk_new[k]);
+            rho_profile[k - 1] = std::max(rho_k_prev, rho_k);
+            rho_k_prev = rho_k;
+            rho = std::max(rho, rho_k);
+        }
+        for (int i = 0; i < n; i++) q_temp[i] = q_new[i];
+    }
+}
+
+// extendGenSpine from a root (its profile, d_c and nearest-point planes) towards q_e. q_out[n]; *d_out = the last
+// distance-to-planes (0 when it was rejected). Returns the status (2 Trapped when the root has no clearance).
+inline int extend_gen_spine(const Robot &rb, size_t M, const Config<float> &cfg, const SpineConfig &sp, const float *q_root, const float *root_profile,
+                            float root_d_c, const float *root_planes, const float *q_e, float *q_out, float *d_out) {
+    const int n = rb.n;
+    for (int i = 0; i < n; i++) q_out[i] = q_root[i];
+    *d_out = root_d_c;
+    if (!(root_d_c > 0)) return 2;
+    std::vector<float> q_cur(q_root, q_root + n), prof_cur(root_profile, root_profile + n), prof_new(n);
+    std::vector<V3<float>> sk(n + 1);
+    float dc_cur = root_d_c;
+    int status = 0;
+    for (int layer = 0; layer < sp.num_layers; layer++) {
+        status = extend_spine(rb, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
+        skeleton(rb, q_out, sk.data());
+        bool rejected;
+        *d_out = underestimation(rb, M, sk.data(), root_planes, cfg, prof_new.data(), &rejected);
+        if (*d_out < sp.d_crit || status != 1) break;
+        q_cur.assign(q_out, q_out + n);
+        prof_cur = prof_new;
+        dc_cur = *d_out;
+    }
+    return status;
+}
+
 // splitmix64-based stateless synthetic configuration generator
 inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

@@ -200,6 +200,19 @@ int orc_underestimation_f32(void *h, const float *q, int64_t N, const float *pla
     return 0;
 }
 
+int orc_extend_spines_f32(void *h, const float *q_root, const float *root_profile, float root_d_c, const float *root_planes, const float *q_targets,
+                          int32_t S, const rvs_spine_params *sp, float *q_reached, float *d_c_reached, uint8_t *status) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    orc::SpineConfig sc;
+    sc.num_layers = sp->num_layers; sc.num_iter_spine = sp->num_iter_spine; sc.use_expanded_bubble = sp->use_expanded_bubble != 0; sc.d_crit = sp->d_crit;
+    for (int32_t s = 0; s < S; s++)
+        status[s] = uint8_t(orc::extend_gen_spine(e->robot, e->sc32.boxes.size(), cfg, sc, q_root, root_profile, root_d_c, root_planes,
+                                                  q_targets + size_t(s) * n, q_reached + size_t(s) * n, d_c_reached + s));
+    return 0;
+}
+
 int orc_enclosing_radii_f32(void *h, const float *q, int64_t N, float *radii) {
     auto *e = static_cast<Engine *>(h);
     const int n = e->robot.n;

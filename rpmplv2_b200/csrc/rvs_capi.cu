@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -228,8 +229,8 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     h->own_stream = true;
     if ((e = cudaMalloc(&h->d_robot, sizeof(RobotDev))) != cudaSuccess) return bail(e, "cudaMalloc(robot)");
     if ((e = cudaMemcpy(h->d_robot, &h->h_robot, sizeof(RobotDev), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(robot)");
-    if ((e = cudaMalloc(&h->d_pair_count, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
-    if ((e = cudaMemset(h->d_pair_count, 0, sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
+    if ((e = cudaMalloc(&h->d_pair_count, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
+    if ((e = cudaMemset(h->d_pair_count, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
     *out = h;
     return RVS_OK;
 }
@@ -315,6 +316,16 @@ int rvs_pair_count(rvs_handle h, int32_t reset, uint64_t *out) {
     unsigned long long v = 0;
     RVS_CUDA(h, cudaMemcpy(&v, h->d_pair_count, sizeof(v), cudaMemcpyDeviceToHost));
     if (out) *out = uint64_t(v);
+    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, 4 * sizeof(v)));
+    return RVS_OK;
+}
+
+int rvs_work_stats(rvs_handle h, int32_t reset, uint64_t *out4) {
+    RVS_TRY(enter(h));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    RVS_CUDA(h, cudaMemcpy(v, h->d_pair_count, sizeof(v), cudaMemcpyDeviceToHost));
+    if (out4) for (int k = 0; k < 4; k++) out4[k] = uint64_t(v[k]);
     if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, sizeof(v)));
     return RVS_OK;
 }
@@ -504,9 +515,40 @@ int rvs_capsule_box_collision(rvs_handle h, const float *AB, const float *radius
     return primitive_impl(h, AB, radius, obs, K, nullptr, hit);
 }
 
-int rvs_extend_spines(rvs_handle h, const float *, const float *, float, const float *, const float *, int32_t, const rvs_spine_params *,
-                      float *, float *, uint8_t *) {
-    return fail(h, RVS_ERR_UNSUPPORTED, "rvs_extend_spines is not implemented yet");
+int rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profile, float root_d_c, const float *root_planes,
+                      const float *q_targets, int32_t S, const rvs_spine_params *sp, float *q_reached, float *d_c_reached, uint8_t *status) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "spines run in FP32: use a REF32/FAST32 handle");
+    if (S < 0 || !sp || sp->num_layers < 1 || sp->num_iter_spine < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad S or spine parameters");
+    if (S == 0) return RVS_OK;
+    if (!q_root || !root_profile || !q_targets || !q_reached || !d_c_reached || !status || (!root_planes && h->M > 0))
+        return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    // one packed upload: [q_root n][root_profile n][q_targets S*n], planes separately; one packed download: [q_reached S*n][d_c S]
+    const size_t n = size_t(h->h_robot.n), in_floats = 2 * n + size_t(S) * n, planes_floats = size_t(h->M) * n * 6;
+    std::vector<float> pack(in_floats);
+    std::copy(q_root, q_root + n, pack.begin());
+    std::copy(root_profile, root_profile + n, pack.begin() + n);
+    std::copy(q_targets, q_targets + size_t(S) * n, pack.begin() + 2 * n);
+    RVS_TRY(h2d(h, B_Q, pack.data(), in_floats * sizeof(float)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));      // `pack` is pageable and dies with this frame
+    RVS_TRY(h2d(h, B_PLANES, root_planes, planes_floats * sizeof(float)));
+    RVS_TRY(reserve(h, B_DC, (size_t(S) * n + size_t(S)) * sizeof(float)));
+    RVS_TRY(reserve(h, B_VERD, size_t(S)));
+    const float *d_in = static_cast<const float *>(h->buf[B_Q].p);
+    float *d_out = static_cast<float *>(h->buf[B_DC].p);
+    SpineArgs a{};
+    a.robot = h->d_robot; a.M = h->M; a.S = S;
+    a.q_root = d_in; a.root_profile = d_in + n; a.q_targets = d_in + 2 * n; a.root_d_c = root_d_c;
+    a.root_planes = static_cast<const float *>(h->buf[B_PLANES].p);
+    a.num_layers = sp->num_layers; a.num_iter_spine = sp->num_iter_spine; a.use_expanded_bubble = sp->use_expanded_bubble;
+    a.d_crit = sp->d_crit; a.max_dist = h->prm.max_distance;
+    a.q_reached = d_out; a.d_c_reached = d_out + size_t(S) * n; a.status = static_cast<uint8_t *>(h->buf[B_VERD].p);
+    RVS_TRY(launched(h, h->lt.spines(a, h->stream), "spine kernel launch"));
+    RVS_CUDA(h, cudaMemcpyAsync(q_reached, d_out, size_t(S) * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RVS_CUDA(h, cudaMemcpyAsync(d_c_reached, d_out + size_t(S) * n, size_t(S) * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RVS_TRY(d2h(h, status, B_VERD, size_t(S)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
 }
 
 }  // extern "C"

@@ -52,7 +52,7 @@ template <int G> struct WqCaps {
     static constexpr int q1 = 32 * G * kWqUnroll + 32;   // one scan iteration can push 32*G*unroll pairs on top of a leftover < 32
     static constexpr int q1b = 64;                        // one re-cull round pushes <= 32 on top of a leftover < 32
     static constexpr int q2 = 32 * 12 + 32;               // one classify round pushes <= 32*12 edges on top of a leftover < 32
-    static constexpr int words = 4 + q1 + q1b + q2;       // 4 tail words first
+    static constexpr int words = 8 + q1 + q1b + q2;       // 8 control words first: 3 tails, 3 work counters
 };
 
 template <class R> struct WqBits;
@@ -86,7 +86,7 @@ struct WqCtx {
     typename WqBits<R>::type *best;           // [L][kWqStride]
     R *radius;                                // [L]
     unsigned *hit;                            // [kWqBlock]
-    volatile unsigned *tails;                 // this warp: [0] Q1, [1] Q1b, [2] Q2
+    volatile unsigned *tails;                 // this warp: [0] Q1, [1] Q1b, [2] Q2 tails; [4], [5], [6] entries popped from each
     unsigned *q1, *q1b, *q2;                  // this warp's queues
     int M, seg_base, wbase;                   // wbase = first thread of this warp in the block
     R eq_thr, max_dist;
@@ -195,7 +195,7 @@ __device__ __forceinline__ unsigned wq_pop(volatile unsigned *tail, const unsign
     const unsigned n = have < 32u ? have : 32u, base = have - n;
     const unsigned e = unsigned(lane) < n ? q[base + lane] : kNoEntry;
     __syncwarp();
-    if (lane == 0) *tail = base;
+    if (lane == 0) { *tail = base; tail[4] += n; }
     return e;
 }
 
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
         p = wq_smem + ((size_t(p - wq_smem) + 15) & ~size_t(15));
         c.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
         unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * WqCaps<G>::words;
-        c.tails = wq; c.q1 = wq + 4; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
+        c.tails = wq; c.q1 = wq + 8; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
     }
     c.obs4 = reinterpret_cast<const float4 *>(a.obstacles);
     c.M = a.M; c.wbase = warp * 32; c.seg_base = 0;
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
     for (int i = 0; i < L; i++) c.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
     c.hit[t] = kNoHit;
     if (t < L) c.radius[t] = RobotScalars<R>::radius(rb, t);
-    if (lane == 0) { c.tails[0] = 0; c.tails[1] = 0; c.tails[2] = 0; }
+    if (lane < 8) c.tails[lane] = 0;
     const int ground_included = rb->ground_included;
     __syncthreads();                                                       // radius[] is shared by the block; everything else is per warp
 
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
         }
         for (int off = 16; off > 0; off >>= 1) visited += __shfl_down_sync(0xffffffffu, visited, off);
         if (lane == 0 && visited) atomicAdd(a.pair_count, (unsigned long long)visited);
+        if (lane >= 1 && lane <= 3 && c.tails[3 + lane]) atomicAdd(a.pair_count + lane, (unsigned long long)c.tails[3 + lane]);
     }
     if (!live) return;
     R d_c = c.max_dist;

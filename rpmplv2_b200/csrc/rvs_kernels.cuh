@@ -235,27 +235,20 @@ __global__ void __launch_bounds__(kBlock) edge_valid_kernel(const KArgs a) {
 }
 
 // ---- computeDistanceUnderestimation (RealVectorSpace.cpp:402-446) ----------------------------------------------------------
-template <class F, class R>
-__global__ void __launch_bounds__(kBlock) underestimation_kernel(const KArgs a) {
-    const RobotDev *__restrict__ rb = a.robot;
-    const int L = rb->n;
-    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-    if (cfg >= a.N) return;
-    const R max_dist = R(a.max_dist);
-    R sk[3 * (kMaxDofs + 1)];
-    fk_skeleton<F, R>(rb, a.q + cfg * L, sk);
-    const int root = a.plane_idx ? a.plane_idx[cfg] : 0;
-    const float *__restrict__ planes = a.planes + size_t(root) * size_t(a.M) * size_t(L) * 6;
+// planes: [M][L][6] = (R, O) per (obstacle, link); prof[L] receives the per-link distance-to-planes (unspecified when
+// rejected). Returns d_c; rejected = a plane distance < 0 (the reference returns 0 and leaves the state untouched, :428-429).
+template <class R>
+__device__ __forceinline__ R underestimation_of(const RobotDev *__restrict__ rb, int L, int M, const R *sk, const float *__restrict__ planes,
+                                                R max_dist, R *prof, bool &rejected) {
     R d_c = max_dist;
-    bool rejected = false;
-    R *prof = static_cast<R *>(a.profile) + cfg * L;
+    rejected = false;
 #pragma unroll 1
     for (int i = 0; i < L && !rejected; i++) {
         const V3<R> A = {sk[3 * i], sk[3 * i + 1], sk[3 * i + 2]}, B = {sk[3 * i + 3], sk[3 * i + 4], sk[3 * i + 5]};
         const R radius = RobotScalars<R>::radius(rb, i);
         R best = max_dist;
 #pragma unroll 1
-        for (int j = 0; j < a.M; j++) {
+        for (int j = 0; j < M; j++) {
             const float2 *src = reinterpret_cast<const float2 *>(planes + (size_t(j) * L + i) * 6);
             const float2 w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
             const V3<R> Rp = {R(w0.x), R(w0.y), R(w1.x)}, Op = {R(w1.y), R(w2.x), R(w2.y)};
@@ -270,12 +263,30 @@ __global__ void __launch_bounds__(kBlock) underestimation_kernel(const KArgs a) 
             if (d < R(0)) { rejected = true; break; }
             if (d < best) best = d;
         }
-        if (a.profile) prof[i] = best;
+        prof[i] = best;
         if (best < d_c) d_c = best;
     }
-    static_cast<R *>(a.d_c)[cfg] = rejected ? R(0) : d_c;
+    return rejected ? R(0) : d_c;
+}
+
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) underestimation_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n;
+    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (cfg >= a.N) return;
+    R sk[3 * (kMaxDofs + 1)];
+    R prof[kMaxDofs];
+    fk_skeleton<F, R>(rb, a.q + cfg * L, sk);
+    const int root = a.plane_idx ? a.plane_idx[cfg] : 0;
+    bool rejected;
+    const R d_c = underestimation_of<R>(rb, L, a.M, sk, a.planes + size_t(root) * size_t(a.M) * size_t(L) * 6, R(a.max_dist), prof, rejected);
+    static_cast<R *>(a.d_c)[cfg] = d_c;
     if (a.status) a.status[cfg] = rejected ? 1 : 0;
-    if (rejected && a.profile) for (int i = 0; i < L; i++) prof[i] = R(0);
+    if (a.profile) {
+        R *out = static_cast<R *>(a.profile) + cfg * L;
+        for (int i = 0; i < L; i++) out[i] = rejected ? R(0) : prof[i];
+    }
 }
 
 // ---- skeleton / enclosing radii / xArm6 capsule self-collision ---------------------------------------------------------
@@ -415,6 +426,111 @@ __global__ void __launch_bounds__(kBlock) primitive_kernel(const KArgs a) {
     }
 }
 
+
+// ---- generalized-bur spines (RBTConnect::extendSpine, RBTConnect.cpp:85-150; RGBTConnect::extendGenSpine, RGBTConnect.cpp:73-92) ----
+// One thread per target configuration q_e; all spines start at the same root (its profile, d_c and nearest-point planes come
+// from one FULL distance query). Self-collision truncation (RBTConnect.cpp:129-131) is not applied: it is `false` for every
+// robot but xArm6, whose check ends in an FCL mesh test that is outside this engine.
+
+// a.dot(b) of dynamic Eigen vectors: SSE2 linear-vectorised reduction order (packets of 4, two accumulators, predux =
+// (l0+l2)+(l1+l3), scalar tail) — the same assumption as coord_norm above. a is read with a stride (a matrix column).
+__device__ __forceinline__ float dot_dyn(const float *a, int stride, const float *b, int n) {
+    const int aligned = (n / 4) * 4, aligned2 = (n / 8) * 8;
+    auto pr = [&](int i) { return a[i * stride] * b[i]; };
+    float res;
+    if (aligned) {
+        float p0[4], p1[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) p0[l] = pr(l);
+        if (aligned > 4) {
+#pragma unroll
+            for (int l = 0; l < 4; l++) p1[l] = pr(4 + l);
+            for (int idx = 8; idx < aligned2; idx += 8) {
+#pragma unroll
+                for (int l = 0; l < 4; l++) { p0[l] = p0[l] + pr(idx + l); p1[l] = p1[l] + pr(idx + 4 + l); }
+            }
+#pragma unroll
+            for (int l = 0; l < 4; l++) p0[l] = p0[l] + p1[l];
+            if (aligned > aligned2) {
+#pragma unroll
+                for (int l = 0; l < 4; l++) p0[l] = p0[l] + pr(aligned2 + l);
+            }
+        }
+        res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+        for (int i = aligned; i < n; i++) res = res + pr(i);
+    } else {
+        res = pr(0);
+        for (int i = 1; i < n; i++) res = res + pr(i);
+    }
+    return res;
+}
+
+template <class F>
+__global__ void __launch_bounds__(64) spine_kernel(const SpineArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n, L = n, W = n + 1;
+    const int s = blockIdx.x * 64 + threadIdx.x;
+    if (s >= a.S) return;
+    const float *q_e = a.q_targets + size_t(s) * n;
+    float *q_out = a.q_reached + size_t(s) * n;
+    float q_cur[kMaxDofs], q_new[kMaxDofs], prof_cur[kMaxDofs], prof_new[kMaxDofs], delta[kMaxDofs], rho_profile[kMaxDofs];
+    float sk[3 * (kMaxDofs + 1)], sk_new[3 * (kMaxDofs + 1)];
+    float Rm[kMaxDofs * (kMaxDofs + 1)];
+    for (int i = 0; i < n; i++) { q_cur[i] = a.q_root[i]; q_new[i] = a.q_root[i]; prof_cur[i] = a.root_profile[i]; }
+    float dc_cur = a.root_d_c, d_out = a.root_d_c;
+    int status = 2;                                                     // Trapped when the root itself has no clearance (:91-92)
+    if (a.root_d_c > 0.f) {
+        status = 0;
+        for (int layer = 0; layer < a.num_layers; layer++) {
+            // ---- extendSpine(q_cur, q_e)
+            status = 1;
+            fk_skeleton<F, float>(rb, q_cur, sk);
+            float rho = 0.f;
+            for (int i = 0; i < L; i++) rho_profile[i] = 0.f;
+            float q_temp[kMaxDofs];
+            for (int i = 0; i < n; i++) q_temp[i] = q_cur[i];
+            for (int counter = 1;; counter++) {
+                if (counter == 1) enclosing_radii_of<float>(rb, sk, Rm);
+                else { fk_skeleton<F, float>(rb, q_temp, sk_new); enclosing_radii_of<float>(rb, sk_new, Rm); }
+                for (int i = 0; i < n; i++) delta[i] = fabsf(q_e[i] - q_temp[i]);
+                float step;
+                if (a.use_expanded_bubble) {
+                    step = __int_as_float(0x7f800000);
+                    for (int i = 0; i < n; i++) {
+                        const float v = (prof_cur[i] - rho_profile[i]) / dot_dyn(Rm + (i + 1), W, delta, n);
+                        if (v < step) step = v;                       // std::min(step, v)
+                    }
+                } else
+                    step = (dc_cur - rho) / dot_dyn(Rm + n, W, delta, n);
+                if (step > 1.f) {
+                    for (int i = 0; i < n; i++) q_new[i] = q_e[i];
+                    status = 3;
+                } else
+                    for (int i = 0; i < n; i++) q_new[i] = q_temp[i] + step * (q_e[i] - q_temp[i]);
+                if (counter == a.num_iter_spine || status != 1) break;
+                fk_skeleton<F, float>(rb, q_new, sk_new);
+                float rho_k_prev = 0.f;
+                for (int k = 1; k <= L; k++) {
+                    const float rho_k = sqrtf(sqD(sk[3 * k] - sk_new[3 * k], sk[3 * k + 1] - sk_new[3 * k + 1], sk[3 * k + 2] - sk_new[3 * k + 2]));
+                    rho_profile[k - 1] = rho_k_prev < rho_k ? rho_k : rho_k_prev;      // std::max(rho_k_prev, rho_k)
+                    rho_k_prev = rho_k;
+                    rho = rho < rho_k ? rho_k : rho;
+                }
+                for (int i = 0; i < n; i++) q_temp[i] = q_new[i];
+            }
+            // ---- distance-to-planes of the new state w.r.t. the ROOT's nearest points (RGBTConnect.cpp:86-88)
+            fk_skeleton<F, float>(rb, q_new, sk_new);
+            bool rejected;
+            d_out = underestimation_of<float>(rb, L, a.M, sk_new, a.root_planes, a.max_dist, prof_new, rejected);
+            if (d_out < a.d_crit || status != 1) break;
+            for (int i = 0; i < n; i++) { q_cur[i] = q_new[i]; prof_cur[i] = prof_new[i]; }
+            dc_cur = d_out;
+        }
+    }
+    for (int i = 0; i < n; i++) q_out[i] = q_new[i];
+    a.d_c_reached[s] = d_out;
+    a.status[s] = uint8_t(status);
+}
 
 // ---- roofline denominators: register-only FMA microbenchmark (FFMA / DFMA issue peak of this device) ---------------------------
 #ifdef RVS_VARIANT_EXACT

@@ -17,6 +17,7 @@ struct LaunchTable {
     LaunchFn enclosing_radii;
     LaunchFn self_collision;
     LaunchFn primitive;
+    cudaError_t (*spines)(const SpineArgs &, cudaStream_t);
 };
 
 LaunchTable launch_table_ref32();    // FK FP64, geometry FP32, no FMA contraction, IEEE div/sqrt

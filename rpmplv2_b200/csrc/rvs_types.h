@@ -72,4 +72,20 @@ struct KArgs {
     unsigned long long *pair_count;   // += pair queries the reference's loop would have visited (early exit respected)
 };
 
+// Arguments of the batched generalized-bur spine kernel (rvs_extend_spines).
+struct SpineArgs {
+    const RobotDev *robot;
+    int32_t M, S;
+    const float *q_root;          // [n]
+    const float *root_profile;    // [L]
+    float root_d_c;
+    const float *root_planes;     // [M][L][6]
+    const float *q_targets;       // [S][n]
+    int32_t num_layers, num_iter_spine, use_expanded_bubble;
+    float d_crit, max_dist;
+    float *q_reached;             // [S][n]
+    float *d_c_reached;           // [S]
+    uint8_t *status;              // [S]  base::State::Status: 1 Advanced, 2 Trapped, 3 Reached
+};
+
 }  // namespace rvs

@@ -74,7 +74,12 @@ struct Variant {
         primitive_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
-    static LaunchTable table() { return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive}; }
+    static cudaError_t spines(const SpineArgs &a, cudaStream_t st) {
+        if (a.S <= 0) return cudaSuccess;
+        spine_kernel<F><<<grid_for(a.S, 64), 64, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static LaunchTable table() { return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines}; }
 };
 
 }  // namespace

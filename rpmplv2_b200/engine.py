@@ -36,6 +36,7 @@ SYMBOLS = {
     "rvs_launch_count": (ctypes.c_int64, [_H]),
     "rvs_measure_fma_peak": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_double)]),
     "rvs_pair_count": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]),
+    "rvs_work_stats": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]),
     "rvs_set_obstacles": (ctypes.c_int, [_H, c_f32p, c_f32p, c_u8p, c_f32p, ctypes.c_int32]),
     "rvs_update_obstacle_aabbs": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int32]),
     "rvs_num_obstacles": (ctypes.c_int, [_H]),
@@ -152,6 +153,12 @@ class Engine:
         self._check(self._lib.rvs_pair_count(self._h, 1 if reset else 0, ctypes.byref(v)))
         return int(v.value)
 
+    def work_stats(self, reset: bool = False) -> dict:
+        """Reference-order pair queries and what the work-queue kernel executed for them (rvs_work_stats)."""
+        v = (ctypes.c_uint64 * 4)()
+        self._check(self._lib.rvs_work_stats(self._h, 1 if reset else 0, v))
+        return {"pair_queries": int(v[0]), "scan_survivors": int(v[1]), "classified": int(v[2]), "edges": int(v[3])}
+
     def measure_fma_peak(self, fp64: bool = False) -> float:
         """FFMA / DFMA issue peak of this device in TFLOP/s (register-only microbenchmark)."""
         v = ctypes.c_double(0)
@@ -229,6 +236,17 @@ class Engine:
         out = np.empty((q.shape[0], self.n, self.n + 1), np.float32)
         self._check(self._lib.rvs_enclosing_radii(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_f32p)))
         return out
+
+    def extend_spines(self, q_root, root_profile, root_d_c: float, root_planes, q_targets, spine_params: Optional[RvsSpineParams] = None):
+        """Generalized-bur spines from one root towards S targets (rvs_extend_spines). Returns (q_reached[S,n], d_c[S], status[S])."""
+        sp = spine_params or RvsSpineParams(5, 1, 1, 0.05)
+        q_root, root_profile = _f32(q_root, (self.n,)), _f32(root_profile, (self.n,))
+        q_targets, root_planes = _f32(q_targets, (-1, self.n)), _f32(root_planes)
+        S = q_targets.shape[0]
+        q_out, d_out, status = np.empty((S, self.n), np.float32), np.empty(S, np.float32), np.empty(S, np.uint8)
+        self._check(self._lib.rvs_extend_spines(self._h, _p(q_root, c_f32p), _p(root_profile, c_f32p), ctypes.c_float(root_d_c), _p(root_planes, c_f32p),
+                                                _p(q_targets, c_f32p), S, ctypes.byref(sp), _p(q_out, c_f32p), _p(d_out, c_f32p), _p(status, c_u8p)))
+        return q_out, d_out, status
 
     def self_collision_capsules(self, q) -> np.ndarray:
         q = _f32(q, (-1, self.n))
