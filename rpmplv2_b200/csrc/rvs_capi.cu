@@ -7,6 +7,7 @@
 #include <cstring>
 #include <algorithm>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "rvs_launch.h"
@@ -35,7 +36,7 @@ struct rvs_engine {
     RobotDev *d_robot = nullptr;
     ObstacleRec *d_obs = nullptr;
     int M = 0, obs_cap = 0;
-    std::vector<ObstacleRec> h_obs;
+    std::vector<ObstacleRec> h_obs, h_obs_scan;
     LaunchTable lt{};
     DevBuf buf[8];            // grow-only device staging for the host-pointer entry points
     int64_t launches = 0;
@@ -102,7 +103,7 @@ int check_params(rvs_engine *h, const rvs_params *p) {
 
 KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
     KArgs a{};
-    a.robot = h->d_robot; a.obstacles = h->d_obs; a.M = h->M; a.N = N; a.q = d_q;
+    a.robot = h->d_robot; a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.M = h->M; a.N = N; a.q = d_q;
     a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
     a.num_checks = h->prm.num_interpolation_validity_checks; a.cull = h->cull;
     a.robot_n_hint = h->h_robot.n;
@@ -330,9 +331,40 @@ int rvs_work_stats(rvs_handle h, int32_t reset, uint64_t *out4) {
     return RVS_OK;
 }
 
+// Uploads the table twice: [0, M) in the caller's order (what every kernel indexes results by) and [cap, cap + M) in SCAN ORDER for
+// the work-queue distance kernel: nearest to the robot base first, so that the per-link minima — and with them the broad-phase
+// thresholds — tighten after a few obstacles. Scan-order records carry their original index in flags bits 8..31.
+namespace {
+int upload_obstacles(rvs_engine *h) {
+    const int M = h->M;
+    if (!M) return RVS_OK;
+    const double bx = h->h_robot.xyz[0][0], by = h->h_robot.xyz[0][1], bz = h->h_robot.xyz[0][2];
+    std::vector<std::pair<double, int>> order;
+    order.resize(size_t(M));
+    for (int j = 0; j < M; j++) {
+        const ObstacleRec &o = h->h_obs[size_t(j)];
+        const double gx = std::max(std::max(double(o.lo[0]) - bx, bx - double(o.hi[0])), 0.0), gy = std::max(std::max(double(o.lo[1]) - by, by - double(o.hi[1])), 0.0),
+                     gz = std::max(std::max(double(o.lo[2]) - bz, bz - double(o.hi[2])), 0.0);
+        const double d2 = gx * gx + gy * gy + gz * gz;
+        order[size_t(j)] = {d2 == d2 ? d2 : 1e300, j};
+    }
+    std::stable_sort(order.begin(), order.end());
+    h->h_obs_scan.resize(size_t(M));
+    for (int k = 0; k < M; k++) {
+        ObstacleRec r = h->h_obs[size_t(order[size_t(k)].second)];
+        r.flags = (r.flags & 1u) | (uint32_t(order[size_t(k)].second) << 8);
+        h->h_obs_scan[size_t(k)] = r;
+    }
+    RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + h->obs_cap, h->h_obs_scan.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+}  // namespace
+
 int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max, const uint8_t *is_ground, const float *min_dist_tol, int32_t M) {
     RVS_TRY(enter(h));
-    if (M < 0 || (M > 0 && (!aabb_min || !aabb_max))) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad obstacle arrays");
+    if (M < 0 || M >= (1 << 24) || (M > 0 && (!aabb_min || !aabb_max))) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad obstacle arrays (0 <= M < 2^24)");
     h->h_obs.resize(size_t(M));
     for (int j = 0; j < M; j++) {
         ObstacleRec &o = h->h_obs[size_t(j)];
@@ -347,13 +379,11 @@ int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max
         if (h->d_obs) RVS_CUDA(h, cudaFree(h->d_obs));
         h->d_obs = nullptr; h->obs_cap = 0;
         const int cap = M + M / 2 + 16;
-        RVS_CUDA(h, cudaMalloc(&h->d_obs, size_t(cap) * sizeof(ObstacleRec)));
+        RVS_CUDA(h, cudaMalloc(&h->d_obs, 2 * size_t(cap) * sizeof(ObstacleRec)));
         h->obs_cap = cap;
     }
     h->M = M;
-    if (M) RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return upload_obstacles(h);
 }
 
 int rvs_update_obstacle_aabbs(rvs_handle h, const float *aabb_min, const float *aabb_max, int32_t M) {
@@ -363,9 +393,7 @@ int rvs_update_obstacle_aabbs(rvs_handle h, const float *aabb_min, const float *
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));       // the pinned-less host mirror is reused: wait for the last copy
     for (int j = 0; j < M; j++)
         for (int c = 0; c < 3; c++) { h->h_obs[size_t(j)].lo[c] = aabb_min[3 * j + c]; h->h_obs[size_t(j)].hi[c] = aabb_max[3 * j + c]; }
-    if (M) RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return upload_obstacles(h);
 }
 
 // ---- device-pointer entry points ---------------------------------------------------------------------------------

@@ -81,7 +81,7 @@ __host__ __device__ inline size_t wq_smem_bytes(int L) {
 
 template <class R>
 struct WqCtx {
-    const float4 *obs4;                       // obstacle table in HBM as pairs of 16-byte words (read through L1)
+    const float4 *obs4;                       // scan-ordered obstacle table in HBM as pairs of 16-byte words (read through L1)
     R *skel;                                  // [3*(L+1)][kWqStride]
     typename WqBits<R>::type *best;           // [L][kWqStride]
     R *radius;                                // [L]
@@ -129,48 +129,56 @@ __device__ __forceinline__ void wq_merge(const WqCtx<R> &c, int t, int link, uns
     else if (d > R(0)) atomicMin(&c.best[link * kWqStride + t], WqBits<R>::to(d));
 }
 
+// entry -> configuration slot, link, capsule axis, obstacle box / tolerance and the pair's key in REFERENCE order
+// (link-major, obstacle index in the caller's order: the scan table is sorted, its records carry the original index)
 template <class R>
-__device__ __forceinline__ void wq_load_pair(const WqCtx<R> &c, int t, int link, int j, V3<R> &A, V3<R> &B, Box<R> &bx, R &tol) {
-    const R *sk = c.skel + (3 * link) * kWqStride + t;
-    A = {sk[0], sk[kWqStride], sk[2 * kWqStride]};
-    B = {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]};
+struct WqPair {
+    int t, link;
+    unsigned key;
+    V3<R> A, B;
+    Box<R> bx;
+    R tol;
+};
+template <class R>
+__device__ __forceinline__ WqPair<R> wq_load_pair(const WqCtx<R> &c, unsigned e) {
+    WqPair<R> p;
+    p.t = c.wbase + int(e & 31u);
+    p.link = int((e >> 5) & 31u);
+    const int j = c.seg_base + int((e >> 10) & 0xFFFFu);
+    const R *sk = c.skel + (3 * p.link) * kWqStride + p.t;
+    p.A = {sk[0], sk[kWqStride], sk[2 * kWqStride]};
+    p.B = {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]};
     const float4 w0 = __ldg(c.obs4 + 2 * j), w1 = __ldg(c.obs4 + 2 * j + 1);
-    bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
-    tol = R(w1.z);
+    p.bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
+    p.tol = R(w1.z);
+    p.key = unsigned(p.link) * unsigned(c.M) + (__float_as_uint(w1.w) >> 8);
+    return p;
 }
-
-#define RVS_WQ_DECODE(e)                                                                                  \
-    const int t = c.wbase + int((e) & 31u), link = int(((e) >> 5) & 31u), j = c.seg_base + int(((e) >> 10) & 0xFFFFu); \
-    const unsigned key = unsigned(link) * unsigned(c.M) + unsigned(j)
 
 // phase B1: does this pair still matter?  Euclidean gap between the segment's bounding box and the obstacle against the
 // CURRENT minimum of its link (the scan used the Chebyshev gap and a possibly older minimum).
 template <class R>
 __device__ __forceinline__ bool wq_recull(const WqCtx<R> &c, unsigned e) {
-    RVS_WQ_DECODE(e);
-    if (key > c.hit[t]) return false;                                      // an earlier pair (reference order) already collides
-    V3<R> A, B; Box<R> bx; R tol;
-    wq_load_pair(c, t, link, j, A, B, bx, tol);
-    const R thr = wq_threshold(WqBits<R>::from(c.best[link * kWqStride + t]), c.radius[link], c.eq_thr);
-    const R gx = fmax(fmax(bx.lo.x - fmax(A.x, B.x), fmin(A.x, B.x) - bx.hi.x), R(0));
-    const R gy = fmax(fmax(bx.lo.y - fmax(A.y, B.y), fmin(A.y, B.y) - bx.hi.y), R(0));
-    const R gz = fmax(fmax(bx.lo.z - fmax(A.z, B.z), fmin(A.z, B.z) - bx.hi.z), R(0));
+    const WqPair<R> p = wq_load_pair(c, e);
+    if (p.key > c.hit[p.t]) return false;                                  // an earlier pair (reference order) already collides
+    const R thr = wq_threshold(WqBits<R>::from(c.best[p.link * kWqStride + p.t]), c.radius[p.link], c.eq_thr);
+    const R gx = fmax(fmax(p.bx.lo.x - fmax(p.A.x, p.B.x), fmin(p.A.x, p.B.x) - p.bx.hi.x), R(0));
+    const R gy = fmax(fmax(p.bx.lo.y - fmax(p.A.y, p.B.y), fmin(p.A.y, p.B.y) - p.bx.hi.y), R(0));
+    const R gz = fmax(fmax(p.bx.lo.z - fmax(p.A.z, p.B.z), fmin(p.A.z, p.B.z) - p.bx.hi.z), R(0));
     return !(gx * gx + gy * gy + gz * gz > thr * thr);
 }
 
 // phase B2: one surviving pair through the reference's classification
 template <class R>
 __device__ __forceinline__ void wq_classify(const WqCtx<R> &c, unsigned e) {
-    RVS_WQ_DECODE(e);
-    if (key > c.hit[t]) return;
-    V3<R> A, B; Box<R> bx; R tol;
-    wq_load_pair(c, t, link, j, A, B, bx, tol);
+    const WqPair<R> p = wq_load_pair(c, e);
+    if (p.key > c.hit[p.t]) return;
     Capsule<R> cp;
-    cp.set(A, B, c.radius[link], R(0));
+    cp.set(p.A, p.B, c.radius[p.link], R(0));
     V3<R> u, v;
-    const PairPlan<R> pl = classify_pair<R, false>(cp, bx, c.eq_thr, c.max_dist, u, v);
-    if (pl.done) { wq_merge(c, t, link, key, pl.d, tol); return; }
-    wq_merge(c, t, link, key, pl.d - cp.radius, tol);                      // face distance (2a) or MAX_DISTANCE (2b)
+    const PairPlan<R> pl = classify_pair<R, false>(cp, p.bx, c.eq_thr, c.max_dist, u, v);
+    if (pl.done) { wq_merge(c, p.t, p.link, p.key, pl.d, p.tol); return; }
+    wq_merge(c, p.t, p.link, p.key, pl.d - cp.radius, p.tol);              // face distance (2a) or MAX_DISTANCE (2b)
     const unsigned pos = atomicAdd(const_cast<unsigned *>(&c.tails[2]), unsigned(pl.count));
 #pragma unroll 1
     for (int k = 0; k < pl.count; k++) c.q2[pos + k] = (e & 0x3FFFFFFu) | (plan_edge(pl, k) << 26);
@@ -179,15 +187,13 @@ __device__ __forceinline__ void wq_classify(const WqCtx<R> &c, unsigned e) {
 // phase C: one box edge of one pair
 template <class R>
 __device__ __forceinline__ void wq_edge(const WqCtx<R> &c, unsigned e) {
-    RVS_WQ_DECODE(e);
-    if (key > c.hit[t]) return;
-    V3<R> A, B; Box<R> bx; R tol;
-    wq_load_pair(c, t, link, j, A, B, bx, tol);
+    const WqPair<R> p = wq_load_pair(c, e);
+    if (p.key > c.hit[p.t]) return;
     Capsule<R> cp;
-    cp.set(A, B, c.radius[link], R(0));
+    cp.set(p.A, p.B, c.radius[p.link], R(0));
     V3<R> u, v;
-    const R de = plan_edge_distance<R, false>(cp, bx, e >> 26, c.eq_thr, c.max_dist, u, v);
-    wq_merge(c, t, link, key, de <= R(0) ? R(0) - cp.radius : de - cp.radius, tol);     // Q14: a touching edge gives -radius
+    const R de = plan_edge_distance<R, false>(cp, p.bx, e >> 26, c.eq_thr, c.max_dist, u, v);
+    wq_merge(c, p.t, p.link, p.key, de <= R(0) ? R(0) - cp.radius : de - cp.radius, p.tol);     // Q14: a touching edge gives -radius
 }
 
 // pop up to 32 entries from the top of a queue (warp-uniform); lanes beyond the count get kNoEntry
@@ -243,7 +249,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
         unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * WqCaps<G>::words;
         c.tails = wq; c.q1 = wq + 8; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
     }
-    c.obs4 = reinterpret_cast<const float4 *>(a.obstacles);
+    c.obs4 = reinterpret_cast<const float4 *>(a.obstacles_scan);
     c.M = a.M; c.wbase = warp * 32; c.seg_base = 0;
     c.eq_thr = R(a.eq_thr); c.max_dist = R(a.max_dist);
 
@@ -291,8 +297,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                         for (int k = 0; k < 3; k++) { lo[l][k] = wq_inf<R>(); hi[l][k] = -wq_inf<R>(); }          // overlaps nothing
                     }
                 }
-                // the minima settle quickly: refresh after 32, 64, 128, ... obstacles
-                const int jend = min(j0 + (j0 < 32 ? 32 : j0), count);
+                // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, ... obstacles
+                const int jend = min(j0 + (j0 < 4 ? 4 : j0), count);
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {
                     // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags) of two obstacles: warp-uniform 16-byte loads

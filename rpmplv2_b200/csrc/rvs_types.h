@@ -45,7 +45,8 @@ struct RobotDev {
 // Arguments of the hot-path kernels (passed by value).
 struct KArgs {
     const RobotDev *robot;
-    const ObstacleRec *obstacles;
+    const ObstacleRec *obstacles;        // caller's order
+    const ObstacleRec *obstacles_scan;   // nearest-to-base first; flags bits 8..31 = index in the caller's order (work-queue kernel only)
     int32_t M;
     int64_t N;
     const float *q;          // N x n
