@@ -31,6 +31,8 @@ struct rvs_engine {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;   // copy streams + second compute stream of the pipelined host-pointer distance path (lazy)
+    cudaEvent_t ev_in[8] = {}, ev_k[8] = {}, ev_done = nullptr;
     rvs_params prm{};
     RobotDev h_robot{};
     RobotDev *d_robot = nullptr;
@@ -136,7 +138,8 @@ int d2h(rvs_engine *h, void *dst, int which, size_t bytes) {
     return RVS_OK;
 }
 
-int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, void *d_dc, void *d_prof, void *d_near, bool want_f64) {
+int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, void *d_dc, void *d_prof, void *d_near, bool want_f64,
+                      cudaStream_t on = nullptr) {
     if ((h->prm.precision == RVS_PREC_F64) != want_f64)
         return fail(h, RVS_ERR_INVALID_ARGUMENT, want_f64 ? "handle was not created with RVS_PREC_F64" : "RVS_PREC_F64 handles use the *_f64 entry points");
     if (N < 0 || mode < RVS_DIST_MIN || mode > RVS_DIST_FULL) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or mode");
@@ -145,9 +148,26 @@ int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, 
         return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer for the requested distance mode");
     KArgs a = base_args(h, d_q, N);
     a.mode = mode; a.d_c = d_dc; a.profile = d_prof; a.nearest = d_near;
-    return launched(h, h->lt.distance(a, h->stream), "distance kernel launch");
+    return launched(h, h->lt.distance(a, on ? on : h->stream), "distance kernel launch");
 }
 
+int pipeline_ready(rvs_engine *h) {
+    if (h->s_in) return RVS_OK;
+    RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_k2, cudaStreamNonBlocking));
+    for (int k = 0; k < 8; k++) {
+        RVS_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
+        RVS_CUDA(h, cudaEventCreateWithFlags(&h->ev_k[k], cudaEventDisableTiming));
+    }
+    RVS_CUDA(h, cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+    return RVS_OK;
+}
+
+// Host-pointer computeDistance. Large MIN/PROFILE batches are cut into up to 8 chunks and pipelined over three streams
+// (H2D of chunk c+1 and D2H of chunk c-1 overlap the kernel of chunk c; consecutive kernels alternate between two compute
+// streams so that the last partial wave of one overlaps the first wave of the next); pinned host buffers give full overlap,
+// pageable ones still work. Small batches and FULL mode (whose output dwarfs everything else) take the single-shot path.
 int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, void *d_c, void *profile, void *nearest, bool want_f64) {
     RVS_TRY(enter(h));
     if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
@@ -156,14 +176,48 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     const size_t rs = want_f64 ? sizeof(double) : sizeof(float);
     const size_t n = size_t(h->h_robot.n), L = n;
     const size_t near_bytes = mode == RVS_DIST_FULL ? size_t(N) * size_t(h->M) * L * 6 * rs : 0;
-    RVS_TRY(h2d(h, B_Q, q, size_t(N) * n * sizeof(float)));
+    RVS_TRY(reserve(h, B_Q, size_t(N) * n * sizeof(float)));
     RVS_TRY(reserve(h, B_DC, size_t(N) * rs));
     RVS_TRY(reserve(h, B_PROF, size_t(N) * L * rs));
     RVS_TRY(reserve(h, B_NEAR, near_bytes));
-    RVS_TRY(distance_dev_impl(h, static_cast<const float *>(h->buf[B_Q].p), N, mode, h->buf[B_DC].p, h->buf[B_PROF].p, h->buf[B_NEAR].p, want_f64));
-    RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * rs));
-    if (mode >= RVS_DIST_PROFILE) RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * L * rs));
-    if (mode == RVS_DIST_FULL) RVS_TRY(d2h(h, nearest, B_NEAR, near_bytes));
+    float *dq = static_cast<float *>(h->buf[B_Q].p);
+    char *ddc = static_cast<char *>(h->buf[B_DC].p), *dprof = static_cast<char *>(h->buf[B_PROF].p);
+    constexpr int64_t kMinChunk = 1 << 16;
+    const int chunks = mode == RVS_DIST_FULL ? 1 : int(std::min<int64_t>(8, N / kMinChunk));
+    if (chunks < 2) {
+        RVS_CUDA(h, cudaMemcpyAsync(dq, q, size_t(N) * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        RVS_TRY(distance_dev_impl(h, dq, N, mode, ddc, dprof, h->buf[B_NEAR].p, want_f64));
+        RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * rs));
+        if (mode >= RVS_DIST_PROFILE) RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * L * rs));
+        if (mode == RVS_DIST_FULL) RVS_TRY(d2h(h, nearest, B_NEAR, near_bytes));
+        RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+        return RVS_OK;
+    }
+    if (mode >= RVS_DIST_PROFILE && !profile) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL profile buffer");
+    RVS_TRY(pipeline_ready(h));
+    RVS_CUDA(h, cudaEventRecord(h->ev_done, h->stream));                 // order the copy streams after earlier work on the handle
+    RVS_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
+    RVS_CUDA(h, cudaStreamWaitEvent(h->s_k2, h->ev_done, 0));
+    const int64_t per = ((N + chunks - 1) / chunks + 127) & ~int64_t(127);
+    int used = 0;
+    for (int c = 0; c < chunks; c++) {
+        const int64_t first = int64_t(c) * per, cnt = std::min(per, N - first);
+        if (cnt <= 0) break;
+        used = c + 1;
+        RVS_CUDA(h, cudaMemcpyAsync(dq + first * n, q + first * n, size_t(cnt) * n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
+        RVS_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
+        cudaStream_t sk = (c & 1) ? h->s_k2 : h->stream;
+        RVS_CUDA(h, cudaStreamWaitEvent(sk, h->ev_in[c], 0));
+        RVS_TRY(distance_dev_impl(h, dq + first * n, cnt, mode, ddc + first * rs, dprof + first * L * rs, nullptr, want_f64, sk));
+        RVS_CUDA(h, cudaEventRecord(h->ev_k[c], sk));
+        RVS_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
+        RVS_CUDA(h, cudaMemcpyAsync(static_cast<char *>(d_c) + first * rs, ddc + first * rs, size_t(cnt) * rs, cudaMemcpyDeviceToHost, h->s_out));
+        if (mode >= RVS_DIST_PROFILE)
+            RVS_CUDA(h, cudaMemcpyAsync(static_cast<char *>(profile) + first * L * rs, dprof + first * L * rs, size_t(cnt) * L * rs, cudaMemcpyDeviceToHost, h->s_out));
+    }
+    (void)used;
+    RVS_CUDA(h, cudaStreamSynchronize(h->s_out));
+    RVS_CUDA(h, cudaStreamSynchronize(h->s_k2));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
     return RVS_OK;
 }

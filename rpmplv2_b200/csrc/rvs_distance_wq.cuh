@@ -303,7 +303,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                 for (int j = j0; j < jend; j += kWqUnroll) {
                     // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags) of two obstacles: warp-uniform 16-byte loads
                     const int j1 = j + 1 < jend ? j + 1 : j;
-                    const float4 w0 = __ldg(o4 + 2 * j), w1 = __ldg(o4 + 2 * j + 1), v0 = __ldg(o4 + 2 * j1), v1 = __ldg(o4 + 2 * j1 + 1);
+                    const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
+                    const float4 w0 = __ldg(pj), w1 = __ldg(pj + 1), v0 = __ldg(pj1), v1 = __ldg(pj1 + 1);
                     unsigned mask = 0;
 #pragma unroll
                     for (int l = 0; l < G; l++) {
