@@ -40,7 +40,8 @@ FLOP_PER_PAIR, FLOP_FK = 150.0, 630.0          # counting convention C1 (SURVEY.
 # what the work-queue kernel executes per unit: 6 compares per scanned pair, ~25 flop per re-culled pair,
 # ~60 per classified pair, 150 per segment-edge evaluation
 FLOP_SCAN, FLOP_RECULL, FLOP_CLASSIFY, FLOP_EDGE = 6.0, 25.0, 60.0, 150.0
-NCU_TRAFFIC_BYTES = None                       # dram__bytes_read+write of one launch from profiles/ (filled in when a capture exists)
+NCU_TRAFFIC_BYTES = 25_361_920 + 38_656        # dram__bytes_read.sum + dram__bytes_write.sum of one launch (ncu --set full, profiles/r1i_*):
+                                               # the configurations are read once; the 29 MB of results are still in the 126 MB L2 at kernel end
 
 
 def scene():
@@ -58,7 +59,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -142,7 +143,7 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="ref32", choices=["ref32", "fast32", "f64"])
