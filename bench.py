@@ -157,6 +157,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # libraries (NCCL's version banner, torch warnings) must not pollute stdout: the contract is ONE JSON line there.
+    # Everything written to fd 1 during the run goes to stderr; the JSON line is written to the real stdout at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from rpmplv2_b200 import engine
@@ -301,7 +307,8 @@ def main():
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(os.cpu_count() or 1)
             out["cpu_baseline_1thread"] = cpu_baseline(1, seconds_target=6.0)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,0 +1,177 @@
+// rvs_valid_wq.cuh — isValid(q) and isValid(q1,q2) (RealVectorSpace.cpp:261-309) as  scan -> warp work queue -> compacted predicate.
+//
+// The reference's predicate collisionCapsuleToBox (CollisionAndDistance.cpp:4-42) starts with a slab test: a pair is rejected when
+// both capsule endpoints lie beyond the box by more than the radius on one axis. The scan applies a slightly LOOSER version of that
+// test (link bounding box inflated by radius * 1.001 + margin, six predicate-chained compares per pair, lane = configuration, no
+// divergence); the ~1 % of pairs that survive are queued and evaluated with the exact reference predicate capsule_hits_box() — which
+// contains the exact slab test — by full warps (lane = queued pair of any configuration of the warp). A configuration is invalid as
+// soon as one of its pairs hits: the verdict is order free, so it is identical to the sequential kernel's.
+// EDGE = true: lane = one interpolated configuration of an edge (k = N..1, RealVectorSpace.cpp:267-269); verdict[edge] &= valid.
+#pragma once
+#include "rvs_distance_wq.cuh"
+
+namespace rvs {
+
+template <int G> struct VqCaps {
+    static constexpr int q1 = 32 * G * kWqUnroll + 32;
+    static constexpr int words = 4 + q1;
+};
+
+template <class R, int G>
+__host__ __device__ inline size_t vq_smem_bytes(int L) {
+    size_t b = size_t(3 * (L + 1)) * kWqStride * sizeof(R);               // skeleton
+    b += 2 * size_t(L) * sizeof(R);                                       // radius, radius * sqrt(3) / 3
+    b = (b + 15) & ~size_t(15);
+    b += size_t(kWqBlock) * sizeof(unsigned);                             // invalid flags
+    b += size_t(kWqWarps) * VqCaps<G>::words * sizeof(unsigned);
+    return b;
+}
+
+template <class F, class R, int G, bool EDGE>
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_kernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char vq_smem[];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n, n = L;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x, wbase = warp * 32;
+    unsigned char *p = vq_smem;
+    R *skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
+    R *radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
+    R *radius_in = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
+    p = vq_smem + ((size_t(p - vq_smem) + 15) & ~size_t(15));
+    unsigned *invalid = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
+    unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * VqCaps<G>::words;
+    volatile unsigned *tail = wq;
+    unsigned *q1 = wq + 4;
+    const float4 *obs4 = reinterpret_cast<const float4 *>(a.obstacles);
+    const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
+
+    const int64_t item = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
+    int64_t edge = 0;
+    bool live;
+    if (!EDGE) {
+        live = item < a.N;
+        if (live) fk_skeleton<F, R>(rb, a.q + item * n, skel + t, kWqStride);
+    } else {
+        edge = item / a.num_checks;
+        const int kidx = int(item - edge * a.num_checks);
+        live = edge < a.N;
+        if (live) {
+            const float *q1p = a.q + edge * n, *q2p = a.q2 + edge * n;
+            const float dist = coord_norm(q1p, q2p, n);
+            const float k = float(a.num_checks - kidx);                 // k = N .. 1
+            const float step = k / float(a.num_checks) * dist;
+            float qn[kMaxDofs];
+            if (dist > 0.f) {
+                const float f = step / dist;
+                for (int i = 0; i < n; i++) qn[i] = q1p[i] + (q2p[i] - q1p[i]) * f;
+            } else
+                for (int i = 0; i < n; i++) qn[i] = q2p[i];
+            fk_skeleton<F, R>(rb, qn, skel + t, kWqStride);
+        }
+    }
+    if (!live) for (int k = 0; k < 3 * (L + 1); k++) skel[k * kWqStride + t] = R(0);
+    invalid[t] = 0u;
+    if (t < L) { radius[t] = RobotScalars<R>::radius(rb, t); radius_in[t] = RobotScalars<R>::radius_in(rb, t); }
+    if (lane < 4) tail[lane] = 0;
+    const int ground_included = rb->ground_included;
+    __syncthreads();
+
+    // evaluate queued pairs with the exact reference predicate, one per lane
+    auto drain = [&](bool flush) {
+        for (;;) {
+            __syncwarp();
+            const unsigned have = tail[0];
+            if (!(have >= 32u || (flush && have > 0u))) break;
+            const unsigned cnt = have < 32u ? have : 32u, base = have - cnt;
+            const unsigned e = unsigned(lane) < cnt ? q1[base + lane] : kNoEntry;
+            __syncwarp();
+            if (lane == 0) tail[0] = base;
+            if (e != kNoEntry) {
+                const int tt = wbase + int(e & 31u), link = int((e >> 5) & 31u), j = int(e >> 10);
+                if (!invalid[tt]) {
+                    const R *sk = skel + (3 * link) * kWqStride + tt;
+                    Capsule<R> cp;
+                    cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, radius[link], radius_in[link]);
+                    const float4 w0 = __ldg(obs4 + 2 * j), w1 = __ldg(obs4 + 2 * j + 1);
+                    const Box<R> bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
+                    if (capsule_hits_box<R>(cp, bx, eq_thr, max_dist)) invalid[tt] = 1u;
+                }
+            }
+        }
+    };
+
+    constexpr int kSeg = 1 << 22;                                          // queue entries carry a 22-bit obstacle index
+    for (int base = 0; base < a.M; base += kSeg) {
+        const int count = min(kSeg, a.M - base);
+#pragma unroll 1
+        for (int g0 = 0; g0 < L; g0 += G) {
+            const int gskip = ground_included - g0;                       // links below ground_included ignore ground objects (:285-286)
+            const unsigned ground_keep1 = gskip <= 0 ? ~0u : (gskip >= G ? 0u : ~((1u << gskip) - 1u));
+            const unsigned ground_keep = (ground_keep1 & ((1u << G) - 1u)) * ((1u << G) + 1u);
+            R lo[G][3], hi[G][3];
+            auto refresh = [&]() {
+                const bool dead = !live || invalid[t] != 0u;
+#pragma unroll
+                for (int l = 0; l < G; l++) {
+                    const int i = g0 + l;
+                    if (!dead && i < L) {
+                        const R *sk = skel + (3 * i) * kWqStride + t;
+                        R mag = R(0);
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride]; mag = fmax(mag, fmax(fabs(u), fabs(v))); }
+                        const R thr = radius[i] * R(1.001) + R(1e-5) + R(4e-6) * mag;      // looser than the reference's `+- radius` slab
+#pragma unroll
+                        for (int k = 0; k < 3; k++) {
+                            const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride];
+                            lo[l][k] = fmin(u, v) - thr;
+                            hi[l][k] = fmax(u, v) + thr;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { lo[l][k] = wq_inf<R>(); hi[l][k] = -wq_inf<R>(); }
+                    }
+                }
+            };
+            const float4 *o4 = obs4 + 2 * size_t(base);
+#pragma unroll 1
+            for (int j0 = 0; j0 < count; j0 += 64) {
+                refresh();                                                  // picks up "already invalid" every 64 obstacles
+                const int jend = min(j0 + 64, count);
+#pragma unroll 1
+                for (int j = j0; j < jend; j += kWqUnroll) {
+                    const int j1 = j + 1 < jend ? j + 1 : j;
+                    const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
+                    const float4 w0 = __ldg(pj), w1 = __ldg(pj + 1), v0 = __ldg(pj1), v1 = __ldg(pj1 + 1);
+                    unsigned mask = 0;
+#pragma unroll
+                    for (int l = 0; l < G; l++) {
+                        wq_overlap<R>(mask, 1u << l, R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[l], hi[l]);
+                        wq_overlap<R>(mask, 1u << (G + l), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[l], hi[l]);
+                    }
+                    if (j1 == j) mask &= (1u << G) - 1u;
+                    if ((__float_as_uint(w1.w) | __float_as_uint(v1.w)) & 1u)
+                        mask &= ((__float_as_uint(w1.w) & 1u) ? (ground_keep | ~((1u << G) - 1u)) : ~0u) &
+                                ((__float_as_uint(v1.w) & 1u) ? (ground_keep | ((1u << G) - 1u)) : ~0u);
+                    if (mask) {
+                        unsigned pos = atomicAdd(const_cast<unsigned *>(&tail[0]), unsigned(__popc(mask)));
+                        do {
+                            const int b = __ffs(int(mask)) - 1;
+                            mask &= mask - 1u;
+                            const int l = b >= G ? b - G : b, jj = base + (b >= G ? j1 : j);
+                            q1[pos++] = unsigned(lane) | (unsigned(g0 + l) << 5) | (unsigned(jj) << 10);
+                        } while (mask);
+                    }
+                    __syncwarp();
+                    if (tail[0] >= 32u) drain(false);
+                }
+            }
+        }
+    }
+    drain(true);
+    __syncwarp();
+    if (!live) return;
+    if (!EDGE) a.verdict[item] = invalid[t] ? 0 : 1;
+    else if (invalid[t]) a.verdict[edge] = 0;                             // verdict[] is pre-set to 1 by the host
+}
+
+}  // namespace rvs

@@ -4,6 +4,7 @@
 //   -DRVS_VARIANT_FAST   -fmad=true                                             -> FAST32 launch table
 #include "rvs_kernels.cuh"
 #include "rvs_distance_wq.cuh"
+#include "rvs_valid_wq.cuh"
 #include "rvs_launch.h"
 
 namespace rvs {
@@ -39,13 +40,28 @@ struct Variant {
         else distance_kernel<F, R, RVS_DIST_FULL><<<g, kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
+    template <int G, bool EDGE>
+    static cudaError_t valid_wq(const KArgs &a, int64_t items, cudaStream_t st) {
+        const size_t smem = vq_smem_bytes<R, G>(a.robot_n_hint);
+        static size_t configured = 0;
+        if (smem > configured) {
+            const cudaError_t e = cudaFuncSetAttribute(valid_wq_kernel<F, R, G, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+            if (e != cudaSuccess) return e;
+            configured = smem;
+        }
+        valid_wq_kernel<F, R, G, EDGE><<<grid_for(items, kWqBlock), kWqBlock, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     static cudaError_t is_valid(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (a.cull && a.M > 0 && a.M < (1 << 22)) return a.robot_n_hint <= 2 ? valid_wq<2, false>(a, a.N, st) : valid_wq<6, false>(a, a.N, st);
         is_valid_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t edge_valid(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (a.cull && a.M > 0 && a.M < (1 << 22))
+            return a.robot_n_hint <= 2 ? valid_wq<2, true>(a, a.N * a.num_checks, st) : valid_wq<6, true>(a, a.N * a.num_checks, st);
         edge_valid_kernel<F, R><<<grid_for(a.N * a.num_checks, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }

@@ -121,6 +121,29 @@ def test_work_queue_kernel_is_bit_identical_to_sequential_kernel(case, prec):
         assert n1 == n0
 
 
+@pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32, robots.PREC_F64])
+@pytest.mark.parametrize("case", ["xarm6_1000", "xarm6_2500_dense", "spatial22", "planar2"])
+def test_work_queue_validity_kernels_equal_sequential_kernels(case, prec):
+    """isValid(q) / isValid(q1,q2) through the scan + queue kernel (rvs_valid_wq.cuh) vs the one-thread-per-configuration kernels."""
+    if case == "xarm6_1000":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(1000, "D2", 0.7)
+    elif case == "xarm6_2500_dense":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(2500, "D1", 0.3)
+    elif case == "spatial22":
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 40)
+    else:
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    eng = make(rb, mn, mx, g, tol, prec)
+    q = synthetic.configs(rb, 30000)
+    q1, q2 = synthetic.edges(rb, 5000, 0.1)
+    eng.set_culling(True)
+    v1, e1 = eng.is_valid(q), eng.is_valid_edges(q1, q2)
+    eng.set_culling(False)
+    v0, e0 = eng.is_valid(q), eng.is_valid_edges(q1, q2)
+    assert (v1 == v0).all() and (e1 == e0).all()
+    assert case == "xarm6_2500_dense" or 0.02 < v0.mean() < 0.999
+
+
 def test_distance_full_nearest_points(ob):
     rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D1", 0.3)
     q = synthetic.configs(rb, 3000)
