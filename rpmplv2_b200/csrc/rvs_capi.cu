@@ -21,9 +21,13 @@ namespace {
 thread_local std::string g_create_error;
 
 struct DevBuf {
-    void *p = nullptr;
+    void *p = nullptr;        // where the current call finds this buffer: the device allocation, or a slice of the pinned arena
+    void *dev = nullptr;      // grow-only device allocation
     size_t cap = 0;
 };
+struct PendingCopy { void *dst; const void *src; size_t bytes; };
+constexpr size_t kArenaBytes = 1 << 20;      // pinned, device-mapped staging for small calls
+constexpr size_t kSmallCall = 192 << 10;     // in + out bytes up to which a host-pointer call takes the zero-copy path
 
 }  // namespace
 
@@ -45,6 +49,13 @@ struct rvs_engine {
     int cull = 1;
     int num_ground = 0;
     unsigned long long *d_pair_count = nullptr;
+    // Small host-pointer calls (planner-shaped: one to a few hundred configurations) skip the three DMA transfers: inputs are
+    // memcpy'd into a pinned, device-mapped arena, the kernel reads and writes that arena over PCIe directly, and the results are
+    // memcpy'd out after one stream synchronisation (a single query drops from ~35-60 us to the launch + sync latency).
+    char *arena = nullptr;
+    size_t arena_off = 0;
+    bool zc = false;
+    std::vector<PendingCopy> pending;
     std::string err;
 };
 
@@ -73,12 +84,37 @@ int cuda_fail(rvs_engine *h, cudaError_t e, const char *what) {
 
 int reserve(rvs_engine *h, int which, size_t bytes) {
     DevBuf &b = h->buf[which];
-    if (bytes <= b.cap) return RVS_OK;
-    if (b.p) RVS_CUDA(h, cudaFree(b.p));
-    b.p = nullptr; b.cap = 0;
-    const size_t cap = bytes + bytes / 4 + 256;
-    RVS_CUDA(h, cudaMalloc(&b.p, cap));
-    b.cap = cap;
+    if (h->zc) {
+        const size_t off = (h->arena_off + 15) & ~size_t(15);
+        if (off + bytes > kArenaBytes) return fail(h, RVS_ERR_OUT_OF_MEMORY, "internal: small-call arena overflow");
+        b.p = h->arena + off;
+        h->arena_off = off + bytes;
+        return RVS_OK;
+    }
+    if (bytes > b.cap) {
+        if (b.dev) RVS_CUDA(h, cudaFree(b.dev));
+        b.dev = nullptr; b.cap = 0;
+        const size_t cap = bytes + bytes / 4 + 256;
+        RVS_CUDA(h, cudaMalloc(&b.dev, cap));
+        b.cap = cap;
+    }
+    b.p = b.dev;
+    return RVS_OK;
+}
+
+// every host-pointer entry point brackets its work with begin_call / finish
+void begin_call(rvs_engine *h, size_t in_plus_out_bytes) {
+    h->zc = h->arena != nullptr && in_plus_out_bytes <= kSmallCall;
+    h->arena_off = 0;
+    h->pending.clear();
+}
+int finish(rvs_engine *h) {
+    const cudaError_t e = cudaStreamSynchronize(h->stream);
+    const bool zc = h->zc;
+    h->zc = false;
+    if (e != cudaSuccess) return cuda_fail(h, e, "cudaStreamSynchronize");
+    if (zc) for (const PendingCopy &c : h->pending) std::memcpy(c.dst, c.src, c.bytes);
+    h->pending.clear();
     return RVS_OK;
 }
 
@@ -116,6 +152,7 @@ KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
 
 int enter(rvs_engine *h) {
     if (!h) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "handle is NULL");
+    h->zc = false;                            // a call that failed half-way must not leave the zero-copy mode on
     RVS_CUDA(h, cudaSetDevice(h->device));
     return RVS_OK;
 }
@@ -130,13 +167,18 @@ int launched(rvs_engine *h, cudaError_t e, const char *what) {
 
 int h2d(rvs_engine *h, int which, const void *src, size_t bytes) {
     RVS_TRY(reserve(h, which, bytes));
-    if (bytes) RVS_CUDA(h, cudaMemcpyAsync(h->buf[which].p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    if (!bytes) return RVS_OK;
+    if (h->zc) std::memcpy(h->buf[which].p, src, bytes);
+    else RVS_CUDA(h, cudaMemcpyAsync(h->buf[which].p, src, bytes, cudaMemcpyHostToDevice, h->stream));
     return RVS_OK;
 }
-int d2h(rvs_engine *h, void *dst, int which, size_t bytes) {
-    if (bytes && dst) RVS_CUDA(h, cudaMemcpyAsync(dst, h->buf[which].p, bytes, cudaMemcpyDeviceToHost, h->stream));
+int d2h_from(rvs_engine *h, void *dst, const void *src, size_t bytes) {
+    if (!bytes || !dst) return RVS_OK;
+    if (h->zc) h->pending.push_back({dst, src, bytes});
+    else RVS_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->stream));
     return RVS_OK;
 }
+int d2h(rvs_engine *h, void *dst, int which, size_t bytes) { return d2h_from(h, dst, h->buf[which].p, bytes); }
 
 int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, void *d_dc, void *d_prof, void *d_near, bool want_f64,
                       cudaStream_t on = nullptr) {
@@ -176,6 +218,7 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     const size_t rs = want_f64 ? sizeof(double) : sizeof(float);
     const size_t n = size_t(h->h_robot.n), L = n;
     const size_t near_bytes = mode == RVS_DIST_FULL ? size_t(N) * size_t(h->M) * L * 6 * rs : 0;
+    begin_call(h, size_t(N) * (n * sizeof(float) + rs * (1 + L)) + near_bytes + 64);
     RVS_TRY(reserve(h, B_Q, size_t(N) * n * sizeof(float)));
     RVS_TRY(reserve(h, B_DC, size_t(N) * rs));
     RVS_TRY(reserve(h, B_PROF, size_t(N) * L * rs));
@@ -185,13 +228,13 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     constexpr int64_t kMinChunk = 1 << 16;
     const int chunks = mode == RVS_DIST_FULL ? 1 : int(std::min<int64_t>(8, N / kMinChunk));
     if (chunks < 2) {
-        RVS_CUDA(h, cudaMemcpyAsync(dq, q, size_t(N) * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+        if (h->zc) std::memcpy(dq, q, size_t(N) * n * sizeof(float));
+        else RVS_CUDA(h, cudaMemcpyAsync(dq, q, size_t(N) * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
         RVS_TRY(distance_dev_impl(h, dq, N, mode, ddc, dprof, h->buf[B_NEAR].p, want_f64));
         RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * rs));
         if (mode >= RVS_DIST_PROFILE) RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * L * rs));
         if (mode == RVS_DIST_FULL) RVS_TRY(d2h(h, nearest, B_NEAR, near_bytes));
-        RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-        return RVS_OK;
+        return finish(h);
     }
     if (mode >= RVS_DIST_PROFILE && !profile) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL profile buffer");
     RVS_TRY(pipeline_ready(h));
@@ -228,6 +271,7 @@ int run_simple(rvs_engine *h, const float *q, int64_t N, LaunchFn fn, void *out,
     if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
     if (N == 0) return RVS_OK;
     if (!q || !out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    begin_call(h, size_t(N) * size_t(h->h_robot.n) * sizeof(float) + out_bytes + 64);
     RVS_TRY(h2d(h, B_Q, q, size_t(N) * size_t(h->h_robot.n) * sizeof(float)));
     const int which = verdict_out ? B_VERD : B_DC;
     RVS_TRY(reserve(h, which, out_bytes));
@@ -235,8 +279,7 @@ int run_simple(rvs_engine *h, const float *q, int64_t N, LaunchFn fn, void *out,
     if (verdict_out) a.verdict = static_cast<uint8_t *>(h->buf[which].p); else a.d_c = h->buf[which].p;
     RVS_TRY(launched(h, fn(a, h->stream), what));
     RVS_TRY(d2h(h, out, which, out_bytes));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return finish(h);
 }
 
 }  // namespace
@@ -286,6 +329,9 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     if ((e = cudaMemcpy(h->d_robot, &h->h_robot, sizeof(RobotDev), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(robot)");
     if ((e = cudaMalloc(&h->d_pair_count, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
     if ((e = cudaMemset(h->d_pair_count, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
+    void *arena = nullptr;
+    if (cudaHostAlloc(&arena, kArenaBytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) h->arena = static_cast<char *>(arena);
+    else cudaGetLastError();                 // no pinned memory to spare: small calls simply take the DMA path
     *out = h;
     return RVS_OK;
 }
@@ -294,7 +340,8 @@ int rvs_destroy(rvs_handle h) {
     if (!h) return RVS_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (auto &b : h->buf) if (b.p) cudaFree(b.p);
+    for (auto &b : h->buf) if (b.dev) cudaFree(b.dev);
+    if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_robot) cudaFree(h->d_robot);
     if (h->d_pair_count) cudaFree(h->d_pair_count);
@@ -473,7 +520,8 @@ int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, i
     if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
     if (E == 0) return RVS_OK;
     if (!d_q1 || !d_q2 || !d_valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
-    RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(E), h->stream));
+    if (h->zc) std::memset(d_valid, 1, size_t(E));                       // small host call: the verdicts live in the pinned arena
+    else RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(E), h->stream));
     KArgs a = base_args(h, d_q1, E);
     a.q2 = d_q2; a.verdict = d_valid;
     return launched(h, h->lt.edge_valid(a, h->stream), "edge kernel launch");
@@ -520,14 +568,14 @@ int rvs_is_valid_edges(rvs_handle h, const float *q1, const float *q2, int64_t E
     if (E == 0) return RVS_OK;
     if (!q1 || !q2 || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
     const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, 2 * bytes + size_t(E) + 64);
     RVS_TRY(h2d(h, B_Q, q1, bytes));
     RVS_TRY(h2d(h, B_Q2, q2, bytes));
     RVS_TRY(reserve(h, B_VERD, size_t(E)));
     RVS_TRY(rvs_is_valid_edges_dev(h, static_cast<const float *>(h->buf[B_Q].p), static_cast<const float *>(h->buf[B_Q2].p), E,
                                    static_cast<uint8_t *>(h->buf[B_VERD].p)));
     RVS_TRY(d2h(h, valid, B_VERD, size_t(E)));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return finish(h);
 }
 int rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *planes, const int32_t *plane_idx, int32_t R,
                         float *d_c, float *profile, uint8_t *status) {
@@ -539,6 +587,7 @@ int rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *pl
         for (int64_t i = 0; i < N; i++)
             if (plane_idx[i] < 0 || plane_idx[i] >= R) return fail(h, RVS_ERR_INVALID_ARGUMENT, "plane_idx out of range");
     const size_t n = size_t(h->h_robot.n);
+    begin_call(h, size_t(N) * (n * 8 + 16) + size_t(R) * size_t(h->M) * n * 6 * sizeof(float) + 128);
     RVS_TRY(h2d(h, B_Q, q, size_t(N) * n * sizeof(float)));
     RVS_TRY(h2d(h, B_PLANES, planes, size_t(R) * size_t(h->M) * n * 6 * sizeof(float)));
     if (plane_idx) RVS_TRY(h2d(h, B_IDX, plane_idx, size_t(N) * sizeof(int32_t)));
@@ -552,8 +601,7 @@ int rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *pl
     RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * sizeof(float)));
     RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * n * sizeof(float)));
     RVS_TRY(d2h(h, status, B_VERD, size_t(N)));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return finish(h);
 }
 int rvs_skeleton(rvs_handle h, const float *q, int64_t N, float *skeleton) {
     if (h && h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "skeleton output is FP32: use a REF32/FAST32 handle");
@@ -576,6 +624,7 @@ static int primitive_impl(rvs_handle h, const float *AB, const float *radius, co
     if (K < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "K < 0");
     if (K == 0) return RVS_OK;
     if (!AB || !radius || !obs || (!out && !hit)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    begin_call(h, size_t(K) * (13 * sizeof(float) + 8 * sizeof(float) + 1) + 128);
     RVS_TRY(h2d(h, B_Q, AB, size_t(K) * 6 * sizeof(float)));
     RVS_TRY(h2d(h, B_Q2, radius, size_t(K) * sizeof(float)));
     RVS_TRY(h2d(h, B_PLANES, obs, size_t(K) * 6 * sizeof(float)));
@@ -587,8 +636,7 @@ static int primitive_impl(rvs_handle h, const float *AB, const float *radius, co
     if (hit) a.verdict = static_cast<uint8_t *>(h->buf[B_VERD].p); else a.d_c = h->buf[B_DC].p;
     RVS_TRY(launched(h, h->lt.primitive(a, h->stream), "primitive kernel launch"));
     if (hit) RVS_TRY(d2h(h, hit, B_VERD, size_t(K))); else RVS_TRY(d2h(h, out, B_DC, size_t(K) * 8 * sizeof(float)));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return finish(h);
 }
 int rvs_capsule_box_distance(rvs_handle h, const float *AB, const float *radius, const float *obs, int64_t K, float *out) {
     return primitive_impl(h, AB, radius, obs, K, out, nullptr);
@@ -607,12 +655,13 @@ int rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profi
         return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
     // one packed upload: [q_root n][root_profile n][q_targets S*n], planes separately; one packed download: [q_reached S*n][d_c S]
     const size_t n = size_t(h->h_robot.n), in_floats = 2 * n + size_t(S) * n, planes_floats = size_t(h->M) * n * 6;
+    begin_call(h, (in_floats + planes_floats + size_t(S) * (n + 2)) * sizeof(float) + 128);
     std::vector<float> pack(in_floats);
     std::copy(q_root, q_root + n, pack.begin());
     std::copy(root_profile, root_profile + n, pack.begin() + n);
     std::copy(q_targets, q_targets + size_t(S) * n, pack.begin() + 2 * n);
     RVS_TRY(h2d(h, B_Q, pack.data(), in_floats * sizeof(float)));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));      // `pack` is pageable and dies with this frame
+    if (!h->zc) RVS_CUDA(h, cudaStreamSynchronize(h->stream));      // `pack` is pageable and dies with this frame
     RVS_TRY(h2d(h, B_PLANES, root_planes, planes_floats * sizeof(float)));
     RVS_TRY(reserve(h, B_DC, (size_t(S) * n + size_t(S)) * sizeof(float)));
     RVS_TRY(reserve(h, B_VERD, size_t(S)));
@@ -626,11 +675,10 @@ int rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profi
     a.d_crit = sp->d_crit; a.max_dist = h->prm.max_distance;
     a.q_reached = d_out; a.d_c_reached = d_out + size_t(S) * n; a.status = static_cast<uint8_t *>(h->buf[B_VERD].p);
     RVS_TRY(launched(h, h->lt.spines(a, h->stream), "spine kernel launch"));
-    RVS_CUDA(h, cudaMemcpyAsync(q_reached, d_out, size_t(S) * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    RVS_CUDA(h, cudaMemcpyAsync(d_c_reached, d_out + size_t(S) * n, size_t(S) * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    RVS_TRY(d2h_from(h, q_reached, d_out, size_t(S) * n * sizeof(float)));
+    RVS_TRY(d2h_from(h, d_c_reached, d_out + size_t(S) * n, size_t(S) * sizeof(float)));
     RVS_TRY(d2h(h, status, B_VERD, size_t(S)));
-    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
-    return RVS_OK;
+    return finish(h);
 }
 
 }  // extern "C"
