@@ -26,6 +26,9 @@
  *                                        (src/robots/xArm6.cpp:374-424; FCL mesh stage is NOT covered)
  *   rvs_capsule_box_distance /        <- the public static primitives CollisionAndDistance::distanceCapsuleToBox /
  *   rvs_capsule_box_collision            collisionCapsuleToBox (CollisionAndDistance.cpp:4-42, 208-214), batched
+ *   rvs_store_distance /              <- base::State's distance cache (include/state_spaces/State.h:24-41) filled by
+ *   rvs_store_extend_spines              computeDistance and consumed by RGBTConnect::extendGenSpine / extendGenSpine2
+ *                                        (src/planners/rbt/RGBTConnect.cpp:73-118), kept resident in HBM
  *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
  *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
  *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
@@ -187,6 +190,30 @@ int  rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_
 int  rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profile, float root_d_c,
                        const float *root_planes, const float *q_targets, int32_t S,
                        const rvs_spine_params *sp, float *q_reached, float *d_c_reached, uint8_t *status);
+
+/* ---- device-resident State cache (what the reference keeps on base::State: d_c, d_c_profile, nearest_points;
+ * include/state_spaces/State.h:24-41) ------------------------------------------------------------------------------
+ * The planners grow every spine of a bur from data that computeDistance left on the root State. Keeping those
+ * 24*L*M bytes per state in HBM "slots" means a planner iteration moves only configurations and scalars over PCIe.
+ * Slots are numbered 0 .. capacity-1 and are owned by the caller (one slot per tree node that served as a bur root).
+ * The cache is FP32 (REF32 / FAST32 handles). rvs_set_obstacles with a different M drops the cache; after
+ * rvs_update_obstacle_aabbs the cached planes are stale exactly as a reference State's are after
+ * Environment::updateEnvironment (the planners then ask again with compute_again = true). */
+int  rvs_store_reserve(rvs_handle h, int32_t capacity);          /* grows (contents preserved), never shrinks */
+int  rvs_store_capacity(rvs_handle h);
+/* computeDistance(q_i) with nearest points (RealVectorSpace.cpp:318-392) for N configurations; everything is
+ * written to slot slots[i]; d_c[N] (and profile[N x L] unless NULL) also come back to the host. */
+int  rvs_store_distance(rvs_handle h, const float *q, int32_t N, const int32_t *slots, float *d_c, float *profile);
+/* Generalized-bur spines whose roots are cached states: spine s starts at slot root_slots[s] towards
+ * q_targets[s]. gen2 = 0: RGBTConnect::extendGenSpine (RGBTConnect.cpp:73-92); gen2 = 1: extendGenSpine2
+ * (:96-118). q_layers[S x num_layers x n] receives the state after every layer, n_layers[S] how many were made
+ * (0 when the root has no clearance: status Trapped), d_c_last[S] the last distance-to-planes, status[S] the
+ * base::State::Status of the last extendSpine (1 Advanced, 2 Trapped, 3 Reached). */
+int  rvs_store_extend_spines(rvs_handle h, const int32_t *root_slots, const float *q_targets, int32_t S,
+                             const rvs_spine_params *sp, int32_t gen2, float *q_layers, int32_t *n_layers,
+                             float *d_c_last, uint8_t *status);
+/* copy one slot back to the host (any of the outputs may be NULL); planes[M x L x 6] */
+int  rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *profile, float *planes);
 
 /* Batched geometric primitives on K independent (capsule, box) pairs, host pointers.
  * AB: K x 6 (A xyz, B xyz); radius: K; obs: K x 6 (x_min,y_min,z_min,x_max,y_max,z_max).

@@ -151,6 +151,21 @@ class Oracle:
                                     _p(status, ctypes.POINTER(ctypes.c_uint8)))
         return q_out, d_out, status
 
+    def extend_spines_layers(self, q_roots, root_profiles, root_d_c, root_planes, root_idx, q_targets, spine_params, gen2=False):
+        """extendGenSpine / extendGenSpine2 with per-spine roots, every layer kept. Returns (q_layers[S,layers,n], n_layers, d_c_last, status)."""
+        q_roots, root_profiles = _f32(q_roots, (-1, self.n)), _f32(root_profiles, (-1, self.n))
+        root_d_c, root_planes = _f32(root_d_c, (-1,)), _f32(root_planes)
+        root_idx = np.ascontiguousarray(root_idx, np.int32)
+        q_targets = _f32(q_targets, (-1, self.n))
+        S = q_targets.shape[0]
+        q_layers = np.zeros((S, spine_params.num_layers, self.n), np.float32)
+        n_layers, d_last, status = np.empty(S, np.int32), np.empty(S, np.float32), np.empty(S, np.uint8)
+        lib().orc_extend_spines_layers_f32(self._h, _p(q_roots, c_f32p), _p(root_profiles, c_f32p), _p(root_d_c, c_f32p), _p(root_planes, c_f32p),
+                                           _p(root_idx, c_i32p), _p(q_targets, c_f32p), ctypes.c_int32(S), ctypes.byref(spine_params),
+                                           ctypes.c_int32(1 if gen2 else 0), _p(q_layers, c_f32p), _p(n_layers, c_i32p), _p(d_last, c_f32p),
+                                           _p(status, ctypes.POINTER(ctypes.c_uint8)))
+        return q_layers, n_layers, d_last, status
+
     def self_collision_capsules(self, q):
         q = _f32(q, (-1, self.n))
         out = np.empty(q.shape[0], np.uint8)

@@ -762,6 +762,35 @@ inline int extend_gen_spine(const Robot &rb, size_t M, const Config<float> &cfg,
     return status;
 }
 
+// extendGenSpine (gen2 = false, RGBTConnect.cpp:73-92) / extendGenSpine2 (gen2 = true, :96-118) keeping the state after
+// every layer: q_layers[num_layers][n], *n_layers = how many were made (0 and status Trapped when the root has no
+// clearance; the reference's extendGenSpine2 is never called for such a root, RGBTConnect.cpp:33,141).
+inline int extend_gen_spine_layers(const Robot &rb, size_t M, const Config<float> &cfg, const SpineConfig &sp, bool gen2, const float *q_root,
+                                   const float *root_profile, float root_d_c, const float *root_planes, const float *q_e, float *q_layers,
+                                   int *n_layers, float *d_out) {
+    const int n = rb.n;
+    *n_layers = 0;
+    *d_out = root_d_c;
+    if (!(root_d_c > 0)) { for (int i = 0; i < n; i++) q_layers[i] = q_root[i]; return 2; }
+    std::vector<float> q_cur(q_root, q_root + n), prof_cur(root_profile, root_profile + n), prof_new(n);
+    std::vector<V3<float>> sk(n + 1);
+    float dc_cur = root_d_c;
+    int status = 0;
+    for (int layer = 0; layer < sp.num_layers; layer++) {
+        float *q_out = q_layers + size_t(layer) * n;
+        status = extend_spine(rb, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
+        *n_layers = layer + 1;
+        skeleton(rb, q_out, sk.data());
+        bool rejected;
+        *d_out = underestimation(rb, M, sk.data(), root_planes, cfg, prof_new.data(), &rejected);
+        if (*d_out < sp.d_crit || (gen2 ? status == 3 : status != 1)) break;
+        q_cur.assign(q_out, q_out + n);
+        prof_cur = prof_new;
+        dc_cur = *d_out;
+    }
+    return status;
+}
+
 // splitmix64-based stateless synthetic configuration generator
 inline uint64_t splitmix64(uint64_t x) {
     x += 0x9E3779B97F4A7C15ull;

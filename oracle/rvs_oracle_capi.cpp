@@ -213,6 +213,26 @@ int orc_extend_spines_f32(void *h, const float *q_root, const float *root_profil
     return 0;
 }
 
+// spines with per-spine roots: root r = (q_roots[r], root_profiles[r], root_d_c[r], root_planes[r]); root_idx[S]
+int orc_extend_spines_layers_f32(void *h, const float *q_roots, const float *root_profiles, const float *root_d_c, const float *root_planes,
+                                 const int32_t *root_idx, const float *q_targets, int32_t S, const rvs_spine_params *sp, int32_t gen2,
+                                 float *q_layers, int32_t *n_layers, float *d_c_last, uint8_t *status) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const size_t n = size_t(e->robot.n), M = e->sc32.boxes.size();
+    orc::SpineConfig sc;
+    sc.num_layers = sp->num_layers; sc.num_iter_spine = sp->num_iter_spine; sc.use_expanded_bubble = sp->use_expanded_bubble != 0; sc.d_crit = sp->d_crit;
+    for (int32_t s = 0; s < S; s++) {
+        const size_t r = size_t(root_idx[s]);
+        int layers = 0;
+        status[s] = uint8_t(orc::extend_gen_spine_layers(e->robot, M, cfg, sc, gen2 != 0, q_roots + r * n, root_profiles + r * n, root_d_c[r],
+                                                         root_planes + r * M * n * 6, q_targets + size_t(s) * n,
+                                                         q_layers + size_t(s) * size_t(sp->num_layers) * n, &layers, d_c_last + s));
+        n_layers[s] = layers;
+    }
+    return 0;
+}
+
 int orc_enclosing_radii_f32(void *h, const float *q, int64_t N, float *radii) {
     auto *e = static_cast<Engine *>(h);
     const int n = e->robot.n;

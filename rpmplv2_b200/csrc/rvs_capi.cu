@@ -49,6 +49,8 @@ struct rvs_engine {
     int cull = 1;
     int num_ground = 0;
     unsigned long long *d_pair_count = nullptr;
+    float *d_store = nullptr;     // device-resident State cache (rvs_store_*): store_cap slots of store_slot_floats(n, M) floats
+    int store_cap = 0;
     // Small host-pointer calls (planner-shaped: one to a few hundred configurations) skip the three DMA transfers: inputs are
     // memcpy'd into a pinned, device-mapped arena, the kernel reads and writes that arena over PCIe directly, and the results are
     // memcpy'd out after one stream synchronisation (a single query drops from ~35-60 us to the launch + sync latency).
@@ -343,6 +345,7 @@ int rvs_destroy(rvs_handle h) {
     for (auto &b : h->buf) if (b.dev) cudaFree(b.dev);
     if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
+    if (h->d_store) cudaFree(h->d_store);
     if (h->d_robot) cudaFree(h->d_robot);
     if (h->d_pair_count) cudaFree(h->d_pair_count);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -482,6 +485,10 @@ int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max
         const int cap = M + M / 2 + 16;
         RVS_CUDA(h, cudaMalloc(&h->d_obs, 2 * size_t(cap) * sizeof(ObstacleRec)));
         h->obs_cap = cap;
+    }
+    if (M != h->M && h->d_store) {          // the slot stride depends on M: cached states of another table are meaningless
+        RVS_CUDA(h, cudaFree(h->d_store));
+        h->d_store = nullptr; h->store_cap = 0;
     }
     h->M = M;
     return upload_obstacles(h);
@@ -679,6 +686,108 @@ int rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profi
     RVS_TRY(d2h_from(h, d_c_reached, d_out + size_t(S) * n, size_t(S) * sizeof(float)));
     RVS_TRY(d2h(h, status, B_VERD, size_t(S)));
     return finish(h);
+}
+
+// ---- device-resident State cache -------------------------------------------------------------------------------------------
+int rvs_store_reserve(rvs_handle h, int32_t capacity) {
+    RVS_TRY(enter(h));
+    if (capacity < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "capacity < 0");
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "the state cache is FP32: use a REF32/FAST32 handle");
+    if (capacity <= h->store_cap) return RVS_OK;
+    const size_t slot = store_slot_floats(h->h_robot.n, h->M) * sizeof(float);
+    float *grown = nullptr;
+    RVS_CUDA(h, cudaMalloc(&grown, slot * size_t(capacity)));
+    if (h->d_store) {
+        RVS_CUDA(h, cudaMemcpyAsync(grown, h->d_store, slot * size_t(h->store_cap), cudaMemcpyDeviceToDevice, h->stream));
+        RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+        RVS_CUDA(h, cudaFree(h->d_store));
+    }
+    h->d_store = grown;
+    h->store_cap = capacity;
+    return RVS_OK;
+}
+
+int rvs_store_capacity(rvs_handle h) { return h ? h->store_cap : 0; }
+
+namespace {
+int check_slots(rvs_engine *h, const int32_t *slots, int32_t count) {
+    for (int32_t i = 0; i < count; i++)
+        if (slots[i] < 0 || slots[i] >= h->store_cap) return fail(h, RVS_ERR_INVALID_ARGUMENT, "slot index outside the reserved state cache");
+    return RVS_OK;
+}
+StoreArgs store_args(rvs_engine *h) {
+    StoreArgs a{};
+    a.robot = h->d_robot; a.obstacles = h->d_obs; a.M = h->M; a.n = h->h_robot.n;
+    a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance; a.store = h->d_store;
+    return a;
+}
+}  // namespace
+
+int rvs_store_distance(rvs_handle h, const float *q, int32_t N, const int32_t *slots, float *d_c, float *profile) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "the state cache is FP32: use a REF32/FAST32 handle");
+    if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
+    if (N == 0) return RVS_OK;
+    if (!q || !slots || !d_c) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(check_slots(h, slots, N));
+    const size_t n = size_t(h->h_robot.n);
+    begin_call(h, size_t(N) * (n * 8 + 16) + 128);
+    RVS_TRY(h2d(h, B_Q, q, size_t(N) * n * sizeof(float)));
+    RVS_TRY(h2d(h, B_IDX, slots, size_t(N) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_DC, size_t(N) * sizeof(float)));
+    RVS_TRY(reserve(h, B_PROF, size_t(N) * n * sizeof(float)));
+    StoreArgs a = store_args(h);
+    a.N = N; a.q = static_cast<const float *>(h->buf[B_Q].p); a.slots = static_cast<const int32_t *>(h->buf[B_IDX].p);
+    a.d_c = static_cast<float *>(h->buf[B_DC].p); a.profile = profile ? static_cast<float *>(h->buf[B_PROF].p) : nullptr;
+    RVS_TRY(launched(h, h->lt.store_distance(a, h->stream), "store distance kernel launch"));
+    RVS_TRY(d2h(h, d_c, B_DC, size_t(N) * sizeof(float)));
+    if (profile) RVS_TRY(d2h(h, profile, B_PROF, size_t(N) * n * sizeof(float)));
+    return finish(h);
+}
+
+int rvs_store_extend_spines(rvs_handle h, const int32_t *root_slots, const float *q_targets, int32_t S, const rvs_spine_params *sp, int32_t gen2,
+                            float *q_layers, int32_t *n_layers, float *d_c_last, uint8_t *status) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "spines run in FP32: use a REF32/FAST32 handle");
+    if (S < 0 || !sp || sp->num_layers < 1 || sp->num_iter_spine < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad S or spine parameters");
+    if (S == 0) return RVS_OK;
+    if (!root_slots || !q_targets || !q_layers || !n_layers || !d_c_last || !status) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(check_slots(h, root_slots, S));
+    const size_t n = size_t(h->h_robot.n), layers = size_t(sp->num_layers);
+    begin_call(h, size_t(S) * (n * 4 + 4 + layers * n * 4 + 4 + 4 + 1) + 256);
+    RVS_TRY(h2d(h, B_Q, q_targets, size_t(S) * n * sizeof(float)));
+    RVS_TRY(h2d(h, B_IDX, root_slots, size_t(S) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_NEAR, size_t(S) * layers * n * sizeof(float)));
+    RVS_TRY(reserve(h, B_DC, size_t(S) * sizeof(float)));
+    RVS_TRY(reserve(h, B_PROF, size_t(S) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_VERD, size_t(S)));
+    StoreArgs a = store_args(h);
+    a.S = S; a.root_slot = static_cast<const int32_t *>(h->buf[B_IDX].p); a.q_targets = static_cast<const float *>(h->buf[B_Q].p);
+    a.num_layers = sp->num_layers; a.num_iter_spine = sp->num_iter_spine; a.use_expanded_bubble = sp->use_expanded_bubble; a.gen2 = gen2 ? 1 : 0;
+    a.d_crit = sp->d_crit;
+    a.q_layers = static_cast<float *>(h->buf[B_NEAR].p); a.n_layers = static_cast<int32_t *>(h->buf[B_PROF].p);
+    a.d_c_last = static_cast<float *>(h->buf[B_DC].p); a.status = static_cast<uint8_t *>(h->buf[B_VERD].p);
+    RVS_TRY(launched(h, h->lt.store_spines(a, h->stream), "store spine kernel launch"));
+    RVS_TRY(d2h(h, q_layers, B_NEAR, size_t(S) * layers * n * sizeof(float)));
+    RVS_TRY(d2h(h, n_layers, B_PROF, size_t(S) * sizeof(int32_t)));
+    RVS_TRY(d2h(h, d_c_last, B_DC, size_t(S) * sizeof(float)));
+    RVS_TRY(d2h(h, status, B_VERD, size_t(S)));
+    return finish(h);
+}
+
+int rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *profile, float *planes) {
+    RVS_TRY(enter(h));
+    RVS_TRY(check_slots(h, &slot, 1));
+    const size_t n = size_t(h->h_robot.n);
+    const size_t stride = store_slot_floats(int(n), h->M), head = store_header_floats(int(n));
+    std::vector<float> tmp(stride);
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    RVS_CUDA(h, cudaMemcpy(tmp.data(), h->d_store + size_t(slot) * stride, stride * sizeof(float), cudaMemcpyDeviceToHost));
+    if (q) std::copy(tmp.begin(), tmp.begin() + n, q);
+    if (d_c) *d_c = tmp[n];
+    if (profile) std::copy(tmp.begin() + n + 1, tmp.begin() + 2 * n + 1, profile);
+    if (planes) std::copy(tmp.begin() + head, tmp.end(), planes);
+    return RVS_OK;
 }
 
 }  // extern "C"

@@ -18,6 +18,8 @@ struct LaunchTable {
     LaunchFn self_collision;
     LaunchFn primitive;
     cudaError_t (*spines)(const SpineArgs &, cudaStream_t);
+    cudaError_t (*store_distance)(const StoreArgs &, cudaStream_t);
+    cudaError_t (*store_spines)(const StoreArgs &, cudaStream_t);
 };
 
 LaunchTable launch_table_ref32();    // FK FP64, geometry FP32, no FMA contraction, IEEE div/sqrt

@@ -89,4 +89,35 @@ struct SpineArgs {
     uint8_t *status;              // [S]  base::State::Status: 1 Advanced, 2 Trapped, 3 Reached
 };
 
+// ---- device-resident State cache (rvs_store.cuh) ----------------------------------------------------------------------
+#ifdef __CUDACC__
+#define RVS_HD __host__ __device__
+#else
+#define RVS_HD
+#endif
+RVS_HD inline size_t store_header_floats(int n) { return size_t((2 * n + 1 + 3) & ~3); }
+RVS_HD inline size_t store_slot_floats(int n, int M) { return store_header_floats(n) + size_t(M) * size_t(n) * 6; }
+
+struct StoreArgs {
+    const RobotDev *robot;
+    const ObstacleRec *obstacles;
+    int32_t M, N, n;
+    float eq_thr, max_dist;
+    float *store;              // slot array
+    const float *q;            // [N][n]
+    const int32_t *slots;      // [N]
+    float *d_c;                // [N]
+    float *profile;            // [N][L] or nullptr
+    // spines
+    const int32_t *root_slot;  // [S]
+    const float *q_targets;    // [S][n]
+    int32_t S, num_layers, num_iter_spine, use_expanded_bubble, gen2;
+    float d_crit;
+    float *q_layers;           // [S][num_layers][n]
+    int32_t *n_layers;         // [S]
+    float *d_c_last;           // [S]
+    uint8_t *status;           // [S]
+};
+
+
 }  // namespace rvs

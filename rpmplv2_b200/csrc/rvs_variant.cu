@@ -5,6 +5,7 @@
 #include "rvs_kernels.cuh"
 #include "rvs_distance_wq.cuh"
 #include "rvs_valid_wq.cuh"
+#include "rvs_store.cuh"
 #include "rvs_launch.h"
 
 namespace rvs {
@@ -95,7 +96,19 @@ struct Variant {
         spine_kernel<F><<<grid_for(a.S, 64), 64, 0, st>>>(a);
         return cudaGetLastError();
     }
-    static LaunchTable table() { return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines}; }
+    static cudaError_t store_distance(const StoreArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        store_distance_kernel<F><<<unsigned(a.N), 32 * kStoreWarps, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static cudaError_t store_spines(const StoreArgs &a, cudaStream_t st) {
+        if (a.S <= 0) return cudaSuccess;
+        store_spine_kernel<F><<<grid_for(a.S, 4), 128, 0, st>>>(a);
+        return cudaGetLastError();
+    }
+    static LaunchTable table() {
+        return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines, store_distance, store_spines};
+    }
 };
 
 }  // namespace

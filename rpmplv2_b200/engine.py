@@ -49,6 +49,12 @@ SYMBOLS = {
     "rvs_self_collision_capsules": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_extend_spines": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int32,
                                          ctypes.POINTER(RvsSpineParams), c_f32p, c_f32p, c_u8p]),
+    "rvs_store_reserve": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_store_capacity": (ctypes.c_int, [_H]),
+    "rvs_store_distance": (ctypes.c_int, [_H, c_f32p, ctypes.c_int32, c_i32p, c_f32p, c_f32p]),
+    "rvs_store_extend_spines": (ctypes.c_int, [_H, c_i32p, c_f32p, ctypes.c_int32, ctypes.POINTER(RvsSpineParams), ctypes.c_int32,
+                                               c_f32p, c_i32p, c_f32p, c_u8p]),
+    "rvs_store_read": (ctypes.c_int, [_H, ctypes.c_int32, c_f32p, c_f32p, c_f32p, c_f32p]),
     "rvs_capsule_box_distance": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p]),
     "rvs_capsule_box_collision": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_distance_f64": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, ctypes.c_int32, c_f64p, c_f64p, c_f64p]),
@@ -247,6 +253,39 @@ class Engine:
         self._check(self._lib.rvs_extend_spines(self._h, _p(q_root, c_f32p), _p(root_profile, c_f32p), ctypes.c_float(root_d_c), _p(root_planes, c_f32p),
                                                 _p(q_targets, c_f32p), S, ctypes.byref(sp), _p(q_out, c_f32p), _p(d_out, c_f32p), _p(status, c_u8p)))
         return q_out, d_out, status
+
+    # -- device-resident State cache ----------------------------------------------------------------------------------
+    def store_reserve(self, capacity: int):
+        self._check(self._lib.rvs_store_reserve(self._h, capacity))
+
+    def store_distance(self, q, slots, want_profile: bool = True):
+        """computeDistance with nearest points for N configurations, cached in slots[i]. Returns (d_c[N], profile[N,L] or None)."""
+        q = _f32(q, (-1, self.n))
+        slots = np.ascontiguousarray(slots, np.int32)
+        N = q.shape[0]
+        d_c = np.empty(N, np.float32)
+        profile = np.empty((N, self.n), np.float32) if want_profile else None
+        self._check(self._lib.rvs_store_distance(self._h, _p(q, c_f32p), N, _p(slots, c_i32p), _p(d_c, c_f32p), _p(profile, c_f32p)))
+        return d_c, profile
+
+    def store_extend_spines(self, root_slots, q_targets, spine_params: Optional[RvsSpineParams] = None, gen2: bool = False):
+        """Generalized-bur spines rooted at cached states. Returns (q_layers[S,layers,n], n_layers[S], d_c_last[S], status[S])."""
+        sp = spine_params or RvsSpineParams(5, 1, 1, 0.05)
+        root_slots = np.ascontiguousarray(root_slots, np.int32)
+        q_targets = _f32(q_targets, (-1, self.n))
+        S = q_targets.shape[0]
+        q_layers = np.zeros((S, sp.num_layers, self.n), np.float32)
+        n_layers, d_last, status = np.empty(S, np.int32), np.empty(S, np.float32), np.empty(S, np.uint8)
+        self._check(self._lib.rvs_store_extend_spines(self._h, _p(root_slots, c_i32p), _p(q_targets, c_f32p), S, ctypes.byref(sp), 1 if gen2 else 0,
+                                                      _p(q_layers, c_f32p), _p(n_layers, c_i32p), _p(d_last, c_f32p), _p(status, c_u8p)))
+        return q_layers, n_layers, d_last, status
+
+    def store_read(self, slot: int):
+        """(q[n], d_c, profile[L], planes[M,L,6]) of one cached state."""
+        q, prof, planes = np.empty(self.n, np.float32), np.empty(self.n, np.float32), np.empty((self.M, self.n, 6), np.float32)
+        d = ctypes.c_float(0)
+        self._check(self._lib.rvs_store_read(self._h, slot, _p(q, c_f32p), ctypes.byref(d), _p(prof, c_f32p), _p(planes, c_f32p)))
+        return q, float(d.value), prof, planes
 
     def self_collision_capsules(self, q) -> np.ndarray:
         q = _f32(q, (-1, self.n))

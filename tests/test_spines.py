@@ -128,3 +128,88 @@ def test_gpu_spines_vs_oracle(ob, case, iters, expanded, layers):
     assert (eng.distance(q_g, robots.DIST_MIN)[0] > 0).all()          # collision-free in the real scene
     q_t, d_t, s_t = eng.extend_spines(q_root, p_e[0], 0.0, near_e[0], targets[:5], sp)
     assert (s_t == TRAPPED).all() and (q_t == q_root).all()
+
+
+def test_oracle_layered_spines_agree_with_the_final_state_variant(ob):
+    """extend_gen_spine_layers (every layer kept, per-spine roots) ends where extend_gen_spine ends; gen2 differs only in its stop rule."""
+    rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D2", 0.45)
+    tol = np.full_like(tol, 1000.0)
+    S = 40
+    o, q_root, prof, d_root, planes, targets = _root_and_targets(ob, rb, mn, mx, g, tol, S)
+    sp = robots.RvsSpineParams(5, 1, 1, 0.05)
+    q_fin, d_fin, st_fin = o.extend_spines(q_root, prof, d_root, planes, targets, sp)
+    for gen2 in (False, True):
+        ql, nl, dl, st = o.extend_spines_layers(q_root[None], prof[None], [d_root], planes[None], np.zeros(S, np.int32), targets, sp, gen2)
+        assert (st == st_fin).all() and (nl >= 1).all() and (nl <= 5).all()
+        last = ql[np.arange(S), nl - 1]
+        assert (last == q_fin).all() and (dl == d_fin).all()
+        # layers advance monotonically along root -> target
+        t = np.einsum("sld,sd->sl", ql - q_root, targets - q_root) / np.einsum("sd,sd->s", targets - q_root, targets - q_root)[:, None]
+        for s in range(S):
+            assert (np.diff(t[s, :nl[s]]) > -1e-6).all()
+    ql, nl, dl, st = o.extend_spines_layers(q_root[None], prof[None], [0.0], planes[None], np.zeros(3, np.int32), targets[:3], sp, True)
+    assert (st == TRAPPED).all() and (nl == 0).all() and (ql[:, 0] == q_root).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,iters,expanded,layers", [("xarm6", 1, 1, 5), ("xarm6", 2, 0, 3), ("planar2", 1, 1, 5), ("spatial22", 1, 1, 5),
+                                                        ("xarm6_m1000", 1, 1, 5)])
+def test_gpu_state_cache_distance_and_spines_vs_oracle(ob, case, iters, expanded, layers):
+    """rvs_store_distance (one CTA per configuration, nearest points kept in HBM) and rvs_store_extend_spines (one warp per spine,
+    per-spine roots) against the oracle's computeDistance / extendGenSpine[2]."""
+    if case == "xarm6":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D2", 0.45)
+    elif case == "xarm6_m1000":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(1000, "D2", 0.9)
+    elif case == "planar2":
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    else:
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 6)
+    tol = np.full_like(tol, 1000.0)                                   # planes of every obstacle, so that the bur property below holds
+    o = ob.Oracle(rb, robots.default_params())
+    o.set_obstacles(mn, mx, g, tol)
+    eng = engine.Engine(rb)
+    eng.set_obstacles(mn, mx, g, tol)
+    R = 96
+    q = synthetic.configs(rb, R, seed=0xABCD)
+    eng.store_reserve(R // 2)
+    eng.store_reserve(2 * R)                                           # growth keeps nothing we need yet, but must not break
+    slots = (np.arange(R, dtype=np.int32) * 2 + 1) % (2 * R)           # scattered slots
+    d_g, p_g = eng.store_distance(q, slots)
+    d_o, p_o, near_o = o.distance(q, robots.DIST_FULL)
+    assert (d_g > 0).sum() >= 8 and ((d_g == 0) == (d_o == 0)).all()
+    assert np.abs(d_g - d_o).max() <= 1e-4 and np.abs(p_g - p_o).max() <= 1e-4
+    assert (d_g == d_o).mean() > 0.99 and (p_g == p_o).mean() > 0.99   # in practice bit-identical
+    free = np.nonzero(d_o > 0)[0]
+    for k in free[:6]:
+        qs, ds, ps, planes = eng.store_read(int(slots[k]))
+        assert (qs == q[k]).all() and ds == d_g[k] and (ps == p_g[k]).all()
+        assert np.abs(planes - near_o[k]).max() <= 1e-4
+    # bit-identical to the engine's own sequential FULL kernel
+    d_f, p_f, near_f = eng.distance(q[free[:6]], robots.DIST_FULL)
+    for i, k in enumerate(free[:6]):
+        _, ds, ps, planes = eng.store_read(int(slots[k]))
+        assert ds == d_f[i] and (ps == p_f[i]).all() and (planes == near_f[i]).all()
+    # spines: every free root grows 7 spines (NUM_SPINES) towards random targets
+    sp = robots.RvsSpineParams(layers, iters, expanded, 0.05)
+    rng = np.random.default_rng(5)
+    roots = np.repeat(np.arange(R, dtype=np.int32), 7)
+    targets = (q[roots] + rng.normal(0, 1.5, (len(roots), rb.num_dofs))).astype(np.float32)
+    for gen2 in (False, True):
+        ql_g, nl_g, dl_g, st_g = eng.store_extend_spines(slots[roots], targets, sp, gen2)
+        # the oracle gets the ENGINE's root data (read back from the cache), as a planner on either backend would hold it
+        prof_e = np.stack([eng.store_read(int(s))[2] for s in slots])
+        planes_e = np.stack([eng.store_read(int(s))[3] for s in slots])
+        ql_o, nl_o, dl_o, st_o = o.extend_spines_layers(q, prof_e, d_g, planes_e, roots, targets, sp, gen2)
+        assert (st_g == st_o).all() and (nl_g == nl_o).all()
+        assert ((st_g == TRAPPED) == (d_g[roots] <= 0)).all()
+        for s in range(len(roots)):
+            k = max(int(nl_o[s]), 1)
+            assert np.abs(ql_g[s, :k] - ql_o[s, :k]).max() <= 1e-5
+        assert np.abs(dl_g - dl_o).max() <= 1e-4
+        live = st_g != TRAPPED
+        last = ql_g[np.arange(len(roots)), np.maximum(nl_g, 1) - 1]
+        assert (eng.distance(last[live], robots.DIST_MIN)[0] > 0).all()    # the bur property in the real scene
+    with pytest.raises(engine.RvsError):
+        eng.store_distance(q[:1], np.array([2 * R], np.int32))
+    eng.close()
