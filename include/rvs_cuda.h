@@ -133,6 +133,9 @@ int  rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int devic
 int  rvs_destroy(rvs_handle h);
 const char *rvs_last_error(rvs_handle h);      /* h may be NULL: last error of a failed rvs_create */
 int  rvs_set_params(rvs_handle h, const rvs_params *params);   /* precision < 0: keep the handle's variant */
+int  rvs_get_params(rvs_handle h, rvs_params *out);
+int  rvs_num_dofs(rvs_handle h);
+int  rvs_get_limits(rvs_handle h, float *limit_lo, float *limit_hi);   /* num_dofs floats each */
 int  rvs_set_stream(rvs_handle h, void *cuda_stream);  /* adopt an external cudaStream_t (e.g. torch's) */
 void *rvs_get_stream(rvs_handle h);
 int  rvs_sync(rvs_handle h);

@@ -225,3 +225,46 @@ def capsule_rect_collision(AB, radius, obs, face, thr=1e-4, maxd=1000.0):
     lib().orc_capsule_rect_collision_f32(ctypes.c_int64(a.shape[0]), _p(a, c_f32p), _p(r, c_f32p), _p(o, c_f32p), _p(f, c_i32p),
                                          ctypes.c_float(thr), ctypes.c_float(maxd), _p(out, c_u8p))
     return out
+
+
+# --- planners driven by the oracle (checker of tests/test_planners.py, CPU baseline of bench.py) ---------------------------
+
+_plan_lib = None
+
+
+def plan_lib():
+    global _plan_lib
+    if _plan_lib is None:
+        from rpmplv2_b200.planning import PlanConfig, PlanResult
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "liborc_planning.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{path} not found: run `make -C oracle oracle`")
+        _plan_lib = ctypes.CDLL(path)
+        _plan_lib.orcplan_solve_batch.restype = ctypes.c_int
+        _plan_lib.orcplan_solve_batch.argtypes = [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64),
+                                                  ctypes.c_int32, ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                  ctypes.POINTER(ctypes.c_int64)]
+        _plan_lib.orcplan_last_error.restype = ctypes.c_char_p
+    return _plan_lib
+
+
+def plan_solve_batch(orc: "Oracle", cfg, q_start, q_goal, seeds=None, max_path: int = 512, threads: int = 1, lockstep: bool = False):
+    """Same planner code as rpmplv2_b200.planning.solve_batch, state-space queries answered by the CPU oracle."""
+    from rpmplv2_b200.planning import PlanResult, unpack_results
+    n = orc.n
+    qs, qg = np.atleast_2d(np.asarray(q_start, np.float32)), np.atleast_2d(np.asarray(q_goal, np.float32))
+    P = len(seeds) if seeds is not None else qs.shape[0]
+    qs = np.ascontiguousarray(np.broadcast_to(qs, (P, n)))
+    qg = np.ascontiguousarray(np.broadcast_to(qg, (P, n)))
+    sd = np.ascontiguousarray(np.arange(P) if seeds is None else seeds, np.uint64)
+    results = (PlanResult * P)()
+    paths = np.zeros((P, max_path, n), np.float32)
+    stats = (ctypes.c_int64 * 3)()
+    lib_ = plan_lib()
+    # the engine handle of the oracle library is a plain heap object: it can be shared with the planning library, which is built
+    # from the same header (rvs_oracle_engine.hpp)
+    rc = lib_.orcplan_solve_batch(orc._h, ctypes.byref(cfg), _p(qs, c_f32p), _p(qg, c_f32p), sd.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), P,
+                                  results, _p(paths, c_f32p), max_path, threads, 1 if lockstep else 0, stats)
+    if rc != 0:
+        raise RuntimeError((lib_.orcplan_last_error() or b"").decode())
+    return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1])}

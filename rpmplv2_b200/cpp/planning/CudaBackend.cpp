@@ -1,0 +1,46 @@
+#include "CudaBackend.h"
+
+#include <stdexcept>
+#include <string>
+
+namespace rvsplan
+{
+	CudaBackend::CudaBackend(rvs_handle h) : engine(h)
+	{
+		if (!h) throw std::runtime_error("CudaBackend: NULL engine handle (there is no CPU fallback)");
+		n = rvs_num_dofs(h);
+		lo.resize(size_t(n));
+		hi.resize(size_t(n));
+		check(rvs_get_limits(h, lo.data(), hi.data()), "rvs_get_limits");
+		rvs_params prm;
+		check(rvs_get_params(h, &prm), "rvs_get_params");
+		eq_thr = prm.equality_threshold;
+	}
+
+	void CudaBackend::check(int status, const char *what) const
+	{
+		if (status != RVS_OK) throw std::runtime_error(std::string(what) + ": " + rvs_last_error(engine));
+	}
+
+	void CudaBackend::reserveSlots(int capacity) { check(rvs_store_reserve(engine, capacity), "rvs_store_reserve"); }
+
+	void CudaBackend::isValid(const float *q, int N, uint8_t *valid) { check(rvs_is_valid(engine, q, N, valid), "rvs_is_valid"); }
+
+	void CudaBackend::isValidEdges(const float *q1, const float *q2, int E, uint8_t *valid)
+	{
+		check(rvs_is_valid_edges(engine, q1, q2, E, valid), "rvs_is_valid_edges");
+	}
+
+	void CudaBackend::distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c)
+	{
+		check(rvs_store_distance(engine, q, N, slots, d_c, nullptr), "rvs_store_distance");
+	}
+
+	void CudaBackend::extendGenSpines(const int32_t *root_slots, const float *q_targets, int S, const SpineParams &sp, bool gen2,
+									  float *q_layers, int32_t *n_layers, float *d_c_last, uint8_t *status)
+	{
+		rvs_spine_params p;
+		p.num_layers = sp.num_layers; p.num_iter_spine = sp.num_iter_spine; p.use_expanded_bubble = sp.use_expanded_bubble ? 1 : 0; p.d_crit = sp.d_crit;
+		check(rvs_store_extend_spines(engine, root_slots, q_targets, S, &p, gen2 ? 1 : 0, q_layers, n_layers, d_c_last, status), "rvs_store_extend_spines");
+	}
+}

@@ -1,0 +1,461 @@
+// Planners.cpp — see Planners.h. Reference citations are relative to the RPMPLv2 tree.
+#include "Planners.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <stdexcept>
+#include <string>
+
+namespace rvsplan
+{
+	namespace
+	{
+		using Clock = std::chrono::steady_clock;
+		using Coord = std::vector<float>;
+
+		inline uint64_t splitmix64(uint64_t x)
+		{
+			x += 0x9E3779B97F4A7C15ull;
+			x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+			x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+			return x ^ (x >> 31);
+		}
+
+		struct Rng                       // counter based: value k of run `seed` is a pure function of (seed, k)
+		{
+			uint64_t seed = 0, counter = 0;
+			float uniform()              // [-1, 1) like Eigen::VectorXf::Random
+			{
+				const uint64_t h = splitmix64(seed ^ (0xD1B54A32D192ED03ull * ++counter));
+				return float(h >> 40) * (2.0f / 16777216.0f) - 1.0f;
+			}
+		};
+
+		inline float norm(const float *a, const float *b, int n)        // RealVectorSpace::getNorm (:47-50)
+		{
+			float s = 0.f;
+			for (int i = 0; i < n; i++) { const float d = a[i] - b[i]; s += d * d; }
+			return std::sqrt(s);
+		}
+	}
+
+	// ---- Tree ------------------------------------------------------------------------------------------------------------
+	int Tree::add(const float *coord_, int parent)
+	{
+		q.insert(q.end(), coord_, coord_ + n);
+		Node nd;
+		nd.parent = parent;
+		nodes.push_back(nd);
+		return int(nodes.size()) - 1;
+	}
+
+	int Tree::nearest(const float *coord_) const
+	{
+		int best = -1;
+		float best_d = INFINITY;
+		const int count = int(nodes.size());
+		for (int k = 0; k < count; k++)
+		{
+			const float *p = &q[size_t(k) * n];
+			float s = 0.f;
+			for (int i = 0; i < n; i++) { const float d = p[i] - coord_[i]; s += d * d; }
+			if (s < best_d) { best_d = s; best = k; }
+		}
+		return best;
+	}
+
+	// ---- one planner run ---------------------------------------------------------------------------------------------------
+	class PlannerRun
+	{
+	public:
+		PlannerRun(const PlannerConfig &cfg_, const SpaceBackend &space, SlotAllocator &slots_, const float *q_start_, const float *q_goal_,
+				   uint64_t seed, Clock::time_point t0_, bool skip_invalid_)
+			: cfg(cfg_), n(space.numDofs()), lo(space.limitsLo()), hi(space.limitsHi()), eq_thr(space.equalityThreshold()), slots(slots_),
+			  trees{Tree(space.numDofs()), Tree(space.numDofs())}, q_start(q_start_, q_start_ + space.numDofs()),
+			  q_goal(q_goal_, q_goal_ + space.numDofs()), t0(t0_), skip_invalid(skip_invalid_)
+		{
+			rng.seed = splitmix64(seed);
+			if (cfg.kind == PlannerKind::RBTConnect) cfg.spine.num_layers = 1;     // a bur spine is a one-layer generalized spine
+		}
+
+		Task<int> solve()
+		{
+			// RRTConnect ctor (RRTConnect.cpp:13-25): both ends must be valid
+			req.kind = Request::VALID; req.count = 2;
+			req.q1 = q_start; req.q1.insert(req.q1.end(), q_goal.begin(), q_goal.end());
+			co_await Query{*this};
+			res.num_valid += 2;
+			if (!req.flags[0] || !req.flags[1])
+			{
+				invalid_ends = req.flags[0] ? "Goal position is invalid!" : "Start position is invalid!";
+				finish(false);
+				co_return 0;
+			}
+			trees[0].add(q_start.data(), -1);
+			trees[1].add(q_goal.data(), -1);
+			res.states = 2;
+			int t = 0;                   // 0: tree from q_start, 1: tree from q_goal
+			Coord q_e(n), q_new(n);
+			while (true)
+			{
+				Status status = Status::None;
+				randomState(nullptr, q_e.data());
+				int near = trees[t].nearest(q_e.data());
+				bool bur = false;
+				if (cfg.kind != PlannerKind::RRTConnect)
+				{
+					const float d_c = co_await computeDistance(t, near);
+					bur = d_c > cfg.spine.d_crit;
+				}
+				if (bur)
+				{
+					// RBTConnect.cpp:32-40 / RGBTConnect.cpp:33-45: NUM_SPINES (generalized) spines from q_near, one spine query
+					req.kind = Request::SPINES; req.count = cfg.num_spines; req.gen2 = true;
+					req.q1.resize(size_t(cfg.num_spines) * n);
+					req.slots.assign(size_t(cfg.num_spines), trees[t].nodes[near].slot);
+					for (int s = 0; s < cfg.num_spines; s++) randomStateAround(trees[t].coord(near), &req.q1[size_t(s) * n]);
+					co_await Query{*this};
+					res.num_spines += cfg.num_spines;
+					for (int s = 0; s < cfg.num_spines; s++)
+					{
+						int parent = near, last = near;
+						last = addLayers(t, s, parent);
+						status = Status(req.flags[s]);
+						if (s == cfg.num_spines - 1) std::copy_n(trees[t].coord(last), n, q_new.begin());
+					}
+				}
+				else
+				{
+					const Coord from(trees[t].coord(near), trees[t].coord(near) + n);
+					status = co_await extend(from, q_e, q_new);
+					if (status != Status::Trapped) trees[t].add(q_new.data(), near);
+				}
+				t = 1 - t;
+				if (status != Status::Trapped)
+				{
+					near = trees[t].nearest(q_new.data());
+					if (cfg.kind == PlannerKind::RRTConnect) status = co_await connect(t, near, q_new, cfg.max_extension_steps);
+					else status = co_await connectGenSpine(t, near, q_new);
+				}
+				res.iterations++;
+				res.states = trees[0].size() + trees[1].size();
+				if (status == Status::Reached)
+				{
+					computePath();
+					finish(true);
+					co_return 0;
+				}
+				if (elapsed() >= cfg.max_planning_time || res.states >= cfg.max_num_states || res.iterations >= cfg.max_num_iter)
+				{
+					finish(false);
+					co_return 0;
+				}
+			}
+		}
+
+		struct Query
+		{
+			PlannerRun &r;
+			bool await_ready() const noexcept { return false; }
+			void await_suspend(std::coroutine_handle<> h) const noexcept { r.resume_at = h; }
+			void await_resume() const noexcept {}
+		};
+
+		Request req;
+		std::coroutine_handle<> resume_at{};
+		PlannerResult res;
+		std::string invalid_ends;
+		bool finished = false;
+
+	private:
+		float elapsed() const { return std::chrono::duration<float>(Clock::now() - t0).count(); }
+		void finish(bool ok) { res.success = ok; res.planning_time = elapsed(); finished = true; req.kind = Request::NONE; }
+
+		// RealVectorSpace::getRandomState (RealVectorSpace.cpp:27-41)
+		void randomState(const float *center, float *out)
+		{
+			for (int i = 0; i < n; i++)
+			{
+				out[i] = ((hi[i] - lo[i]) * rng.uniform() + lo[i] + hi[i]) / 2;
+				if (center) out[i] += center[i];
+			}
+		}
+
+		// RBTConnect::getRandomState(q_center) (RBTConnect.cpp:69-81): saturate to DELTA, prune to the joint limits
+		void randomStateAround(const float *center, float *out)
+		{
+			Coord tmp(n);
+			do
+			{
+				randomState(center, tmp.data());
+				const float dist = norm(center, tmp.data(), n);                                    // interpolateEdge (:78-91)
+				if (dist > 0) for (int i = 0; i < n; i++) tmp[i] = center[i] + (tmp[i] - center[i]) * (cfg.delta / dist);
+				pruneEdge(center, tmp.data(), out);
+			} while (norm(center, out, n) < eq_thr);                                                // isEqual (:53-59)
+		}
+
+		// RealVectorSpace::pruneEdge (:118-163) with the robot's joint limits
+		void pruneEdge(const float *q1, const float *q2, float *out) const
+		{
+			std::vector<float> bounds(n);
+			std::vector<int> indices;
+			for (int k = 0; k < n; k++)
+			{
+				if (q2[k] > hi[k]) { bounds[k] = hi[k]; indices.push_back(k); }
+				else if (q2[k] < lo[k]) { bounds[k] = lo[k]; indices.push_back(k); }
+			}
+			for (int idx : indices)
+			{
+				const float t = (bounds[idx] - q1[idx]) / (q2[idx] - q1[idx]);
+				bool found = true;
+				for (int k = 0; k < n; k++)
+				{
+					out[k] = q1[k] + t * (q2[k] - q1[k]);
+					if (out[k] < lo[k] - eq_thr || out[k] > hi[k] + eq_thr) { found = false; break; }
+				}
+				if (found)
+				{
+					for (int k = 0; k < n; k++) out[k] = q1[k] + t * (q2[k] - q1[k]);
+					return;
+				}
+			}
+			std::copy_n(q2, n, out);
+		}
+
+		// RealVectorSpace::interpolateEdge2 (:95-114)
+		Status interpolateEdge2(const float *q1, const float *q2, float step, float *out) const
+		{
+			const float dist = norm(q1, q2, n);
+			if (step < dist)
+			{
+				if (dist > 0) for (int i = 0; i < n; i++) out[i] = q1[i] + (q2[i] - q1[i]) * (step / dist);
+				else std::copy_n(q2, n, out);
+				return Status::Advanced;
+			}
+			std::copy_n(q2, n, out);
+			return Status::Reached;
+		}
+
+		// computeDistance with the State cache rule (RealVectorSpace.cpp:320-321): reuse d_c when it is real and > 0
+		Task<float> computeDistance(int t, int idx)
+		{
+			Node &nd = trees[t].nodes[idx];
+			if (nd.d_c > 0 && nd.is_real) co_return nd.d_c;
+			int slot = nd.slot;
+			if (slot < 0) slot = slots.next();
+			req.kind = Request::DISTANCE; req.count = 1;
+			req.q1.assign(trees[t].coord(idx), trees[t].coord(idx) + n);
+			req.slots.assign(1, slot);
+			co_await Query{*this};
+			res.num_distances++;
+			Node &nd2 = trees[t].nodes[idx];                    // the vector may have grown meanwhile
+			nd2.slot = slot; nd2.d_c = req.d[0]; nd2.is_real = true;
+			co_return nd2.d_c;
+		}
+
+		// RRTConnect::extend (RRTConnect.cpp:92-106): one EPS_STEP towards q_e, kept when the edge is valid
+		Task<Status> extend(Coord from, Coord q_e, Coord &q_new)
+		{
+			const Status status = interpolateEdge2(from.data(), q_e.data(), cfg.eps_step, q_new.data());
+			req.kind = Request::EDGES; req.count = 1;
+			req.q1 = from; req.q2 = q_new;
+			co_await Query{*this};
+			res.num_edges++;
+			co_return req.flags[0] ? status : Status::Trapped;
+		}
+
+		// RRTConnect::connect (RRTConnect.cpp:108-125). The marching points q_{k+1} = interpolateEdge2(q_k, q_e, EPS_STEP) do not
+		// depend on the verdicts, so all (up to `steps`) edges go out as ONE query and the longest valid prefix is kept.
+		Task<Status> connect(int t, int idx, Coord q_e, int steps)
+		{
+			if (steps <= 0) co_return Status::Advanced;
+			Coord cur(trees[t].coord(idx), trees[t].coord(idx) + n), next(n);
+			req.kind = Request::EDGES; req.q1.clear(); req.q2.clear();
+			std::vector<Status> st;
+			for (int k = 0; k < steps; k++)
+			{
+				st.push_back(interpolateEdge2(cur.data(), q_e.data(), cfg.eps_step, next.data()));
+				req.q1.insert(req.q1.end(), cur.begin(), cur.end());
+				req.q2.insert(req.q2.end(), next.begin(), next.end());
+				if (st.back() == Status::Reached) break;
+				cur = next;
+			}
+			const int E = int(st.size());
+			req.count = E;
+			co_await Query{*this};
+			res.num_edges += E;
+			int parent = idx;
+			for (int k = 0; k < E; k++)
+			{
+				if (!req.flags[k]) co_return Status::Trapped;
+				parent = trees[t].add(&req.q2[size_t(k) * n], parent);
+			}
+			co_return st.back();               // Reached, or Advanced when MAX_EXTENSION_STEPS ran out
+		}
+
+		// adds the states of spine s (answer of the last SPINES query) below `parent`; returns the last node
+		int addLayers(int t, int s, int parent)
+		{
+			const int layers = std::max(1, int(req.n_layers[s]));
+			const size_t stride = size_t(cfg.spine.num_layers) * n;
+			for (int l = 0; l < layers; l++) parent = trees[t].add(&req.q_layers[size_t(s) * stride + size_t(l) * n], parent);
+			return parent;
+		}
+
+		// RBTConnect::connectSpine (RBTConnect.cpp:152-180) / RGBTConnect::connectGenSpine (RGBTConnect.cpp:120-150)
+		Task<Status> connectGenSpine(int t, int idx, Coord q_e)
+		{
+			float d_c = co_await computeDistance(t, idx);
+			int q_new = idx;
+			Status status = Status::Advanced;
+			int num_ext = 0;
+			while (status == Status::Advanced && num_ext++ < cfg.max_extension_steps)
+			{
+				const int q_temp = q_new;
+				if (d_c > cfg.spine.d_crit)
+				{
+					req.kind = Request::SPINES; req.count = 1; req.gen2 = true;
+					req.q1 = q_e;
+					req.slots.assign(1, trees[t].nodes[q_temp].slot);
+					co_await Query{*this};
+					res.num_spines++;
+					status = Status(req.flags[0]);
+					q_new = addLayers(t, 0, q_temp);
+					d_c = co_await computeDistance(t, q_new);
+				}
+				else
+				{
+					// below D_CRIT the loop stays in RRT mode until it ends (d_c is not refreshed, :141-146): march the rest at once
+					status = co_await connect(t, q_temp, q_e, cfg.max_extension_steps - num_ext + 1);
+					co_return status;
+				}
+			}
+			co_return status;
+		}
+
+		// RRTConnect::computePath (RRTConnect.cpp:127-145)
+		void computePath()
+		{
+			std::vector<int> chain;
+			for (int k = trees[0].nodes[trees[0].size() - 1].parent; k >= 0; k = trees[0].nodes[k].parent) chain.push_back(k);
+			std::reverse(chain.begin(), chain.end());
+			for (int k : chain) res.path.insert(res.path.end(), trees[0].coord(k), trees[0].coord(k) + n);
+			for (int k = trees[1].size() - 1; k >= 0; k = trees[1].nodes[k].parent) res.path.insert(res.path.end(), trees[1].coord(k), trees[1].coord(k) + n);
+		}
+
+		PlannerConfig cfg;
+		int n;
+		const float *lo, *hi;
+		float eq_thr;
+		SlotAllocator &slots;
+		Rng rng;
+		Tree trees[2];
+		Coord q_start, q_goal;
+		Clock::time_point t0;
+		bool skip_invalid;
+	};
+
+	// ---- the pool -----------------------------------------------------------------------------------------------------------
+	std::vector<PlannerResult> PlannerPool::solve(const float *q_start, const float *q_goal, const uint64_t *seeds, int P, bool skip_invalid)
+	{
+		const int n = backend.numDofs();
+		SlotAllocator slots;
+		const auto t0 = Clock::now();
+		std::vector<std::unique_ptr<PlannerRun>> runs;
+		std::vector<Task<int>> tasks;
+		runs.reserve(size_t(P));
+		tasks.reserve(size_t(P));
+		for (int p = 0; p < P; p++)
+		{
+			runs.emplace_back(new PlannerRun(cfg, backend, slots, q_start + size_t(p) * n, q_goal + size_t(p) * n, seeds ? seeds[p] : uint64_t(p), t0, skip_invalid));
+			tasks.emplace_back(runs.back()->solve());
+			tasks.back().handle().resume();
+		}
+		std::vector<float> q1, q2, d, q_layers;
+		std::vector<int32_t> sl, n_layers;
+		std::vector<uint8_t> flags;
+		std::vector<int> who;
+		int slot_cap = 0;
+		const size_t layer_stride = size_t(cfg.kind == PlannerKind::RBTConnect ? 1 : cfg.spine.num_layers) * n;
+		SpineParams sp = cfg.spine;
+		if (cfg.kind == PlannerKind::RBTConnect) sp.num_layers = 1;
+		while (true)
+		{
+			bool any = false;
+			for (int kind = Request::VALID; kind <= Request::SPINES; kind++)
+			{
+				who.clear(); q1.clear(); q2.clear(); sl.clear();
+				int total = 0;
+				for (int p = 0; p < P; p++)
+				{
+					Request &r = runs[p]->req;
+					if (runs[p]->finished || r.kind != kind) continue;
+					who.push_back(p);
+					total += r.count;
+					q1.insert(q1.end(), r.q1.begin(), r.q1.begin() + size_t(r.count) * n);
+					if (kind == Request::EDGES) q2.insert(q2.end(), r.q2.begin(), r.q2.begin() + size_t(r.count) * n);
+					if (kind == Request::DISTANCE || kind == Request::SPINES) sl.insert(sl.end(), r.slots.begin(), r.slots.begin() + r.count);
+				}
+				if (who.empty()) continue;
+				any = true;
+				num_calls++;
+				if (slots.used() > slot_cap)
+				{
+					slot_cap = std::max(256, 2 * slots.used());
+					backend.reserveSlots(slot_cap);
+				}
+				switch (kind)
+				{
+					case Request::VALID:
+						flags.resize(size_t(total));
+						backend.isValid(q1.data(), total, flags.data());
+						break;
+					case Request::EDGES:
+						flags.resize(size_t(total));
+						backend.isValidEdges(q1.data(), q2.data(), total, flags.data());
+						break;
+					case Request::DISTANCE:
+						d.resize(size_t(total));
+						backend.distanceToSlots(q1.data(), total, sl.data(), d.data());
+						break;
+					default:
+						flags.resize(size_t(total)); d.resize(size_t(total)); n_layers.resize(size_t(total));
+						q_layers.resize(size_t(total) * layer_stride);
+						backend.extendGenSpines(sl.data(), q1.data(), total, sp, true, q_layers.data(), n_layers.data(), d.data(), flags.data());
+						break;
+				}
+				size_t off = 0;
+				for (int p : who)
+				{
+					Request &r = runs[p]->req;
+					const size_t c = size_t(r.count);
+					if (kind == Request::VALID || kind == Request::EDGES || kind == Request::SPINES) r.flags.assign(flags.begin() + off, flags.begin() + off + c);
+					if (kind == Request::DISTANCE || kind == Request::SPINES) r.d.assign(d.begin() + off, d.begin() + off + c);
+					if (kind == Request::SPINES)
+					{
+						r.n_layers.assign(n_layers.begin() + off, n_layers.begin() + off + c);
+						r.q_layers.assign(q_layers.begin() + off * layer_stride, q_layers.begin() + (off + c) * layer_stride);
+					}
+					off += c;
+					r.kind = Request::NONE;
+					runs[p]->res.rounds++;
+				}
+				// resume after the scatter: a resumed run overwrites its request with the next one (possibly of a kind served later in this round)
+				for (int p : who) runs[p]->resume_at.resume();
+			}
+			if (!any) break;
+			num_rounds++;
+		}
+		std::vector<PlannerResult> out;
+		out.reserve(size_t(P));
+		for (int p = 0; p < P; p++)
+		{
+			auto &pr = tasks[p].handle().promise();
+			if (pr.error) std::rethrow_exception(pr.error);
+			if (!runs[p]->invalid_ends.empty() && !skip_invalid) throw std::domain_error(runs[p]->invalid_ends);
+			out.push_back(std::move(runs[p]->res));
+		}
+		return out;
+	}
+}

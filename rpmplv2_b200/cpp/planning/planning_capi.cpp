@@ -1,0 +1,52 @@
+// planning_capi.cpp — librvs_planning.so: include/rvs_planning.h over CudaBackend. There is no CPU path in this library.
+#include "planning_capi.h"
+
+#include <exception>
+#include <string>
+
+#include "CudaBackend.h"
+
+namespace
+{
+	thread_local std::string g_error;
+}
+
+extern "C" {
+
+void rvsplan_default_config(int32_t kind, rvsplan_config *out)
+{
+	if (!out) return;
+	out->kind = kind;
+	out->max_num_iter = 1000000000; out->max_num_states = 1000000000; out->max_planning_time = 10.f;   // configuration_*.yaml:1-3
+	out->eps_step = 0.1f; out->max_extension_steps = 50;                                               // configuration_rrtconnect.yaml:4-5
+	out->delta = 3.14159f; out->num_spines = 7;                                                        // configuration_rbtconnect.yaml:5-6
+	out->spine.num_layers = kind == RVSPLAN_RBT_CONNECT ? 1 : 5;                                       // configuration_rgbtconnect.yaml:4
+	out->spine.num_iter_spine = 1; out->spine.use_expanded_bubble = 1; out->spine.d_crit = 0.05f;      // configuration_rbtconnect.yaml:4,7,8
+}
+
+const char *rvsplan_last_error(void) { return g_error.c_str(); }
+
+int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
+						int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats)
+{
+	if (!h || !cfg || !q_start || !q_goal || !results || P < 0) { g_error = "rvsplan_solve_batch: NULL argument or P < 0"; return RVS_ERR_INVALID_ARGUMENT; }
+	if (cfg->kind < RVSPLAN_RRT_CONNECT || cfg->kind > RVSPLAN_RGBT_CONNECT || cfg->num_spines < 1 || cfg->spine.num_layers < 1 ||
+		cfg->max_extension_steps < 1 || !(cfg->eps_step > 0)) { g_error = "rvsplan_solve_batch: bad planner configuration"; return RVS_ERR_INVALID_ARGUMENT; }
+	try
+	{
+		rvsplan::CudaBackend backend(h);
+		rvsplan::PlannerPool pool(backend, rvsplan::config_from_c(*cfg));
+		const int64_t launches0 = rvs_launch_count(h);
+		const std::vector<rvsplan::PlannerResult> res = pool.solve(q_start, q_goal, seeds, P, true);
+		rvsplan::results_to_c(res, backend.numDofs(), results, paths, max_path);
+		if (pool_stats) { pool_stats[0] = pool.rounds(); pool_stats[1] = pool.backendCalls(); pool_stats[2] = rvs_launch_count(h) - launches0; }
+	}
+	catch (const std::exception &e)
+	{
+		g_error = e.what();
+		return RVS_ERR_CUDA;
+	}
+	return RVS_OK;
+}
+
+}

@@ -362,6 +362,20 @@ int rvs_set_params(rvs_handle h, const rvs_params *params) {
     return select_table(h);
 }
 
+int rvs_get_params(rvs_handle h, rvs_params *out) {
+    if (!h || !out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = h->prm;
+    return RVS_OK;
+}
+
+int rvs_num_dofs(rvs_handle h) { return h ? h->h_robot.n : 0; }
+
+int rvs_get_limits(rvs_handle h, float *limit_lo, float *limit_hi) {
+    if (!h || !limit_lo || !limit_hi) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL argument");
+    for (int i = 0; i < h->h_robot.n; i++) { limit_lo[i] = h->h_robot.limit_lo[i]; limit_hi[i] = h->h_robot.limit_hi[i]; }
+    return RVS_OK;
+}
+
 int rvs_set_stream(rvs_handle h, void *cuda_stream) {
     RVS_TRY(enter(h));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));

@@ -30,6 +30,9 @@ SYMBOLS = {
     "rvs_destroy": (ctypes.c_int, [_H]),
     "rvs_last_error": (ctypes.c_char_p, [_H]),
     "rvs_set_params": (ctypes.c_int, [_H, ctypes.POINTER(RvsParams)]),
+    "rvs_get_params": (ctypes.c_int, [_H, ctypes.POINTER(RvsParams)]),
+    "rvs_num_dofs": (ctypes.c_int, [_H]),
+    "rvs_get_limits": (ctypes.c_int, [_H, c_f32p, c_f32p]),
     "rvs_set_stream": (ctypes.c_int, [_H, ctypes.c_void_p]),
     "rvs_get_stream": (ctypes.c_void_p, [_H]),
     "rvs_sync": (ctypes.c_int, [_H]),

@@ -1,0 +1,96 @@
+"""ctypes binding of librvs_planning.so (include/rvs_planning.h): RRT-Connect / RBT-Connect / RGBT-Connect over the batched
+state-space queries of the CUDA engine, P planner runs in lockstep. No CPU fallback: the library links librvs_cuda.so."""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+from .engine import Engine, RvsError, c_f32p
+from .robots import RvsSpineParams
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "librvs_planning.so")
+
+RRT_CONNECT, RBT_CONNECT, RGBT_CONNECT = 0, 1, 2
+KIND_NAMES = {RRT_CONNECT: "RRT-Connect", RBT_CONNECT: "RBT-Connect", RGBT_CONNECT: "RGBT-Connect"}
+
+
+class PlanConfig(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("max_num_iter", ctypes.c_int64), ("max_num_states", ctypes.c_int64),
+                ("max_planning_time", ctypes.c_float), ("eps_step", ctypes.c_float), ("max_extension_steps", ctypes.c_int32),
+                ("delta", ctypes.c_float), ("num_spines", ctypes.c_int32), ("spine", RvsSpineParams)]
+
+
+class PlanResult(ctypes.Structure):
+    _fields_ = [("success", ctypes.c_int32), ("invalid_ends", ctypes.c_int32), ("iterations", ctypes.c_int64), ("states", ctypes.c_int64),
+                ("planning_time", ctypes.c_float), ("path_len", ctypes.c_int32), ("rounds", ctypes.c_int64), ("num_valid", ctypes.c_int64),
+                ("num_edges", ctypes.c_int64), ("num_distances", ctypes.c_int64), ("num_spines", ctypes.c_int64)]
+
+
+SYMBOLS = {
+    "rvsplan_default_config": (None, [ctypes.c_int32, ctypes.POINTER(PlanConfig)]),
+    "rvsplan_solve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
+                                           ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
+    "rvsplan_last_error": (ctypes.c_char_p, []),
+}
+
+_lib = None
+
+
+def load_library(path: Optional[str] = None):
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise FileNotFoundError(f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def default_config(kind: int = RGBT_CONNECT, **overrides) -> PlanConfig:
+    cfg = PlanConfig()
+    load_library().rvsplan_default_config(kind, ctypes.byref(cfg))
+    for k, v in overrides.items():
+        if k in ("num_layers", "num_iter_spine", "use_expanded_bubble", "d_crit"):
+            setattr(cfg.spine, k, v)
+        else:
+            setattr(cfg, k, v)
+    return cfg
+
+
+def unpack_results(results, paths, n):
+    out = []
+    for p, r in enumerate(results):
+        d = {f: getattr(r, f) for f, _ in PlanResult._fields_}
+        d["path"] = None if paths is None else paths[p, :min(r.path_len, paths.shape[1])].copy()
+        out.append(d)
+    return out
+
+
+def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_path: int = 512):
+    """P planner runs on the engine's resident scene. q_start / q_goal: [P, n] (or [n], broadcast over the seeds).
+    Returns (list of result dicts incl. 'path' [len, n], pool stats dict)."""
+    lib = load_library()
+    n = eng.n
+    qs, qg = np.atleast_2d(np.asarray(q_start, np.float32)), np.atleast_2d(np.asarray(q_goal, np.float32))
+    P = len(seeds) if seeds is not None else qs.shape[0]
+    qs = np.ascontiguousarray(np.broadcast_to(qs, (P, n)))
+    qg = np.ascontiguousarray(np.broadcast_to(qg, (P, n)))
+    sd = np.ascontiguousarray(np.arange(P) if seeds is None else seeds, np.uint64)
+    results = (PlanResult * P)()
+    paths = np.zeros((P, max_path, n), np.float32)
+    stats = (ctypes.c_int64 * 3)()
+    rc = lib.rvsplan_solve_batch(eng._h, ctypes.byref(cfg), qs.ctypes.data_as(c_f32p), qg.ctypes.data_as(c_f32p),
+                                 sd.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), P, results, paths.ctypes.data_as(c_f32p), max_path, stats)
+    if rc != 0:
+        raise RvsError(rc, (lib.rvsplan_last_error() or b"").decode())
+    return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1]), "kernel_launches": int(stats[2])}

@@ -25,6 +25,13 @@ def xarm6_scenario1():
     return robots.xarm6(), mn, mx, np.array([1, 0, 0, 0, 0], np.uint8), np.array([0.05, 1000, 1000, 1000, 1000], np.float32)
 
 
+def spatial10_scenario1():
+    """spatial_10dof scenario1: the same ground + four pillars around a 10-DOF spatial chain, radii 0.025, ground_included 2
+    (/root/reference/data/spatial_10dof/scenario1/scenario1.yaml:1-40)."""
+    _, mn, mx, g, tol = xarm6_scenario1()
+    return robots.spatial(10), mn, mx, g, tol
+
+
 def chain_scene(rb, M, seed=77):
     """Random boxes around a planar / spatial chain whose reach is ~ n * link length."""
     rng = np.random.default_rng(seed)

@@ -1,0 +1,117 @@
+"""Row f-1 / f-4: RRT-Connect, RBT-Connect and RGBT-Connect on the batched state space (rpmplv2_b200/cpp/planning).
+
+CPU part (oracle backend): the planners solve the reference's shipped scenarios (planar_2dof scenario_test, xarm6 scenario1,
+spatial_10dof scenario1 — geometry retyped in tests/scenes.py), every returned path starts/ends at q_start/q_goal and is
+collision-free when densely re-sampled, and running P runs in lockstep (one pool) gives exactly the runs a pool of one gives
+(batching queries across runs must not change any run).
+GPU part: the same planner code on the CUDA backend must reproduce the oracle-backed runs seed by seed (the two arms differ
+only in who answers the state-space queries), and its paths must be collision-free according to the ORACLE.
+"""
+import numpy as np
+import pytest
+
+import scenes
+from rpmplv2_b200 import engine, planning, robots
+
+SCENARIOS = {
+    # q_start / q_goal: data/planar_2dof/scenario_test/scenario_test.yaml:24-25, data/xarm6/scenario1/scenario1.yaml:31-32,
+    # data/spatial_10dof/scenario1/scenario1.yaml:31-32 (of the reference tree)
+    "planar2": (scenes.planar2_scenario_test, [-2, -2.5], [2, 2.5]),
+    "xarm6": (scenes.xarm6_scenario1, [0, 0.7854, -2.3562, 0, 0, 0], [3.14159, 0.7854, -2.3562, 3.14159, 0, 3.14159]),
+    "spatial10": (scenes.spatial10_scenario1, [0, 1.57, 0, 0, 0, 0, 0, 0, 0, 0], [3.14, 1.57, 0, 0, 0, 0, 0, 0, 0, 0]),
+}
+
+
+def _oracle(ob, name):
+    fn, qs, qg = SCENARIOS[name]
+    rb, mn, mx, g, tol = fn()
+    o = ob.Oracle(rb, robots.default_params())
+    o.set_obstacles(mn, mx, g, tol)
+    return o, (rb, mn, mx, g, tol), np.asarray(qs, np.float32), np.asarray(qg, np.float32)
+
+
+def _dense_path_is_free(o, path, step=0.01):
+    pts = []
+    for a, b in zip(path[:-1], path[1:]):
+        k = max(2, int(np.ceil(np.linalg.norm(b - a) / step)) + 1)
+        pts.append(a + (b - a) * np.linspace(0, 1, k, dtype=np.float32)[:, None])
+    return bool(o.is_valid(np.concatenate(pts)).all())
+
+
+@pytest.mark.parametrize("name", ["planar2", "xarm6", "spatial10"])
+@pytest.mark.parametrize("kind", [planning.RRT_CONNECT, planning.RBT_CONNECT, planning.RGBT_CONNECT])
+def test_oracle_backed_planners_solve_the_shipped_scenarios(ob, name, kind):
+    o, _, qs, qg = _oracle(ob, name)
+    cfg = planning.default_config(kind, max_planning_time=60.0, max_num_iter=20000)
+    P = 4
+    res, _ = ob.plan_solve_batch(o, cfg, qs, qg, seeds=np.arange(P) + 100, max_path=2048)
+    assert all(r["success"] for r in res)
+    for r in res:
+        path = r["path"]
+        assert r["path_len"] == len(path) >= 2 and r["states"] >= r["path_len"]
+        assert (path[0] == qs).all() and (path[-1] == qg).all()
+        assert _dense_path_is_free(o, path)
+        if kind == planning.RRT_CONNECT:
+            assert r["num_distances"] == 0 and r["num_spines"] == 0
+            assert np.linalg.norm(np.diff(path, axis=0), axis=1).max() <= cfg.eps_step + 1e-4     # every edge is one EPS_STEP
+        else:
+            assert r["num_distances"] > 0 and r["num_spines"] > 0
+    # lockstep over the P runs == P pools of one run
+    res_l, st = ob.plan_solve_batch(o, cfg, qs, qg, seeds=np.arange(P) + 100, max_path=2048, lockstep=True)
+    assert st["rounds"] > 0 and st["backend_calls"] >= st["rounds"]
+    for a, b in zip(res, res_l):
+        assert a["iterations"] == b["iterations"] and a["states"] == b["states"] and (a["path"] == b["path"]).all()
+    # different seeds give different trees
+    assert len({r["states"] for r in res}) > 1
+
+
+def test_invalid_start_is_reported_not_planned(ob):
+    o, _, qs, qg = _oracle(ob, "planar2")
+    bad = np.array([np.pi / 4, 0], np.float32)            # link 2 reaches (1.41, 1.41)... link 1 passes through the box at (1, 1)
+    assert not o.is_valid(bad[None])[0]
+    res, _ = ob.plan_solve_batch(o, planning.default_config(planning.RGBT_CONNECT), np.stack([bad, qs]), np.stack([qg, qg]), seeds=[1, 2])
+    assert res[0]["invalid_ends"] == 1 and not res[0]["success"] and res[0]["iterations"] == 0
+    assert res[1]["success"] and res[1]["invalid_ends"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["planar2", "xarm6", "spatial10"])
+@pytest.mark.parametrize("kind", [planning.RRT_CONNECT, planning.RBT_CONNECT, planning.RGBT_CONNECT])
+def test_gpu_backed_planners_reproduce_the_oracle_backed_runs(ob, name, kind):
+    o, (rb, mn, mx, g, tol), qs, qg = _oracle(ob, name)
+    eng = engine.Engine(rb)
+    eng.set_obstacles(mn, mx, g, tol)
+    cfg = planning.default_config(kind, max_planning_time=60.0, max_num_iter=20000)
+    P = 12
+    seeds = np.arange(P) + 7
+    res_g, st = planning.solve_batch(eng, cfg, qs, qg, seeds=seeds, max_path=2048)
+    res_o, _ = ob.plan_solve_batch(o, cfg, qs, qg, seeds=seeds, max_path=2048, threads=4)
+    assert st["kernel_launches"] >= st["backend_calls"] > 0
+    same = 0
+    for a, b in zip(res_g, res_o):
+        assert a["success"] and b["success"]
+        assert (a["path"][0] == qs).all() and (a["path"][-1] == qg).all()
+        assert _dense_path_is_free(o, a["path"])           # GPU-planned path checked by the CPU oracle
+        if a["iterations"] == b["iterations"] and a["states"] == b["states"] and a["path_len"] == b["path_len"]:
+            assert np.abs(a["path"] - b["path"]).max() <= 1e-4
+            same += 1
+    # the arms differ only by last-ulp effects of FK (device vs host sin/cos) on a few queries; a diverged run is still a valid run
+    assert same >= P - 2
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_planner_pool_scales_in_rounds_not_runs():
+    """64 runs in lockstep need about as many backend rounds as the longest single run, not 64 times as many."""
+    fn, qs, qg = SCENARIOS["xarm6"]
+    rb, mn, mx, g, tol = fn()
+    eng = engine.Engine(rb)
+    eng.set_obstacles(mn, mx, g, tol)
+    cfg = planning.default_config(planning.RGBT_CONNECT, max_planning_time=60.0)
+    res1, st1 = planning.solve_batch(eng, cfg, qs, qg, seeds=[3])
+    res64, st64 = planning.solve_batch(eng, cfg, qs, qg, seeds=np.arange(64))
+    assert all(r["success"] for r in res64)
+    longest = max(r["rounds"] for r in res64)
+    assert st64["backend_calls"] <= 1.2 * longest + 8
+    assert st1["backend_calls"] == res1[0]["rounds"]
+    eng.close()
