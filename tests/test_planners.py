@@ -112,6 +112,8 @@ def test_gpu_planner_pool_scales_in_rounds_not_runs():
     res64, st64 = planning.solve_batch(eng, cfg, qs, qg, seeds=np.arange(64))
     assert all(r["success"] for r in res64)
     longest = max(r["rounds"] for r in res64)
-    assert st64["backend_calls"] <= 1.2 * longest + 8
+    # runs drift apart (one asks for spines while another asks for a distance), so a round can need one call per query kind
+    assert st64["backend_calls"] <= 2.5 * longest + 8
+    assert st64["backend_calls"] < 0.1 * sum(r["rounds"] for r in res64)
     assert st1["backend_calls"] == res1[0]["rounds"]
     eng.close()
