@@ -43,6 +43,7 @@ struct rvs_engine {
     ObstacleRec *d_obs = nullptr;
     int M = 0, obs_cap = 0;
     std::vector<ObstacleRec> h_obs, h_obs_scan;
+    std::vector<float> h_scan_dist;
     LaunchTable lt{};
     DevBuf buf[8];            // grow-only device staging for the host-pointer entry points
     int64_t launches = 0;
@@ -143,7 +144,7 @@ int check_params(rvs_engine *h, const rvs_params *p) {
 
 KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
     KArgs a{};
-    a.robot = h->d_robot; a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.M = h->M; a.N = N; a.q = d_q;
+    a.robot = h->d_robot; a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.scan_dist = reinterpret_cast<const float *>(h->d_obs + 2 * size_t(h->obs_cap)); a.M = h->M; a.N = N; a.q = d_q;
     a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
     a.num_checks = h->prm.num_interpolation_validity_checks; a.cull = h->cull;
     a.robot_n_hint = h->h_robot.n;
@@ -468,6 +469,14 @@ int upload_obstacles(rvs_engine *h) {
     }
     std::stable_sort(order.begin(), order.end());
     h->h_obs_scan.resize(size_t(M));
+    h->h_scan_dist.resize(size_t(M));
+    for (int k = 0; k < M; k++) {
+        // lower bound of the obstacle's distance from the base in float (the kernel's cut-off must never overestimate it)
+        const double d = std::sqrt(std::min(order[size_t(k)].first, 1e60));
+        float f = float(d);
+        if (double(f) > d) f = std::nextafterf(f, 0.0f);
+        h->h_scan_dist[size_t(k)] = f;
+    }
     for (int k = 0; k < M; k++) {
         ObstacleRec r = h->h_obs[size_t(order[size_t(k)].second)];
         r.flags = (r.flags & 1u) | (uint32_t(order[size_t(k)].second) << 8);
@@ -475,6 +484,7 @@ int upload_obstacles(rvs_engine *h) {
     }
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + h->obs_cap, h->h_obs_scan.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + 2 * size_t(h->obs_cap), h->h_scan_dist.data(), size_t(M) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
     return RVS_OK;
 }
@@ -497,7 +507,7 @@ int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max
         if (h->d_obs) RVS_CUDA(h, cudaFree(h->d_obs));
         h->d_obs = nullptr; h->obs_cap = 0;
         const int cap = M + M / 2 + 16;
-        RVS_CUDA(h, cudaMalloc(&h->d_obs, 2 * size_t(cap) * sizeof(ObstacleRec)));
+        RVS_CUDA(h, cudaMalloc(&h->d_obs, 2 * size_t(cap) * sizeof(ObstacleRec) + size_t(cap) * sizeof(float)));   // caller order, scan order, scan distances
         h->obs_cap = cap;
     }
     if (M != h->M && h->d_store) {          // the slot stride depends on M: cached states of another table are meaningless

@@ -47,12 +47,15 @@ constexpr int kWqUnroll = 2;                      // obstacles tested per scan i
 constexpr unsigned kNoHit = 0xFFFFFFFFu;
 constexpr unsigned kNoEntry = 0xFFFFFFFFu;
 
-// queue entry: lane (5) | link (5) << 5 | obstacle-in-segment (16) << 10 | edge code (6) << 26
+// Q0 hit word (one per lane and scan iteration with any hit): slot mask (2*G bits: slot s x first obstacle, then slot s x second
+// obstacle) | lane (5) << 12 | obstacle-pair-in-segment (15) << 17
+// Q1 / Q1b / Q2 entry: lane (5) | link (5) << 5 | obstacle-in-segment (16) << 10 | edge code (6) << 26
 template <int G> struct WqCaps {
-    static constexpr int q1 = 32 * G * kWqUnroll + 32;   // one scan iteration can push 32*G*unroll pairs on top of a leftover < 32
+    static constexpr int q0 = 64;                         // one scan iteration pushes <= 32 hit words on top of a leftover < 32
+    static constexpr int q1 = 32 * G * kWqUnroll + 32;   // one expansion unpacks <= 32*G*unroll pairs on top of a leftover < 32
     static constexpr int q1b = 64;                        // one re-cull round pushes <= 32 on top of a leftover < 32
     static constexpr int q2 = 32 * 12 + 32;               // one classify round pushes <= 32*12 edges on top of a leftover < 32
-    static constexpr int words = 8 + q1 + q1b + q2;       // 8 control words first: 3 tails, 3 work counters
+    static constexpr int words = 8 + q0 + q1 + q1b + q2;  // 8 control words first: 3 tails, 3 work counters
 };
 
 template <class R> struct WqBits;
@@ -72,6 +75,7 @@ template <class R, int G>
 __host__ __device__ inline size_t wq_smem_bytes(int L) {
     size_t b = size_t(3 * (L + 1)) * kWqStride * sizeof(R);               // skeleton
     b += size_t(L) * kWqStride * sizeof(typename WqBits<R>::type);        // per-link minima
+    b += size_t(L) * kWqStride * sizeof(R);                               // per-link reach (farthest axis point from the base)
     b += size_t(L) * sizeof(R);                                           // radii
     b = (b + 15) & ~size_t(15);
     b += size_t(kWqBlock) * sizeof(unsigned);                             // first-collision keys
@@ -84,13 +88,36 @@ struct WqCtx {
     const float4 *obs4;                       // scan-ordered obstacle table in HBM as pairs of 16-byte words (read through L1)
     R *skel;                                  // [3*(L+1)][kWqStride]
     typename WqBits<R>::type *best;           // [L][kWqStride]
+    R *reach;                                 // [L][kWqStride] max(|A - base|, |B - base|) of the link's axis
     R *radius;                                // [L]
     unsigned *hit;                            // [kWqBlock]
     volatile unsigned *tails;                 // this warp: [0] Q1, [1] Q1b, [2] Q2 tails; [4], [5], [6] entries popped from each
-    unsigned *q1, *q1b, *q2;                  // this warp's queues
+    unsigned *q0, *q1, *q1b, *q2;             // this warp's queues
     int M, seg_base, wbase;                   // wbase = first thread of this warp in the block
     R eq_thr, max_dist;
 };
+
+// carve the block's dynamic shared memory; cheap enough to redo inside the out-of-line drain (which gets scalars in registers
+// instead of a context object through local memory)
+template <class R, int G>
+__device__ __forceinline__ WqCtx<R> wq_make_ctx(unsigned char *smem, const float4 *obs4, int L, int M, int seg_base, R eq_thr, R max_dist) {
+    typedef typename WqBits<R>::type Bits;
+    const int warp = threadIdx.x >> 5;
+    WqCtx<R> c;
+    unsigned char *p = smem;
+    c.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
+    c.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqStride * sizeof(Bits);
+    c.reach = reinterpret_cast<R *>(p); p += size_t(L) * kWqStride * sizeof(R);
+    c.radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
+    p = smem + ((size_t(p - smem) + 15) & ~size_t(15));
+    c.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
+    unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * WqCaps<G>::words;
+    c.tails = wq; c.q0 = wq + 8; c.q1 = c.q0 + WqCaps<G>::q0; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
+    c.obs4 = obs4;
+    c.M = M; c.wbase = warp * 32; c.seg_base = seg_base;
+    c.eq_thr = eq_thr; c.max_dist = max_dist;
+    return c;
+}
 
 template <class R> __device__ __forceinline__ R wq_inf() { return R(__int_as_float(0x7f800000)); }
 
@@ -205,59 +232,105 @@ __device__ __forceinline__ unsigned wq_pop(volatile unsigned *tail, const unsign
     return e;
 }
 
-// run compacted phases while a queue holds a full warp of work (or anything at all when flushing)
-template <class R>
-__device__ __forceinline__ void wq_drain(const WqCtx<R> &c, bool flush) {
+// phase A': unpack up to 32 hit words of the scan (one lane each) into pair entries of Q1.  The scan pushes ONE word per lane and
+// iteration (a predicated store at a ballot-computed position); turning its bits into pairs here, with every lane busy, is ~4x
+// cheaper than a divergent per-lane loop inside the scan.  `n0` (Q0 fill, warp-uniform, kept in a register) is returned reduced.
+template <class R, int G>
+__device__ __forceinline__ unsigned wq_expand(const WqCtx<R> &c, unsigned n0, unsigned slotmap, int lane) {
+    const unsigned n = n0 < 32u ? n0 : 32u, base0 = n0 - n;
+    const unsigned w = unsigned(lane) < n ? c.q0[base0 + lane] : 0u;
+    unsigned m = w & ((1u << (2 * G)) - 1u);
+    const unsigned cnt = unsigned(__popc(m));
+    unsigned incl = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+    }
+    const unsigned total = __shfl_sync(0xffffffffu, incl, 31);
+    const unsigned t1 = c.tails[0];
+    unsigned pos = t1 + incl - cnt;
+    const unsigned from = (w >> 12) & 31u, j = (w >> 17) << 1;
+    while (m) {
+        const int b = __ffs(int(m)) - 1;
+        m &= m - 1u;
+        const int sl = b >= G ? b - G : b;
+        c.q1[pos++] = from | (((slotmap >> (5 * sl)) & 31u) << 5) | ((j + (b >= G ? 1u : 0u)) << 10);
+    }
+    __syncwarp();
+    if (lane == 0) c.tails[0] = t1 + total;
+    return base0;
+}
+
+// run compacted phases while a queue holds a full warp of work.  flush = 1: also unpack a partly filled Q0 (its words refer to
+// the CURRENT slot -> link map, so the scan empties it before the map changes); flush = 2: empty every queue.
+// Inlined at exactly ONE call site (the scan loop is arranged for that): the compacted phases are ~1500 instructions, and several
+// copies made the kernel outgrow the instruction cache (ncu: 31 % of the stall samples were `no_instruction`); an out-of-line
+// copy costs ~45 register spills around every call instead.
+template <class R, int G>
+__device__ __forceinline__ unsigned wq_drain(const WqCtx<R> &c, int flush, unsigned n0, unsigned slotmap) {
     const int lane = threadIdx.x & 31;
     for (;;) {
         __syncwarp();
         const unsigned t1 = c.tails[0], t1b = c.tails[1], t2 = c.tails[2];
-        if (t2 >= 32u || (flush && t2 > 0u && t1 == 0u && t1b == 0u)) {
+        if (t2 >= 32u || (flush == 2 && t2 > 0u && n0 == 0u && t1 == 0u && t1b == 0u)) {
             const unsigned e = wq_pop(&c.tails[2], c.q2, t2, lane);
             if (e != kNoEntry) wq_edge<R>(c, e);
-        } else if (t1b >= 32u || (flush && t1b > 0u && t1 == 0u)) {
+        } else if (t1b >= 32u || (flush == 2 && t1b > 0u && n0 == 0u && t1 == 0u)) {
             const unsigned e = wq_pop(&c.tails[1], c.q1b, t1b, lane);
             if (e != kNoEntry) wq_classify<R>(c, e);
-        } else if (t1 >= 32u || (flush && t1 > 0u)) {
+        } else if (t1 >= 32u || (flush == 2 && t1 > 0u && n0 == 0u)) {
             const unsigned e = wq_pop(&c.tails[0], c.q1, t1, lane);
             const bool keep = e != kNoEntry && wq_recull<R>(c, e);
             const unsigned b = __ballot_sync(0xffffffffu, keep);
             if (keep) c.q1b[t1b + __popc(b & ((1u << lane) - 1u))] = e;
             if (lane == 0) c.tails[1] = t1b + __popc(b);
+        } else if (n0 >= 32u || (flush && n0 > 0u)) {
+            n0 = wq_expand<R, G>(c, n0, slotmap, lane);
         } else
             break;
     }
+    return n0;
+}
+
+// the first-collision replay of the epilogue runs once per colliding configuration: out of line as well
+template <class R>
+__device__ __noinline__ R wq_replay_pair(R ax, R ay, R az, R bx_, R by, R bz, R radius, const ObstacleRec *o, R eq_thr, R max_dist) {
+    Capsule<R> cp;
+    cp.set({ax, ay, az}, {bx_, by, bz}, radius, R(0));
+    V3<R> u, v;
+    return capsule_box_distance<R, false>(cp, load_box<R>(*o), eq_thr, max_dist, u, v);
 }
 
 // F = FK scalar, R = geometry scalar, MODE = RVS_DIST_MIN | RVS_DIST_PROFILE, G = links scanned per obstacle pass.
 template <class F, class R, int MODE, int G>
 __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char wq_smem[];
+    static_assert(G >= 1 && G <= 6, "the slot -> link map packs at most six 5-bit link indices");
     typedef typename WqBits<R>::type Bits;
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    WqCtx<R> c;
-    {
-        unsigned char *p = wq_smem;
-        c.skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
-        c.best = reinterpret_cast<Bits *>(p); p += size_t(L) * kWqStride * sizeof(Bits);
-        c.radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
-        p = wq_smem + ((size_t(p - wq_smem) + 15) & ~size_t(15));
-        c.hit = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
-        unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * WqCaps<G>::words;
-        c.tails = wq; c.q1 = wq + 8; c.q1b = c.q1 + WqCaps<G>::q1; c.q2 = c.q1b + WqCaps<G>::q1b;
-    }
-    c.obs4 = reinterpret_cast<const float4 *>(a.obstacles_scan);
-    c.M = a.M; c.wbase = warp * 32; c.seg_base = 0;
-    c.eq_thr = R(a.eq_thr); c.max_dist = R(a.max_dist);
+    WqCtx<R> c = wq_make_ctx<R, G>(wq_smem, reinterpret_cast<const float4 *>(a.obstacles_scan), L, a.M, 0, R(a.eq_thr), R(a.max_dist));
 
     const int64_t cfg = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
     const bool live = cfg < a.N;
     const int t = threadIdx.x;
     if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.skel + t, kWqStride);
     else for (int k = 0; k < 3 * (L + 1); k++) c.skel[k * kWqStride + t] = R(0);
+    // reach of every link: no point of its axis is farther from the base than this, so an obstacle at distance d from the base
+    // is at least d - reach away from the link (the scan table is sorted by d: see the cut-off below)
+    {
+        const R bx = R(rb->xyz[0][0]), by = R(rb->xyz[0][1]), bz = R(rb->xyz[0][2]);
+        R prev = 0;
+        for (int i = 0; i <= L; i++) {
+            const R x = c.skel[(3 * i) * kWqStride + t] - bx, y = c.skel[(3 * i + 1) * kWqStride + t] - by, z = c.skel[(3 * i + 2) * kWqStride + t] - bz;
+            const R nrm = sqrt(x * x + y * y + z * z);
+            if (i > 0) c.reach[(i - 1) * kWqStride + t] = fmax(prev, nrm);
+            prev = nrm;
+        }
+    }
     for (int i = 0; i < L; i++) c.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
     c.hit[t] = kNoHit;
     if (t < L) c.radius[t] = RobotScalars<R>::radius(rb, t);
@@ -269,36 +342,67 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
         const int count = min(kWqSegment, a.M - base);
         c.seg_base = base;
         const float4 *o4 = c.obs4 + 2 * size_t(base);
+        const float *sd = a.scan_dist + base;
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
-            const int gskip = ground_included - g0;                       // links g0 .. g0+gskip-1 ignore ground objects (:336)
-            const unsigned ground_keep1 = gskip <= 0 ? ~0u : (gskip >= G ? 0u : ~((1u << gskip) - 1u));
-            const unsigned ground_keep = (ground_keep1 & ((1u << G) - 1u)) * ((1u << G) + 1u);     // replicated for both unrolled obstacles
+            // links of this group that some configuration of the warp can still improve (warp-uniform, only ever shrinks)
+            unsigned alive = (1u << min(G, L - g0)) - 1u;
+            unsigned slotmap = 0, n0 = 0;                                  // slot -> link map (5 bits per slot); hit words waiting in Q0
 #pragma unroll 1
             for (int j0 = 0; j0 < count;) {
-                // inflated link boxes from the current minima; links at or above a known collision are dead
-                R lo[G][3], hi[G][3];
+                // Cut-off: the table is sorted by distance from the base, so once  d(j0) - reach > threshold  for a link, neither
+                // obstacle j0 nor any later one can lower its minimum.  Links at or above a known collision are dead as well.
                 const unsigned hk = c.hit[t];
                 const int limit = !live ? 0 : (hk == kNoHit ? L : int(hk / unsigned(a.M)) + 1);
+                const R dnext = R(__ldg(sd + j0));
+                unsigned mine = 0;
 #pragma unroll
                 for (int l = 0; l < G; l++) {
                     const int i = g0 + l;
                     if (i < limit && i < L) {
-                        const R *sk = c.skel + (3 * i) * kWqStride + t;
                         const R thr = wq_threshold(WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
-                            lo[l][k] = fmin(p, q) - thr;
-                            hi[l][k] = fmax(p, q) + thr;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 3; k++) { lo[l][k] = wq_inf<R>(); hi[l][k] = -wq_inf<R>(); }          // overlaps nothing
+                        if (!(dnext > (c.reach[i * kWqStride + t] + thr) * R(1.00001))) mine |= 1u << l;
                     }
                 }
-                // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, ... obstacles
-                const int jend = min(j0 + (j0 < 4 ? 4 : j0), count);
+                alive &= __reduce_or_sync(0xffffffffu, mine);
+                // No live link left: one empty iteration over the tail of the table, so that the end-of-segment flush below (the only
+                // inlined copy of the compacted phases) still runs.
+                if (!alive) j0 = (count - 1) & ~1;
+                // live links are packed into slots 0..K-1 (K, the slot -> link map and the ground filter are warp-uniform);
+                // slot boxes = link bounding boxes inflated by the current threshold, empty for lanes that are done with the link
+                const int K = __popc(alive);
+                unsigned ground_keep = 0;
+                slotmap = 0;                                                // (Q0 is empty here: every interval ends with a flush)
+                R lo[G][3], hi[G][3];
+                {
+                    unsigned rem = alive;
+#pragma unroll
+                    for (int s = 0; s < G; s++) {
+                        const int l = __ffs(int(rem)) - 1, i = g0 + l;
+                        rem &= rem - 1u;
+                        if (s < K && ((mine >> l) & 1u)) {
+                            const R *sk = c.skel + (3 * i) * kWqStride + t;
+                            const R thr = wq_threshold(WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
+                                lo[s][k] = fmin(p, q) - thr;
+                                hi[s][k] = fmax(p, q) + thr;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<R>(); hi[s][k] = -wq_inf<R>(); }          // overlaps nothing
+                        }
+                        if (s < K) {
+                            slotmap |= unsigned(i) << (5 * s);
+                            if (i >= ground_included) ground_keep |= 1u << s;                 // links below ground_included ignore ground objects (:336)
+                        }
+                    }
+                    ground_keep *= (1u << G) + 1u;                                            // replicated for both unrolled obstacles
+                }
+                // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, 64, 128, 192, ... obstacles
+                const int jend = alive ? min(j0 + (j0 < 4 ? 4 : min(j0, 64)), count) : count;
+                const bool seg_end = jend == count && g0 + G >= L;         // queue entries index this segment: empty every queue before moving on
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {
                     // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags) of two obstacles: warp-uniform 16-byte loads
@@ -306,31 +410,36 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                     const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
                     const float4 w0 = __ldg(pj), w1 = __ldg(pj + 1), v0 = __ldg(pj1), v1 = __ldg(pj1 + 1);
                     unsigned mask = 0;
-#pragma unroll
-                    for (int l = 0; l < G; l++) {
-                        wq_overlap<R>(mask, 1u << l, R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[l], hi[l]);
-                        wq_overlap<R>(mask, 1u << (G + l), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[l], hi[l]);
+#define RVS_WQ_SLOT(S)                                                                                                             \
+    if (S < G) {                                                                                                                   \
+        wq_overlap<R>(mask, 1u << (S), R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<R>(mask, 1u << (G + (S)), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+    }
+                    switch (K) {                                                              // warp-uniform: only live slots are tested
+                        case 0: break;
+                        default: RVS_WQ_SLOT(5) [[fallthrough]];
+                        case 5: RVS_WQ_SLOT(4) [[fallthrough]];
+                        case 4: RVS_WQ_SLOT(3) [[fallthrough]];
+                        case 3: RVS_WQ_SLOT(2) [[fallthrough]];
+                        case 2: RVS_WQ_SLOT(1) [[fallthrough]];
+                        case 1: RVS_WQ_SLOT(0)
                     }
+#undef RVS_WQ_SLOT
                     if (j1 == j) mask &= (1u << G) - 1u;                                    // odd tail: the second slot is a duplicate
                     if ((__float_as_uint(w1.w) | __float_as_uint(v1.w)) & 1u)
                         mask &= ((__float_as_uint(w1.w) & 1u) ? (ground_keep | ~((1u << G) - 1u)) : ~0u) &
                                 ((__float_as_uint(v1.w) & 1u) ? (ground_keep | ((1u << G) - 1u)) : ~0u);
-                    if (mask) {
-                        unsigned pos = atomicAdd(const_cast<unsigned *>(&c.tails[0]), unsigned(__popc(mask)));
-                        do {
-                            const int b = __ffs(int(mask)) - 1;
-                            mask &= mask - 1u;
-                            const int l = b >= G ? b - G : b, jj = b >= G ? j1 : j;
-                            c.q1[pos++] = unsigned(lane) | (unsigned(g0 + l) << 5) | (unsigned(jj) << 10);
-                        } while (mask);
-                    }
-                    __syncwarp();
-                    if (c.tails[0] >= 32u) wq_drain<R>(c, false);
+                    // one hit word per lane with any hit, at a ballot-computed position of Q0 (no divergence in the scan)
+                    const unsigned hits = __ballot_sync(0xffffffffu, mask != 0u);
+                    if (mask) c.q0[n0 + __popc(hits & ((1u << lane) - 1u))] = mask | (unsigned(lane) << 12) | (unsigned(j >> 1) << 17);
+                    n0 += unsigned(__popc(hits));
+                    // hit words refer to the current slot -> link map: the last iteration of an interval unpacks all of them
+                    const bool last = j + kWqUnroll >= jend;
+                    if (n0 >= 32u || (last && (n0 || seg_end))) n0 = wq_drain<R, G>(c, !last ? 0 : (seg_end ? 2 : 1), n0, slotmap);
                 }
                 j0 = jend;
             }
         }
-        wq_drain<R>(c, true);                                              // queue entries index this segment: empty them before moving on
     }
     __syncwarp();
 
@@ -342,11 +451,9 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
     R hit_d = 0;
     if (collided) {
         // the value the reference stores for the colliding link: replay exactly that pair sequentially
-        Capsule<R> cp;
         const R *sk = c.skel + (3 * limit) * kWqStride + t;
-        cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, c.radius[limit], R(0));
-        V3<R> u, v;
-        hit_d = capsule_box_distance<R, false>(cp, load_box<R>(a.obstacles[hit_j]), c.eq_thr, c.max_dist, u, v);
+        hit_d = wq_replay_pair<R>(sk[0], sk[kWqStride], sk[2 * kWqStride], sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride], c.radius[limit],
+                                  a.obstacles + hit_j, c.eq_thr, c.max_dist);
     }
     if (a.pair_count) {
         // pair queries the REFERENCE's loop (link-major, stop at the first collision) would have made

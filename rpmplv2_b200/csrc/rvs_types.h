@@ -47,6 +47,7 @@ struct KArgs {
     const RobotDev *robot;
     const ObstacleRec *obstacles;        // caller's order
     const ObstacleRec *obstacles_scan;   // nearest-to-base first; flags bits 8..31 = index in the caller's order (work-queue kernel only)
+    const float *scan_dist;              // [M] distance of scan-order obstacle k from the robot base, rounded down (ascending)
     int32_t M;
     int64_t N;
     const float *q;          // N x n

@@ -20,6 +20,7 @@ template <int G> struct VqCaps {
 template <class R, int G>
 __host__ __device__ inline size_t vq_smem_bytes(int L) {
     size_t b = size_t(3 * (L + 1)) * kWqStride * sizeof(R);               // skeleton
+    b += size_t(L) * kWqStride * sizeof(R);                               // per-link cut-off distance from the base (reach + slab threshold)
     b += 2 * size_t(L) * sizeof(R);                                       // radius, radius * sqrt(3) / 3
     b = (b + 15) & ~size_t(15);
     b += size_t(kWqBlock) * sizeof(unsigned);                             // invalid flags
@@ -35,6 +36,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = threadIdx.x, wbase = warp * 32;
     unsigned char *p = vq_smem;
     R *skel = reinterpret_cast<R *>(p); p += size_t(3 * (L + 1)) * kWqStride * sizeof(R);
+    R *cut = reinterpret_cast<R *>(p); p += size_t(L) * kWqStride * sizeof(R);
     R *radius = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
     R *radius_in = reinterpret_cast<R *>(p); p += size_t(L) * sizeof(R);
     p = vq_smem + ((size_t(p - vq_smem) + 15) & ~size_t(15));
@@ -42,7 +44,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
     unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * VqCaps<G>::words;
     volatile unsigned *tail = wq;
     unsigned *q1 = wq + 4;
-    const float4 *obs4 = reinterpret_cast<const float4 *>(a.obstacles);
+    const float4 *obs4 = reinterpret_cast<const float4 *>(a.obstacles_scan);   // nearest to the base first (the verdict is order free)
     const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
 
     const int64_t item = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
@@ -70,6 +72,25 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
         }
     }
     if (!live) for (int k = 0; k < 3 * (L + 1); k++) skel[k * kWqStride + t] = R(0);
+    {
+        // slab threshold (looser than the reference's `+- radius`) and the distance from the base beyond which no obstacle can
+        // touch the link: reach (farthest axis point from the base) + threshold.  The scan table is sorted by that distance.
+        const R bx = R(rb->xyz[0][0]), by = R(rb->xyz[0][1]), bz = R(rb->xyz[0][2]);
+        R prev = 0;
+        for (int i = 0; i <= L; i++) {
+            const R x = skel[(3 * i) * kWqStride + t] - bx, y = skel[(3 * i + 1) * kWqStride + t] - by, z = skel[(3 * i + 2) * kWqStride + t] - bz;
+            const R nrm = sqrt(x * x + y * y + z * z);
+            if (i > 0) {
+                const R *sk = skel + (3 * (i - 1)) * kWqStride + t;
+                R mag = R(0);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride]; mag = fmax(mag, fmax(fabs(u), fabs(v))); }
+                const R thr = RobotScalars<R>::radius(rb, i - 1) * R(1.001) + R(1e-5) + R(4e-6) * mag;
+                cut[(i - 1) * kWqStride + t] = (fmax(prev, nrm) + R(1.7320509) * thr) * R(1.00001);
+            }
+            prev = nrm;
+        }
+    }
     invalid[t] = 0u;
     if (t < L) { radius[t] = RobotScalars<R>::radius(rb, t); radius_in[t] = RobotScalars<R>::radius_in(rb, t); }
     if (lane < 4) tail[lane] = 0;
@@ -105,37 +126,55 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
         const int count = min(kSeg, a.M - base);
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
-            const int gskip = ground_included - g0;                       // links below ground_included ignore ground objects (:285-286)
-            const unsigned ground_keep1 = gskip <= 0 ? ~0u : (gskip >= G ? 0u : ~((1u << gskip) - 1u));
-            const unsigned ground_keep = (ground_keep1 & ((1u << G) - 1u)) * ((1u << G) + 1u);
-            R lo[G][3], hi[G][3];
-            auto refresh = [&]() {
+            unsigned alive = (1u << min(G, L - g0)) - 1u;                 // links some configuration of the warp still has to test (warp-uniform)
+            const float4 *o4 = obs4 + 2 * size_t(base);
+            const float *sd = a.scan_dist + base;
+#pragma unroll 1
+            for (int j0 = 0; j0 < count; j0 += 64) {
+                // every 64 obstacles: drop configurations that are already invalid and links no later obstacle can reach; pack the
+                // live links into slots 0..K-1 (K and the slot -> link map are warp-uniform)
                 const bool dead = !live || invalid[t] != 0u;
+                const R dnext = R(__ldg(sd + j0));
+                unsigned mine = 0;
 #pragma unroll
                 for (int l = 0; l < G; l++) {
                     const int i = g0 + l;
-                    if (!dead && i < L) {
-                        const R *sk = skel + (3 * i) * kWqStride + t;
-                        R mag = R(0);
-#pragma unroll
-                        for (int k = 0; k < 3; k++) { const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride]; mag = fmax(mag, fmax(fabs(u), fabs(v))); }
-                        const R thr = radius[i] * R(1.001) + R(1e-5) + R(4e-6) * mag;      // looser than the reference's `+- radius` slab
-#pragma unroll
-                        for (int k = 0; k < 3; k++) {
-                            const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride];
-                            lo[l][k] = fmin(u, v) - thr;
-                            hi[l][k] = fmax(u, v) + thr;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 3; k++) { lo[l][k] = wq_inf<R>(); hi[l][k] = -wq_inf<R>(); }
-                    }
+                    if (!dead && i < L && !(dnext > cut[i * kWqStride + t])) mine |= 1u << l;
                 }
-            };
-            const float4 *o4 = obs4 + 2 * size_t(base);
-#pragma unroll 1
-            for (int j0 = 0; j0 < count; j0 += 64) {
-                refresh();                                                  // picks up "already invalid" every 64 obstacles
+                alive &= __reduce_or_sync(0xffffffffu, mine);
+                if (!alive) break;
+                const int K = __popc(alive);
+                unsigned slotmap = 0, ground_keep = 0;
+                R lo[G][3], hi[G][3];
+                {
+                    unsigned rem = alive;
+#pragma unroll
+                    for (int s = 0; s < G; s++) {
+                        const int l = __ffs(int(rem)) - 1, i = g0 + l;
+                        rem &= rem - 1u;
+                        if (s < K && ((mine >> l) & 1u)) {
+                            const R *sk = skel + (3 * i) * kWqStride + t;
+                            R mag = R(0);
+#pragma unroll
+                            for (int k = 0; k < 3; k++) { const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride]; mag = fmax(mag, fmax(fabs(u), fabs(v))); }
+                            const R thr = radius[i] * R(1.001) + R(1e-5) + R(4e-6) * mag;      // looser than the reference's `+- radius` slab
+#pragma unroll
+                            for (int k = 0; k < 3; k++) {
+                                const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride];
+                                lo[s][k] = fmin(u, v) - thr;
+                                hi[s][k] = fmax(u, v) + thr;
+                            }
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<R>(); hi[s][k] = -wq_inf<R>(); }
+                        }
+                        if (s < K) {
+                            slotmap |= unsigned(i) << (5 * s);
+                            if (i >= ground_included) ground_keep |= 1u << s;                 // links below ground_included ignore ground objects (:285-286)
+                        }
+                    }
+                    ground_keep *= (1u << G) + 1u;
+                }
                 const int jend = min(j0 + 64, count);
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {
@@ -143,11 +182,20 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                     const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
                     const float4 w0 = __ldg(pj), w1 = __ldg(pj + 1), v0 = __ldg(pj1), v1 = __ldg(pj1 + 1);
                     unsigned mask = 0;
-#pragma unroll
-                    for (int l = 0; l < G; l++) {
-                        wq_overlap<R>(mask, 1u << l, R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[l], hi[l]);
-                        wq_overlap<R>(mask, 1u << (G + l), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[l], hi[l]);
+#define RVS_VQ_SLOT(S)                                                                                                             \
+    if (S < G) {                                                                                                                   \
+        wq_overlap<R>(mask, 1u << (S), R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<R>(mask, 1u << (G + (S)), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+    }
+                    switch (K) {
+                        default: RVS_VQ_SLOT(5) [[fallthrough]];
+                        case 5: RVS_VQ_SLOT(4) [[fallthrough]];
+                        case 4: RVS_VQ_SLOT(3) [[fallthrough]];
+                        case 3: RVS_VQ_SLOT(2) [[fallthrough]];
+                        case 2: RVS_VQ_SLOT(1) [[fallthrough]];
+                        case 1: RVS_VQ_SLOT(0)
                     }
+#undef RVS_VQ_SLOT
                     if (j1 == j) mask &= (1u << G) - 1u;
                     if ((__float_as_uint(w1.w) | __float_as_uint(v1.w)) & 1u)
                         mask &= ((__float_as_uint(w1.w) & 1u) ? (ground_keep | ~((1u << G) - 1u)) : ~0u) &
@@ -157,8 +205,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                         do {
                             const int b = __ffs(int(mask)) - 1;
                             mask &= mask - 1u;
-                            const int l = b >= G ? b - G : b, jj = base + (b >= G ? j1 : j);
-                            q1[pos++] = unsigned(lane) | (unsigned(g0 + l) << 5) | (unsigned(jj) << 10);
+                            const int sl = b >= G ? b - G : b, jj = base + (b >= G ? j1 : j);
+                            q1[pos++] = unsigned(lane) | (((slotmap >> (5 * sl)) & 31u) << 5) | (unsigned(jj) << 10);
                         } while (mask);
                     }
                     __syncwarp();
