@@ -187,8 +187,11 @@ __device__ __forceinline__ WqPair<R> wq_load_pair(const WqCtx<R> &c, unsigned e)
 template <class R>
 __device__ __forceinline__ bool wq_recull(const WqCtx<R> &c, unsigned e) {
     const WqPair<R> p = wq_load_pair(c, e);
-    if (p.key > c.hit[p.t]) return false;                                  // an earlier pair (reference order) already collides
-    const R thr = wq_threshold(WqBits<R>::from(c.best[p.link * kWqStride + p.t]), c.radius[p.link], c.eq_thr);
+    const unsigned hk = c.hit[p.t];
+    if (p.key > hk) return false;                                          // an earlier pair (reference order) already collides
+    // on the link of the current first collision only an earlier COLLISION matters (its minimum is not an output)
+    const bool hit_link = hk < unsigned(p.link + 1) * unsigned(c.M);
+    const R thr = wq_threshold(hit_link ? R(0) : WqBits<R>::from(c.best[p.link * kWqStride + p.t]), c.radius[p.link], c.eq_thr);
     const R gx = fmax(fmax(p.bx.lo.x - fmax(p.A.x, p.B.x), fmin(p.A.x, p.B.x) - p.bx.hi.x), R(0));
     const R gy = fmax(fmax(p.bx.lo.y - fmax(p.A.y, p.B.y), fmin(p.A.y, p.B.y) - p.bx.hi.y), R(0));
     const R gz = fmax(fmax(p.bx.lo.z - fmax(p.A.z, p.B.z), fmin(p.A.z, p.B.z) - p.bx.hi.z), R(0));
@@ -353,14 +356,16 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                 // Cut-off: the table is sorted by distance from the base, so once  d(j0) - reach > threshold  for a link, neither
                 // obstacle j0 nor any later one can lower its minimum.  Links at or above a known collision are dead as well.
                 const unsigned hk = c.hit[t];
-                const int limit = !live ? 0 : (hk == kNoHit ? L : int(hk / unsigned(a.M)) + 1);
+                const int hit_link = hk == kNoHit ? -1 : int(hk / unsigned(a.M));
+                const int limit = !live ? 0 : (hk == kNoHit ? L : hit_link + 1);
                 const R dnext = R(__ldg(sd + j0));
                 unsigned mine = 0;
 #pragma unroll
                 for (int l = 0; l < G; l++) {
                     const int i = g0 + l;
                     if (i < limit && i < L) {
-                        const R thr = wq_threshold(WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
+                        // the link of the current first collision only looks for EARLIER collisions (its minimum is not an output)
+                        const R thr = wq_threshold(i == hit_link ? R(0) : WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
                         if (!(dnext > (c.reach[i * kWqStride + t] + thr) * R(1.00001))) mine |= 1u << l;
                     }
                 }
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                         rem &= rem - 1u;
                         if (s < K && ((mine >> l) & 1u)) {
                             const R *sk = c.skel + (3 * i) * kWqStride + t;
-                            const R thr = wq_threshold(WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
+                            const R thr = wq_threshold(i == hit_link ? R(0) : WqBits<R>::from(c.best[i * kWqStride + t]), c.radius[i], c.eq_thr);
 #pragma unroll
                             for (int k = 0; k < 3; k++) {
                                 const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
@@ -435,7 +440,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                     n0 += unsigned(__popc(hits));
                     // hit words refer to the current slot -> link map: the last iteration of an interval unpacks all of them
                     const bool last = j + kWqUnroll >= jend;
-                    if (n0 >= 32u || (last && (n0 || seg_end))) n0 = wq_drain<R, G>(c, !last ? 0 : (seg_end ? 2 : 1), n0, slotmap);
+                    if (n0 >= 32u || last) n0 = wq_drain<R, G>(c, last ? 2 : 0, n0, slotmap);      // interval end: every queue is emptied, so the next thresholds are exact
                 }
                 j0 = jend;
             }
