@@ -8,7 +8,16 @@
 // How (one warp = 32 configurations, lane = configuration during the scan, lane = work item afterwards):
 //   phase A  scan      each lane tests every obstacle (warp-uniform 16-byte loads of the HBM-resident table, served by
 //                      L1) against its links' axis-aligned bounding boxes inflated by (running minimum + radius):
-//                      6 predicate-chained compares per pair, no divergence.  Survivors go to the pair queue Q1.
+//                      6 predicate-chained compares per pair, no divergence.  A lane with any hit stores ONE hit word
+//                      (slot mask | lane | obstacle pair) at a ballot-computed position of Q0.
+//                      The table is sorted by distance d from the robot base and every link knows its reach (farthest
+//                      axis point from the base): once d - reach exceeds a link's threshold for all 32 configurations,
+//                      the link is dropped for the rest of the table.  Live links are packed into warp-uniform slots,
+//                      so an iteration only pays for the links that are still open (2-3 of 6 on the sweep workload).
+//                      The link of the current first collision only searches for EARLIER collisions (threshold =
+//                      radius): its minimum is not an output, and without this a colliding configuration would push
+//                      every obstacle of that link through the queues.
+//   phase A' unpack    Q0 >= 32: every lane turns one hit word into pair entries of Q1 (warp prefix sum).
 //   phase B1 re-cull   Q1 >= 32: every lane pops ONE pair (of any configuration of the warp) and re-tests it with the
 //                      Euclidean box gap against the now tighter minimum; survivors are ballot-compacted into Q1b.
 //   phase B2 classify  Q1b >= 32: every lane runs the reference's endpoint-projection / region classification
@@ -16,12 +25,15 @@
 //                      hand to distanceLineSegToLineSeg are appended to the edge queue Q2.
 //   phase C  edges     Q2 >= 32: every lane pops ONE edge and evaluates seg_edge().
 // All phases run with (nearly) full warps.  Results are merged with shared-memory atomicMin on the IEEE bit pattern
-// (distances that reach the minimum are > 0, so integer order == float order).
+// (distances that reach the minimum are > 0, so integer order == float order).  Thresholds are refreshed after 4, 8, 16, ...,
+// 128 and then every 128 obstacles; every refresh interval ends with a full flush of the queues, so the next thresholds
+// (and the cut-off) are exact for the scanned prefix.
 //
 // Exactness (bit-identical outputs to the sequential kernel / the reference loop, in any processing order):
 //   * culling is conservative: a pair is skipped only if a lower bound of ANY candidate distance the reference
 //     could compute for it exceeds (current minimum of that link + radius) by a safety margin (0.1 % + 1e-4 m),
-//     so a skipped pair can neither lower the minimum nor be a collision;
+//     so a skipped pair can neither lower the minimum nor be a collision; the base-distance cut-off uses the triangle
+//     inequality dist(x, box) >= dist(base, box) - |x - base| with dist(base, box) rounded DOWN on the host;
 //   * min(c_k) - r == min(c_k - r) and the min_dist_tol filter d > tol is monotone, so candidates can be merged one
 //     by one instead of per pair;
 //   * first-collision semantics (RealVectorSpace.cpp:370-378) are order dependent in the reference: we keep the
@@ -43,6 +55,13 @@ constexpr int kWqWarps = kWqBlock / 32;
 constexpr int kWqStride = kWqBlock + 1;           // row pitch of the per-thread shared arrays: row r of thread t sits in bank (r + t) % 32, so
                                                   // popped work items of ONE configuration (same t, different links) do not collide
 constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bit obstacle index: the table is walked in segments of 65536
+#ifndef RVS_WQ_INTERVAL
+#define RVS_WQ_INTERVAL 128
+#endif
+#ifndef RVS_WQ_FLUSH
+#define RVS_WQ_FLUSH 2
+#endif
+constexpr int kWqInterval = RVS_WQ_INTERVAL;      // obstacles between two threshold refreshes (after the first doublings 4, 8, 16, ...)
 constexpr int kWqUnroll = 2;                      // obstacles tested per scan iteration
 constexpr unsigned kNoHit = 0xFFFFFFFFu;
 constexpr unsigned kNoEntry = 0xFFFFFFFFu;
@@ -405,8 +424,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                     }
                     ground_keep *= (1u << G) + 1u;                                            // replicated for both unrolled obstacles
                 }
-                // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, 64, 128, 192, ... obstacles
-                const int jend = alive ? min(j0 + (j0 < 4 ? 4 : min(j0, 64)), count) : count;
+                // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, 64, 128, 256, 384, ... obstacles
+                const int jend = alive ? min(j0 + (j0 < 4 ? 4 : min(j0, kWqInterval)), count) : count;
                 const bool seg_end = jend == count && g0 + G >= L;         // queue entries index this segment: empty every queue before moving on
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {
@@ -440,7 +459,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
                     n0 += unsigned(__popc(hits));
                     // hit words refer to the current slot -> link map: the last iteration of an interval unpacks all of them
                     const bool last = j + kWqUnroll >= jend;
-                    if (n0 >= 32u || last) n0 = wq_drain<R, G>(c, last ? 2 : 0, n0, slotmap);      // interval end: every queue is emptied, so the next thresholds are exact
+                    if (n0 >= 32u || last) n0 = wq_drain<R, G>(c, last ? (seg_end ? 2 : RVS_WQ_FLUSH) : 0, n0, slotmap);      // interval end: every queue is emptied, so the next thresholds are exact
                 }
                 j0 = jend;
             }

@@ -14,7 +14,7 @@ from .robots import (DIST_FULL, DIST_MIN, DIST_PROFILE, PREC_F64, PREC_REF32, Ro
                      default_params)
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "librvs_cuda.so")
+LIB_PATH = os.environ.get("RVS_CUDA_LIB") or os.path.join(_PKG, "librvs_cuda.so")   # RVS_CUDA_LIB: a differently tuned build of the same ABI
 
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_f64p = ctypes.POINTER(ctypes.c_double)
