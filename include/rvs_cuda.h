@@ -29,6 +29,10 @@
  *   rvs_store_distance /              <- base::State's distance cache (include/state_spaces/State.h:24-41) filled by
  *   rvs_store_extend_spines              computeDistance and consumed by RGBTConnect::extendGenSpine / extendGenSpine2
  *                                        (src/planners/rbt/RGBTConnect.cpp:73-118), kept resident in HBM
+ *   rvs_env_set / rvs_env_step /      <- env::Environment's dynamic obstacles: updateEnvironment and its motion laws
+ *   rvs_env_get                          (src/environments/Environment.cpp:194-377), env::Object::setPosition (Object.cpp:21-26)
+ *   rvs_motion_validity               <- planning::trajectory::MotionValidity::check(q_previous, q_current)
+ *                                        (src/planners/trajectory/MotionValidity.cpp:30-51), obstacles moving on the device
  *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
  *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
  *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
@@ -217,6 +221,47 @@ int  rvs_store_extend_spines(rvs_handle h, const int32_t *root_slots, const floa
                              float *d_c_last, uint8_t *status);
 /* copy one slot back to the host (any of the outputs may be NULL); planes[M x L x 6] */
 int  rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *profile, float *planes);
+
+/* ---- dynamic environment on the device ------------------------------------------------------
+ * env::Environment keeps position / velocity / max_vel per object and moves every object labelled "dynamic_obstacle" by one of
+ * its motion laws in updateEnvironment(delta_time); MotionValidity::check interleaves K such updates with K validity points of
+ * the robot's motion.  Behind a device engine that is K obstacle uploads + K tiny launches per planner iteration.  These entry
+ * points keep the obstacle STATES resident and do all K steps in one call. */
+typedef enum {
+    RVS_MOTION_STRAIGHT = 0,           /* Environment::moveStraight          (Environment.cpp:224-238) */
+    RVS_MOTION_CIRCULAR = 1,           /* Environment::moveCircular          (:241-258) */
+    RVS_MOTION_TWO_TUNNELS = 2,        /* Environment::moveTwoTunnels        (:261-289) */
+    RVS_MOTION_RANDOM_DIRECTIONS = 3,  /* Environment::moveRandomDirections  (:293-333) draws from libc rand(): RVS_ERR_UNSUPPORTED */
+    RVS_MOTION_LIGHT_DIRECTIONS = 4    /* Environment::moveLightDirections   (:336-377) */
+} rvs_motion_type;
+
+typedef struct {
+    int32_t motion_type;               /* one of rvs_motion_type: scenario YAML testing.motion_type */
+    float   ws_center[3];              /* robot.WS_center */
+    float   ws_radius;                 /* robot.WS_radius */
+    float   base_radius;               /* Environment::setBaseRadius */
+    float   robot_max_vel;             /* Environment::setRobotMaxVel */
+} rvs_env_params;
+
+/* Defines the environment AND the resident obstacle table (it replaces rvs_set_obstacles): M boxes with dim / pos (M x 3),
+ * rotated[j] != 0 when the box has a non-identity rotation (FCL then reports the bounding-sphere cube; NULL = none),
+ * vel (M x 3, NULL = zero), max_vel (M, NULL = zero), is_dynamic (label == "dynamic_obstacle"), is_ground, min_dist_tol as in
+ * rvs_set_obstacles.  Environment::sign starts at +1 and path_len at 0 (Environment.cpp:76-77). */
+int  rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const float *pos, const uint8_t *rotated,
+                 const float *vel, const float *max_vel, const uint8_t *is_dynamic, const uint8_t *is_ground,
+                 const float *min_dist_tol, int32_t M);
+/* `steps` x Environment::updateEnvironment(delta_time) on the device; the resident obstacle table follows. */
+int  rvs_env_step(rvs_handle h, float delta_time, int32_t steps);
+/* current object positions / velocities (M x 3 each, either may be NULL) */
+int  rvs_env_get(rvs_handle h, float *pos, float *vel);
+/* MotionValidity::check(q_previous_e, q_current_e) for E motions that share ONE obstacle timeline of K updates of delta_time:
+ * validity point k (k = 1..K, interpolateEdge(q_previous, q_current, dist * k / K, dist)) is tested against the environment
+ * after k updates.  valid[e] = the reference's return value, first_invalid[e] = k of the first invalid point (0 if valid).
+ * commit_edge >= 0: the environment is left exactly as the reference leaves it after checking THAT motion (updated
+ * first_invalid times — the reference returns at once — or K times); commit_edge < 0: the environment is not changed
+ * (what-if queries for many candidate motions).  Self-collision (xArm6 meshes, FCL) is not part of this check. */
+int  rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float delta_time,
+                         int32_t commit_edge, uint8_t *valid, int32_t *first_invalid);
 
 /* Batched geometric primitives on K independent (capsule, box) pairs, host pointers.
  * AB: K x 6 (A xyz, B xyz); radius: K; obs: K x 6 (x_min,y_min,z_min,x_max,y_max,z_max).

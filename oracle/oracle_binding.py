@@ -86,6 +86,53 @@ class Oracle:
         t = None if min_dist_tol is None else _f32(min_dist_tol)
         lib().orc_set_obstacles(self._h, _p(mn, c_f32p), _p(mx, c_f32p), _p(g, c_u8p), _p(t, c_f32p), ctypes.c_int32(self.M))
 
+    # ---- dynamic environment (row f-2): the state arrays live on this object, like env::Environment's objects -------------
+    def env_set(self, ep, dim, pos, vel=None, max_vel=None, is_dynamic=None, is_ground=None, min_dist_tol=None, rotated=None):
+        dim, pos = _f32(dim, (-1, 3)), _f32(pos, (-1, 3)).copy()
+        M = dim.shape[0]
+        half = (np.float32(0.5) * dim).astype(np.float32)
+        if rotated is not None:
+            # FCL's bounding-sphere cube for rotated boxes, summed as the engine's host code does: (x*x + y*y) + z*z
+            rad = np.sqrt(((half[:, 0] * half[:, 0] + half[:, 1] * half[:, 1]) + half[:, 2] * half[:, 2]).astype(np.float32)).astype(np.float32)
+            half = np.where(np.asarray(rotated, bool)[:, None], rad[:, None], half).astype(np.float32)
+        self._env = dict(ep=ep, M=M, half=np.ascontiguousarray(half), pos=pos,
+                         vel=np.zeros((M, 3), np.float32) if vel is None else _f32(vel, (M, 3)).copy(),
+                         max_vel=np.zeros(M, np.float32) if max_vel is None else _f32(max_vel, (M,)).copy(),
+                         sign=np.ones(M, np.int32), path_len=np.zeros(M, np.float32),
+                         dynamic=np.zeros(M, np.uint8) if is_dynamic is None else np.ascontiguousarray(is_dynamic, np.uint8).copy())
+        self._env["ground"], self._env["tol"] = is_ground, min_dist_tol
+        self.set_obstacles(pos + (-half), pos + half, is_ground, min_dist_tol)
+
+    def _env_args(self):
+        e = self._env
+        ep = e["ep"]
+        prm = np.array([ep.ws_center[0], ep.ws_center[1], ep.ws_center[2], ep.ws_radius, ep.base_radius, ep.robot_max_vel], np.float32)
+        return prm, [ctypes.c_int32(ep.motion_type), ctypes.c_int32(e["M"]), _p(e["half"], c_f32p), _p(e["pos"], c_f32p), _p(e["vel"], c_f32p),
+                     _p(e["max_vel"], c_f32p), _p(e["sign"], c_i32p), _p(e["path_len"], c_f32p), _p(e["dynamic"], c_u8p)]
+
+    def env_step(self, delta_time: float, steps: int = 1):
+        prm, args = self._env_args()
+        M = self._env["M"]
+        mn, mx = np.empty((M, 3), np.float32), np.empty((M, 3), np.float32)
+        rc = lib().orc_env_update(_p(prm, c_f32p), *args, ctypes.c_float(delta_time), ctypes.c_int32(steps), _p(mn, c_f32p), _p(mx, c_f32p))
+        if rc:
+            raise RuntimeError(f"orc_env_update rc={rc}")
+        self.set_obstacles(mn, mx, self._env["ground"], self._env["tol"])
+
+    def env_get(self):
+        return self._env["pos"].copy(), self._env["vel"].copy()
+
+    def motion_validity(self, q_prev, q_cur, K: int, delta_time: float, commit_edge: int = -1):
+        q_prev, q_cur = _f32(q_prev, (-1, self.n)), _f32(q_cur, (-1, self.n))
+        E = q_prev.shape[0]
+        valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        prm, args = self._env_args()
+        rc = lib().orc_motion_validity(self._h, _p(prm, c_f32p), *args, _p(q_prev, c_f32p), _p(q_cur, c_f32p), ctypes.c_int64(E), ctypes.c_int32(K),
+                                       ctypes.c_float(delta_time), ctypes.c_int32(commit_edge), _p(valid, c_u8p), _p(first, c_i32p))
+        if rc:
+            raise RuntimeError(f"orc_motion_validity rc={rc}")
+        return valid.astype(bool), first
+
     def skeleton(self, q, f64=False):
         q = _f32(q, (-1, self.n))
         N = q.shape[0]

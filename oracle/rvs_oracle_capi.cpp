@@ -2,6 +2,7 @@
 // Mirrors the argument layout of include/rvs_cuda.h so the parity tests can feed both sides the same arrays.
 
 #include "rvs_oracle_engine.hpp"
+#include "rvs_oracle_env.hpp"
 
 using namespace orc_capi;
 
@@ -267,4 +268,83 @@ int orc_capsule_rect_collision_f32(int64_t K, const float *AB, const float *radi
     return 0;
 }
 
+
+// ---- dynamic environment (row f-2): Environment::updateEnvironment + MotionValidity::check ------------------------------------
+// env_params[6] = (WS_center xyz, WS_radius, base_radius, robot_max_vel); state arrays are updated in place.
+static std::vector<orc::EnvObject> env_objects(int M, const float *half, const float *pos, const float *vel, const float *max_vel, const int32_t *sign,
+                                               const float *path_len, const uint8_t *dynamic) {
+    std::vector<orc::EnvObject> objs(size_t(M > 0 ? M : 0));
+    for (int j = 0; j < M; j++) {
+        orc::EnvObject &o = objs[size_t(j)];
+        o.half = {half[3 * j], half[3 * j + 1], half[3 * j + 2]};
+        o.pos = {pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]};
+        o.vel = {vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]};
+        o.max_vel = max_vel[j]; o.sign = sign[j]; o.path_len = path_len[j]; o.dynamic = dynamic[j] != 0;
+    }
+    return objs;
+}
+static void env_store(const std::vector<orc::EnvObject> &objs, float *pos, float *vel, int32_t *sign, float *path_len) {
+    for (size_t j = 0; j < objs.size(); j++) {
+        const orc::EnvObject &o = objs[j];
+        pos[3 * j] = o.pos.x; pos[3 * j + 1] = o.pos.y; pos[3 * j + 2] = o.pos.z;
+        vel[3 * j] = o.vel.x; vel[3 * j + 1] = o.vel.y; vel[3 * j + 2] = o.vel.z;
+        sign[j] = o.sign; path_len[j] = o.path_len;
+    }
+}
+static orc::EnvParams env_params_of(const float *p, int motion_type) { return {motion_type, {p[0], p[1], p[2]}, p[3], p[4], p[5]}; }
+
+int orc_env_update(const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel, int32_t *sign,
+                   float *path_len, const uint8_t *dynamic, float dt, int32_t steps, float *aabb_min, float *aabb_max) {
+    if (motion_type == orc::MOTION_RANDOM_DIRECTIONS) return 5;
+    const orc::EnvParams ep = env_params_of(env_params, motion_type);
+    auto objs = env_objects(M, half, pos, vel, max_vel, sign, path_len, dynamic);
+    for (int k = 0; k < steps; k++) orc::env_update(ep, objs, dt);
+    env_store(objs, pos, vel, sign, path_len);
+    if (aabb_min && aabb_max) for (int j = 0; j < M; j++) orc::env_aabb(objs[size_t(j)], aabb_min + 3 * j, aabb_max + 3 * j);
+    return 0;
+}
+
+// MotionValidity::check(q_previous, q_current) for E motions that share one obstacle timeline: validity point k (1..K) of every
+// motion is tested against the environment after k updates.  first_invalid[e] = k of the first invalid point, 0 if the motion is
+// valid.  commit_edge >= 0: the state arrays and the engine's obstacle table are left as the reference leaves them after checking
+// THAT motion (updated first_invalid times, or K times); commit_edge < 0: nothing is changed.
+int orc_motion_validity(void *h, const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel,
+                        int32_t *sign, float *path_len, const uint8_t *dynamic, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float dt,
+                        int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
+    auto *e = static_cast<Engine *>(h);
+    if (motion_type == orc::MOTION_RANDOM_DIRECTIONS) return 5;
+    if (int(e->sc32.boxes.size()) != M || commit_edge >= E) return 1;
+    const orc::EnvParams ep = env_params_of(env_params, motion_type);
+    auto objs = env_objects(M, half, pos, vel, max_vel, sign, path_len, dynamic);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    orc::Scene<float> sc = e->sc32;
+    std::vector<orc::V3<float>> sk(size_t(n + 1));
+    std::vector<float> qk(size_t(n), 0.f);
+    std::vector<std::vector<orc::EnvObject>> timeline;
+    for (int64_t i = 0; i < E; i++) { valid[i] = 1; first_invalid[i] = 0; }
+    for (int k = 1; k <= K; k++) {
+        orc::env_update(ep, objs, dt);
+        timeline.push_back(objs);
+        for (int j = 0; j < M; j++) { float mn[3], mx[3]; orc::env_aabb(objs[size_t(j)], mn, mx); sc.boxes[size_t(j)] = {{mn[0], mn[1], mn[2], mx[0], mx[1], mx[2]}}; }
+        for (int64_t i = 0; i < E; i++) {
+            if (!valid[i]) continue;
+            orc::motion_point(q_prev + i * n, q_cur + i * n, n, k, K, qk.data());
+            orc::skeleton(e->robot, qk.data(), sk.data());
+            if (!orc::is_valid(e->robot, sc, sk.data(), cfg)) { valid[i] = 0; first_invalid[i] = k; }
+        }
+    }
+    if (commit_edge >= 0 && K > 0) {
+        const int kc = first_invalid[commit_edge] ? first_invalid[commit_edge] : K;
+        const auto &st = timeline[size_t(kc - 1)];
+        env_store(st, pos, vel, sign, path_len);
+        for (int j = 0; j < M; j++) {
+            float mn[3], mx[3];
+            orc::env_aabb(st[size_t(j)], mn, mx);
+            e->sc32.boxes[size_t(j)] = {{mn[0], mn[1], mn[2], mx[0], mx[1], mx[2]}};
+            for (int c = 0; c < 3; c++) { e->sc64.boxes[size_t(j)].o[c] = double(mn[c]); e->sc64.boxes[size_t(j)].o[3 + c] = double(mx[c]); }
+        }
+    }
+    return 0;
+}
 }  // extern "C"

@@ -1,0 +1,108 @@
+// rvs_oracle_env.hpp — CPU ORACLE (TEST INFRASTRUCTURE, NOT A PRODUCT PATH) of the dynamic environment:
+// the obstacle motion laws of env::Environment::updateEnvironment and the discretised motion check of
+// planning::trajectory::MotionValidity::check, restated from
+//   /root/reference/src/environments/Environment.cpp:194-377   (moveStraight, moveCircular, moveTwoTunnels, moveLightDirections)
+//   /root/reference/src/environments/Object.cpp:21-26 + objects/Box.cpp:3-8   (setPosition -> computeAABB: pos -/+ dim/2)
+//   /root/reference/src/planners/trajectory/MotionValidity.cpp:30-51          (check(q_previous, q_current))
+// in plain FP32 with Eigen's evaluation order (fixed-size Vector3f reductions as x0 + (x1 + x2), see rvs_oracle.hpp).
+//
+// PARITY STATUS: parity unpinned — the reference ships no golden vectors for the motion laws and Environment.cpp needs FCL and
+// yaml-cpp, which are absent here.  Pinned instead by closed-form known answers (tests/test_env_oracle.py): straight-line motion,
+// circular motion stays on its circle, the reflection law preserves speed and keeps every obstacle inside the workspace shell.
+// moveRandomDirections draws from Eigen::Vector3f::Random (libc rand()) and is therefore not restated (not reproducible).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+#include "rvs_oracle.hpp"
+
+namespace orc {
+
+enum MotionType { MOTION_STRAIGHT = 0, MOTION_CIRCULAR = 1, MOTION_TWO_TUNNELS = 2, MOTION_RANDOM_DIRECTIONS = 3, MOTION_LIGHT_DIRECTIONS = 4 };
+
+struct EnvParams {
+    int motion_type;
+    V3<float> ws_center;
+    float ws_radius, base_radius, robot_max_vel;
+};
+
+struct EnvObject {
+    V3<float> half;          // half extents of the AABB FCL computes (0.5 * dim; bounding-sphere cube for rotated boxes)
+    V3<float> pos, vel;
+    float max_vel;
+    int sign;                // Environment::sign(i)      (two_tunnels)
+    float path_len;          // Environment::path_len(i)  (two_tunnels)
+    bool dynamic;            // label == "dynamic_obstacle"
+};
+
+inline float norm2(float x, float y) { return std::sqrt(x * x + y * y); }
+
+// one updateEnvironment(delta_time) (Environment.cpp:194-222)
+inline void env_update(const EnvParams &ep, std::vector<EnvObject> &objs, float dt) {
+    for (size_t i = 0; i < objs.size(); i++) {
+        EnvObject &o = objs[i];
+        if (!o.dynamic) continue;
+        switch (ep.motion_type) {
+            case MOTION_STRAIGHT:                                       // (:224-238)
+                o.pos.x -= dt * o.max_vel;
+                break;
+            case MOTION_CIRCULAR: {                                     // (:241-258)
+                const float phi = std::atan2(o.pos.y, o.pos.x);
+                o.vel = {-std::sin(phi) * o.max_vel, std::cos(phi) * o.max_vel, 0.0f * o.max_vel};
+                o.pos = o.pos + dt * o.vel;
+                break;
+            }
+            case MOTION_TWO_TUNNELS: {                                  // (:261-289)
+                const float path_len_max = 0.2f;
+                if (o.path_len > path_len_max) { o.sign *= -1; o.path_len = -path_len_max; }
+                const float s = float(o.sign);
+                if (o.pos.y > 0) o.vel = {1.0f * s * o.max_vel, 0.0f * s * o.max_vel, 0.0f * s * o.max_vel};
+                else o.vel = {0.0f * s * o.max_vel, 1.0f * s * o.max_vel, 0.0f * s * o.max_vel};
+                o.path_len += normF(o.vel) * dt;
+                o.pos = o.pos + dt * o.vel;
+                break;
+            }
+            case MOTION_LIGHT_DIRECTIONS: {                             // (:336-377)
+                const float tol_radius = std::max(normF(o.vel) / ep.robot_max_vel, ep.base_radius);
+                const V3<float> pos_next = o.pos + dt * o.vel;
+                V3<float> n{0, 0, 0};
+                bool change = true;
+                if (pos_next.z < 0) n = {0, 0, 1};
+                else if (normF(pos_next - ep.ws_center) > ep.ws_radius) n = {-pos_next.x, -pos_next.y, -(pos_next.z - ep.ws_center.z)};
+                else if (norm2(pos_next.x, pos_next.y) < tol_radius && pos_next.z < ep.ws_center.z) n = {pos_next.x, pos_next.y, 0};
+                else if (normF(pos_next - ep.ws_center) < tol_radius) n = {pos_next.x, pos_next.y, pos_next.z - ep.ws_center.z};
+                else { o.pos = pos_next; change = false; }
+                if (change) {
+                    const float t_param = dotF(pos_next - o.pos, n) / sqnF(n);
+                    const float two_t = 2 * t_param;
+                    const V3<float> p_new{2 * pos_next.x - o.pos.x - two_t * n.x, 2 * pos_next.y - o.pos.y - two_t * n.y, 2 * pos_next.z - o.pos.z - two_t * n.z};
+                    o.pos = p_new;
+                    o.vel = {(p_new.x - pos_next.x) / dt, (p_new.y - pos_next.y) / dt, (p_new.z - pos_next.z) / dt};
+                }
+                break;
+            }
+            default: break;                                             // random_directions: not restated (libc rand())
+        }
+    }
+}
+
+// AABB of object i as FCL's computeAABB leaves it after setPosition (Object.cpp:21-26)
+inline void env_aabb(const EnvObject &o, float *mn, float *mx) {
+    mn[0] = o.pos.x + (-o.half.x); mn[1] = o.pos.y + (-o.half.y); mn[2] = o.pos.z + (-o.half.z);
+    mx[0] = o.pos.x + o.half.x;    mx[1] = o.pos.y + o.half.y;    mx[2] = o.pos.z + o.half.z;
+}
+
+// coordinates of the k-th validity point of MotionValidity::check (MotionValidity.cpp:40-44):
+//   interpolateEdge(q_previous, q_current, dist * k / K, dist)   (RealVectorSpace.cpp:75-88)
+inline void motion_point(const float *q_prev, const float *q_cur, int n, int k, int K, float *out) {
+    const float dist = coord_norm(q_prev, q_cur, n);
+    const float step = dist * float(k) / float(K);
+    if (dist > 0) {
+        const float f = step / dist;
+        for (int i = 0; i < n; i++) out[i] = q_prev[i] + (q_cur[i] - q_prev[i]) * f;
+    } else
+        for (int i = 0; i < n; i++) out[i] = q_cur[i];
+}
+
+}  // namespace orc

@@ -50,6 +50,15 @@ struct rvs_engine {
     int cull = 1;
     int num_ground = 0;
     unsigned long long *d_pair_count = nullptr;
+    // dynamic environment (rvs_env_*): obstacle states + the timeline of the last advance, all resident
+    EnvRec *d_env = nullptr;      // [env_cap] current states, then [env_tl_cap] timeline records, allocated separately
+    EnvRec *d_env_tl = nullptr;
+    float *d_scan_key = nullptr;
+    int32_t *d_first_invalid = nullptr;
+    int env_cap = 0;
+    size_t env_tl_cap = 0, env_fi_cap = 0;
+    bool env_on = false;
+    rvs_env_params env_prm{};
     float *d_store = nullptr;     // device-resident State cache (rvs_store_*): store_cap slots of store_slot_floats(n, M) floats
     int store_cap = 0;
     // Small host-pointer calls (planner-shaped: one to a few hundred configurations) skip the three DMA transfers: inputs are
@@ -347,6 +356,10 @@ int rvs_destroy(rvs_handle h) {
     if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_store) cudaFree(h->d_store);
+    if (h->d_env) cudaFree(h->d_env);
+    if (h->d_env_tl) cudaFree(h->d_env_tl);
+    if (h->d_scan_key) cudaFree(h->d_scan_key);
+    if (h->d_first_invalid) cudaFree(h->d_first_invalid);
     if (h->d_robot) cudaFree(h->d_robot);
     if (h->d_pair_count) cudaFree(h->d_pair_count);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -515,11 +528,13 @@ int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max
         h->d_store = nullptr; h->store_cap = 0;
     }
     h->M = M;
+    h->env_on = false;                       // a plain table: rvs_env_set switches the dynamic environment on again
     return upload_obstacles(h);
 }
 
 int rvs_update_obstacle_aabbs(rvs_handle h, const float *aabb_min, const float *aabb_max, int32_t M) {
     RVS_TRY(enter(h));
+    if (h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "the obstacle table is driven by rvs_env_*: move the objects with rvs_env_step / rvs_env_set");
     if (M != h->M) return fail(h, RVS_ERR_INVALID_ARGUMENT, "M differs from the resident obstacle table");
     if (M > 0 && (!aabb_min || !aabb_max)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL AABB arrays");
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));       // the pinned-less host mirror is reused: wait for the last copy
@@ -811,6 +826,142 @@ int rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *prof
     if (d_c) *d_c = tmp[n];
     if (profile) std::copy(tmp.begin() + n + 1, tmp.begin() + 2 * n + 1, profile);
     if (planes) std::copy(tmp.begin() + head, tmp.end(), planes);
+    return RVS_OK;
+}
+
+
+// ---- dynamic environment (rvs_env.cuh) ---------------------------------------------------------------------------------
+namespace {
+EnvArgs env_args(rvs_engine *h, int32_t K, float dt) {
+    EnvArgs a{};
+    a.robot = h->d_robot; a.state = h->d_env; a.timeline = h->d_env_tl; a.M = h->M; a.K = K; a.dt = dt;
+    a.motion_type = h->env_prm.motion_type;
+    for (int c = 0; c < 3; c++) a.ws_center[c] = h->env_prm.ws_center[c];
+    a.ws_radius = h->env_prm.ws_radius; a.base_radius = h->env_prm.base_radius; a.robot_max_vel = h->env_prm.robot_max_vel;
+    a.first_invalid = h->d_first_invalid; a.commit_edge = -1;
+    a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
+    a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.scan_dist = reinterpret_cast<float *>(h->d_obs + 2 * size_t(h->obs_cap));
+    a.scan_key = h->d_scan_key;
+    return a;
+}
+int env_ready(rvs_engine *h, int32_t K, float dt) {
+    if (!h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no dynamic environment: call rvs_env_set first");
+    if (K < 1 || !(dt > 0.f)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "steps / K >= 1 and delta_time > 0 required");
+    const size_t need = size_t(K) * size_t(h->M);
+    if (need > h->env_tl_cap) {
+        if (h->d_env_tl) RVS_CUDA(h, cudaFree(h->d_env_tl));
+        h->d_env_tl = nullptr; h->env_tl_cap = 0;
+        RVS_CUDA(h, cudaMalloc(&h->d_env_tl, std::max<size_t>(need, 1) * sizeof(EnvRec)));
+        h->env_tl_cap = need;
+    }
+    return RVS_OK;
+}
+}  // namespace
+
+int rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const float *pos, const uint8_t *rotated, const float *vel, const float *max_vel,
+                const uint8_t *is_dynamic, const uint8_t *is_ground, const float *min_dist_tol, int32_t M) {
+    RVS_TRY(enter(h));
+    if (!ep || M < 0 || (M > 0 && (!dim || !pos))) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad environment arrays");
+    if (ep->motion_type == RVS_MOTION_RANDOM_DIRECTIONS)
+        return fail(h, RVS_ERR_UNSUPPORTED, "random_directions draws from libc rand() in the reference (Environment.cpp:293-333): not reproducible, not supported");
+    if (ep->motion_type < RVS_MOTION_STRAIGHT || ep->motion_type > RVS_MOTION_LIGHT_DIRECTIONS) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown motion_type");
+    std::vector<EnvRec> recs(size_t(M), EnvRec{});
+    std::vector<float> mn(size_t(M) * 3), mx(size_t(M) * 3);
+    for (int j = 0; j < M; j++) {
+        EnvRec &r = recs[size_t(j)];
+        float half[3];
+        for (int c = 0; c < 3; c++) half[c] = 0.5f * dim[3 * j + c];
+        if (rotated && rotated[j]) {          // FCL: AABB of the bounding sphere for a non-identity rotation
+            const float rad = std::sqrt(half[0] * half[0] + half[1] * half[1] + half[2] * half[2]);
+            half[0] = half[1] = half[2] = rad;
+        }
+        for (int c = 0; c < 3; c++) {
+            r.half[c] = half[c]; r.pos[c] = pos[3 * j + c]; r.vel[c] = vel ? vel[3 * j + c] : 0.f;
+            mn[size_t(3 * j + c)] = r.pos[c] + (-half[c]); mx[size_t(3 * j + c)] = r.pos[c] + half[c];
+        }
+        r.max_vel = max_vel ? max_vel[j] : 0.f; r.path_len = 0.f; r.sign = 1;             // Environment.cpp:76-77
+        r.dynamic = (is_dynamic && is_dynamic[j]) ? 1u : 0u;
+        r.tol = min_dist_tol ? min_dist_tol[j] : h->prm.max_distance;
+        r.flags = (is_ground && is_ground[j]) ? 1u : 0u;
+    }
+    RVS_TRY(rvs_set_obstacles(h, mn.data(), mx.data(), is_ground, min_dist_tol, M));
+    if (M > h->env_cap) {
+        if (h->d_env) RVS_CUDA(h, cudaFree(h->d_env));
+        if (h->d_scan_key) RVS_CUDA(h, cudaFree(h->d_scan_key));
+        h->d_env = nullptr; h->d_scan_key = nullptr; h->env_cap = 0;
+        const int cap = M + M / 2 + 16;
+        RVS_CUDA(h, cudaMalloc(&h->d_env, size_t(cap) * sizeof(EnvRec)));
+        RVS_CUDA(h, cudaMalloc(&h->d_scan_key, size_t(cap) * sizeof(float)));
+        h->env_cap = cap;
+    }
+    if (M > 0) RVS_CUDA(h, cudaMemcpy(h->d_env, recs.data(), size_t(M) * sizeof(EnvRec), cudaMemcpyHostToDevice));
+    h->env_prm = *ep;
+    h->env_on = true;
+    return RVS_OK;
+}
+
+int rvs_env_step(rvs_handle h, float delta_time, int32_t steps) {
+    RVS_TRY(enter(h));
+    if (steps == 0) return RVS_OK;
+    RVS_TRY(env_ready(h, steps, delta_time));
+    if (h->M == 0) return RVS_OK;
+    EnvArgs a = env_args(h, steps, delta_time);
+    RVS_TRY(launched(h, launch_env_advance(a, h->stream), "environment advance launch"));
+    RVS_TRY(launched(h, launch_env_commit(a, h->stream), "environment commit launch"));
+    h->launches++;                                                          // commit = two grids
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    return RVS_OK;
+}
+
+int rvs_env_get(rvs_handle h, float *pos, float *vel) {
+    RVS_TRY(enter(h));
+    if (!h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no dynamic environment: call rvs_env_set first");
+    std::vector<EnvRec> recs(static_cast<size_t>(h->M), EnvRec{});
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->M > 0) RVS_CUDA(h, cudaMemcpy(recs.data(), h->d_env, size_t(h->M) * sizeof(EnvRec), cudaMemcpyDeviceToHost));
+    for (int j = 0; j < h->M; j++)
+        for (int c = 0; c < 3; c++) {
+            if (pos) pos[3 * j + c] = recs[size_t(j)].pos[c];
+            if (vel) vel[3 * j + c] = recs[size_t(j)].vel[c];
+        }
+    return RVS_OK;
+}
+
+int rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float delta_time, int32_t commit_edge, uint8_t *valid,
+                        int32_t *first_invalid) {
+    RVS_TRY(enter(h));
+    if (E < 0 || commit_edge >= E) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad E or commit_edge");
+    if (E == 0) return RVS_OK;
+    if (!q_prev || !q_cur || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(env_ready(h, K, delta_time));
+    if (size_t(E) > h->env_fi_cap) {
+        if (h->d_first_invalid) RVS_CUDA(h, cudaFree(h->d_first_invalid));
+        h->d_first_invalid = nullptr; h->env_fi_cap = 0;
+        const size_t cap = size_t(E) + size_t(E) / 2 + 64;
+        RVS_CUDA(h, cudaMalloc(&h->d_first_invalid, cap * sizeof(int32_t)));
+        h->env_fi_cap = cap;
+    }
+    const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, size_t(-1));                                              // device staging (first_invalid lives in device memory anyway)
+    RVS_TRY(h2d(h, B_Q, q_prev, bytes));
+    RVS_TRY(h2d(h, B_Q2, q_cur, bytes));
+    RVS_CUDA(h, cudaMemsetAsync(h->d_first_invalid, 0x7f, size_t(E) * sizeof(int32_t), h->stream));      // 0x7f7f7f7f: "no invalid point"
+    EnvArgs a = env_args(h, K, delta_time);
+    a.q_prev = static_cast<const float *>(h->buf[B_Q].p); a.q_cur = static_cast<const float *>(h->buf[B_Q2].p); a.E = E; a.commit_edge = commit_edge;
+    if (h->M > 0) RVS_TRY(launched(h, launch_env_advance(a, h->stream), "environment advance launch"));
+    RVS_TRY(launched(h, h->lt.motion_valid(a, h->stream), "motion validity launch"));
+    if (commit_edge >= 0 && h->M > 0) {
+        RVS_TRY(launched(h, launch_env_commit(a, h->stream), "environment commit launch"));
+        h->launches++;
+    }
+    std::vector<int32_t> fi(static_cast<size_t>(E), 0);
+    RVS_CUDA(h, cudaMemcpyAsync(fi.data(), h->d_first_invalid, size_t(E) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    RVS_TRY(finish(h));
+    for (int64_t e = 0; e < E; e++) {
+        const bool ok = fi[size_t(e)] > K;
+        valid[e] = ok ? 1 : 0;
+        if (first_invalid) first_invalid[e] = ok ? 0 : fi[size_t(e)];
+    }
     return RVS_OK;
 }
 

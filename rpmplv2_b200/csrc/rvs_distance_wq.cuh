@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_
     typedef typename WqBits<R>::type Bits;
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 
     WqCtx<R> c = wq_make_ctx<R, G>(wq_smem, reinterpret_cast<const float4 *>(a.obstacles_scan), L, a.M, 0, R(a.eq_thr), R(a.max_dist));
 

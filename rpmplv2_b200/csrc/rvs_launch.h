@@ -20,12 +20,15 @@ struct LaunchTable {
     cudaError_t (*spines)(const SpineArgs &, cudaStream_t);
     cudaError_t (*store_distance)(const StoreArgs &, cudaStream_t);
     cudaError_t (*store_spines)(const StoreArgs &, cudaStream_t);
+    cudaError_t (*motion_valid)(const EnvArgs &, cudaStream_t);
 };
 
 LaunchTable launch_table_ref32();    // FK FP64, geometry FP32, no FMA contraction, IEEE div/sqrt
 LaunchTable launch_table_f64();      // everything FP64, no FMA contraction
 LaunchTable launch_table_fast32();   // everything FP32, FMA contraction allowed
 cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st);
+cudaError_t launch_env_advance(const EnvArgs &a, cudaStream_t st);          // K updates of every obstacle -> timeline
+cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st);           // adopt timeline[kc], rewrite both copies of the obstacle table
 cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st);
 
 }  // namespace rvs

@@ -120,5 +120,37 @@ struct StoreArgs {
     uint8_t *status;           // [S]
 };
 
+// ---- dynamic environment (rvs_env.cuh) -------------------------------------------------------------------------------
+// One obstacle of env::Environment as it sits in HBM (64 bytes): what Environment::updateEnvironment reads and writes.
+struct EnvRec {
+    float half[3];        // half extents of the AABB that FCL's computeAABB produces (0.5 * dim; bounding-sphere cube if rotated)
+    float pos[3];         // env::Object::position
+    float vel[3];         // env::Object::velocity
+    float max_vel;        // env::Object::max_vel
+    float path_len;       // Environment::path_len(i)   (two_tunnels)
+    int32_t sign;         // Environment::sign(i)       (two_tunnels)
+    uint32_t dynamic;     // label == "dynamic_obstacle"
+    float tol;            // min_dist_tol
+    uint32_t flags;       // bit0: label == "ground"
+    uint32_t pad;
+};
+static_assert(sizeof(EnvRec) == 64, "EnvRec must be 64 bytes");
+
+struct EnvArgs {
+    const RobotDev *robot;
+    EnvRec *state;               // [M] current environment
+    EnvRec *timeline;            // [K][M] state after k = 1..K updates
+    int32_t M, K;
+    float dt;
+    int32_t motion_type;         // rvs_motion_type
+    float ws_center[3], ws_radius, base_radius, robot_max_vel;
+    const float *q_prev, *q_cur; // [E][n]
+    int64_t E;
+    int32_t *first_invalid;      // [E]
+    int32_t commit_edge;
+    float eq_thr, max_dist;
+    ObstacleRec *obstacles, *obstacles_scan;
+    float *scan_dist, *scan_key;
+};
 
 }  // namespace rvs

@@ -6,6 +6,7 @@
 #include "rvs_distance_wq.cuh"
 #include "rvs_valid_wq.cuh"
 #include "rvs_store.cuh"
+#include "rvs_env.cuh"
 #include "rvs_launch.h"
 
 namespace rvs {
@@ -106,8 +107,14 @@ struct Variant {
         store_spine_kernel<F><<<grid_for(a.S, 4), 128, 0, st>>>(a);
         return cudaGetLastError();
     }
+    static cudaError_t motion_valid(const EnvArgs &a, cudaStream_t st) {
+        if (a.E <= 0 || a.K <= 0) return cudaSuccess;
+        motion_valid_kernel<F, R><<<grid_for(a.E * a.K, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     static LaunchTable table() {
-        return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines, store_distance, store_spines};
+        return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines, store_distance, store_spines,
+                motion_valid};
     }
 };
 
@@ -119,6 +126,19 @@ LaunchTable launch_table_f64() { return Variant<double, double>::table(); }
 cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st) {
     if (a.N <= 0) return cudaSuccess;
     generate_configs_kernel<<<grid_for(a.N * a.robot_n_hint, 256), 256, 0, st>>>(a, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_env_advance(const EnvArgs &a, cudaStream_t st) {
+    if (a.M <= 0 || a.K <= 0) return cudaSuccess;
+    env_advance_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st) {
+    if (a.M <= 0 || a.K <= 0) return cudaSuccess;
+    env_commit_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    env_rank_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st) {

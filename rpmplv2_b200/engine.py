@@ -21,6 +21,21 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_u8p = ctypes.POINTER(ctypes.c_uint8)
 c_i32p = ctypes.POINTER(ctypes.c_int32)
 
+MOTION_STRAIGHT, MOTION_CIRCULAR, MOTION_TWO_TUNNELS, MOTION_RANDOM_DIRECTIONS, MOTION_LIGHT_DIRECTIONS = range(5)
+MOTION_TYPES = {"straight": MOTION_STRAIGHT, "circular": MOTION_CIRCULAR, "two_tunnels": MOTION_TWO_TUNNELS,
+                "random_directions": MOTION_RANDOM_DIRECTIONS, "light_directions": MOTION_LIGHT_DIRECTIONS}
+
+
+class RvsEnvParams(ctypes.Structure):
+    """rvs_env_params (include/rvs_cuda.h)."""
+    _fields_ = [("motion_type", ctypes.c_int32), ("ws_center", ctypes.c_float * 3), ("ws_radius", ctypes.c_float),
+                ("base_radius", ctypes.c_float), ("robot_max_vel", ctypes.c_float)]
+
+
+def env_params(motion_type, ws_center=(0.0, 0.0, 0.267), ws_radius=1.0, base_radius=0.3, robot_max_vel=1.0) -> RvsEnvParams:
+    mt = MOTION_TYPES[motion_type] if isinstance(motion_type, str) else int(motion_type)
+    return RvsEnvParams(mt, (ctypes.c_float * 3)(*[float(x) for x in ws_center]), float(ws_radius), float(base_radius), float(robot_max_vel))
+
 #: every symbol include/rvs_cuda.h declares: name -> (restype, argtypes)
 _H = ctypes.c_void_p
 SYMBOLS = {
@@ -70,6 +85,10 @@ SYMBOLS = {
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rvs_generate_configs_dev": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "rvs_set_culling": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_env_set": (ctypes.c_int, [_H, ctypes.POINTER(RvsEnvParams), c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_u8p, c_u8p, c_f32p, ctypes.c_int32]),
+    "rvs_env_step": (ctypes.c_int, [_H, ctypes.c_float, ctypes.c_int32]),
+    "rvs_env_get": (ctypes.c_int, [_H, c_f32p, c_f32p]),
+    "rvs_motion_validity": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, c_u8p, c_i32p]),
 }
 
 _lib = None
@@ -289,6 +308,37 @@ class Engine:
         d = ctypes.c_float(0)
         self._check(self._lib.rvs_store_read(self._h, slot, _p(q, c_f32p), ctypes.byref(d), _p(prof, c_f32p), _p(planes, c_f32p)))
         return q, float(d.value), prof, planes
+
+    # ---- dynamic environment ---------------------------------------------------------------------
+    def env_set(self, ep: RvsEnvParams, dim, pos, vel=None, max_vel=None, is_dynamic=None, is_ground=None, min_dist_tol=None, rotated=None):
+        """env::Environment with moving objects; replaces set_obstacles (Environment.cpp:13-109, 194-377)."""
+        dim, pos = _f32(dim, (-1, 3)), _f32(pos, (-1, 3))
+        M = dim.shape[0]
+        u8 = lambda a: None if a is None else np.ascontiguousarray(a, np.uint8).reshape(M)
+        f = lambda a, shape: None if a is None else _f32(a, shape)
+        vel, max_vel, tol = f(vel, (M, 3)), f(max_vel, (M,)), f(min_dist_tol, (M,))
+        rot, dyn, gr = u8(rotated), u8(is_dynamic), u8(is_ground)
+        self._env_keep = (dim, pos, vel, max_vel, tol, rot, dyn, gr)
+        self._check(self._lib.rvs_env_set(self._h, ctypes.byref(ep), _p(dim, c_f32p), _p(pos, c_f32p), _p(rot, c_u8p), _p(vel, c_f32p),
+                                         _p(max_vel, c_f32p), _p(dyn, c_u8p), _p(gr, c_u8p), _p(tol, c_f32p), M))
+        self.M = M
+
+    def env_step(self, delta_time: float, steps: int = 1):
+        self._check(self._lib.rvs_env_step(self._h, float(delta_time), int(steps)))
+
+    def env_get(self):
+        pos, vel = np.empty((self.M, 3), np.float32), np.empty((self.M, 3), np.float32)
+        self._check(self._lib.rvs_env_get(self._h, _p(pos, c_f32p), _p(vel, c_f32p)))
+        return pos, vel
+
+    def motion_validity(self, q_prev, q_cur, K: int, delta_time: float, commit_edge: int = -1):
+        """MotionValidity::check for E motions over one obstacle timeline -> (valid[E] bool, first_invalid[E])."""
+        q_prev, q_cur = _f32(q_prev, (-1, self.n)), _f32(q_cur, (-1, self.n))
+        E = q_prev.shape[0]
+        valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        self._check(self._lib.rvs_motion_validity(self._h, _p(q_prev, c_f32p), _p(q_cur, c_f32p), E, int(K), float(delta_time), int(commit_edge),
+                                                 _p(valid, c_u8p), _p(first, c_i32p)))
+        return valid.astype(bool), first
 
     def self_collision_capsules(self, q) -> np.ndarray:
         q = _f32(q, (-1, self.n))

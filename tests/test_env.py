@@ -1,0 +1,243 @@
+"""Dynamic environment: Environment::updateEnvironment's motion laws and MotionValidity::check.
+
+CPU part: the oracle restatement (oracle/rvs_oracle_env.hpp) against closed-form / invariant known answers and against an
+independent composition of its own primitives.  GPU part (-m gpu): rvs_env_* / rvs_motion_validity through the C ABI against the
+oracle on the same seeded inputs — bit-exact for the straight, two_tunnels and light_directions laws (add / mul / div / sqrt only),
+1e-5 m for the circular law (atan2f / sinf / cosf differ in the last ulp between CUDA and glibc).
+Reference: /root/reference/src/environments/Environment.cpp:194-377, src/planners/trajectory/MotionValidity.cpp:30-51.
+"""
+import numpy as np
+import pytest
+
+from rpmplv2_b200 import robots, synthetic
+from rpmplv2_b200.engine import env_params
+
+LAWS = ["straight", "circular", "two_tunnels", "light_directions"]
+WS_CENTER = (0.0, 0.0, 0.267)
+
+
+def dynamic_scene(rb, M_dyn, seed, speed=0.8, size=0.3, r_lo=0.45, r_hi=0.95):
+    """Ground box (static) + M_dyn cubes of side `size` in a shell around WS_center with random velocities (|v| <= max_vel = speed),
+    the shape of data/xarm6/scenario_random_obstacles and data/spatial_22dof/scenario_random_obstacles."""
+    rng = np.random.default_rng(seed)
+    d = rng.normal(size=(M_dyn, 3))
+    d[:, 2] = np.abs(d[:, 2])
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    r = rng.uniform(r_lo, r_hi, (M_dyn, 1))
+    pos = np.vstack([[0.0, 0.0, -0.05], np.asarray(WS_CENTER) + d * r]).astype(np.float32)
+    dim = np.vstack([[1.5, 1.5, 0.1], np.full((M_dyn, 3), size)]).astype(np.float32)
+    v = rng.normal(size=(M_dyn, 3))
+    v *= (rng.uniform(0.3, 1.0, (M_dyn, 1)) * speed) / np.linalg.norm(v, axis=1, keepdims=True)
+    vel = np.vstack([[0, 0, 0], v]).astype(np.float32)
+    max_vel = np.array([0.0] + [speed] * M_dyn, np.float32)
+    dyn = np.array([0] + [1] * M_dyn, np.uint8)
+    ground = np.array([1] + [0] * M_dyn, np.uint8)
+    tol = np.array([0.05] + [1000.0] * M_dyn, np.float32)
+    return dict(dim=dim, pos=pos, vel=vel, max_vel=max_vel, is_dynamic=dyn, is_ground=ground, min_dist_tol=tol)
+
+
+def params_for(law):
+    return env_params(law, ws_center=WS_CENTER, ws_radius=1.0, base_radius=0.3, robot_max_vel=1.5)
+
+
+def random_motions(rb, E, seed, length=0.3):
+    q1, q2 = synthetic.edges(rb, E, length=length, seed=seed)
+    return q1, q2
+
+
+# ---------------------------------------------------------------------------------------------------------------- CPU: oracle
+def test_oracle_straight_law_is_the_float_recurrence(ob):
+    sc = dynamic_scene(robots.xarm6(), 4, 1)
+    o = ob.Oracle(robots.xarm6())
+    o.env_set(params_for("straight"), **sc)
+    dt, steps = np.float32(0.013), 57
+    o.env_step(float(dt), steps)
+    pos, vel = o.env_get()
+    want = sc["pos"].copy()
+    for _ in range(steps):
+        want[1:, 0] = want[1:, 0] - dt * sc["max_vel"][1:]                # pos.x() -= delta_time * max_vel   (Environment.cpp:233)
+    assert np.array_equal(pos, want)
+    assert np.array_equal(vel, sc["vel"])                                   # the straight law never touches the velocity
+    assert np.array_equal(pos[0], sc["pos"][0])                             # the ground is not a dynamic_obstacle
+
+
+def test_oracle_circular_law_keeps_height_speed_and_spirals_out_by_the_euler_step(ob):
+    sc = dynamic_scene(robots.xarm6(), 5, 2)
+    o = ob.Oracle(robots.xarm6())
+    o.env_set(params_for("circular"), **sc)
+    dt = 0.004
+    r0 = np.hypot(sc["pos"][1:, 0], sc["pos"][1:, 1]).astype(np.float64)
+    for k in range(1, 40):
+        o.env_step(dt, 1)
+        pos, vel = o.env_get()
+        assert np.array_equal(pos[1:, 2], sc["pos"][1:, 2])
+        assert np.allclose(np.linalg.norm(vel[1:], axis=1), sc["max_vel"][1:], rtol=1e-6)
+        # explicit Euler along the tangent: r_k^2 = r_0^2 + k (v dt)^2
+        want = np.sqrt(r0 ** 2 + k * (sc["max_vel"][1:].astype(np.float64) * dt) ** 2)
+        assert np.allclose(np.hypot(pos[1:, 0], pos[1:, 1]), want, atol=2e-6)
+        # velocity is tangential (perpendicular to the radius before the step)
+    assert np.all(np.abs(np.einsum("ij,ij->i", vel[1:, :2], (pos[1:, :2] - vel[1:, :2] * np.float32(dt)))) < 1e-5)
+
+
+def test_oracle_two_tunnels_law_oscillates_along_the_axis_chosen_by_the_sign_of_y(ob):
+    sc = dynamic_scene(robots.xarm6(), 6, 3, speed=0.5)
+    o = ob.Oracle(robots.xarm6())
+    o.env_set(params_for("two_tunnels"), **sc)
+    p0 = sc["pos"].copy()
+    lo, hi = p0.copy(), p0.copy()
+    for _ in range(400):
+        o.env_step(0.01, 1)
+        pos, vel = o.env_get()
+        lo, hi = np.minimum(lo, pos), np.maximum(hi, pos)
+    along_x = p0[1:, 1] > 0
+    span = hi[1:] - lo[1:]
+    step = 0.5 * 0.01
+    checked = 0
+    for j in range(6):
+        a = 0 if along_x[j] else 1                                           # y > 0: along x, otherwise along y (Environment.cpp:276-279)
+        if not along_x[j] and p0[j + 1, 1] > -0.45:
+            continue                                                         # would cross y = 0 and change its axis on the way
+        checked += 1
+        # first leg 0.2 forwards (+ one step of overshoot), then legs of 0.4 backwards / forwards
+        assert 0.4 <= span[j, a] <= 0.4 + 3 * step
+        assert hi[j + 1, a] - p0[j + 1, a] <= 0.2 + 2 * step
+        assert np.all(span[j, [c for c in range(3) if c != a]] == 0)
+    assert checked >= 3
+
+
+def test_oracle_light_law_preserves_speed_and_keeps_objects_inside_the_workspace_shell(ob):
+    sc = dynamic_scene(robots.xarm6(), 12, 4, speed=0.9)
+    o = ob.Oracle(robots.xarm6())
+    ep = params_for("light_directions")
+    o.env_set(ep, **sc)
+    speed0 = np.linalg.norm(sc["vel"][1:], axis=1)
+    dt = 0.01
+    c = np.asarray(WS_CENTER, np.float32)
+    bounced = False
+    for _ in range(600):
+        o.env_step(dt, 1)
+        pos, vel = o.env_get()
+        assert np.allclose(np.linalg.norm(vel[1:], axis=1), speed0, rtol=2e-3)        # a mirror reflection keeps the speed
+        bounced |= not np.allclose(vel[1:], sc["vel"][1:])
+        rc = np.linalg.norm(pos[1:] - c, axis=1)
+        assert np.all(rc <= ep.ws_radius + 1e-3) and np.all(pos[1:, 2] >= -1e-3)         # reflected at the sphere and at z = 0
+        tol = np.maximum(speed0 / ep.robot_max_vel, ep.base_radius)
+        assert np.all(rc >= tol - 2 * 0.9 * dt)                                           # and at the robot-base exclusion zone
+    assert bounced
+
+
+def test_oracle_motion_validity_is_update_then_is_valid_point_by_point(ob):
+    """MotionValidity::check composed by hand from env_step + isValid (an independent path through the oracle's own primitives)."""
+    rb = robots.xarm6()
+    sc = dynamic_scene(rb, 5, 5)
+    K, dt = 8, 0.006
+    q1, q2 = random_motions(rb, 40, 0x77)
+    o = ob.Oracle(rb)
+    o.env_set(params_for("light_directions"), **sc)
+    valid, first = o.motion_validity(q1, q2, K, dt, commit_edge=-1)
+    p_before, _ = o.env_get()
+    assert np.array_equal(p_before, sc["pos"])                                          # what-if query: nothing moved
+    o2 = ob.Oracle(rb)
+    o2.env_set(params_for("light_directions"), **sc)
+    want_first = np.zeros(40, np.int32)
+    dist = np.sqrt(((q2.astype(np.float64) - q1) ** 2).sum(axis=1))
+    for k in range(1, K + 1):
+        o2.env_step(dt, 1)
+        f = (dist * k / K) / np.maximum(dist, 1e-30)
+        qk = (q1 + (q2 - q1) * f[:, None].astype(np.float32)).astype(np.float32)
+        ok = o2.is_valid(qk).astype(bool)
+        want_first[(want_first == 0) & ~ok] = k
+    # the interpolation factor above is computed in double: compare away from verdict flips caused by the last ulp of q
+    assert (first == want_first).mean() >= 0.95
+    assert np.array_equal(valid, first == 0)
+    assert 0 < valid.sum() < 40                                                         # the case set exercises both outcomes
+    # committing motion e leaves the environment after first_invalid[e] (or K) updates
+    e = int(np.flatnonzero(~valid)[0])
+    o.motion_validity(q1, q2, K, dt, commit_edge=e)
+    o3 = ob.Oracle(rb)
+    o3.env_set(params_for("light_directions"), **sc)
+    o3.env_step(dt, int(first[e]))
+    assert np.array_equal(o.env_get()[0], o3.env_get()[0])
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU parity
+def _pair(rb, ob_mod, law, sc, precision=None):
+    from rpmplv2_b200.engine import Engine
+    prm = robots.default_params() if precision is None else robots.default_params(precision=precision)
+    eng, orc = Engine(rb, prm), ob_mod.Oracle(rb, prm)
+    eng.env_set(params_for(law), **sc)
+    orc.env_set(params_for(law), **sc)
+    return eng, orc
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("law", LAWS)
+def test_gpu_motion_laws_match_the_oracle(ob, law):
+    rb = robots.xarm6()
+    sc = dynamic_scene(rb, 50, 11)
+    eng, orc = _pair(rb, ob, law, sc)
+    q = synthetic.configs(rb, 2048, seed=0xE1)
+    for steps, dt in [(1, 0.01), (7, 0.004), (120, 0.01), (33, 0.02)]:
+        eng.env_step(dt, steps)
+        orc.env_step(dt, steps)
+        (pe, ve), (po, vo) = eng.env_get(), orc.env_get()
+        if law == "circular":
+            assert np.allclose(pe, po, atol=1e-5) and np.allclose(ve, vo, atol=1e-5)
+        else:
+            assert np.array_equal(pe, po), np.abs(pe - po).max()
+            assert np.array_equal(ve, vo)
+    if law != "circular":
+        # the resident obstacle table (both copies: caller order and re-ranked scan order) followed the objects
+        d_e, p_e = eng.distance(q)[:2]
+        d_o, p_o = orc.distance(q)[:2]
+        assert np.array_equal(d_e, d_o) and np.array_equal(p_e, p_o)
+        assert np.array_equal(eng.is_valid(q), orc.is_valid(q))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("robot,M_dyn,law", [("xarm6", 5, "light_directions"), ("xarm6", 50, "light_directions"), ("xarm6", 5, "straight"),
+                                             ("spatial22", 5, "light_directions"), ("planar10", 4, "two_tunnels")])
+def test_gpu_motion_validity_matches_the_oracle(ob, robot, M_dyn, law):
+    rb = {"xarm6": robots.xarm6, "spatial22": lambda: robots.spatial(22), "planar10": lambda: robots.planar(10)}[robot]()
+    reach = 1.0 if robot == "xarm6" else float(np.abs(rb.xyz).sum())
+    sc = dynamic_scene(rb, M_dyn, 21, r_lo=0.45 * reach, r_hi=0.95 * reach, size=0.3 * reach)
+    if rb.ground_included == 0:                                             # planar chains live in the z = 0 plane, without a ground box
+        sc = {k: v[1:].copy() for k, v in sc.items()}
+        sc["pos"][:, 2] = 0.0
+    eng, orc = _pair(rb, ob, law, sc)
+    K, dt = 10, 0.005
+    q1, q2 = random_motions(rb, 512, 0x99)
+    v_e, f_e = eng.motion_validity(q1, q2, K, dt)
+    v_o, f_o = orc.motion_validity(q1, q2, K, dt)
+    assert np.array_equal(v_e, v_o) and np.array_equal(f_e, f_o)
+    assert 0 < v_o.sum() < len(v_o)
+    assert np.array_equal(eng.env_get()[0], sc["pos"])                                  # what-if: the environment did not move
+    # a DRGBT-like run: the committed motion decides how far the environment advances, iteration after iteration
+    for it in range(6):
+        e = it * 37 % 512
+        v_e, f_e = eng.motion_validity(q1, q2, K, dt, commit_edge=e)
+        v_o, f_o = orc.motion_validity(q1, q2, K, dt, commit_edge=e)
+        assert np.array_equal(f_e, f_o), it
+        assert np.array_equal(eng.env_get()[0], orc.env_get()[0]) and np.array_equal(eng.env_get()[1], orc.env_get()[1])
+    q = synthetic.configs(rb, 1024, seed=0xE2)
+    assert np.array_equal(eng.distance(q)[0], orc.distance(q)[0])
+
+
+@pytest.mark.gpu
+def test_gpu_env_argument_errors(ob):
+    from rpmplv2_b200.engine import Engine, RvsError
+    rb = robots.xarm6()
+    sc = dynamic_scene(rb, 3, 31)
+    eng = Engine(rb)
+    with pytest.raises(RvsError):
+        eng.env_step(0.01, 1)                                               # no environment yet
+    with pytest.raises(RvsError) as ei:
+        eng.env_set(params_for("random_directions"), **sc)                  # libc rand() in the reference: unsupported
+    assert ei.value.code == 5
+    eng.env_set(params_for("straight"), **sc)
+    with pytest.raises(RvsError):
+        eng.update_obstacle_aabbs(sc["pos"], sc["pos"])                     # the table is driven by the environment now
+    with pytest.raises(RvsError):
+        eng.motion_validity(np.zeros((2, 6), np.float32), np.zeros((2, 6), np.float32), 0, 0.01)
+    v, f = eng.motion_validity(np.zeros((0, 6), np.float32), np.zeros((0, 6), np.float32), 5, 0.01)
+    assert len(v) == 0
