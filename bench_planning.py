@@ -67,12 +67,12 @@ def _prune(eng_or_orc, sc):
     sc["obstacles"] = (mn[keep], mx[keep], g[keep], tol[keep])
 
 
-def run(P: int = 64, device: int = 0, cpu: bool = True, max_time: float = 30.0, only=None):
+def run(P: int = 64, device: int = 0, cpu: bool = True, max_time: float = 30.0, only=None, skip=None):
     from rpmplv2_b200 import engine
     threads = os.cpu_count() or 1
     rows = []
     for sc in scenarios():
-        if only and only not in sc["name"]:
+        if (only and only not in sc["name"]) or (skip and skip in sc["name"]):
             continue
         rb = sc["robot"]
         eng = engine.Engine(rb, robots.default_params(), device=device)
@@ -125,6 +125,7 @@ if __name__ == "__main__":
     ap.add_argument("--runs", type=int, default=64)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--only", default=None)
+    ap.add_argument("--skip", default=None, help="skip scenarios whose name contains this (e.g. 'M=1000' for large --runs)")
     args = ap.parse_args()
-    for row in run(args.runs, cpu=not args.no_cpu, only=args.only):
+    for row in run(args.runs, cpu=not args.no_cpu, only=args.only, skip=args.skip):
         print(json.dumps(row))

@@ -142,6 +142,43 @@ def main():
                  reached=int((st == 3).sum()), advanced=int((st == 1).sum()), all_collision_free=bool((dd > 0).all()))
         e2.close()
 
+    # ---- S2 (d) MotionValidity::check with the environment on the device (row f-2; config 4: spatial_22dof + 5 moving cubes) ----------
+    from oracle import oracle_binding as ob      # CPU column only (checker / baseline, never the measured product path)
+    for name, rbm in (("spatial_22dof", robots.spatial(22)), ("xarm6", rb)):
+        reach = 1.0 if name == "xarm6" else float(np.abs(rbm.xyz).sum())
+        sc = scenes.dynamic_scene(rbm, 5, 21, r_lo=0.45 * reach, r_hi=0.95 * reach, size=0.3 * reach)
+        ep = engine.env_params("light_directions", ws_center=scenes.WS_CENTER, ws_radius=1.0, base_radius=0.3, robot_max_vel=1.5)
+        em = engine.Engine(rbm, robots.default_params(), device=0)
+        orc = ob.Oracle(rbm)
+        K, dt = 10, 0.005
+        for E in (1, 64, 4096):
+            q1, q2 = synthetic.edges(rbm, E, length=0.3, seed=0x99)
+            em.env_set(ep, **sc)
+            orc.env_set(ep, **sc)
+            t = []
+            for _ in range(args.reps + 20):
+                t0 = time.perf_counter(); v, f = em.motion_validity(q1, q2, K, dt); t.append((time.perf_counter() - t0) * 1e3)
+            # what an integration WITHOUT the device environment pays: K x (host update + table upload + isValid launch)
+            half = np.float32(0.5) * sc["dim"]
+            t2 = []
+            em2 = engine.Engine(rbm, robots.default_params(), device=0)
+            em2.set_obstacles(sc["pos"] - half, sc["pos"] + half, sc["is_ground"], sc["min_dist_tol"])
+            dist = np.linalg.norm(q2 - q1, axis=1, keepdims=True)
+            for _ in range(args.reps + 5):
+                t0 = time.perf_counter()
+                pos = sc["pos"].copy()
+                for k in range(1, K + 1):
+                    pos = pos + np.float32(dt) * sc["vel"]                                   # stand-in for Environment::updateEnvironment on the host
+                    em2.update_obstacle_aabbs(pos - half, pos + half)
+                    em2.is_valid(q1 + (q2 - q1) * np.float32(k / K))
+                t2.append((time.perf_counter() - t0) * 1e3)
+            em2.close()
+            t0 = time.perf_counter(); vo, fo = orc.motion_validity(q1, q2, K, dt); cpu_ms = (time.perf_counter() - t0) * 1e3
+            emit(set="S2d", robot=name, M=6, E=E, checks=K, call="motion_validity (1 call)", host_call_ms=float(np.median(t[5:])),
+                 per_point_path_ms=float(np.median(t2[2:])), cpu_oracle_1thread_ms=cpu_ms, edges_per_s=E / np.median(t[5:]) * 1e3,
+                 valid=round(float(v.mean()), 4), identical_to_oracle=bool(np.array_equal(f, fo)))
+        em.close()
+
     # ---- S2 (c) single-query latency, planar_2dof scenario_test ----------------------------------------------------------
     rb2, pmn, pmx, pg, ptol = scenes.planar2_scenario_test()
     e3 = engine.Engine(rb2, robots.default_params(), device=0)
@@ -170,6 +207,8 @@ def main():
                 note = f"host call {r['host_call_us_median']:.1f} us (p95 {r['host_call_us_p95']:.1f})"
             if "hbm_write_gbs" in r:
                 note = f"{r['hbm_write_gbs']:.0f} GB/s written"
+            if "per_point_path_ms" in r:
+                note += f"; K x (upload + isValid) {r['per_point_path_ms']:.3f} ms; CPU oracle 1 thread {r['cpu_oracle_1thread_ms']:.3f} ms; identical {r['identical_to_oracle']}"
             if "reached" in r:
                 note += f"; reached {r['reached']}, advanced {r['advanced']}, collision-free {r['all_collision_free']}"
             pq = r.get("pair_queries_per_s") or r.get("nominal_pairs_per_s")

@@ -4,8 +4,10 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <functional>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 namespace rvsplan
 {
@@ -357,6 +359,85 @@ namespace rvsplan
 	};
 
 	// ---- the pool -----------------------------------------------------------------------------------------------------------
+	namespace
+	{
+		// Persistent helper threads for the resume step: run(count, fn) calls fn(i) for i in [0, count) on the caller and on whichever
+		// helpers are awake (dynamic chunks of 4) and returns when every item is done. The caller never waits for a helper to wake
+		// up: work is claimed through one atomic word (round << 32 | next index), so a helper that arrives late finds nothing to
+		// claim. Helpers spin for ~50 us after a round (rounds are separated by one backend call) before sleeping on the word.
+		class ResumeCrew
+		{
+		public:
+			explicit ResumeCrew(int threads)
+			{
+				for (int t = 1; t < threads; t++) helpers.emplace_back([this] { loop(); });
+			}
+			~ResumeCrew()
+			{
+				stop.store(true);
+				state.fetch_add(uint64_t(1) << 32);
+				state.notify_all();
+				for (auto &th : helpers) th.join();
+			}
+			template <class F>
+			void run(int count, F &&fn)
+			{
+				if (helpers.empty() || count < 32) { for (int i = 0; i < count; i++) fn(i); return; }
+				job = [&fn](int i) { fn(i); };
+				total.store(count, std::memory_order_relaxed);
+				done.store(0, std::memory_order_relaxed);
+				const uint64_t round = (state.load(std::memory_order_relaxed) >> 32) + 1;
+				state.store(round << 32, std::memory_order_release);
+				if (sleepers.load(std::memory_order_acquire) > 0) state.notify_all();
+				work(round);
+				for (int spin = 0; done.load(std::memory_order_acquire) < count; spin++)
+					if (spin > 4000) std::this_thread::yield();
+			}
+		private:
+			void work(uint64_t round)
+			{
+				for (;;)
+				{
+					uint64_t cur = state.load(std::memory_order_acquire);
+					const int n = total.load(std::memory_order_relaxed);
+					if ((cur >> 32) != round || int(cur & 0xffffffffu) >= n) return;
+					if (!state.compare_exchange_weak(cur, cur + 4, std::memory_order_acq_rel)) continue;
+					const int b = int(cur & 0xffffffffu), e = std::min(n, b + 4);
+					for (int i = b; i < e; i++) job(i);
+					done.fetch_add(e - b, std::memory_order_release);
+				}
+			}
+			void loop()
+			{
+				uint64_t seen = 0;
+				for (;;)
+				{
+					uint64_t cur;
+					const auto t_spin = std::chrono::steady_clock::now();
+					for (int spin = 0;; spin++)
+					{
+						cur = state.load(std::memory_order_acquire);
+						if ((cur >> 32) != seen) break;
+						if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t_spin > std::chrono::microseconds(50))
+						{
+							sleepers.fetch_add(1, std::memory_order_acq_rel);
+							state.wait(cur);
+							sleepers.fetch_sub(1, std::memory_order_acq_rel);
+						}
+					}
+					seen = cur >> 32;
+					if (stop.load()) return;
+					work(seen);
+				}
+			}
+			std::vector<std::thread> helpers;
+			std::function<void(int)> job;
+			std::atomic<int> total{0}, done{0}, sleepers{0};
+			std::atomic<uint64_t> state{0};
+			std::atomic<bool> stop{false};
+		};
+	}
+
 	std::vector<PlannerResult> PlannerPool::solve(const float *q_start, const float *q_goal, const uint64_t *seeds, int P, bool skip_invalid)
 	{
 		const int n = backend.numDofs();
@@ -372,6 +453,8 @@ namespace rvsplan
 			tasks.emplace_back(runs.back()->solve());
 			tasks.back().handle().resume();
 		}
+		int nthreads = host_threads > 0 ? host_threads : int(std::thread::hardware_concurrency());
+		ResumeCrew crew(std::max(1, std::min({nthreads, 32, P / 16})));
 		std::vector<float> q1, q2, d, q_layers;
 		std::vector<int32_t> sl, n_layers;
 		std::vector<uint8_t> flags;
@@ -442,7 +525,7 @@ namespace rvsplan
 					runs[p]->res.rounds++;
 				}
 				// resume after the scatter: a resumed run overwrites its request with the next one (possibly of a kind served later in this round)
-				for (int p : who) runs[p]->resume_at.resume();
+				crew.run(int(who.size()), [&](int i) { runs[size_t(who[size_t(i)])]->resume_at.resume(); });
 			}
 			if (!any) break;
 			num_rounds++;

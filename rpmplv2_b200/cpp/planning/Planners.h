@@ -13,7 +13,8 @@
 // their answers. On the GPU a round costs a few kernel launches whatever P is, so P runs finish in about the time of the
 // slowest one. Inside one run the planner also batches what the reference does one call at a time: the NUM_SPINES spines
 // of a bur are one spine query, and the straight-line marching of connect() is one edge query (the marching points do not
-// depend on the verdicts, only the stopping index does).
+// depend on the verdicts, only the stopping index does). Between two backend calls the runs are resumed by a small pool of host
+// threads (tree growth and the linear nearest-neighbour scans are the host-side cost of a round).
 //
 // Differences from the reference, all outside the collision/distance path: nearest neighbours are found by a linear scan
 // instead of nanoflann's kd-tree (both exact); random numbers come from a counter-based generator instead of
@@ -23,6 +24,7 @@
 #ifndef RVS_PLANNING_PLANNERS_H
 #define RVS_PLANNING_PLANNERS_H
 
+#include <atomic>
 #include <coroutine>
 #include <cstdint>
 #include <exception>
@@ -144,13 +146,13 @@ namespace rvsplan
 		std::vector<float> q;
 	};
 
-	class SlotAllocator
+	class SlotAllocator                      // shared by the runs of a pool, which are resumed from several host threads
 	{
 	public:
-		int next() { return count++; }
-		int used() const { return count; }
+		int next() { return count.fetch_add(1, std::memory_order_relaxed); }
+		int used() const { return count.load(std::memory_order_relaxed); }
 	private:
-		int count = 0;
+		std::atomic<int> count{0};
 	};
 
 	class PlannerRun;
@@ -159,7 +161,9 @@ namespace rvsplan
 	class PlannerPool
 	{
 	public:
-		PlannerPool(SpaceBackend &backend_, const PlannerConfig &cfg_) : backend(backend_), cfg(cfg_) {}
+		// host_threads: threads that resume the runs between two backend calls (0 = all hardware threads, 1 = serial). The runs
+		// are independent (own tree, own random stream), so this only changes the wall time, never a result.
+		PlannerPool(SpaceBackend &backend_, const PlannerConfig &cfg_, int host_threads_ = 0) : backend(backend_), cfg(cfg_), host_threads(host_threads_) {}
 		// q_start / q_goal: P x n. Throws std::domain_error when a start or goal is invalid (RRTConnect.cpp:13-16) unless
 		// skip_invalid is set, in which case that run reports success = false with 0 iterations.
 		std::vector<PlannerResult> solve(const float *q_start, const float *q_goal, const uint64_t *seeds, int P, bool skip_invalid = false);
@@ -168,6 +172,7 @@ namespace rvsplan
 	private:
 		SpaceBackend &backend;
 		PlannerConfig cfg;
+		int host_threads;
 		int64_t num_rounds = 0, num_calls = 0;
 	};
 }

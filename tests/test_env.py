@@ -11,29 +11,9 @@ import pytest
 
 from rpmplv2_b200 import robots, synthetic
 from rpmplv2_b200.engine import env_params
+from scenes import WS_CENTER, dynamic_scene
 
 LAWS = ["straight", "circular", "two_tunnels", "light_directions"]
-WS_CENTER = (0.0, 0.0, 0.267)
-
-
-def dynamic_scene(rb, M_dyn, seed, speed=0.8, size=0.3, r_lo=0.45, r_hi=0.95):
-    """Ground box (static) + M_dyn cubes of side `size` in a shell around WS_center with random velocities (|v| <= max_vel = speed),
-    the shape of data/xarm6/scenario_random_obstacles and data/spatial_22dof/scenario_random_obstacles."""
-    rng = np.random.default_rng(seed)
-    d = rng.normal(size=(M_dyn, 3))
-    d[:, 2] = np.abs(d[:, 2])
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    r = rng.uniform(r_lo, r_hi, (M_dyn, 1))
-    pos = np.vstack([[0.0, 0.0, -0.05], np.asarray(WS_CENTER) + d * r]).astype(np.float32)
-    dim = np.vstack([[1.5, 1.5, 0.1], np.full((M_dyn, 3), size)]).astype(np.float32)
-    v = rng.normal(size=(M_dyn, 3))
-    v *= (rng.uniform(0.3, 1.0, (M_dyn, 1)) * speed) / np.linalg.norm(v, axis=1, keepdims=True)
-    vel = np.vstack([[0, 0, 0], v]).astype(np.float32)
-    max_vel = np.array([0.0] + [speed] * M_dyn, np.float32)
-    dyn = np.array([0] + [1] * M_dyn, np.uint8)
-    ground = np.array([1] + [0] * M_dyn, np.uint8)
-    tol = np.array([0.05] + [1000.0] * M_dyn, np.float32)
-    return dict(dim=dim, pos=pos, vel=vel, max_vel=max_vel, is_dynamic=dyn, is_ground=ground, min_dist_tol=tol)
 
 
 def params_for(law):
