@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
 #pragma unroll
                 for (int k = 0; k < 3; k++) { const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride]; mag = fmax(mag, fmax(fabs(u), fabs(v))); }
                 const R thr = RobotScalars<R>::radius(rb, i - 1) * R(1.001) + R(1e-5) + R(4e-6) * mag;
-                cut[(i - 1) * kWqStride + t] = (fmax(prev, nrm) + R(1.7320509) * thr) * R(1.00001);
+                cut[(i - 1) * kWqStride + t] = (fmax(prev, nrm) + fmax(R(1.7320509) * thr, eq_thr * R(1.001) + R(1e-5))) * R(1.00001);
             }
             prev = nrm;
         }
@@ -115,7 +115,23 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                     cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, radius[link], radius_in[link]);
                     const float4 w0 = __ldg(obs4 + 2 * j), w1 = __ldg(obs4 + 2 * j + 1);
                     const Box<R> bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
-                    if (capsule_hits_box<R>(cp, bx, eq_thr, max_dist)) invalid[tt] = 1u;
+                    // Cheap exact-safe reject in front of the reference predicate (up to ~5000 instructions when all three face tests
+                    // run): every `true` of collisionCapsuleToBox implies an axis point within sqrt(2) * radius of the box (endpoint in the
+                    // box inflated by r/sqrt(3); crossing point inside the rectangle oversized by r; an edge or face distance < r), hence
+                    // within sqrt(2) r + (half diagonal) of the box centre.  A diagonal link's bounding box passes the slab test for many
+                    // small boxes that are nowhere near the segment itself.
+                    const R cx = (bx.lo.x + bx.hi.x) * R(0.5), cy = (bx.lo.y + bx.hi.y) * R(0.5), cz = (bx.lo.z + bx.hi.z) * R(0.5);
+                    const R hx = (bx.hi.x - bx.lo.x) * R(0.5), hy = (bx.hi.y - bx.lo.y) * R(0.5), hz = (bx.hi.z - bx.lo.z) * R(0.5);
+                    const R ux = cp.B.x - cp.A.x, uy = cp.B.y - cp.A.y, uz = cp.B.z - cp.A.z;
+                    const R vx = cx - cp.A.x, vy = cy - cp.A.y, vz = cz - cp.A.z;
+                    const R uu = ux * ux + uy * uy + uz * uz, uv = ux * vx + uy * vy + uz * vz, vv = vx * vx + vy * vy + vz * vz;
+                    R d2;                                                       // squared distance of the box centre from the segment
+                    if (!(uv > R(0))) d2 = vv;
+                    else if (uv >= uu) { const R wx = cx - cp.B.x, wy = cy - cp.B.y, wz = cz - cp.B.z; d2 = wx * wx + wy * wy + wz * wz; }
+                    else d2 = vv - uv * uv / uu;
+                    const R reach = sqrt(hx * hx + hy * hy + hz * hz) + fmax(R(1.41422) * radius[link], eq_thr) * R(1.001) + R(1e-4);      // (a segment-edge distance below EQUALITY_THRESHOLD snaps to 0 = hit)
+                    const bool far = d2 - R(4e-6) * (vv + R(1)) > reach * reach * R(1.002);     // (NaN anywhere: not far, the predicate decides)
+                    if (!far && capsule_hits_box<R>(cp, bx, eq_thr, max_dist)) invalid[tt] = 1u;
                 }
             }
         }
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
             const float4 *o4 = obs4 + 2 * size_t(base);
             const float *sd = a.scan_dist + base;
 #pragma unroll 1
-            for (int j0 = 0; j0 < count; j0 += 64) {
+            for (int j0 = 0; j0 < count; j0 += 64) {      // (an interval = 64 obstacles)
                 // every 64 obstacles: drop configurations that are already invalid and links no later obstacle can reach; pack the
                 // live links into slots 0..K-1 (K and the slot -> link map are warp-uniform)
                 const bool dead = !live || invalid[t] != 0u;
@@ -142,7 +158,9 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                     if (!dead && i < L && !(dnext > cut[i * kWqStride + t])) mine |= 1u << l;
                 }
                 alive &= __reduce_or_sync(0xffffffffu, mine);
-                if (!alive) break;
+                // nothing left to test: one empty iteration over the tail of the table, so that the flush at the end of every
+                // interval (the only inlined copy of the exact predicate) still runs for this group
+                const int jfirst = alive ? j0 : (count - 1) & ~1;
                 const int K = __popc(alive);
                 unsigned slotmap = 0, ground_keep = 0;
                 R lo[G][3], hi[G][3];
@@ -175,9 +193,9 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                     }
                     ground_keep *= (1u << G) + 1u;
                 }
-                const int jend = min(j0 + 64, count);
+                const int jend = alive ? min(j0 + 64, count) : count;
 #pragma unroll 1
-                for (int j = j0; j < jend; j += kWqUnroll) {
+                for (int j = jfirst; j < jend; j += kWqUnroll) {
                     const int j1 = j + 1 < jend ? j + 1 : j;
                     const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
                     const float4 w0 = __ldg(pj), w1 = __ldg(pj + 1), v0 = __ldg(pj1), v1 = __ldg(pj1 + 1);
@@ -188,6 +206,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
         wq_overlap<R>(mask, 1u << (G + (S)), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
     }
                     switch (K) {
+                        case 0: break;
                         default: RVS_VQ_SLOT(5) [[fallthrough]];
                         case 5: RVS_VQ_SLOT(4) [[fallthrough]];
                         case 4: RVS_VQ_SLOT(3) [[fallthrough]];
@@ -210,12 +229,15 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                         } while (mask);
                     }
                     __syncwarp();
-                    if (tail[0] >= 32u) drain(false);
+                    // Every interval ends with a flush: a configuration whose only colliding pairs wait in a partly filled queue would
+                    // otherwise stay "valid" and keep its links open (and the whole warp scanning) to the end of the table.
+                    const bool last = j + kWqUnroll >= jend;
+                    if (tail[0] >= 32u || last) drain(last);
                 }
+                if (!alive) break;
             }
         }
     }
-    drain(true);
     __syncwarp();
     if (!live) return;
     if (!EDGE) a.verdict[item] = invalid[t] ? 0 : 1;
