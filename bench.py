@@ -50,14 +50,29 @@ def scene():
 
 
 class ClockSampler:
-    """nvidia-smi sampler running DURING the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock / throttle-reason sampler running DURING the timed region (B200_PROFILING.md clocks line).
+
+    NVML in-process (one sample per ~2 ms: the timed region of this bench is only tens of milliseconds long, and an `nvidia-smi -lms`
+    child needs longer than that to print its first line); falls back to the nvidia-smi child when pynvml is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, index: int):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml, self.samples, self.run = index, [], None, None, [], False
+        self.t0 = self.t1 = None
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.handle = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.run = True
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -65,11 +80,41 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        while self.run:
+            try:
+                self.samples.append((time.perf_counter(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetCurrentClocksThrottleReasons(h),
+                                     nv.nvmlDeviceGetPowerUsage(h) / 1000.0))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml:
+            self.run = False
+            self.thread.join(timeout=1.0)
+            nv = self.nvml
+            inside = [x for x in self.samples if self.t0 is not None and self.t1 is not None and self.t0 <= x[0] <= self.t1]
+            if not inside:
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+            sm = sorted(x[1] for x in inside)
+            mask = 0
+            for x in inside:
+                mask |= int(x[2])
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)),
+                    "reasons": [n for b, n in self.REASONS if mask & b], "samples": len(inside), "power_w_max": round(max(x[3] for x in inside), 2),
+                    "source": "nvml, sampled inside the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -81,7 +126,7 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for k, n in enumerate(names) if any(r[4 + k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(rows[0][2]), "reasons": reasons, "samples": len(rows),
-                "power_w_max": max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit())}
+                "power_w_max": max(float(r[3]) for r in rows if r[3].replace(".", "").isdigit()), "source": "nvidia-smi -lms 20"}
 
 
 def measured_peaks():
@@ -211,12 +256,14 @@ def main():
     sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
+    sampler.mark_begin()
     for s in range(K):
         flush.fill_(s & 0xFF)                     # L2 flush, outside the event bracket
         ev[s][0].record(stream)
         step(W + s)
         ev[s][1].record(stream)
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     ms = [a.elapsed_time(b) for a, b in ev]
     t_rank = sum(ms) * 1e-3
