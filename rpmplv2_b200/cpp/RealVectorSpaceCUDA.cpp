@@ -110,6 +110,84 @@ void base::RealVectorSpaceCUDA::refreshObstacles()
 	check(rvs_set_obstacles(engine, aabb_min.data(), aabb_max.data(), is_ground.data(), tol.data(), int32_t(num_objects)), "refreshObstacles");
 }
 
+/// env::Environment's dynamic state (Object.h:27-31, Environment.h:54-60) -> rvs_env_set.
+void base::RealVectorSpaceCUDA::attachDynamicEnvironment(rvs_motion_type motion_type)
+{
+	num_objects = env->getNumObjects();
+	std::vector<float> dim(3 * num_objects), pos(3 * num_objects), vel(3 * num_objects), max_vel(num_objects), tol(num_objects);
+	std::vector<uint8_t> is_ground(num_objects), is_dynamic(num_objects);
+	for (size_t j = 0; j < num_objects; j++)
+	{
+		if (env->getCollObject(j)->getNodeType() != fcl::GEOM_BOX)
+			throw std::runtime_error("RealVectorSpaceCUDA: only box obstacles are supported (the reference's sphere branch is a TODO stub)");
+		const fcl::AABB &AABB { env->getCollObject(j)->getAABB() };
+		const std::shared_ptr<env::Object> object { env->getObject(j) };
+		for (int k = 0; k < 3; k++)
+		{
+			dim[3 * j + k] = AABB.max_[k] - AABB.min_[k];
+			pos[3 * j + k] = object->getPosition()(k);
+			vel[3 * j + k] = object->getVelocity()(k);
+		}
+		max_vel[j] = object->getMaxVel();
+		is_ground[j] = object->getLabel() == "ground" ? 1 : 0;
+		is_dynamic[j] = object->getLabel() == "dynamic_obstacle" ? 1 : 0;
+		tol[j] = object->getMinDistTol();
+	}
+	rvs_env_params ep;
+	ep.motion_type = int32_t(motion_type);
+	for (int k = 0; k < 3; k++)
+		ep.ws_center[k] = env->getWSCenter()(k);
+	ep.ws_radius = env->getWSRadius();
+	ep.base_radius = env->getBaseRadius();
+	ep.robot_max_vel = env->getRobotMaxVel();
+	check(rvs_env_set(engine, &ep, dim.data(), pos.data(), nullptr, vel.data(), max_vel.data(), is_dynamic.data(), is_ground.data(), tol.data(),
+					  int32_t(num_objects)), "attachDynamicEnvironment");
+}
+
+bool base::RealVectorSpaceCUDA::checkMotion(const std::shared_ptr<base::State> q_previous, const std::shared_ptr<base::State> q_current,
+	size_t num_checks, float delta_time, std::vector<std::shared_ptr<base::State>> *path)
+{
+	uint8_t valid { 0 };
+	int32_t first_invalid { 0 };
+	check(rvs_motion_validity(engine, q_previous->getCoord().data(), q_current->getCoord().data(), 1, int32_t(num_checks), delta_time, 0,
+							  &valid, &first_invalid), "checkMotion");
+
+	// the objects are where the reference's loop would have left them: mirror them back for logging / the next planner step
+	std::vector<float> pos(3 * num_objects), vel(3 * num_objects);
+	check(rvs_env_get(engine, pos.data(), vel.data()), "checkMotion");
+	for (size_t j = 0; j < num_objects; j++)
+	{
+		if (env->getObject(j)->getLabel() != "dynamic_obstacle")
+			continue;
+		env->getObject(j)->setPosition(fcl::Vector3f(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]));
+		env->getObject(j)->setVelocity(fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
+	}
+
+	if (path != nullptr)
+	{
+		const float dist { getNorm(q_previous, q_current) };
+		const size_t passed { valid ? num_checks : size_t(first_invalid - 1) };
+		for (size_t num_check = 1; num_check <= passed; num_check++)
+			path->emplace_back(interpolateEdge(q_previous, q_current, dist * num_check / num_checks, dist));
+	}
+	return valid != 0;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::checkMotionBatch
+	(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &motions, size_t num_checks, float delta_time)
+{
+	std::vector<float> q1(motions.size() * num_dimensions), q2(motions.size() * num_dimensions);
+	for (size_t e = 0; e < motions.size(); e++)
+	{
+		std::memcpy(&q1[e * num_dimensions], motions[e].first->getCoord().data(), num_dimensions * sizeof(float));
+		std::memcpy(&q2[e * num_dimensions], motions[e].second->getCoord().data(), num_dimensions * sizeof(float));
+	}
+	std::vector<uint8_t> valid(motions.size());
+	check(rvs_motion_validity(engine, q1.data(), q2.data(), int64_t(motions.size()), int32_t(num_checks), delta_time, -1, valid.data(), nullptr),
+		  "checkMotionBatch");
+	return valid;
+}
+
 void base::RealVectorSpaceCUDA::gather(const std::vector<std::shared_ptr<base::State>> &states, std::vector<float> &q) const
 {
 	q.resize(states.size() * num_dimensions);

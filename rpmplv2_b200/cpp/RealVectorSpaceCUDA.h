@@ -18,6 +18,8 @@
 //     robots::AbstractRobot the scenario built. Obstacles are read from env::Environment (AABB of every
 //     fcl::CollisionObject, label == "ground", min_dist_tol); call refreshObstacles() after the environment changed
 //     (Environment::addObject / removeObject / updateEnvironment).
+//   * dynamic scenes: attachDynamicEnvironment + checkMotion replace the K x { env->updateEnvironment; isValid } loop of
+//     planning::trajectory::MotionValidity::check by one engine call (rvs_motion_validity).
 //   * there is NO CPU fallback: the constructor throws std::runtime_error when the engine cannot be created.
 #ifndef RPMPL_REALVECTORSPACECUDA_H
 #define RPMPL_REALVECTORSPACECUDA_H
@@ -65,6 +67,21 @@ namespace base
 		// computeDistanceUnderestimation of every state w.r.t. ONE root's planes (the spine set of a bur)
 		std::vector<float> computeDistanceUnderestimationBatch(const std::vector<std::shared_ptr<base::State>> &states,
 			const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points);
+
+		// ---- dynamic environment on the device ----
+		// Hands env's objects (position, velocity, max_vel, label == "dynamic_obstacle"; box side = extent of the current AABB,
+		// use fcl::Box::side with the real FCL) and the workspace parameters to the engine, which from then on moves the objects
+		// itself. motion_type is the scenario YAML's testing.motion_type (env::Environment keeps it private, Environment.h:62-70).
+		void attachDynamicEnvironment(rvs_motion_type motion_type);
+		// planning::trajectory::MotionValidity::check(q_previous, q_current) (MotionValidity.cpp:30-51): num_checks times
+		// { updateEnvironment(delta_time); interpolateEdge; isValid } in ONE engine call. Afterwards env's objects sit where the
+		// reference leaves them (positions / velocities mirrored back with setPosition / setVelocity); `path`, if given, receives
+		// the validity points that passed, as the reference appends them. robot->checkSelfCollision stays with the caller.
+		bool checkMotion(const std::shared_ptr<base::State> q_previous, const std::shared_ptr<base::State> q_current, size_t num_checks,
+						 float delta_time, std::vector<std::shared_ptr<base::State>> *path = nullptr);
+		// The same check for many candidate motions against ONE obstacle timeline; the environment is not moved.
+		std::vector<uint8_t> checkMotionBatch(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &motions,
+											  size_t num_checks, float delta_time);
 
 		// re-read env->getObjects() into the device obstacle table (24 B per object)
 		void refreshObstacles();

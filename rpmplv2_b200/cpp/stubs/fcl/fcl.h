@@ -4,8 +4,12 @@
 namespace fcl {
 struct Vector3f {
     float v[3] = {0, 0, 0};
+    Vector3f() = default;
+    Vector3f(float x, float y, float z) : v{x, y, z} {}
     float &operator[](int i) { return v[i]; }
     float operator[](int i) const { return v[i]; }
+    float &operator()(int i) { return v[i]; }
+    float operator()(int i) const { return v[i]; }
 };
 struct AABB { Vector3f min_, max_; };
 enum NODE_TYPE { BV_UNKNOWN, GEOM_BOX, GEOM_SPHERE };

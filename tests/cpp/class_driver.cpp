@@ -119,4 +119,48 @@ int drv_run(const char *urdf_path, const char *robot_type, int n, const float *r
     }
 }
 
+
+// Dynamic environment (row f-2): T consecutive MotionValidity-style checks q_t -> q_{t+1} through checkMotion (the environment
+// advances as the reference's loop would), then one what-if batch of all T motions against the final environment.
+// Outputs: valid[T], passed[T] (validity points appended to `path`), pos_after[T*M*3] (object positions mirrored back into
+// env::Object after every check), batch_valid[T].
+int drv_motion(const char *urdf_path, const char *robot_type, int n, const float *radii, float gripper_length, int ground_included, const float *limits,
+               const float *dim, const float *pos, const float *vel, const float *max_vel, const uint8_t *is_dynamic, const uint8_t *is_ground,
+               const float *tol, int M, int motion_type, const float *ws /*center xyz, radius, base_radius, robot_max_vel*/,
+               const float *q, int T, int num_checks, float delta_time, uint8_t *valid, int32_t *passed, float *pos_after, uint8_t *batch_valid) {
+    try {
+        std::vector<float> mn(size_t(3 * M)), mx(size_t(3 * M));
+        for (int j = 0; j < M; j++)
+            for (int k = 0; k < 3; k++) { const float half = 0.5f * dim[3 * j + k]; mn[3 * j + k] = pos[3 * j + k] + (-half); mx[3 * j + k] = pos[3 * j + k] + half; }
+        auto ss = make_space(urdf_path, robot_type, n, radii, gripper_length, ground_included, limits, mn.data(), mx.data(), is_ground, tol, M, 1e-4f, 10);
+        for (int j = 0; j < M; j++) {
+            auto obj = ss->env->getObject(size_t(j));
+            if (is_dynamic[j]) obj->setLabel("dynamic_obstacle");
+            obj->setPosition(fcl::Vector3f(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]));
+            obj->setVelocity(fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
+            obj->setMaxVel(max_vel[j]);
+        }
+        ss->env->stubSetWorkspace(fcl::Vector3f(ws[0], ws[1], ws[2]), ws[3]);
+        ss->env->setBaseRadius(ws[4]);
+        ss->env->setRobotMaxVel(ws[5]);
+        ss->attachDynamicEnvironment(rvs_motion_type(motion_type));
+        std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> motions;
+        for (int t = 0; t < T; t++) {
+            auto a = state_of(*ss, q + size_t(t) * n, n), b = state_of(*ss, q + size_t(t + 1) * n, n);
+            motions.emplace_back(a, b);
+            std::vector<std::shared_ptr<base::State>> path;
+            valid[t] = ss->checkMotion(a, b, size_t(num_checks), delta_time, &path) ? 1 : 0;
+            passed[t] = int32_t(path.size());
+            for (int j = 0; j < M; j++)
+                for (int k = 0; k < 3; k++) pos_after[(size_t(t) * M + j) * 3 + k] = ss->env->getObject(size_t(j))->getPosition()(k);
+        }
+        const std::vector<uint8_t> bv = ss->checkMotionBatch(motions, size_t(num_checks), delta_time);
+        for (int t = 0; t < T; t++) batch_valid[t] = bv[size_t(t)];
+        return 0;
+    } catch (const std::exception &e) {
+        g_error = e.what();
+        return 1;
+    }
+}
+
 }  // extern "C"

@@ -116,3 +116,40 @@ def test_cpp_class_matches_oracle_and_keeps_reference_state_semantics(driver, ob
     assert np.abs(un - du_o).max() <= 1e-4 and (un_b == un).all()
     assert ((un == 0) == (st_o == 1)).all()
     assert (is_real[st_o == 0] == 0).all() and (is_real[st_o == 1] == 1).all()      # accepted: is_real_d_c = false; rejected: untouched
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("law", ["light_directions", "straight"])
+def test_cpp_class_motion_check_moves_the_environment_like_the_reference_loop(driver, ob, tmp_path, law):
+    """attachDynamicEnvironment + checkMotion / checkMotionBatch (row f-2) against the oracle's MotionValidity::check."""
+    from rpmplv2_b200.engine import MOTION_TYPES, env_params
+    rb = robots.xarm6()
+    sc = scenes.dynamic_scene(rb, 5, 41)
+    n, M, T, K, dt = rb.num_dofs, len(sc["max_vel"]), 24, 10, 0.005
+    o = ob.Oracle(rb, robots.default_params())
+    ep = env_params(law, ws_center=scenes.WS_CENTER, ws_radius=1.0, base_radius=0.3, robot_max_vel=1.5)
+    o.env_set(ep, **sc)
+    cand = synthetic.configs(rb, 400, seed=0xC3)
+    d0 = o.distance(cand)[0]
+    q = synthetic.configs(rb, T + 1, seed=0xC4)
+    q[0] = cand[int(np.argmax(d0))]                                                  # start with clearance, then a slow random walk
+    q[1:] = q[:1] + np.cumsum((q[1:] - q[:-1]) * np.float32(0.03), axis=0)
+    ws = np.array(list(scenes.WS_CENTER) + [1.0, 0.3, 1.5], np.float32)
+    valid = np.zeros(T, np.uint8); passed = np.zeros(T, np.int32); pos_after = np.zeros((T, M, 3), np.float32); bvalid = np.zeros(T, np.uint8)
+    limits = np.ascontiguousarray(rb.limits, np.float32)
+    P = lambda a, t: a.ctypes.data_as(t)
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    rc = driver.drv_motion(_write_urdf(tmp_path, rb).encode(), rb.name.encode(), n, P(rb.radius, f32p), ctypes.c_float(rb.gripper_length), rb.ground_included,
+                           P(limits, f32p), P(sc["dim"], f32p), P(sc["pos"], f32p), P(sc["vel"], f32p), P(sc["max_vel"], f32p), P(sc["is_dynamic"], u8p),
+                           P(sc["is_ground"], u8p), P(sc["min_dist_tol"], f32p), M, MOTION_TYPES[law], P(ws, f32p), P(q, f32p), T, K, ctypes.c_float(dt),
+                           P(valid, u8p), P(passed, i32p), P(pos_after, f32p), P(bvalid, u8p))
+    driver.drv_last_error.restype = ctypes.c_char_p
+    assert rc == 0, driver.drv_last_error()
+    for t in range(T):
+        v, f = o.motion_validity(q[t:t + 1], q[t + 1:t + 2], K, dt, commit_edge=0)
+        assert bool(valid[t]) == bool(v[0]), t
+        assert passed[t] == (K if v[0] else f[0] - 1)
+        assert np.array_equal(pos_after[t], o.env_get()[0]), t                          # env::Object positions mirrored back
+    vb, _ = o.motion_validity(q[:-1], q[1:], K, dt, commit_edge=-1)
+    assert np.array_equal(bvalid.astype(bool), vb)
+    assert valid.sum() > 0
