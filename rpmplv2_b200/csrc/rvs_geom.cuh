@@ -311,21 +311,28 @@ __device__ __forceinline__ R capsule_box_distance(const Capsule<R> &cp, const Bo
 // Collision predicate: collisionCapsuleToBox / collisionCapsuleToRectangle / checkCases
 // (CollisionAndDistance.cpp:4-148).  A different decision tree from the distance (Q3-Q7) — kept as such.
 // ---------------------------------------------------------------------------------------------------------------
-template <class R>
-__device__ __forceinline__ R rect_edge_cases(const Capsule<R> &cp, const Box<R> &bx, int c, unsigned s, R pa, R pb, R eq_thr, R max_dist) {
+// The predicate is evaluated in two halves, like the distance (classify_pair / seg_edge):
+//   hit_box_plan()        everything that needs no segment-edge distance: the endpoint accept, the slab reject and, per face chosen by
+//                         A's side, the crossing test and the projection tests.  It returns 1 when the collision is already decided;
+//                         otherwise it has emitted the box edges (6-bit codes, at most 4 per face) whose distance the reference would
+//                         compare with the radius, and the pair collides iff one of them is closer than the radius.
+//   plan_edge_distance()  one such evaluation.
+// Why this is the same verdict in any order: checkCases (:113-148) returns min(d_c1, d_c2) and computes d_c2 only when d_c1 > 0 — but
+// d_c1 <= 0 is already < radius (the radius > 0 block), so "min < radius" == "d_c1 < radius or d_c2 < radius"; the callers combine
+// faces, endpoints and checkCases results with min / || only (:86-107, :19-40).
+template <class R, class Emit>
+__device__ __forceinline__ void hit_edge_cases(const Box<R> &bx, int c, unsigned s, R pa, R pb, Emit &emit) {
     const int a = axis_a(c), b = axis_b(c);
     const unsigned ua = 1u << a, ub = 1u << b;
-    R d1 = max_dist, d2 = max_dist;
-    V3<R> u, v;
-    if (pa < sel3(bx.lo, a)) d1 = seg_edge<R, false>(cp, bx.corner(int(s)), b, sel3(bx.hi, b), eq_thr, max_dist, u, v);
-    else if (pa > sel3(bx.hi, a)) d1 = seg_edge<R, false>(cp, bx.corner(int(s | ua)), b, sel3(bx.hi, b), eq_thr, max_dist, u, v);
-    if (d1 > R(0) && pb < sel3(bx.lo, b)) d2 = seg_edge<R, false>(cp, bx.corner(int(s)), a, sel3(bx.hi, a), eq_thr, max_dist, u, v);
-    else if (d1 > R(0) && pb > sel3(bx.hi, b)) d2 = seg_edge<R, false>(cp, bx.corner(int(s | ub)), a, sel3(bx.hi, a), eq_thr, max_dist, u, v);
-    return d2 < d1 ? d2 : d1;
+    if (pa < sel3(bx.lo, a)) emit(edge_code(s, s | ub));                      // d_c1: the edge at a_min ...
+    else if (pa > sel3(bx.hi, a)) emit(edge_code(s | ua, s | ua | ub));       // ... or at a_max
+    if (pb < sel3(bx.lo, b)) emit(edge_code(s, s | ua));                      // d_c2: the edge at b_min ...
+    else if (pb > sel3(bx.hi, b)) emit(edge_code(s | ub, s | ub | ua));       // ... or at b_max
 }
 
-template <class R>
-__device__ __noinline__ bool capsule_hits_rectangle(const Capsule<R> &cp, const Box<R> &bx, int face, R eq_thr, R max_dist) {
+// collisionCapsuleToRectangle (:46-111) without its segment-edge distances: 1 = true, 0 = not decided here (edges emitted, or false)
+template <class R, class Emit>
+__device__ __forceinline__ int hit_rectangle_plan(const Capsule<R> &cp, const Box<R> &bx, int face, R max_dist, Emit &emit) {
     const R radius = cp.radius;
     const int c = face > 2 ? face - 3 : face, a = axis_a(c), b = axis_b(c);
     const unsigned s = unsigned(face > 2) << c;
@@ -347,46 +354,72 @@ __device__ __noinline__ bool capsule_hits_rectangle(const Capsule<R> &cp, const 
                 (M0 < r0 && M1 > r3 && rsqrt_of((M0 - r0) * (M0 - r0) + (M1 - r3) * (M1 - r3)) < radius) ||
                 (M0 > r1 && M1 < r2 && rsqrt_of((M0 - r1) * (M0 - r1) + (M1 - r2) * (M1 - r2)) < radius) ||
                 (M0 > r1 && M1 > r3 && rsqrt_of((M0 - r1) * (M0 - r1) + (M1 - r3) * (M1 - r3)) < radius))
-                return true;
+                return 1;
         }
     } else if (nmin > radius)
-        return false;
+        return 0;
 
     if (radius > R(0)) {
         const bool Ain = Aa > r0 && Aa < r2 && Ab > r1 && Ab < r3;
         const bool Bin = Ba > r0 && Ba < r2 && Bb > r1 && Bb < r3;
         if (Ain) {
-            if (Bin) return nmin < radius;
-            const R dd = rect_edge_cases(cp, bx, c, s, Ba, Bb, eq_thr, max_dist);
-            return (nA < dd ? nA : dd) < radius;
+            if (Bin) return nmin < radius ? 1 : 0;
+            if (nA < radius) return 1;
+            hit_edge_cases(bx, c, s, Ba, Bb, emit);
         } else if (Bin) {
-            const R dd = rect_edge_cases(cp, bx, c, s, Aa, Ab, eq_thr, max_dist);
-            return (nB < dd ? nB : dd) < radius;
+            if (nB < radius) return 1;
+            hit_edge_cases(bx, c, s, Aa, Ab, emit);
         } else {
-            if (rect_edge_cases(cp, bx, c, s, Aa, Ab, eq_thr, max_dist) < radius) return true;
-            return rect_edge_cases(cp, bx, c, s, Ba, Bb, eq_thr, max_dist) < radius;
+            hit_edge_cases(bx, c, s, Aa, Ab, emit);
+            hit_edge_cases(bx, c, s, Ba, Bb, emit);
         }
     }
-    return false;
+    return 0;
 }
 
-template <class R>
-__device__ __forceinline__ bool capsule_hits_box(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist) {
+// collisionCapsuleToBox (:4-42) without the segment-edge distances: 1 = collision, 0 = the emitted edges (possibly none) decide
+template <class R, class Emit>
+__device__ __forceinline__ int hit_box_plan(const Capsule<R> &cp, const Box<R> &bx, R max_dist, Emit &emit) {
     const V3<R> &A = cp.A, &B = cp.B;
     const R rn = cp.radius_in, radius = cp.radius;
     if ((A.x > bx.lo.x - rn && A.y > bx.lo.y - rn && A.z > bx.lo.z - rn && A.x < bx.hi.x + rn && A.y < bx.hi.y + rn && A.z < bx.hi.z + rn) ||
         (B.x > bx.lo.x - rn && B.y > bx.lo.y - rn && B.z > bx.lo.z - rn && B.x < bx.hi.x + rn && B.y < bx.hi.y + rn && B.z < bx.hi.z + rn))
-        return true;
+        return 1;
     if ((A.x < bx.lo.x - radius && B.x < bx.lo.x - radius) || (A.x > bx.hi.x + radius && B.x > bx.hi.x + radius) ||
         (A.y < bx.lo.y - radius && B.y < bx.lo.y - radius) || (A.y > bx.hi.y + radius && B.y > bx.hi.y + radius) ||
         (A.z < bx.lo.z - radius && B.z < bx.lo.z - radius) || (A.z > bx.hi.z + radius && B.z > bx.hi.z + radius))
-        return false;
+        return 0;
     // faces chosen by A's side only, x then y then z (Q4)
 #pragma unroll 1
     for (int k = 0; k < 3; k++) {
         const R ak = sel3(A, k);
         const int face = ak < sel3(bx.lo, k) ? k : (ak > sel3(bx.hi, k) ? k + 3 : -1);
-        if (face >= 0 && capsule_hits_rectangle(cp, bx, face, eq_thr, max_dist)) return true;
+        if (face >= 0 && hit_rectangle_plan(cp, bx, face, max_dist, emit)) return 1;
+    }
+    return 0;
+}
+
+// up to 12 edge codes of one pair (4 per face), 6 bits each, in two 64-bit words
+struct HitEdges {
+    unsigned long long lo = 0ull, hi = 0ull;
+    int count = 0;
+    __device__ __forceinline__ void operator()(unsigned code) {
+        if (count < 10) lo |= (unsigned long long)code << (6 * count);
+        else hi |= (unsigned long long)code << (6 * (count - 10));
+        count++;
+    }
+    __device__ __forceinline__ unsigned at(int k) const { return unsigned((k < 10 ? lo >> (6 * k) : hi >> (6 * (k - 10))) & 63ull); }
+};
+
+// the sequential composition (one-thread-per-item kernels, primitives, motion check)
+template <class R>
+__device__ __forceinline__ bool capsule_hits_box(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist) {
+    HitEdges edges;
+    if (hit_box_plan(cp, bx, max_dist, edges)) return true;
+#pragma unroll 1
+    for (int k = 0; k < edges.count; k++) {
+        V3<R> u, v;
+        if (plan_edge_distance<R, false>(cp, bx, edges.at(k), eq_thr, max_dist, u, v) < cp.radius) return true;
     }
     return false;
 }

@@ -13,8 +13,9 @@
 namespace rvs {
 
 template <int G> struct VqCaps {
-    static constexpr int q1 = 32 * G * kWqUnroll + 32;
-    static constexpr int words = 4 + q1;
+    static constexpr int q1 = 32 * G * kWqUnroll + 32;   // pairs: one scan iteration pushes <= 32*G*unroll on top of a leftover < 32
+    static constexpr int q2 = 32 * 12 + 32;               // box edges: one classification round pushes <= 32*12 on top of a leftover < 32
+    static constexpr int words = 4 + q1 + q2;             // control words first: [0] pair tail, [1] edge tail
 };
 
 template <class R, int G>
@@ -43,9 +44,10 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
     unsigned *invalid = reinterpret_cast<unsigned *>(p); p += size_t(kWqBlock) * sizeof(unsigned);
     unsigned *wq = reinterpret_cast<unsigned *>(p) + size_t(warp) * VqCaps<G>::words;
     volatile unsigned *tail = wq;
-    unsigned *q1 = wq + 4;
+    unsigned *q1 = wq + 4, *q2 = q1 + VqCaps<G>::q1;
     const float4 *obs4 = reinterpret_cast<const float4 *>(a.obstacles_scan);   // nearest to the base first (the verdict is order free)
     const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
+    int seg_base = 0;
 
     const int64_t item = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
     int64_t edge = 0;
@@ -97,49 +99,82 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
     const int ground_included = rb->ground_included;
     __syncthreads();
 
-    // evaluate queued pairs with the exact reference predicate, one per lane
+    // The exact reference predicate in two compacted phases (lane = queued item of ANY configuration of the warp):
+    //   pairs  hit_box_plan(): endpoint accept, slab reject, crossing / projection tests; decided collisions are recorded, the box
+    //          edges the reference would measure go to the edge queue
+    //   edges  one segment-edge distance per lane: closer than the radius = collision
+    // (the one-piece predicate ran its segment-edge evaluations with ~2 of 32 lanes active and, inlined a dozen times, made the
+    // kernel 126 KB of SASS: 71 % of the stall samples were instruction-cache misses on dense scenes, profiles/README.md)
+    auto load_item = [&](unsigned e, int &tt, int &link, Capsule<R> &cp, Box<R> &bx) {
+        tt = wbase + int(e & 31u);
+        link = int((e >> 5) & 31u);
+        const int j = seg_base + int((e >> 10) & 0xFFFFu);
+        const R *sk = skel + (3 * link) * kWqStride + tt;
+        cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, radius[link], radius_in[link]);
+        const float4 w0 = __ldg(obs4 + 2 * j), w1 = __ldg(obs4 + 2 * j + 1);
+        bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
+    };
     auto drain = [&](bool flush) {
         for (;;) {
             __syncwarp();
-            const unsigned have = tail[0];
-            if (!(have >= 32u || (flush && have > 0u))) break;
-            const unsigned cnt = have < 32u ? have : 32u, base = have - cnt;
-            const unsigned e = unsigned(lane) < cnt ? q1[base + lane] : kNoEntry;
-            __syncwarp();
-            if (lane == 0) tail[0] = base;
-            if (e != kNoEntry) {
-                const int tt = wbase + int(e & 31u), link = int((e >> 5) & 31u), j = int(e >> 10);
-                if (!invalid[tt]) {
-                    const R *sk = skel + (3 * link) * kWqStride + tt;
-                    Capsule<R> cp;
-                    cp.set({sk[0], sk[kWqStride], sk[2 * kWqStride]}, {sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride]}, radius[link], radius_in[link]);
-                    const float4 w0 = __ldg(obs4 + 2 * j), w1 = __ldg(obs4 + 2 * j + 1);
-                    const Box<R> bx = {{R(w0.x), R(w0.y), R(w0.z)}, {R(w0.w), R(w1.x), R(w1.y)}};
-                    // Cheap exact-safe reject in front of the reference predicate (up to ~5000 instructions when all three face tests
-                    // run): every `true` of collisionCapsuleToBox implies an axis point within sqrt(2) * radius of the box (endpoint in the
-                    // box inflated by r/sqrt(3); crossing point inside the rectangle oversized by r; an edge or face distance < r), hence
-                    // within sqrt(2) r + (half diagonal) of the box centre.  A diagonal link's bounding box passes the slab test for many
-                    // small boxes that are nowhere near the segment itself.
-                    const R cx = (bx.lo.x + bx.hi.x) * R(0.5), cy = (bx.lo.y + bx.hi.y) * R(0.5), cz = (bx.lo.z + bx.hi.z) * R(0.5);
-                    const R hx = (bx.hi.x - bx.lo.x) * R(0.5), hy = (bx.hi.y - bx.lo.y) * R(0.5), hz = (bx.hi.z - bx.lo.z) * R(0.5);
-                    const R ux = cp.B.x - cp.A.x, uy = cp.B.y - cp.A.y, uz = cp.B.z - cp.A.z;
-                    const R vx = cx - cp.A.x, vy = cy - cp.A.y, vz = cz - cp.A.z;
-                    const R uu = ux * ux + uy * uy + uz * uz, uv = ux * vx + uy * vy + uz * vz, vv = vx * vx + vy * vy + vz * vz;
-                    R d2;                                                       // squared distance of the box centre from the segment
-                    if (!(uv > R(0))) d2 = vv;
-                    else if (uv >= uu) { const R wx = cx - cp.B.x, wy = cy - cp.B.y, wz = cz - cp.B.z; d2 = wx * wx + wy * wy + wz * wz; }
-                    else d2 = vv - uv * uv / uu;
-                    const R reach = sqrt(hx * hx + hy * hy + hz * hz) + fmax(R(1.41422) * radius[link], eq_thr) * R(1.001) + R(1e-4);      // (a segment-edge distance below EQUALITY_THRESHOLD snaps to 0 = hit)
-                    const bool far = d2 - R(4e-6) * (vv + R(1)) > reach * reach * R(1.002);     // (NaN anywhere: not far, the predicate decides)
-                    if (!far && capsule_hits_box<R>(cp, bx, eq_thr, max_dist)) invalid[tt] = 1u;
+            const unsigned t1 = tail[0], t2 = tail[1];
+            if (t2 >= 32u || (flush && t2 > 0u && t1 == 0u)) {
+                const unsigned cnt = t2 < 32u ? t2 : 32u, base = t2 - cnt;
+                const unsigned e = unsigned(lane) < cnt ? q2[base + lane] : kNoEntry;
+                __syncwarp();
+                if (lane == 0) tail[1] = base;
+                if (e != kNoEntry) {
+                    int tt, link; Capsule<R> cp; Box<R> bx;
+                    load_item(e, tt, link, cp, bx);
+                    if (!invalid[tt]) {
+                        V3<R> u, v;
+                        if (plan_edge_distance<R, false>(cp, bx, e >> 26, eq_thr, max_dist, u, v) < cp.radius) invalid[tt] = 1u;
+                    }
                 }
-            }
+            } else if (t1 >= 32u || (flush && t1 > 0u)) {
+                const unsigned cnt = t1 < 32u ? t1 : 32u, base = t1 - cnt;
+                const unsigned e = unsigned(lane) < cnt ? q1[base + lane] : kNoEntry;
+                __syncwarp();
+                if (lane == 0) tail[0] = base;
+                if (e != kNoEntry) {
+                    int tt, link; Capsule<R> cp; Box<R> bx;
+                    load_item(e, tt, link, cp, bx);
+                    if (!invalid[tt]) {
+                        // Cheap exact-safe reject in front of the predicate: every `true` of collisionCapsuleToBox implies an axis point
+                        // within sqrt(2) * radius of the box (endpoint in the box inflated by r/sqrt(3); crossing point inside the rectangle
+                        // oversized by r; an edge or face distance < r), hence within sqrt(2) r + (half diagonal) of the box centre.  A
+                        // diagonal link's bounding box passes the slab test for many small boxes that are nowhere near the segment.
+                        const R cx = (bx.lo.x + bx.hi.x) * R(0.5), cy = (bx.lo.y + bx.hi.y) * R(0.5), cz = (bx.lo.z + bx.hi.z) * R(0.5);
+                        const R hx = (bx.hi.x - bx.lo.x) * R(0.5), hy = (bx.hi.y - bx.lo.y) * R(0.5), hz = (bx.hi.z - bx.lo.z) * R(0.5);
+                        const R ux = cp.B.x - cp.A.x, uy = cp.B.y - cp.A.y, uz = cp.B.z - cp.A.z;
+                        const R vx = cx - cp.A.x, vy = cy - cp.A.y, vz = cz - cp.A.z;
+                        const R uu = ux * ux + uy * uy + uz * uz, uv = ux * vx + uy * vy + uz * vz, vv = vx * vx + vy * vy + vz * vz;
+                        R d2;                                                       // squared distance of the box centre from the segment
+                        if (!(uv > R(0))) d2 = vv;
+                        else if (uv >= uu) { const R wx = cx - cp.B.x, wy = cy - cp.B.y, wz = cz - cp.B.z; d2 = wx * wx + wy * wy + wz * wz; }
+                        else d2 = vv - uv * uv / uu;
+                        const R reach = sqrt(hx * hx + hy * hy + hz * hz) + fmax(R(1.41422) * radius[link], eq_thr) * R(1.001) + R(1e-4);      // (a segment-edge distance below EQUALITY_THRESHOLD snaps to 0 = hit)
+                        const bool far = d2 - R(4e-6) * (vv + R(1)) > reach * reach * R(1.002);     // (NaN anywhere: not far, the predicate decides)
+                        if (!far) {
+                            HitEdges edges;
+                            if (hit_box_plan(cp, bx, max_dist, edges)) invalid[tt] = 1u;
+                            else if (edges.count) {
+                                const unsigned pos = atomicAdd(const_cast<unsigned *>(&tail[1]), unsigned(edges.count));
+#pragma unroll 1
+                                for (int k = 0; k < edges.count; k++) q2[pos + k] = (e & 0x3FFFFFFu) | (edges.at(k) << 26);
+                            }
+                        }
+                    }
+                }
+            } else
+                break;
         }
     };
 
-    constexpr int kSeg = 1 << 22;                                          // queue entries carry a 22-bit obstacle index
+    constexpr int kSeg = kWqSegment;                                       // queue entries carry a 16-bit obstacle index: lane | link << 5 | obstacle << 10 | edge code << 26
     for (int base = 0; base < a.M; base += kSeg) {
         const int count = min(kSeg, a.M - base);
+        seg_base = base;                                                   // (every interval ends with a flush, so no entry outlives its segment)
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
             unsigned alive = (1u << min(G, L - g0)) - 1u;                 // links some configuration of the warp still has to test (warp-uniform)
@@ -224,7 +259,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                         do {
                             const int b = __ffs(int(mask)) - 1;
                             mask &= mask - 1u;
-                            const int sl = b >= G ? b - G : b, jj = base + (b >= G ? j1 : j);
+                            const int sl = b >= G ? b - G : b, jj = b >= G ? j1 : j;
                             q1[pos++] = unsigned(lane) | (((slotmap >> (5 * sl)) & 31u) << 5) | (unsigned(jj) << 10);
                         } while (mask);
                     }
