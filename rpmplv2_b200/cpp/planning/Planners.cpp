@@ -454,7 +454,7 @@ namespace rvsplan
 			tasks.back().handle().resume();
 		}
 		int nthreads = host_threads > 0 ? host_threads : int(std::thread::hardware_concurrency());
-		ResumeCrew crew(std::max(1, std::min({nthreads, 32, P / 16})));
+		ResumeCrew crew(P < 256 ? 1 : std::max(1, std::min({nthreads, 32, P / 16})));      // small pools stay serial: a helper descheduled with a claimed chunk costs more than it saves
 		std::vector<float> q1, q2, d, q_layers;
 		std::vector<int32_t> sl, n_layers;
 		std::vector<uint8_t> flags;
