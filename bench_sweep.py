@@ -179,6 +179,40 @@ def main():
                  valid=round(float(v.mean()), 4), identical_to_oracle=bool(np.array_equal(f, fo)))
         em.close()
 
+    # ---- S2 (e) one DRGBT iteration's geometry (row f-1): computeDistance(q_current, true) + H generalized-bur spines + H real
+    # distances (DRGBT.cpp:101, 272-320, 475-495) + the motion check with moving obstacles (MotionValidity.cpp:30-51);
+    # spatial_22dof, ground + 5 moving cubes (BASELINE config 4); H = 10 + 2n - 2 = 52 and 10n = 220 (critical clearance)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_drgbt import OracleSpace, _horizon
+    from rpmplv2_b200 import drgbt
+    rbd = robots.spatial(22)
+    scd = scenes.dynamic_scene(rbd, 5, 21, r_lo=0.45 * 2.2, r_hi=0.95 * 2.2, size=0.3 * 2.2)
+    scd["min_dist_tol"] = np.full(6, 1000.0, np.float32)
+    epd = engine.env_params("light_directions", ws_center=scenes.WS_CENTER, ws_radius=2.2, base_radius=0.3, robot_max_vel=1.5)
+    ed = engine.Engine(rbd, robots.default_params(), device=0)
+    od = ob.Oracle(rbd)
+    ed.env_set(epd, **scd)
+    od.env_set(epd, **scd)
+    candd = synthetic.configs(rbd, 300, seed=0xD6)
+    q_cur = candd[int(np.argmax(od.distance(candd)[0]))]
+    for H in (52, 220):
+        hor = _horizon(rbd, q_cur, H, 11)
+        tg, tc = [], []
+        for _ in range(args.reps + 10):
+            t0 = time.perf_counter()
+            g = drgbt.generate_gbur(ed, q_cur, hor)
+            v, f = ed.motion_validity(q_cur[None], g["q_reached"][:1], 10, 0.005)
+            tg.append((time.perf_counter() - t0) * 1e3)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            go = drgbt.generate_gbur(OracleSpace(od), q_cur, hor)
+            vo, fo = od.motion_validity(q_cur[None], go["q_reached"][:1], 10, 0.005)
+            tc.append((time.perf_counter() - t0) * 1e3)
+        emit(set="S2e", robot="spatial_22dof", M=6, H=H, layers=5, call="DRGBT iteration geometry (4 engine calls)", host_call_ms=float(np.median(tg[5:])),
+             cpu_oracle_1thread_ms=float(np.median(tc)), spines_per_s=H / np.median(tg[5:]) * 1e3,
+             same_statuses=bool(np.array_equal(g["spine_status"], go["spine_status"])), max_dq=float(np.abs(g["q_reached"] - go["q_reached"]).max()))
+    ed.close()
+
     # ---- S2 (c) single-query latency, planar_2dof scenario_test ----------------------------------------------------------
     rb2, pmn, pmx, pg, ptol = scenes.planar2_scenario_test()
     e3 = engine.Engine(rb2, robots.default_params(), device=0)
@@ -207,6 +241,8 @@ def main():
                 note = f"host call {r['host_call_us_median']:.1f} us (p95 {r['host_call_us_p95']:.1f})"
             if "hbm_write_gbs" in r:
                 note = f"{r['hbm_write_gbs']:.0f} GB/s written"
+            if r.get("set") == "S2e":
+                note += f"; CPU oracle 1 thread {r['cpu_oracle_1thread_ms']:.3f} ms; same spine statuses {r['same_statuses']}"
             if "per_point_path_ms" in r:
                 note += f"; K x (upload + isValid) {r['per_point_path_ms']:.3f} ms; CPU oracle 1 thread {r['cpu_oracle_1thread_ms']:.3f} ms; identical {r['identical_to_oracle']}"
             if "reached" in r:
