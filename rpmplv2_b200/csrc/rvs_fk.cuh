@@ -16,8 +16,10 @@ __device__ __forceinline__ void sincos_of(float a, float *s, float *c) { sincosf
 // sk[(3k + c) * stride] (stride 1: a private array; stride = block size: a shared-memory column per thread).
 // Reference semantics: KDL tree FK (T_k = T_{k-1} Trans(xyz_k) RPY(rpy_k) Rot(axis_k, q_k)) and
 // computeSkeleton (xArm6.cpp:209-235, Planar2DOF.cpp:117-130).
-template <class F, class R>
-__device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, const float *__restrict__ q, R *sk_base, const int stride = 1) {
+// `joint_sincos(k, &s, &c)` supplies sin / cos of joint k's angle: computed on the spot (fk_skeleton) or fetched from the lane that
+// computed it (fk_skeleton_warp: the 2n transcendental evaluations are the long part of a 22-joint chain and are independent).
+template <class F, class R, class SinCos>
+__device__ __forceinline__ void fk_skeleton_with(const RobotDev *__restrict__ rb, SinCos joint_sincos, R *sk_base, const int stride = 1) {
     struct Strided {
         R *p; int s;
         __device__ __forceinline__ R &operator[](int k) const { return p[k * s]; }
@@ -43,7 +45,7 @@ __device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, con
         }
         if (k < n) {
             F s, c;
-            sincos_of(F(q[k]), &s, &c);
+            joint_sincos(k, &s, &c);
             const int code = rb->axis_code[k];
             if (code == AXIS_Z) {            // columns 0,1 mix; the products dropped are exact zeros
                 const F a00 = r00 * c + r01 * s, a01 = r01 * c - r00 * s;
@@ -87,5 +89,25 @@ __device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, con
         }
     }
 }
+
+template <class F, class R>
+__device__ __forceinline__ void fk_skeleton(const RobotDev *__restrict__ rb, const float *__restrict__ q, R *sk_base, const int stride = 1) {
+    fk_skeleton_with<F, R>(rb, [q](int k, F *s, F *c) { sincos_of(F(q[k]), s, c); }, sk_base, stride);
+}
+
+#ifdef __CUDACC__
+// Warp-cooperative variant for kernels in which a whole warp works on ONE configuration (every lane holds the same q): lane k
+// evaluates sincos(q_k), the chain products then run (redundantly, in registers) on every lane with the values shuffled in.
+// Same operations in the same order as fk_skeleton -> bit-identical skeleton.  All 32 lanes must call it.
+__device__ __forceinline__ double shfl_f(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float shfl_f(float v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class F, class R>
+__device__ __forceinline__ void fk_skeleton_warp(const RobotDev *__restrict__ rb, const float *__restrict__ q, R *sk_base, const int stride = 1) {
+    const int lane = threadIdx.x & 31, n = rb->n;
+    F s_mine = 0, c_mine = 1;
+    if (lane < n) sincos_of(F(q[lane]), &s_mine, &c_mine);
+    fk_skeleton_with<F, R>(rb, [=](int k, F *s, F *c) { *s = shfl_f(s_mine, k); *c = shfl_f(c_mine, k); }, sk_base, stride);
+}
+#endif
 
 }  // namespace rvs

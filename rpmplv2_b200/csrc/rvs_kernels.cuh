@@ -303,36 +303,42 @@ __global__ void __launch_bounds__(kBlock) skeleton_kernel(const KArgs a) {
 }
 
 // computeEnclosingRadii: xArm6.cpp:237-275, Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30. out: n x (n+1) row-major.
+// row i of AbstractRobot::computeEnclosingRadii (xArm6.cpp:237-275, Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30): out[j], j = 0..n
 template <class R>
-__device__ __forceinline__ void enclosing_radii_of(const RobotDev *__restrict__ rb, const R *sk, R *out) {
-    const int n = rb->n, W = n + 1;
-    for (int k = 0; k < n * W; k++) out[k] = R(0);
+__device__ __forceinline__ void enclosing_radii_row(const RobotDev *__restrict__ rb, const R *sk, int i, R *out) {
+    const int n = rb->n;
+    for (int j = 0; j <= n; j++) out[j] = R(0);
     auto P = [&](int k) { return V3<R>{sk[3 * k], sk[3 * k + 1], sk[3 * k + 2]}; };
     auto norm_xy = [&](int k) { return rsqrt_of(sk[3 * k] * sk[3 * k] + sk[3 * k + 1] * sk[3 * k + 1]); };
     auto dist = [&](const V3<R> &u, const V3<R> &v) { return rsqrt_of(sqD(u.x - v.x, u.y - v.y, u.z - v.z)); };
     if (rb->kind == RVS_ROBOT_XARM6) {
-        for (int i = 0; i < n - 1; i++)
-            for (int j = i + 1; j <= n; j++) {
-                const R rn = R(rb->radius_new[j - 1]);
-                R len;
-                if (i == 0) { if (j < 2) continue; len = norm_xy(j); }
-                else if (i == 3) {
-                    if (j < 5) continue;
-                    const V3<R> AB = sub(P(4), P(3)), v = sub(P(j), P(3));
-                    const R t = ((v.x * AB.x + v.y * AB.y) + v.z * AB.z) / dotF(AB, AB);
-                    len = dist(P(j), lerp_from(P(3), t, AB));
-                } else len = dist(P(j), P(i));
-                const R cand = len + rn, prev = out[i * W + j - 1];
-                out[i * W + j] = prev < cand ? cand : prev;
-            }
+        if (i >= n - 1) return;
+        for (int j = i + 1; j <= n; j++) {
+            const R rn = R(rb->radius_new[j - 1]);
+            R len;
+            if (i == 0) { if (j < 2) continue; len = norm_xy(j); }
+            else if (i == 3) {
+                if (j < 5) continue;
+                const V3<R> AB = sub(P(4), P(3)), v = sub(P(j), P(3));
+                const R t = ((v.x * AB.x + v.y * AB.y) + v.z * AB.z) / dotF(AB, AB);
+                len = dist(P(j), lerp_from(P(3), t, AB));
+            } else len = dist(P(j), P(i));
+            const R cand = len + rn, prev = out[j - 1];
+            out[j] = prev < cand ? cand : prev;
+        }
     } else {
-        for (int i = 0; i < n; i++)
-            for (int j = i + 1; j <= n; j++) {
-                const R len = (rb->kind == RVS_ROBOT_SPATIAL && i == 0) ? norm_xy(j) : dist(P(j), P(i));
-                const R cand = len + R(rb->radius[j - 1]), prev = out[i * W + j - 1];
-                out[i * W + j] = prev < cand ? cand : prev;
-            }
+        for (int j = i + 1; j <= n; j++) {
+            const R len = (rb->kind == RVS_ROBOT_SPATIAL && i == 0) ? norm_xy(j) : dist(P(j), P(i));
+            const R cand = len + R(rb->radius[j - 1]), prev = out[j - 1];
+            out[j] = prev < cand ? cand : prev;
+        }
     }
+}
+
+template <class R>
+__device__ __forceinline__ void enclosing_radii_of(const RobotDev *__restrict__ rb, const R *sk, R *out) {
+    const int n = rb->n, W = n + 1;
+    for (int i = 0; i < n; i++) enclosing_radii_row<R>(rb, sk, i, out + i * W);
 }
 
 template <class F, class R>

@@ -131,74 +131,159 @@ __device__ __forceinline__ float underestimation_warp(const RobotDev *__restrict
     return rejected ? 0.f : d_c;
 }
 
-// One warp per spine. gen2 = 0: extendGenSpine (stop when d_c < D_CRIT or status != Advanced, RGBTConnect.cpp:73-92);
-// gen2 = 1: extendGenSpine2 (stop when d_c < D_CRIT or status == Reached, :96-118). Every layer's state is written to q_layers.
+// One warp per spine, LANE i OWNS JOINT / LINK i (n <= 32): q_i, the profile entry of link i, its rho and its bubble ratio live in
+// that lane's registers; the skeletons, the enclosing-radii matrix (row i written by lane i) and |q_e - q| sit in shared memory.
+// A 22-DOF layer is ~23 000 dependent instructions when one thread walks it (profiles/README.md: a lone warp issues one
+// instruction every ~6 cycles, so that is 70 us per layer); spread over the lanes it is a few thousand.  Same arithmetic per
+// element, in the same order, as spine_kernel / the oracle; the minima over links are order-free (NaN ratios are skipped as
+// `std::min(step, v)` skips them).
+// gen2 = 0: extendGenSpine (stop when d_c < D_CRIT or status != Advanced, RGBTConnect.cpp:73-92); gen2 = 1: extendGenSpine2 (stop
+// when d_c < D_CRIT or status == Reached, :96-118). Every layer's state is written to q_layers.
+constexpr int kSpineWarps = 4;
+__host__ __device__ inline size_t store_spine_smem_bytes(int n) {
+    return size_t(kSpineWarps) * (size_t(2 * 3 * (n + 1)) + size_t(n) * (n + 1) + size_t(n)) * sizeof(float);
+}
+
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, v, off); if (o < v) v = o; }
+    return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { const float o = __shfl_xor_sync(0xffffffffu, v, off); if (v < o) v = o; }
+    return v;
+}
+
+// distance-to-planes of link `lane` (RealVectorSpace.cpp:402-446): lanes over links when there are at least as many links as
+// obstacles, otherwise lanes over obstacles link by link.  Returns this lane's profile entry; d_c / rejected are warp-uniform.
+__device__ __forceinline__ float underestimation_lanes(const RobotDev *__restrict__ rb, int L, int M, const float *sk, const float *__restrict__ planes,
+                                                       float max_dist, float &d_c, bool &rejected, int lane) {
+    auto plane_distance = [&](int i, int j, bool &skip) {
+        const float2 *src = reinterpret_cast<const float2 *>(planes + (size_t(j) * L + i) * 6);
+        const float2 w0 = src[0], w1 = src[1], w2 = src[2];
+        const V3<float> Rp = {w0.x, w0.y, w1.x}, Op = {w1.y, w2.x, w2.y};
+        skip = rsqrt_of(dotF(Op, Op)) == max_dist;
+        V3<float> nrm = sub(Rp, Op);
+        const float z = dotF(nrm, nrm);
+        if (z > 0.f) { const float len = rsqrt_of(z); nrm = {nrm.x / len, nrm.y / len, nrm.z / len}; }
+        const V3<float> A = {sk[3 * i], sk[3 * i + 1], sk[3 * i + 2]}, B = {sk[3 * i + 3], sk[3 * i + 4], sk[3 * i + 5]};
+        const V3<float> ao = sub(A, Op), bo = sub(B, Op);
+        const float da = (ao.x * nrm.x + ao.y * nrm.y) + ao.z * nrm.z;
+        const float db = (bo.x * nrm.x + bo.y * nrm.y) + bo.z * nrm.z;
+        return (db < da ? db : da) - rb->radius[i];
+    };
+    float mine = max_dist;
+    bool rej = false;
+    if (L >= M) {
+        if (lane < L) {
+#pragma unroll 1
+            for (int j = 0; j < M; j++) {
+                bool skip;
+                const float d = plane_distance(lane, j, skip);
+                if (skip) continue;
+                if (d < 0.f) rej = true;
+                if (d < mine) mine = d;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < L; i++) {
+            float best = max_dist;
+#pragma unroll 1
+            for (int j = lane; j < M; j += 32) {
+                bool skip;
+                const float d = plane_distance(i, j, skip);
+                if (skip) continue;
+                if (d < 0.f) rej = true;
+                if (d < best) best = d;
+            }
+            best = warp_min_f(best);
+            if (lane == i) mine = best;
+        }
+    }
+    rejected = __any_sync(0xffffffffu, rej);
+    d_c = rejected ? 0.f : warp_min_f(lane < L ? mine : max_dist);
+    return mine;
+}
+
 template <class F>
-__global__ void __launch_bounds__(128) store_spine_kernel(const StoreArgs a) {
+__global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const StoreArgs a) {
+    extern __shared__ __align__(16) float spine_smem[];
     const RobotDev *__restrict__ rb = a.robot;
     const int n = a.n, L = n, W = n + 1, M = a.M;
-    const int s = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (s >= a.S) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = blockIdx.x * kSpineWarps + warp;
+    if (s >= a.S) return;                                              // (whole warps leave together; no block-level barrier below)
+    float *sk = spine_smem + size_t(warp) * (2 * 3 * W + n * W + n), *sk_new = sk + 3 * W, *Rm = sk_new + 3 * W, *delta = Rm + n * W;
     const float *slot = a.store + size_t(a.root_slot[s]) * store_slot_floats(n, M);
     const float *root_planes = slot + store_header_floats(n);
-    const float *q_e = a.q_targets + size_t(s) * n;
     float *q_out = a.q_layers + size_t(s) * a.num_layers * n;
-    float q_cur[kMaxDofs], q_new[kMaxDofs], prof_cur[kMaxDofs], prof_new[kMaxDofs], delta[kMaxDofs], rho_profile[kMaxDofs];
-    float sk[3 * (kMaxDofs + 1)], sk_new[3 * (kMaxDofs + 1)];
-    float Rm[kMaxDofs * (kMaxDofs + 1)];
-    for (int i = 0; i < n; i++) { q_cur[i] = slot[i]; q_new[i] = slot[i]; prof_cur[i] = slot[n + 1 + i]; }
+    const bool own = lane < n;
+    const float q_e = own ? a.q_targets[size_t(s) * n + lane] : 0.f;
+    float q_cur = own ? slot[lane] : 0.f, q_new = q_cur, prof_cur = own ? slot[n + 1 + lane] : 0.f;
     const float root_d_c = slot[n];
     float dc_cur = root_d_c, d_out = root_d_c;
     int status = 2, layers = 0;                                        // Trapped when the root itself has no clearance (RBTConnect.cpp:91-92)
+    const float inf = __int_as_float(0x7f800000);
+    // FK of the state whose joint i sits in lane i's register
+    auto fk_of = [&](float q_i, float *out) {
+        F s_mine = 0, c_mine = 1;
+        if (own) sincos_of(F(q_i), &s_mine, &c_mine);
+        fk_skeleton_with<F, float>(rb, [=](int k, F *sn, F *cs) { *sn = shfl_f(s_mine, k); *cs = shfl_f(c_mine, k); }, out);
+        __syncwarp();
+    };
     if (root_d_c > 0.f) {
         for (int layer = 0; layer < a.num_layers; layer++) {
             status = 1;
-            fk_skeleton<F, float>(rb, q_cur, sk);
-            float rho = 0.f;
-            for (int i = 0; i < L; i++) rho_profile[i] = 0.f;
-            float q_temp[kMaxDofs];
-            for (int i = 0; i < n; i++) q_temp[i] = q_cur[i];
+            fk_of(q_cur, sk);
+            float rho = 0.f, rho_profile = 0.f, q_temp = q_cur;
             for (int counter = 1;; counter++) {
-                if (counter == 1) enclosing_radii_of<float>(rb, sk, Rm);
-                else { fk_skeleton<F, float>(rb, q_temp, sk_new); enclosing_radii_of<float>(rb, sk_new, Rm); }
-                for (int i = 0; i < n; i++) delta[i] = fabsf(q_e[i] - q_temp[i]);
+                const float *sk_use = sk;
+                if (counter > 1) { fk_of(q_temp, sk_new); sk_use = sk_new; }
+                if (own) { enclosing_radii_row<float>(rb, sk_use, lane, Rm + lane * W); delta[lane] = fabsf(q_e - q_temp); }
+                __syncwarp();
                 float step;
                 if (a.use_expanded_bubble) {
-                    step = __int_as_float(0x7f800000);
-                    for (int i = 0; i < n; i++) {
-                        const float v = (prof_cur[i] - rho_profile[i]) / dot_dyn(Rm + (i + 1), W, delta, n);
-                        if (v < step) step = v;
-                    }
-                } else
-                    step = (dc_cur - rho) / dot_dyn(Rm + n, W, delta, n);
-                if (step > 1.f) {
-                    for (int i = 0; i < n; i++) q_new[i] = q_e[i];
-                    status = 3;
-                } else
-                    for (int i = 0; i < n; i++) q_new[i] = q_temp[i] + step * (q_e[i] - q_temp[i]);
-                if (counter == a.num_iter_spine || status != 1) break;
-                fk_skeleton<F, float>(rb, q_new, sk_new);
-                float rho_k_prev = 0.f;
-                for (int k = 1; k <= L; k++) {
-                    const float rho_k = sqrtf(sqD(sk[3 * k] - sk_new[3 * k], sk[3 * k + 1] - sk_new[3 * k + 1], sk[3 * k + 2] - sk_new[3 * k + 2]));
-                    rho_profile[k - 1] = rho_k_prev < rho_k ? rho_k : rho_k_prev;
-                    rho_k_prev = rho_k;
-                    rho = rho < rho_k ? rho_k : rho;
+                    float v = inf;
+                    if (own) { v = (prof_cur - rho_profile) / dot_dyn(Rm + (lane + 1), W, delta, n); if (!(v == v)) v = inf; }
+                    step = warp_min_f(v);
+                } else {
+                    float dot = 0.f;
+                    if (lane == n - 1) dot = dot_dyn(Rm + n, W, delta, n);
+                    step = (dc_cur - rho) / __shfl_sync(0xffffffffu, dot, n - 1);
                 }
-                for (int i = 0; i < n; i++) q_temp[i] = q_new[i];
+                if (step > 1.f) { q_new = q_e; status = 3; }
+                else q_new = q_temp + step * (q_e - q_temp);
+                if (counter == a.num_iter_spine || status != 1) break;
+                fk_of(q_new, sk_new);
+                // rho_k = |sk_k - sk_new_k| for k = 1..L (lane k-1); rho_profile[k-1] = max(rho_{k-1}, rho_k); rho = max(rho, rho_k)
+                float rho_k = 0.f;
+                if (own) {
+                    const int k = lane + 1;
+                    rho_k = sqrtf(sqD(sk[3 * k] - sk_new[3 * k], sk[3 * k + 1] - sk_new[3 * k + 1], sk[3 * k + 2] - sk_new[3 * k + 2]));
+                }
+                float rho_prev = __shfl_up_sync(0xffffffffu, rho_k, 1);
+                if (lane == 0) rho_prev = 0.f;
+                rho_profile = rho_prev < rho_k ? rho_k : rho_prev;
+                const float m = warp_max_f(rho_k);
+                rho = rho < m ? m : rho;
+                q_temp = q_new;
+                __syncwarp();
             }
-            if (lane == 0) for (int i = 0; i < n; i++) q_out[size_t(layer) * n + i] = q_new[i];
+            if (own) q_out[size_t(layer) * n + lane] = q_new;
             layers = layer + 1;
-            fk_skeleton<F, float>(rb, q_new, sk_new);
+            __syncwarp();
+            fk_of(q_new, sk_new);
             bool rejected;
-            d_out = underestimation_warp(rb, L, M, sk_new, root_planes, a.max_dist, prof_new, rejected, lane);
+            const float prof_new = underestimation_lanes(rb, L, M, sk_new, root_planes, a.max_dist, d_out, rejected, lane);
             if (d_out < a.d_crit || (a.gen2 ? status == 3 : status != 1)) break;
-            for (int i = 0; i < n; i++) { q_cur[i] = q_new[i]; prof_cur[i] = prof_new[i]; }
-            dc_cur = d_out;
+            q_cur = q_new; prof_cur = prof_new; dc_cur = d_out;
+            __syncwarp();
         }
     }
+    if (layers == 0 && own) q_out[lane] = q_new;
     if (lane == 0) {
-        if (layers == 0) { for (int i = 0; i < n; i++) q_out[i] = q_new[i]; }
         a.n_layers[s] = layers;
         a.d_c_last[s] = d_out;
         a.status[s] = uint8_t(status);

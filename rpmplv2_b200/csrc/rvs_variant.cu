@@ -104,7 +104,7 @@ struct Variant {
     }
     static cudaError_t store_spines(const StoreArgs &a, cudaStream_t st) {
         if (a.S <= 0) return cudaSuccess;
-        store_spine_kernel<F><<<grid_for(a.S, 4), 128, 0, st>>>(a);
+        store_spine_kernel<F><<<grid_for(a.S, kSpineWarps), 32 * kSpineWarps, store_spine_smem_bytes(a.n), st>>>(a);      // <= 21 KB at n = 32
         return cudaGetLastError();
     }
     static cudaError_t motion_valid(const EnvArgs &a, cudaStream_t st) {
