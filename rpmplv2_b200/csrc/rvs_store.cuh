@@ -92,6 +92,83 @@ __global__ void __launch_bounds__(32 * kStoreWarps) store_distance_kernel(const 
     }
 }
 
+// computeDistance for a SMALL batch through the host / device-pointer entry points (rvs_distance*): the same decomposition as
+// store_distance_kernel — one CTA per configuration, one warp per link, one lane per obstacle — because what a planner waits for is
+// the latency of a handful of configurations, not throughput: a single xArm6 query against 51 boxes with nearest points takes the
+// one-thread-per-configuration kernel 256 us (306 pairs in sequence), this one ~45 us.  MODE as in distance_kernel; FP32 geometry.
+// Results are bit-identical to distance_kernel (same per-pair routine; minima and the first-collision rule are order free).
+template <class F, int MODE>
+__global__ void __launch_bounds__(32 * kStoreWarps) distance_cta_kernel(const KArgs a) {
+    __shared__ float s_sk[3 * (kMaxDofs + 1)];
+    __shared__ float s_prof[kMaxDofs];
+    __shared__ float s_hit_d[kMaxDofs];
+    __shared__ int s_hit_j[kMaxDofs];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n, M = a.M;
+    const int64_t cfg = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) fk_skeleton_warp<F, float>(rb, a.q + cfg * L, s_sk);      // lane k evaluates sincos(q_k); every lane stores the same skeleton
+    __syncthreads();
+    const int ground_included = rb->ground_included;
+    const float eq_thr = a.eq_thr, max_dist = a.max_dist;
+    float *nearest = MODE == RVS_DIST_FULL ? static_cast<float *>(a.nearest) + size_t(cfg) * size_t(M) * size_t(L) * 6 : nullptr;
+    for (int i = warp; i < L; i += kStoreWarps) {
+        Capsule<float> cp;
+        cp.set({s_sk[3 * i], s_sk[3 * i + 1], s_sk[3 * i + 2]}, {s_sk[3 * i + 3], s_sk[3 * i + 4], s_sk[3 * i + 5]}, rb->radius[i], 0.f);
+        float best = max_dist, hit_d = 0.f;
+        int hit_j = 0x7fffffff;
+        for (int j = lane; j < M; j += 32) {
+            const ObstacleRec o = a.obstacles[j];
+            float d;
+            V3<float> P1 = {0, 0, 0}, P2 = {0, 0, 0};
+            if ((o.flags & 1u) && i < ground_included) {               // ground rule (RealVectorSpace.cpp:336-341)
+                d = max_dist;
+                P2.z = -max_dist;
+            } else
+                d = capsule_box_distance<float, MODE == RVS_DIST_FULL>(cp, load_box<float>(o), eq_thr, max_dist, P1, P2);
+            if (d > o.tol) d = max_dist;                               // min_dist_tol (:367-368)
+            if (d <= 0.f) { if (j < hit_j) { hit_j = j; hit_d = d; } }
+            else if (d < best) best = d;
+            if (MODE == RVS_DIST_FULL) {
+                float2 *dst = reinterpret_cast<float2 *>(nearest + (size_t(j) * L + i) * 6);
+                dst[0] = make_float2(P1.x, P1.y); dst[1] = make_float2(P1.z, P2.x); dst[2] = make_float2(P2.y, P2.z);
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oj = __shfl_xor_sync(0xffffffffu, hit_j, off);
+            const float od = __shfl_xor_sync(0xffffffffu, hit_d, off);
+            if (ob < best) best = ob;
+            if (oj < hit_j) { hit_j = oj; hit_d = od; }
+        }
+        if (lane == 0) { s_prof[i] = best; s_hit_j[i] = hit_j; s_hit_d[i] = hit_d; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int limit = L;                                                  // first colliding link (link-major early exit, :371-378)
+        for (int i = 0; i < L; i++) if (s_hit_j[i] != 0x7fffffff) { limit = i; break; }
+        float d_c = max_dist;
+        for (int i = 0; i < L; i++) if (s_prof[i] < d_c) d_c = s_prof[i];
+        static_cast<float *>(a.d_c)[cfg] = limit < L ? 0.f : d_c;
+        if (MODE >= RVS_DIST_PROFILE) {
+            float *out = static_cast<float *>(a.profile) + cfg * L;
+            for (int i = 0; i < L; i++) out[i] = limit == L ? s_prof[i] : (i < limit ? s_prof[i] : (i == limit ? s_hit_d[i] : 0.f));
+        }
+        if (a.pair_count) {                                             // pair queries the reference's loop would have made
+            unsigned visited = 0;
+            for (int i = 0; i < limit; i++) visited += unsigned(M - (i < ground_included ? a.num_ground : 0));
+            if (limit < L) {
+                unsigned upto = unsigned(s_hit_j[limit] + 1);
+                if (limit < ground_included && a.num_ground > 0)
+                    for (int j = 0; j <= s_hit_j[limit]; j++) upto -= (a.obstacles[j].flags & 1u);
+                visited += upto;
+            }
+            atomicAdd(a.pair_count, (unsigned long long)visited);
+        }
+    }
+}
+
 // distance-to-planes (RealVectorSpace.cpp:402-446) with the L*M planes of one layer split over the lanes of a warp;
 // every lane returns the same d_c / prof / rejected. Values are those of underestimation_of() (same per-plane arithmetic).
 __device__ __forceinline__ float underestimation_warp(const RobotDev *__restrict__ rb, int L, int M, const float *sk, const float *__restrict__ planes,

@@ -13,6 +13,7 @@ namespace rvs {
 namespace {
 
 inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
+constexpr int64_t kSmallBatch = 1024;      // rvs_distance* calls up to this many configurations take the one-CTA-per-configuration kernel
 
 template <class F, class R>
 struct Variant {
@@ -28,8 +29,19 @@ struct Variant {
         distance_wq_kernel<F, R, MODE, G><<<grid_for(a.N, kWqBlock), kWqBlock, smem, st>>>(a);
         return cudaGetLastError();
     }
+    // small batches (what a planner sends): one CTA per configuration (rvs_store.cuh), latency instead of throughput
+    template <int MODE>
+    static cudaError_t distance_cta(const KArgs &a, cudaStream_t st) {
+        distance_cta_kernel<F, MODE><<<unsigned(a.N), 32 * kStoreWarps, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= kSmallBatch) {
+            if (a.mode == RVS_DIST_MIN) return distance_cta<RVS_DIST_MIN>(a, st);
+            if (a.mode == RVS_DIST_PROFILE) return distance_cta<RVS_DIST_PROFILE>(a, st);
+            return distance_cta<RVS_DIST_FULL>(a, st);
+        }
         if (a.cull && a.mode != RVS_DIST_FULL && a.M > 0) {
             // work-queue kernel (rvs_distance_wq.cuh): results identical to the sequential kernel below
             const bool narrow = a.robot_n_hint <= 2;

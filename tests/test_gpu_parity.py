@@ -121,6 +121,49 @@ def test_work_queue_kernel_is_bit_identical_to_sequential_kernel(case, prec):
         assert n1 == n0
 
 
+@pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32])
+@pytest.mark.parametrize("case", ["xarm6_51", "xarm6_1000", "xarm6_dense", "spatial22", "planar2"])
+def test_small_batch_kernel_is_bit_identical_to_sequential_kernel(case, prec):
+    """rvs_distance* calls of up to 1024 configurations take distance_cta_kernel (one CTA per configuration, rvs_store.cuh): every
+    output of every mode — d_c, the profile with its early-exit fill, the nearest points of collision-free configurations and the
+    reference-order pair count — must equal the one-thread-per-configuration kernel (rvs_set_culling(0)) bit for bit."""
+    if case == "xarm6_51":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D2", 0.45)
+    elif case == "xarm6_1000":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(1000, "D2", 0.9)
+    elif case == "xarm6_dense":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(300, "D2", 0.0)
+    elif case == "spatial22":
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 40)
+    else:
+        rb, mn, mx, g, tol = scenes.planar2_scenario_test()
+    eng = make(rb, mn, mx, g, tol, prec, 1e-4)
+    for N in (1, 7, 300, 1024):
+        q = synthetic.configs(rb, N, seed=0x51 + N)
+        for mode in (robots.DIST_MIN, robots.DIST_PROFILE, robots.DIST_FULL):
+            eng.set_culling(True)
+            eng.pair_count(reset=True)
+            d1, p1, n1 = eng.distance(q, mode)
+            c1 = eng.pair_count(reset=True)
+            eng.set_culling(False)
+            d0, p0, n0 = eng.distance(q, mode)
+            c0 = eng.pair_count(reset=True)
+            # REF32 (no FMA contraction): bit for bit. FAST32 lets the compiler contract differently at the two inlining sites.
+            same = (lambda x, y: (x.view(np.uint8) == y.view(np.uint8)).all()) if prec == robots.PREC_REF32 else \
+                   (lambda x, y: np.abs(x - y).max(initial=0.0) <= 1e-5)
+            assert same(d1, d0) and ((d1 == 0) == (d0 == 0)).all()
+            assert c1 == c0 or prec != robots.PREC_REF32
+            if mode >= robots.DIST_PROFILE:
+                assert same(p1, p0)
+            if mode == robots.DIST_FULL:
+                free = d0 > 0
+                if prec == robots.PREC_REF32:
+                    assert same(n1[free], n0[free])
+                elif free.any():     # FAST32: among equidistant candidates a differently contracted product may pick another point
+                    assert (np.abs(n1[free] - n0[free]) <= 1e-5).mean() > 0.98
+    eng.close()
+
+
 @pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32, robots.PREC_F64])
 @pytest.mark.parametrize("case", ["xarm6_1000", "xarm6_2500_dense", "spatial22", "planar2"])
 def test_work_queue_validity_kernels_equal_sequential_kernels(case, prec):
