@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -364,7 +365,8 @@ namespace rvsplan
 		// Persistent helper threads for the resume step: run(count, fn) calls fn(i) for i in [0, count) on the caller and on whichever
 		// helpers are awake (dynamic chunks of 4) and returns when every item is done. The caller never waits for a helper to wake
 		// up: work is claimed through one atomic word (round << 32 | next index), so a helper that arrives late finds nothing to
-		// claim. Helpers spin for ~50 us after a round (rounds are separated by one backend call) before sleeping on the word.
+		// claim. Helpers spin for ~600 us after a round before sleeping on the word: rounds are separated by one backend call (150-400 us), and a
+		// helper that has to be woken through the kernel arrives after the caller has done the round alone.
 		class ResumeCrew
 		{
 		public:
@@ -418,7 +420,7 @@ namespace rvsplan
 					{
 						cur = state.load(std::memory_order_acquire);
 						if ((cur >> 32) != seen) break;
-						if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t_spin > std::chrono::microseconds(50))
+						if ((spin & 255) == 255 && std::chrono::steady_clock::now() - t_spin > std::chrono::microseconds(600))
 						{
 							sleepers.fetch_add(1, std::memory_order_acq_rel);
 							state.wait(cur);
@@ -454,7 +456,8 @@ namespace rvsplan
 			tasks.back().handle().resume();
 		}
 		int nthreads = host_threads > 0 ? host_threads : int(std::thread::hardware_concurrency());
-		ResumeCrew crew(P < 256 ? 1 : std::max(1, std::min({nthreads, 32, P / 16})));      // small pools stay serial: a helper descheduled with a claimed chunk costs more than it saves
+		if (const char *env = std::getenv("RVS_PLAN_THREADS")) { nthreads = std::max(1, std::atoi(env)); host_threads = nthreads; }    // tuning / debugging knob
+		ResumeCrew crew(P < 256 ? 1 : std::max(1, std::min({host_threads > 0 ? nthreads : nthreads - 2, 32, P / 16})));   // default: leave two hardware threads to the caller and the CUDA runtime
 		std::vector<float> q1, q2, d, q_layers;
 		std::vector<int32_t> sl, n_layers;
 		std::vector<uint8_t> flags;
