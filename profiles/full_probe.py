@@ -1,0 +1,25 @@
+#!/usr/bin/env python
+"""profiles/full_probe.py — FULL-mode (nearest points) throughput, device-resident, xArm6 x 51 boxes, N = 131072."""
+import os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from rpmplv2_b200 import engine, robots, synthetic
+rb = robots.xarm6()
+eng = engine.Engine(rb, robots.default_params(), device=0)
+stream = torch.cuda.current_stream(); eng.set_stream(stream.cuda_stream)
+for N, M in ((131072, 51), (16384, 51), (2048, 51), (131072, 6)):
+    mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1", r_min=0.3)
+    eng.set_obstacles(mn, mx, g, tol)
+    d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+    eng.generate_configs_dev(synthetic.SEED_CONFIGS, 0, N, d_q.data_ptr())
+    d_dc = torch.empty(N, dtype=torch.float32, device="cuda"); d_p = torch.empty((N, 6), dtype=torch.float32, device="cuda")
+    d_n = torch.empty((N, M, 6, 6), dtype=torch.float32, device="cuda")
+    for mode, name in ((robots.DIST_FULL, "FULL"), (robots.DIST_PROFILE, "PROFILE")):
+        ms = []
+        for _ in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); eng.distance_dev(d_q.data_ptr(), N, mode, d_dc.data_ptr(), d_p.data_ptr(), d_n.data_ptr()); b.record(stream); torch.cuda.synchronize(); ms.append(a.elapsed_time(b))
+        t = float(np.median(ms[1:]))
+        print("N", N, "M", M, name, "ms %.3f" % t, "configs/s %.3g" % (N / t * 1e3), "GB/s written %.0f" % (N * M * 6 * 24 / t / 1e6) if mode == robots.DIST_FULL else "", flush=True)

@@ -13,7 +13,10 @@ namespace rvs {
 namespace {
 
 inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
-constexpr int64_t kSmallBatch = 1024;      // rvs_distance* calls up to this many configurations take the one-CTA-per-configuration kernel
+#ifndef RVS_SMALL_BATCH
+#define RVS_SMALL_BATCH 4096
+#endif
+constexpr int64_t kSmallBatch = RVS_SMALL_BATCH;      // rvs_distance* calls up to this many configurations (4x for FULL) take the one-CTA-per-configuration kernel
 
 template <class F, class R>
 struct Variant {
@@ -37,7 +40,7 @@ struct Variant {
     }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
-        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= kSmallBatch) {
+        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= (a.M > 256 ? kSmallBatch / 4 : (a.mode == RVS_DIST_FULL ? 4 * kSmallBatch : kSmallBatch))) {     // measured cross-overs (profiles/README.md): ~4k configurations for MIN / PROFILE, ~16k for FULL
             if (a.mode == RVS_DIST_MIN) return distance_cta<RVS_DIST_MIN>(a, st);
             if (a.mode == RVS_DIST_PROFILE) return distance_cta<RVS_DIST_PROFILE>(a, st);
             return distance_cta<RVS_DIST_FULL>(a, st);
