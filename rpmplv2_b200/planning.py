@@ -94,3 +94,36 @@ def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_p
     if rc != 0:
         raise RvsError(rc, (lib.rvsplan_last_error() or b"").decode())
     return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1]), "kernel_launches": int(stats[2])}
+
+
+def _eigen_row(v) -> str:
+    """Eigen's default IOFormat for `vec.transpose()`: 6 significant digits (StreamPrecision), coefficients separated by one space,
+    every coefficient right-aligned to the widest one."""
+    cells = [f"{float(x):.6g}" for x in v]
+    w = max(len(c) for c in cells)
+    return " ".join(c.rjust(w) for c in cells)
+
+
+def write_planner_log(filename: str, result: dict, kind: int, num_dimensions: int, space_type: str = "RealVectorSpaceCUDA type",
+                      append: bool = False) -> None:
+    """The planner `.log` the reference's visualizer reads (RBTConnect::outputPlannerData, /root/reference/src/planners/rbt/RBTConnect.cpp:203-253;
+    /root/reference/visualizer/log_parser.py:33-67 parses the `Path:` block): header, planner info, the path as
+    `q: (...); parent q: (...)` lines (State's operator<<, src/state_spaces/State.cpp:58-65), the 25-dash terminator. The two tree
+    dumps the reference writes between the info and the path are omitted: the batched planners return paths, not trees, and the
+    parser does not read them."""
+    path = result.get("path")
+    with open(filename, "a" if append else "w") as f:
+        f.write(f"Space Type:      {space_type}\n")
+        f.write(f"Dimensionality:  {num_dimensions}\n")
+        f.write(f"Planner type:    {KIND_NAMES[kind]}\n")
+        f.write("Planner info:\n")
+        f.write(f"\t Succesfull:           {'yes' if result['success'] else 'no'}\n")
+        f.write(f"\t Number of iterations: {int(result['iterations'])}\n")
+        f.write(f"\t Number of states:     {int(result['states'])}\n")
+        f.write(f"\t Planning time [s]:    {float(result['planning_time']):.6g}\n")
+        if path is not None and len(path) > 0:
+            f.write("Path:\n")
+            for i, q in enumerate(path):
+                parent = "NONE" if i == 0 else f"({_eigen_row(path[i - 1])})"
+                f.write(f"q: ({_eigen_row(q)}); parent q: {parent}\n")
+        f.write("-" * 25 + "\n")

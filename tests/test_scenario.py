@@ -122,3 +122,48 @@ def test_gpu_engine_built_from_a_scenario_matches_the_oracle(ob):
     v_e, f_e = eng2.motion_validity(q[:-1], q[1:], 10, 0.005)
     v_o, f_o = o.motion_validity(q[:-1], q[1:], 10, 0.005)
     assert np.array_equal(f_e, f_o)
+
+
+def _parse_planner_log(text):
+    """What the reference's visualizer does with a planner log (visualizer/log_parser.py:33-67), re-expressed: take everything after
+    `Path:`, strip the `q: ` / `parent q: ` tags, stop at the dashes, keep the first configuration of every line."""
+    import re
+    block = re.findall(r"Path:\n(.*\n)+", text.replace("NONE", "None"), flags=re.DOTALL)[0]
+    out = []
+    for line in block.split("\n"):
+        line = line.replace("parent q: ", "").replace("q: ", "")
+        if not line:
+            continue
+        if line[0] == "-":
+            break
+        first = line.split("; ")[0].replace("(", "").replace(")", "")
+        out.append([float(x) for x in first.split(" ") if x])
+    return out
+
+
+def test_planner_log_is_readable_by_the_visualizer_parser(tmp_path):
+    from rpmplv2_b200 import planning
+    rng = np.random.default_rng(9)
+    path = rng.uniform(-3.1, 3.1, (7, 6)).astype(np.float32)
+    res = dict(success=1, iterations=123, states=456, planning_time=0.03125, path=path)
+    f = tmp_path / "plannerData.log"
+    planning.write_planner_log(str(f), res, planning.RGBT_CONNECT, 6)
+    text = f.read_text()
+    assert text.startswith("Space Type:      RealVectorSpaceCUDA type\nDimensionality:  6\nPlanner type:    RGBT-Connect\nPlanner info:\n\t Succesfull:           yes\n")
+    assert text.endswith("-" * 25 + "\n") and "parent q: NONE" in text.split("Path:\n")[1].split("\n")[0]
+    got = np.asarray(_parse_planner_log(text), np.float32)
+    assert got.shape == (7, 6) and np.allclose(got, path, rtol=2e-6, atol=1e-6)          # 6 significant digits, like Eigen's stream precision
+    vis = os.path.join(os.path.dirname(REFERENCE_DATA), "visualizer", "log_parser.py")
+    if os.path.isfile(vis):                                                              # the real parser, when the reference tree is here
+        import importlib.util
+        try:
+            spec = importlib.util.spec_from_file_location("ref_log_parser", vis)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+        except ImportError:
+            mod = None                                                                   # (it imports sre_parse, gone in recent Pythons)
+        if mod is not None:
+            ref = np.asarray(mod.LogParser(str(f)).get_path(), np.float32)
+            assert ref.shape == (7, 6) and np.allclose(ref, path, rtol=2e-6, atol=1e-6)
+    planning.write_planner_log(str(f), dict(success=0, iterations=5, states=2, planning_time=1.5, path=None), planning.RRT_CONNECT, 6, append=True)
+    assert f.read_text().count("Planner type:") == 2 and "Succesfull:           no" in f.read_text()
