@@ -58,6 +58,9 @@ constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bi
 #ifndef RVS_WQ_INTERVAL
 #define RVS_WQ_INTERVAL 128
 #endif
+#ifndef RVS_WQ_MINBLOCKS
+#define RVS_WQ_MINBLOCKS 5
+#endif
 #ifndef RVS_WQ_FLUSH
 #define RVS_WQ_FLUSH 2
 #endif
@@ -326,7 +329,7 @@ __device__ __noinline__ R wq_replay_pair(R ax, R ay, R az, R bx_, R by, R bz, R 
 
 // F = FK scalar, R = geometry scalar, MODE = RVS_DIST_MIN | RVS_DIST_PROFILE, G = links scanned per obstacle pass.
 template <class F, class R, int MODE, int G>
-__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) distance_wq_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 2) distance_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char wq_smem[];
     static_assert(G >= 1 && G <= 6, "the slot -> link map packs at most six 5-bit link indices");
     typedef typename WqBits<R>::type Bits;
