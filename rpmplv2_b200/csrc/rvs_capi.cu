@@ -159,7 +159,18 @@ KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
     a.robot_n_hint = h->h_robot.n;
     a.num_ground = h->num_ground;
     a.pair_count = h->d_pair_count;
+    a.slices = 1;
     return a;
+}
+
+// validity work-queue kernel: how many slices of the obstacle table per batch of `items` configurations (1 = every warp walks the
+// whole table).  Worth it when the batch alone cannot fill the GPU and the table is long.
+int valid_slices(const rvs_engine *h, int64_t items) {
+#ifdef RVS_NO_SLICES
+    return 1;
+#endif
+    if (!h->cull || h->M < 256 || items >= 32768) return 1;
+    return std::min(8, h->M / 128);
 }
 
 int enter(rvs_engine *h) {
@@ -289,6 +300,13 @@ int run_simple(rvs_engine *h, const float *q, int64_t N, LaunchFn fn, void *out,
     RVS_TRY(reserve(h, which, out_bytes));
     KArgs a = base_args(h, static_cast<const float *>(h->buf[B_Q].p), N);
     if (verdict_out) a.verdict = static_cast<uint8_t *>(h->buf[which].p); else a.d_c = h->buf[which].p;
+    if (verdict_out && fn == h->lt.is_valid) {
+        a.slices = valid_slices(h, N);
+        if (a.slices > 1) {                                                // the slices only ever clear a verdict
+            if (h->zc) std::memset(h->buf[which].p, 1, out_bytes);
+            else RVS_CUDA(h, cudaMemsetAsync(h->buf[which].p, 1, out_bytes, h->stream));
+        }
+    }
     RVS_TRY(launched(h, fn(a, h->stream), what));
     RVS_TRY(d2h(h, out, which, out_bytes));
     return finish(h);
@@ -559,6 +577,11 @@ int rvs_is_valid_dev(rvs_handle h, const float *d_q, int64_t N, uint8_t *d_valid
     if (!d_q || !d_valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
     KArgs a = base_args(h, d_q, N);
     a.verdict = d_valid;
+    a.slices = valid_slices(h, N);
+    if (a.slices > 1) {                                                    // the slices only ever clear a verdict
+        if (h->zc) std::memset(d_valid, 1, size_t(N));
+        else RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(N), h->stream));
+    }
     return launched(h, h->lt.is_valid(a, h->stream), "is_valid kernel launch");
 }
 int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid) {
@@ -570,6 +593,7 @@ int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, i
     else RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(E), h->stream));
     KArgs a = base_args(h, d_q1, E);
     a.q2 = d_q2; a.verdict = d_valid;
+    a.slices = valid_slices(h, E * int64_t(h->prm.num_interpolation_validity_checks));
     return launched(h, h->lt.edge_valid(a, h->stream), "edge kernel launch");
 }
 int rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,

@@ -57,6 +57,7 @@ struct KArgs {
     int32_t num_checks;
     int32_t mode;            // rvs_distance_mode
     int32_t cull;
+    int32_t slices;          // validity work-queue kernel: the (sorted) obstacle table is split over gridDim.y blocks per item batch
     void *d_c;               // float* or double*
     void *profile;
     void *nearest;

@@ -171,9 +171,15 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
         }
     };
 
+    // Mid-size batches (a planner's edge batch against a thousand boxes) leave most SMs idle while every warp walks the whole table:
+    // the table is split over gridDim.y slices (multiples of 64 obstacles); the verdict is the AND over the slices (pre-set to 1 by
+    // the host, cleared by any slice that finds a collision).  The table is sorted, so the far slices end at their first cut-off test.
+    const int slices = int(gridDim.y);
+    const int per = (((a.M + slices - 1) / slices) + 63) & ~63;
+    const int j_lo = int(blockIdx.y) * per, j_hi = min(a.M, j_lo + per);
     constexpr int kSeg = kWqSegment;                                       // queue entries carry a 16-bit obstacle index: lane | link << 5 | obstacle << 10 | edge code << 26
-    for (int base = 0; base < a.M; base += kSeg) {
-        const int count = min(kSeg, a.M - base);
+    for (int base = j_lo; base < j_hi; base += kSeg) {
+        const int count = min(kSeg, j_hi - base);
         seg_base = base;                                                   // (every interval ends with a flush, so no entry outlives its segment)
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
@@ -275,8 +281,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
     }
     __syncwarp();
     if (!live) return;
-    if (!EDGE) a.verdict[item] = invalid[t] ? 0 : 1;
-    else if (invalid[t]) a.verdict[edge] = 0;                             // verdict[] is pre-set to 1 by the host
+    if (!EDGE && slices == 1) a.verdict[item] = invalid[t] ? 0 : 1;
+    else if (invalid[t]) a.verdict[EDGE ? edge : item] = 0;               // verdict[] is pre-set to 1 by the host
 }
 
 }  // namespace rvs

@@ -66,7 +66,7 @@ struct Variant {
             if (e != cudaSuccess) return e;
             configured = smem;
         }
-        valid_wq_kernel<F, R, G, EDGE><<<grid_for(items, kWqBlock), kWqBlock, smem, st>>>(a);
+        valid_wq_kernel<F, R, G, EDGE><<<dim3(grid_for(items, kWqBlock), unsigned(a.slices > 1 ? a.slices : 1)), kWqBlock, smem, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t is_valid(const KArgs &a, cudaStream_t st) {
