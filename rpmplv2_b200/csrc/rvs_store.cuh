@@ -169,6 +169,87 @@ __global__ void __launch_bounds__(32 * kStoreWarps) distance_cta_kernel(const KA
     }
 }
 
+// isValid(q) / isValid(q1,q2) for a SMALL batch: one CTA per configuration (EDGE: per interpolated configuration of an edge), one warp
+// per link, one lane per obstacle (slab reject per lane, survivors through the reference predicate 32 at a time), first hit ends the CTA.  In the work-queue kernel 32
+// configurations share one warp's queues, so a planner-sized batch waits for ~10 rounds of the compacted phases per interval
+// (64 configurations against 1000 boxes: 147 us); here the latency is one pass over M / 32 obstacles per lane.  Verdicts are order free.
+template <class F, bool EDGE>
+__global__ void __launch_bounds__(32 * kStoreWarps) valid_cta_kernel(const KArgs a) {
+    __shared__ float s_sk[3 * (kMaxDofs + 1)];
+    __shared__ float s_q[kMaxDofs];
+    __shared__ int s_list[kStoreWarps][64];                              // per warp: obstacles that passed the slab test (leftover < 32 + 32 new)
+    __shared__ int s_hit;
+    const RobotDev *__restrict__ rb = a.robot;
+    const int L = rb->n, n = L, M = a.M;
+    const int64_t item = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int64_t edge = 0;
+    if (threadIdx.x == 0) s_hit = 0;
+    if (warp == 0) {
+        const float *q = a.q + item * n;
+        if (EDGE) {                                                       // RealVectorSpace.cpp:267-269: k = N .. 1, interpolateEdge(q1, q2, k / N * dist, dist)
+            edge = item / a.num_checks;
+            const int kidx = int(item - edge * a.num_checks);
+            const float *q1p = a.q + edge * n, *q2p = a.q2 + edge * n;
+            const float dist = coord_norm(q1p, q2p, n);
+            const float step = float(a.num_checks - kidx) / float(a.num_checks) * dist;
+            if (lane < n) s_q[lane] = dist > 0.f ? q1p[lane] + (q2p[lane] - q1p[lane]) * (step / dist) : q2p[lane];
+            __syncwarp();
+            q = s_q;
+        }
+        fk_skeleton_warp<F, float>(rb, q, s_sk);
+    }
+    if (EDGE) edge = item / a.num_checks;
+    __syncthreads();
+    const int ground_included = rb->ground_included;
+    const float eq_thr = a.eq_thr, max_dist = a.max_dist;
+    // Per link: every lane applies the predicate's own slab reject (CollisionAndDistance.cpp:14-17, the exit ~98 % of the pairs take)
+    // to its obstacle; the survivors are ballot-compacted into a small list and go through the full predicate 32 at a time, so the
+    // warp does not pay the face / edge tests once per 32 obstacles because ONE lane needs them.  (An endpoint inside the inflated
+    // box — the predicate's first, accepting test — is never slab-rejected, so nothing that collides is filtered.)
+    auto stopped = [&]() { return __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int *>(&s_hit), 0) != 0; };
+    for (int i = warp; i < L; i += kStoreWarps) {
+        Capsule<float> cp;
+        cp.set({s_sk[3 * i], s_sk[3 * i + 1], s_sk[3 * i + 2]}, {s_sk[3 * i + 3], s_sk[3 * i + 4], s_sk[3 * i + 5]}, rb->radius[i], rb->radius_in[i]);
+        const V3<float> &A = cp.A, &B = cp.B;
+        const float radius = cp.radius;
+        int have = 0;
+        bool done = false;
+        auto exact = [&](int count) {                                     // the top `count` list entries through the reference predicate
+            bool hit = false;
+            if (lane < count) hit = capsule_hits_box<float>(cp, load_box<float>(a.obstacles[s_list[warp][have + lane]]), eq_thr, max_dist);
+            if (__any_sync(0xffffffffu, hit)) { if (lane == 0) s_hit = 1; done = true; }
+            __syncwarp();
+        };
+        for (int j0 = 0; j0 < M && !done; j0 += 32) {
+            const int j = j0 + lane;
+            bool pass = false;
+            if (j < M) {
+                const ObstacleRec o = a.obstacles[j];
+                if (!((o.flags & 1u) && i < ground_included)) {
+                    const Box<float> bx = load_box<float>(o);
+                    pass = !((A.x < bx.lo.x - radius && B.x < bx.lo.x - radius) || (A.x > bx.hi.x + radius && B.x > bx.hi.x + radius) ||
+                             (A.y < bx.lo.y - radius && B.y < bx.lo.y - radius) || (A.y > bx.hi.y + radius && B.y > bx.hi.y + radius) ||
+                             (A.z < bx.lo.z - radius && B.z < bx.lo.z - radius) || (A.z > bx.hi.z + radius && B.z > bx.hi.z + radius));
+                }
+            }
+            const unsigned b = __ballot_sync(0xffffffffu, pass);
+            if (pass) s_list[warp][have + __popc(b & ((1u << lane) - 1u))] = j;
+            have += __popc(b);
+            __syncwarp();
+            if (have >= 32) { have -= 32; exact(32); }
+            if (!done && stopped()) done = true;                         // another link already collides
+        }
+        if (!done && have > 0) { const int count = have; have = 0; exact(count); }
+        if (done || stopped()) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (!EDGE) a.verdict[item] = s_hit ? 0 : 1;
+        else if (s_hit) a.verdict[edge] = 0;                              // verdict[] is pre-set to 1 by the host
+    }
+}
+
 // distance-to-planes (RealVectorSpace.cpp:402-446) with the L*M planes of one layer split over the lanes of a warp;
 // every lane returns the same d_c / prof / rejected. Values are those of underestimation_of() (same per-plane arithmetic).
 __device__ __forceinline__ float underestimation_warp(const RobotDev *__restrict__ rb, int L, int M, const float *sk, const float *__restrict__ planes,

@@ -16,6 +16,7 @@ inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1)
 #ifndef RVS_SMALL_BATCH
 #define RVS_SMALL_BATCH 4096
 #endif
+constexpr int64_t kSmallValid = 2048;       // validity items (configurations, or edges x checks) up to which one CTA per item is used
 constexpr int64_t kSmallBatch = RVS_SMALL_BATCH;      // rvs_distance* calls up to this many configurations (4x for FULL) take the one-CTA-per-configuration kernel
 
 template <class F, class R>
@@ -71,12 +72,20 @@ struct Variant {
     }
     static cudaError_t is_valid(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= kSmallValid) {              // planner-sized batch: one CTA per configuration
+            valid_cta_kernel<F, false><<<unsigned(a.N), 32 * kStoreWarps, 0, st>>>(a);
+            return cudaGetLastError();
+        }
         if (a.cull && a.M > 0 && a.M < (1 << 22)) return a.robot_n_hint <= 2 ? valid_wq<2, false>(a, a.N, st) : valid_wq<6, false>(a, a.N, st);
         is_valid_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t edge_valid(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
+        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N * a.num_checks <= kSmallValid) {
+            valid_cta_kernel<F, true><<<unsigned(a.N * a.num_checks), 32 * kStoreWarps, 0, st>>>(a);
+            return cudaGetLastError();
+        }
         if (a.cull && a.M > 0 && a.M < (1 << 22))
             return a.robot_n_hint <= 2 ? valid_wq<2, true>(a, a.N * a.num_checks, st) : valid_wq<6, true>(a, a.N * a.num_checks, st);
         edge_valid_kernel<F, R><<<grid_for(a.N * a.num_checks, kBlock), kBlock, 0, st>>>(a);
