@@ -180,8 +180,6 @@ int enter(rvs_engine *h) {
     return RVS_OK;
 }
 
-size_t real_size(rvs_engine *h) { return h->prm.precision == RVS_PREC_F64 ? sizeof(double) : sizeof(float); }
-
 int launched(rvs_engine *h, cudaError_t e, const char *what) {
     if (e != cudaSuccess) return cuda_fail(h, e, what);
     h->launches++;
@@ -265,11 +263,9 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_k2, h->ev_done, 0));
     const int64_t per = ((N + chunks - 1) / chunks + 127) & ~int64_t(127);
-    int used = 0;
     for (int c = 0; c < chunks; c++) {
         const int64_t first = int64_t(c) * per, cnt = std::min(per, N - first);
         if (cnt <= 0) break;
-        used = c + 1;
         RVS_CUDA(h, cudaMemcpyAsync(dq + first * n, q + first * n, size_t(cnt) * n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
         RVS_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
         cudaStream_t sk = (c & 1) ? h->s_k2 : h->stream;
