@@ -277,7 +277,6 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
         if (mode >= RVS_DIST_PROFILE)
             RVS_CUDA(h, cudaMemcpyAsync(static_cast<char *>(profile) + first * L * rs, dprof + first * L * rs, size_t(cnt) * L * rs, cudaMemcpyDeviceToHost, h->s_out));
     }
-    (void)used;
     RVS_CUDA(h, cudaStreamSynchronize(h->s_out));
     RVS_CUDA(h, cudaStreamSynchronize(h->s_k2));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
