@@ -141,6 +141,12 @@ __device__ __forceinline__ WqCtx<R> wq_make_ctx(unsigned char *smem, const float
     return c;
 }
 
+// scan boxes are FP32 in every variant (the obstacle table is FP32): an F64 bound is rounded OUTWARDS, which keeps the test conservative
+__device__ __forceinline__ float wq_round_down(float v) { return v; }
+__device__ __forceinline__ float wq_round_up(float v) { return v; }
+__device__ __forceinline__ float wq_round_down(double v) { return __double2float_rd(v); }
+__device__ __forceinline__ float wq_round_up(double v) { return __double2float_ru(v); }
+
 template <class R> __device__ __forceinline__ R wq_inf() { return R(__int_as_float(0x7f800000)); }
 
 template <class R> __device__ __forceinline__ R wq_threshold(R best, R radius, R eq_thr) {
@@ -329,7 +335,7 @@ __device__ __noinline__ R wq_replay_pair(R ax, R ay, R az, R bx_, R by, R bz, R 
 
 // F = FK scalar, R = geometry scalar, MODE = RVS_DIST_MIN | RVS_DIST_PROFILE, G = links scanned per obstacle pass.
 template <class F, class R, int MODE, int G>
-__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 2) distance_wq_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 3) distance_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char wq_smem[];
     static_assert(G >= 1 && G <= 6, "the slot -> link map packs at most six 5-bit link indices");
     typedef typename WqBits<R>::type Bits;
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
                 const int K = __popc(alive);
                 unsigned ground_keep = 0;
                 slotmap = 0;                                                // (Q0 is empty here: every interval ends with a flush)
-                R lo[G][3], hi[G][3];
+                float lo[G][3], hi[G][3];
                 {
                     unsigned rem = alive;
 #pragma unroll
@@ -413,12 +419,12 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
 #pragma unroll
                             for (int k = 0; k < 3; k++) {
                                 const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
-                                lo[s][k] = fmin(p, q) - thr;
-                                hi[s][k] = fmax(p, q) + thr;
+                                lo[s][k] = wq_round_down(fmin(p, q) - thr);
+                                hi[s][k] = wq_round_up(fmax(p, q) + thr);
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<R>(); hi[s][k] = -wq_inf<R>(); }          // overlaps nothing
+                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<float>(); hi[s][k] = -wq_inf<float>(); }  // overlaps nothing
                         }
                         if (s < K) {
                             slotmap |= unsigned(i) << (5 * s);
@@ -439,8 +445,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
                     unsigned mask = 0;
 #define RVS_WQ_SLOT(S)                                                                                                             \
     if (S < G) {                                                                                                                   \
-        wq_overlap<R>(mask, 1u << (S), R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
-        wq_overlap<R>(mask, 1u << (G + (S)), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<float>(mask, 1u << (S), w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<float>(mask, 1u << (G + (S)), v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, lo[S < G ? S : 0], hi[S < G ? S : 0]); \
     }
                     switch (K) {                                                              // warp-uniform: only live slots are tested
                         case 0: break;
