@@ -30,7 +30,7 @@ __host__ __device__ inline size_t vq_smem_bytes(int L) {
 }
 
 template <class F, class R, int G, bool EDGE>
-__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char vq_smem[];
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n, n = L;
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                 const int jfirst = alive ? j0 : (count - 1) & ~1;
                 const int K = __popc(alive);
                 unsigned slotmap = 0, ground_keep = 0;
-                R lo[G][3], hi[G][3];
+                float lo[G][3], hi[G][3];                                 // FP32 in every variant (the table is FP32); F64 bounds rounded outwards
                 {
                     unsigned rem = alive;
 #pragma unroll
@@ -220,12 +220,12 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
 #pragma unroll
                             for (int k = 0; k < 3; k++) {
                                 const R u = sk[k * kWqStride], v = sk[(3 + k) * kWqStride];
-                                lo[s][k] = fmin(u, v) - thr;
-                                hi[s][k] = fmax(u, v) + thr;
+                                lo[s][k] = wq_round_down(fmin(u, v) - thr);
+                                hi[s][k] = wq_round_up(fmax(u, v) + thr);
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<R>(); hi[s][k] = -wq_inf<R>(); }
+                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<float>(); hi[s][k] = -wq_inf<float>(); }
                         }
                         if (s < K) {
                             slotmap |= unsigned(i) << (5 * s);
@@ -243,8 +243,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 2) valid_wq_ker
                     unsigned mask = 0;
 #define RVS_VQ_SLOT(S)                                                                                                             \
     if (S < G) {                                                                                                                   \
-        wq_overlap<R>(mask, 1u << (S), R(w0.x), R(w0.y), R(w0.z), R(w0.w), R(w1.x), R(w1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
-        wq_overlap<R>(mask, 1u << (G + (S)), R(v0.x), R(v0.y), R(v0.z), R(v0.w), R(v1.x), R(v1.y), lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<float>(mask, 1u << (S), w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, lo[S < G ? S : 0], hi[S < G ? S : 0]); \
+        wq_overlap<float>(mask, 1u << (G + (S)), v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, lo[S < G ? S : 0], hi[S < G ? S : 0]); \
     }
                     switch (K) {
                         case 0: break;
