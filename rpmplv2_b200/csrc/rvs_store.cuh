@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const Sto
     if (root_d_c > 0.f) {
         for (int layer = 0; layer < a.num_layers; layer++) {
             status = 1;
-            fk_of(q_cur, sk);
+            if (layer == 0) fk_of(q_cur, sk);                          // later layers start where the previous one ended: its skeleton is kept
             float rho = 0.f, rho_profile = 0.f, q_temp = q_cur;
             for (int counter = 1;; counter++) {
                 const float *sk_use = sk;
@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const Sto
             const float prof_new = underestimation_lanes(rb, L, M, sk_new, root_planes, a.max_dist, d_out, rejected, lane);
             if (d_out < a.d_crit || (a.gen2 ? status == 3 : status != 1)) break;
             q_cur = q_new; prof_cur = prof_new; dc_cur = d_out;
+            for (int k = lane; k < 3 * W; k += 32) sk[k] = sk_new[k];  // FK(q_cur) of the next layer == FK(q_new) of this one
             __syncwarp();
         }
     }
