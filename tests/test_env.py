@@ -221,3 +221,41 @@ def test_gpu_env_argument_errors(ob):
         eng.motion_validity(np.zeros((2, 6), np.float32), np.zeros((2, 6), np.float32), 0, 0.01)
     v, f = eng.motion_validity(np.zeros((0, 6), np.float32), np.zeros((0, 6), np.float32), 5, 0.01)
     assert len(v) == 0
+
+
+@pytest.mark.gpu
+def test_gpu_env_edge_cases(ob):
+    """Empty environment, a single update / validity point, objects at rest, and a handle switching between a plain table and an
+    environment."""
+    from rpmplv2_b200.engine import Engine
+    rb = robots.xarm6()
+    q1, q2 = random_motions(rb, 17, 0x31)
+    eng = Engine(rb)
+    empty = dict(dim=np.zeros((0, 3), np.float32), pos=np.zeros((0, 3), np.float32))
+    eng.env_set(params_for("straight"), **empty)
+    v, f = eng.motion_validity(q1, q2, 3, 0.01, commit_edge=0)
+    assert v.all() and (f == 0).all()                                        # nothing to collide with
+    eng.env_step(0.01, 5)
+    assert eng.env_get()[0].shape == (0, 3)
+    sc = dynamic_scene(rb, 4, 51)
+    sc["vel"][:] = 0
+    sc["max_vel"][:] = 0
+    eng.env_set(params_for("light_directions"), **sc)
+    orc = ob.Oracle(rb)
+    orc.env_set(params_for("light_directions"), **sc)
+    for K in (1, 2, 25):
+        v_e, f_e = eng.motion_validity(q1, q2, K, 0.02, commit_edge=3)
+        v_o, f_o = orc.motion_validity(q1, q2, K, 0.02, commit_edge=3)
+        assert np.array_equal(f_e, f_o)
+        assert np.array_equal(eng.env_get()[0], sc["pos"])                   # objects at rest stay where they are
+    # with resting objects the K-th validity point is q2 itself: MotionValidity(K = 1) == isValid(q2)
+    v1, _ = eng.motion_validity(q1, q2, 1, 0.02)
+    assert np.array_equal(v1, eng.is_valid(q2))
+    # back to a plain obstacle table: the environment is switched off
+    half = np.float32(0.5) * sc["dim"]
+    eng.set_obstacles(sc["pos"] - half, sc["pos"] + half, sc["is_ground"], sc["min_dist_tol"])
+    from rpmplv2_b200.engine import RvsError
+    with pytest.raises(RvsError):
+        eng.env_step(0.01, 1)
+    eng.update_obstacle_aabbs(sc["pos"] - half, sc["pos"] + half)            # allowed again
+    eng.close()
