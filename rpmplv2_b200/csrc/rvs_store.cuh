@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(32 * kStoreWarps) valid_cta_kernel(const KArgs
     // to its obstacle; the survivors are ballot-compacted into a small list and go through the full predicate 32 at a time, so the
     // warp does not pay the face / edge tests once per 32 obstacles because ONE lane needs them.  (An endpoint inside the inflated
     // box — the predicate's first, accepting test — is never slab-rejected, so nothing that collides is filtered.)
-    auto stopped = [&]() { return __shfl_sync(0xffffffffu, *reinterpret_cast<volatile int *>(&s_hit), 0) != 0; };
+    // the flag only ever goes 0 -> 1 and is polled: atomics keep the inter-warp traffic well defined (and racecheck quiet)
+    auto stopped = [&]() { return __shfl_sync(0xffffffffu, lane == 0 ? atomicOr(&s_hit, 0) : 0, 0) != 0; };
     for (int i = warp; i < L; i += kStoreWarps) {
         Capsule<float> cp;
         cp.set({s_sk[3 * i], s_sk[3 * i + 1], s_sk[3 * i + 2]}, {s_sk[3 * i + 3], s_sk[3 * i + 4], s_sk[3 * i + 5]}, rb->radius[i], rb->radius_in[i]);
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(32 * kStoreWarps) valid_cta_kernel(const KArgs
         auto exact = [&](int count) {                                     // the top `count` list entries through the reference predicate
             bool hit = false;
             if (lane < count) hit = capsule_hits_box<float>(cp, load_box<float>(a.obstacles[s_list[warp][have + lane]]), eq_thr, max_dist);
-            if (__any_sync(0xffffffffu, hit)) { if (lane == 0) s_hit = 1; done = true; }
+            if (__any_sync(0xffffffffu, hit)) { if (lane == 0) atomicOr(&s_hit, 1); done = true; }
             __syncwarp();
         };
         for (int j0 = 0; j0 < M && !done; j0 += 32) {

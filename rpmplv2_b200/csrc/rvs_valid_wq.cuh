@@ -126,9 +126,9 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_ker
                 if (e != kNoEntry) {
                     int tt, link; Capsule<R> cp; Box<R> bx;
                     load_item(e, tt, link, cp, bx);
-                    if (!invalid[tt]) {
+                    if (!atomicOr(&invalid[tt], 0u)) {                            // (the flag only goes 0 -> 1; atomics keep the polling well defined)
                         V3<R> u, v;
-                        if (plan_edge_distance<R, false>(cp, bx, e >> 26, eq_thr, max_dist, u, v) < cp.radius) invalid[tt] = 1u;
+                        if (plan_edge_distance<R, false>(cp, bx, e >> 26, eq_thr, max_dist, u, v) < cp.radius) atomicOr(&invalid[tt], 1u);
                     }
                 }
             } else if (t1 >= 32u || (flush && t1 > 0u)) {
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_ker
                 if (e != kNoEntry) {
                     int tt, link; Capsule<R> cp; Box<R> bx;
                     load_item(e, tt, link, cp, bx);
-                    if (!invalid[tt]) {
+                    if (!atomicOr(&invalid[tt], 0u)) {                            // (the flag only goes 0 -> 1; atomics keep the polling well defined)
                         // Cheap exact-safe reject in front of the predicate: every `true` of collisionCapsuleToBox implies an axis point
                         // within sqrt(2) * radius of the box (endpoint in the box inflated by r/sqrt(3); crossing point inside the rectangle
                         // oversized by r; an edge or face distance < r), hence within sqrt(2) r + (half diagonal) of the box centre.  A
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_ker
                         const bool far = d2 - R(4e-6) * (vv + R(1)) > reach * reach * R(1.002);     // (NaN anywhere: not far, the predicate decides)
                         if (!far) {
                             HitEdges edges;
-                            if (hit_box_plan(cp, bx, max_dist, edges)) invalid[tt] = 1u;
+                            if (hit_box_plan(cp, bx, max_dist, edges)) atomicOr(&invalid[tt], 1u);
                             else if (edges.count) {
                                 const unsigned pos = atomicAdd(const_cast<unsigned *>(&tail[1]), unsigned(edges.count));
 #pragma unroll 1
