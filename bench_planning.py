@@ -98,6 +98,9 @@ def run(P: int = 64, device: int = 0, cpu: bool = True, max_time: float = 30.0, 
                    gpu_lockstep=dict(wall_s=t_lock, per_run_ms=1e3 * t_lock / P, rounds=st["rounds"], backend_calls=st["backend_calls"],
                                      kernel_launches=st["kernel_launches"], us_per_backend_call=1e6 * t_lock / max(1, st["backend_calls"])),
                    gpu_single=dict(per_run_ms=1e3 * t_single, runs=k, success=int(sum(r["success"] for r in single))))
+        # a pool that ran into max_planning_time reports the budget, not a speed: compare `success` within the budget instead
+        row["gpu_lockstep"]["time_limited"] = bool(t_lock >= 0.98 * max_time)
+        row["planning_time_budget_s"] = max_time
         if cpu:
             from oracle import oracle_binding as ob
             o = ob.Oracle(rb, robots.default_params())
