@@ -299,6 +299,22 @@ def main():
     pairs_e2e = eng.pair_count(reset=True)
     esz = 8 if prec == robots.PREC_F64 else 4
 
+    # supplementary (not part of the metric): isValid over the same batch, device-resident, median of 5 launches on this rank
+    verdict = None
+    if prec != robots.PREC_F64:
+        d_v = torch.empty(N_CONFIGS, dtype=torch.uint8, device=dev)
+        vms = []
+        for s in range(6):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); eng.is_valid_dev(d_q[W + (s % K)].data_ptr(), N_CONFIGS, d_v.data_ptr()); b.record(stream)
+            torch.cuda.synchronize()
+            vms.append(a.elapsed_time(b))
+        vmed = sorted(vms[1:])[2]
+        verdict = {"ms_per_launch": vmed, "configs_per_s": N_CONFIGS / vmed * 1e3,
+                   "collision_pair_queries_per_s": N_CONFIGS * synthetic.pair_queries(rb, g) / vmed * 1e3,
+                   "valid_fraction": round(float(d_v.float().mean().item()), 4),
+                   "kernel": "rvs::valid_wq_kernel (scan + pair / edge phases); nominal pairs L*M per configuration, no early-exit credit"}
+
     # reductions across ranks: time = max, pairs = sum
     red = torch.tensor([t_rank, t_e2e], dtype=torch.float64, device=dev)
     tot = torch.tensor([float(pairs_rank), float(pairs_e2e), float(launches)], dtype=torch.float64, device=dev)
@@ -339,6 +355,7 @@ def main():
                     "d2h_bytes_per_step": N_CONFIGS * esz * (1 + L), "steps": e2e_steps, "ms_per_step": 1e3 * t_e2e_all / e2e_steps,
                     "api": "rvs_distance (host pointers, pinned), H2D + kernel + D2H inside the timed region"},
             "gpu_launches": int(launches_all),
+            "is_valid": verdict,
             "roofline": {"bound": "fp32" if prec != robots.PREC_F64 else "fp64", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": achieved / peak if peak else None, "traffic": NCU_TRAFFIC_BYTES,
                          "convention": "C1: 630 flop FK per config + 150 flop per reference pair query (SURVEY.md 8d)",
