@@ -89,3 +89,36 @@ def test_gpu_gbur_matches_the_oracle_backed_driver(ob, robot, H):
         assert np.abs(ge["d_c"] - go["d_c"]).max() <= 1e-4
         assert np.array_equal(ge["status"], go["status"]) or np.abs(go["d_c"] - 0.05).min() < 1e-4
     eng.close()
+
+
+def test_horizon_weights_equal_a_literal_loop_restatement():
+    """drgbt.horizon_weights (vectorised) against DRGBT::computeNextState (DRGBT.cpp:499-561) written out state by state."""
+    rng = np.random.default_rng(12)
+    H, n = 37, 6
+    q_reached = rng.uniform(-2, 2, (H, n)).astype(np.float32)
+    q_goal = rng.uniform(-2, 2, n).astype(np.float32)
+    d_c = rng.uniform(0.0, 0.6, H).astype(np.float32)
+    d_prev = (d_c + rng.normal(0, 0.05, H)).astype(np.float32)
+    index = np.where(rng.random(H) < 0.4, -1, np.arange(H))
+    status = np.where(d_c < 0.05, drgbt.STATUS_CRITICAL, drgbt.STATUS_GOOD)
+    for num_iter, dmm in ((0, 0.0), (17, 0.31)):
+        w, best, dmm_new = drgbt.horizon_weights(q_reached, d_c, d_prev, index, status, q_goal, dmm, num_iter)
+        f = np.float32
+        dist_to_goal = [f(np.sqrt(((q_reached[i] - q_goal) ** 2).sum(dtype=np.float32))) for i in range(H)]
+        d_goal_min, d_c_max = min(dist_to_goal), max(d_c)
+        weights_dist = [f(d_goal_min / dist_to_goal[i]) for i in range(H)]
+        d_max_mean = f((f(num_iter) * f(dmm) + d_c_max) / f(num_iter + 1))
+        mean = f(sum(float(x) for x in weights_dist) / H)
+        max_weight, idx_best = 0.0, -1
+        for i in range(H):
+            if status[i] == drgbt.STATUS_CRITICAL:
+                assert w[i] == 0
+                continue
+            weight = f(d_c[i] / d_max_mean + (d_c[i] - d_prev[i]) / d_max_mean + weights_dist[i] - mean)
+            weight = min(max(weight, f(0)), f(1))
+            if index[i] == -1:
+                weight = f(weight * f(0.5))
+            assert abs(float(w[i]) - float(weight)) <= 2e-6
+            if weight > max_weight:
+                max_weight, idx_best = weight, i
+        assert best == idx_best and dmm_new == pytest.approx(float(d_max_mean))
