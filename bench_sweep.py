@@ -182,9 +182,9 @@ def main():
     # ---- S2 (e) one DRGBT iteration's geometry (row f-1): computeDistance(q_current, true) + H generalized-bur spines + H real
     # distances (DRGBT.cpp:101, 272-320, 475-495) + the motion check with moving obstacles (MotionValidity.cpp:30-51);
     # spatial_22dof, ground + 5 moving cubes (BASELINE config 4); H = 10 + 2n - 2 = 52 and 10n = 220 (critical clearance)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from test_drgbt import OracleSpace, _horizon
+    from oracle.oracle_space import OracleSpace      # CPU column only
     from rpmplv2_b200 import drgbt
+    _horizon = synthetic.horizon_states
     rbd = robots.spatial(22)
     scd = scenes.dynamic_scene(rbd, 5, 21, r_lo=0.45 * 2.2, r_hi=0.95 * 2.2, size=0.3 * 2.2)
     scd["min_dist_tol"] = np.full(6, 1000.0, np.float32)

@@ -5,8 +5,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import scenes
-from test_drgbt import _horizon
 from rpmplv2_b200 import drgbt, engine, robots, synthetic
+_horizon = synthetic.horizon_states
 
 def med(fn, n=60):
     fn(); t = []

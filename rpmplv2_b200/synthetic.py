@@ -130,3 +130,12 @@ def pair_queries(robot: Robot, is_ground: np.ndarray) -> int:
     L, M = robot.num_links, int(len(is_ground))
     skipped = int(np.count_nonzero(is_ground)) * min(int(robot.ground_included), L)
     return L * M - skipped
+
+
+def horizon_states(robot: Robot, q_current: np.ndarray, H: int, seed: int, delta: float = math.pi) -> np.ndarray:
+    """H states RBTConnectConfig::DELTA away from q_current in random directions, clipped to the joint limits: the shape of DRGBT's
+    lateral / random horizon states (/root/reference/src/planners/drbt/DRGBT.cpp:358-420)."""
+    rng = np.random.default_rng(seed)
+    step = rng.normal(0, 1.0, (H, robot.num_dofs)).astype(np.float32)
+    step *= np.float32(delta) / np.linalg.norm(step, axis=1, keepdims=True)
+    return np.clip(q_current + step, robot.limits[:, 0], robot.limits[:, 1]).astype(np.float32)

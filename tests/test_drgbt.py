@@ -9,37 +9,11 @@ import scenes
 from rpmplv2_b200 import drgbt, robots, synthetic
 
 
-class OracleSpace:
-    """store_distance / store_extend_spines / distance on top of the CPU oracle (tests only)."""
-
-    def __init__(self, o):
-        self.o, self.slots = o, {}
-
-    def store_reserve(self, capacity):
-        pass
-
-    def store_distance(self, q, slots):
-        d, p, near = self.o.distance(q, robots.DIST_FULL)
-        for k, s in enumerate(slots):
-            self.slots[int(s)] = (q[k].copy(), float(d[k]), p[k].copy(), near[k].copy())
-        return d, p
-
-    def store_extend_spines(self, root_slots, q_targets, sp, gen2=False):
-        uniq = sorted(set(int(s) for s in root_slots))
-        idx = np.array([uniq.index(int(s)) for s in root_slots], np.int32)
-        return self.o.extend_spines_layers(np.stack([self.slots[s][0] for s in uniq]), np.stack([self.slots[s][2] for s in uniq]),
-                                           np.array([self.slots[s][1] for s in uniq], np.float32), np.stack([self.slots[s][3] for s in uniq]),
-                                           idx, q_targets, sp, gen2)
-
-    def distance(self, q, mode=robots.DIST_PROFILE):
-        return self.o.distance(q, mode)
+from oracle.oracle_space import OracleSpace
 
 
 def _horizon(rb, q_current, H, seed):
-    rng = np.random.default_rng(seed)
-    step = rng.normal(0, 1.0, (H, rb.num_dofs)).astype(np.float32)
-    step *= np.float32(np.pi) / np.linalg.norm(step, axis=1, keepdims=True)          # RBTConnectConfig::DELTA away, like lateral / random states
-    return np.clip(q_current + step, rb.limits[:, 0], rb.limits[:, 1]).astype(np.float32)
+    return synthetic.horizon_states(rb, q_current, H, seed)
 
 
 def test_oracle_gbur_reached_states_are_collision_free_and_weights_follow_the_heuristic(ob):
