@@ -6,9 +6,14 @@
 //   /root/reference/src/planners/trajectory/MotionValidity.cpp:30-51          (check(q_previous, q_current))
 // in plain FP32 with Eigen's evaluation order (fixed-size Vector3f reductions as x0 + (x1 + x2), see rvs_oracle.hpp).
 //
-// PARITY STATUS: parity unpinned — the reference ships no golden vectors for the motion laws and Environment.cpp needs FCL and
-// yaml-cpp, which are absent here.  Pinned instead by closed-form known answers (tests/test_env_oracle.py): straight-line motion,
-// circular motion stays on its circle, the reflection law preserves speed and keeps every obstacle inside the workspace shell.
+// PARITY STATUS: the reference ships no golden vectors for the motion laws.  The LOGIC of this file is pinned against the reference's
+// own Environment.cpp / Object.cpp / objects/Box.cpp, compiled unmodified from /root/reference against oracle/eigen_shim plus
+// stand-ins for the slices of FCL and yaml-cpp they touch (oracle/env_shim, oracle/env_ref_capi.cpp, Makefile target `ref`):
+// positions, velocities, the two_tunnels bookkeeping and the AABBs agree bit for bit over all four laws, random restarts included
+// (tests/test_env.py; committed vectors: tests/golden/env_golden.npz from tests/golden/make_env_golden.py).  What stays "parity
+// unpinned" is third-party arithmetic: Eigen's reduction order (the shim encodes the same assumption) and FCL's
+// computeAABB (pos -/+ side/2).  Closed-form known answers are checked as well (straight-line motion, circular motion
+// spirals out by the Euler step, the reflection law preserves speed and keeps every obstacle inside the workspace shell).
 // moveRandomDirections draws from Eigen::Vector3f::Random (libc rand()) and is therefore not restated (not reproducible).
 #pragma once
 #include <cmath>

@@ -6,11 +6,14 @@ oracle on the same seeded inputs — bit-exact for the straight, two_tunnels and
 1e-5 m for the circular law (atan2f / sinf / cosf differ in the last ulp between CUDA and glibc).
 Reference: /root/reference/src/environments/Environment.cpp:194-377, src/planners/trajectory/MotionValidity.cpp:30-51.
 """
+import os
+
 import numpy as np
 import pytest
 
 from rpmplv2_b200 import robots, synthetic
 from rpmplv2_b200.engine import env_params
+from conftest import ROOT
 from scenes import WS_CENTER, dynamic_scene
 
 LAWS = ["straight", "circular", "two_tunnels", "light_directions"]
@@ -259,3 +262,52 @@ def test_gpu_env_edge_cases(ob):
         eng.env_step(0.01, 1)
     eng.update_obstacle_aabbs(sc["pos"] - half, sc["pos"] + half)            # allowed again
     eng.close()
+
+
+# ------------------------------------------------------------------- pinned by the reference's own Environment.cpp (compiled with shims)
+def _golden_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_env_golden", os.path.join(ROOT, "tests", "golden", "make_env_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_oracle_motion_laws_match_the_reference_environment_golden(ob):
+    """oracle/rvs_oracle_env.hpp against vectors produced by the reference's Environment.cpp / Object.cpp / Box.cpp compiled against
+    oracle/eigen_shim + oracle/env_shim (tests/golden/make_env_golden.py): positions, velocities, two_tunnels bookkeeping and the AABBs
+    after 1 .. 250 updates, bit for bit (circular: the same libm on both sides here)."""
+    mod = _golden_cases()
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "env_golden.npz"))
+    for k, (law, prm, sc, dt, steps) in enumerate(mod.cases()):
+        o = ob.Oracle(robots.xarm6())
+        o.env_set(env_params(law, ws_center=tuple(prm[:3]), ws_radius=float(prm[3]), base_radius=float(prm[4]), robot_max_vel=float(prm[5])), **sc)
+        o.env_step(float(dt), steps)
+        pos, vel = o.env_get()
+        assert np.array_equal(pos, gold[f"c{k}_pos"]), (law, k, np.abs(pos - gold[f"c{k}_pos"]).max())
+        assert np.array_equal(vel, gold[f"c{k}_vel"]), (law, k)
+        assert np.array_equal(o._env["sign"], gold[f"c{k}_sign"]) and np.array_equal(o._env["path_len"], gold[f"c{k}_plen"])
+        half = np.float32(0.5) * sc["dim"]
+        assert np.array_equal(pos + (-half), gold[f"c{k}_mn"]) and np.array_equal(pos + half, gold[f"c{k}_mx"])
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libenv_ref.so")), reason="oracle/_ref is built where /root/reference exists")
+def test_oracle_motion_laws_match_the_compiled_reference_step_by_step(ob):
+    """The same comparison against the compiled reference itself, continuing from state to state (random restarts exercise the
+    reflection branches and the two_tunnels reversal with arbitrary bookkeeping)."""
+    import ctypes
+    mod = _golden_cases()
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libenv_ref.so"))
+    rb = robots.xarm6()
+    prm = np.array(list(WS_CENTER) + [0.9, 0.25, 1.2], np.float32)
+    for law in mod.LAWS:
+        sc = dynamic_scene(rb, 14, 77, speed=1.1)
+        o = ob.Oracle(rb)
+        o.env_set(env_params(law, ws_center=WS_CENTER, ws_radius=0.9, base_radius=0.25, robot_max_vel=1.2), **sc)
+        state = None
+        for dt, steps in ((0.013, 5), (0.02, 61), (0.007, 200), (0.031, 17)):
+            state = mod.ref_update(lib, prm, law, sc, dt, steps, state)
+            o.env_step(dt, steps)
+            pos, vel = o.env_get()
+            assert np.array_equal(pos, state[0]) and np.array_equal(vel, state[1]), law
+            assert np.array_equal(o._env["sign"], state[2]) and np.array_equal(o._env["path_len"], state[3]), law
