@@ -55,6 +55,7 @@ public:
         else { const Vector3f d(geom->radius, geom->radius, geom->radius); aabb.min_ = pos - d; aabb.max_ = pos + d; }
     }
     const AABB<S> &getAABB() const { return aabb; }
+    void stubSetAABB(const Vector3f &mn, const Vector3f &mx) { aabb.min_ = mn; aabb.max_ = mx; }      // stand-in only: exact table values for the harness
     NODE_TYPE getNodeType() const { return geom->getNodeType(); }
 private:
     std::shared_ptr<CollisionGeometry<S>> geom;

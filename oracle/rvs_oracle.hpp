@@ -9,12 +9,16 @@
 //
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use this.
 //
-// PARITY STATUS: the reference ships no golden vectors for this path and cannot be built here (Eigen, FCL,
-// KDL, yaml-cpp absent).  The decision logic of this file is pinned against the reference's own
-// CollisionAndDistance.cpp compiled from /root/reference against a minimal Eigen work-alike
-// (oracle/eigen_shim, see oracle/Makefile target `_ref`) plus analytic known answers; third-party
-// arithmetic (Eigen reduction order, KDL FK, FCL AABB) is restated from published behaviour and is
-// "parity unpinned" (SURVEY.md §8c, Q22-Q24).
+// PARITY STATUS: the reference ships no golden vectors for this path and cannot be built with its own build system here (Eigen, FCL,
+// KDL, yaml-cpp absent).  Instead its own sources are compiled, unmodified and where they lie, against work-alikes of the API slices
+// they use (oracle/eigen_shim, oracle/env_shim; oracle/Makefile target `ref` -> oracle/_ref/):
+//   * CollisionAndDistance.cpp                      -> libcad_ref.so: every primitive, 2.4 M random + degenerate pairs, bit for bit;
+//   * RealVectorSpace.cpp + State / StateSpace / Environment / Object / Box / AbstractRobot sources -> librvs_ref.so: the LOOPS
+//     (isValid(q), isValid(q1,q2), computeDistance with profile / nearest points / nullptr rule, computeDistanceUnderestimation),
+//     nine scenes, bit for bit (tests/test_oracle_golden.py, tests/golden/rvs_golden.npz);
+//   * Environment.cpp's motion laws                 -> libenv_ref.so (rvs_oracle_env.hpp).
+// Third-party arithmetic (Eigen reduction order, KDL FK, FCL AABB) is restated from published behaviour and stays "parity unpinned"
+// (SURVEY.md §8c, Q22-Q24); so do the bur spines, whose reference sources need the planner base classes.
 //
 // All `file:line` citations are relative to /root/reference/.
 // Build: g++ -O3 -std=c++17 -ffp-contract=off  (the reference is an x86-64 Release build without FMA).

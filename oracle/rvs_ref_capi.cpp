@@ -1,0 +1,160 @@
+// rvs_ref_capi.cpp — C entry points around the REFERENCE's own base::RealVectorSpace (isValid(q), isValid(q1,q2), computeDistance,
+// computeDistanceUnderestimation), compiled from /root/reference/src/state_spaces/real_vector_space/RealVectorSpace.cpp (+ State.cpp,
+// StateSpace.cpp, RealVectorSpaceState.cpp, CollisionAndDistance.cpp, AbstractRobot.cpp, Environment.cpp, Object.cpp, Box.cpp),
+// unmodified and where they lie, against oracle/eigen_shim and oracle/env_shim.  TEST INFRASTRUCTURE ONLY (oracle/_ref/, git-ignored).
+//
+// What this pins: the LOOPS of the hot path — link / obstacle order, the ground rule, min_dist_tol, the first-collision exit and its
+// profile fill, nearest-point storage, the edge discretisation (k = N..1, float step), the underestimation's reject rule and state
+// side effects — on top of the already pinned capsule / box primitives.  What it cannot pin: the robot's forward kinematics (KDL) —
+// the harness robot answers computeSkeleton with the oracle's own FK restatement, so both sides see identical skeletons.
+#include <cstdint>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../include/rvs_cuda.h"
+#include "rvs_oracle.hpp"
+
+#include "RealVectorSpace.h"
+
+namespace {
+
+class HarnessRobot : public robots::AbstractRobot {
+public:
+    orc::Robot chain;
+    explicit HarnessRobot(const rvs_robot_desc *rd) {
+        chain.kind = rd->kind; chain.n = rd->num_dofs; chain.ground_included = rd->ground_included; chain.gripper_length = rd->gripper_length;
+        for (int k = 0; k <= chain.n; k++) {
+            chain.fixed_rot.push_back(orc::rpy_matrix(rd->joint_rpy[k][0], rd->joint_rpy[k][1], rd->joint_rpy[k][2]));
+            chain.xyz.push_back({rd->joint_xyz[k][0], rd->joint_xyz[k][1], rd->joint_xyz[k][2]});
+        }
+        for (int k = 0; k < chain.n; k++) {
+            const double *a = rd->joint_axis[k];
+            const double len = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+            chain.axis.push_back({a[0] / len, a[1] / len, a[2] / len});
+            chain.radius.push_back(rd->capsule_radius[k]);
+            capsules_radius.push_back(rd->capsule_radius[k]);
+            limits.emplace_back(rd->limit_lo[k], rd->limit_hi[k]);
+        }
+        type = "harness";
+        num_DOFs = size_t(chain.n);
+        links.resize(size_t(chain.n));                       // getNumLinks() == links.size()
+        ground_included = size_t(rd->ground_included);
+        gripper_length = rd->gripper_length;
+        self_collision_checking = false;
+    }
+    void setState(const std::shared_ptr<base::State>) override {}
+    std::shared_ptr<std::vector<KDL::Frame>> computeForwardKinematics(const std::shared_ptr<base::State>) override { return nullptr; }
+    std::shared_ptr<base::State> computeInverseKinematics(const KDL::Rotation &, const KDL::Vector &, const std::shared_ptr<base::State>) override { return nullptr; }
+    std::shared_ptr<Eigen::MatrixXf> computeSkeleton(const std::shared_ptr<base::State> &q) override {
+        std::vector<orc::V3<float>> sk(size_t(chain.n + 1));
+        std::vector<float> qq(size_t(chain.n));
+        for (int i = 0; i < chain.n; i++) qq[size_t(i)] = q->getCoord(i);
+        orc::skeleton(chain, qq.data(), sk.data());
+        auto m = std::make_shared<Eigen::MatrixXf>(3, chain.n + 1);
+        for (int k = 0; k <= chain.n; k++) { (*m)(0, k) = sk[size_t(k)].x; (*m)(1, k) = sk[size_t(k)].y; (*m)(2, k) = sk[size_t(k)].z; }
+        return m;
+    }
+    std::shared_ptr<Eigen::MatrixXf> computeEnclosingRadii(const std::shared_ptr<base::State> &) override { return nullptr; }
+    bool checkSelfCollision(const std::shared_ptr<base::State> &, std::shared_ptr<base::State> &) override { return false; }
+    bool checkSelfCollision(const std::shared_ptr<base::State> &) override { return false; }
+};
+
+struct Harness {
+    std::shared_ptr<HarnessRobot> robot;
+    std::shared_ptr<env::Environment> env;
+    std::shared_ptr<base::RealVectorSpace> ss;
+    int n = 0;
+};
+
+std::shared_ptr<base::State> state_of(Harness &h, const float *q) {
+    Eigen::VectorXf c(h.n);
+    for (int i = 0; i < h.n; i++) c(i) = q[i];
+    return h.ss->getNewState(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+void *rvsref_create(const rvs_robot_desc *rd, float eq_thr, float max_dist, int32_t num_checks) {
+    RealVectorSpaceConfig::EQUALITY_THRESHOLD = eq_thr;
+    RealVectorSpaceConfig::MAX_DISTANCE = max_dist;
+    RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS = size_t(num_checks);
+    auto *h = new Harness();
+    h->n = rd->num_dofs;
+    h->robot = std::make_shared<HarnessRobot>(rd);
+    std::streambuf *keep = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());                              // the YAML constructor reports the (stubbed, empty) file
+    h->env = std::make_shared<env::Environment>(std::string("unused.yaml"), std::string(""));
+    std::cout.rdbuf(keep);
+    h->ss = std::make_shared<base::RealVectorSpace>(size_t(h->n), h->robot, h->env);
+    return h;
+}
+void rvsref_destroy(void *p) { delete static_cast<Harness *>(p); }
+
+int rvsref_set_obstacles(void *p, const float *mn, const float *mx, const uint8_t *ground, const float *tol, int32_t M) {
+    auto *h = static_cast<Harness *>(p);
+    h->env->removeAllObjects();
+    for (int j = 0; j < M; j++) {
+        const fcl::Vector3f lo(mn[3 * j], mn[3 * j + 1], mn[3 * j + 2]), hi(mx[3 * j], mx[3 * j + 1], mx[3 * j + 2]);
+        auto obj = std::make_shared<env::Box>(fcl::Vector3f(hi - lo), fcl::Vector3f(0.5f * (lo + hi)), fcl::Quaternionf::Identity(), (ground && ground[j]) ? "ground" : "");
+        obj->getCollObject()->stubSetAABB(lo, hi);              // the table's exact values (what FCL's computeAABB would report is not pinned here)
+        if (tol) obj->setMinDistTol(tol[j]);
+        h->env->addObject(obj);
+    }
+    return 0;
+}
+
+int rvsref_is_valid(void *p, const float *q, int64_t N, uint8_t *out) {
+    auto *h = static_cast<Harness *>(p);
+    for (int64_t i = 0; i < N; i++) out[i] = h->ss->isValid(state_of(*h, q + i * h->n)) ? 1 : 0;
+    return 0;
+}
+int rvsref_is_valid_edges(void *p, const float *q1, const float *q2, int64_t E, uint8_t *out) {
+    auto *h = static_cast<Harness *>(p);
+    for (int64_t i = 0; i < E; i++) out[i] = h->ss->isValid(state_of(*h, q1 + i * h->n), state_of(*h, q2 + i * h->n)) ? 1 : 0;
+    return 0;
+}
+// d_c[N], profile[N x L], nearest[N x M x L x 6] (zeros where the State holds nullptr), has_nearest[N], is_real[N]
+int rvsref_distance(void *p, const float *q, int64_t N, float *d_c, float *profile, float *nearest, uint8_t *has_nearest, uint8_t *is_real) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t L = size_t(h->n), M = h->env->getNumObjects();
+    for (int64_t i = 0; i < N; i++) {
+        auto s = state_of(*h, q + i * h->n);
+        d_c[i] = h->ss->computeDistance(s, false);
+        if (s->getDistance() != d_c[i]) return 2;
+        for (size_t l = 0; l < L; l++) profile[size_t(i) * L + l] = s->getDistanceProfile()[l];
+        const auto np = s->getNearestPoints();
+        has_nearest[i] = np ? 1 : 0;
+        is_real[i] = s->getIsRealDistance() ? 1 : 0;
+        if (nearest)
+            for (size_t j = 0; j < M; j++)
+                for (size_t l = 0; l < L; l++)
+                    for (int k = 0; k < 6; k++) nearest[((size_t(i) * M + j) * L + l) * 6 + k] = np ? (*np)[j](k, Eigen::Index(l)) : 0.f;
+    }
+    return 0;
+}
+// planes: M x L x 6 of ONE root.  status[i] = 1 when the reference returned 0 and left the state untouched (d_c stays -1).
+int rvsref_underestimation(void *p, const float *q, int64_t N, const float *planes, float *d_c, float *profile, uint8_t *status, uint8_t *is_real) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t L = size_t(h->n), M = h->env->getNumObjects();
+    auto np = std::make_shared<std::vector<Eigen::MatrixXf>>(M, Eigen::MatrixXf(6, Eigen::Index(L)));
+    for (size_t j = 0; j < M; j++)
+        for (size_t l = 0; l < L; l++)
+            for (int k = 0; k < 6; k++) (*np)[j](k, Eigen::Index(l)) = planes[(j * L + l) * 6 + size_t(k)];
+    for (int64_t i = 0; i < N; i++) {
+        auto s = state_of(*h, q + i * h->n);
+        d_c[i] = h->ss->computeDistanceUnderestimation(s, np);
+        const bool untouched = s->getDistance() == -1;
+        status[i] = untouched ? 1 : 0;
+        is_real[i] = s->getIsRealDistance() ? 1 : 0;
+        for (size_t l = 0; l < L; l++) profile[size_t(i) * L + l] = untouched ? 0.f : s->getDistanceProfile()[l];
+    }
+    return 0;
+}
+
+}  // extern "C"

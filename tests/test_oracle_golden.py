@@ -131,3 +131,86 @@ def test_distance_early_exit_fill_and_ground_rule(ob):
     o.set_obstacles(mn[:1], mx[:1], g[:1], tol[:1])
     _, p2, _ = o.distance(q[:20], robots.DIST_PROFILE)
     assert (p2[:, :2] == 1000.0).all()
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# The LOOPS of the hot path, pinned by the reference's own RealVectorSpace.cpp (compiled unmodified against oracle/eigen_shim +
+# oracle/env_shim; tests/golden/make_rvs_golden.py -> tests/golden/rvs_golden.npz): isValid(q), isValid(q1,q2), computeDistance (d_c,
+# profile with its first-collision fill, nearest points and their nullptr rule, is_real) and computeDistanceUnderestimation (values,
+# the reject rule, untouched states).  Skeletons come from the oracle's FK on both sides (KDL itself cannot be pinned here).
+# --------------------------------------------------------------------------------------------------------------------------------
+def _rvs_golden_module():
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_rvs_golden", os.path.join(ROOT, "tests", "golden", "make_rvs_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, dict(np.load(os.path.join(ROOT, "tests", "golden", "rvs_golden.npz")))
+
+
+def _check_space_against(space_factory, name, case, gold, exact=True):
+    from rpmplv2_b200 import robots
+    rb, mn, mx, g, tol, thr, N = case
+    mod, _ = _rvs_golden_module()
+    q, q1, q2 = mod.inputs(rb, N)
+    sp = space_factory(rb, robots.default_params(equality_threshold=thr))
+    sp.set_obstacles(mn, mx, g, tol)
+    G = lambda k: gold[f"{name}__{k}"]
+    assert np.array_equal(sp.is_valid(q).astype(np.uint8), G("valid")), name
+    assert np.array_equal(sp.is_valid_edges(q1, q2).astype(np.uint8), G("edge")), name
+    d, p, near = sp.distance(q, robots.DIST_FULL)
+    free = G("d") > 0
+    assert np.array_equal(G("has_near").astype(bool), free) and G("is_real").all()         # nullptr exactly after a collision
+    if exact:
+        assert np.array_equal(d, G("d")) and np.array_equal(p, G("prof")) and np.array_equal(near[free], G("near")[free]), name
+    else:
+        assert ((d == 0) == (G("d") == 0)).all() and np.abs(d - G("d")).max() <= 1e-4 and np.abs(p - G("prof")).max() <= 1e-4
+        assert np.abs(near[free] - G("near")[free]).max() <= 1e-4
+        assert (d != G("d")).mean() < 5e-3                                                   # bit-exact up to rare FK last-ulp effects
+    root = int(G("root"))
+    du, pu, st = sp.underestimation(q, np.ascontiguousarray(G("near")[root])[None], np.zeros(N, np.int32))
+    assert np.array_equal(st, G("un_status")), name
+    acc = G("un_status") == 0
+    assert not G("un_is_real")[acc].any()                                                    # accepted: is_real_d_c = false
+    if exact:
+        assert np.array_equal(du, G("un_d")) and np.array_equal(pu[acc], G("un_prof")[acc]), name
+    else:
+        assert np.abs(du - G("un_d")).max() <= 1e-4 and np.abs(pu[acc] - G("un_prof")[acc]).max() <= 1e-4
+    assert 0 < free.sum() < N and 0 < G("un_status").sum()
+
+
+def test_oracle_loops_match_the_reference_realvectorspace_golden(ob):
+    mod, gold = _rvs_golden_module()
+    for name, case in mod.cases().items():
+        _check_space_against(lambda rb, prm: ob.Oracle(rb, prm), name, case, gold, exact=True)
+
+
+def test_oracle_loops_match_the_compiled_reference_on_fresh_inputs(ob):
+    """The same comparison against oracle/_ref/librvs_ref.so itself on scenes that are not in the golden file (only where the
+    reference tree was available to build it)."""
+    import os
+    from conftest import ROOT
+    import scenes
+    so = os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref is built where /root/reference exists")
+    import ctypes
+    mod, _ = _rvs_golden_module()
+    lib = ctypes.CDLL(so)
+    from rpmplv2_b200 import robots
+    fresh = {"xarm6_m120": scenes.xarm6_scene(120, "D2", 0.3) + (1e-4, 150), "planar10": scenes.chain_scene(robots.planar(10), 8) + (1e-4, 150),
+             "spatial14": scenes.chain_scene(robots.spatial(14), 20) + (1e-5, 120)}
+    for name, case in fresh.items():
+        r = mod.run_reference(lib, *case)
+        gold = {f"{name}__{k}": v for k, v in r.items()}
+        _check_space_against(lambda rb, prm: ob.Oracle(rb, prm), name, case, gold, exact=True)
+
+
+@pytest.mark.gpu
+def test_gpu_engine_matches_the_reference_realvectorspace_golden():
+    """The CUDA engine (REF32) straight against the vectors of the compiled reference — not via the oracle."""
+    from rpmplv2_b200 import engine
+    mod, gold = _rvs_golden_module()
+    for name, case in mod.cases().items():
+        _check_space_against(lambda rb, prm: engine.Engine(rb, prm), name, case, gold, exact=False)
