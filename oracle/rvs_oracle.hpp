@@ -16,9 +16,12 @@
 //   * RealVectorSpace.cpp + State / StateSpace / Environment / Object / Box / AbstractRobot sources -> librvs_ref.so: the LOOPS
 //     (isValid(q), isValid(q1,q2), computeDistance with profile / nearest points / nullptr rule, computeDistanceUnderestimation),
 //     nine scenes, bit for bit (tests/test_oracle_golden.py, tests/golden/rvs_golden.npz);
+//   * RBTConnect.cpp / RGBTConnect.cpp (+ RRTConnect, AbstractPlanner, PlannerInfo, PlanningTypes, Tree, the *ConnectConfig sources)
+//     -> the same librvs_ref.so: extendSpine / extendGenSpine / extendGenSpine2, every layer, status and cached distance, bit for
+//     bit (tests/test_spines.py, tests/golden/spine_golden.npz);
 //   * Environment.cpp's motion laws                 -> libenv_ref.so (rvs_oracle_env.hpp).
-// Third-party arithmetic (Eigen reduction order, KDL FK, FCL AABB) is restated from published behaviour and stays "parity unpinned"
-// (SURVEY.md §8c, Q22-Q24); so do the bur spines, whose reference sources need the planner base classes.
+// Third-party arithmetic (Eigen reduction order, KDL FK and the robot classes' computeEnclosingRadii that sit on it, FCL AABB) is
+// restated from published behaviour / the robot sources and stays "parity unpinned" (SURVEY.md §8c, Q22-Q24).
 //
 // All `file:line` citations are relative to /root/reference/.
 // Build: g++ -O3 -std=c++17 -ffp-contract=off  (the reference is an x86-64 Release build without FMA).

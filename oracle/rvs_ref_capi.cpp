@@ -18,6 +18,9 @@
 #include "rvs_oracle.hpp"
 
 #include "RealVectorSpace.h"
+#define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
+#include "RGBTConnect.h"
+#undef protected
 
 namespace {
 
@@ -57,7 +60,18 @@ public:
         for (int k = 0; k <= chain.n; k++) { (*m)(0, k) = sk[size_t(k)].x; (*m)(1, k) = sk[size_t(k)].y; (*m)(2, k) = sk[size_t(k)].z; }
         return m;
     }
-    std::shared_ptr<Eigen::MatrixXf> computeEnclosingRadii(const std::shared_ptr<base::State> &) override { return nullptr; }
+    // the robot classes need KDL: the harness answers with the oracle's restatement of computeEnclosingRadii on the same skeleton
+    std::shared_ptr<Eigen::MatrixXf> computeEnclosingRadii(const std::shared_ptr<base::State> &q) override {
+        std::vector<orc::V3<float>> sk(size_t(chain.n + 1));
+        std::vector<float> qq(size_t(chain.n)), R(size_t(chain.n) * size_t(chain.n + 1));
+        for (int i = 0; i < chain.n; i++) qq[size_t(i)] = q->getCoord(i);
+        orc::skeleton(chain, qq.data(), sk.data());
+        orc::enclosing_radii(chain, sk.data(), R.data());
+        auto m = std::make_shared<Eigen::MatrixXf>(chain.n, chain.n + 1);
+        for (int i = 0; i < chain.n; i++)
+            for (int j = 0; j <= chain.n; j++) (*m)(i, j) = R[size_t(i) * size_t(chain.n + 1) + size_t(j)];
+        return m;
+    }
     bool checkSelfCollision(const std::shared_ptr<base::State> &, std::shared_ptr<base::State> &) override { return false; }
     bool checkSelfCollision(const std::shared_ptr<base::State> &) override { return false; }
 };
@@ -153,6 +167,46 @@ int rvsref_underestimation(void *p, const float *q, int64_t N, const float *plan
         status[i] = untouched ? 1 : 0;
         is_real[i] = s->getIsRealDistance() ? 1 : 0;
         for (size_t l = 0; l < L; l++) profile[size_t(i) * L + l] = untouched ? 0.f : s->getDistanceProfile()[l];
+    }
+    return 0;
+}
+
+
+// Bur spines (row f-1) through the reference's own planning::rbt::RBTConnect::extendSpine (RBTConnect.cpp:85-150) and
+// RGBTConnect::extendGenSpine / extendGenSpine2 (RGBTConnect.cpp:73-118, use_real_dist = false), compiled unmodified.
+// mode 0: extendSpine (one layer), 1: extendGenSpine (only the final state, written as layer 0), 2: extendGenSpine2 (every layer).
+// Every spine starts from a FRESH root state at q_roots[s] (computeDistance fills its profile and planes, as the planners do).
+// q_layers[S x num_layers x n], n_layers[S], d_last[S] (distance cached in the last state: underestimation or -1), status[S].
+int rvsref_extend_spines(void *p, const float *q_roots, const float *q_targets, int32_t S, int32_t num_layers, int32_t num_iter_spine,
+                         int32_t use_expanded_bubble, float d_crit, int32_t mode, float *q_layers, int32_t *n_layers, float *d_last, uint8_t *status) {
+    auto *h = static_cast<Harness *>(p);
+    RGBTConnectConfig::NUM_LAYERS = size_t(num_layers);
+    RBTConnectConfig::NUM_ITER_SPINE = size_t(num_iter_spine);
+    RBTConnectConfig::USE_EXPANDED_BUBBLE = use_expanded_bubble != 0;
+    RBTConnectConfig::D_CRIT = d_crit;
+    planning::rbt::RGBTConnect planner(h->ss);
+    const size_t n = size_t(h->n);
+    for (int32_t s = 0; s < S; s++) {
+        auto q = state_of(*h, q_roots + size_t(s) * n), q_e = state_of(*h, q_targets + size_t(s) * n);
+        h->ss->computeDistance(q, false);
+        std::vector<std::shared_ptr<base::State>> made;
+        base::State::Status st;
+        if (mode == 2) {
+            if (!(q->getDistance() > 0)) { n_layers[s] = 0; d_last[s] = q->getDistance(); status[s] = uint8_t(base::State::Status::Trapped); continue; }
+            std::shared_ptr<std::vector<std::shared_ptr<base::State>>> list;
+            std::tie(st, list) = planner.extendGenSpine2(q, q_e, false);
+            made = *list;
+        } else {
+            std::shared_ptr<base::State> q_new;
+            if (mode == 1) std::tie(st, q_new) = planner.extendGenSpine(q, q_e, false);
+            else std::tie(st, q_new) = planner.extendSpine(q, q_e);
+            made.push_back(q_new);
+        }
+        n_layers[s] = int32_t(made.size());
+        status[s] = uint8_t(st);
+        d_last[s] = made.back()->getDistance();
+        for (size_t l = 0; l < made.size(); l++)
+            for (size_t i = 0; i < n; i++) q_layers[(size_t(s) * size_t(num_layers) + l) * n + i] = made[l]->getCoord(int(i));
     }
     return 0;
 }

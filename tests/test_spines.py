@@ -213,3 +213,133 @@ def test_gpu_state_cache_distance_and_spines_vs_oracle(ob, case, iters, expanded
     with pytest.raises(engine.RvsError):
         eng.store_distance(q[:1], np.array([2 * R], np.int32))
     eng.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# The spines pinned by the reference's own RBTConnect::extendSpine / RGBTConnect::extendGenSpine / extendGenSpine2, compiled
+# unmodified (oracle/rvs_ref_capi.cpp, oracle/Makefile target `ref`; vectors: tests/golden/spine_golden.npz from
+# tests/golden/make_spine_golden.py).  Bit for bit: every layer's configuration, the number of layers, the status, and the distance
+# the last state carries.  Skeletons and enclosing radii come from the oracle's restatements on both sides (the robot classes need KDL).
+# --------------------------------------------------------------------------------------------------------------------------------
+def _spine_golden_module():
+    import importlib.util
+    import os
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    spec = importlib.util.spec_from_file_location("make_spine_golden", os.path.join(ROOT, "tests", "golden", "make_spine_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _oracle_spines(o, q_r, q_e, prm, mode):
+    layers, iters, expanded, d_crit = prm
+    d, p, near = o.distance(q_r, robots.DIST_FULL)
+    sp = robots.RvsSpineParams(1 if mode == 0 else layers, iters, expanded, d_crit)
+    return o.extend_spines_layers(q_r, p, d, near, np.arange(len(q_r), dtype=np.int32), q_e, sp, gen2=(mode == 2)), d
+
+
+def _compare_spines(got, d_root, want, mode, exact=True, tag=""):
+    (ql, nl, dl, st), (ql_w, nl_w, dl_w, st_w) = got, want
+    S = len(st_w)
+    trapped = ~(d_root > 0)
+    assert np.array_equal(st, st_w), tag
+    assert ((st_w == TRAPPED) == trapped).all(), tag                  # Trapped exactly for roots without clearance (self-collision off)
+    if mode == 2:
+        assert np.array_equal(nl[~trapped], nl_w[~trapped]), tag       # extendGenSpine2 is never called on such a root (RGBTConnect.cpp:33)
+        pairs = [(ql[s, :nl_w[s]], ql_w[s, :nl_w[s]]) for s in range(S) if not trapped[s]]
+    else:                                                              # only the final state comes back: it is layer 0 of the golden row
+        last = np.maximum(nl, 1) - 1
+        pairs = [(ql[np.arange(S), last], ql_w[:, 0])]
+    for a, b in pairs:
+        assert np.array_equal(a, b) if exact else np.abs(a - b).max() <= 1e-5, tag
+    if mode != 0:                                                      # the state extendSpine returns carries no distance yet
+        want_d = np.where(dl_w < 0, np.float32(0), dl_w)               # rejected underestimation: the reference returns 0, state keeps -1
+        live = ~trapped
+        assert np.array_equal(dl[live], want_d[live]) if exact else np.abs(dl[live] - want_d[live]).max() <= 1e-4, tag
+
+
+def test_oracle_spines_match_the_reference_planner_golden(ob):
+    import os
+    from conftest import ROOT
+    mod = _spine_golden_module()
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "spine_golden.npz")))
+    seen = np.zeros(4, np.int64)
+    for name, (rb, mn, mx, g, tol, thr, N) in mod.rvs.cases().items():
+        o = ob.Oracle(rb, robots.default_params(equality_threshold=thr))
+        o.set_obstacles(mn, mx, g, tol)
+        q, _, _ = mod.rvs.inputs(rb, N)
+        free = o.is_valid(q).astype(bool)
+        assert np.array_equal(free, gold[f"{name}__free"])
+        q_r, q_e = mod.spine_inputs(rb, N, free)
+        for pi, prm in enumerate(mod.PARAMS):
+            for mode in mod.MODES:
+                want = tuple(gold[f"{name}__p{pi}_m{mode}_{k}"] for k in ("q", "n", "d", "st"))
+                got, d_root = _oracle_spines(o, q_r, q_e, prm, mode)
+                _compare_spines(got, d_root, want, mode, exact=True, tag=f"{name} {prm} {mod.MODES[mode]}")
+                seen += np.bincount(want[3], minlength=4)[:4]
+    assert seen[ADVANCED] > 1000 and seen[REACHED] > 300 and seen[TRAPPED] > 10          # every status is exercised
+
+
+def test_oracle_spines_match_the_compiled_reference_on_fresh_inputs(ob):
+    """Same comparison against oracle/_ref/librvs_ref.so itself on scenes outside the golden file (where the reference tree was present)."""
+    import ctypes
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref is built where /root/reference exists")
+    lib = ctypes.CDLL(so)
+    if not hasattr(lib, "rvsref_extend_spines"):
+        pytest.skip("oracle/_ref/librvs_ref.so predates the spine harness")
+    mod = _spine_golden_module()
+    fresh = {"xarm6_m120": scenes.xarm6_scene(120, "D2", 0.3) + (1e-4, 150), "planar10": scenes.chain_scene(robots.planar(10), 8) + (1e-4, 150),
+             "spatial14": scenes.chain_scene(robots.spatial(14), 20) + (1e-5, 120)}
+    for name, (rb, mn, mx, g, tol, thr, N) in fresh.items():
+        h = mod.open_reference(lib, rb, mn, mx, g, tol, thr)
+        free = mod.reference_free(lib, h, rb, N)
+        q_r, q_e = mod.spine_inputs(rb, N, free)
+        o = ob.Oracle(rb, robots.default_params(equality_threshold=thr))
+        o.set_obstacles(mn, mx, g, tol)
+        for prm in mod.PARAMS + [(7, 3, 1, 0.01)]:
+            for mode in mod.MODES:
+                want = mod.run_reference_spines(lib, h, rb.num_dofs, q_r, q_e, prm, mode)
+                got, d_root = _oracle_spines(o, q_r, q_e, prm, mode)
+                _compare_spines(got, d_root, want, mode, exact=True, tag=f"{name} {prm} {mod.MODES[mode]}")
+        lib.rvsref_destroy(h)
+
+
+@pytest.mark.gpu
+def test_gpu_spines_match_the_reference_planner_golden():
+    """The CUDA engine (rvs_store_distance + rvs_store_extend_spines) straight against the compiled reference's vectors."""
+    import os
+    from conftest import ROOT
+    mod = _spine_golden_module()
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "spine_golden.npz")))
+    for name, (rb, mn, mx, g, tol, thr, N) in mod.rvs.cases().items():
+        eng = engine.Engine(rb, robots.default_params(equality_threshold=thr))
+        eng.set_obstacles(mn, mx, g, tol)
+        q_r, q_e = mod.spine_inputs(rb, N, gold[f"{name}__free"])
+        S = len(q_r)
+        eng.store_reserve(S)
+        slots = np.arange(S, dtype=np.int32)
+        d_root, _ = eng.store_distance(q_r, slots)
+        for pi, prm in enumerate(mod.PARAMS):
+            layers, iters, expanded, d_crit = prm
+            for mode in (1, 2):
+                want = tuple(gold[f"{name}__p{pi}_m{mode}_{k}"] for k in ("q", "n", "d", "st"))
+                got = eng.store_extend_spines(slots, q_e, robots.RvsSpineParams(layers, iters, expanded, d_crit), gen2=(mode == 2))
+                # a step that lands within an ulp of 1 can flip Advanced/Reached between FK evaluations that differ in the last bit
+                agree = got[3] == want[3]
+                if mode == 2:
+                    agree &= (got[1] == want[1]) | ~(d_root > 0)      # ... or a layer's distance within an ulp of D_CRIT
+                assert agree.mean() > 0.99, name
+                if not agree.all():
+                    keep = agree
+                    got = tuple(a[keep] for a in got)
+                    want = tuple(a[keep] for a in want)
+                    _compare_spines(got, d_root[keep], want, mode, exact=False, tag=f"{name} {prm} {mod.MODES[mode]}")
+                else:
+                    _compare_spines(got, d_root, want, mode, exact=False, tag=f"{name} {prm} {mod.MODES[mode]}")
+        eng.close()
