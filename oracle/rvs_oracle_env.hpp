@@ -10,7 +10,10 @@
 // own Environment.cpp / Object.cpp / objects/Box.cpp, compiled unmodified from /root/reference against oracle/eigen_shim plus
 // stand-ins for the slices of FCL and yaml-cpp they touch (oracle/env_shim, oracle/env_ref_capi.cpp, Makefile target `ref`):
 // positions, velocities, the two_tunnels bookkeeping and the AABBs agree bit for bit over all four laws, random restarts included
-// (tests/test_env.py; committed vectors: tests/golden/env_golden.npz from tests/golden/make_env_golden.py).  What stays "parity
+// (tests/test_env.py; committed vectors: tests/golden/env_golden.npz from tests/golden/make_env_golden.py).  MotionValidity::check is
+// pinned the same way: MotionValidity.cpp compiled unmodified on top of the reference's own Environment / RealVectorSpace
+// (oracle/rvs_ref_capi.cpp: rvsref_motion_run; tests/golden/motion_golden.npz) — runs of consecutive checks agree bit for bit in
+// verdicts, passed validity points and the obstacles' state after every check.  What stays "parity
 // unpinned" is third-party arithmetic: Eigen's reduction order (the shim encodes the same assumption) and FCL's
 // computeAABB (pos -/+ side/2).  Closed-form known answers are checked as well (straight-line motion, circular motion
 // spirals out by the Euler step, the reflection law preserves speed and keeps every obstacle inside the workspace shell).

@@ -1,12 +1,17 @@
-// rvs_ref_capi.cpp — C entry points around the REFERENCE's own base::RealVectorSpace (isValid(q), isValid(q1,q2), computeDistance,
-// computeDistanceUnderestimation), compiled from /root/reference/src/state_spaces/real_vector_space/RealVectorSpace.cpp (+ State.cpp,
-// StateSpace.cpp, RealVectorSpaceState.cpp, CollisionAndDistance.cpp, AbstractRobot.cpp, Environment.cpp, Object.cpp, Box.cpp),
-// unmodified and where they lie, against oracle/eigen_shim and oracle/env_shim.  TEST INFRASTRUCTURE ONLY (oracle/_ref/, git-ignored).
-//
-// What this pins: the LOOPS of the hot path — link / obstacle order, the ground rule, min_dist_tol, the first-collision exit and its
-// profile fill, nearest-point storage, the edge discretisation (k = N..1, float step), the underestimation's reject rule and state
-// side effects — on top of the already pinned capsule / box primitives.  What it cannot pin: the robot's forward kinematics (KDL) —
-// the harness robot answers computeSkeleton with the oracle's own FK restatement, so both sides see identical skeletons.
+// rvs_ref_capi.cpp — C entry points around the REFERENCE's own classes, compiled from /root/reference unmodified and where they lie,
+// against oracle/eigen_shim and oracle/env_shim.  TEST INFRASTRUCTURE ONLY (oracle/_ref/librvs_ref.so, git-ignored):
+//   * base::RealVectorSpace (isValid(q), isValid(q1,q2), computeDistance, computeDistanceUnderestimation) from RealVectorSpace.cpp
+//     (+ State.cpp, StateSpace.cpp, RealVectorSpaceState.cpp, CollisionAndDistance.cpp, AbstractRobot.cpp, Environment.cpp, Object.cpp,
+//     Box.cpp): pins the LOOPS of the hot path — link / obstacle order, the ground rule, min_dist_tol, the first-collision exit and
+//     its profile fill, nearest-point storage, the edge discretisation (k = N..1, float step), the underestimation's reject rule and
+//     state side effects — on top of the already pinned capsule / box primitives;
+//   * planning::rbt::RBTConnect::extendSpine and RGBTConnect::extendGenSpine / extendGenSpine2 from RBTConnect.cpp / RGBTConnect.cpp
+//     (+ RRTConnect, AbstractPlanner, PlannerInfo, PlanningTypes, Tree, the *ConnectConfig sources; nanoflann is a declarations-only
+//     stand-in, no kd-tree is ever built): pins the bur spines (row f-1);
+//   * planning::trajectory::MotionValidity::check(q_previous, q_current) from MotionValidity.cpp on the reference's own
+//     Environment::updateEnvironment: pins the dynamic-obstacle motion check (row f-2).
+// What it cannot pin: the robot's forward kinematics and enclosing radii (KDL) — the harness robot answers computeSkeleton and
+// computeEnclosingRadii with the oracle's own restatements, so both sides see identical skeletons and radii.
 #include <cstdint>
 #include <iostream>
 #include <memory>
@@ -17,7 +22,11 @@
 #include "../include/rvs_cuda.h"
 #include "rvs_oracle.hpp"
 
+#define private public                                         // env::Environment keeps WS_center / WS_radius / motion_type / sign / path_len private
+#include "Environment.h"
+#undef private
 #include "RealVectorSpace.h"
+#include "MotionValidity.h"
 #define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
 #include "RGBTConnect.h"
 #undef protected
@@ -207,6 +216,48 @@ int rvsref_extend_spines(void *p, const float *q_roots, const float *q_targets, 
         d_last[s] = made.back()->getDistance();
         for (size_t l = 0; l < made.size(); l++)
             for (size_t i = 0; i < n; i++) q_layers[(size_t(s) * size_t(num_layers) + l) * n + i] = made[l]->getCoord(int(i));
+    }
+    return 0;
+}
+
+
+// Row f-2 through the reference's own planning::trajectory::MotionValidity::check(q_previous, q_current) (MotionValidity.cpp:30-51),
+// compiled unmodified: T consecutive motions on ONE environment, as a DRGBT run makes them (every check advances the obstacles by the
+// updates it made before returning).  The environment's private parameters are set directly (the YAML reader is a stand-in).
+// Outputs: valid[T], passed[T] (validity points appended to `path` by that check), pos_after / vel_after [T x M x 3].
+int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radius, base_radius, robot_max_vel*/, int32_t motion_type, int32_t M,
+                      const float *dim, const float *pos, const float *vel, const float *max_vel, const uint8_t *dynamic, const uint8_t *ground,
+                      const float *tol, const float *q_prev, const float *q_cur, int32_t T, int32_t K, float max_iter_time, uint8_t *valid,
+                      int32_t *passed, float *pos_after, float *vel_after) {
+    auto *h = static_cast<Harness *>(p);
+    auto &e = *h->env;
+    e.removeAllObjects();
+    e.WS_center = fcl::Vector3f(env_params[0], env_params[1], env_params[2]);
+    e.WS_radius = env_params[3];
+    e.setBaseRadius(env_params[4]);
+    e.setRobotMaxVel(env_params[5]);
+    e.motion_type = static_cast<decltype(e.motion_type)>(motion_type);
+    e.sign = Eigen::VectorXi::Ones(M);
+    e.path_len = Eigen::VectorXf::Zero(M);
+    for (int j = 0; j < M; j++) {
+        auto obj = std::make_shared<env::Box>(fcl::Vector3f(dim[3 * j], dim[3 * j + 1], dim[3 * j + 2]), fcl::Vector3f(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]),
+                                              fcl::Quaternionf::Identity(), ground[j] ? "ground" : (dynamic[j] ? "dynamic_obstacle" : ""));
+        obj->setMaxVel(max_vel[j]);
+        obj->setMinDistTol(tol[j]);
+        e.addObject(obj, fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
+    }
+    std::vector<std::shared_ptr<base::State>> path;
+    planning::trajectory::MotionValidity mv(h->ss, 0.01f, max_iter_time, &path);
+    TrajectoryConfig::NUM_VALIDITY_POINTS_CHECK = size_t(K);       // the constructor derives it from the obstacles' max_vel; the test fixes it
+    for (int32_t t = 0; t < T; t++) {
+        const size_t before = path.size();
+        valid[t] = mv.check(state_of(*h, q_prev + size_t(t) * size_t(h->n)), state_of(*h, q_cur + size_t(t) * size_t(h->n))) ? 1 : 0;
+        passed[t] = int32_t(path.size() - before);
+        for (int j = 0; j < M; j++)
+            for (int c = 0; c < 3; c++) {
+                pos_after[(size_t(t) * size_t(M) + size_t(j)) * 3 + size_t(c)] = e.getObject(size_t(j))->getPosition()(c);
+                vel_after[(size_t(t) * size_t(M) + size_t(j)) * 3 + size_t(c)] = e.getObject(size_t(j))->getVelocity()(c);
+            }
     }
     return 0;
 }

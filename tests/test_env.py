@@ -311,3 +311,79 @@ def test_oracle_motion_laws_match_the_compiled_reference_step_by_step(ob):
             pos, vel = o.env_get()
             assert np.array_equal(pos, state[0]) and np.array_equal(vel, state[1]), law
             assert np.array_equal(o._env["sign"], state[2]) and np.array_equal(o._env["path_len"], state[3]), law
+
+
+# ---------------------------------------------- pinned by the reference's own MotionValidity.cpp on its own Environment / RealVectorSpace
+def _motion_golden():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_motion_golden", os.path.join(ROOT, "tests", "golden", "make_motion_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _run_motions(space, mod, law, sc, q1, q2, K, mit):
+    """T committed checks on one environment through a space with the engine's env_set / motion_validity / env_get methods."""
+    space.env_set(env_params(law, **mod.ENV), **sc)
+    dt = mod.delta_time(K, mit)
+    T = len(q1)
+    out = dict(valid=np.zeros(T, np.uint8), passed=np.zeros(T, np.int32), pos=[], vel=[])
+    for t in range(T):
+        v, first = space.motion_validity(q1[t:t + 1], q2[t:t + 1], K, dt, commit_edge=0)
+        out["valid"][t] = 1 if v[0] else 0
+        out["passed"][t] = K if v[0] else first[0] - 1                   # `path` receives the points that passed before the failing one
+        pos, vel = space.env_get()
+        out["pos"].append(pos)
+        out["vel"].append(vel)
+    out["pos"], out["vel"] = np.stack(out["pos"]), np.stack(out["vel"])
+    return out
+
+
+def _compare_motion_run(got, want, tag, pos_tol=0.0):
+    assert np.array_equal(got["valid"], want["valid"]) and np.array_equal(got["passed"], want["passed"]), tag
+    for k in ("pos", "vel"):
+        assert np.array_equal(got[k], want[k]) if pos_tol == 0 else np.abs(got[k] - want[k]).max() <= pos_tol, (tag, k)
+
+
+def test_oracle_motion_check_matches_the_reference_motionvalidity_golden(ob):
+    """oracle (env_update + motion_point + is_valid, commit semantics) against runs of the reference's MotionValidity::check compiled
+    unmodified (tests/golden/make_motion_golden.py): verdicts, the number of validity points that passed, and the obstacles'
+    positions / velocities after every check — bit for bit."""
+    mod = _motion_golden()
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "motion_golden.npz"))
+    n_valid = n_all = 0
+    for k, (robot, M_dyn, law, T, K, mit) in enumerate(mod.CASES):
+        rb, sc, q1, q2 = mod.case_inputs(robot, M_dyn, law, T)
+        got = _run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit)
+        _compare_motion_run(got, {n: gold[f"c{k}_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K))
+        n_valid, n_all = n_valid + int(got["valid"].sum()), n_all + T
+    assert 0.2 < n_valid / n_all < 0.8
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so")), reason="oracle/_ref is built where /root/reference exists")
+def test_oracle_motion_check_matches_the_compiled_reference_on_fresh_runs(ob):
+    import ctypes
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    if not hasattr(lib, "rvsref_motion_run"):
+        pytest.skip("oracle/_ref/librvs_ref.so predates the MotionValidity harness")
+    mod = _motion_golden()
+    for robot, M_dyn, law, T, K, mit, seed in [("xarm6", 20, "light_directions", 80, 5, 0.03, 3), ("xarm6", 6, "two_tunnels", 80, 12, 0.1, 4),
+                                               ("spatial22", 9, "circular", 50, 10, 0.05, 5), ("planar10", 6, "straight", 50, 3, 0.04, 6)]:
+        rb, sc, q1, q2 = mod.case_inputs(robot, M_dyn, law, T, seed=seed)
+        want = mod.run_reference(lib, rb, sc, law, q1, q2, K, mit)
+        _compare_motion_run(_run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit), want, (robot, law, K))
+
+
+@pytest.mark.gpu
+def test_gpu_motion_check_matches_the_reference_motionvalidity_golden():
+    """rvs_env_set + rvs_motion_validity (commit) + rvs_env_get straight against the compiled reference's runs.  The circular law goes
+    through atan2f / sinf / cosf (last-ulp differences between CUDA and glibc): positions within 1e-5 m there, bit for bit elsewhere."""
+    from rpmplv2_b200.engine import Engine
+    mod = _motion_golden()
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "motion_golden.npz"))
+    for k, (robot, M_dyn, law, T, K, mit) in enumerate(mod.CASES):
+        rb, sc, q1, q2 = mod.case_inputs(robot, M_dyn, law, T)
+        eng = Engine(rb)
+        got = _run_motions(eng, mod, law, sc, q1, q2, K, mit)
+        _compare_motion_run(got, {n: gold[f"c{k}_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K), pos_tol=1e-5 if law == "circular" else 0.0)
+        eng.close()
