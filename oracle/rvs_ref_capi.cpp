@@ -262,4 +262,48 @@ int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radiu
     return 0;
 }
 
+
+// Row f-3 through the reference's own planners: ONE run of RRTConnect / RBTConnect / RGBTConnect::solve() (kind 0 / 1 / 2) on the
+// harness scene after srand(seed) — Eigen::VectorXf::Random (here: the work-alike's, one std::rand() per coefficient) is the planners'
+// only source of randomness, so a planner that draws from the same stream can be compared state by state.  base::Tree's kd-tree is the
+// exhaustive stand-in of env_shim/nanoflann.hpp (exact nearest neighbour, like nanoflann).
+// Returns 0, or 2 when the constructor throws (start / goal invalid).  path: path_len x n (truncated to max_path rows).
+int rvsref_plan(void *p, int32_t kind, const float *q_start, const float *q_goal, uint32_t seed, int64_t max_num_iter, int64_t max_num_states,
+                float max_planning_time, float eps_step, int32_t max_extension_steps, float delta, int32_t num_spines, int32_t num_layers,
+                int32_t num_iter_spine, int32_t use_expanded_bubble, float d_crit, int32_t *success, int64_t *iterations, int64_t *states,
+                int32_t *path_len, float *path, int32_t max_path, int64_t *tree_sizes) {
+    auto *h = static_cast<Harness *>(p);
+    RRTConnectConfig::MAX_NUM_ITER = RBTConnectConfig::MAX_NUM_ITER = RGBTConnectConfig::MAX_NUM_ITER = size_t(max_num_iter);
+    RRTConnectConfig::MAX_NUM_STATES = RBTConnectConfig::MAX_NUM_STATES = RGBTConnectConfig::MAX_NUM_STATES = size_t(max_num_states);
+    RRTConnectConfig::MAX_PLANNING_TIME = RBTConnectConfig::MAX_PLANNING_TIME = RGBTConnectConfig::MAX_PLANNING_TIME = max_planning_time;
+    RRTConnectConfig::EPS_STEP = eps_step;
+    RRTConnectConfig::MAX_EXTENSION_STEPS = size_t(max_extension_steps);
+    RBTConnectConfig::DELTA = delta;
+    RBTConnectConfig::NUM_SPINES = size_t(num_spines);
+    RBTConnectConfig::NUM_ITER_SPINE = size_t(num_iter_spine);
+    RBTConnectConfig::USE_EXPANDED_BUBBLE = use_expanded_bubble != 0;
+    RBTConnectConfig::D_CRIT = d_crit;
+    RGBTConnectConfig::NUM_LAYERS = size_t(num_layers);
+    std::srand(seed);
+    std::unique_ptr<planning::rrt::RRTConnect> planner;
+    try {
+        auto qs = state_of(*h, q_start), qg = state_of(*h, q_goal);
+        if (kind == 0) planner = std::make_unique<planning::rrt::RRTConnect>(h->ss, qs, qg);
+        else if (kind == 1) planner = std::make_unique<planning::rbt::RBTConnect>(h->ss, qs, qg);
+        else planner = std::make_unique<planning::rbt::RGBTConnect>(h->ss, qs, qg);
+    } catch (const std::domain_error &) {
+        return 2;
+    }
+    *success = planner->solve() ? 1 : 0;
+    *iterations = int64_t(planner->getPlannerInfo()->getNumIterations());
+    *states = int64_t(planner->getPlannerInfo()->getNumStates());
+    const auto &pth = planner->getPath();
+    *path_len = *success ? int32_t(pth.size()) : 0;
+    for (int32_t k = 0; k < *path_len && k < max_path; k++)
+        for (int i = 0; i < h->n; i++) path[size_t(k) * size_t(h->n) + size_t(i)] = pth[size_t(k)]->getCoord(i);
+    tree_sizes[0] = int64_t(planner->trees[0]->getNumStates());      // (getTree() returns a copy whose destructor clears the shared state list)
+    tree_sizes[1] = int64_t(planner->trees[1]->getNumStates());
+    return 0;
+}
+
 }  // extern "C"

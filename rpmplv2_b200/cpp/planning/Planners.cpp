@@ -25,21 +25,58 @@ namespace rvsplan
 			return x ^ (x >> 31);
 		}
 
+		// RVS_PLAN_RNG=libc: draw from std::rand() exactly as Eigen::VectorXf::Random does (one call per coefficient, in index order),
+		// so that a SINGLE run (P = 1, after srand(seed)) consumes the reference's own random stream and can be compared with
+		// RRTConnect/RBTConnect/RGBTConnect::solve() state by state (tests/test_planners.py).  Not meaningful for P > 1.
+		inline bool libcStream()
+		{
+			const char *e = std::getenv("RVS_PLAN_RNG");          // read per run: a test switches it on for single runs only
+			return e && std::string(e) == "libc";
+		}
+
 		struct Rng                       // counter based: value k of run `seed` is a pure function of (seed, k)
 		{
 			uint64_t seed = 0, counter = 0;
+			bool libc = false;
 			float uniform()              // [-1, 1) like Eigen::VectorXf::Random
 			{
+				if (libc) return 2.0f * float(std::rand()) / float(RAND_MAX) - 1.0f;
 				const uint64_t h = splitmix64(seed ^ (0xD1B54A32D192ED03ull * ++counter));
 				return float(h >> 40) * (2.0f / 16777216.0f) - 1.0f;
 			}
 		};
 
-		inline float norm(const float *a, const float *b, int n)        // RealVectorSpace::getNorm (:47-50)
+		// RealVectorSpace::getNorm (:47-50): (q1 - q2).norm() of a dynamic VectorXf, summed in Eigen's linear-vectorised order (packets of
+		// 4, two accumulators, (l0 + l2) + (l1 + l3), scalar tail) — the same order as coord_norm in csrc/rvs_kernels.cuh, so that the
+		// host's interpolation fractions and the device's edge discretisation see the same distance
+		inline float norm(const float *a, const float *b, int n)
 		{
-			float s = 0.f;
-			for (int i = 0; i < n; i++) { const float d = a[i] - b[i]; s += d * d; }
-			return std::sqrt(s);
+			float sq[64] = {};                                               // RVS_MAX_DOFS is 32
+			for (int i = 0; i < n; i++) { const float d = a[i] - b[i]; sq[i] = d * d; }
+			const int aligned = (n / 4) * 4, aligned2 = (n / 8) * 8;
+			float res;
+			if (aligned)
+			{
+				float p0[4], p1[4];
+				for (int l = 0; l < 4; l++) p0[l] = sq[l];
+				if (aligned > 4)
+				{
+					for (int l = 0; l < 4; l++) p1[l] = sq[4 + l];
+					for (int k = 8; k < aligned2; k += 8)
+						for (int l = 0; l < 4; l++) { p0[l] = p0[l] + sq[k + l]; p1[l] = p1[l] + sq[k + 4 + l]; }
+					for (int l = 0; l < 4; l++) p0[l] = p0[l] + p1[l];
+					if (aligned > aligned2)
+						for (int l = 0; l < 4; l++) p0[l] = p0[l] + sq[aligned2 + l];
+				}
+				res = (p0[0] + p0[2]) + (p0[1] + p0[3]);
+				for (int i = aligned; i < n; i++) res = res + sq[i];
+			}
+			else
+			{
+				res = sq[0];
+				for (int i = 1; i < n; i++) res = res + sq[i];
+			}
+			return std::sqrt(res);
 		}
 	}
 
@@ -79,6 +116,7 @@ namespace rvsplan
 			  q_goal(q_goal_, q_goal_ + space.numDofs()), t0(t0_), skip_invalid(skip_invalid_)
 		{
 			rng.seed = splitmix64(seed);
+			if (libcStream()) { rng.libc = true; std::srand(unsigned(seed)); }
 			if (cfg.kind == PlannerKind::RBTConnect) cfg.spine.num_layers = 1;     // a bur spine is a one-layer generalized spine
 		}
 

@@ -117,3 +117,102 @@ def test_gpu_planner_pool_scales_in_rounds_not_runs():
     assert st64["backend_calls"] < 0.1 * sum(r["rounds"] for r in res64)
     assert st1["backend_calls"] == res1[0]["rounds"]
     eng.close()
+
+
+# --------------------------------------------------------------------------------------------------------------------------------
+# Row f-3 pinned by the reference's own planners: RRTConnect / RBTConnect / RGBTConnect::solve() compiled unmodified on top of the
+# reference's own Tree and RealVectorSpace (oracle/rvs_ref_capi.cpp: rvsref_plan; tests/golden/make_plan_golden.py ->
+# tests/golden/plan_golden.npz).  With RVS_PLAN_RNG=libc a single run of rpmplv2_b200/cpp/planning draws from the same std::rand()
+# stream as Eigen::VectorXf::Random does in the work-alike, and must then reproduce the reference run: success, iterations, number of
+# states, and the path bit for bit.
+# --------------------------------------------------------------------------------------------------------------------------------
+def _plan_golden():
+    import importlib.util
+    import os
+    from conftest import ROOT
+    spec = importlib.util.spec_from_file_location("make_plan_golden", os.path.join(ROOT, "tests", "golden", "make_plan_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, dict(np.load(os.path.join(ROOT, "tests", "golden", "plan_golden.npz")))
+
+
+def _same_run(r, counts, path, exact=True):
+    if not (r["success"] == bool(counts[0]) and r["iterations"] == counts[1] and r["states"] == counts[2] and r["path_len"] == len(path)):
+        return False
+    return np.array_equal(r["path"], path) if exact else bool(np.abs(r["path"] - path).max() <= 1e-4)
+
+
+def test_oracle_backed_planners_reproduce_the_reference_planner_runs(ob, monkeypatch):
+    mod, gold = _plan_golden()
+    monkeypatch.setenv("RVS_PLAN_RNG", "libc")
+    for name in mod.SCENARIOS:
+        o, _, qs, qg = _oracle(ob, name)
+        for kind in mod.KINDS:
+            for seed in mod.SEEDS:
+                res, _ = ob.plan_solve_batch(o, mod.config(kind), qs, qg, seeds=[seed], max_path=mod.MAX_PATH)
+                counts, path = gold[f"{name}_k{kind}_s{seed}_counts"], gold[f"{name}_k{kind}_s{seed}_path"]
+                assert counts[0] == 1 and counts[3] + counts[4] == counts[2]
+                assert _same_run(res[0], counts, path), (name, kind, seed, res[0]["iterations"], counts)
+    # without the switch the planners use their own counter-based stream: a different (still valid) run
+    monkeypatch.delenv("RVS_PLAN_RNG")
+    o, _, qs, qg = _oracle(ob, "xarm6")
+    res, _ = ob.plan_solve_batch(o, mod.config(planning.RGBT_CONNECT), qs, qg, seeds=[1], max_path=mod.MAX_PATH)
+    assert res[0]["success"] and not _same_run(res[0], gold["xarm6_k2_s1_counts"], gold["xarm6_k2_s1_path"])
+
+
+def test_oracle_backed_planners_reproduce_the_compiled_reference_on_fresh_runs(ob, monkeypatch):
+    """Same comparison against oracle/_ref/librvs_ref.so itself: other seeds and non-default parameters (plain bubble, 3 spine
+    iterations, 3 layers, a coarser EPS_STEP), and the invalid-start rule."""
+    import ctypes
+    import os
+    from conftest import ROOT
+    so = os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so")
+    if not os.path.exists(so):
+        pytest.skip("oracle/_ref is built where /root/reference exists")
+    lib = ctypes.CDLL(so)
+    if not hasattr(lib, "rvsref_plan"):
+        pytest.skip("oracle/_ref/librvs_ref.so predates the planner harness")
+    mod, _ = _plan_golden()
+    monkeypatch.setenv("RVS_PLAN_RNG", "libc")
+    variants = [dict(), dict(eps_step=0.25, max_extension_steps=10, num_spines=3, delta=1.5,
+                             spine=robots.RvsSpineParams(3, 3, 0, 0.03))]
+    for name in mod.SCENARIOS:
+        h, rb, qs, qg = mod.open_reference(lib, name)
+        o, _, _, _ = _oracle(ob, name)
+        for kind in mod.KINDS:
+            for vi, over in enumerate(variants):
+                cfg = mod.config(kind, **over)
+                for seed in (11 + vi, 29 + vi):
+                    want = mod.run_reference(lib, h, rb.num_dofs, cfg, qs, qg, seed)
+                    res, _ = ob.plan_solve_batch(o, cfg, qs, qg, seeds=[seed], max_path=mod.MAX_PATH)
+                    counts = (want["success"], want["iterations"], want["states"])
+                    assert _same_run(res[0], counts, want["path"]), (name, kind, vi, seed, res[0]["iterations"], counts)
+        if name == "xarm6":
+            bad = np.array([0, 1.5, 0, 0, 0, 0], np.float32)                     # arm through the table
+            assert mod.run_reference(lib, h, rb.num_dofs, mod.config(planning.RRT_CONNECT), bad, qg, 1)["invalid_ends"]
+            res, _ = ob.plan_solve_batch(o, mod.config(planning.RRT_CONNECT), bad, qg, seeds=[1])
+            assert res[0]["invalid_ends"] and not res[0]["success"]
+        lib.rvsref_destroy(h)
+
+
+@pytest.mark.gpu
+def test_gpu_backed_planners_reproduce_the_reference_planner_runs(monkeypatch):
+    """The planners on the CUDA backend against the compiled reference's runs.  A device FK that differs from the host's in the last
+    ulp can flip one verdict in a run of thousands of queries; such a run diverges into another valid run, so a few are tolerated."""
+    mod, gold = _plan_golden()
+    monkeypatch.setenv("RVS_PLAN_RNG", "libc")
+    same = total = 0
+    for name in mod.SCENARIOS:
+        fn, qs, qg = SCENARIOS[name]
+        rb, mn, mx, g, tol = fn()
+        eng = engine.Engine(rb)
+        eng.set_obstacles(mn, mx, g, tol)
+        qs, qg = np.asarray(qs, np.float32), np.asarray(qg, np.float32)
+        for kind in mod.KINDS:
+            for seed in mod.SEEDS:
+                res, _ = planning.solve_batch(eng, mod.config(kind), qs, qg, seeds=[seed], max_path=mod.MAX_PATH)
+                assert res[0]["success"]
+                same += _same_run(res[0], gold[f"{name}_k{kind}_s{seed}_counts"], gold[f"{name}_k{kind}_s{seed}_path"], exact=False)
+                total += 1
+        eng.close()
+    assert same >= total - 4, (same, total)
