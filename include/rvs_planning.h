@@ -9,6 +9,12 @@
  *   the repetition loop of the test apps  apps/test_rgbtconnect.cpp (scenario `testing: max_num` runs of one scenario)
  * Configuration values are those of data/configurations/configuration_{rrtconnect,rbtconnect,rgbtconnect}.yaml.
  * Plain C: pointers and sizes only, status ints, no exception crosses the boundary.
+ *
+ * Environment switches (read per call): RVS_PLAN_THREADS = host threads that resume the runs between backend calls;
+ * RVS_PLAN_RNG=libc = draw random states from std::rand() after srand(seed), one call per coordinate like Eigen::VectorXf::Random —
+ * a SINGLE run (P = 1) then follows the reference planner's own random stream and reproduces its run state by state
+ * (tests/test_planners.py checks exactly that against the reference's compiled solve() loops). Default: a counter-based stream
+ * per run, independent of P and of the thread schedule.
  */
 #ifndef RVS_PLANNING_H
 #define RVS_PLANNING_H

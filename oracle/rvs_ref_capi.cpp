@@ -6,8 +6,10 @@
 //     its profile fill, nearest-point storage, the edge discretisation (k = N..1, float step), the underestimation's reject rule and
 //     state side effects — on top of the already pinned capsule / box primitives;
 //   * planning::rbt::RBTConnect::extendSpine and RGBTConnect::extendGenSpine / extendGenSpine2 from RBTConnect.cpp / RGBTConnect.cpp
-//     (+ RRTConnect, AbstractPlanner, PlannerInfo, PlanningTypes, Tree, the *ConnectConfig sources; nanoflann is a declarations-only
-//     stand-in, no kd-tree is ever built): pins the bur spines (row f-1);
+//     (+ RRTConnect, AbstractPlanner, PlannerInfo, PlanningTypes, Tree, the *ConnectConfig sources; nanoflann is an exhaustive
+//     exact-nearest-neighbour stand-in): pins the bur spines (row f-1);
+//   * RRTConnect / RBTConnect / RGBTConnect::solve() themselves, one run per srand(seed): pins the planners of
+//     rpmplv2_b200/cpp/planning run by run (rows f-3 / f-4);
 //   * planning::trajectory::MotionValidity::check(q_previous, q_current) from MotionValidity.cpp on the reference's own
 //     Environment::updateEnvironment: pins the dynamic-obstacle motion check (row f-2).
 // What it cannot pin: the robot's forward kinematics and enclosing radii (KDL) — the harness robot answers computeSkeleton and
