@@ -12,6 +12,10 @@
 //     rpmplv2_b200/cpp/planning run by run (rows f-3 / f-4);
 //   * planning::trajectory::MotionValidity::check(q_previous, q_current) from MotionValidity.cpp on the reference's own
 //     Environment::updateEnvironment: pins the dynamic-obstacle motion check (row f-2).
+// Built a second time with -DRVS_DROPIN (oracle/_ref/libdropin_ref.so, linked against rpmplv2_b200/librvs_cuda.so): the harness then
+// constructs base::RealVectorSpaceCUDA (rpmplv2_b200/cpp, compiled here against the reference's REAL headers) instead of
+// base::RealVectorSpace, and the reference's own planners / loops run over the CUDA engine through base::StateSpace's virtual
+// interface — the drop-in itself, checked on the GPU box against the golden vectors of the CPU build (tests/test_dropin.py).
 // What it cannot pin: the robot's forward kinematics and enclosing radii (KDL) — the harness robot answers computeSkeleton and
 // computeEnclosingRadii with the oracle's own restatements, so both sides see identical skeletons and radii.
 #include <cstdint>
@@ -28,6 +32,9 @@
 #include "Environment.h"
 #undef private
 #include "RealVectorSpace.h"
+#ifdef RVS_DROPIN                                              // the same harness with the CUDA state space under the reference's planners
+#include "RealVectorSpaceCUDA.h"
+#endif
 #include "MotionValidity.h"
 #define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
 #include "RGBTConnect.h"
@@ -116,7 +123,17 @@ void *rvsref_create(const rvs_robot_desc *rd, float eq_thr, float max_dist, int3
     std::cout.rdbuf(sink.rdbuf());                              // the YAML constructor reports the (stubbed, empty) file
     h->env = std::make_shared<env::Environment>(std::string("unused.yaml"), std::string(""));
     std::cout.rdbuf(keep);
+#ifdef RVS_DROPIN
+    try {
+        h->ss = std::make_shared<base::RealVectorSpaceCUDA>(size_t(h->n), h->robot, h->env, *rd);
+    } catch (const std::exception &e) {
+        std::cerr << "rvsref_create (drop-in): " << e.what() << std::endl;
+        delete h;
+        return nullptr;
+    }
+#else
     h->ss = std::make_shared<base::RealVectorSpace>(size_t(h->n), h->robot, h->env);
+#endif
     return h;
 }
 void rvsref_destroy(void *p) { delete static_cast<Harness *>(p); }
@@ -131,6 +148,9 @@ int rvsref_set_obstacles(void *p, const float *mn, const float *mx, const uint8_
         if (tol) obj->setMinDistTol(tol[j]);
         h->env->addObject(obj);
     }
+#ifdef RVS_DROPIN
+    static_cast<base::RealVectorSpaceCUDA *>(h->ss.get())->refreshObstacles();
+#endif
     return 0;
 }
 

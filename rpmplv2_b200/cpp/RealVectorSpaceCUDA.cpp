@@ -8,6 +8,12 @@
 #include "RealVectorSpaceConfig.h"
 #include "rvs_urdf.h"
 
+// base::StateSpaceType::RealVectorSpaceCUDA is the enum value INTEGRATION.md adds to include/state_spaces/StateSpaceType.h.  A build
+// against an UNPATCHED reference tree (oracle/Makefile: _ref/libdropin_ref.so) passes -DRVS_STATE_SPACE_TYPE=base::StateSpaceType::RealVectorSpace.
+#ifndef RVS_STATE_SPACE_TYPE
+#define RVS_STATE_SPACE_TYPE base::StateSpaceType::RealVectorSpaceCUDA
+#endif
+
 namespace
 {
 	rvs_params currentParams(rvs_precision precision)
@@ -41,7 +47,7 @@ base::RealVectorSpaceCUDA::RealVectorSpaceCUDA(size_t num_dimensions_, const std
 
 void base::RealVectorSpaceCUDA::create(const rvs_robot_desc &chain, int device, rvs_precision precision)
 {
-	setStateSpaceType(base::StateSpaceType::RealVectorSpaceCUDA);
+	setStateSpaceType(RVS_STATE_SPACE_TYPE);
 	if (precision == RVS_PREC_F64)
 		throw std::runtime_error("RealVectorSpaceCUDA: base::State stores float distances; use RVS_PREC_REF32 or RVS_PREC_FAST32");
 	if (size_t(chain.num_dofs) != robot->getNumDOFs() || size_t(chain.num_dofs) != num_dimensions)
@@ -98,7 +104,7 @@ void base::RealVectorSpaceCUDA::refreshObstacles()
 	{
 		if (env->getCollObject(j)->getNodeType() != fcl::GEOM_BOX)
 			throw std::runtime_error("RealVectorSpaceCUDA: only box obstacles are supported (the reference's sphere branch is a TODO stub)");
-		const fcl::AABB &AABB { env->getCollObject(j)->getAABB() };
+		const auto &AABB { env->getCollObject(j)->getAABB() };        // fcl::AABB<float> with the real FCL
 		for (int k = 0; k < 3; k++)
 		{
 			aabb_min[3 * j + k] = AABB.min_[k];
@@ -120,7 +126,7 @@ void base::RealVectorSpaceCUDA::attachDynamicEnvironment(rvs_motion_type motion_
 	{
 		if (env->getCollObject(j)->getNodeType() != fcl::GEOM_BOX)
 			throw std::runtime_error("RealVectorSpaceCUDA: only box obstacles are supported (the reference's sphere branch is a TODO stub)");
-		const fcl::AABB &AABB { env->getCollObject(j)->getAABB() };
+		const auto &AABB { env->getCollObject(j)->getAABB() };        // fcl::AABB<float> with the real FCL
 		const std::shared_ptr<env::Object> object { env->getObject(j) };
 		for (int k = 0; k < 3; k++)
 		{
