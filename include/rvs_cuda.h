@@ -33,6 +33,8 @@
  *   rvs_env_get                          (src/environments/Environment.cpp:194-377), env::Object::setPosition (Object.cpp:21-26)
  *   rvs_motion_validity               <- planning::trajectory::MotionValidity::check(q_previous, q_current)
  *                                        (src/planners/trajectory/MotionValidity.cpp:30-51), obstacles moving on the device
+ *   rvs_motion_validity_points        <- MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-82): the validity
+ *                                        points come from the caller's spline / Ruckig trajectory instead of an interpolated edge
  *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
  *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
  *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
@@ -262,6 +264,10 @@ int  rvs_env_get(rvs_handle h, float *pos, float *vel);
  * (what-if queries for many candidate motions).  Self-collision (xArm6 meshes, FCL) is not part of this check. */
 int  rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float delta_time,
                          int32_t commit_edge, uint8_t *valid, int32_t *first_invalid);
+/* MotionValidity::check(traj_points_current_iter) for E candidate trajectories of K points each (points: E x K x num_dofs): point k
+ * is tested, as it is, against the environment after k updates of delta_time.  Same outputs and commit rule as above. */
+int  rvs_motion_validity_points(rvs_handle h, const float *points, int64_t E, int32_t K, float delta_time,
+                                int32_t commit_edge, uint8_t *valid, int32_t *first_invalid);
 
 /* Batched geometric primitives on K independent (capsule, box) pairs, host pointers.
  * AB: K x 6 (A xyz, B xyz); radius: K; obs: K x 6 (x_min,y_min,z_min,x_max,y_max,z_max).

@@ -133,6 +133,19 @@ class Oracle:
             raise RuntimeError(f"orc_motion_validity rc={rc}")
         return valid.astype(bool), first
 
+    def motion_validity_points(self, points, delta_time: float, commit_edge: int = -1):
+        points = np.ascontiguousarray(points, np.float32)
+        if points.ndim == 2:
+            points = points[None]
+        E, K, _ = points.shape
+        valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        prm, args = self._env_args()
+        rc = lib().orc_motion_validity_points(self._h, _p(prm, c_f32p), *args, _p(points, c_f32p), ctypes.c_int64(E), ctypes.c_int32(K),
+                                              ctypes.c_float(delta_time), ctypes.c_int32(commit_edge), _p(valid, c_u8p), _p(first, c_i32p))
+        if rc:
+            raise RuntimeError(f"orc_motion_validity_points rc={rc}")
+        return valid.astype(bool), first
+
     def skeleton(self, q, f64=False):
         q = _f32(q, (-1, self.n))
         N = q.shape[0]

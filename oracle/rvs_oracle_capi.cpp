@@ -308,9 +308,10 @@ int orc_env_update(const float *env_params, int32_t motion_type, int32_t M, cons
 // motion is tested against the environment after k updates.  first_invalid[e] = k of the first invalid point, 0 if the motion is
 // valid.  commit_edge >= 0: the state arrays and the engine's obstacle table are left as the reference leaves them after checking
 // THAT motion (updated first_invalid times, or K times); commit_edge < 0: nothing is changed.
-int orc_motion_validity(void *h, const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel,
-                        int32_t *sign, float *path_len, const uint8_t *dynamic, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float dt,
-                        int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
+// points != nullptr: MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-82) — validity point k of motion i is points[i][k-1][:]
+static int motion_validity_impl(void *h, const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel,
+                                int32_t *sign, float *path_len, const uint8_t *dynamic, const float *q_prev, const float *q_cur, const float *points, int64_t E,
+                                int32_t K, float dt, int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
     auto *e = static_cast<Engine *>(h);
     if (motion_type == orc::MOTION_RANDOM_DIRECTIONS) return 5;
     if (int(e->sc32.boxes.size()) != M || commit_edge >= E) return 1;
@@ -329,7 +330,8 @@ int orc_motion_validity(void *h, const float *env_params, int32_t motion_type, i
         for (int j = 0; j < M; j++) { float mn[3], mx[3]; orc::env_aabb(objs[size_t(j)], mn, mx); sc.boxes[size_t(j)] = {{mn[0], mn[1], mn[2], mx[0], mx[1], mx[2]}}; }
         for (int64_t i = 0; i < E; i++) {
             if (!valid[i]) continue;
-            orc::motion_point(q_prev + i * n, q_cur + i * n, n, k, K, qk.data());
+            if (points) std::copy_n(points + (i * K + (k - 1)) * n, n, qk.begin());
+            else orc::motion_point(q_prev + i * n, q_cur + i * n, n, k, K, qk.data());
             orc::skeleton(e->robot, qk.data(), sk.data());
             if (!orc::is_valid(e->robot, sc, sk.data(), cfg)) { valid[i] = 0; first_invalid[i] = k; }
         }
@@ -346,5 +348,15 @@ int orc_motion_validity(void *h, const float *env_params, int32_t motion_type, i
         }
     }
     return 0;
+}
+int orc_motion_validity(void *h, const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel,
+                        int32_t *sign, float *path_len, const uint8_t *dynamic, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float dt,
+                        int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
+    return motion_validity_impl(h, env_params, motion_type, M, half, pos, vel, max_vel, sign, path_len, dynamic, q_prev, q_cur, nullptr, E, K, dt, commit_edge, valid, first_invalid);
+}
+int orc_motion_validity_points(void *h, const float *env_params, int32_t motion_type, int32_t M, const float *half, float *pos, float *vel, const float *max_vel,
+                               int32_t *sign, float *path_len, const uint8_t *dynamic, const float *points, int64_t E, int32_t K, float dt,
+                               int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
+    return motion_validity_impl(h, env_params, motion_type, M, half, pos, vel, max_vel, sign, path_len, dynamic, nullptr, nullptr, points, E, K, dt, commit_edge, valid, first_invalid);
 }
 }  // extern "C"

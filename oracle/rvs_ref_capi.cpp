@@ -247,11 +247,8 @@ int rvsref_extend_spines(void *p, const float *q_roots, const float *q_targets, 
 // compiled unmodified: T consecutive motions on ONE environment, as a DRGBT run makes them (every check advances the obstacles by the
 // updates it made before returning).  The environment's private parameters are set directly (the YAML reader is a stand-in).
 // Outputs: valid[T], passed[T] (validity points appended to `path` by that check), pos_after / vel_after [T x M x 3].
-int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radius, base_radius, robot_max_vel*/, int32_t motion_type, int32_t M,
-                      const float *dim, const float *pos, const float *vel, const float *max_vel, const uint8_t *dynamic, const uint8_t *ground,
-                      const float *tol, const float *q_prev, const float *q_cur, int32_t T, int32_t K, float max_iter_time, uint8_t *valid,
-                      int32_t *passed, float *pos_after, float *vel_after) {
-    auto *h = static_cast<Harness *>(p);
+static void motion_env_setup(Harness *h, const float *env_params, int32_t motion_type, int32_t M, const float *dim, const float *pos, const float *vel,
+                             const float *max_vel, const uint8_t *dynamic, const uint8_t *ground, const float *tol) {
     auto &e = *h->env;
     e.removeAllObjects();
     e.WS_center = fcl::Vector3f(env_params[0], env_params[1], env_params[2]);
@@ -268,6 +265,21 @@ int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radiu
         obj->setMinDistTol(tol[j]);
         e.addObject(obj, fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
     }
+}
+static void motion_env_read(Harness *h, int32_t M, float *pos_after, float *vel_after) {
+    for (int j = 0; j < M; j++)
+        for (int c = 0; c < 3; c++) {
+            pos_after[size_t(j) * 3 + size_t(c)] = h->env->getObject(size_t(j))->getPosition()(c);
+            vel_after[size_t(j) * 3 + size_t(c)] = h->env->getObject(size_t(j))->getVelocity()(c);
+        }
+}
+
+int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radius, base_radius, robot_max_vel*/, int32_t motion_type, int32_t M,
+                      const float *dim, const float *pos, const float *vel, const float *max_vel, const uint8_t *dynamic, const uint8_t *ground,
+                      const float *tol, const float *q_prev, const float *q_cur, int32_t T, int32_t K, float max_iter_time, uint8_t *valid,
+                      int32_t *passed, float *pos_after, float *vel_after) {
+    auto *h = static_cast<Harness *>(p);
+    motion_env_setup(h, env_params, motion_type, M, dim, pos, vel, max_vel, dynamic, ground, tol);
     std::vector<std::shared_ptr<base::State>> path;
     planning::trajectory::MotionValidity mv(h->ss, 0.01f, max_iter_time, &path);
     TrajectoryConfig::NUM_VALIDITY_POINTS_CHECK = size_t(K);       // the constructor derives it from the obstacles' max_vel; the test fixes it
@@ -275,11 +287,33 @@ int rvsref_motion_run(void *p, const float *env_params /*WS_center xyz, WS_radiu
         const size_t before = path.size();
         valid[t] = mv.check(state_of(*h, q_prev + size_t(t) * size_t(h->n)), state_of(*h, q_cur + size_t(t) * size_t(h->n))) ? 1 : 0;
         passed[t] = int32_t(path.size() - before);
-        for (int j = 0; j < M; j++)
-            for (int c = 0; c < 3; c++) {
-                pos_after[(size_t(t) * size_t(M) + size_t(j)) * 3 + size_t(c)] = e.getObject(size_t(j))->getPosition()(c);
-                vel_after[(size_t(t) * size_t(M) + size_t(j)) * 3 + size_t(c)] = e.getObject(size_t(j))->getVelocity()(c);
-            }
+        motion_env_read(h, M, pos_after + size_t(t) * size_t(M) * 3, vel_after + size_t(t) * size_t(M) * 3);
+    }
+    return 0;
+}
+
+// The other overload, MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-82): T consecutive checks of K explicit
+// trajectory points each (points: T x K x n), delta_time = max_iter_time / NUM_VALIDITY_POINTS_CHECK with that static set to K.
+int rvsref_motion_points_run(void *p, const float *env_params, int32_t motion_type, int32_t M, const float *dim, const float *pos, const float *vel,
+                             const float *max_vel, const uint8_t *dynamic, const uint8_t *ground, const float *tol, const float *points, int32_t T,
+                             int32_t K, float max_iter_time, uint8_t *valid, int32_t *passed, float *pos_after, float *vel_after) {
+    auto *h = static_cast<Harness *>(p);
+    motion_env_setup(h, env_params, motion_type, M, dim, pos, vel, max_vel, dynamic, ground, tol);
+    std::vector<std::shared_ptr<base::State>> path;
+    planning::trajectory::MotionValidity mv(h->ss, 0.01f, max_iter_time, &path);
+    TrajectoryConfig::NUM_VALIDITY_POINTS_CHECK = size_t(K);
+    const size_t n = size_t(h->n);
+    for (int32_t t = 0; t < T; t++) {
+        std::vector<Eigen::VectorXf> traj;
+        for (int32_t k = 0; k < K; k++) {
+            Eigen::VectorXf v(h->n);
+            for (size_t i = 0; i < n; i++) v(int(i)) = points[(size_t(t) * size_t(K) + size_t(k)) * n + i];
+            traj.push_back(v);
+        }
+        const size_t before = path.size();
+        valid[t] = mv.check(traj) ? 1 : 0;
+        passed[t] = int32_t(path.size() - before);
+        motion_env_read(h, M, pos_after + size_t(t) * size_t(M) * 3, vel_after + size_t(t) * size_t(M) * 3);
     }
     return 0;
 }

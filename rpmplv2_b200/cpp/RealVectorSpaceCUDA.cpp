@@ -158,16 +158,7 @@ bool base::RealVectorSpaceCUDA::checkMotion(const std::shared_ptr<base::State> q
 	check(rvs_motion_validity(engine, q_previous->getCoord().data(), q_current->getCoord().data(), 1, int32_t(num_checks), delta_time, 0,
 							  &valid, &first_invalid), "checkMotion");
 
-	// the objects are where the reference's loop would have left them: mirror them back for logging / the next planner step
-	std::vector<float> pos(3 * num_objects), vel(3 * num_objects);
-	check(rvs_env_get(engine, pos.data(), vel.data()), "checkMotion");
-	for (size_t j = 0; j < num_objects; j++)
-	{
-		if (env->getObject(j)->getLabel() != "dynamic_obstacle")
-			continue;
-		env->getObject(j)->setPosition(fcl::Vector3f(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]));
-		env->getObject(j)->setVelocity(fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
-	}
+	mirrorEnvironment();
 
 	if (path != nullptr)
 	{
@@ -177,6 +168,44 @@ bool base::RealVectorSpaceCUDA::checkMotion(const std::shared_ptr<base::State> q
 			path->emplace_back(interpolateEdge(q_previous, q_current, dist * num_check / num_checks, dist));
 	}
 	return valid != 0;
+}
+
+/// planning::trajectory::MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-82): the trajectory's own points,
+/// one environment update of delta_time before each, in ONE engine call.
+bool base::RealVectorSpaceCUDA::checkMotion(const std::vector<Eigen::VectorXf> &traj_points, float delta_time,
+	std::vector<std::shared_ptr<base::State>> *path)
+{
+	if (traj_points.empty())
+		return true;
+	std::vector<float> points(traj_points.size() * num_dimensions);
+	for (size_t k = 0; k < traj_points.size(); k++)
+		std::memcpy(&points[k * num_dimensions], traj_points[k].data(), num_dimensions * sizeof(float));
+	uint8_t valid { 0 };
+	int32_t first_invalid { 0 };
+	check(rvs_motion_validity_points(engine, points.data(), 1, int32_t(traj_points.size()), delta_time, 0, &valid, &first_invalid), "checkMotion");
+	mirrorEnvironment();
+
+	if (path != nullptr)
+	{
+		const size_t passed { valid ? traj_points.size() : size_t(first_invalid - 1) };
+		for (size_t k = 0; k < passed; k++)
+			path->emplace_back(getNewState(traj_points[k]));
+	}
+	return valid != 0;
+}
+
+/// the objects are where the reference's loop would have left them: mirror them back for logging / the next planner step
+void base::RealVectorSpaceCUDA::mirrorEnvironment()
+{
+	std::vector<float> pos(3 * num_objects), vel(3 * num_objects);
+	check(rvs_env_get(engine, pos.data(), vel.data()), "checkMotion");
+	for (size_t j = 0; j < num_objects; j++)
+	{
+		if (env->getObject(j)->getLabel() != "dynamic_obstacle")
+			continue;
+		env->getObject(j)->setPosition(fcl::Vector3f(pos[3 * j], pos[3 * j + 1], pos[3 * j + 2]));
+		env->getObject(j)->setVelocity(fcl::Vector3f(vel[3 * j], vel[3 * j + 1], vel[3 * j + 2]));
+	}
 }
 
 std::vector<uint8_t> base::RealVectorSpaceCUDA::checkMotionBatch

@@ -79,6 +79,9 @@ namespace base
 		// the validity points that passed, as the reference appends them. robot->checkSelfCollision stays with the caller.
 		bool checkMotion(const std::shared_ptr<base::State> q_previous, const std::shared_ptr<base::State> q_current, size_t num_checks,
 						 float delta_time, std::vector<std::shared_ptr<base::State>> *path = nullptr);
+		// The other overload, MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-82; traj_interpolation "Spline" /
+		// "Ruckig"): the trajectory's own points, one update of delta_time before each.
+		bool checkMotion(const std::vector<Eigen::VectorXf> &traj_points, float delta_time, std::vector<std::shared_ptr<base::State>> *path = nullptr);
 		// The same check for many candidate motions against ONE obstacle timeline; the environment is not moved.
 		std::vector<uint8_t> checkMotionBatch(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &motions,
 											  size_t num_checks, float delta_time);
@@ -94,6 +97,7 @@ namespace base
 		void check(int status, const char *what) const;
 		void gather(const std::vector<std::shared_ptr<base::State>> &states, std::vector<float> &q) const;
 		void packPlanes(const std::vector<Eigen::MatrixXf> &nearest_points, std::vector<float> &planes) const;
+		void mirrorEnvironment();
 		void storeDistance(const std::shared_ptr<base::State> &q, float d_c, const float *profile, const float *nearest) const;
 
 		rvs_handle engine = nullptr;

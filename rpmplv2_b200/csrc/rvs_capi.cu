@@ -946,12 +946,13 @@ int rvs_env_get(rvs_handle h, float *pos, float *vel) {
     return RVS_OK;
 }
 
-int rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float delta_time, int32_t commit_edge, uint8_t *valid,
-                        int32_t *first_invalid) {
+// q_prev / q_cur [E][n] (points == nullptr) or points [E][K][n]
+static int motion_validity_impl(rvs_handle h, const float *q_prev, const float *q_cur, const float *points, int64_t E, int32_t K, float delta_time,
+                                int32_t commit_edge, uint8_t *valid, int32_t *first_invalid) {
     RVS_TRY(enter(h));
     if (E < 0 || commit_edge >= E) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad E or commit_edge");
     if (E == 0) return RVS_OK;
-    if (!q_prev || !q_cur || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if ((points ? false : (!q_prev || !q_cur)) || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
     RVS_TRY(env_ready(h, K, delta_time));
     if (size_t(E) > h->env_fi_cap) {
         if (h->d_first_invalid) RVS_CUDA(h, cudaFree(h->d_first_invalid));
@@ -962,11 +963,16 @@ int rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, i
     }
     const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
     begin_call(h, size_t(-1));                                              // device staging (first_invalid lives in device memory anyway)
-    RVS_TRY(h2d(h, B_Q, q_prev, bytes));
-    RVS_TRY(h2d(h, B_Q2, q_cur, bytes));
+    if (points) RVS_TRY(h2d(h, B_Q, points, bytes * size_t(K)));
+    else {
+        RVS_TRY(h2d(h, B_Q, q_prev, bytes));
+        RVS_TRY(h2d(h, B_Q2, q_cur, bytes));
+    }
     RVS_CUDA(h, cudaMemsetAsync(h->d_first_invalid, 0x7f, size_t(E) * sizeof(int32_t), h->stream));      // 0x7f7f7f7f: "no invalid point"
     EnvArgs a = env_args(h, K, delta_time);
-    a.q_prev = static_cast<const float *>(h->buf[B_Q].p); a.q_cur = static_cast<const float *>(h->buf[B_Q2].p); a.E = E; a.commit_edge = commit_edge;
+    if (points) { a.points = static_cast<const float *>(h->buf[B_Q].p); a.q_prev = a.q_cur = nullptr; }
+    else { a.points = nullptr; a.q_prev = static_cast<const float *>(h->buf[B_Q].p); a.q_cur = static_cast<const float *>(h->buf[B_Q2].p); }
+    a.E = E; a.commit_edge = commit_edge;
     if (h->M > 0) RVS_TRY(launched(h, launch_env_advance(a, h->stream), "environment advance launch"));
     RVS_TRY(launched(h, h->lt.motion_valid(a, h->stream), "motion validity launch"));
     if (commit_edge >= 0 && h->M > 0) {
@@ -982,6 +988,17 @@ int rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, i
         if (first_invalid) first_invalid[e] = ok ? 0 : fi[size_t(e)];
     }
     return RVS_OK;
+}
+
+int rvs_motion_validity(rvs_handle h, const float *q_prev, const float *q_cur, int64_t E, int32_t K, float delta_time, int32_t commit_edge, uint8_t *valid,
+                        int32_t *first_invalid) {
+    return motion_validity_impl(h, q_prev, q_cur, nullptr, E, K, delta_time, commit_edge, valid, first_invalid);
+}
+
+int rvs_motion_validity_points(rvs_handle h, const float *points, int64_t E, int32_t K, float delta_time, int32_t commit_edge, uint8_t *valid,
+                               int32_t *first_invalid) {
+    if (!points && E > 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    return motion_validity_impl(h, nullptr, nullptr, points, E, K, delta_time, commit_edge, valid, first_invalid);
 }
 
 }  // extern "C"

@@ -106,16 +106,22 @@ __global__ void __launch_bounds__(kBlock) motion_valid_kernel(const EnvArgs a) {
     const int64_t e = item / a.K;
     if (e >= a.E) return;
     const int k = int(item - e * a.K) + 1;
-    // interpolateEdge(q_previous, q_current, dist * k / K, dist)  (MotionValidity.cpp:43, RealVectorSpace.cpp:75-88)
-    const float *qp = a.q_prev + e * n, *qc = a.q_cur + e * n;
-    const float dist = coord_norm(qp, qc, n);
-    const float step = dist * float(k) / float(a.K);
     float qn[kMaxDofs];
-    if (dist > 0.f) {
-        const float f = step / dist;
-        for (int i = 0; i < n; i++) qn[i] = qp[i] + (qc[i] - qp[i]) * f;
-    } else
-        for (int i = 0; i < n; i++) qn[i] = qc[i];
+    if (a.points) {
+        // MotionValidity::check(traj_points_current_iter) (MotionValidity.cpp:60-74): the k-th trajectory point as it is
+        const float *pt = a.points + (e * a.K + (k - 1)) * n;
+        for (int i = 0; i < n; i++) qn[i] = pt[i];
+    } else {
+        // interpolateEdge(q_previous, q_current, dist * k / K, dist)  (MotionValidity.cpp:43, RealVectorSpace.cpp:75-88)
+        const float *qp = a.q_prev + e * n, *qc = a.q_cur + e * n;
+        const float dist = coord_norm(qp, qc, n);
+        const float step = dist * float(k) / float(a.K);
+        if (dist > 0.f) {
+            const float f = step / dist;
+            for (int i = 0; i < n; i++) qn[i] = qp[i] + (qc[i] - qp[i]) * f;
+        } else
+            for (int i = 0; i < n; i++) qn[i] = qc[i];
+    }
     R sk[3 * (kMaxDofs + 1)];
     fk_skeleton<F, R>(rb, qn, sk);
     const EnvRec *__restrict__ tl = a.timeline + size_t(k - 1) * a.M;

@@ -146,6 +146,7 @@ struct EnvArgs {
     int32_t motion_type;         // rvs_motion_type
     float ws_center[3], ws_radius, base_radius, robot_max_vel;
     const float *q_prev, *q_cur; // [E][n]
+    const float *points;         // [E][K][n] explicit validity points (MotionValidity::check(traj_points)); nullptr = interpolate q_prev -> q_cur
     int64_t E;
     int32_t *first_invalid;      // [E]
     int32_t commit_edge;

@@ -89,6 +89,7 @@ SYMBOLS = {
     "rvs_env_step": (ctypes.c_int, [_H, ctypes.c_float, ctypes.c_int32]),
     "rvs_env_get": (ctypes.c_int, [_H, c_f32p, c_f32p]),
     "rvs_motion_validity": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, c_u8p, c_i32p]),
+    "rvs_motion_validity_points": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, c_u8p, c_i32p]),
 }
 
 _lib = None
@@ -338,6 +339,19 @@ class Engine:
         valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
         self._check(self._lib.rvs_motion_validity(self._h, _p(q_prev, c_f32p), _p(q_cur, c_f32p), E, int(K), float(delta_time), int(commit_edge),
                                                  _p(valid, c_u8p), _p(first, c_i32p)))
+        return valid.astype(bool), first
+
+    def motion_validity_points(self, points, delta_time: float, commit_edge: int = -1):
+        """MotionValidity::check(traj_points) for E trajectories of K explicit points (points: [E, K, n]) -> (valid[E] bool, first_invalid[E])."""
+        points = np.ascontiguousarray(points, np.float32)
+        if points.ndim == 2:
+            points = points[None]
+        E, K, n = points.shape
+        if n != self.n:
+            raise ValueError("points must be [E, K, num_dofs]")
+        valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
+        self._check(self._lib.rvs_motion_validity_points(self._h, _p(points, c_f32p), E, int(K), float(delta_time), int(commit_edge),
+                                                        _p(valid, c_u8p), _p(first, c_i32p)))
         return valid.astype(bool), first
 
     def self_collision_capsules(self, q) -> np.ndarray:

@@ -156,6 +156,20 @@ int drv_motion(const char *urdf_path, const char *robot_type, int n, const float
         }
         const std::vector<uint8_t> bv = ss->checkMotionBatch(motions, size_t(num_checks), delta_time);
         for (int t = 0; t < T; t++) batch_valid[t] = bv[size_t(t)];
+        // the other overload (MotionValidity.cpp:60-82): the same motion handed over as explicit trajectory points must get the what-if
+        // verdict of the interpolated edge, append the points that passed, and move the environment
+        {
+            const auto &m = motions[size_t(T - 1)];
+            const float dist = ss->getNorm(m.first, m.second);
+            std::vector<Eigen::VectorXf> traj;
+            for (size_t k = 1; k <= size_t(num_checks); k++) traj.push_back(ss->interpolateEdge(m.first, m.second, dist * k / num_checks, dist)->getCoord());
+            const float before = ss->env->getObject(size_t(M - 1))->getPosition()(0);
+            std::vector<std::shared_ptr<base::State>> path;
+            const bool ok = ss->checkMotion(traj, delta_time, &path);
+            if (ok != (bv[size_t(T - 1)] != 0)) { g_error = "checkMotion(traj_points) disagrees with the what-if check of the same motion"; return 10; }
+            if (ok && path.size() != size_t(num_checks)) { g_error = "checkMotion(traj_points) did not append every point"; return 11; }
+            if (is_dynamic[M - 1] && max_vel[M - 1] > 0 && ss->env->getObject(size_t(M - 1))->getPosition()(0) == before) { g_error = "checkMotion(traj_points) did not move the environment"; return 12; }
+        }
         return 0;
     } catch (const std::exception &e) {
         g_error = e.what();

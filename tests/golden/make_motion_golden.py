@@ -39,12 +39,20 @@ def case_inputs(robot, M_dyn, law, T, seed=21):
     return rb, sc, q1, q2
 
 
+def trajectory_points(q1, q2, K):
+    """K explicit points per motion, as a spline / Ruckig trajectory would hand them over (MotionValidity.cpp:60): the straight edge
+    bent by a sine bump, [T, K, n] float32."""
+    s = (np.arange(1, K + 1, dtype=np.float32) / np.float32(K))[None, :, None]
+    bump = np.float32(1.5) * np.sin(np.float32(np.pi) * s) * np.roll(q2 - q1, 1, axis=1)[:, None, :]
+    return np.ascontiguousarray(q1[:, None, :] + (q2 - q1)[:, None, :] * s + bump, np.float32)
+
+
 def delta_time(K, max_iter_time):
     """MotionValidity.cpp:34: float delta_time = max_iter_time / NUM_VALIDITY_POINTS_CHECK."""
     return float(np.float32(max_iter_time) / np.float32(K))
 
 
-def run_reference(lib, rb, sc, law, q1, q2, K, max_iter_time):
+def run_reference(lib, rb, sc, law, q1, q2, K, max_iter_time, points=None):
     lib.rvsref_create.restype = ctypes.c_void_p
     desc = rb.to_desc()
     h = ctypes.c_void_p(lib.rvsref_create(ctypes.byref(desc), ctypes.c_float(1e-4), ctypes.c_float(1000.0), 10))
@@ -52,10 +60,13 @@ def run_reference(lib, rb, sc, law, q1, q2, K, max_iter_time):
     T, M = len(q1), len(sc["dim"])
     c = lambda k, dt: np.ascontiguousarray(sc[k], dt)
     r = dict(valid=np.zeros(T, np.uint8), passed=np.zeros(T, np.int32), pos=np.zeros((T, M, 3), np.float32), vel=np.zeros((T, M, 3), np.float32))
-    assert lib.rvsref_motion_run(h, P(prm, f32p), MOTION_TYPES[law], M, P(c("dim", np.float32), f32p), P(c("pos", np.float32), f32p),
-                                 P(c("vel", np.float32), f32p), P(c("max_vel", np.float32), f32p), P(c("is_dynamic", np.uint8), u8p),
-                                 P(c("is_ground", np.uint8), u8p), P(c("min_dist_tol", np.float32), f32p), P(q1, f32p), P(q2, f32p), T, K,
-                                 ctypes.c_float(max_iter_time), P(r["valid"], u8p), P(r["passed"], i32p), P(r["pos"], f32p), P(r["vel"], f32p)) == 0
+    env = (P(prm, f32p), MOTION_TYPES[law], M, P(c("dim", np.float32), f32p), P(c("pos", np.float32), f32p), P(c("vel", np.float32), f32p),
+           P(c("max_vel", np.float32), f32p), P(c("is_dynamic", np.uint8), u8p), P(c("is_ground", np.uint8), u8p), P(c("min_dist_tol", np.float32), f32p))
+    out = (ctypes.c_float(max_iter_time), P(r["valid"], u8p), P(r["passed"], i32p), P(r["pos"], f32p), P(r["vel"], f32p))
+    if points is None:
+        assert lib.rvsref_motion_run(h, *env, P(q1, f32p), P(q2, f32p), T, K, *out) == 0
+    else:
+        assert lib.rvsref_motion_points_run(h, *env, P(points, f32p), T, K, *out) == 0
     lib.rvsref_destroy(h)
     return r
 
@@ -69,4 +80,8 @@ if __name__ == "__main__":
         print(robot, M_dyn, law, "valid", int(r["valid"].sum()), "of", T)
         for name, v in r.items():
             data[f"c{k}_{name}"] = v
+        r = run_reference(lib, rb, sc, law, q1, q2, K, mit, points=trajectory_points(q1, q2, K))
+        print("   explicit points: valid", int(r["valid"].sum()), "of", T)
+        for name, v in r.items():
+            data[f"c{k}_pts_{name}"] = v
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "motion_golden.npz"), **data)

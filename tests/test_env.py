@@ -322,14 +322,17 @@ def _motion_golden():
     return mod
 
 
-def _run_motions(space, mod, law, sc, q1, q2, K, mit):
-    """T committed checks on one environment through a space with the engine's env_set / motion_validity / env_get methods."""
+def _run_motions(space, mod, law, sc, q1, q2, K, mit, points=None):
+    """T committed checks on one environment through a space with the engine's env_set / motion_validity[_points] / env_get methods."""
     space.env_set(env_params(law, **mod.ENV), **sc)
     dt = mod.delta_time(K, mit)
     T = len(q1)
     out = dict(valid=np.zeros(T, np.uint8), passed=np.zeros(T, np.int32), pos=[], vel=[])
     for t in range(T):
-        v, first = space.motion_validity(q1[t:t + 1], q2[t:t + 1], K, dt, commit_edge=0)
+        if points is None:
+            v, first = space.motion_validity(q1[t:t + 1], q2[t:t + 1], K, dt, commit_edge=0)
+        else:
+            v, first = space.motion_validity_points(points[t:t + 1], dt, commit_edge=0)
         out["valid"][t] = 1 if v[0] else 0
         out["passed"][t] = K if v[0] else first[0] - 1                   # `path` receives the points that passed before the failing one
         pos, vel = space.env_get()
@@ -357,6 +360,9 @@ def test_oracle_motion_check_matches_the_reference_motionvalidity_golden(ob):
         got = _run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit)
         _compare_motion_run(got, {n: gold[f"c{k}_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K))
         n_valid, n_all = n_valid + int(got["valid"].sum()), n_all + T
+        # the other overload: explicit trajectory points (MotionValidity.cpp:60-82)
+        got = _run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit, points=mod.trajectory_points(q1, q2, K))
+        _compare_motion_run(got, {n: gold[f"c{k}_pts_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K, "points"))
     assert 0.2 < n_valid / n_all < 0.8
 
 
@@ -372,6 +378,10 @@ def test_oracle_motion_check_matches_the_compiled_reference_on_fresh_runs(ob):
         rb, sc, q1, q2 = mod.case_inputs(robot, M_dyn, law, T, seed=seed)
         want = mod.run_reference(lib, rb, sc, law, q1, q2, K, mit)
         _compare_motion_run(_run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit), want, (robot, law, K))
+        if hasattr(lib, "rvsref_motion_points_run"):
+            pts = mod.trajectory_points(q1, q2, K)
+            want = mod.run_reference(lib, rb, sc, law, q1, q2, K, mit, points=pts)
+            _compare_motion_run(_run_motions(ob.Oracle(rb), mod, law, sc, q1, q2, K, mit, points=pts), want, (robot, law, K, "points"))
 
 
 @pytest.mark.gpu
@@ -386,4 +396,13 @@ def test_gpu_motion_check_matches_the_reference_motionvalidity_golden():
         eng = Engine(rb)
         got = _run_motions(eng, mod, law, sc, q1, q2, K, mit)
         _compare_motion_run(got, {n: gold[f"c{k}_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K), pos_tol=1e-5 if law == "circular" else 0.0)
+        got = _run_motions(eng, mod, law, sc, q1, q2, K, mit, points=mod.trajectory_points(q1, q2, K))
+        _compare_motion_run(got, {n: gold[f"c{k}_pts_{n}"] for n in ("valid", "passed", "pos", "vel")}, (robot, law, K, "points"),
+                            pos_tol=1e-5 if law == "circular" else 0.0)
+        # what-if form: many candidate trajectories against one timeline, nothing moves
+        eng.env_set(env_params(law, **mod.ENV), **sc)
+        pts = mod.trajectory_points(q1, q2, K)
+        v_all, f_all = eng.motion_validity_points(pts, mod.delta_time(K, mit))
+        v_one = np.array([eng.motion_validity_points(pts[t:t + 1], mod.delta_time(K, mit))[0][0] for t in range(0, len(pts), 7)])
+        assert np.array_equal(v_all[::7], v_one) and np.array_equal(eng.env_get()[0], sc["pos"])
         eng.close()
