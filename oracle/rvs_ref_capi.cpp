@@ -38,6 +38,7 @@
 #include "MotionValidity.h"
 #define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
 #include "RGBTConnect.h"
+#include "PatternTree.h"
 #undef protected
 
 namespace {
@@ -360,6 +361,35 @@ int rvsref_plan(void *p, int32_t kind, const float *q_start, const float *q_goal
     tree_sizes[0] = int64_t(planner->trees[0]->getNumStates());      // (getTree() returns a copy whose destructor clears the shared state list)
     tree_sizes[1] = int64_t(planner->trees[1]->getNumStates());
     return 0;
+}
+
+
+// planning::rbt::PatternTree::generateLocalTree (PatternTree.cpp:62-91), compiled unmodified: the local tree of generalized burs around
+// q_root.  Outputs (node order = the reference's base::Tree order): coord[count x n], parent[count] (-1 for the root), d_c[count],
+// profile[count x n] (NaN where the State holds no profile), is_real[count].  Returns the number of nodes (<= max_nodes), or -1.
+int64_t rvsref_pattern_tree(void *p, const float *q_root, int32_t tree_layers, int32_t num_layers, int32_t num_iter_spine, int32_t use_expanded_bubble,
+                            float d_crit, float delta, int64_t max_nodes, float *coord, int32_t *parent, float *d_c, float *profile, uint8_t *is_real) {
+    auto *h = static_cast<Harness *>(p);
+    RGBTConnectConfig::NUM_LAYERS = size_t(num_layers);
+    RBTConnectConfig::NUM_ITER_SPINE = size_t(num_iter_spine);
+    RBTConnectConfig::USE_EXPANDED_BUBBLE = use_expanded_bubble != 0;
+    RBTConnectConfig::D_CRIT = d_crit;
+    RBTConnectConfig::DELTA = delta;
+    planning::rbt::PatternTree pattern(h->ss, size_t(tree_layers));
+    const auto tree = pattern.generateLocalTree(state_of(*h, q_root));
+    const int64_t count = int64_t(tree->getNumStates());
+    if (count > max_nodes) return -1;
+    const size_t n = size_t(h->n);
+    for (int64_t k = 0; k < count; k++) {
+        const auto q = tree->getState(size_t(k));
+        for (size_t i = 0; i < n; i++) coord[size_t(k) * n + i] = q->getCoord(int(i));
+        parent[k] = q->getParent() ? int32_t(q->getParent()->getIdx()) : -1;
+        d_c[k] = q->getDistance();
+        is_real[k] = q->getIsRealDistance() ? 1 : 0;
+        const auto &prof = q->getDistanceProfile();
+        for (size_t i = 0; i < n; i++) profile[size_t(k) * n + i] = prof.size() == n ? prof[i] : NAN;
+    }
+    return count;
 }
 
 }  // extern "C"
