@@ -47,23 +47,45 @@ def prune_edge(q1, q2, lo, hi, eq_thr):
     return q2.copy()
 
 
-def _axis_targets(root, parent, lo, hi, delta, eq_thr):
-    """The q_e of generateGBur for one root (PatternTree.cpp:34-55): axis order, sign -1 then +1, the direction back to the parent skipped."""
+def _axis_targets(roots, parents, has_parent, lo, hi, delta, eq_thr):
+    """The q_e of generateGBur for a whole layer (PatternTree.cpp:34-55), vectorised: for every root, axis order, sign -1 then +1, the
+    direction that points back at the parent skipped, every target pruned to the joint limits.  roots / parents: [F, n].
+    Returns (root_index [S], targets [S, n])."""
     f = np.float32
-    out = []
-    for i in range(len(root)):
-        for sign in (-1, 1):
-            q_e = root.copy()
-            q_e[i] = f(root[i] + f(sign) * f(delta))
-            if parent is not None:
-                a, b = (q_e - root).astype(f), (parent - root).astype(f)
-                den = f(np.sqrt((a * a).sum(dtype=f)) * np.sqrt((b * b).sum(dtype=f)))
-                with np.errstate(divide="ignore", invalid="ignore"):
-                    cos_phi = f((a * b).sum(dtype=f) / den)
-                if abs(cos_phi - f(1)) < f(eq_thr):
-                    continue
-            out.append(prune_edge(root, q_e, lo, hi, eq_thr))
-    return out
+    F, n = roots.shape
+    signs = np.tile(np.array([-1, 1], f), n)                                  # [2n]
+    axes = np.repeat(np.arange(n), 2)                                         # [2n]
+    q_e = np.repeat(roots[:, None, :], 2 * n, axis=1)                         # [F, 2n, n]
+    q_e[:, np.arange(2 * n), axes] = (roots[:, axes] + signs[None, :] * f(delta)).astype(f)
+    # the skip rule: |cos(q_e - root, parent - root) - 1| < threshold (NaN, i.e. a zero-length spine, never skips)
+    a_i = (q_e[:, np.arange(2 * n), axes] - roots[:, axes]).astype(f)         # the only non-zero component of q_e - root
+    b = (parents - roots).astype(f)                                           # [F, n]
+    norm_a = np.sqrt((a_i * a_i).astype(f))
+    norm_b = np.sqrt((b * b).sum(axis=1, dtype=f)).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        cos_phi = ((a_i * b[:, axes]).astype(f) / (norm_a * norm_b[:, None]).astype(f)).astype(f)
+        skip = has_parent[:, None] & (np.abs(cos_phi - f(1)) < f(eq_thr))
+    # pruneEdge: q_e leaves the limits along its own axis only, unless the root itself is outside (then the generic routine decides)
+    qi = q_e[:, np.arange(2 * n), axes]
+    over, under = qi > hi[axes][None, :], qi < lo[axes][None, :]
+    bound = np.where(over, hi[axes][None, :], lo[axes][None, :]).astype(f)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        t = ((bound - roots[:, axes]) / (qi - roots[:, axes])).astype(f)
+        cand_i = (roots[:, axes] + t * a_i).astype(f)
+    inside = (roots >= lo - f(eq_thr)) & (roots <= hi + f(eq_thr))            # the untouched coordinates of a candidate are the root's
+    root_out = ((roots > hi) | (roots < lo))                                  # coordinates pruneEdge would also list
+    ok_i = ~((cand_i < lo[axes][None, :] - f(eq_thr)) | (cand_i > hi[axes][None, :] + f(eq_thr)))
+    others_inside = np.stack([np.delete(inside, i, axis=1).all(axis=1) for i in range(n)], axis=1)[:, axes] if n > 1 else np.ones((F, 2 * n), bool)
+    pruned = (over | under) & ok_i & others_inside
+    q_e[:, np.arange(2 * n), axes] = np.where(pruned, cand_i, qi)
+    generic = root_out.any(axis=1)
+    for fi in np.flatnonzero(generic):                                        # rare: a root outside its limits
+        for j in range(2 * n):
+            raw = roots[fi].copy()
+            raw[axes[j]] = f(roots[fi, axes[j]] + signs[j] * f(delta))
+            q_e[fi, j] = prune_edge(roots[fi], raw, lo, hi, eq_thr)
+    keep = ~skip
+    return np.nonzero(keep)[0].astype(np.int32), q_e[keep]
 
 
 def generate_local_tree(space, robot: Robot, q_root, num_layers: int, spine_params: Optional[RvsSpineParams] = None, delta: float = DELTA,
@@ -75,42 +97,42 @@ def generate_local_tree(space, robot: Robot, q_root, num_layers: int, spine_para
     f = np.float32
     n = robot.num_dofs
     lo, hi = np.asarray(robot.limits[:, 0], f), np.asarray(robot.limits[:, 1], f)
-    coord, parent, layer, status = [np.asarray(q_root, f).copy()], [-1], [0], [0]
-    d_c, profile = [np.nan], [np.full(n, np.nan, f)]
-    frontier = [0]
-    space.store_reserve(max(1, (2 * n) ** max(num_layers - 1, 0) + 1))
+    coord, parent, layer, status = [np.asarray(q_root, f).reshape(1, n).copy()], [np.array([-1], np.int32)], [np.zeros(1, np.int32)], [np.zeros(1, np.uint8)]
+    d_c, profile = [np.full(1, np.nan, f)], [np.full((1, n), np.nan, f)]
+    first, count = 0, 1                                               # the frontier = nodes [first, first + count) of the flat arrays
+    all_coord = coord[0]
+    all_parent = parent[0]
     for depth in range(num_layers):
-        if not frontier:
+        if count == 0:
             break
         # (1) the layer's real distances, nearest points kept on the device
-        q_layer = np.stack([coord[k] for k in frontier])
-        slots = np.arange(len(frontier), dtype=np.int32)
-        space.store_reserve(len(frontier))
-        d, p = space.store_distance(q_layer, slots)
+        q_layer = all_coord[first:first + count]
+        space.store_reserve(count)
+        d, p = space.store_distance(q_layer, np.arange(count, dtype=np.int32))
+        dl, pl = np.concatenate(d_c), np.concatenate(profile)
+        dl[first:first + count], pl[first:first + count] = d, p
+        d_c, profile = [dl], [pl]
         # (2) every spine of the layer
-        roots, targets = [], []
-        for s, k in enumerate(frontier):
-            d_c[k], profile[k] = float(d[s]), p[s].copy()
-            for q_e in _axis_targets(coord[k], coord[parent[k]] if parent[k] >= 0 else None, lo, hi, delta, equality_threshold):
-                roots.append(s)
-                targets.append(q_e)
-        if not targets:
+        par = all_parent[first:first + count]
+        has_parent = par >= 0
+        roots, targets = _axis_targets(q_layer, all_coord[np.maximum(par, 0)], has_parent, lo, hi, delta, equality_threshold)
+        if len(roots) == 0:
             break
-        q_lay, n_lay, _, st = space.store_extend_spines(np.asarray(roots, np.int32), np.stack(targets), sp, gen2=False)
-        nxt = []
-        for j, s in enumerate(roots):
-            k = frontier[s]
-            q_new = q_lay[j, max(int(n_lay[j]), 1) - 1] if n_lay[j] > 0 else coord[k]      # Trapped: extendGenSpine returns the root itself
-            coord.append(np.asarray(q_new, f).copy())
-            parent.append(k)
-            layer.append(depth + 1)
-            status.append(int(st[j]))
-            d_c.append(np.nan)
-            profile.append(np.full(n, np.nan, f))
-            nxt.append(len(coord) - 1)
-        frontier = nxt
-    return dict(coord=np.stack(coord), parent=np.asarray(parent, np.int32), layer=np.asarray(layer, np.int32), d_c=np.asarray(d_c, f),
-                profile=np.stack(profile), status=np.asarray(status, np.uint8))
+        q_lay, n_lay, _, st = space.store_extend_spines(roots, targets, sp, gen2=False)
+        last = np.maximum(n_lay, 1) - 1
+        q_new = np.where((n_lay > 0)[:, None], q_lay[np.arange(len(roots)), last], q_layer[roots]).astype(f)    # Trapped: the root itself
+        S = len(roots)
+        coord.append(q_new)
+        parent.append((first + roots).astype(np.int32))
+        layer.append(np.full(S, depth + 1, np.int32))
+        status.append(st.astype(np.uint8))
+        d_c.append(np.full(S, np.nan, f))
+        profile.append(np.full((S, n), np.nan, f))
+        all_coord, all_parent = np.concatenate(coord), np.concatenate(parent)
+        coord, parent = [all_coord], [all_parent]
+        first, count = first + count, S
+    return dict(coord=all_coord, parent=all_parent, layer=np.concatenate(layer), d_c=np.concatenate(d_c), profile=np.concatenate(profile),
+                status=np.concatenate(status))
 
 
 # ------------------------------------------------------------------------------------------------- dataset.csv (generate_dataset.cpp)
