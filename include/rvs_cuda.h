@@ -24,6 +24,8 @@
  *                                        Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30)
  *   rvs_self_collision_capsules       <- xArm6::checkSelfCollision(q) capsule pre-filter
  *                                        (src/robots/xArm6.cpp:374-424; FCL mesh stage is NOT covered)
+ *   rvs_set_self_collision            <- AbstractRobot::setSelfCollisionChecking (src/scenario/Scenario.cpp:101-103)
+ *   rvs_self_collision_edges          <- xArm6::checkSelfCollision(q1, q2&) (src/robots/xArm6.cpp:284-368), capsule stage
  *   rvs_capsule_box_distance /        <- the public static primitives CollisionAndDistance::distanceCapsuleToBox /
  *   rvs_capsule_box_collision            collisionCapsuleToBox (CollisionAndDistance.cpp:4-42, 208-214), batched
  *   rvs_store_distance /              <- base::State's distance cache (include/state_spaces/State.h:24-41) filled by
@@ -193,6 +195,28 @@ int  rvs_enclosing_radii(rvs_handle h, const float *q, int64_t N, float *radii);
  * when computeCapsulesDistance < 0 ("maybe": the reference then runs an FCL mesh test, which is out of scope).
  * For every other robot kind the reference's answer is the constant `false` -> all zero. */
 int  rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_t *mask);
+/* AbstractRobot::setSelfCollisionChecking (src/scenario/Scenario.cpp:101-103; robots::xArm6's constructor default is true,
+ * src/robots/xArm6.cpp:67) plus RRTConnectConfig::EPS_STEP, the marching step of xArm6::checkSelfCollision(q1, q2)
+ * (src/robots/xArm6.cpp:340-341; data/configurations/configuration_rrtconnect.yaml:4 = 0.1).  A new handle has the check OFF.
+ * While it is on, rvs_extend_spines / rvs_store_extend_spines apply the reference's truncation
+ * (src/planners/rbt/RBTConnect.cpp:129-131).  Only xArm6 has a self-collision check at all (the other classes return false). */
+int  rvs_set_self_collision(rvs_handle h, int32_t enabled, float eps_step);
+int  rvs_get_self_collision(rvs_handle h, int32_t *enabled, float *eps_step);
+/* xArm6::checkSelfCollision(q1, q2&) (src/robots/xArm6.cpp:284-368) for E motions q1[e] -> q2[e]: up to five enclosing-radii
+ * bubble steps, then EPS_STEP marching with the capsule test of the pairs {0-5, 1-5, 0-4, 1-4}.  hit[e] = 1 on a self-collision;
+ * q2_out[E x n] = q2 after the call (the last collision-free configuration on a hit, q2 itself otherwise).
+ * Capsule stage only: the FCL mesh confirmation (xArm6.cpp:426-464) is host-side and out of contract, so a hit means "maybe"
+ * (conservative).  hit = 0 / q2_out = q2 when the check is off or the robot is not an xArm6. */
+int  rvs_self_collision_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *hit, float *q2_out);
+int  rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_hit, float *d_q2_out);
+/* The two composite tests every planner of the reference writes out by hand, as ONE call (one upload, one synchronisation):
+ *   rvs_check_states: valid[i] = ss->isValid(q_i) && !ss->robot->checkSelfCollision(q_i)
+ *                     (src/planners/rrt/RRTConnect.cpp:13-15, trajectory/MotionValidity.cpp:42, rbt_star/RGBMTStar.cpp:202)
+ *   rvs_check_edges:  valid[e] = ss->isValid(q1_e, q2_e) && !ss->robot->checkSelfCollision(q1_e, q2_e)
+ *                     (src/planners/rrt/RRTConnect.cpp:100, rrtx/RRTx.cpp:467-468, 507-508)
+ * Identical to rvs_is_valid / rvs_is_valid_edges while the self-collision check is off (rvs_set_self_collision). */
+int  rvs_check_states(rvs_handle h, const float *q, int64_t N, uint8_t *valid);
+int  rvs_check_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *valid);
 /* Generalized-bur spines from ONE root towards S targets (RGBTConnect::extendGenSpine with
  * underestimation). q_root[L dofs], root profile/planes come from a FULL distance query of the root.
  * q_reached[S x n]; d_c_reached[S]; status[S] (base::State::Status: 1 Advanced, 2 Trapped, 3 Reached). */

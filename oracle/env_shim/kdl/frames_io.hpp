@@ -1,8 +1,3 @@
-// oracle/env_shim/kdl — stand-in for the orocos-KDL types that RPMPLv2's State.h / AbstractRobot.h mention (never used by the
-// RealVectorSpace hot path itself).  TEST INFRASTRUCTURE ONLY.
+// oracle/env_shim/kdl — see kdl_shim.hpp (work-alike of the orocos-KDL slice the reference's robot classes use).  TEST INFRASTRUCTURE ONLY.
 #pragma once
-namespace KDL {
-struct Vector { double data[3] = {0, 0, 0}; };
-struct Rotation { double data[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}; };
-struct Frame { Rotation M; Vector p; };
-}  // namespace KDL
+#include "kdl_shim.hpp"

@@ -68,6 +68,9 @@ class Oracle:
         self._h = ctypes.c_void_p(lib().orc_create(ctypes.byref(self._desc), ctypes.byref(self.params)))
         if not self._h:
             raise RuntimeError("orc_create failed")
+        # robots::xArm6's constructor switches self-collision checking on (xArm6.cpp:67); every other class has none
+        if robot.self_collision_checking:
+            self.set_self_collision(True, 0.1)
 
     def close(self):
         if getattr(self, "_h", None):
@@ -231,6 +234,17 @@ class Oracle:
         out = np.empty(q.shape[0], np.uint8)
         lib().orc_self_collision_capsules_f32(self._h, _p(q, c_f32p), ctypes.c_int64(q.shape[0]), _p(out, c_u8p))
         return out
+
+    def set_self_collision(self, enabled: bool, eps_step: float = 0.1):
+        """AbstractRobot::setSelfCollisionChecking + RRTConnectConfig::EPS_STEP (xArm6.cpp:340-341)."""
+        lib().orc_set_self_collision(self._h, ctypes.c_int32(1 if enabled else 0), ctypes.c_float(eps_step))
+
+    def self_collision_edges(self, q1, q2):
+        """xArm6::checkSelfCollision(q1, q2&) capsule stage (xArm6.cpp:284-368) -> (hit[E], q2 after the call)."""
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        hit, out = np.empty(q1.shape[0], np.uint8), np.empty_like(q2)
+        lib().orc_self_collision_edges_f32(self._h, _p(q1, c_f32p), _p(q2, c_f32p), ctypes.c_int64(q1.shape[0]), _p(hit, c_u8p), _p(out, c_f32p))
+        return hit, out
 
     def generate_configs(self, seed: int, first: int, N: int):
         q = np.empty((N, self.n), np.float32)

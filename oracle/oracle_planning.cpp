@@ -34,10 +34,17 @@ public:
         for (int i = 0; i < N; i++) {
             orc::skeleton(e.robot, q + size_t(i) * n, sk.data());
             valid[i] = orc::is_valid(e.robot, e.sc32, sk.data(), cfg) ? 1 : 0;
+            if (valid[i] && e.robot.self_collision_checking && orc::self_collision_mask(e.robot, sk.data(), cfg)) valid[i] = 0;      // RRTConnect.cpp:13-15
         }
     }
     void isValidEdges(const float *q1, const float *q2, int E, uint8_t *valid) override {
-        for (int i = 0; i < E; i++) valid[i] = orc::is_valid_edge(e.robot, e.sc32, q1 + size_t(i) * n, q2 + size_t(i) * n, cfg) ? 1 : 0;
+        std::vector<float> end(static_cast<size_t>(n), 0.f);
+        for (int i = 0; i < E; i++) {
+            valid[i] = orc::is_valid_edge(e.robot, e.sc32, q1 + size_t(i) * n, q2 + size_t(i) * n, cfg) ? 1 : 0;
+            if (!valid[i]) continue;
+            std::copy_n(q2 + size_t(i) * n, n, end.data());                                   // RRTConnect.cpp:100 (the truncated q2 is discarded)
+            if (orc::self_collision_edge(e.robot, cfg, q1 + size_t(i) * n, end.data())) valid[i] = 0;
+        }
     }
     void distanceToSlots(const float *q, int N, const int32_t *slot_idx, float *d_c) override {
         std::vector<orc::V3<float>> sk(n + 1);

@@ -432,6 +432,8 @@ struct Robot {
     std::vector<std::array<double, 3>> xyz;   // n+1
     std::vector<std::array<double, 3>> axis;  // n (unit)
     std::vector<float> radius;           // n
+    bool self_collision_checking = false;     // AbstractRobot::getSelfCollisionChecking (xArm6 ctor: true; Scenario.cpp:101-103 overrides)
+    float eps_step = 0.1f;                    // RRTConnectConfig::EPS_STEP, the marching step of xArm6::checkSelfCollision(q1, q2) (xArm6.cpp:340-341)
 };
 
 struct Frame { M3 R; double p[3]; };
@@ -707,8 +709,70 @@ inline float dot_dyn(const float *a, int stride, const float *b, int n) {
     return res;
 }
 
+// xArm6::computeCapsulesDistance (xArm6.cpp:417-424) on a skeleton
+inline float capsules_distance(const Robot &rb, const V3<float> *sk, int a, int b, const Config<float> &cfg) {
+    return seg_seg(sk[a], sk[a + 1], sk[b], sk[b + 1], cfg).d - rb.radius[a] - rb.radius[b];
+}
+
+// xArm6::checkSelfCollision(q1, q2&) (xArm6.cpp:284-368), capsule stage (the FCL mesh confirmation of checkRealSelfCollision is
+// third-party arithmetic and out of contract: it is taken to answer "collide", which makes the check conservative).
+//   1. up to 5 bubble steps from q1 towards q2: step = min over the pairs {0-4, 0-5, 1-4, 1-5} of capsule distance / covered distance
+//      (phi_k = R.col(k) . |q2 - q1_temp| from the enclosing radii); step > 1 => no self-collision possible;
+//   2. from the configuration the bubble steps reached, march towards q2 in EPS_STEP pieces and test the pairs in the order
+//      {0-5, 1-5, 0-4, 1-4}, skipping a pair while its own bubble step still covers the marched fraction; on a hit q2 is replaced by
+//      the last collision-free configuration and the function returns true.
+// std::min / std::max are the reference's ((b < a) ? b : a and (a < b) ? b : a): NaN / inf from zero-length motions propagate as there.
+// Every other robot class answers the constant false (Planar2DOF.cpp:151-161, Spatial10DOF.cpp:32-43).
+inline bool self_collision_edge(const Robot &rb, const Config<float> &cfg, const float *q1, float *q2) {
+    if (rb.kind != XARM6 || !rb.self_collision_checking) return false;
+    const int n = rb.n, W = n + 1;
+    std::vector<V3<float>> sk(n + 1);
+    std::vector<float> R(size_t(n) * W), delta(n), q1_temp(q1, q1 + n), q_new(n);
+    float step04 = 0, step05 = 0, step14 = 0, step15 = 0;
+    int num_iter = 0;
+    while (true) {
+        skeleton(rb, q1_temp.data(), sk.data());
+        enclosing_radii(rb, sk.data(), R.data());
+        for (int i = 0; i < n; i++) delta[i] = std::fabs(q2[i] - q1_temp[i]);
+        const float phi2 = dot_dyn(R.data() + 2, W, delta.data(), n), phi4 = dot_dyn(R.data() + 4, W, delta.data(), n),
+                    phi5 = dot_dyn(R.data() + 5, W, delta.data(), n), phi6 = dot_dyn(R.data() + 6, W, delta.data(), n);
+        step04 = capsules_distance(rb, sk.data(), 0, 4, cfg) / std::max(phi4, phi5);
+        step05 = capsules_distance(rb, sk.data(), 0, 5, cfg) / std::max(phi5, phi6);
+        step14 = capsules_distance(rb, sk.data(), 1, 4, cfg) / (phi2 + std::max(phi4, phi5));
+        step15 = capsules_distance(rb, sk.data(), 1, 5, cfg) / (phi2 + std::max(phi5, phi6));
+        const float step = std::min(std::min(step04, step05), std::min(step14, step15));
+        if (step > 1) return false;
+        if (++num_iter == 5 || step <= 0) break;
+        if (step > 0)
+            for (int i = 0; i < n; i++) q1_temp[i] = q1_temp[i] + step * (q2[i] - q1_temp[i]);
+    }
+    const float D = coord_norm(q2, q1_temp.data(), n);
+    float dist = D;
+    bool advanced = true;
+    while (advanced) {
+        if (dist > rb.eps_step)
+            for (int i = 0; i < n; i++) q_new[i] = q1_temp[i] + (q2[i] - q1_temp[i]) / dist * rb.eps_step;
+        else {
+            for (int i = 0; i < n; i++) q_new[i] = q2[i];
+            advanced = false;
+        }
+        dist = coord_norm(q2, q_new.data(), n);
+        const float step_crit = 1 - dist / D;
+        const bool skip[4] = {step05 > step_crit, step15 > step_crit, step04 > step_crit, step14 > step_crit};
+        static const int pairs[4][2] = {{0, 5}, {1, 5}, {0, 4}, {1, 4}};
+        skeleton(rb, q_new.data(), sk.data());
+        for (int k = 0; k < 4; k++)
+            if (!skip[k] && capsules_distance(rb, sk.data(), pairs[k][0], pairs[k][1], cfg) < 0) {
+                for (int i = 0; i < n; i++) q2[i] = q1_temp[i];
+                return true;
+            }
+        q1_temp = q_new;
+    }
+    return false;
+}
+
 // One extendSpine call from state (q, profile, d_c) towards q_e. Returns base::State::Status (1 Advanced, 3 Reached).
-inline int extend_spine(const Robot &rb, const float *q, const float *profile, float d_c, const float *q_e, const SpineConfig &sp, float *q_new) {
+inline int extend_spine(const Robot &rb, const Config<float> &cfg, const float *q, const float *profile, float d_c, const float *q_e, const SpineConfig &sp, float *q_new) {
     const int n = rb.n, W = n + 1;
     std::vector<V3<float>> sk(n + 1), sk_new(n + 1);
     std::vector<float> R(size_t(n) * W), delta(n), rho_profile(n, 0.f), q_temp(q, q + n);
@@ -730,7 +794,10 @@ inline int extend_spine(const Robot &rb, const float *q, const float *profile, f
             status = 3;
         } else
             for (int i = 0; i < n; i++) q_new[i] = q_temp[i] + step * (q_e[i] - q_temp[i]);
-        if (counter == sp.num_iter_spine || status != 1) return status;
+        // RBTConnect.cpp:129-131: a self-collision on [q_temp, q_new] truncates q_new to the last collision-free configuration
+        const bool self_collision = self_collision_edge(rb, cfg, q_temp.data(), q_new);
+        if (self_collision) status = !(coord_norm(q_temp.data(), q_new, n) < cfg.eq_thr) ? 1 : 2;
+        if (counter == sp.num_iter_spine || status != 1 || self_collision) return status;
         skeleton(rb, q_new, sk_new.data());
         std::fill(rho_profile.begin(), rho_profile.end(), 0.f);
         float rho_k_prev = 0.f;
@@ -757,7 +824,7 @@ inline int extend_gen_spine(const Robot &rb, size_t M, const Config<float> &cfg,
     float dc_cur = root_d_c;
     int status = 0;
     for (int layer = 0; layer < sp.num_layers; layer++) {
-        status = extend_spine(rb, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
+        status = extend_spine(rb, cfg, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
         skeleton(rb, q_out, sk.data());
         bool rejected;
         *d_out = underestimation(rb, M, sk.data(), root_planes, cfg, prof_new.data(), &rejected);
@@ -785,7 +852,7 @@ inline int extend_gen_spine_layers(const Robot &rb, size_t M, const Config<float
     int status = 0;
     for (int layer = 0; layer < sp.num_layers; layer++) {
         float *q_out = q_layers + size_t(layer) * n;
-        status = extend_spine(rb, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
+        status = extend_spine(rb, cfg, q_cur.data(), prof_cur.data(), dc_cur, q_e, sp, q_out);
         *n_layers = layer + 1;
         skeleton(rb, q_out, sk.data());
         bool rejected;

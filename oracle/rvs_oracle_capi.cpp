@@ -224,6 +224,25 @@ int orc_self_collision_capsules_f32(void *h, const float *q, int64_t N, uint8_t 
     return 0;
 }
 
+// AbstractRobot::setSelfCollisionChecking (Scenario.cpp:101-103) + RRTConnectConfig::EPS_STEP (the marching step of xArm6.cpp:340-341)
+int orc_set_self_collision(void *h, int32_t enabled, float eps_step) {
+    auto *e = static_cast<Engine *>(h);
+    e->robot.self_collision_checking = enabled != 0;
+    e->robot.eps_step = eps_step;
+    return 0;
+}
+// xArm6::checkSelfCollision(q1, q2&) (xArm6.cpp:284-368), capsule stage: hit[E], q2_out[E x n] (= q2, truncated on a hit)
+int orc_self_collision_edges_f32(void *h, const float *q1, const float *q2, int64_t E, uint8_t *hit, float *q2_out) {
+    auto *e = static_cast<Engine *>(h);
+    const auto cfg = config_of<float>(e->prm);
+    const int n = e->robot.n;
+    for (int64_t i = 0; i < E; i++) {
+        for (int k = 0; k < n; k++) q2_out[i * n + k] = q2[i * n + k];
+        hit[i] = orc::self_collision_edge(e->robot, cfg, q1 + i * n, q2_out + i * n) ? 1 : 0;
+    }
+    return 0;
+}
+
 int orc_generate_configs(void *h, uint64_t seed, int64_t first, int64_t N, float *q) {
     auto *e = static_cast<Engine *>(h);
     const int n = e->robot.n;

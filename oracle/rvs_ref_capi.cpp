@@ -16,9 +16,16 @@
 // constructs base::RealVectorSpaceCUDA (rpmplv2_b200/cpp, compiled here against the reference's REAL headers) instead of
 // base::RealVectorSpace, and the reference's own planners / loops run over the CUDA engine through base::StateSpace's virtual
 // interface — the drop-in itself, checked on the GPU box against the golden vectors of the CPU build (tests/test_dropin.py).
-// What it cannot pin: the robot's forward kinematics and enclosing radii (KDL) — the harness robot answers computeSkeleton and
-// computeEnclosingRadii with the oracle's own restatements, so both sides see identical skeletons and radii.
+// Round 2: the ROBOT classes are the reference's own too.  oracle/env_shim now carries work-alikes of orocos-KDL, kdl_parser, urdfdom
+// and glog (third-party, not in /root/reference), so src/robots/{xArm6,Planar2DOF,Planar10DOF,Spatial10DOF,Spatial14DOF,Spatial18DOF,
+// Spatial22DOF}.cpp compile unmodified and rvsref_create_robot() builds the very class scenario::Scenario would (Scenario.cpp:13-51)
+// from the reference's own URDF.  computeSkeleton (xArm6.cpp:209-235, Planar2DOF.cpp:117-130), computeEnclosingRadii
+// (xArm6.cpp:237-275, Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30), computeCapsulesDistance and both checkSelfCollision overloads
+// (xArm6.cpp:284-424; the FCL mesh stage answers "collide", see env_shim/fcl/fcl.h) are therefore the reference's code on every golden
+// path; only KDL's frame arithmetic underneath is a restatement of a third-party library (env_shim/kdl/kdl_shim.hpp).
+// rvsref_create() keeps the descriptor-only HarnessRobot (oracle FK + oracle radii) for chains that have no reference class.
 #include <cstdint>
+#include <cstring>
 #include <iostream>
 #include <memory>
 #include <sstream>
@@ -28,14 +35,19 @@
 #include "../include/rvs_cuda.h"
 #include "rvs_oracle.hpp"
 
-#define private public                                         // env::Environment keeps WS_center / WS_radius / motion_type / sign / path_len private
-#include "Environment.h"
-#undef private
+#define private public                                         // env::Environment keeps WS_center / WS_radius / motion_type / sign / path_len private,
+#include "Environment.h"                                       // xArm6 (pulled in by RealVectorSpace.h) its computeCapsulesDistance
 #include "RealVectorSpace.h"
+#include "xArm6.h"
+#undef private
 #ifdef RVS_DROPIN                                              // the same harness with the CUDA state space under the reference's planners
 #include "RealVectorSpaceCUDA.h"
 #endif
 #include "MotionValidity.h"
+#include "Planar10DOF.h"
+#include "Spatial14DOF.h"
+#include "Spatial18DOF.h"
+#include "Spatial22DOF.h"
 #define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
 #include "RGBTConnect.h"
 #include "PatternTree.h"
@@ -67,6 +79,7 @@ public:
         gripper_length = rd->gripper_length;
         self_collision_checking = false;
     }
+    void setType(const std::string &t) { type = t; }
     void setState(const std::shared_ptr<base::State>) override {}
     std::shared_ptr<std::vector<KDL::Frame>> computeForwardKinematics(const std::shared_ptr<base::State>) override { return nullptr; }
     std::shared_ptr<base::State> computeInverseKinematics(const KDL::Rotation &, const KDL::Vector &, const std::shared_ptr<base::State>) override { return nullptr; }
@@ -91,12 +104,35 @@ public:
             for (int j = 0; j <= chain.n; j++) (*m)(i, j) = R[size_t(i) * size_t(chain.n + 1) + size_t(j)];
         return m;
     }
-    bool checkSelfCollision(const std::shared_ptr<base::State> &, std::shared_ptr<base::State> &) override { return false; }
-    bool checkSelfCollision(const std::shared_ptr<base::State> &) override { return false; }
+    // Where the reference's own robot class cannot be built (no /root/reference on the GPU box, generic test chains) the harness robot
+    // answers self-collision with the oracle's restatement of xArm6.cpp:284-424 — checked bit for bit against the compiled xArm6.cpp in
+    // this container (tests/golden/make_robot_golden.py); every other kind answers false like the reference's stubs.
+    bool checkSelfCollision(const std::shared_ptr<base::State> &q1, std::shared_ptr<base::State> &q2) override {
+        if (!self_collision_checking || chain.kind != orc::XARM6) return false;
+        chain.self_collision_checking = true;
+        chain.eps_step = RRTConnectConfig::EPS_STEP;
+        const orc::Config<float> cfg{RealVectorSpaceConfig::EQUALITY_THRESHOLD, RealVectorSpaceConfig::MAX_DISTANCE, int(RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS)};
+        std::vector<float> a(size_t(chain.n)), b(size_t(chain.n));
+        for (int i = 0; i < chain.n; i++) { a[size_t(i)] = q1->getCoord(i); b[size_t(i)] = q2->getCoord(i); }
+        if (!orc::self_collision_edge(chain, cfg, a.data(), b.data())) return false;
+        Eigen::VectorXf c(chain.n);
+        for (int i = 0; i < chain.n; i++) c(i) = b[size_t(i)];
+        q2 = std::make_shared<base::RealVectorSpaceState>(c);
+        return true;
+    }
+    bool checkSelfCollision(const std::shared_ptr<base::State> &q) override {
+        if (!self_collision_checking || chain.kind != orc::XARM6) return false;
+        const orc::Config<float> cfg{RealVectorSpaceConfig::EQUALITY_THRESHOLD, RealVectorSpaceConfig::MAX_DISTANCE, int(RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS)};
+        std::vector<orc::V3<float>> sk(size_t(chain.n + 1));
+        std::vector<float> qq(size_t(chain.n));
+        for (int i = 0; i < chain.n; i++) qq[size_t(i)] = q->getCoord(i);
+        orc::skeleton(chain, qq.data(), sk.data());
+        return orc::self_collision_mask(chain, sk.data(), cfg) != 0;
+    }
 };
 
 struct Harness {
-    std::shared_ptr<HarnessRobot> robot;
+    std::shared_ptr<robots::AbstractRobot> robot;
     std::shared_ptr<env::Environment> env;
     std::shared_ptr<base::RealVectorSpace> ss;
     int n = 0;
@@ -112,13 +148,11 @@ std::shared_ptr<base::State> state_of(Harness &h, const float *q) {
 
 extern "C" {
 
-void *rvsref_create(const rvs_robot_desc *rd, float eq_thr, float max_dist, int32_t num_checks) {
+static void *harness_finish(Harness *h, const rvs_robot_desc *rd, float eq_thr, float max_dist, int32_t num_checks) {
     RealVectorSpaceConfig::EQUALITY_THRESHOLD = eq_thr;
     RealVectorSpaceConfig::MAX_DISTANCE = max_dist;
     RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS = size_t(num_checks);
-    auto *h = new Harness();
     h->n = rd->num_dofs;
-    h->robot = std::make_shared<HarnessRobot>(rd);
     std::streambuf *keep = std::cout.rdbuf();
     std::ostringstream sink;
     std::cout.rdbuf(sink.rdbuf());                              // the YAML constructor reports the (stubbed, empty) file
@@ -137,7 +171,44 @@ void *rvsref_create(const rvs_robot_desc *rd, float eq_thr, float max_dist, int3
 #endif
     return h;
 }
+
+void *rvsref_create(const rvs_robot_desc *rd, float eq_thr, float max_dist, int32_t num_checks) {
+    auto *h = new Harness();
+    h->robot = std::make_shared<HarnessRobot>(rd);
+    return harness_finish(h, rd, eq_thr, max_dist, num_checks);
+}
+
+// The reference's OWN robot class, constructed the way scenario::Scenario does (Scenario.cpp:13-51) from the reference's own URDF:
+// type = "xarm6" | "planar_2dof" | "planar_10dof" | "spatial_10dof" | "spatial_14dof" | "spatial_18dof" | "spatial_22dof".
+// gripper_length / ground_included / capsule radii come from `rd` (the scenario YAML's robot node); self_collision overrides the
+// constructor's default (Scenario.cpp:101-103).  Returns nullptr when the class cannot be built (URDF missing, chain mismatch).
+void *rvsref_create_robot(const rvs_robot_desc *rd, const char *type_c, const char *urdf, int32_t self_collision, float eq_thr, float max_dist,
+                          int32_t num_checks) {
+    const std::string type(type_c);
+    std::shared_ptr<robots::AbstractRobot> robot;
+    try {
+        if (type == "xarm6") robot = std::make_shared<robots::xArm6>(urdf, rd->gripper_length, size_t(rd->ground_included));
+        else if (type == "planar_2dof") robot = std::make_shared<robots::Planar2DOF>(urdf);
+        else if (type == "planar_10dof") robot = std::make_shared<robots::Planar10DOF>(urdf);
+        else if (type == "spatial_10dof") robot = std::make_shared<robots::Spatial10DOF>(urdf, size_t(rd->ground_included));
+        else if (type == "spatial_14dof") robot = std::make_shared<robots::Spatial14DOF>(urdf, size_t(rd->ground_included));
+        else if (type == "spatial_18dof") robot = std::make_shared<robots::Spatial18DOF>(urdf, size_t(rd->ground_included));
+        else if (type == "spatial_22dof") robot = std::make_shared<robots::Spatial22DOF>(urdf, size_t(rd->ground_included));
+        else return nullptr;
+    } catch (const std::exception &e) {
+        std::cerr << "rvsref_create_robot: " << e.what() << std::endl;
+        return nullptr;
+    }
+    if (int(robot->getNumDOFs()) != rd->num_dofs) return nullptr;
+    robot->setCapsulesRadius(std::vector<float>(rd->capsule_radius, rd->capsule_radius + rd->num_dofs));
+    robot->setSelfCollisionChecking(self_collision != 0);
+    auto *h = new Harness();
+    h->robot = robot;
+    return harness_finish(h, rd, eq_thr, max_dist, num_checks);
+}
 void rvsref_destroy(void *p) { delete static_cast<Harness *>(p); }
+// AbstractRobot::setSelfCollisionChecking (Scenario.cpp:101-103) on whichever robot class the harness holds
+void rvsref_set_self_collision(void *p, int32_t enabled) { static_cast<Harness *>(p)->robot->setSelfCollisionChecking(enabled != 0); }
 
 int rvsref_set_obstacles(void *p, const float *mn, const float *mx, const uint8_t *ground, const float *tol, int32_t M) {
     auto *h = static_cast<Harness *>(p);
@@ -392,4 +463,311 @@ int64_t rvsref_pattern_tree(void *p, const float *q_root, int32_t tree_layers, i
     return count;
 }
 
+// ---- the robot classes themselves (rows A8, A10, A11) ------------------------------------------------------------------------------
+// frames[N x n x 12] (row-major 3x3 rotation then translation, double): computeForwardKinematics (xArm6.cpp:107-134, Planar2DOF.cpp:82-108)
+int rvsref_frames(void *p, const float *q, int64_t N, double *frames) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t n = size_t(h->n);
+    for (int64_t i = 0; i < N; i++) {
+        const auto fr = h->robot->computeForwardKinematics(state_of(*h, q + size_t(i) * n));
+        if (!fr) return 2;
+        for (size_t k = 0; k < n; k++) {
+            double *o = frames + (size_t(i) * n + k) * 12;
+            for (int c = 0; c < 9; c++) o[c] = (*fr)[k].M.data[c];
+            for (int c = 0; c < 3; c++) o[9 + c] = (*fr)[k].p(c);
+        }
+    }
+    return 0;
+}
+// sk[N x (n+1) x 3]: computeSkeleton (xArm6.cpp:209-235, Planar2DOF.cpp:117-130)
+int rvsref_skeleton(void *p, const float *q, int64_t N, float *sk) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t n = size_t(h->n);
+    for (int64_t i = 0; i < N; i++) {
+        const auto m = h->robot->computeSkeleton(state_of(*h, q + size_t(i) * n));
+        for (size_t k = 0; k <= n; k++)
+            for (int c = 0; c < 3; c++) sk[(size_t(i) * (n + 1) + k) * 3 + size_t(c)] = (*m)(c, Eigen::Index(k));
+    }
+    return 0;
+}
+// R[N x n x (n+1)] row-major: computeEnclosingRadii (xArm6.cpp:237-275, Planar2DOF.cpp:132-149, Spatial10DOF.cpp:11-30)
+int rvsref_enclosing_radii(void *p, const float *q, int64_t N, float *R) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t n = size_t(h->n);
+    for (int64_t i = 0; i < N; i++) {
+        const auto m = h->robot->computeEnclosingRadii(state_of(*h, q + size_t(i) * n));
+        for (size_t a = 0; a < n; a++)
+            for (size_t b = 0; b <= n; b++) R[(size_t(i) * n + a) * (n + 1) + b] = (*m)(Eigen::Index(a), Eigen::Index(b));
+    }
+    return 0;
+}
+// xArm6 only: d[N x 4] = computeCapsulesDistance for the pairs {0-5, 1-5, 0-4, 1-4} in checkSelfCollision's order (xArm6.cpp:374-424);
+// hit[N] = checkSelfCollision(q) (capsule stage; the mesh stage answers "collide").  Other robots: hit = their constant answer, d = 0.
+int rvsref_self_collision(void *p, const float *q, int64_t N, float *d, uint8_t *hit) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t n = size_t(h->n);
+    auto *xarm = dynamic_cast<robots::xArm6 *>(h->robot.get());
+    static const size_t pairs[4][2] = {{0, 5}, {1, 5}, {0, 4}, {1, 4}};
+    for (int64_t i = 0; i < N; i++) {
+        auto s = state_of(*h, q + size_t(i) * n);
+        for (int k = 0; k < 4; k++) d[size_t(i) * 4 + size_t(k)] = xarm ? xarm->computeCapsulesDistance(s, pairs[k][0], pairs[k][1]) : 0.f;
+        const std::shared_ptr<base::State> cs = s;
+        hit[i] = h->robot->checkSelfCollision(cs) ? 1 : 0;
+    }
+    return 0;
+}
+// checkSelfCollision(q1, q2&) (xArm6.cpp:284-368): hit[E], q2_out[E x n] = q2 after the call (truncated on a hit).  eps_step = RRTConnectConfig::EPS_STEP.
+int rvsref_self_collision_edges(void *p, const float *q1, const float *q2, int64_t E, float eps_step, uint8_t *hit, float *q2_out) {
+    auto *h = static_cast<Harness *>(p);
+    const size_t n = size_t(h->n);
+    RRTConnectConfig::EPS_STEP = eps_step;
+    for (int64_t e = 0; e < E; e++) {
+        const std::shared_ptr<base::State> a = state_of(*h, q1 + size_t(e) * n);
+        std::shared_ptr<base::State> b = state_of(*h, q2 + size_t(e) * n);
+        hit[e] = h->robot->checkSelfCollision(a, b) ? 1 : 0;
+        for (size_t i = 0; i < n; i++) q2_out[size_t(e) * n + i] = b->getCoord(int(i));
+    }
+    return 0;
+}
+// what the class reports about itself (limits[n x 2], radii[n]); returns num_DOFs
+int rvsref_robot_info(void *p, float *limits, float *radii, int32_t *ground_included, float *gripper_length, int32_t *self_collision, int32_t *num_links) {
+    auto *h = static_cast<Harness *>(p);
+    const auto &rb = *h->robot;
+    for (size_t i = 0; i < rb.getNumDOFs(); i++) {
+        limits[2 * i] = rb.getLimits()[i].first; limits[2 * i + 1] = rb.getLimits()[i].second;
+        radii[i] = rb.getCapsuleRadius(i);
+    }
+    *ground_included = int32_t(rb.getGroundIncluded());
+    *gripper_length = rb.getGripperLength();
+    *self_collision = rb.getSelfCollisionChecking() ? 1 : 0;
+    *num_links = int32_t(rb.getNumLinks());
+    return int(rb.getNumDOFs());
+}
+
 }  // extern "C"
+
+#ifdef RVS_DROPIN
+// ---- the drop-in class driven like a maintainer's code would drive it (tests/test_cpp_class.py) --------------------------------------
+// base::RealVectorSpaceCUDA constructed through its URDF constructor (rvs::chain_from_urdf_file), single-query overrides against the
+// batched overloads, the State cache rules (Q19 / Q20 of SURVEY.md §8.1), the staleness guard, the dynamic environment.
+#include "rvs_urdf.h"
+namespace {
+std::string g_drv_error;
+struct DrvSpace {
+    std::shared_ptr<HarnessRobot> robot;
+    std::shared_ptr<env::Environment> env;
+    std::shared_ptr<base::RealVectorSpaceCUDA> ss;
+};
+void drv_add_boxes(env::Environment &e, const float *mn, const float *mx, const uint8_t *ground, const float *tol, int M) {
+    for (int j = 0; j < M; j++) {
+        const fcl::Vector3f lo(mn[3 * j], mn[3 * j + 1], mn[3 * j + 2]), hi(mx[3 * j], mx[3 * j + 1], mx[3 * j + 2]);
+        auto obj = std::make_shared<env::Box>(fcl::Vector3f(hi - lo), fcl::Vector3f(0.5f * (lo + hi)), fcl::Quaternionf::Identity(), ground[j] ? "ground" : "random_obstacle");
+        obj->getCollObject()->stubSetAABB(lo, hi);
+        obj->setMinDistTol(tol[j]);
+        e.addObject(obj);
+    }
+}
+DrvSpace drv_make_space(const char *urdf_path, const rvs_robot_desc *rd, const float *mn, const float *mx, const uint8_t *ground, const float *tol, int M,
+                        float eq_thr, int num_checks) {
+    RealVectorSpaceConfig::EQUALITY_THRESHOLD = eq_thr;
+    RealVectorSpaceConfig::MAX_DISTANCE = 1000.f;
+    RealVectorSpaceConfig::NUM_INTERPOLATION_VALIDITY_CHECKS = size_t(num_checks);
+    DrvSpace d;
+    d.robot = std::make_shared<HarnessRobot>(rd);
+    d.robot->setType(rd->kind == RVS_ROBOT_XARM6 ? "xarm6" : rd->kind == RVS_ROBOT_PLANAR ? "planar_" + std::to_string(rd->num_dofs) + "dof"
+                                                                                            : "spatial_" + std::to_string(rd->num_dofs) + "dof");
+    std::streambuf *keep = std::cout.rdbuf();
+    std::ostringstream sink;
+    std::cout.rdbuf(sink.rdbuf());
+    d.env = std::make_shared<env::Environment>(std::string("unused.yaml"), std::string(""));
+    std::cout.rdbuf(keep);
+    drv_add_boxes(*d.env, mn, mx, ground, tol, M);
+    d.ss = std::make_shared<base::RealVectorSpaceCUDA>(size_t(rd->num_dofs), d.robot, d.env, std::string(urdf_path));
+    return d;
+}
+std::shared_ptr<base::State> drv_state(base::StateSpace &ss, const float *q, int n) {
+    Eigen::VectorXf v(n);
+    for (int i = 0; i < n; i++) v(i) = q[i];
+    return ss.getNewState(v);
+}
+}  // namespace
+
+extern "C" {
+const char *drv_last_error() { return g_drv_error.c_str(); }
+
+// URDF reader only (no GPU needed)
+int drv_parse_urdf(const char *path, const char *robot_type, rvs_robot_desc *out) {
+    return rvs::chain_from_urdf_file(path, robot_type, out, &g_drv_error) ? 0 : 1;
+}
+
+// Runs N configurations through (a) the single-query overrides, state by state, and (b) the batched overloads.
+// Outputs: valid[N], d_c[N], profile[N*L], nearest[N*M*L*6] (zeros where the State holds nullptr), has_nearest[N],
+//          d_c_batch[N], valid_batch[N], edge_valid[N-1] (q_i -> q_{i+1}), edge_valid_batch[N-1],
+//          under[N] / under_batch[N]: underestimation w.r.t. the planes of configuration `root` (must be collision-free).
+int drv_run(const char *urdf_path, const rvs_robot_desc *rd, const float *aabb_min, const float *aabb_max, const uint8_t *is_ground, const float *tol, int M,
+            float eq_thr, int num_checks, const float *q, int N, int root,
+            uint8_t *valid, float *d_c, float *profile, float *nearest, uint8_t *has_nearest, float *d_c_batch, uint8_t *valid_batch,
+            uint8_t *edge_valid, uint8_t *edge_valid_batch, float *under, float *under_batch, uint8_t *under_is_real) {
+    try {
+        const int n = rd->num_dofs;
+        DrvSpace sp = drv_make_space(urdf_path, rd, aabb_min, aabb_max, is_ground, tol, M, eq_thr, num_checks);
+        auto &ss = sp.ss;
+        const size_t L = size_t(n);
+        std::vector<std::shared_ptr<base::State>> single, batch;
+        for (int i = 0; i < N; i++) { single.push_back(drv_state(*ss, q + size_t(i) * n, n)); batch.push_back(drv_state(*ss, q + size_t(i) * n, n)); }
+        for (int i = 0; i < N; i++) {
+            valid[i] = ss->isValid(single[i]) ? 1 : 0;
+            d_c[i] = ss->computeDistance(single[i]);
+            if (single[i]->getDistance() != d_c[i] || !single[i]->getIsRealDistance()) { g_drv_error = "State cache not written"; return 3; }
+            std::memcpy(profile + i * L, single[i]->getDistanceProfile().data(), L * sizeof(float));
+            const auto np = single[i]->getNearestPoints();
+            has_nearest[i] = np ? 1 : 0;
+            if (np)
+                for (int j = 0; j < M; j++)
+                    for (size_t l = 0; l < L; l++)
+                        for (int k = 0; k < 6; k++) nearest[((size_t(i) * M + j) * L + l) * 6 + k] = (*np)[j](k, Eigen::Index(l));
+            // cached value is returned without recomputation (RealVectorSpace.cpp:320-321)
+            if (d_c[i] > 0 && ss->computeDistance(single[i]) != d_c[i]) { g_drv_error = "cache rule broken"; return 4; }
+        }
+        const std::vector<uint8_t> vb = ss->isValidBatch(batch);
+        const std::vector<float> db = ss->computeDistanceBatch(batch);
+        std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> edges;
+        for (int i = 0; i + 1 < N; i++) {
+            edge_valid[i] = ss->isValid(single[i], single[i + 1]) ? 1 : 0;
+            edges.emplace_back(batch[i], batch[i + 1]);
+        }
+        const std::vector<uint8_t> eb = ss->isValidEdges(edges);
+        for (int i = 0; i < N; i++) {
+            valid_batch[i] = vb[i]; d_c_batch[i] = db[i];
+            if (batch[i]->getDistance() != db[i]) { g_drv_error = "batched State cache not written"; return 5; }
+            if (std::memcmp(batch[i]->getDistanceProfile().data(), profile + i * L, L * sizeof(float)) != 0) { g_drv_error = "batched profile differs from single-query profile"; return 6; }
+        }
+        for (int i = 0; i + 1 < N; i++) edge_valid_batch[i] = eb[i];
+        // underestimation against the root's planes on fresh states (a state with a real distance returns it unchanged, Q20)
+        const auto planes = single[root]->getNearestPoints();
+        if (!planes) { g_drv_error = "root configuration collides"; return 7; }
+        if (ss->computeDistanceUnderestimation(single[0], planes) != d_c[0] && d_c[0] > 0) { g_drv_error = "real distance must be returned unchanged"; return 8; }
+        std::vector<std::shared_ptr<base::State>> fresh_single, fresh_batch;
+        for (int i = 0; i < N; i++) { fresh_single.push_back(drv_state(*ss, q + size_t(i) * n, n)); fresh_batch.push_back(drv_state(*ss, q + size_t(i) * n, n)); }
+        for (int i = 0; i < N; i++) {
+            under[i] = ss->computeDistanceUnderestimation(fresh_single[i], planes);
+            under_is_real[i] = fresh_single[i]->getIsRealDistance() ? 1 : 0;
+            // rejected (a plane distance < 0): returns 0 and leaves the state untouched (d_c stays -1)
+            if (under[i] == 0 && fresh_single[i]->getDistance() != -1) { g_drv_error = "rejected underestimation touched the state"; return 9; }
+        }
+        const std::vector<float> ub = ss->computeDistanceUnderestimationBatch(fresh_batch, planes);
+        for (int i = 0; i < N; i++) under_batch[i] = ub[i];
+        // profile-only batch: distance + profile land on the State, planes do not; the next single call supplies them
+        {
+            std::vector<std::shared_ptr<base::State>> lean;
+            for (int i = 0; i < N; i++) lean.push_back(drv_state(*ss, q + size_t(i) * n, n));
+            const std::vector<float> dl = ss->computeDistanceBatch(lean, false, false);
+            for (int i = 0; i < N; i++) {
+                if (dl[i] != d_c[i]) { g_drv_error = "profile-only batch distance differs"; return 13; }
+                if (lean[i]->getNearestPoints() != nullptr) { g_drv_error = "profile-only batch left nearest points behind"; return 14; }
+                if (d_c[i] > 0 && (ss->computeDistance(lean[i]) != d_c[i] || lean[i]->getNearestPoints() == nullptr)) { g_drv_error = "single call after a profile-only batch did not supply the planes"; return 15; }
+            }
+        }
+        // staleness guard: the environment changes behind the state space's back (as MotionValidity::check / DRGBT / RRTx do) and the
+        // very next query must see it.  Object 0..M-1 are pushed 10 m away: everything becomes valid.
+        {
+            for (int j = 0; j < M; j++) {
+                auto obj = sp.env->getObject(size_t(j));
+                const fcl::Vector3f far_lo(10.f + j, 10.f, 10.f), far_hi(10.2f + j, 10.2f, 10.2f);
+                obj->getCollObject()->stubSetAABB(far_lo, far_hi);
+            }
+            for (int i = 0; i < N; i++)
+                if (!ss->isValid(drv_state(*ss, q + size_t(i) * n, n))) { g_drv_error = "stale obstacle table: a query after the environment moved still collides"; return 16; }
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_drv_error = e.what();
+        return 1;
+    }
+}
+
+// Spine sets and self-collision through the class (xArm6): extendSpinesBatch from ONE root towards S targets, checkEdgesBatch and
+// checkSelfCollisionEdges on E edges.  Outputs: q_reached[S x n], d_reached[S], status[S]; edge_ok[E]; sc_hit[E], q2_after[E x n].
+int drv_spines(const char *urdf_path, const rvs_robot_desc *rd, int self_collision, const float *aabb_min, const float *aabb_max, const uint8_t *is_ground, const float *tol,
+               int M, const float *q_root, const float *q_targets, int S, int num_layers, int num_iter_spine, int use_expanded_bubble, float d_crit,
+               float *q_reached, float *d_reached, uint8_t *status, const float *e1, const float *e2, int E, uint8_t *edge_ok, uint8_t *sc_hit, float *q2_after) {
+    try {
+        const int n = rd->num_dofs;
+        DrvSpace sp = drv_make_space(urdf_path, rd, aabb_min, aabb_max, is_ground, tol, M, 1e-4f, 10);
+        sp.robot->setSelfCollisionChecking(self_collision != 0);
+        RRTConnectConfig::EPS_STEP = 0.1f;
+        auto &ss = sp.ss;
+        auto root = drv_state(*ss, q_root, n);
+        std::vector<std::shared_ptr<base::State>> targets;
+        for (int s = 0; s < S; s++) targets.push_back(drv_state(*ss, q_targets + size_t(s) * n, n));
+        const auto res = ss->extendSpinesBatch(root, targets, size_t(num_layers), size_t(num_iter_spine), use_expanded_bubble != 0, d_crit);
+        for (int s = 0; s < S; s++) {
+            status[s] = uint8_t(res[size_t(s)].first);
+            d_reached[s] = res[size_t(s)].second->getDistance();
+            for (int i = 0; i < n; i++) q_reached[size_t(s) * n + i] = res[size_t(s)].second->getCoord(i);
+        }
+        std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> edges;
+        for (int e = 0; e < E; e++) edges.emplace_back(drv_state(*ss, e1 + size_t(e) * n, n), drv_state(*ss, e2 + size_t(e) * n, n));
+        const auto ok = ss->checkEdgesBatch(edges);
+        const auto hit = ss->checkSelfCollisionEdges(edges);
+        for (int e = 0; e < E; e++) {
+            edge_ok[e] = ok[size_t(e)]; sc_hit[e] = hit[size_t(e)];
+            for (int i = 0; i < n; i++) q2_after[size_t(e) * n + i] = edges[size_t(e)].second->getCoord(i);
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_drv_error = e.what();
+        return 1;
+    }
+}
+
+// Dynamic environment (row f-2): T consecutive MotionValidity-style checks q_t -> q_{t+1} through checkMotion (the environment
+// advances as the reference's loop would), then one what-if batch of all T motions against the final environment.
+// Outputs: valid[T], passed[T] (validity points appended to `path`), pos_after[T*M*3] (object positions mirrored back into
+// env::Object after every check), batch_valid[T].
+int drv_motion(const char *urdf_path, const rvs_robot_desc *rd, const float *dim, const float *pos, const float *vel, const float *max_vel,
+               const uint8_t *is_dynamic, const uint8_t *is_ground, const float *tol, int M, int motion_type,
+               const float *ws /*center xyz, radius, base_radius, robot_max_vel*/, const float *q, int T, int num_checks, float delta_time, uint8_t *valid,
+               int32_t *passed, float *pos_after, uint8_t *batch_valid) {
+    try {
+        const int n = rd->num_dofs;
+        DrvSpace sp = drv_make_space(urdf_path, rd, nullptr, nullptr, nullptr, nullptr, 0, 1e-4f, 10);
+        Harness hh;
+        hh.env = sp.env; hh.n = n;
+        motion_env_setup(&hh, ws, motion_type, M, dim, pos, vel, max_vel, is_dynamic, is_ground, tol);
+        auto &ss = sp.ss;
+        ss->attachDynamicEnvironment(rvs_motion_type(motion_type));
+        std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> motions;
+        for (int t = 0; t < T; t++) {
+            auto a = drv_state(*ss, q + size_t(t) * n, n), b = drv_state(*ss, q + size_t(t + 1) * n, n);
+            motions.emplace_back(a, b);
+            std::vector<std::shared_ptr<base::State>> path;
+            valid[t] = ss->checkMotion(a, b, size_t(num_checks), delta_time, &path) ? 1 : 0;
+            passed[t] = int32_t(path.size());
+            for (int j = 0; j < M; j++)
+                for (int k = 0; k < 3; k++) pos_after[(size_t(t) * M + j) * 3 + k] = ss->env->getObject(size_t(j))->getPosition()(k);
+        }
+        const std::vector<uint8_t> bv = ss->checkMotionBatch(motions, size_t(num_checks), delta_time);
+        for (int t = 0; t < T; t++) batch_valid[t] = bv[size_t(t)];
+        // the other overload (MotionValidity.cpp:60-82): the same motion handed over as explicit trajectory points must get the what-if
+        // verdict of the interpolated edge, append the points that passed, and move the environment
+        {
+            const auto &m = motions[size_t(T - 1)];
+            const float dist = ss->getNorm(m.first, m.second);
+            std::vector<Eigen::VectorXf> traj;
+            for (size_t k = 1; k <= size_t(num_checks); k++) traj.push_back(ss->interpolateEdge(m.first, m.second, dist * k / num_checks, dist)->getCoord());
+            const float before = ss->env->getObject(size_t(M - 1))->getPosition()(0);
+            std::vector<std::shared_ptr<base::State>> path;
+            const bool ok = ss->checkMotion(traj, delta_time, &path);
+            if (ok != (bv[size_t(T - 1)] != 0)) { g_drv_error = "checkMotion(traj_points) disagrees with the what-if check of the same motion"; return 10; }
+            if (ok && path.size() != size_t(num_checks)) { g_drv_error = "checkMotion(traj_points) did not append every point"; return 11; }
+            if (is_dynamic[M - 1] && max_vel[M - 1] > 0 && ss->env->getObject(size_t(M - 1))->getPosition()(0) == before) { g_drv_error = "checkMotion(traj_points) did not move the environment"; return 12; }
+        }
+        return 0;
+    } catch (const std::exception &e) {
+        g_drv_error = e.what();
+        return 1;
+    }
+}
+}  // extern "C"
+#endif  // RVS_DROPIN

@@ -6,6 +6,7 @@
 #include <stdexcept>
 
 #include "RealVectorSpaceConfig.h"
+#include "RRTConnectConfig.h"
 #include "rvs_urdf.h"
 
 // base::StateSpaceType::RealVectorSpaceCUDA is the enum value INTEGRATION.md adds to include/state_spaces/StateSpaceType.h.  A build
@@ -114,6 +115,44 @@ void base::RealVectorSpaceCUDA::refreshObstacles()
 		tol[j] = env->getObject(j)->getMinDistTol();
 	}
 	check(rvs_set_obstacles(engine, aabb_min.data(), aabb_max.data(), is_ground.data(), tol.data(), int32_t(num_objects)), "refreshObstacles");
+	uploaded_aabb.resize(6 * num_objects);
+	for (size_t j = 0; j < num_objects; j++)
+		for (int k = 0; k < 3; k++)
+		{
+			uploaded_aabb[6 * j + k] = aabb_min[3 * j + k];
+			uploaded_aabb[6 * j + 3 + k] = aabb_max[3 * j + k];
+		}
+	uploaded_tol = tol;
+	uploaded_ground = is_ground;
+	device_moves_obstacles = false;
+}
+
+/// Staleness guard.  The reference's own callers move the environment between two queries (MotionValidity.cpp:37-46,
+/// DRGBT.cpp:79-175, RRTx.cpp:97-175: env->updateEnvironment(dt) then ss->isValid(q)); the engine answers from a device copy, so
+/// every query first compares the environment's AABBs / labels / tolerances (24 M bytes of host reads) with what was uploaded and
+/// re-uploads on any difference.  The self-collision switch of the robot and RRTConnectConfig::EPS_STEP are mirrored the same way.
+void base::RealVectorSpaceCUDA::syncIfStale()
+{
+	const int sc { robot->getSelfCollisionChecking() ? 1 : 0 };
+	if (sc != uploaded_self_collision || RRTConnectConfig::EPS_STEP != uploaded_eps_step)
+	{
+		check(rvs_set_self_collision(engine, sc, RRTConnectConfig::EPS_STEP), "syncIfStale");
+		uploaded_self_collision = sc;
+		uploaded_eps_step = RRTConnectConfig::EPS_STEP;
+	}
+	if (device_moves_obstacles)
+		return;
+	bool stale { env->getNumObjects() != num_objects };
+	for (size_t j = 0; j < num_objects && !stale; j++)
+	{
+		const auto &AABB { env->getCollObject(j)->getAABB() };
+		for (int k = 0; k < 3 && !stale; k++)
+			stale = AABB.min_[k] != uploaded_aabb[6 * j + k] || AABB.max_[k] != uploaded_aabb[6 * j + 3 + k];
+		stale = stale || env->getObject(j)->getMinDistTol() != uploaded_tol[j] ||
+				(env->getObject(j)->getLabel() == "ground" ? 1 : 0) != uploaded_ground[j];
+	}
+	if (stale)
+		refreshObstacles();
 }
 
 /// env::Environment's dynamic state (Object.h:27-31, Environment.h:54-60) -> rvs_env_set.
@@ -148,6 +187,7 @@ void base::RealVectorSpaceCUDA::attachDynamicEnvironment(rvs_motion_type motion_
 	ep.robot_max_vel = env->getRobotMaxVel();
 	check(rvs_env_set(engine, &ep, dim.data(), pos.data(), nullptr, vel.data(), max_vel.data(), is_dynamic.data(), is_ground.data(), tol.data(),
 					  int32_t(num_objects)), "attachDynamicEnvironment");
+	device_moves_obstacles = true;		// from here on the engine advances the obstacles and checkMotion mirrors them back into env
 }
 
 bool base::RealVectorSpaceCUDA::checkMotion(const std::shared_ptr<base::State> q_previous, const std::shared_ptr<base::State> q_current,
@@ -252,7 +292,10 @@ void base::RealVectorSpaceCUDA::storeDistance(const std::shared_ptr<base::State>
 		return;
 	}
 	if (nearest == nullptr)
+	{
+		q->setNearestPoints(nullptr);		// planes were not asked for: never leave those of an older environment / configuration behind
 		return;
+	}
 	std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points { std::make_shared<std::vector<Eigen::MatrixXf>>
 		(num_objects, Eigen::MatrixXf(6, num_links)) };
 	for (size_t j = 0; j < num_objects; j++)
@@ -264,6 +307,7 @@ void base::RealVectorSpaceCUDA::storeDistance(const std::shared_ptr<base::State>
 
 bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q)
 {
+	syncIfStale();
 	uint8_t valid = 0;
 	check(rvs_is_valid(engine, q->getCoord().data(), 1, &valid), "isValid");
 	return valid != 0;
@@ -271,6 +315,7 @@ bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q)
 
 bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q1, const std::shared_ptr<base::State> q2)
 {
+	syncIfStale();
 	uint8_t valid = 0;
 	check(rvs_is_valid_edges(engine, q1->getCoord().data(), q2->getCoord().data(), 1, &valid), "isValid(q1, q2)");
 	return valid != 0;
@@ -278,9 +323,12 @@ bool base::RealVectorSpaceCUDA::isValid(const std::shared_ptr<base::State> q1, c
 
 float base::RealVectorSpaceCUDA::computeDistance(const std::shared_ptr<base::State> q, bool compute_again)
 {
-	if (!compute_again && q->getDistance() > 0 && q->getIsRealDistance())
+	// (a state filled by computeDistanceBatch(with_nearest_points = false) has a real distance but no planes: the next single call
+	// computes them — a state the reference itself filled always has both, so the reference's cache rule is unchanged)
+	if (!compute_again && q->getDistance() > 0 && q->getIsRealDistance() && q->getNearestPoints() != nullptr)
 		return q->getDistance();
 
+	syncIfStale();
 	float d_c = 0;
 	std::vector<float> profile(num_links), nearest(num_objects * num_links * 6);
 	check(rvs_distance(engine, q->getCoord().data(), 1, RVS_DIST_FULL, &d_c, profile.data(), nearest.data()), "computeDistance");
@@ -294,6 +342,9 @@ float base::RealVectorSpaceCUDA::computeDistanceUnderestimation(const std::share
 	if (q->getDistance() > 0 && q->getIsRealDistance()) 	// Real distance was already computed
 		return q->getDistance();
 
+	if (nearest_points == nullptr)
+		throw std::runtime_error("RealVectorSpaceCUDA::computeDistanceUnderestimation: nearest_points is null (root state without planes)");
+	syncIfStale();
 	std::vector<float> planes;
 	packPlanes(*nearest_points, planes);
 	float d_c = 0;
@@ -311,6 +362,7 @@ float base::RealVectorSpaceCUDA::computeDistanceUnderestimation(const std::share
 
 std::vector<uint8_t> base::RealVectorSpaceCUDA::isValidBatch(const std::vector<std::shared_ptr<base::State>> &states)
 {
+	syncIfStale();
 	std::vector<float> q;
 	gather(states, q);
 	std::vector<uint8_t> valid(states.size());
@@ -328,8 +380,103 @@ std::vector<uint8_t> base::RealVectorSpaceCUDA::isValidEdges
 		std::memcpy(&q2[e * num_dimensions], edges[e].second->getCoord().data(), num_dimensions * sizeof(float));
 	}
 	std::vector<uint8_t> valid(edges.size());
+	syncIfStale();
 	check(rvs_is_valid_edges(engine, q1.data(), q2.data(), int64_t(edges.size()), valid.data()), "isValidEdges");
 	return valid;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::checkStatesBatch(const std::vector<std::shared_ptr<base::State>> &states)
+{
+	syncIfStale();
+	std::vector<float> q;
+	gather(states, q);
+	std::vector<uint8_t> valid(states.size());
+	check(rvs_check_states(engine, q.data(), int64_t(states.size()), valid.data()), "checkStatesBatch");
+	return valid;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::checkEdgesBatch
+	(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges)
+{
+	syncIfStale();
+	std::vector<float> q1(edges.size() * num_dimensions), q2(edges.size() * num_dimensions);
+	for (size_t e = 0; e < edges.size(); e++)
+	{
+		std::memcpy(&q1[e * num_dimensions], edges[e].first->getCoord().data(), num_dimensions * sizeof(float));
+		std::memcpy(&q2[e * num_dimensions], edges[e].second->getCoord().data(), num_dimensions * sizeof(float));
+	}
+	std::vector<uint8_t> valid(edges.size());
+	check(rvs_check_edges(engine, q1.data(), q2.data(), int64_t(edges.size()), valid.data()), "checkEdgesBatch");
+	return valid;
+}
+
+std::vector<uint8_t> base::RealVectorSpaceCUDA::checkSelfCollisionEdges
+	(std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges)
+{
+	syncIfStale();
+	std::vector<float> q1(edges.size() * num_dimensions), q2(edges.size() * num_dimensions), q2_out(edges.size() * num_dimensions);
+	for (size_t e = 0; e < edges.size(); e++)
+	{
+		std::memcpy(&q1[e * num_dimensions], edges[e].first->getCoord().data(), num_dimensions * sizeof(float));
+		std::memcpy(&q2[e * num_dimensions], edges[e].second->getCoord().data(), num_dimensions * sizeof(float));
+	}
+	std::vector<uint8_t> hit(edges.size());
+	check(rvs_self_collision_edges(engine, q1.data(), q2.data(), int64_t(edges.size()), hit.data(), q2_out.data()), "checkSelfCollisionEdges");
+	for (size_t e = 0; e < edges.size(); e++)
+	{
+		if (!hit[e])
+			continue;
+		Eigen::VectorXf coord(num_dimensions);
+		for (size_t i = 0; i < num_dimensions; i++)
+			coord(i) = q2_out[e * num_dimensions + i];
+		edges[e].second = getNewState(coord);			// xArm6.cpp:355: q2 = make_shared<RealVectorSpaceState>(q1_temp_coord)
+	}
+	return hit;
+}
+
+std::vector<std::pair<base::State::Status, std::shared_ptr<base::State>>> base::RealVectorSpaceCUDA::extendSpinesBatch
+	(const std::shared_ptr<base::State> root, const std::vector<std::shared_ptr<base::State>> &targets, size_t num_layers, size_t num_iter_spine,
+	 bool use_expanded_bubble, float d_crit)
+{
+	std::vector<std::pair<base::State::Status, std::shared_ptr<base::State>>> result;
+	if (targets.empty())
+		return result;
+	if (root->getDistance() < 0 || root->getNearestPoints() == nullptr)		// RBTConnect.cpp:88-89
+		computeDistance(root, root->getDistance() > 0);
+	if (root->getDistance() <= 0)											// RBTConnect.cpp:91-92
+	{
+		for (size_t s = 0; s < targets.size(); s++)
+			result.emplace_back(base::State::Status::Trapped, root);
+		return result;
+	}
+	syncIfStale();
+	std::vector<float> q_e, planes;
+	gather(targets, q_e);
+	packPlanes(*root->getNearestPoints(), planes);
+	rvs_spine_params sp;
+	sp.num_layers = int32_t(num_layers);
+	sp.num_iter_spine = int32_t(num_iter_spine);
+	sp.use_expanded_bubble = use_expanded_bubble ? 1 : 0;
+	sp.d_crit = d_crit;
+	const size_t S { targets.size() };
+	std::vector<float> q_reached(S * num_dimensions), d_c(S);
+	std::vector<uint8_t> status(S);
+	check(rvs_extend_spines(engine, root->getCoord().data(), root->getDistanceProfile().data(), root->getDistance(), planes.data(), q_e.data(),
+							int32_t(S), &sp, q_reached.data(), d_c.data(), status.data()), "extendSpinesBatch");
+	for (size_t s = 0; s < S; s++)
+	{
+		Eigen::VectorXf coord(num_dimensions);
+		for (size_t i = 0; i < num_dimensions; i++)
+			coord(i) = q_reached[s * num_dimensions + i];
+		std::shared_ptr<base::State> q_new { getNewState(coord) };
+		if (d_c[s] > 0)					// a rejected underestimation returns 0 and leaves the state untouched (RealVectorSpace.cpp:428-429)
+		{
+			q_new->setDistance(d_c[s]);
+			q_new->setIsRealDistance(false);
+		}
+		result.emplace_back(static_cast<base::State::Status>(status[s]), q_new);
+	}
+	return result;
 }
 
 std::vector<float> base::RealVectorSpaceCUDA::computeDistanceBatch(const std::vector<std::shared_ptr<base::State>> &states,
@@ -351,6 +498,7 @@ std::vector<float> base::RealVectorSpaceCUDA::computeDistanceBatch(const std::ve
 	if (todo.empty())
 		return result;
 
+	syncIfStale();
 	std::vector<float> q;
 	gather(todo, q);
 	const size_t per_state = num_objects * num_links * 6;
@@ -384,6 +532,9 @@ std::vector<float> base::RealVectorSpaceCUDA::computeDistanceUnderestimationBatc
 	if (todo.empty())
 		return result;
 
+	if (nearest_points == nullptr)
+		throw std::runtime_error("RealVectorSpaceCUDA::computeDistanceUnderestimationBatch: nearest_points is null (root state without planes)");
+	syncIfStale();
 	std::vector<float> q, planes;
 	gather(todo, q);
 	packPlanes(*nearest_points, planes);

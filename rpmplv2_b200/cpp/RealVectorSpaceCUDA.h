@@ -12,12 +12,15 @@
 //     setIsRealDistance / setNearestPoints) and the same caching rules (Q20 of SURVEY.md §8.1). Everything else
 //     (sampling, interpolation, pruning, path preprocessing) is inherited unchanged.
 //   * adds the batched overloads the bur planners call for whole spine sets / edge batches:
-//         isValidBatch, isValidEdges, computeDistanceBatch, computeDistanceUnderestimationBatch.
+//         isValidBatch, isValidEdges, computeDistanceBatch, computeDistanceUnderestimationBatch, extendSpinesBatch,
+//         checkStatesBatch / checkEdgesBatch (validity AND robot->checkSelfCollision in one engine call), checkSelfCollisionEdges.
 //   * robot chain: taken from the robot's URDF with rvs::chain_from_urdf_file (rvs_urdf.h) — the same chain the
 //     reference's robot classes hand to KDL; radii, gripper length, ground_included and limits are read from the
 //     robots::AbstractRobot the scenario built. Obstacles are read from env::Environment (AABB of every
-//     fcl::CollisionObject, label == "ground", min_dist_tol); call refreshObstacles() after the environment changed
-//     (Environment::addObject / removeObject / updateEnvironment).
+//     fcl::CollisionObject, label == "ground", min_dist_tol).  Every query first compares the environment's current AABBs with the
+//     table it uploaded last and re-uploads when they differ (Environment::addObject / removeObject / updateEnvironment between two
+//     queries, as MotionValidity::check, DRGBT and RRTx do): a stale table would be a silent false `valid`.  refreshObstacles()
+//     forces the upload.  robot->getSelfCollisionChecking() and RRTConnectConfig::EPS_STEP are mirrored the same way.
 //   * dynamic scenes: attachDynamicEnvironment + checkMotion replace the K x { env->updateEnvironment; isValid } loop of
 //     planning::trajectory::MotionValidity::check by one engine call (rvs_motion_validity).
 //   * there is NO CPU fallback: the constructor throws std::runtime_error when the engine cannot be created.
@@ -68,6 +71,20 @@ namespace base
 		std::vector<float> computeDistanceUnderestimationBatch(const std::vector<std::shared_ptr<base::State>> &states,
 			const std::shared_ptr<std::vector<Eigen::MatrixXf>> nearest_points);
 
+		// One RBTConnect::extendSpine / RGBTConnect::extendGenSpine per target from ONE root whose real distance, profile and nearest
+		// points are on the State (computeDistance(root) is called when they are not): RBTConnect.cpp:85-150, RGBTConnect.cpp:73-92,
+		// xArm6 self-collision truncation included (RBTConnect.cpp:129-131, capsule stage).  Returns {status, reached state} per target;
+		// a reached state carries the distance-to-planes (setDistance / setIsRealDistance(false)) like the reference's q_new.
+		std::vector<std::pair<base::State::Status, std::shared_ptr<base::State>>> extendSpinesBatch(const std::shared_ptr<base::State> root,
+			const std::vector<std::shared_ptr<base::State>> &targets, size_t num_layers, size_t num_iter_spine, bool use_expanded_bubble, float d_crit);
+		// valid[i] = isValid(states[i]) && !robot->checkSelfCollision(states[i])                 (RRTConnect.cpp:13-15, MotionValidity.cpp:42)
+		std::vector<uint8_t> checkStatesBatch(const std::vector<std::shared_ptr<base::State>> &states);
+		// valid[e] = isValid(first, second) && !robot->checkSelfCollision(first, second)         (RRTConnect.cpp:100, RRTx.cpp:467-468, 507-508)
+		std::vector<uint8_t> checkEdgesBatch(const std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges);
+		// robot->checkSelfCollision(first, second&) for every edge (xArm6.cpp:284-368, capsule stage): hit[e]; on a hit edges[e].second is
+		// replaced by a new state at the last collision-free configuration, as the reference does with its q2 reference
+		std::vector<uint8_t> checkSelfCollisionEdges(std::vector<std::pair<std::shared_ptr<base::State>, std::shared_ptr<base::State>>> &edges);
+
 		// ---- dynamic environment on the device ----
 		// Hands env's objects (position, velocity, max_vel, label == "dynamic_obstacle"; box side = extent of the current AABB,
 		// use fcl::Box::side with the real FCL) and the workspace parameters to the engine, which from then on moves the objects
@@ -98,11 +115,18 @@ namespace base
 		void gather(const std::vector<std::shared_ptr<base::State>> &states, std::vector<float> &q) const;
 		void packPlanes(const std::vector<Eigen::MatrixXf> &nearest_points, std::vector<float> &planes) const;
 		void mirrorEnvironment();
+		void syncIfStale();          // staleness guard: obstacle table + self-collision flags
 		void storeDistance(const std::shared_ptr<base::State> &q, float d_c, const float *profile, const float *nearest) const;
 
 		rvs_handle engine = nullptr;
 		size_t num_links = 0;
 		size_t num_objects = 0;
+		std::vector<float> uploaded_aabb;          // [M][6] what the device table holds (staleness guard)
+		std::vector<float> uploaded_tol;
+		std::vector<uint8_t> uploaded_ground;
+		bool device_moves_obstacles = false;       // after attachDynamicEnvironment the ENGINE owns the obstacle motion
+		int uploaded_self_collision = -1;
+		float uploaded_eps_step = 0.f;
 	};
 }
 

@@ -24,11 +24,12 @@ namespace rvsplan
 
 	void CudaBackend::reserveSlots(int capacity) { check(rvs_store_reserve(engine, capacity), "rvs_store_reserve"); }
 
-	void CudaBackend::isValid(const float *q, int N, uint8_t *valid) { check(rvs_is_valid(engine, q, N, valid), "rvs_is_valid"); }
+	// the planners always pair the obstacle test with the robot's self-collision test (RRTConnect.cpp:13-15, :100): one engine call each
+	void CudaBackend::isValid(const float *q, int N, uint8_t *valid) { check(rvs_check_states(engine, q, N, valid), "rvs_check_states"); }
 
 	void CudaBackend::isValidEdges(const float *q1, const float *q2, int E, uint8_t *valid)
 	{
-		check(rvs_is_valid_edges(engine, q1, q2, E, valid), "rvs_is_valid_edges");
+		check(rvs_check_edges(engine, q1, q2, E, valid), "rvs_check_edges");
 	}
 
 	void CudaBackend::distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c)

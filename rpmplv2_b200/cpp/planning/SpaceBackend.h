@@ -35,9 +35,9 @@ namespace rvsplan
 		// State cache: slots 0 .. capacity-1 hold (q, d_c, d_c_profile, nearest points) of states that served as bur roots.
 		virtual void reserveSlots(int capacity) = 0;
 
-		// valid[i] = isValid(q_i)
+		// valid[i] = isValid(q_i) && !robot->checkSelfCollision(q_i)                      (RRTConnect.cpp:13-15)
 		virtual void isValid(const float *q, int N, uint8_t *valid) = 0;
-		// valid[e] = isValid(q1_e, q2_e)
+		// valid[e] = isValid(q1_e, q2_e) && !robot->checkSelfCollision(q1_e, q2_e)        (RRTConnect.cpp:100)
 		virtual void isValidEdges(const float *q1, const float *q2, int E, uint8_t *valid) = 0;
 		// d_c[i] = computeDistance(q_i); everything the spines need later stays in slot slots[i]
 		virtual void distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c) = 0;

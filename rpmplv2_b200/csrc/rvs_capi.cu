@@ -130,6 +130,10 @@ int finish(rvs_engine *h) {
     return RVS_OK;
 }
 
+int edges_dev_impl(rvs_engine *h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid);
+int underestimation_dev_impl(rvs_engine *h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R, float *d_d_c,
+                             float *d_profile, uint8_t *d_status);
+
 int build_robot(rvs_engine *h, const rvs_robot_desc *rd) {
     const char *why = fill_robot_dev(rd, &h->h_robot);
     return why ? fail(h, RVS_ERR_INVALID_ARGUMENT, why) : RVS_OK;
@@ -581,6 +585,12 @@ int rvs_is_valid_dev(rvs_handle h, const float *d_q, int64_t N, uint8_t *d_valid
 }
 int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid) {
     RVS_TRY(enter(h));
+    return edges_dev_impl(h, d_q1, d_q2, E, d_valid);
+}
+}  // extern "C"
+namespace {
+// (no enter(): the host wrappers call these after begin_call(), and enter() would switch the zero-copy mode off again)
+int edges_dev_impl(rvs_engine *h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid) {
     if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
     if (E == 0) return RVS_OK;
     if (!d_q1 || !d_q2 || !d_valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
@@ -591,9 +601,8 @@ int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, i
     a.slices = valid_slices(h, E * int64_t(h->prm.num_interpolation_validity_checks));
     return launched(h, h->lt.edge_valid(a, h->stream), "edge kernel launch");
 }
-int rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,
-                            float *d_d_c, float *d_profile, uint8_t *d_status) {
-    RVS_TRY(enter(h));
+int underestimation_dev_impl(rvs_engine *h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,
+                             float *d_d_c, float *d_profile, uint8_t *d_status) {
     if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "underestimation has no FP64 entry point");
     if (N < 0 || R < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or R");
     if (N == 0) return RVS_OK;
@@ -601,6 +610,13 @@ int rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const flo
     KArgs a = base_args(h, d_q, N);
     a.planes = d_planes; a.plane_idx = d_plane_idx; a.R = R; a.d_c = d_d_c; a.profile = d_profile; a.status = d_status;
     return launched(h, h->lt.underestimation(a, h->stream), "underestimation kernel launch");
+}
+}  // namespace
+extern "C" {
+int rvs_underestimation_dev(rvs_handle h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,
+                            float *d_d_c, float *d_profile, uint8_t *d_status) {
+    RVS_TRY(enter(h));
+    return underestimation_dev_impl(h, d_q, N, d_planes, d_plane_idx, R, d_d_c, d_profile, d_status);
 }
 int rvs_generate_configs_dev(rvs_handle h, uint64_t seed, int64_t first, int64_t N, float *d_q) {
     RVS_TRY(enter(h));
@@ -637,8 +653,8 @@ int rvs_is_valid_edges(rvs_handle h, const float *q1, const float *q2, int64_t E
     RVS_TRY(h2d(h, B_Q, q1, bytes));
     RVS_TRY(h2d(h, B_Q2, q2, bytes));
     RVS_TRY(reserve(h, B_VERD, size_t(E)));
-    RVS_TRY(rvs_is_valid_edges_dev(h, static_cast<const float *>(h->buf[B_Q].p), static_cast<const float *>(h->buf[B_Q2].p), E,
-                                   static_cast<uint8_t *>(h->buf[B_VERD].p)));
+    RVS_TRY(edges_dev_impl(h, static_cast<const float *>(h->buf[B_Q].p), static_cast<const float *>(h->buf[B_Q2].p), E,
+                           static_cast<uint8_t *>(h->buf[B_VERD].p)));
     RVS_TRY(d2h(h, valid, B_VERD, size_t(E)));
     return finish(h);
 }
@@ -659,7 +675,7 @@ int rvs_underestimation(rvs_handle h, const float *q, int64_t N, const float *pl
     RVS_TRY(reserve(h, B_DC, size_t(N) * sizeof(float)));
     RVS_TRY(reserve(h, B_PROF, size_t(N) * n * sizeof(float)));
     RVS_TRY(reserve(h, B_VERD, size_t(N)));
-    RVS_TRY(rvs_underestimation_dev(h, static_cast<const float *>(h->buf[B_Q].p), N, static_cast<const float *>(h->buf[B_PLANES].p),
+    RVS_TRY(underestimation_dev_impl(h, static_cast<const float *>(h->buf[B_Q].p), N, static_cast<const float *>(h->buf[B_PLANES].p),
                                     plane_idx ? static_cast<const int32_t *>(h->buf[B_IDX].p) : nullptr, R,
                                     static_cast<float *>(h->buf[B_DC].p), static_cast<float *>(h->buf[B_PROF].p),
                                     static_cast<uint8_t *>(h->buf[B_VERD].p)));
@@ -680,6 +696,97 @@ int rvs_enclosing_radii(rvs_handle h, const float *q, int64_t N, float *radii) {
 }
 int rvs_self_collision_capsules(rvs_handle h, const float *q, int64_t N, uint8_t *mask) {
     return run_simple(h, q, N, h ? h->lt.self_collision : nullptr, mask, size_t(N > 0 ? N : 0), true, "self collision kernel launch");
+}
+int rvs_set_self_collision(rvs_handle h, int32_t enabled, float eps_step) {
+    RVS_TRY(enter(h));
+    if (!(eps_step > 0.f)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "eps_step must be > 0");
+    h->h_robot.self_collision = enabled ? 1 : 0;
+    h->h_robot.eps_step = eps_step;
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));                        // no kernel of this handle may still be reading the old flags
+    RVS_CUDA(h, cudaMemcpy(h->d_robot, &h->h_robot, sizeof(RobotDev), cudaMemcpyHostToDevice));
+    return RVS_OK;
+}
+int rvs_get_self_collision(rvs_handle h, int32_t *enabled, float *eps_step) {
+    if (!h) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "handle is NULL");
+    if (enabled) *enabled = h->h_robot.self_collision;
+    if (eps_step) *eps_step = h->h_robot.eps_step;
+    return RVS_OK;
+}
+// ss->isValid(q) && !ss->robot->checkSelfCollision(q)  (RRTConnect.cpp:13-15, MotionValidity.cpp:42, RGBMTStar.cpp:202)
+int rvs_check_states(rvs_handle h, const float *q, int64_t N, uint8_t *valid) {
+    RVS_TRY(enter(h));
+    if (N < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "N < 0");
+    if (N == 0) return RVS_OK;
+    if (!q || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    const size_t bytes = size_t(N) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, bytes + size_t(N) + 64);
+    RVS_TRY(h2d(h, B_Q, q, bytes));
+    RVS_TRY(reserve(h, B_VERD, size_t(N)));
+    KArgs a = base_args(h, static_cast<const float *>(h->buf[B_Q].p), N);
+    a.verdict = static_cast<uint8_t *>(h->buf[B_VERD].p);
+    a.slices = valid_slices(h, N);
+    if (a.slices > 1) {
+        if (h->zc) std::memset(a.verdict, 1, size_t(N));
+        else RVS_CUDA(h, cudaMemsetAsync(a.verdict, 1, size_t(N), h->stream));
+    }
+    RVS_TRY(launched(h, h->lt.is_valid(a, h->stream), "is_valid kernel launch"));
+    if (h->h_robot.self_collision && h->h_robot.kind == RVS_ROBOT_XARM6 && h->prm.precision != RVS_PREC_F64) {
+        a.mode = 1; a.slices = 0;
+        RVS_TRY(launched(h, h->lt.self_collision(a, h->stream), "self collision kernel launch"));
+    }
+    RVS_TRY(d2h(h, valid, B_VERD, size_t(N)));
+    return finish(h);
+}
+// ss->isValid(q1, q2) && !ss->robot->checkSelfCollision(q1, q2)  (RRTConnect.cpp:100, RRTx.cpp:467-468, 507-508)
+int rvs_check_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *valid) {
+    RVS_TRY(enter(h));
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!q1 || !q2 || !valid) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, 2 * bytes + size_t(E) + 64);
+    RVS_TRY(h2d(h, B_Q, q1, bytes));
+    RVS_TRY(h2d(h, B_Q2, q2, bytes));
+    RVS_TRY(reserve(h, B_VERD, size_t(E)));
+    const float *d_q1 = static_cast<const float *>(h->buf[B_Q].p), *d_q2 = static_cast<const float *>(h->buf[B_Q2].p);
+    uint8_t *d_valid = static_cast<uint8_t *>(h->buf[B_VERD].p);
+    RVS_TRY(edges_dev_impl(h, d_q1, d_q2, E, d_valid));
+    if (h->h_robot.self_collision && h->h_robot.kind == RVS_ROBOT_XARM6 && h->prm.precision != RVS_PREC_F64) {
+        KArgs a = base_args(h, d_q1, E);
+        a.q2 = d_q2; a.verdict = d_valid; a.d_c = nullptr;
+        RVS_TRY(launched(h, h->lt.self_collision_edges(a, h->stream), "self collision edge kernel launch"));
+    }
+    RVS_TRY(d2h(h, valid, B_VERD, size_t(E)));
+    return finish(h);
+}
+int rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_hit, float *d_q2_out) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "self-collision runs on REF32 / FAST32 handles");
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!d_q1 || !d_q2 || !d_hit || !d_q2_out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    KArgs a = base_args(h, d_q1, E);
+    a.q2 = d_q2; a.verdict = d_hit; a.d_c = d_q2_out;
+    return launched(h, h->lt.self_collision_edges(a, h->stream), "self collision edge kernel launch");
+}
+int rvs_self_collision_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *hit, float *q2_out) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "self-collision runs on REF32 / FAST32 handles");
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!q1 || !q2 || !hit || !q2_out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, 3 * bytes + size_t(E) + 64);
+    RVS_TRY(h2d(h, B_Q, q1, bytes));
+    RVS_TRY(h2d(h, B_Q2, q2, bytes));
+    RVS_TRY(reserve(h, B_VERD, size_t(E)));
+    RVS_TRY(reserve(h, B_DC, bytes));
+    KArgs a = base_args(h, static_cast<const float *>(h->buf[B_Q].p), E);
+    a.q2 = static_cast<const float *>(h->buf[B_Q2].p); a.verdict = static_cast<uint8_t *>(h->buf[B_VERD].p); a.d_c = h->buf[B_DC].p;
+    RVS_TRY(launched(h, h->lt.self_collision_edges(a, h->stream), "self collision edge kernel launch"));
+    RVS_TRY(d2h(h, hit, B_VERD, size_t(E)));
+    RVS_TRY(d2h(h, q2_out, B_DC, bytes));
+    return finish(h);
 }
 
 
@@ -737,7 +844,7 @@ int rvs_extend_spines(rvs_handle h, const float *q_root, const float *root_profi
     a.q_root = d_in; a.root_profile = d_in + n; a.q_targets = d_in + 2 * n; a.root_d_c = root_d_c;
     a.root_planes = static_cast<const float *>(h->buf[B_PLANES].p);
     a.num_layers = sp->num_layers; a.num_iter_spine = sp->num_iter_spine; a.use_expanded_bubble = sp->use_expanded_bubble;
-    a.d_crit = sp->d_crit; a.max_dist = h->prm.max_distance;
+    a.d_crit = sp->d_crit; a.max_dist = h->prm.max_distance; a.eq_thr = h->prm.equality_threshold;
     a.q_reached = d_out; a.d_c_reached = d_out + size_t(S) * n; a.status = static_cast<uint8_t *>(h->buf[B_VERD].p);
     RVS_TRY(launched(h, h->lt.spines(a, h->stream), "spine kernel launch"));
     RVS_TRY(d2h_from(h, q_reached, d_out, size_t(S) * n * sizeof(float)));

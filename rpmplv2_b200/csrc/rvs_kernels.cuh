@@ -404,7 +404,8 @@ __global__ void __launch_bounds__(kBlock) self_collision_kernel(const KArgs a) {
             if (d < R(0)) mask |= uint8_t(1u << k);
         }
     }
-    a.verdict[cfg] = mask;
+    if (a.mode == 1) { if (mask) a.verdict[cfg] = 0; }          // rvs_check_states: clear the validity verdict of a self-colliding configuration
+    else a.verdict[cfg] = mask;
 }
 
 
@@ -435,8 +436,8 @@ __global__ void __launch_bounds__(kBlock) primitive_kernel(const KArgs a) {
 
 // ---- generalized-bur spines (RBTConnect::extendSpine, RBTConnect.cpp:85-150; RGBTConnect::extendGenSpine, RGBTConnect.cpp:73-92) ----
 // One thread per target configuration q_e; all spines start at the same root (its profile, d_c and nearest-point planes come
-// from one FULL distance query). Self-collision truncation (RBTConnect.cpp:129-131) is not applied: it is `false` for every
-// robot but xArm6, whose check ends in an FCL mesh test that is outside this engine.
+// from one FULL distance query). Self-collision truncation (RBTConnect.cpp:129-131) is applied through self_collision_edge_of()
+// when rvs_set_self_collision enabled it: the capsule stage of xArm6::checkSelfCollision(q_temp, q_new); `false` for every other robot.
 
 // a.dot(b) of dynamic Eigen vectors: SSE2 linear-vectorised reduction order (packets of 4, two accumulators, predux =
 // (l0+l2)+(l1+l3), scalar tail) — the same assumption as coord_norm above. a is read with a stride (a matrix column).
@@ -469,6 +470,84 @@ __device__ __forceinline__ float dot_dyn(const float *a, int stride, const float
         for (int i = 1; i < n; i++) res = res + pr(i);
     }
     return res;
+}
+
+// xArm6::computeCapsulesDistance (xArm6.cpp:417-424) on a packed skeleton
+__device__ __forceinline__ float capsules_distance(const RobotDev *__restrict__ rb, const float *sk, int a, int b, float eq_thr, float max_dist) {
+    auto P = [&](int k) { return V3<float>{sk[3 * k], sk[3 * k + 1], sk[3 * k + 2]}; };
+    return seg_seg_distance<float>(P(a), P(a + 1), P(b), P(b + 1), eq_thr, max_dist) - rb->radius[a] - rb->radius[b];
+}
+
+// The four bubble steps of one iteration of xArm6::checkSelfCollision(q1, q2) (xArm6.cpp:303-314) from the skeleton and the
+// enclosing radii of q1_temp and delta = |q2 - q1_temp|; returns step = min(min(step04, step05), min(step14, step15)) with the
+// reference's std::min / std::max ((b < a) ? b : a, (a < b) ? b : a: inf / NaN of a zero-length motion propagate as there).
+__device__ __forceinline__ float self_collision_steps(const RobotDev *__restrict__ rb, const float *sk, const float *Rm, const float *delta, float eq_thr,
+                                                      float max_dist, float &step04, float &step05, float &step14, float &step15) {
+    constexpr int n = 6, W = 7;
+    const float phi2 = dot_dyn(Rm + 2, W, delta, n), phi4 = dot_dyn(Rm + 4, W, delta, n), phi5 = dot_dyn(Rm + 5, W, delta, n), phi6 = dot_dyn(Rm + 6, W, delta, n);
+    const float m45 = phi4 < phi5 ? phi5 : phi4, m56 = phi5 < phi6 ? phi6 : phi5;
+    step04 = capsules_distance(rb, sk, 0, 4, eq_thr, max_dist) / m45;
+    step05 = capsules_distance(rb, sk, 0, 5, eq_thr, max_dist) / m56;
+    step14 = capsules_distance(rb, sk, 1, 4, eq_thr, max_dist) / (phi2 + m45);
+    step15 = capsules_distance(rb, sk, 1, 5, eq_thr, max_dist) / (phi2 + m56);
+    const float a = step05 < step04 ? step05 : step04, b = step15 < step14 ? step15 : step14;
+    return b < a ? b : a;
+}
+
+// xArm6::checkSelfCollision(q1, q2&) (xArm6.cpp:284-368), capsule stage, one thread.  The FCL mesh confirmation of
+// checkRealSelfCollision (xArm6.cpp:426-464) is outside this engine: a negative capsule distance counts as a self-collision
+// (conservative).  On a hit q2 is overwritten with the last collision-free configuration.  Every other robot class
+// answers false (Planar2DOF.cpp:151-161, Spatial10DOF.cpp:32-43).  Out of line: it is called from the spine kernels' rare path.
+template <class F>
+__device__ __noinline__ bool self_collision_edge_of(const RobotDev *__restrict__ rb, const float *q1, float *q2, float eq_thr, float max_dist) {
+    if (rb->kind != RVS_ROBOT_XARM6 || !rb->self_collision || rb->n != 6) return false;
+    constexpr int n = 6, W = 7;
+    float sk[3 * W], Rm[n * W], delta[n], q1t[n], qn[n];
+    float step04 = 0.f, step05 = 0.f, step14 = 0.f, step15 = 0.f;
+    for (int i = 0; i < n; i++) q1t[i] = q1[i];
+    for (int num_iter = 0;;) {
+        fk_skeleton<F, float>(rb, q1t, sk);
+        enclosing_radii_of<float>(rb, sk, Rm);
+        for (int i = 0; i < n; i++) delta[i] = fabsf(q2[i] - q1t[i]);
+        const float step = self_collision_steps(rb, sk, Rm, delta, eq_thr, max_dist, step04, step05, step14, step15);
+        if (step > 1.f) return false;
+        if (++num_iter == 5 || step <= 0.f) break;
+        if (step > 0.f)
+            for (int i = 0; i < n; i++) q1t[i] = q1t[i] + step * (q2[i] - q1t[i]);
+    }
+    const float D = coord_norm(q2, q1t, n), eps = rb->eps_step;
+    float dist = D;
+    for (bool advanced = true; advanced;) {
+        if (dist > eps) { for (int i = 0; i < n; i++) qn[i] = q1t[i] + (q2[i] - q1t[i]) / dist * eps; }
+        else { for (int i = 0; i < n; i++) qn[i] = q2[i]; advanced = false; }
+        dist = coord_norm(q2, qn, n);
+        const float step_crit = 1.f - dist / D;
+        fk_skeleton<F, float>(rb, qn, sk);
+        // pairs in the reference's order {0-5, 1-5, 0-4, 1-4}; a pair is skipped while its own bubble step covers the marched fraction
+        const bool hit = (!(step05 > step_crit) && capsules_distance(rb, sk, 0, 5, eq_thr, max_dist) < 0.f) ||
+                         (!(step15 > step_crit) && capsules_distance(rb, sk, 1, 5, eq_thr, max_dist) < 0.f) ||
+                         (!(step04 > step_crit) && capsules_distance(rb, sk, 0, 4, eq_thr, max_dist) < 0.f) ||
+                         (!(step14 > step_crit) && capsules_distance(rb, sk, 1, 4, eq_thr, max_dist) < 0.f);
+        if (hit) { for (int i = 0; i < n; i++) q2[i] = q1t[i]; return true; }
+        for (int i = 0; i < n; i++) q1t[i] = qn[i];
+    }
+    return false;
+}
+
+// rvs_self_collision_edges: a.q = q1 [E x n], a.q2 = q2 [E x n]; a.verdict[E] = 1 on a self-collision, a.d_c = q2 after the call [E x n]
+template <class F, class R>
+__global__ void __launch_bounds__(kBlock) self_collision_edge_kernel(const KArgs a) {
+    const RobotDev *__restrict__ rb = a.robot;
+    const int n = rb->n;
+    const int64_t e = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    if (e >= a.N) return;
+    float q1[kMaxDofs], q2[kMaxDofs];
+    for (int i = 0; i < n; i++) { q1[i] = a.q[e * n + i]; q2[i] = a.q2[e * n + i]; }
+    const bool hit = self_collision_edge_of<F>(rb, q1, q2, a.eq_thr, a.max_dist);
+    if (!a.d_c) { if (hit) a.verdict[e] = 0; return; }          // rvs_check_edges: clear the validity verdict of a self-colliding motion
+    a.verdict[e] = hit ? 1 : 0;
+    float *out = static_cast<float *>(a.d_c) + e * n;
+    for (int i = 0; i < n; i++) out[i] = q2[i];
 }
 
 template <class F>
@@ -513,7 +592,10 @@ __global__ void __launch_bounds__(64) spine_kernel(const SpineArgs a) {
                     status = 3;
                 } else
                     for (int i = 0; i < n; i++) q_new[i] = q_temp[i] + step * (q_e[i] - q_temp[i]);
-                if (counter == a.num_iter_spine || status != 1) break;
+                // RBTConnect.cpp:129-131: a self-collision on [q_temp, q_new] truncates q_new; Trapped when nothing was gained
+                const bool self_collision = self_collision_edge_of<F>(rb, q_temp, q_new, a.eq_thr, a.max_dist);
+                if (self_collision) status = !(coord_norm(q_temp, q_new, n) < a.eq_thr) ? 1 : 2;
+                if (counter == a.num_iter_spine || status != 1 || self_collision) break;
                 fk_skeleton<F, float>(rb, q_new, sk_new);
                 float rho_k_prev = 0.f;
                 for (int k = 1; k <= L; k++) {

@@ -16,6 +16,7 @@ struct LaunchTable {
     LaunchFn skeleton;
     LaunchFn enclosing_radii;
     LaunchFn self_collision;
+    LaunchFn self_collision_edges;
     LaunchFn primitive;
     cudaError_t (*spines)(const SpineArgs &, cudaStream_t);
     cudaError_t (*store_distance)(const StoreArgs &, cudaStream_t);

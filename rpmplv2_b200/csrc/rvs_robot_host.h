@@ -23,6 +23,7 @@ inline const char *fill_robot_dev(const rvs_robot_desc *rd, RobotDev *out) {
     RobotDev &r = *out;
     std::memset(&r, 0, sizeof(r));
     r.kind = rd->kind; r.n = rd->num_dofs; r.ground_included = rd->ground_included; r.gripper_length = rd->gripper_length;
+    r.self_collision = 0; r.eps_step = 0.1f;                               // rvs_set_self_collision switches the xArm6 check on
     const int n = r.n;
     for (int k = 0; k <= n; k++) {
         for (int c = 0; c < 3; c++) r.xyz[k][c] = rd->joint_xyz[k][c];

@@ -414,7 +414,38 @@ __global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const Sto
                 }
                 if (step > 1.f) { q_new = q_e; status = 3; }
                 else q_new = q_temp + step * (q_e - q_temp);
-                if (counter == a.num_iter_spine || status != 1) break;
+                // RBTConnect.cpp:129-131: self-collision on [q_temp, q_new] (xArm6 only, n == 6).  The first bubble iteration of
+                // xArm6::checkSelfCollision needs exactly the skeleton and enclosing radii of q_temp that are already in shared
+                // memory: lane 0 evaluates its four bubble steps, and `step > 1` (no self-collision possible, by far the common
+                // answer) ends the check there.  Otherwise lane 0 walks the whole routine (bubble steps + EPS_STEP marching).
+                bool self_collision = false;
+                if (rb->self_collision && rb->kind == RVS_ROBOT_XARM6 && n == 6) {
+                    __syncwarp();
+                    if (own) delta[lane] = fabsf(q_new - q_temp);
+                    __syncwarp();
+                    float q1v[6], q2v[6];
+#pragma unroll
+                    for (int k = 0; k < 6; k++) { q1v[k] = __shfl_sync(0xffffffffu, q_temp, k); q2v[k] = __shfl_sync(0xffffffffu, q_new, k); }
+                    int hit = 0;
+                    if (lane == 0) {
+                        float s04, s05, s14, s15;
+                        const float sc_step = self_collision_steps(rb, sk_use, Rm, delta, a.eq_thr, a.max_dist, s04, s05, s14, s15);
+                        if (!(sc_step > 1.f)) hit = self_collision_edge_of<F>(rb, q1v, q2v, a.eq_thr, a.max_dist) ? 1 : 0;
+                    }
+                    hit = __shfl_sync(0xffffffffu, hit, 0);
+                    if (hit) {
+                        self_collision = true;
+                        float mine = q_new;
+#pragma unroll
+                        for (int k = 0; k < 6; k++) { const float v = __shfl_sync(0xffffffffu, q2v[k], 0); if (lane == k) mine = v; }
+                        q_new = mine;
+                        float moved = 0.f;
+                        if (lane == 0) moved = coord_norm(q1v, q2v, 6);
+                        moved = __shfl_sync(0xffffffffu, moved, 0);
+                        status = !(moved < a.eq_thr) ? 1 : 2;
+                    }
+                }
+                if (counter == a.num_iter_spine || status != 1 || self_collision) break;
                 fk_of(q_new, sk_new);
                 // rho_k = |sk_k - sk_new_k| for k = 1..L (lane k-1); rho_profile[k-1] = max(rho_{k-1}, rho_k); rho = max(rho, rho_k)
                 float rho_k = 0.f;

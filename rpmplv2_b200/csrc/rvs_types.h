@@ -40,6 +40,8 @@ struct RobotDev {
     int32_t n;                       // DOFs == links
     int32_t ground_included;
     float gripper_length;
+    int32_t self_collision;          // AbstractRobot::getSelfCollisionChecking (rvs_set_self_collision); only xArm6 has a check at all
+    float eps_step;                  // RRTConnectConfig::EPS_STEP: marching step of xArm6::checkSelfCollision(q1, q2) (xArm6.cpp:340-341)
 };
 
 // Arguments of the hot-path kernels (passed by value).
@@ -85,7 +87,7 @@ struct SpineArgs {
     const float *root_planes;     // [M][L][6]
     const float *q_targets;       // [S][n]
     int32_t num_layers, num_iter_spine, use_expanded_bubble;
-    float d_crit, max_dist;
+    float d_crit, max_dist, eq_thr;
     float *q_reached;             // [S][n]
     float *d_c_reached;           // [S]
     uint8_t *status;              // [S]  base::State::Status: 1 Advanced, 2 Trapped, 3 Reached

@@ -9,6 +9,10 @@
 #include "rvs_env.cuh"
 #include "rvs_launch.h"
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 namespace rvs {
 namespace {
 
@@ -19,16 +23,33 @@ inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1)
 constexpr int64_t kSmallValid = 2048;       // validity items (configurations, or edges x checks) up to which one CTA per item is used
 constexpr int64_t kSmallBatch = RVS_SMALL_BATCH;      // rvs_distance* calls up to this many configurations (4x for FULL) take the one-CTA-per-configuration kernel
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device).  One table per process: (function, device) -> bytes already
+// granted; looked up under a mutex because handles on different devices may be driven from different host threads.
+inline cudaError_t raise_smem_limit(const void *fn, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<const void *, int>, size_t> granted;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &have = granted[{fn, dev}];
+    if (smem <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    if (e == cudaSuccess) have = smem;
+    return e;
+}
+
 template <class F, class R>
 struct Variant {
     template <int MODE, int G>
     static cudaError_t distance_wq(const KArgs &a, cudaStream_t st) {
         const size_t smem = wq_smem_bytes<R, G>(a.robot_n_hint);
-        static size_t configured = 0;                     // per instantiation: raise the dynamic shared-memory limit once
-        if (smem > configured) {
-            const cudaError_t e = cudaFuncSetAttribute(distance_wq_kernel<F, R, MODE, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        // The dynamic shared-memory limit is an attribute of the function ON THE CURRENT DEVICE: handles may live on several devices
+        // (and host threads) of one process, so it is raised per device (a small table indexed by cudaGetDevice, written under a
+        // mutex) and not once per process.
+        if (smem > 48u * 1024u) {
+            const cudaError_t e = raise_smem_limit(reinterpret_cast<const void *>(distance_wq_kernel<F, R, MODE, G>), smem);
             if (e != cudaSuccess) return e;
-            configured = smem;
         }
         distance_wq_kernel<F, R, MODE, G><<<grid_for(a.N, kWqBlock), kWqBlock, smem, st>>>(a);
         return cudaGetLastError();
@@ -61,11 +82,9 @@ struct Variant {
     template <int G, bool EDGE>
     static cudaError_t valid_wq(const KArgs &a, int64_t items, cudaStream_t st) {
         const size_t smem = vq_smem_bytes<R, G>(a.robot_n_hint);
-        static size_t configured = 0;
-        if (smem > configured) {
-            const cudaError_t e = cudaFuncSetAttribute(valid_wq_kernel<F, R, G, EDGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+        if (smem > 48u * 1024u) {
+            const cudaError_t e = raise_smem_limit(reinterpret_cast<const void *>(valid_wq_kernel<F, R, G, EDGE>), smem);
             if (e != cudaSuccess) return e;
-            configured = smem;
         }
         valid_wq_kernel<F, R, G, EDGE><<<dim3(grid_for(items, kWqBlock), unsigned(a.slices > 1 ? a.slices : 1)), kWqBlock, smem, st>>>(a);
         return cudaGetLastError();
@@ -111,6 +130,11 @@ struct Variant {
         self_collision_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
+    static cudaError_t self_collision_edges(const KArgs &a, cudaStream_t st) {
+        if (a.N <= 0) return cudaSuccess;
+        self_collision_edge_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        return cudaGetLastError();
+    }
     static cudaError_t primitive(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
         primitive_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
@@ -137,7 +161,7 @@ struct Variant {
         return cudaGetLastError();
     }
     static LaunchTable table() {
-        return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, primitive, spines, store_distance, store_spines,
+        return {distance, is_valid, edge_valid, underestimation, skeleton, enclosing_radii, self_collision, self_collision_edges, primitive, spines, store_distance, store_spines,
                 motion_valid};
     }
 };

@@ -65,6 +65,12 @@ SYMBOLS = {
     "rvs_skeleton": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_f32p]),
     "rvs_enclosing_radii": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_f32p]),
     "rvs_self_collision_capsules": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_set_self_collision": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_float]),
+    "rvs_get_self_collision": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)]),
+    "rvs_check_states": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_check_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
+    "rvs_self_collision_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p, c_f32p]),
+    "rvs_self_collision_edges_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "rvs_extend_spines": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int32,
                                          ctypes.POINTER(RvsSpineParams), c_f32p, c_f32p, c_u8p]),
     "rvs_store_reserve": (ctypes.c_int, [_H, ctypes.c_int32]),
@@ -146,6 +152,10 @@ class Engine:
         if rc != 0:
             raise RvsError(rc, (self._lib.rvs_last_error(None) or b"").decode())
         self._h = h
+        # robots::xArm6's constructor switches self-collision checking on (xArm6.cpp:67; the scenario YAML may override it,
+        # Scenario.cpp:101-103); EPS_STEP 0.1 is the shipped RRTConnectConfig value.  Precision F64 has no self-collision kernels.
+        if robot.self_collision_checking and self.params.precision != PREC_F64:
+            self.set_self_collision(True, 0.1)
 
     # -- plumbing ---------------------------------------------------------------------------------------------
     def _check(self, rc: int):
@@ -359,6 +369,32 @@ class Engine:
         out = np.empty(q.shape[0], np.uint8)
         self._check(self._lib.rvs_self_collision_capsules(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_u8p)))
         return out
+
+    def set_self_collision(self, enabled: bool, eps_step: float = 0.1) -> None:
+        """AbstractRobot::setSelfCollisionChecking (Scenario.cpp:101-103) + RRTConnectConfig::EPS_STEP (xArm6.cpp:340-341).
+        While on, the spine entry points apply the reference's self-collision truncation (RBTConnect.cpp:129-131)."""
+        self._check(self._lib.rvs_set_self_collision(self._h, 1 if enabled else 0, float(eps_step)))
+
+    def self_collision_edges(self, q1, q2):
+        """xArm6::checkSelfCollision(q1, q2&), capsule stage (xArm6.cpp:284-368) -> (hit[E], q2 after the call)."""
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        hit, out = np.empty(q1.shape[0], np.uint8), np.empty_like(q2)
+        self._check(self._lib.rvs_self_collision_edges(self._h, _p(q1, c_f32p), _p(q2, c_f32p), q1.shape[0], _p(hit, c_u8p), _p(out, c_f32p)))
+        return hit, out
+
+    def check_states(self, q) -> np.ndarray:
+        """isValid(q) && !robot->checkSelfCollision(q) in one call (RRTConnect.cpp:13-15, MotionValidity.cpp:42)."""
+        q = _f32(q, (-1, self.n))
+        out = np.empty(q.shape[0], np.uint8)
+        self._check(self._lib.rvs_check_states(self._h, _p(q, c_f32p), q.shape[0], _p(out, c_u8p)))
+        return out.astype(bool)
+
+    def check_edges(self, q1, q2) -> np.ndarray:
+        """isValid(q1, q2) && !robot->checkSelfCollision(q1, q2) in one call (RRTConnect.cpp:100, RRTx.cpp:467-468)."""
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        out = np.empty(q1.shape[0], np.uint8)
+        self._check(self._lib.rvs_check_edges(self._h, _p(q1, c_f32p), _p(q2, c_f32p), q1.shape[0], _p(out, c_u8p)))
+        return out.astype(bool)
 
     def capsule_box_distance(self, AB, radius, obs) -> np.ndarray:
         """Batched CollisionAndDistance::distanceCapsuleToBox: rows (d, has_points, P1 xyz, P2 xyz)."""

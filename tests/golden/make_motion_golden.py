@@ -14,6 +14,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refharness  # noqa: E402
 import scenes  # noqa: E402
 from rpmplv2_b200 import robots, synthetic  # noqa: E402
 from rpmplv2_b200.engine import MOTION_TYPES  # noqa: E402
@@ -53,9 +55,9 @@ def delta_time(K, max_iter_time):
 
 
 def run_reference(lib, rb, sc, law, q1, q2, K, max_iter_time, points=None):
-    lib.rvsref_create.restype = ctypes.c_void_p
-    desc = rb.to_desc()
-    h = ctypes.c_void_p(lib.rvsref_create(ctypes.byref(desc), ctypes.c_float(1e-4), ctypes.c_float(1000.0), 10))
+    # MotionValidity::check also asks robot->checkSelfCollision(q) (MotionValidity.cpp:42,71): kept off here, the engine's motion check
+    # covers the obstacle part (the capsule self-collision of the K points is a separate engine call)
+    h, _ = refharness.create(lib, rb, 1e-4, self_collision=False)
     prm = np.array(list(ENV["ws_center"]) + [ENV["ws_radius"], ENV["base_radius"], ENV["robot_max_vel"]], np.float32)
     T, M = len(q1), len(sc["dim"])
     c = lambda k, dt: np.ascontiguousarray(sc[k], dt)
@@ -72,7 +74,7 @@ def run_reference(lib, rb, sc, law, q1, q2, K, max_iter_time, points=None):
 
 
 if __name__ == "__main__":
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    lib = refharness.load()
     data = {}
     for k, (robot, M_dyn, law, T, K, mit) in enumerate(CASES):
         rb, sc, q1, q2 = case_inputs(robot, M_dyn, law, T)

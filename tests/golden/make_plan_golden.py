@@ -16,6 +16,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refharness  # noqa: E402
 import scenes  # noqa: E402
 from rpmplv2_b200 import planning  # noqa: E402
 
@@ -39,9 +41,8 @@ def config(kind, **over):
 def open_reference(lib, name):
     fn, qs, qg = SCENARIOS[name]
     rb, mn, mx, g, tol = fn()
-    lib.rvsref_create.restype = ctypes.c_void_p
-    desc = rb.to_desc()
-    h = ctypes.c_void_p(lib.rvsref_create(ctypes.byref(desc), ctypes.c_float(1e-4), ctypes.c_float(1000.0), 10))
+    h, _ = refharness.create(lib, rb, 1e-4)      # the reference's own robot class; xArm6 plans with self_collision_checking = true
+    lib.rvsref_set_self_collision(h, int(rb.self_collision_checking))
     mn, mx, g, tol = [np.ascontiguousarray(a) for a in (mn, mx, g, tol)]
     lib.rvsref_set_obstacles(h, P(mn, f32p), P(mx, f32p), P(g, u8p), P(tol, f32p), len(g))
     return h, rb, np.asarray(qs, np.float32), np.asarray(qg, np.float32)
@@ -61,7 +62,7 @@ def run_reference(lib, h, n, cfg, qs, qg, seed):
 
 
 if __name__ == "__main__":
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    lib = refharness.load()
     data = {}
     for name in SCENARIOS:
         h, rb, qs, qg = open_reference(lib, name)

@@ -12,6 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refharness  # noqa: E402
 import scenes  # noqa: E402
 from rpmplv2_b200 import robots, synthetic  # noqa: E402
 
@@ -40,9 +42,7 @@ def inputs(rb, N):
 
 
 def run_reference(lib, rb, mn, mx, g, tol, thr, N):
-    lib.rvsref_create.restype = ctypes.c_void_p
-    desc = rb.to_desc()
-    h = ctypes.c_void_p(lib.rvsref_create(ctypes.byref(desc), ctypes.c_float(thr), ctypes.c_float(1000.0), 10))
+    h, _ = refharness.create(lib, rb, thr)       # the reference's own robot class (FK through the KDL work-alike) where it ships one
     mn, mx, g, tol = [np.ascontiguousarray(a) for a in (mn, mx, g, tol)]
     M, n = len(g), rb.num_dofs
     lib.rvsref_set_obstacles(h, P(mn, f32p), P(mx, f32p), P(g, u8p), P(tol, f32p), M)
@@ -61,7 +61,7 @@ def run_reference(lib, rb, mn, mx, g, tol, thr, N):
 
 
 if __name__ == "__main__":
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    lib = refharness.load()
     data = {}
     for name, (rb, mn, mx, g, tol, thr, N) in cases().items():
         r = run_reference(lib, rb, mn, mx, g, tol, thr, N)

@@ -14,6 +14,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refharness  # noqa: E402
 import make_rvs_golden as rvs  # noqa: E402
 from rpmplv2_b200 import synthetic  # noqa: E402
 
@@ -42,9 +44,10 @@ def spine_inputs(rb, N, root_free):
 
 
 def open_reference(lib, rb, mn, mx, g, tol, thr):
-    lib.rvsref_create.restype = ctypes.c_void_p
-    desc = rb.to_desc()
-    h = ctypes.c_void_p(lib.rvsref_create(ctypes.byref(desc), ctypes.c_float(thr), ctypes.c_float(1000.0), 10))
+    # the reference's own robot class where it ships one: its computeEnclosingRadii and — xArm6, self_collision_checking = true as in
+    # every shipped xarm6 scenario — its checkSelfCollision(q_temp, q_new) inside extendSpine (RBTConnect.cpp:129-131)
+    h, _ = refharness.create(lib, rb, thr)
+    lib.rvsref_set_self_collision(h, int(rb.self_collision_checking))
     mn, mx, g, tol = [np.ascontiguousarray(a) for a in (mn, mx, g, tol)]
     lib.rvsref_set_obstacles(h, P(mn, f32p), P(mx, f32p), P(g, u8p), P(tol, f32p), len(g))
     return h
@@ -68,7 +71,7 @@ def run_reference_spines(lib, h, n, q_r, q_e, prm, mode):
 
 
 if __name__ == "__main__":
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    lib = refharness.load()
     data = {}
     for name, (rb, mn, mx, g, tol, thr, N) in rvs.cases().items():
         h = open_reference(lib, rb, mn, mx, g, tol, thr)

@@ -12,6 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import refharness  # noqa: E402
 import make_plan_golden as mp  # noqa: E402
 
 f32p, u8p, i32p = mp.f32p, mp.u8p, ctypes.POINTER(ctypes.c_int32)
@@ -32,7 +34,7 @@ def run_reference(lib, h, n, q_root, tree_layers, prm, max_nodes=20000):
 
 
 if __name__ == "__main__":
-    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "librvs_ref.so"))
+    lib = refharness.load()
     data = {}
     for k, (name, layers, prm) in enumerate(CASES):
         h, rb, qs, qg = mp.open_reference(lib, name)

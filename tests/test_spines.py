@@ -79,6 +79,8 @@ def test_oracle_spines_follow_the_recurrences_and_stay_collision_free(ob, case, 
     tol = np.full_like(tol, 1000.0)                                   # planes of every obstacle (as the dynamic planners configure it)
     S = 60
     o, q_root, prof, d_root, planes, targets = _root_and_targets(ob, rb, mn, mx, g, tol, S)
+    o.set_self_collision(False)      # the numpy re-expression below covers the bubble recurrences only; the xArm6 self-collision
+                                     # truncation (RBTConnect.cpp:129-131) is pinned by spine_golden / robot_golden (the reference's own code)
     sp = robots.RvsSpineParams(5, iters, expanded, 0.05)
     q_out, d_out, status = o.extend_spines(q_root, prof, d_root, planes, targets, sp)
     assert status[0] == REACHED and (q_out[0] == targets[0]).all()
@@ -245,7 +247,8 @@ def _compare_spines(got, d_root, want, mode, exact=True, tag=""):
     S = len(st_w)
     trapped = ~(d_root > 0)
     assert np.array_equal(st, st_w), tag
-    assert ((st_w == TRAPPED) == trapped).all(), tag                  # Trapped exactly for roots without clearance (self-collision off)
+    assert (st_w[trapped] == TRAPPED).all(), tag                      # roots without clearance are Trapped; with xArm6's self-collision check on,
+                                                                       # a spine whose first marching step already self-collides is Trapped too (RBTConnect.cpp:129-131)
     if mode == 2:
         assert np.array_equal(nl[~trapped], nl_w[~trapped]), tag       # extendGenSpine2 is never called on such a root (RGBTConnect.cpp:33)
         pairs = [(ql[s, :nl_w[s]], ql_w[s, :nl_w[s]]) for s in range(S) if not trapped[s]]
@@ -268,6 +271,7 @@ def test_oracle_spines_match_the_reference_planner_golden(ob):
     seen = np.zeros(4, np.int64)
     for name, (rb, mn, mx, g, tol, thr, N) in mod.rvs.cases().items():
         o = ob.Oracle(rb, robots.default_params(equality_threshold=thr))
+        o.set_self_collision(rb.self_collision_checking)               # xArm6: on, as in every shipped xarm6 scenario (the golden runs had it on)
         o.set_obstacles(mn, mx, g, tol)
         q, _, _ = mod.rvs.inputs(rb, N)
         free = o.is_valid(q).astype(bool)
@@ -301,6 +305,7 @@ def test_oracle_spines_match_the_compiled_reference_on_fresh_inputs(ob):
         free = mod.reference_free(lib, h, rb, N)
         q_r, q_e = mod.spine_inputs(rb, N, free)
         o = ob.Oracle(rb, robots.default_params(equality_threshold=thr))
+        o.set_self_collision(rb.self_collision_checking)
         o.set_obstacles(mn, mx, g, tol)
         for prm in mod.PARAMS + [(7, 3, 1, 0.01)]:
             for mode in mod.MODES:
