@@ -275,6 +275,45 @@ int rvsref_underestimation(void *p, const float *q, int64_t N, const float *plan
 }
 
 
+#ifndef RVS_DROPIN
+// CPU arm of bench.py (`cpu_baseline.kind = "reference"`, `--impl reference`): base::RealVectorSpace::computeDistance — the reference's
+// own loops and CollisionAndDistance primitives, compiled from /root/reference at -O3 — over N configurations, split statically over
+// `threads` std::threads.  The reference is single-threaded and not re-entrant (robot->setConfiguration, per-State caches), so every
+// thread owns a complete harness (robot + environment + state space), all built before the threads start; the static
+// RealVectorSpaceConfig values are only read.  Every configuration gets a fresh State, as a sampler would make it (no cache hits).
+// FK comes from the harness robot (the reference's URDF / mesh files do not travel to the GPU box).  d_c[N], profile[N x L].
+}  // extern "C"
+#include <thread>
+extern "C" {
+int rvsref_distance_mt(const rvs_robot_desc *rd, float eq_thr, float max_dist, const float *mn, const float *mx, const uint8_t *ground, const float *tol,
+                       int32_t M, const float *q, int64_t N, int32_t threads, float *d_c, float *profile) {
+    if (threads < 1) threads = 1;
+    std::vector<void *> hs;
+    for (int t = 0; t < threads; t++) {
+        void *h = rvsref_create(rd, eq_thr, max_dist, 10);
+        if (!h) return 1;
+        rvsref_set_obstacles(h, mn, mx, ground, tol, M);
+        hs.push_back(h);
+    }
+    const size_t L = size_t(rd->num_dofs);
+    std::vector<std::thread> pool;
+    const int64_t chunk = (N + threads - 1) / threads;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([&, t] {
+            auto *h = static_cast<Harness *>(hs[size_t(t)]);
+            const int64_t b = int64_t(t) * chunk, e = std::min<int64_t>(N, b + chunk);
+            for (int64_t i = b; i < e; i++) {
+                auto s = state_of(*h, q + size_t(i) * L);
+                d_c[i] = h->ss->computeDistance(s, false);
+                for (size_t l = 0; l < L; l++) profile[size_t(i) * L + l] = s->getDistanceProfile()[l];
+            }
+        });
+    for (auto &th : pool) th.join();
+    for (void *h : hs) rvsref_destroy(h);
+    return 0;
+}
+#endif
+
 // Bur spines (row f-1) through the reference's own planning::rbt::RBTConnect::extendSpine (RBTConnect.cpp:85-150) and
 // RGBTConnect::extendGenSpine / extendGenSpine2 (RGBTConnect.cpp:73-118, use_real_dist = false), compiled unmodified.
 // mode 0: extendSpine (one layer), 1: extendGenSpine (only the final state, written as layer 0), 2: extendGenSpine2 (every layer).

@@ -63,12 +63,13 @@ def rotated_box_aabbs(dim: np.ndarray, pos: np.ndarray) -> Tuple[np.ndarray, np.
 
 
 def sweep_obstacles(M: int, dist: str = "D2", seed: int = SEED_OBSTACLES, ws_center=(0.0, 0.0, 0.267), ws_radius: float = 1.5,
-                    ground: bool = True, rotated: bool = False, base_clearance: float = 0.2, r_min: float = 0.0):
+                    ground: bool = True, rotated: bool = False, base_clearance: float = 0.2, r_min: float = 0.0, r_max: float = None):
     """Obstacle table of the S1 sweep. Object 0 is the ground box (dim 1.5 x 1.5 x 0.1 at z = -0.05, min_dist_tol 0.05,
     label "ground"); the others have centres drawn like initRandomObstacles (/root/reference/apps/CommonFunctions.h:95-100):
     r = u*R, phi = 2*pi*u, theta = pi*u around WS_center. Sizes: D1 = 0.01^3 cubes, D2 = each side uniform [0.05, 0.30].
     `r_min` > 0 draws r = r_min + u*(R - r_min) instead (a shell: obstacles kept out of the inner workspace so that most
-    random configurations stay collision-free and every pair goes through the narrow phase).
+    random configurations stay collision-free and every pair goes through the narrow phase); `r_max` < R keeps them inside a
+    smaller sphere (near field: every obstacle within the arm's reach).
     Returns (aabb_min[M,3], aabb_max[M,3], is_ground[M], min_dist_tol[M])."""
     if M < 1:
         raise ValueError("M >= 1")
@@ -86,7 +87,7 @@ def sweep_obstacles(M: int, dist: str = "D2", seed: int = SEED_OBSTACLES, ws_cen
             break
         ctr = (k[todo] + np.uint64(attempt) * np.uint64(1 << 32)) * np.uint64(8)
         u = [unit24(seed, ctr + np.uint64(c)).astype(np.float64) for c in range(6)]
-        r, phi, theta = r_min + u[0] * (ws_radius - r_min), 2.0 * math.pi * u[1], math.pi * u[2]
+        r, phi, theta = r_min + u[0] * ((ws_radius if r_max is None else r_max) - r_min), 2.0 * math.pi * u[1], math.pi * u[2]
         p = np.stack([ws_center[0] + r * np.cos(phi) * np.sin(theta), ws_center[1] + r * np.sin(phi) * np.sin(theta),
                       ws_center[2] + r * np.cos(theta)], axis=1).astype(np.float32)
         if dist == "D1":
