@@ -40,6 +40,7 @@ struct rvs_engine {
     rvs_params prm{};
     RobotDev h_robot{};
     RobotDev *d_robot = nullptr;
+    void *d_obs_pack = nullptr;               // fp16 boxes of the scan-order table, two obstacles per 32-byte record
     ObstacleRec *d_obs = nullptr;
     int M = 0, obs_cap = 0;
     std::vector<ObstacleRec> h_obs, h_obs_scan;
@@ -157,6 +158,7 @@ int check_params(rvs_engine *h, const rvs_params *p) {
 
 KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
     KArgs a{};
+    a.obstacles_pack = h->d_obs_pack;
     a.robot = h->d_robot; a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.scan_dist = reinterpret_cast<const float *>(h->d_obs + 2 * size_t(h->obs_cap)); a.M = h->M; a.N = N; a.q = d_q;
     a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
     a.num_checks = h->prm.num_interpolation_validity_checks; a.cull = h->cull;
@@ -372,6 +374,7 @@ int rvs_destroy(rvs_handle h) {
     for (auto &b : h->buf) if (b.dev) cudaFree(b.dev);
     if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
+    if (h->d_obs_pack) cudaFree(h->d_obs_pack);
     if (h->d_store) cudaFree(h->d_store);
     if (h->d_env) cudaFree(h->d_env);
     if (h->d_env_tl) cudaFree(h->d_env_tl);
@@ -515,6 +518,7 @@ int upload_obstacles(rvs_engine *h) {
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs, h->h_obs.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + h->obs_cap, h->h_obs_scan.data(), size_t(M) * sizeof(ObstacleRec), cudaMemcpyHostToDevice, h->stream));
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + 2 * size_t(h->obs_cap), h->h_scan_dist.data(), size_t(M) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, launch_pack_scan(h->d_obs + h->obs_cap, M, h->d_obs_pack, h->stream));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
     return RVS_OK;
 }
@@ -538,6 +542,9 @@ int rvs_set_obstacles(rvs_handle h, const float *aabb_min, const float *aabb_max
         h->d_obs = nullptr; h->obs_cap = 0;
         const int cap = M + M / 2 + 16;
         RVS_CUDA(h, cudaMalloc(&h->d_obs, 2 * size_t(cap) * sizeof(ObstacleRec) + size_t(cap) * sizeof(float)));   // caller order, scan order, scan distances
+        if (h->d_obs_pack) RVS_CUDA(h, cudaFree(h->d_obs_pack));
+        h->d_obs_pack = nullptr;
+        RVS_CUDA(h, cudaMalloc(&h->d_obs_pack, (size_t(cap) + 2) * 16));                                             // fp16 copy of the scan-order table: 32 B per obstacle pair
         h->obs_cap = cap;
     }
     if (M != h->M && h->d_store) {          // the slot stride depends on M: cached states of another table are meaningless
@@ -967,6 +974,7 @@ EnvArgs env_args(rvs_engine *h, int32_t K, float dt) {
     a.first_invalid = h->d_first_invalid; a.commit_edge = -1;
     a.eq_thr = h->prm.equality_threshold; a.max_dist = h->prm.max_distance;
     a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.scan_dist = reinterpret_cast<float *>(h->d_obs + 2 * size_t(h->obs_cap));
+    a.obstacles_pack = h->d_obs_pack;
     a.scan_key = h->d_scan_key;
     return a;
 }

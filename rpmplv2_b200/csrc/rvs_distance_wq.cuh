@@ -41,6 +41,7 @@
 //     dropped), then replay exactly that one pair sequentially to obtain the value the reference stores in
 //     d_c_profile[link]; the pair count the reference would have visited follows from the same key.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "rvs_fk.cuh"
@@ -59,11 +60,22 @@ constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bi
 #define RVS_WQ_INTERVAL 128
 #endif
 #ifndef RVS_WQ_MINBLOCKS
-#define RVS_WQ_MINBLOCKS 5
+#define RVS_WQ_MINBLOCKS 7
 #endif
 #ifndef RVS_WQ_FLUSH
 #define RVS_WQ_FLUSH 2
 #endif
+#ifndef RVS_WQ_EXPAND
+#define RVS_WQ_EXPAND 32
+#endif
+#ifndef RVS_WQ_G
+#define RVS_WQ_G 3
+#endif
+#ifndef RVS_WQ_HALF
+#define RVS_WQ_HALF 1
+#endif
+constexpr int kWqExpand = RVS_WQ_EXPAND;          // hit words unpacked per expansion round (bounds the pair queue: kWqExpand * 2G + 32 entries)
+constexpr int kWqG = RVS_WQ_G;                    // links scanned per pass over the obstacle table (slots of the scan loop)
 constexpr int kWqInterval = RVS_WQ_INTERVAL;      // obstacles between two threshold refreshes (after the first doublings 4, 8, 16, ...)
 constexpr int kWqUnroll = 2;                      // obstacles tested per scan iteration
 constexpr unsigned kNoHit = 0xFFFFFFFFu;
@@ -74,7 +86,7 @@ constexpr unsigned kNoEntry = 0xFFFFFFFFu;
 // Q1 / Q1b / Q2 entry: lane (5) | link (5) << 5 | obstacle-in-segment (16) << 10 | edge code (6) << 26
 template <int G> struct WqCaps {
     static constexpr int q0 = 64;                         // one scan iteration pushes <= 32 hit words on top of a leftover < 32
-    static constexpr int q1 = 32 * G * kWqUnroll + 32;   // one expansion unpacks <= 32*G*unroll pairs on top of a leftover < 32
+    static constexpr int q1 = kWqExpand * G * kWqUnroll + 32;   // one expansion unpacks <= kWqExpand*G*unroll pairs on top of a leftover < 32
     static constexpr int q1b = 64;                        // one re-cull round pushes <= 32 on top of a leftover < 32
     static constexpr int q2 = 32 * 12 + 32;               // one classify round pushes <= 32*12 edges on top of a leftover < 32
     static constexpr int words = 8 + q0 + q1 + q1b + q2;  // 8 control words first: 3 tails, 3 work counters
@@ -176,6 +188,45 @@ __device__ __forceinline__ void wq_overlap<float>(unsigned &mask, unsigned bit, 
         : "f"(ox), "f"(oy), "f"(oz), "f"(px), "f"(py), "f"(pz), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(lo[0]), "f"(lo[1]), "f"(lo[2]), "r"(bit));
 }
 
+// ---- half-precision scan boxes -----------------------------------------------------------------------------------------------------
+// The scan is a CONSERVATIVE filter (every survivor is re-tested exactly in phase B1), so its boxes may be rounded OUTWARDS to fp16:
+// obstacle lo / link lo down, obstacle hi / link hi up (<= 1 mm at 1 m, 2 mm at 2-4 m: noise next to thresholds of 5-30 cm).  Two
+// obstacles are packed per half2, so ONE packed compare (HSET2, on the FMA pipe) tests two pairs: 6 HSET2 + ~4 LOP3 per slot and
+// obstacle pair instead of 14 FSETP / LOP, and the compare work moves off the ALU pipe, which the FP32 scan saturated (FSETP issues at
+// half rate: the FP32 scan could not exceed 0.5 instructions per cycle and scheduler).
+// Packed table: two uint4 per obstacle PAIR (2p, 2p+1) of the scan-ordered table:
+//   w0 = (lo.x | lo.y | lo.z | hi.x)   w1 = (hi.y | hi.z | flags | 0)     each 32-bit word = half2 (obstacle 2p in the low half)
+//   flags: bit 0 / bit 16 = label "ground" of obstacle 2p / 2p+1.  A missing second obstacle (odd M) is an empty box (lo = +inf, hi = -inf).
+__device__ __forceinline__ unsigned wq_h2(__half a, __half b) { const __half2 v = __halves2half2(a, b); return *reinterpret_cast<const unsigned *>(&v); }
+__device__ __forceinline__ unsigned wq_dup_down(float x) { const __half v = __float2half_rd(x); return wq_h2(v, v); }
+__device__ __forceinline__ unsigned wq_dup_up(float x) { const __half v = __float2half_ru(x); return wq_h2(v, v); }
+__device__ __forceinline__ unsigned wq_le2(unsigned a, unsigned b) { return __hle2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b)); }
+__device__ __forceinline__ unsigned wq_ge2(unsigned a, unsigned b) { return __hge2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b)); }
+
+#ifdef RVS_VARIANT_EXACT
+// one thread per obstacle pair: scan-ordered ObstacleRec table -> packed half2 table (launched after every upload / re-ranking of the table)
+__global__ void __launch_bounds__(128) pack_scan_kernel(const ObstacleRec *__restrict__ scan, int M, uint4 *__restrict__ pack) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (2 * p >= M) return;
+    const float inf = __int_as_float(0x7f800000);
+    const ObstacleRec a = scan[2 * p];
+    ObstacleRec b;
+    if (2 * p + 1 < M) b = scan[2 * p + 1];
+    else { b.lo[0] = b.lo[1] = b.lo[2] = inf; b.hi[0] = b.hi[1] = b.hi[2] = -inf; b.tol = 0.f; b.flags = 0u; }
+    uint4 w0, w1;
+    w0.x = wq_h2(__float2half_rd(a.lo[0]), __float2half_rd(b.lo[0]));
+    w0.y = wq_h2(__float2half_rd(a.lo[1]), __float2half_rd(b.lo[1]));
+    w0.z = wq_h2(__float2half_rd(a.lo[2]), __float2half_rd(b.lo[2]));
+    w0.w = wq_h2(__float2half_ru(a.hi[0]), __float2half_ru(b.hi[0]));
+    w1.x = wq_h2(__float2half_ru(a.hi[1]), __float2half_ru(b.hi[1]));
+    w1.y = wq_h2(__float2half_ru(a.hi[2]), __float2half_ru(b.hi[2]));
+    w1.z = (a.flags & 1u) | ((b.flags & 1u) << 16);
+    w1.w = 0u;
+    pack[2 * p] = w0;
+    pack[2 * p + 1] = w1;
+}
+#endif
+
 // merge one finished candidate distance (radius already subtracted) of pair `key` into configuration slot `t`
 template <class R>
 __device__ __forceinline__ void wq_merge(const WqCtx<R> &c, int t, int link, unsigned key, R d, R tol) {
@@ -268,7 +319,7 @@ __device__ __forceinline__ unsigned wq_pop(volatile unsigned *tail, const unsign
 // cheaper than a divergent per-lane loop inside the scan.  `n0` (Q0 fill, warp-uniform, kept in a register) is returned reduced.
 template <class R, int G>
 __device__ __forceinline__ unsigned wq_expand(const WqCtx<R> &c, unsigned n0, unsigned slotmap, int lane) {
-    const unsigned n = n0 < 32u ? n0 : 32u, base0 = n0 - n;
+    const unsigned n = n0 < unsigned(kWqExpand) ? n0 : unsigned(kWqExpand), base0 = n0 - n;
     const unsigned w = unsigned(lane) < n ? c.q0[base0 + lane] : 0u;
     unsigned m = w & ((1u << (2 * G)) - 1u);
     const unsigned cnt = unsigned(__popc(m));
@@ -373,6 +424,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
         const int count = min(kWqSegment, a.M - base);
         c.seg_base = base;
         const float4 *o4 = c.obs4 + 2 * size_t(base);
+        const uint4 *op = static_cast<const uint4 *>(a.obstacles_pack) + size_t(base);                 // two uint4 per obstacle pair; base is even
         const float *sd = a.scan_dist + base;
 #pragma unroll 1
         for (int g0 = 0; g0 < L; g0 += G) {
@@ -406,7 +458,11 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
                 const int K = __popc(alive);
                 unsigned ground_keep = 0;
                 slotmap = 0;                                                // (Q0 is empty here: every interval ends with a flush)
+#if RVS_WQ_HALF
+                unsigned lo[G][3], hi[G][3];                                // half2, the link box value in both halves (rounded outwards)
+#else
                 float lo[G][3], hi[G][3];
+#endif
                 {
                     unsigned rem = alive;
 #pragma unroll
@@ -419,25 +475,61 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
 #pragma unroll
                             for (int k = 0; k < 3; k++) {
                                 const R p = sk[k * kWqStride], q = sk[(3 + k) * kWqStride];
+#if RVS_WQ_HALF
+                                lo[s][k] = wq_dup_down(wq_round_down(fmin(p, q) - thr));
+                                hi[s][k] = wq_dup_up(wq_round_up(fmax(p, q) + thr));
+#else
                                 lo[s][k] = wq_round_down(fmin(p, q) - thr);
                                 hi[s][k] = wq_round_up(fmax(p, q) + thr);
+#endif
                             }
                         } else {
 #pragma unroll
-                            for (int k = 0; k < 3; k++) { lo[s][k] = wq_inf<float>(); hi[s][k] = -wq_inf<float>(); }  // overlaps nothing
+                            for (int k = 0; k < 3; k++) {                                      // overlaps nothing
+#if RVS_WQ_HALF
+                                lo[s][k] = 0x7C007C00u; hi[s][k] = 0xFC00FC00u;                // (+inf, +inf) / (-inf, -inf) in half2
+#else
+                                lo[s][k] = wq_inf<float>(); hi[s][k] = -wq_inf<float>();
+#endif
+                            }
                         }
                         if (s < K) {
                             slotmap |= unsigned(i) << (5 * s);
                             if (i >= ground_included) ground_keep |= 1u << s;                 // links below ground_included ignore ground objects (:336)
                         }
                     }
+#if !RVS_WQ_HALF
                     ground_keep *= (1u << G) + 1u;                                            // replicated for both unrolled obstacles
+#endif
                 }
                 // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, 64, 128, 256, 384, ... obstacles
                 const int jend = alive ? min(j0 + (j0 < 4 ? 4 : min(j0, kWqInterval)), count) : count;
                 const bool seg_end = jend == count && g0 + G >= L;         // queue entries index this segment: empty every queue before moving on
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {
+#if RVS_WQ_HALF
+                    // two obstacles per packed record (see pack_scan_kernel): two warp-uniform 16-byte loads, 6 packed compares per slot
+                    const uint4 w0 = __ldg(op + (j)), w1 = __ldg(op + (j) + 1);
+                    unsigned m2 = 0;                                                          // bit S: obstacle j x slot S, bit 16 + S: obstacle j + 1 x slot S
+#define RVS_WQ_SLOT(S)                                                                                                             \
+    if (S < G) {                                                                                                                   \
+        const unsigned ax = wq_le2(w0.x, hi[S < G ? S : 0][0]) & wq_ge2(w0.w, lo[S < G ? S : 0][0]) & wq_le2(w0.y, hi[S < G ? S : 0][1]);      \
+        const unsigned bx = wq_ge2(w1.x, lo[S < G ? S : 0][1]) & wq_le2(w0.z, hi[S < G ? S : 0][2]) & wq_ge2(w1.y, lo[S < G ? S : 0][2]);      \
+        m2 |= ax & bx & (0x00010001u << (S));                                                                                      \
+    }
+                    switch (K) {                                                              // warp-uniform: only live slots are tested
+                        case 0: break;
+                        default: RVS_WQ_SLOT(5) [[fallthrough]];
+                        case 5: RVS_WQ_SLOT(4) [[fallthrough]];
+                        case 4: RVS_WQ_SLOT(3) [[fallthrough]];
+                        case 3: RVS_WQ_SLOT(2) [[fallthrough]];
+                        case 2: RVS_WQ_SLOT(1) [[fallthrough]];
+                        case 1: RVS_WQ_SLOT(0)
+                    }
+#undef RVS_WQ_SLOT
+                    if (w1.z) m2 &= ((w1.z & 1u) ? (ground_keep | 0xFFFF0000u) : ~0u) & ((w1.z & 0x10000u) ? ((ground_keep << 16) | 0x0000FFFFu) : ~0u);
+                    const unsigned mask = (m2 & 0xFFFFu) | ((m2 >> 16) << G);                 // hit-word layout: slot bits of obstacle j, then of obstacle j + 1
+#else
                     // (lo.xyz, hi.x) (hi.y, hi.z, tol, flags) of two obstacles: warp-uniform 16-byte loads
                     const int j1 = j + 1 < jend ? j + 1 : j;
                     const float4 *pj = o4 + 2 * j, *pj1 = pj + (j1 - j) * 2;
@@ -462,6 +554,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
                     if ((__float_as_uint(w1.w) | __float_as_uint(v1.w)) & 1u)
                         mask &= ((__float_as_uint(w1.w) & 1u) ? (ground_keep | ~((1u << G) - 1u)) : ~0u) &
                                 ((__float_as_uint(v1.w) & 1u) ? (ground_keep | ((1u << G) - 1u)) : ~0u);
+#endif
                     // one hit word per lane with any hit, at a ballot-computed position of Q0 (no divergence in the scan)
                     const unsigned hits = __ballot_sync(0xffffffffu, mask != 0u);
                     if (mask) c.q0[n0 + __popc(hits & ((1u << lane) - 1u))] = mask | (unsigned(lane) << 12) | (unsigned(j >> 1) << 17);

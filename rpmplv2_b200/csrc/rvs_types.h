@@ -50,6 +50,7 @@ struct KArgs {
     const ObstacleRec *obstacles;        // caller's order
     const ObstacleRec *obstacles_scan;   // nearest-to-base first; flags bits 8..31 = index in the caller's order (work-queue kernel only)
     const float *scan_dist;              // [M] distance of scan-order obstacle k from the robot base, rounded down (ascending)
+    const void *obstacles_pack;          // scan-order table as fp16 boxes rounded outwards, two obstacles per record (rvs_distance_wq.cuh, pack_scan_kernel)
     int32_t M;
     int64_t N;
     const float *q;          // N x n
@@ -155,6 +156,7 @@ struct EnvArgs {
     float eq_thr, max_dist;
     ObstacleRec *obstacles, *obstacles_scan;
     float *scan_dist, *scan_key;
+    void *obstacles_pack;        // fp16 copy of the scan-order table (re-packed after every re-ranking)
 };
 
 }  // namespace rvs

@@ -70,8 +70,8 @@ struct Variant {
         if (a.cull && a.mode != RVS_DIST_FULL && a.M > 0) {
             // work-queue kernel (rvs_distance_wq.cuh): results identical to the sequential kernel below
             const bool narrow = a.robot_n_hint <= 2;
-            if (a.mode == RVS_DIST_MIN) return narrow ? distance_wq<RVS_DIST_MIN, 2>(a, st) : distance_wq<RVS_DIST_MIN, 6>(a, st);
-            return narrow ? distance_wq<RVS_DIST_PROFILE, 2>(a, st) : distance_wq<RVS_DIST_PROFILE, 6>(a, st);
+            if (a.mode == RVS_DIST_MIN) return narrow ? distance_wq<RVS_DIST_MIN, 2>(a, st) : distance_wq<RVS_DIST_MIN, kWqG>(a, st);
+            return narrow ? distance_wq<RVS_DIST_PROFILE, 2>(a, st) : distance_wq<RVS_DIST_PROFILE, kWqG>(a, st);
         }
         const unsigned g = grid_for(a.N, kBlock);
         if (a.mode == RVS_DIST_MIN) distance_kernel<F, R, RVS_DIST_MIN><<<g, kBlock, 0, st>>>(a);
@@ -187,6 +187,13 @@ cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     env_rank_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    return launch_pack_scan(a.obstacles_scan, a.M, a.obstacles_pack, st);
+}
+cudaError_t launch_pack_scan(const ObstacleRec *scan, int M, void *pack, cudaStream_t st) {
+    if (M <= 0) return cudaSuccess;
+    pack_scan_kernel<<<grid_for((M + 1) / 2, 128), 128, 0, st>>>(scan, M, static_cast<uint4 *>(pack));
     return cudaGetLastError();
 }
 cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st) {
