@@ -209,6 +209,21 @@ int  rvs_get_self_collision(rvs_handle h, int32_t *enabled, float *eps_step);
  * (conservative).  hit = 0 / q2_out = q2 when the check is off or the robot is not an xArm6. */
 int  rvs_self_collision_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *hit, float *q2_out);
 int  rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_hit, float *d_q2_out);
+/* Device-resident planner trees: the states of base::Tree kept as a [count][n] array in HBM, answering
+ *   rvs_tree_nearest  <- base::Tree::getNearestState (src/state_spaces/Tree.cpp:35-50; nanoflann kd-tree, exact 1-NN in the squared
+ *                        L2 metric): Q queries in ONE launch, query k against tree trees[k] (NULL = tree 0) -> idx[k] (-1 for an empty
+ *                        tree) and the squared distance; brute force, ties to the lowest index
+ *   rvs_tree_radius   <- planning::rrtx::RRTx::findNeighbors (src/planners/rrtx/RRTx.cpp:424-452): every state within `radius` of the
+ *                        query in ss->getNorm, in TREE ORDER, except index `exclude`; *count = number of hits (when it exceeds `capacity`
+ *                        only the first `capacity` are written: call again with more room)
+ * Trees are append-only arrays (rvs_tree_clear empties one); ids are dense from 0 per handle. */
+int  rvs_tree_create(rvs_handle h, int32_t *tree);
+int  rvs_tree_clear(rvs_handle h, int32_t tree);
+int  rvs_tree_size(rvs_handle h, int32_t tree);
+int  rvs_tree_append(rvs_handle h, int32_t tree, const float *q, int32_t count);
+int  rvs_tree_nearest(rvs_handle h, const int32_t *trees, const float *queries, int32_t Q, int32_t *idx, float *dist2);
+int  rvs_tree_radius(rvs_handle h, int32_t tree, const float *query, float radius, int32_t exclude, int32_t capacity, int32_t *idx,
+                     float *dist, int32_t *count);
 /* The two composite tests every planner of the reference writes out by hand, as ONE call (one upload, one synchronisation):
  *   rvs_check_states: valid[i] = ss->isValid(q_i) && !ss->robot->checkSelfCollision(q_i)
  *                     (src/planners/rrt/RRTConnect.cpp:13-15, trajectory/MotionValidity.cpp:42, rbt_star/RGBMTStar.cpp:202)

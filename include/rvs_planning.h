@@ -62,6 +62,41 @@ int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_
                         int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats);
 const char *rvsplan_last_error(void);
 
+/* ---- RRTx's edge-batch consumers ----------------------------------------------------------------------------
+ * Reference: planning::rrtx::RRTx::solve's tree-growth block  src/planners/rrtx/RRTx.cpp:157-190
+ *            findNeighbors :424-452, chooseParent :454-491, rewireNeighbors :493-529, propagateCostChanges :531-548,
+ *            updatePath :550-572, computePath :575-592, shrinkingBallRadius :636-639; configuration_rrtx.yaml.
+ * rvsplan_rrtx_grow builds the tree the reference's loop builds from `q_root` (RRTx roots its single tree at the goal) when its
+ * random states are `samples` [S x num_dofs], in that order: per sample  nearest state -> extend by EPS_STEP -> findNeighbors ->
+ * chooseParent -> upgradeTree -> rewireNeighbors.  Every candidate edge of an iteration (1 + up to 2 * MAX_NEIGHBORS edges) is ONE
+ * batched rvs_check_edges call; the reference's sequential cost logic is replayed over the verdicts, so parents and costs are the
+ * reference's, state by state (tests/test_rrtx.py, against RRTx.cpp compiled unmodified).
+ * Outputs (capacity max_states rows; the call fails with RVS_ERR_INVALID_ARGUMENT when the tree outgrows it): coord [states x
+ * num_dofs], parent [states] (-1: none), cost [states]; new_index [S] = index of the state sample s added, -1 when Trapped.
+ * path_start >= 0: also walk updatePath / computePath from that state: path [<= max_states] = state indices from path_start to the
+ * root (path_len = 0 when path_start has no parent), *path_invalid = 1 when any edge of the chain is blocked (one batched query). */
+typedef struct {
+    float   eps_step;                 /* RRTxConfig::EPS_STEP (yaml: 1.0) */
+    float   r_rewire;                 /* RRTxConfig::R_REWIRE (yaml: 3.14); 0 = shrinking ball */
+    int32_t max_neighbors;            /* RRTxConfig::MAX_NEIGHBORS (1000) */
+    int32_t one_call_per_iteration;   /* 1: all candidate edges of an iteration in one engine call; 0: three calls with fewer edges */
+    int32_t device_index;             /* 1: nearest / radius queries on the device-resident tree (rvs_tree_*); 0: host scans */
+} rvsplan_rrtx_config;
+
+typedef struct {
+    int64_t states, iterations, trapped;
+    int64_t backend_calls;            /* batched state-space calls issued */
+    int64_t edges_checked;            /* edges sent to the state space */
+    int64_t edges_reference;          /* edge checks the reference's one-at-a-time loop makes for the same tree */
+    int64_t reparented, rewired;      /* q_new that took a parent other than q_near; neighbours re-parented to q_new */
+    int64_t reseated;                 /* chooseParent loops in which a self-collision hit re-seated q_new (xArm6.cpp:284-352) */
+} rvsplan_rrtx_stats;
+
+void rvsplan_rrtx_default_config(rvsplan_rrtx_config *out);
+int rvsplan_rrtx_grow(rvs_handle h, const rvsplan_rrtx_config *cfg, const float *q_root, const float *samples, int32_t S, int32_t max_states,
+                      float *coord, int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path, int32_t *path_len,
+                      int32_t *path_invalid, rvsplan_rrtx_stats *stats);
+
 #ifdef __cplusplus
 }
 #endif

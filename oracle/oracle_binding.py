@@ -319,6 +319,8 @@ def plan_lib():
                                                   ctypes.c_int32, ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.POINTER(ctypes.c_int64)]
         _plan_lib.orcplan_last_error.restype = ctypes.c_char_p
+        from rpmplv2_b200.planning import SYMBOLS as _PS
+        _plan_lib.orcplan_rrtx_grow.restype, _plan_lib.orcplan_rrtx_grow.argtypes = _PS["rvsplan_rrtx_grow"]
     return _plan_lib
 
 
@@ -342,3 +344,13 @@ def plan_solve_batch(orc: "Oracle", cfg, q_start, q_goal, seeds=None, max_path: 
     if rc != 0:
         raise RuntimeError((lib_.orcplan_last_error() or b"").decode())
     return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1])}
+
+
+def plan_rrtx_grow(orc: "Oracle", cfg, q_root, samples, path_start: int = -1, max_states=None) -> dict:
+    """Same RRTx code as rpmplv2_b200.planning.rrtx_grow (cpp/planning/Rrtx.cpp), edges answered by the CPU oracle, host neighbour scans."""
+    from rpmplv2_b200.planning import rrtx_call
+    lib_ = plan_lib()
+    rc, out = rrtx_call(lib_.orcplan_rrtx_grow, orc._h, cfg, orc.n, q_root, samples, path_start, max_states)
+    if rc != 0:
+        raise RuntimeError((lib_.orcplan_last_error() or b"").decode())
+    return out

@@ -46,6 +46,14 @@ public:
             if (orc::self_collision_edge(e.robot, cfg, q1 + size_t(i) * n, end.data())) valid[i] = 0;
         }
     }
+    bool hasSelfCollision() const override { return e.robot.self_collision_checking && e.robot.kind == orc::XARM6; }
+    void isValidEdgesDetailed(const float *q1, const float *q2, int E, uint8_t *obstacle_ok, uint8_t *self_hit, float *q2_out) override {
+        for (int i = 0; i < E; i++) {
+            obstacle_ok[i] = orc::is_valid_edge(e.robot, e.sc32, q1 + size_t(i) * n, q2 + size_t(i) * n, cfg) ? 1 : 0;
+            std::copy_n(q2 + size_t(i) * n, n, q2_out + size_t(i) * n);
+            self_hit[i] = orc::self_collision_edge(e.robot, cfg, q1 + size_t(i) * n, q2_out + size_t(i) * n) ? 1 : 0;
+        }
+    }
     void distanceToSlots(const float *q, int N, const int32_t *slot_idx, float *d_c) override {
         std::vector<orc::V3<float>> sk(n + 1);
         for (int i = 0; i < N; i++) {
@@ -123,6 +131,25 @@ int orcplan_solve_batch(void *orc_handle, const rvsplan_config *cfg, const float
         });
         if (!first_error.empty()) { g_error = first_error; return 2; }
         if (pool_stats) { pool_stats[0] = pool_stats[1] = pool_stats[2] = 0; }
+    } catch (const std::exception &ex) {
+        g_error = ex.what();
+        return 2;
+    }
+    return 0;
+}
+
+
+// RRTx's tree growth (rpmplv2_b200/cpp/planning/Rrtx.cpp) over the oracle: the CPU twin of rvsplan_rrtx_grow
+int orcplan_rrtx_grow(void *orc_handle, const rvsplan_rrtx_config *cfg, const float *q_root, const float *samples, int32_t S, int32_t max_states, float *coord,
+                      int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path, int32_t *path_len, int32_t *path_invalid,
+                      rvsplan_rrtx_stats *stats) {
+    if (!orc_handle || !cfg || !q_root || !coord || !parent || !cost) { g_error = "orcplan_rrtx_grow: bad argument"; return 1; }
+    auto &eng = *static_cast<orc_capi::Engine *>(orc_handle);
+    try {
+        OracleBackend backend(eng);
+        rvsplan::HostNeighborIndex index(eng.robot.n);
+        if (rvsplan::rrtx_grow(backend, index, *cfg, q_root, samples, S, max_states, coord, parent, cost, new_index, path_start, path, path_len, path_invalid, stats))
+        { g_error = "orcplan_rrtx_grow: the tree outgrew max_states"; return 1; }
     } catch (const std::exception &ex) {
         g_error = ex.what();
         return 2;

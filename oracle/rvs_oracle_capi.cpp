@@ -323,6 +323,38 @@ int orc_env_update(const float *env_params, int32_t motion_type, int32_t M, cons
     return 0;
 }
 
+// Environment::moveRandomDirections (Environment.cpp:289-333): `steps` updates with the libc stream `rand_state` (36 words: LibcRand's table, position,
+// draws; orc_libc_srand fills it).  acc is updated in place like pos and vel.
+void orc_libc_srand(uint32_t seed, uint32_t *rand_state) {
+    orc::LibcRand g;
+    g.seed(seed);
+    std::copy_n(g.r, 34, rand_state); rand_state[34] = g.pos; rand_state[35] = g.draws;
+}
+uint32_t orc_libc_rand(uint32_t *rand_state) {
+    orc::LibcRand g;
+    std::copy_n(rand_state, 34, g.r); g.pos = rand_state[34]; g.draws = rand_state[35];
+    const uint32_t v = g.next();
+    std::copy_n(g.r, 34, rand_state); rand_state[34] = g.pos; rand_state[35] = g.draws;
+    return v;
+}
+int orc_env_update_random(const float *env_params, int32_t ground_included, int32_t M, const float *half, float *pos, float *vel, float *acc, const float *max_vel,
+                          const uint8_t *dynamic, float dt, int32_t steps, uint32_t *rand_state, float *aabb_min, float *aabb_max) {
+    orc::EnvParams ep = env_params_of(env_params, orc::MOTION_RANDOM_DIRECTIONS);
+    orc::LibcRand g;
+    std::copy_n(rand_state, 34, g.r); g.pos = rand_state[34]; g.draws = rand_state[35];
+    ep.ground_included = ground_included; ep.rng = &g;
+    std::vector<int32_t> sign(size_t(M > 0 ? M : 0), 1);
+    std::vector<float> path_len(size_t(M > 0 ? M : 0), 0.f);
+    auto objs = env_objects(M, half, pos, vel, max_vel, sign.data(), path_len.data(), dynamic);
+    for (int j = 0; j < M; j++) objs[size_t(j)].acc = {acc[3 * j], acc[3 * j + 1], acc[3 * j + 2]};
+    for (int k = 0; k < steps; k++) orc::env_update(ep, objs, dt);
+    env_store(objs, pos, vel, sign.data(), path_len.data());
+    for (int j = 0; j < M; j++) { acc[3 * j] = objs[size_t(j)].acc.x; acc[3 * j + 1] = objs[size_t(j)].acc.y; acc[3 * j + 2] = objs[size_t(j)].acc.z; }
+    if (aabb_min && aabb_max) for (int j = 0; j < M; j++) orc::env_aabb(objs[size_t(j)], aabb_min + 3 * j, aabb_max + 3 * j);
+    std::copy_n(g.r, 34, rand_state); rand_state[34] = g.pos; rand_state[35] = g.draws;
+    return 0;
+}
+
 // MotionValidity::check(q_previous, q_current) for E motions that share one obstacle timeline: validity point k (1..K) of every
 // motion is tested against the environment after k updates.  first_invalid[e] = k of the first invalid point, 0 if the motion is
 // valid.  commit_edge >= 0: the state arrays and the engine's obstacle table are left as the reference leaves them after checking

@@ -17,7 +17,10 @@
 // unpinned" is third-party arithmetic: Eigen's reduction order (the shim encodes the same assumption) and FCL's
 // computeAABB (pos -/+ side/2).  Closed-form known answers are checked as well (straight-line motion, circular motion
 // spirals out by the Euler step, the reflection law preserves speed and keeps every obstacle inside the workspace shell).
-// moveRandomDirections draws from Eigen::Vector3f::Random (libc rand()) and is therefore not restated (not reproducible).
+// moveRandomDirections (:289-333) draws from Eigen::Vector3f::Random, i.e. libc rand(): restated here on top of LibcRand, a restatement of
+// glibc's rand() (random_r TYPE_3: the additive feedback generator r[i] = r[i-3] + r[i-31] over a 34-word table seeded by the
+// Lehmer recurrence 16807 * x mod (2^31 - 1), first 310 outputs discarded, result = r[i] >> 1), so that a run after srand(seed) in the
+// reference and a run after LibcRand::seed(seed) here see the same stream (checked against the C library's own rand(), tests/test_env.py).
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -29,10 +32,43 @@ namespace orc {
 
 enum MotionType { MOTION_STRAIGHT = 0, MOTION_CIRCULAR = 1, MOTION_TWO_TUNNELS = 2, MOTION_RANDOM_DIRECTIONS = 3, MOTION_LIGHT_DIRECTIONS = 4 };
 
+// glibc rand() after srand(seed) (stdlib/random_r.c, TYPE_3); state = 34 table words + position + number of draws so far
+struct LibcRand {
+    uint32_t r[34];
+    uint32_t pos = 0;          // index (mod 34) of the next word to produce
+    uint32_t draws = 0;
+    void seed(uint32_t s) {
+        if (s == 0) s = 1;
+        int32_t word = int32_t(s);
+        r[0] = uint32_t(word);
+        for (int i = 1; i < 31; i++) {
+            const int32_t hi = word / 127773, lo = word % 127773;           // 16807 * word mod (2^31 - 1) without overflow (Schrage)
+            word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            r[i] = uint32_t(word);
+        }
+        for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+        pos = 0; draws = 0;                                                 // word 34 is the next one: 34 mod 34 = 0
+        for (int i = 0; i < 310; i++) next();
+        draws = 0;
+    }
+    uint32_t next() {                                                       // r[i] = r[i - 31] + r[i - 3]; rand() returns r[i] >> 1
+        const uint32_t v = r[(pos + 3) % 34] + r[(pos + 31) % 34];
+        r[pos] = v;
+        pos = (pos + 1) % 34;
+        draws++;
+        return v >> 1;
+    }
+    // Eigen::internal::random<float>() as the work-alike (and Eigen 3.4 for floats) evaluates it: 2 * rand() / RAND_MAX - 1
+    float uniform() { return 2.0f * float(next()) / float(2147483647) - 1.0f; }
+};
+
 struct EnvParams {
     int motion_type;
     V3<float> ws_center;
     float ws_radius, base_radius, robot_max_vel;
+    int ground_included = 2;   // Environment::ground_included (only Environment::isValid reads it: random_directions)
+    LibcRand *rng = nullptr;   // random_directions
 };
 
 struct EnvObject {
@@ -42,7 +78,21 @@ struct EnvObject {
     int sign;                // Environment::sign(i)      (two_tunnels)
     float path_len;          // Environment::path_len(i)  (two_tunnels)
     bool dynamic;            // label == "dynamic_obstacle"
+    V3<float> acc{0, 0, 0};  // env::Object::acceleration (random_directions)
 };
+
+// Environment::isValid(pos, vel) (Environment.cpp:169-190)
+inline bool env_pos_valid(const EnvParams &ep, const V3<float> &pos, float vel) {
+    const float tol_radius = std::max(vel / ep.robot_max_vel, ep.base_radius);
+    const float rc = normF(pos - ep.ws_center);
+    const float rxy = std::sqrt(pos.x * pos.x + pos.y * pos.y);
+    if (ep.ground_included > 0) {
+        if (rc > ep.ws_radius || pos.z < 0 || (rxy < tol_radius && pos.z < ep.ws_center.z) || rc < tol_radius) return false;
+    } else {
+        if (rc > ep.ws_radius || (rxy < tol_radius && pos.z < ep.ws_center.z && pos.z > -ep.base_radius) || rc < tol_radius) return false;
+    }
+    return true;
+}
 
 inline float norm2(float x, float y) { return std::sqrt(x * x + y * y); }
 
@@ -90,7 +140,33 @@ inline void env_update(const EnvParams &ep, std::vector<EnvObject> &objs, float 
                 }
                 break;
             }
-            default: break;                                             // random_directions: not restated (libc rand())
+            case MOTION_RANDOM_DIRECTIONS: {                            // (:289-333); the reference's `i--` = retry the same object
+                for (int tries = 0; tries < 100000; tries++) {
+                    const V3<float> vel = o.vel + dt * o.acc;
+                    const V3<float> pos = o.pos + dt * vel;
+                    const float vel_intensity = normF(vel);
+                    if (vel_intensity > o.max_vel) {
+                        V3<float> a{0, 0, 0};
+                        a.x = ep.rng->uniform(); a.y = ep.rng->uniform(); a.z = ep.rng->uniform();
+                        const float na = normF(a);
+                        a = {a.x / na, a.y / na, a.z / na};                 // normalize(): *this /= norm()
+                        const float keep = normF(o.acc);
+                        o.acc = {keep * a.x, keep * a.y, keep * a.z};
+                    } else if (!env_pos_valid(ep, pos, vel_intensity)) {
+                        V3<float> v{0, 0, 0};
+                        v.x = ep.rng->uniform(); v.y = ep.rng->uniform(); v.z = ep.rng->uniform();
+                        const float nv = normF(v);
+                        v = {v.x / nv, v.y / nv, v.z / nv};
+                        o.vel = {vel_intensity * v.x, vel_intensity * v.y, vel_intensity * v.z};
+                    } else {
+                        o.vel = vel;
+                        o.pos = pos;
+                        break;
+                    }
+                }
+                break;
+            }
+            default: break;
         }
     }
 }

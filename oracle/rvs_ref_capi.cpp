@@ -48,9 +48,13 @@
 #include "Spatial14DOF.h"
 #include "Spatial18DOF.h"
 #include "Spatial22DOF.h"
-#define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members
-#include "RGBTConnect.h"
+#include <queue>                                               // RRTx.h relies on these arriving through its third-party includes
+#include <random>
+#include <unordered_set>
+#define protected public                                       // extendSpine / extendGenSpine / extendGenSpine2 are protected members,
+#include "RGBTConnect.h"                                       // and so are RRTx's findNeighbors / chooseParent / rewireNeighbors / updatePath
 #include "PatternTree.h"
+#include "RRTx.h"
 #undef protected
 
 namespace {
@@ -810,3 +814,78 @@ int drv_motion(const char *urdf_path, const rvs_robot_desc *rd, const float *dim
 }
 }  // extern "C"
 #endif  // RVS_DROPIN
+
+// ---- RRTx's edge-batch consumers (row f-4): RRTx.cpp compiled unmodified -----------------------------------------------------------
+// RRTx.cpp references five symbols of the trajectory classes (spline / Ruckig interpolation of the executed motion: outside the path,
+// and their sources need more of Eigen than the work-alike has).  Four are never reached with TRAJECTORY_INTERPOLATION = None; the
+// UpdatingState constructor is, from RRTx's own constructor: it leaves a zeroed object (null shared_ptrs), which RRTx only ever hands a
+// null trajectory to.  The definitions carry the symbols' mangled names so that the unmodified object file links.
+extern "C" {
+[[noreturn]] static void rvsref_unlinked_abort() { std::cerr << "rvsref: a trajectory symbol outside the harness was called" << std::endl; std::abort(); }
+void rvsref_unlinked_a() __asm__("_ZN8planning10trajectory10TrajectoryC1ERKSt10shared_ptrIN4base10StateSpaceEENS0_5StateEf");
+void rvsref_unlinked_a() { rvsref_unlinked_abort(); }
+void rvsref_unlinked_b() __asm__("_ZN8planning10trajectory16TrajectoryRuckigC1ERKSt10shared_ptrIN4base10StateSpaceEENS0_5StateEf");
+void rvsref_unlinked_b() { rvsref_unlinked_abort(); }
+void rvsref_unlinked_c() __asm__("_ZN8planning10trajectory5StateC1ERKN5Eigen6MatrixIfLin1ELi1EEE");
+void rvsref_unlinked_c() { rvsref_unlinked_abort(); }
+void rvsref_unlinked_d() __asm__("_ZN8planning10trajectory13UpdatingState6updateERSt10shared_ptrIN4base5StateEES6_S5_RNS4_6StatusE");
+void rvsref_unlinked_d() { rvsref_unlinked_abort(); }
+void rvsref_unlinked_e(void *self) __asm__("_ZN8planning10trajectory13UpdatingStateC1ERKSt10shared_ptrIN4base10StateSpaceEENS_23TrajectoryInterpolationEf");
+void rvsref_unlinked_e(void *self) { std::memset(self, 0, sizeof(planning::trajectory::UpdatingState)); }
+
+// The tree RRTx grows from q_goal when its random states are `samples`: the tree-growth block of RRTx::solve (RRTx.cpp:157-190) —
+// getNearestState, extend, setCost, findNeighbors, chooseParent, upgradeTree, rewireNeighbors, all the reference's own members, called
+// in the reference's order on the planner object RRTx's own constructor set up (tree, kd-tree, eta / mi / zeta / gamma_rrt).
+// r_rewire > 0: constant radius (RRTxConfig::R_REWIRE), else shrinkingBallRadius(tree size) per iteration; radii_out [S] records it.
+// path_start >= 0: updatePath() / computePath() with start_state = that tree state.  Returns the number of states, -1 when the tree
+// outgrows max_states, -2 when the constructor throws (q_start invalid).
+int64_t rvsref_rrtx_grow(void *p, float eps_step, float r_rewire, int32_t max_neighbors, const float *q_start, const float *q_goal, const float *samples,
+                         int32_t S, int64_t max_states, float *coord, int32_t *parent, float *cost, int32_t *new_index, float *radii_out, int32_t path_start,
+                         int32_t *path, int32_t *path_len, int32_t *path_invalid) {
+    auto *h = static_cast<Harness *>(p);
+    RRTxConfig::EPS_STEP = eps_step;
+    RRTxConfig::R_REWIRE = r_rewire;
+    RRTxConfig::MAX_NEIGHBORS = size_t(max_neighbors);
+    RRTxConfig::TRAJECTORY_INTERPOLATION = planning::TrajectoryInterpolation::None;
+    std::unique_ptr<planning::rrtx::RRTx> planner;
+    try {
+        planner = std::make_unique<planning::rrtx::RRTx>(h->ss, state_of(*h, q_start), state_of(*h, q_goal));
+    } catch (const std::domain_error &) {
+        return -2;
+    }
+    const size_t n = size_t(h->n);
+    for (int32_t s = 0; s < S; s++) {
+        if (int64_t(planner->tree->getNumStates()) >= max_states) return -1;
+        planner->r_rewire = RRTxConfig::R_REWIRE > 0 ? RRTxConfig::R_REWIRE : planner->shrinkingBallRadius(planner->tree->getNumStates());
+        if (radii_out) radii_out[s] = planner->r_rewire;
+        const auto q_rand = state_of(*h, samples + size_t(s) * n);
+        const auto q_near = planner->tree->getNearestState(q_rand);
+        base::State::Status status;
+        std::shared_ptr<base::State> q_new;
+        std::tie(status, q_new) = planner->extend(q_near, q_rand);
+        new_index[s] = -1;
+        if (status == base::State::Status::Trapped) continue;
+        q_new->setCost(q_near->getCost() + planner->distance(q_near, q_new));
+        const auto neighbors = planner->findNeighbors(q_new, planner->r_rewire);
+        planner->chooseParent(q_new, neighbors);
+        planner->tree->upgradeTree(q_new, q_new->getParent());
+        planner->rewireNeighbors(q_new, neighbors);
+        new_index[s] = int32_t(q_new->getIdx());
+    }
+    const int64_t count = int64_t(planner->tree->getNumStates());
+    for (int64_t k = 0; k < count; k++) {
+        const auto q = planner->tree->getState(size_t(k));
+        for (size_t i = 0; i < n; i++) coord[size_t(k) * n + i] = q->getCoord(int(i));
+        parent[k] = q->getParent() ? int32_t(q->getParent()->getIdx()) : -1;
+        cost[k] = q->getCost();
+    }
+    if (path_start >= 0 && path_start < count) {
+        planner->start_state = planner->tree->getState(size_t(path_start));
+        planner->computePath();
+        *path_len = int32_t(planner->path_current.size());
+        for (int32_t k = 0; k < *path_len; k++) path[k] = int32_t(planner->path_current[size_t(k)]->getIdx());
+        *path_invalid = planner->path_current.empty() ? 0 : (planner->updatePath() ? 1 : 0);
+    }
+    return count;
+}
+}

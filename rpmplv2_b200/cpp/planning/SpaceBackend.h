@@ -39,6 +39,13 @@ namespace rvsplan
 		virtual void isValid(const float *q, int N, uint8_t *valid) = 0;
 		// valid[e] = isValid(q1_e, q2_e) && !robot->checkSelfCollision(q1_e, q2_e)        (RRTConnect.cpp:100)
 		virtual void isValidEdges(const float *q1, const float *q2, int E, uint8_t *valid) = 0;
+		// Does robot->checkSelfCollision ever answer true (xArm6 with self_collision_checking)?  Only then isValidEdgesDetailed differs
+		// from isValidEdges.
+		virtual bool hasSelfCollision() const = 0;
+		// The two halves of the edge test apart, for callers whose control flow depends on WHICH one failed (RRTx::chooseParent,
+		// RRTx.cpp:466-468): obstacle_ok[e] = isValid(q1_e, q2_e); self_hit[e] = robot->checkSelfCollision(q1_e, q2_e) and, on a hit,
+		// q2_out[e] = the last collision-free point of the edge the reference re-seats q2 on (xArm6.cpp:284-352; q2_e otherwise).
+		virtual void isValidEdgesDetailed(const float *q1, const float *q2, int E, uint8_t *obstacle_ok, uint8_t *self_hit, float *q2_out) = 0;
 		// d_c[i] = computeDistance(q_i); everything the spines need later stays in slot slots[i]
 		virtual void distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c) = 0;
 		// spine s: from the cached state root_slots[s] towards q_targets[s]; q_layers[S][num_layers][n]

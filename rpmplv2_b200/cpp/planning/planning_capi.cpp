@@ -49,4 +49,43 @@ int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_
 	return RVS_OK;
 }
 
+
+void rvsplan_rrtx_default_config(rvsplan_rrtx_config *out)
+{
+	if (!out) return;
+	out->eps_step = 1.0f; out->r_rewire = 3.14f; out->max_neighbors = 1000;                           // configuration_rrtx.yaml:4-6
+	out->one_call_per_iteration = 1; out->device_index = 0;
+}
+
+int rvsplan_rrtx_grow(rvs_handle h, const rvsplan_rrtx_config *cfg, const float *q_root, const float *samples, int32_t S, int32_t max_states,
+					  float *coord, int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path, int32_t *path_len,
+					  int32_t *path_invalid, rvsplan_rrtx_stats *stats)
+{
+	if (!h || !cfg || !q_root || (S > 0 && !samples) || S < 0 || max_states < 1 || !coord || !parent || !cost)
+	{ g_error = "rvsplan_rrtx_grow: NULL argument, S < 0 or max_states < 1"; return RVS_ERR_INVALID_ARGUMENT; }
+	if (!(cfg->eps_step > 0) || cfg->r_rewire < 0 || cfg->max_neighbors < 1) { g_error = "rvsplan_rrtx_grow: bad configuration"; return RVS_ERR_INVALID_ARGUMENT; }
+	try
+	{
+		rvsplan::CudaBackend backend(h);
+		int rc;
+		if (cfg->device_index)
+		{
+			rvsplan::CudaNeighborIndex index(h);
+			rc = rvsplan::rrtx_grow(backend, index, *cfg, q_root, samples, S, max_states, coord, parent, cost, new_index, path_start, path, path_len, path_invalid, stats);
+		}
+		else
+		{
+			rvsplan::HostNeighborIndex index(backend.numDofs());
+			rc = rvsplan::rrtx_grow(backend, index, *cfg, q_root, samples, S, max_states, coord, parent, cost, new_index, path_start, path, path_len, path_invalid, stats);
+		}
+		if (rc) { g_error = "rvsplan_rrtx_grow: the tree outgrew max_states"; return RVS_ERR_INVALID_ARGUMENT; }
+	}
+	catch (const std::exception &e)
+	{
+		g_error = e.what();
+		return RVS_ERR_CUDA;
+	}
+	return RVS_OK;
+}
+
 }

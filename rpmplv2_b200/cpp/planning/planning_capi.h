@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "Planners.h"
+#include "Rrtx.h"
 #include "rvs_planning.h"
 
 namespace rvsplan
@@ -39,6 +40,43 @@ namespace rvsplan
 				std::copy_n(r.path.begin(), keep * size_t(n), paths + p * size_t(max_path) * size_t(n));
 			}
 		}
+	}
+
+	// the body of rvsplan_rrtx_grow / its CPU-oracle twin: 0, or 1 when the tree outgrows max_states
+	inline int rrtx_grow(SpaceBackend &backend, NeighborIndex &index, const rvsplan_rrtx_config &c, const float *q_root, const float *samples, int32_t S,
+						 int32_t max_states, float *coord, int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path,
+						 int32_t *path_len, int32_t *path_invalid, rvsplan_rrtx_stats *stats)
+	{
+		RrtxConfig cfg;
+		cfg.eps_step = c.eps_step; cfg.r_rewire = c.r_rewire; cfg.max_neighbors = c.max_neighbors; cfg.one_call_per_iteration = c.one_call_per_iteration != 0;
+		RrtxTree tree(backend, index, cfg);
+		const int n = backend.numDofs();
+		tree.addRoot(q_root);
+		for (int32_t s = 0; s < S; s++)
+		{
+			if (tree.size() >= max_states) return 1;
+			const int id = tree.grow(samples + size_t(s) * size_t(n));
+			if (new_index) new_index[s] = id;
+		}
+		for (int k = 0; k < tree.size(); k++)
+		{
+			std::copy_n(tree.coord(k), n, coord + size_t(k) * size_t(n));
+			parent[k] = tree.parent[size_t(k)];
+			cost[k] = tree.cost[size_t(k)];
+		}
+		if (path_start >= 0 && path_start < tree.size() && path && path_len && path_invalid)
+		{
+			*path_invalid = tree.pathInvalid(path_start) ? 1 : 0;
+			const std::vector<int> p = tree.pathToRoot(path_start);
+			*path_len = int32_t(p.size());
+			std::copy(p.begin(), p.end(), path);
+		}
+		if (stats)
+		{
+			const RrtxStats &t = tree.stats;
+			*stats = {int64_t(tree.size()), t.iterations, t.trapped, t.backend_calls, t.edges_checked, t.edges_reference, t.reparented, t.rewired, t.reseated};
+		}
+		return 0;
 	}
 }
 

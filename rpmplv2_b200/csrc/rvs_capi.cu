@@ -70,6 +70,14 @@ struct rvs_engine {
     bool zc = false;
     std::vector<PendingCopy> pending;
     std::string err;
+    // device-resident planner trees (rvs_tree_*): states of tree t at trees[t].d [cap][n]; the pointer / count tables the kernels read
+    // are mirrored in d_tree_ptr / d_tree_cnt and refreshed lazily
+    struct DevTree { float *d = nullptr; int count = 0, cap = 0; };
+    std::vector<DevTree> trees;
+    const float **d_tree_ptr = nullptr;
+    int32_t *d_tree_cnt = nullptr;
+    int tree_tab_cap = 0;
+    bool tree_tab_dirty = true;
 };
 
 namespace {
@@ -375,6 +383,9 @@ int rvs_destroy(rvs_handle h) {
     if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_obs_pack) cudaFree(h->d_obs_pack);
+    for (auto &t : h->trees) if (t.d) cudaFree(t.d);
+    if (h->d_tree_ptr) cudaFree(h->d_tree_ptr);
+    if (h->d_tree_cnt) cudaFree(h->d_tree_cnt);
     if (h->d_store) cudaFree(h->d_store);
     if (h->d_env) cudaFree(h->d_env);
     if (h->d_env_tl) cudaFree(h->d_env_tl);
@@ -1116,4 +1127,123 @@ int rvs_motion_validity_points(rvs_handle h, const float *points, int64_t E, int
     return motion_validity_impl(h, nullptr, nullptr, points, E, K, delta_time, commit_edge, valid, first_invalid);
 }
 
+}  // extern "C"
+
+// ---- device-resident planner trees: nearest neighbour and radius queries (rvs_nn.cuh) --------------------------------------------
+namespace {
+int tree_tables(rvs_engine *h) {
+    if (!h->tree_tab_dirty) return RVS_OK;
+    const int T = int(h->trees.size());
+    if (T > h->tree_tab_cap) {
+        if (h->d_tree_ptr) RVS_CUDA(h, cudaFree(h->d_tree_ptr));
+        if (h->d_tree_cnt) RVS_CUDA(h, cudaFree(h->d_tree_cnt));
+        h->d_tree_ptr = nullptr; h->d_tree_cnt = nullptr;
+        const int cap = T + T / 2 + 16;
+        RVS_CUDA(h, cudaMalloc(&h->d_tree_ptr, size_t(cap) * sizeof(float *)));
+        RVS_CUDA(h, cudaMalloc(&h->d_tree_cnt, size_t(cap) * sizeof(int32_t)));
+        h->tree_tab_cap = cap;
+    }
+    std::vector<const float *> ptr(static_cast<size_t>(T), nullptr);
+    std::vector<int32_t> cnt(static_cast<size_t>(T), 0);
+    for (int t = 0; t < T; t++) { ptr[size_t(t)] = h->trees[size_t(t)].d; cnt[size_t(t)] = h->trees[size_t(t)].count; }
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (T > 0) {
+        RVS_CUDA(h, cudaMemcpy(h->d_tree_ptr, ptr.data(), size_t(T) * sizeof(float *), cudaMemcpyHostToDevice));
+        RVS_CUDA(h, cudaMemcpy(h->d_tree_cnt, cnt.data(), size_t(T) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    }
+    h->tree_tab_dirty = false;
+    return RVS_OK;
+}
+}  // namespace
+
+extern "C" {
+int rvs_tree_create(rvs_handle h, int32_t *tree) {
+    RVS_TRY(enter(h));
+    if (!tree) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL tree id");
+    h->trees.emplace_back();
+    h->tree_tab_dirty = true;
+    *tree = int32_t(h->trees.size() - 1);
+    return RVS_OK;
+}
+int rvs_tree_clear(rvs_handle h, int32_t tree) {
+    RVS_TRY(enter(h));
+    if (tree < 0 || size_t(tree) >= h->trees.size()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
+    h->trees[size_t(tree)].count = 0;
+    h->tree_tab_dirty = true;
+    return RVS_OK;
+}
+int rvs_tree_size(rvs_handle h, int32_t tree) {
+    if (!h || tree < 0 || size_t(tree) >= h->trees.size()) return -1;
+    return h->trees[size_t(tree)].count;
+}
+int rvs_tree_append(rvs_handle h, int32_t tree, const float *q, int32_t count) {
+    RVS_TRY(enter(h));
+    if (tree < 0 || size_t(tree) >= h->trees.size() || count < 0 || (count > 0 && !q)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad tree append");
+    if (count == 0) return RVS_OK;
+    auto &t = h->trees[size_t(tree)];
+    const size_t row = size_t(h->h_robot.n) * sizeof(float);
+    if (t.count + count > t.cap) {
+        const int cap = std::max(2 * t.cap, std::max(t.count + count, 1024));
+        float *grown = nullptr;
+        RVS_CUDA(h, cudaMalloc(&grown, size_t(cap) * row));
+        RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+        if (t.d && t.count > 0) RVS_CUDA(h, cudaMemcpy(grown, t.d, size_t(t.count) * row, cudaMemcpyDeviceToDevice));
+        if (t.d) RVS_CUDA(h, cudaFree(t.d));
+        t.d = grown; t.cap = cap;
+    }
+    RVS_CUDA(h, cudaMemcpyAsync(t.d + size_t(t.count) * size_t(h->h_robot.n), q, size_t(count) * row, cudaMemcpyHostToDevice, h->stream));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));                    // q is the caller's pageable memory
+    t.count += count;
+    h->tree_tab_dirty = true;
+    return RVS_OK;
+}
+int rvs_tree_nearest(rvs_handle h, const int32_t *trees, const float *queries, int32_t Q, int32_t *idx, float *dist2) {
+    RVS_TRY(enter(h));
+    if (Q < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "Q < 0");
+    if (Q == 0) return RVS_OK;
+    if (!queries || !idx) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    if (h->trees.empty()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no tree");
+    if (trees)
+        for (int k = 0; k < Q; k++)
+            if (trees[k] < 0 || size_t(trees[k]) >= h->trees.size()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
+    RVS_TRY(tree_tables(h));
+    const size_t n = size_t(h->h_robot.n);
+    begin_call(h, size_t(Q) * (n * 4 + 12) + 64);
+    RVS_TRY(h2d(h, B_Q, queries, size_t(Q) * n * sizeof(float)));
+    if (trees) RVS_TRY(h2d(h, B_IDX, trees, size_t(Q) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_PROF, size_t(Q) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_DC, size_t(Q) * sizeof(float)));
+    NnArgs a{};
+    a.points = h->d_tree_ptr; a.counts = h->d_tree_cnt; a.n = int32_t(n);
+    a.tree_of = trees ? static_cast<const int32_t *>(h->buf[B_IDX].p) : nullptr;
+    a.queries = static_cast<const float *>(h->buf[B_Q].p); a.Q = Q;
+    a.idx = static_cast<int32_t *>(h->buf[B_PROF].p); a.dist2 = static_cast<float *>(h->buf[B_DC].p);
+    RVS_TRY(launched(h, launch_nn_nearest(a, h->stream), "nearest-neighbour kernel launch"));
+    RVS_TRY(d2h(h, idx, B_PROF, size_t(Q) * sizeof(int32_t)));
+    if (dist2) RVS_TRY(d2h(h, dist2, B_DC, size_t(Q) * sizeof(float)));
+    return finish(h);
+}
+int rvs_tree_radius(rvs_handle h, int32_t tree, const float *query, float radius, int32_t exclude, int32_t capacity, int32_t *idx, float *dist,
+                    int32_t *count) {
+    RVS_TRY(enter(h));
+    if (tree < 0 || size_t(tree) >= h->trees.size() || !query || !idx || !dist || !count || capacity < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad radius query");
+    RVS_TRY(tree_tables(h));
+    const size_t n = size_t(h->h_robot.n);
+    begin_call(h, n * 4 + size_t(capacity) * 8 + 64);
+    RVS_TRY(h2d(h, B_Q, query, n * sizeof(float)));
+    RVS_TRY(reserve(h, B_PROF, (size_t(capacity) + 1) * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_DC, size_t(capacity) * sizeof(float)));
+    NnArgs a{};
+    a.points = h->d_tree_ptr; a.counts = h->d_tree_cnt; a.n = int32_t(n);
+    a.queries = static_cast<const float *>(h->buf[B_Q].p);
+    a.tree = tree; a.radius = radius; a.exclude = exclude; a.capacity = capacity;
+    a.out_idx = static_cast<int32_t *>(h->buf[B_PROF].p) + 1; a.out_dist = static_cast<float *>(h->buf[B_DC].p);
+    a.out_count = static_cast<int32_t *>(h->buf[B_PROF].p);
+    RVS_TRY(launched(h, launch_nn_radius(a, h->stream), "radius kernel launch"));
+    RVS_TRY(d2h(h, count, B_PROF, sizeof(int32_t)));
+    // the hit lists are copied in full (the count is only known after the synchronisation); capacity bounds them
+    RVS_TRY(d2h_from(h, idx, static_cast<int32_t *>(h->buf[B_PROF].p) + 1, size_t(capacity) * sizeof(int32_t)));
+    RVS_TRY(d2h(h, dist, B_DC, size_t(capacity) * sizeof(float)));
+    return finish(h);
+}
 }  // extern "C"

@@ -30,6 +30,8 @@ LaunchTable launch_table_fast32();   // everything FP32, FMA contraction allowed
 cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st);
 cudaError_t launch_env_advance(const EnvArgs &a, cudaStream_t st);          // K updates of every obstacle -> timeline
 cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st);           // adopt timeline[kc], rewrite both copies of the obstacle table
+cudaError_t launch_nn_nearest(const NnArgs &a, cudaStream_t st);
+cudaError_t launch_nn_radius(const NnArgs &a, cudaStream_t st);
 cudaError_t launch_pack_scan(const ObstacleRec *scan, int M, void *pack, cudaStream_t st);   // fp16 copy of the scan-order obstacle table
 cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st);
 

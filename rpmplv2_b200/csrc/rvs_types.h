@@ -124,6 +124,27 @@ struct StoreArgs {
     uint8_t *status;           // [S]
 };
 
+// ---- nearest-neighbour / radius queries over device-resident planner trees (rvs_nn.cuh) ----------------------------------------------
+struct NnArgs {
+    const float *const *points;     // [T] device pointer of every tree's states
+    const int32_t *counts;          // [T] states per tree
+    int32_t n;                      // DOFs
+    // nearest: Q queries, query k against tree tree_of[k]
+    const int32_t *tree_of;         // [Q]
+    const float *queries;           // [Q][n]
+    int32_t Q;
+    int32_t *idx;                   // [Q]  (-1: empty tree)
+    float *dist2;                   // [Q]  squared distance (nanoflann's out_dist_sqr)
+    // radius: ONE query against ONE tree
+    int32_t tree;
+    float radius;
+    int32_t exclude;                // state index that is the query itself (-1: none)
+    int32_t capacity;               // room in out_idx / out_dist
+    int32_t *out_idx;               // hits in TREE ORDER
+    float *out_dist;
+    int32_t *out_count;             // total number of hits (may exceed capacity: the caller then re-queries with more room)
+};
+
 // ---- dynamic environment (rvs_env.cuh) -------------------------------------------------------------------------------
 // One obstacle of env::Environment as it sits in HBM (64 bytes): what Environment::updateEnvironment reads and writes.
 struct EnvRec {

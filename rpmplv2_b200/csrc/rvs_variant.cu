@@ -7,6 +7,7 @@
 #include "rvs_valid_wq.cuh"
 #include "rvs_store.cuh"
 #include "rvs_env.cuh"
+#include "rvs_nn.cuh"
 #include "rvs_launch.h"
 
 #include <map>
@@ -190,6 +191,15 @@ cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st) {
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_pack_scan(a.obstacles_scan, a.M, a.obstacles_pack, st);
+}
+cudaError_t launch_nn_nearest(const NnArgs &a, cudaStream_t st) {
+    if (a.Q <= 0) return cudaSuccess;
+    nn_nearest_kernel<<<unsigned(a.Q), kNnBlock, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_nn_radius(const NnArgs &a, cudaStream_t st) {
+    nn_radius_kernel<<<1, kNnBlock, 0, st>>>(a);
+    return cudaGetLastError();
 }
 cudaError_t launch_pack_scan(const ObstacleRec *scan, int M, void *pack, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;

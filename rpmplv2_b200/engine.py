@@ -67,6 +67,12 @@ SYMBOLS = {
     "rvs_self_collision_capsules": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_set_self_collision": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.c_float]),
     "rvs_get_self_collision": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)]),
+    "rvs_tree_create": (ctypes.c_int, [_H, c_i32p]),
+    "rvs_tree_clear": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_tree_size": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_tree_append": (ctypes.c_int, [_H, ctypes.c_int32, c_f32p, ctypes.c_int32]),
+    "rvs_tree_nearest": (ctypes.c_int, [_H, c_i32p, c_f32p, ctypes.c_int32, c_i32p, c_f32p]),
+    "rvs_tree_radius": (ctypes.c_int, [_H, ctypes.c_int32, c_f32p, ctypes.c_float, ctypes.c_int32, ctypes.c_int32, c_i32p, c_f32p, c_i32p]),
     "rvs_check_states": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_check_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_self_collision_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p, c_f32p]),
@@ -381,6 +387,41 @@ class Engine:
         hit, out = np.empty(q1.shape[0], np.uint8), np.empty_like(q2)
         self._check(self._lib.rvs_self_collision_edges(self._h, _p(q1, c_f32p), _p(q2, c_f32p), q1.shape[0], _p(hit, c_u8p), _p(out, c_f32p)))
         return hit, out
+
+    # -- device-resident planner trees (base::Tree's nearest neighbour, RRTx::findNeighbors) ---------------------
+    def tree_create(self) -> int:
+        t = ctypes.c_int32(-1)
+        self._check(self._lib.rvs_tree_create(self._h, ctypes.byref(t)))
+        return int(t.value)
+
+    def tree_append(self, tree: int, q) -> None:
+        q = _f32(q, (-1, self.n))
+        self._check(self._lib.rvs_tree_append(self._h, tree, _p(q, c_f32p), q.shape[0]))
+
+    def tree_clear(self, tree: int) -> None:
+        self._check(self._lib.rvs_tree_clear(self._h, tree))
+
+    def tree_size(self, tree: int) -> int:
+        return int(self._lib.rvs_tree_size(self._h, tree))
+
+    def tree_nearest(self, queries, trees=None):
+        """Tree::getNearestState for Q queries in one launch -> (index[Q], squared distance[Q])."""
+        queries = _f32(queries, (-1, self.n))
+        Q = queries.shape[0]
+        idx, d2 = np.empty(Q, np.int32), np.empty(Q, np.float32)
+        tr = None if trees is None else np.ascontiguousarray(trees, np.int32)
+        self._check(self._lib.rvs_tree_nearest(self._h, _p(tr, c_i32p), _p(queries, c_f32p), Q, _p(idx, c_i32p), _p(d2, c_f32p)))
+        return idx, d2
+
+    def tree_radius(self, tree: int, query, radius: float, exclude: int = -1, capacity: int = 4096):
+        """RRTx::findNeighbors: (indices in tree order, distances) of the states within `radius` (ss->getNorm) of `query`."""
+        query = _f32(query, (self.n,))
+        while True:
+            idx, dist, cnt = np.empty(capacity, np.int32), np.empty(capacity, np.float32), ctypes.c_int32(0)
+            self._check(self._lib.rvs_tree_radius(self._h, tree, _p(query, c_f32p), float(radius), exclude, capacity, _p(idx, c_i32p), _p(dist, c_f32p), ctypes.byref(cnt)))
+            if cnt.value <= capacity:
+                return idx[:cnt.value].copy(), dist[:cnt.value].copy()
+            capacity = int(cnt.value)
 
     def check_states(self, q) -> np.ndarray:
         """isValid(q) && !robot->checkSelfCollision(q) in one call (RRTConnect.cpp:13-15, MotionValidity.cpp:42)."""

@@ -30,11 +30,25 @@ class PlanResult(ctypes.Structure):
                 ("num_edges", ctypes.c_int64), ("num_distances", ctypes.c_int64), ("num_spines", ctypes.c_int64)]
 
 
+class RrtxConfig(ctypes.Structure):
+    _fields_ = [("eps_step", ctypes.c_float), ("r_rewire", ctypes.c_float), ("max_neighbors", ctypes.c_int32),
+                ("one_call_per_iteration", ctypes.c_int32), ("device_index", ctypes.c_int32)]
+
+
+class RrtxStats(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int64) for k in ("states", "iterations", "trapped", "backend_calls", "edges_checked", "edges_reference", "reparented", "rewired", "reseated")]
+
+
+c_i32p = ctypes.POINTER(ctypes.c_int32)
+
 SYMBOLS = {
     "rvsplan_default_config": (None, [ctypes.c_int32, ctypes.POINTER(PlanConfig)]),
     "rvsplan_solve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
                                            ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
     "rvsplan_last_error": (ctypes.c_char_p, []),
+    "rvsplan_rrtx_default_config": (None, [ctypes.POINTER(RrtxConfig)]),
+    "rvsplan_rrtx_grow": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(RrtxConfig), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_i32p, c_f32p,
+                                         c_i32p, ctypes.c_int32, c_i32p, c_i32p, c_i32p, ctypes.POINTER(RrtxStats)]),
 }
 
 _lib = None
@@ -94,6 +108,44 @@ def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_p
     if rc != 0:
         raise RvsError(rc, (lib.rvsplan_last_error() or b"").decode())
     return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1]), "kernel_launches": int(stats[2])}
+
+
+def rrtx_config(**overrides) -> RrtxConfig:
+    """configuration_rrtx.yaml's EPS_STEP / R_REWIRE / MAX_NEIGHBORS plus the two execution switches of rvsplan_rrtx_grow."""
+    cfg = RrtxConfig()
+    load_library().rvsplan_rrtx_default_config(ctypes.byref(cfg))
+    for k, v in overrides.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def rrtx_call(fn, handle, cfg: RrtxConfig, n: int, q_root, samples, path_start: int = -1, max_states: Optional[int] = None):
+    """Shared by rrtx_grow and the CPU-oracle twin (oracle_binding.plan_rrtx_grow): same signature after the handle."""
+    q_root = np.ascontiguousarray(q_root, np.float32).reshape(n)
+    samples = np.ascontiguousarray(samples, np.float32).reshape(-1, n)
+    S = samples.shape[0]
+    cap = max_states or S + 1
+    coord, parent, cost = np.zeros((cap, n), np.float32), np.zeros(cap, np.int32), np.zeros(cap, np.float32)
+    new_index, path = np.zeros(max(S, 1), np.int32), np.zeros(cap, np.int32)
+    path_len, path_invalid, stats = ctypes.c_int32(0), ctypes.c_int32(0), RrtxStats()
+    rc = fn(handle, ctypes.byref(cfg), q_root.ctypes.data_as(c_f32p), samples.ctypes.data_as(c_f32p), S, cap, coord.ctypes.data_as(c_f32p),
+            parent.ctypes.data_as(c_i32p), cost.ctypes.data_as(c_f32p), new_index.ctypes.data_as(c_i32p), path_start, path.ctypes.data_as(c_i32p),
+            ctypes.byref(path_len), ctypes.byref(path_invalid), ctypes.byref(stats))
+    if rc != 0:
+        return rc, None
+    k = int(stats.states)
+    return 0, dict(coord=coord[:k].copy(), parent=parent[:k].copy(), cost=cost[:k].copy(), new_index=new_index[:S].copy(), path=path[:path_len.value].copy(),
+                   path_invalid=bool(path_invalid.value), stats={f: int(getattr(stats, f)) for f, _ in RrtxStats._fields_})
+
+
+def rrtx_grow(eng: Engine, cfg: RrtxConfig, q_root, samples, path_start: int = -1, max_states: Optional[int] = None) -> dict:
+    """RRTx's tree growth over the CUDA engine (include/rvs_planning.h: rvsplan_rrtx_grow): the tree rooted at q_root that RRTx::solve's
+    loop builds from the random states `samples`; every candidate edge of an iteration is one batched engine call."""
+    lib = load_library()
+    rc, out = rrtx_call(lib.rvsplan_rrtx_grow, eng._h, cfg, eng.n, q_root, samples, path_start, max_states)
+    if rc != 0:
+        raise RvsError(rc, (lib.rvsplan_last_error() or b"").decode())
+    return out
 
 
 def _eigen_row(v) -> str:
