@@ -272,7 +272,7 @@ typedef enum {
     RVS_MOTION_STRAIGHT = 0,           /* Environment::moveStraight          (Environment.cpp:224-238) */
     RVS_MOTION_CIRCULAR = 1,           /* Environment::moveCircular          (:241-258) */
     RVS_MOTION_TWO_TUNNELS = 2,        /* Environment::moveTwoTunnels        (:261-289) */
-    RVS_MOTION_RANDOM_DIRECTIONS = 3,  /* Environment::moveRandomDirections  (:293-333) draws from libc rand(): RVS_ERR_UNSUPPORTED */
+    RVS_MOTION_RANDOM_DIRECTIONS = 3,  /* Environment::moveRandomDirections  (:289-333); see rvs_env_set_random_directions */
     RVS_MOTION_LIGHT_DIRECTIONS = 4    /* Environment::moveLightDirections   (:336-377) */
 } rvs_motion_type;
 
@@ -291,6 +291,18 @@ typedef struct {
 int  rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const float *pos, const uint8_t *rotated,
                  const float *vel, const float *max_vel, const uint8_t *is_dynamic, const uint8_t *is_ground,
                  const float *min_dist_tol, int32_t M);
+/* Extra state of Environment::moveRandomDirections (Environment.cpp:289-333), set after rvs_env_set:
+ *   acc             M x 3 object accelerations (env::Object::acceleration; NULL = keep, rvs_env_set starts them at zero like
+ *                   Environment::addObject's default argument)
+ *   ground_included Environment::ground_included as Environment::isValid reads it (< 0 = keep; rvs_env_set takes the robot's)
+ *   seed            the law draws its new directions from Eigen::Vector3f::Random, i.e. libc rand(), one stream for all objects in index
+ *                   order.  The engine replays that stream on the device (glibc's rand(): additive feedback r[i] = r[i-3] + r[i-31]):
+ *                   seed >= 0 = srand(seed); < 0 = keep the stream where it is (a fresh handle starts like a process that never
+ *                   called srand, i.e. srand(1)).  After srand(seed) on both sides the objects move exactly as in the reference.
+ * rvs_env_get_random_directions: current accelerations (may be NULL) and the number of rand() calls consumed since the last seed, so
+ * a host that shares its libc stream with the environment can advance its own by as many draws. */
+int  rvs_env_set_random_directions(rvs_handle h, const float *acc, int32_t ground_included, int64_t seed);
+int  rvs_env_get_random_directions(rvs_handle h, float *acc, uint32_t *draws);
 /* `steps` x Environment::updateEnvironment(delta_time) on the device; the resident obstacle table follows. */
 int  rvs_env_step(rvs_handle h, float delta_time, int32_t steps);
 /* current object positions / velocities (M x 3 each, either may be NULL) */

@@ -56,6 +56,14 @@ def _f32(a, shape=None):
     return a if shape is None else a.reshape(shape)
 
 
+def lib_norm(a, b) -> float:
+    """(q1 - q2).norm() in Eigen's summation order (rvs_oracle.hpp coord_norm) through the library."""
+    a, b = _f32(a), _f32(b)
+    fn = lib().orc_coord_norm
+    fn.restype = ctypes.c_float
+    return float(fn(_p(a, c_f32p), _p(b, c_f32p), ctypes.c_int32(len(a))))
+
+
 class Oracle:
     """CPU oracle with the same call surface as rpmplv2_b200.engine.Engine (host arrays)."""
 
@@ -113,10 +121,37 @@ class Oracle:
         return prm, [ctypes.c_int32(ep.motion_type), ctypes.c_int32(e["M"]), _p(e["half"], c_f32p), _p(e["pos"], c_f32p), _p(e["vel"], c_f32p),
                      _p(e["max_vel"], c_f32p), _p(e["sign"], c_i32p), _p(e["path_len"], c_f32p), _p(e["dynamic"], c_u8p)]
 
+    def env_set_random_directions(self, acc=None, ground_included: int = -1, seed: int = -1):
+        """Extra state of Environment::moveRandomDirections (Environment.cpp:289-333): accelerations, Environment::ground_included, srand(seed)."""
+        e = self._env
+        if "acc" not in e:
+            e["acc"], e["ground_included"], e["rand"] = np.zeros((e["M"], 3), np.float32), int(self.robot.ground_included), np.zeros(36, np.uint32)
+            lib().orc_libc_srand(ctypes.c_uint32(1), _p(e["rand"], ctypes.POINTER(ctypes.c_uint32)))
+        if acc is not None:
+            e["acc"] = _f32(acc, (e["M"], 3)).copy()
+        if ground_included >= 0:
+            e["ground_included"] = int(ground_included)
+        if seed >= 0:
+            lib().orc_libc_srand(ctypes.c_uint32(seed), _p(e["rand"], ctypes.POINTER(ctypes.c_uint32)))
+
+    def env_get_random_directions(self):
+        return self._env["acc"].copy(), int(self._env["rand"][35])
+
     def env_step(self, delta_time: float, steps: int = 1):
         prm, args = self._env_args()
         M = self._env["M"]
         mn, mx = np.empty((M, 3), np.float32), np.empty((M, 3), np.float32)
+        if self._env["ep"].motion_type == 3:
+            if "acc" not in self._env:
+                self.env_set_random_directions()
+            e = self._env
+            rc = lib().orc_env_update_random(_p(prm, c_f32p), ctypes.c_int32(e["ground_included"]), ctypes.c_int32(M), _p(e["half"], c_f32p), _p(e["pos"], c_f32p),
+                                             _p(e["vel"], c_f32p), _p(e["acc"], c_f32p), _p(e["max_vel"], c_f32p), _p(e["dynamic"], c_u8p), ctypes.c_float(delta_time),
+                                             ctypes.c_int32(steps), _p(e["rand"], ctypes.POINTER(ctypes.c_uint32)), _p(mn, c_f32p), _p(mx, c_f32p))
+            if rc:
+                raise RuntimeError(f"orc_env_update_random rc={rc}")
+            self.set_obstacles(mn, mx, e["ground"], e["tol"])
+            return
         rc = lib().orc_env_update(_p(prm, c_f32p), *args, ctypes.c_float(delta_time), ctypes.c_int32(steps), _p(mn, c_f32p), _p(mx, c_f32p))
         if rc:
             raise RuntimeError(f"orc_env_update rc={rc}")
@@ -125,9 +160,36 @@ class Oracle:
     def env_get(self):
         return self._env["pos"].copy(), self._env["vel"].copy()
 
+    def _motion_validity_random(self, q_prev, q_cur, K, delta_time, commit_edge):
+        """MotionValidity::check under random_directions as a composition of this oracle's own pieces: K x (one update; interpolate; isValid)."""
+        e = self._env
+        keep = {k: e[k].copy() for k in ("pos", "vel", "acc", "rand")}
+        E = q_prev.shape[0]
+        first = np.zeros(E, np.int32)
+        states = []
+        dist = np.array([np.float32(lib_norm(q_prev[i], q_cur[i])) for i in range(E)], np.float32)
+        for k in range(1, K + 1):
+            self.env_step(delta_time, 1)
+            states.append({kk: e[kk].copy() for kk in ("pos", "vel", "acc", "rand")})
+            step = (dist * np.float32(k) / np.float32(K)).astype(np.float32)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                f = (step / dist).astype(np.float32)
+            pts = np.where((dist > 0)[:, None], q_prev + (q_cur - q_prev) * f[:, None], q_cur).astype(np.float32)
+            ok = self.is_valid(pts)
+            first[(first == 0) & ~ok.astype(bool)] = k
+        kc = None if commit_edge < 0 else (int(first[commit_edge]) or K)
+        st = keep if kc is None else states[kc - 1]
+        for kk in ("pos", "vel", "acc", "rand"):
+            e[kk] = st[kk].copy()
+        half = e["half"]
+        self.set_obstacles(e["pos"] + (-half), e["pos"] + half, e["ground"], e["tol"])
+        return first == 0, first
+
     def motion_validity(self, q_prev, q_cur, K: int, delta_time: float, commit_edge: int = -1):
         q_prev, q_cur = _f32(q_prev, (-1, self.n)), _f32(q_cur, (-1, self.n))
         E = q_prev.shape[0]
+        if self._env["ep"].motion_type == 3:
+            return self._motion_validity_random(q_prev, q_cur, K, delta_time, commit_edge)
         valid, first = np.empty(E, np.uint8), np.empty(E, np.int32)
         prm, args = self._env_args()
         rc = lib().orc_motion_validity(self._h, _p(prm, c_f32p), *args, _p(q_prev, c_f32p), _p(q_cur, c_f32p), ctypes.c_int64(E), ctypes.c_int32(K),

@@ -325,6 +325,7 @@ int orc_env_update(const float *env_params, int32_t motion_type, int32_t M, cons
 
 // Environment::moveRandomDirections (Environment.cpp:289-333): `steps` updates with the libc stream `rand_state` (36 words: LibcRand's table, position,
 // draws; orc_libc_srand fills it).  acc is updated in place like pos and vel.
+float orc_coord_norm(const float *a, const float *b, int32_t n) { return orc::coord_norm(a, b, n); }
 void orc_libc_srand(uint32_t seed, uint32_t *rand_state) {
     orc::LibcRand g;
     g.seed(seed);

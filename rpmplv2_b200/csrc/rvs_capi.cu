@@ -56,6 +56,9 @@ struct rvs_engine {
     EnvRec *d_env_tl = nullptr;
     float *d_scan_key = nullptr;
     int32_t *d_first_invalid = nullptr;
+    LibcRand *d_rand = nullptr;   // [1 + rand_tl_cap]: the libc stream of random_directions, then its per-update timeline
+    size_t rand_tl_cap = 0;
+    int32_t env_ground_included = 0;
     int env_cap = 0;
     size_t env_tl_cap = 0, env_fi_cap = 0;
     bool env_on = false;
@@ -391,6 +394,7 @@ int rvs_destroy(rvs_handle h) {
     if (h->d_env_tl) cudaFree(h->d_env_tl);
     if (h->d_scan_key) cudaFree(h->d_scan_key);
     if (h->d_first_invalid) cudaFree(h->d_first_invalid);
+    if (h->d_rand) cudaFree(h->d_rand);
     if (h->d_robot) cudaFree(h->d_robot);
     if (h->d_pair_count) cudaFree(h->d_pair_count);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
@@ -987,7 +991,27 @@ EnvArgs env_args(rvs_engine *h, int32_t K, float dt) {
     a.obstacles = h->d_obs; a.obstacles_scan = h->d_obs + h->obs_cap; a.scan_dist = reinterpret_cast<float *>(h->d_obs + 2 * size_t(h->obs_cap));
     a.obstacles_pack = h->d_obs_pack;
     a.scan_key = h->d_scan_key;
+    a.env_ground_included = h->env_ground_included;
+    a.rand_state = h->d_rand; a.rand_timeline = h->d_rand ? h->d_rand + 1 : nullptr;
     return a;
+}
+// (re)allocate the stream + its timeline of K states, keeping the current stream
+int env_rand_ready(rvs_engine *h, size_t K) {
+    if (h->d_rand && K <= h->rand_tl_cap) return RVS_OK;
+    const size_t cap = std::max<size_t>(K, 16);
+    LibcRand *grown = nullptr;
+    RVS_CUDA(h, cudaMalloc(&grown, (1 + cap) * sizeof(LibcRand)));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->d_rand) {
+        RVS_CUDA(h, cudaMemcpy(grown, h->d_rand, sizeof(LibcRand), cudaMemcpyDeviceToDevice));
+        RVS_CUDA(h, cudaFree(h->d_rand));
+    } else {
+        LibcRand g;
+        g.seed(1);                                                         // rand() without srand() behaves as after srand(1)
+        RVS_CUDA(h, cudaMemcpy(grown, &g, sizeof(LibcRand), cudaMemcpyHostToDevice));
+    }
+    h->d_rand = grown; h->rand_tl_cap = cap;
+    return RVS_OK;
 }
 int env_ready(rvs_engine *h, int32_t K, float dt) {
     if (!h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no dynamic environment: call rvs_env_set first");
@@ -999,6 +1023,7 @@ int env_ready(rvs_engine *h, int32_t K, float dt) {
         RVS_CUDA(h, cudaMalloc(&h->d_env_tl, std::max<size_t>(need, 1) * sizeof(EnvRec)));
         h->env_tl_cap = need;
     }
+    if (h->env_prm.motion_type == RVS_MOTION_RANDOM_DIRECTIONS) RVS_TRY(env_rand_ready(h, size_t(K)));
     return RVS_OK;
 }
 }  // namespace
@@ -1007,8 +1032,6 @@ int rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const 
                 const uint8_t *is_dynamic, const uint8_t *is_ground, const float *min_dist_tol, int32_t M) {
     RVS_TRY(enter(h));
     if (!ep || M < 0 || (M > 0 && (!dim || !pos))) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad environment arrays");
-    if (ep->motion_type == RVS_MOTION_RANDOM_DIRECTIONS)
-        return fail(h, RVS_ERR_UNSUPPORTED, "random_directions draws from libc rand() in the reference (Environment.cpp:293-333): not reproducible, not supported");
     if (ep->motion_type < RVS_MOTION_STRAIGHT || ep->motion_type > RVS_MOTION_LIGHT_DIRECTIONS) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown motion_type");
     std::vector<EnvRec> recs(size_t(M), EnvRec{});
     std::vector<float> mn(size_t(M) * 3), mx(size_t(M) * 3);
@@ -1029,6 +1052,7 @@ int rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const 
         r.tol = min_dist_tol ? min_dist_tol[j] : h->prm.max_distance;
         r.flags = (is_ground && is_ground[j]) ? 1u : 0u;
     }
+    h->env_ground_included = h->h_robot.ground_included;                    // Environment.cpp:64-68: the robot node's ground_included
     RVS_TRY(rvs_set_obstacles(h, mn.data(), mx.data(), is_ground, min_dist_tol, M));
     if (M > h->env_cap) {
         if (h->d_env) RVS_CUDA(h, cudaFree(h->d_env));
@@ -1042,6 +1066,49 @@ int rvs_env_set(rvs_handle h, const rvs_env_params *ep, const float *dim, const 
     if (M > 0) RVS_CUDA(h, cudaMemcpy(h->d_env, recs.data(), size_t(M) * sizeof(EnvRec), cudaMemcpyHostToDevice));
     h->env_prm = *ep;
     h->env_on = true;
+    return RVS_OK;
+}
+
+// random_directions' extra state: accelerations, the ground rule of Environment::isValid, and the libc stream (srand(seed))
+int rvs_env_set_random_directions(rvs_handle h, const float *acc, int32_t ground_included, int64_t seed) {
+    RVS_TRY(enter(h));
+    if (!h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no dynamic environment: call rvs_env_set first");
+    if (seed > 0xFFFFFFFFll) return fail(h, RVS_ERR_INVALID_ARGUMENT, "seed does not fit srand()'s unsigned int");
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (acc && h->M > 0) {
+        std::vector<EnvRec> recs(static_cast<size_t>(h->M), EnvRec{});
+        RVS_CUDA(h, cudaMemcpy(recs.data(), h->d_env, size_t(h->M) * sizeof(EnvRec), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < h->M; j++)
+            for (int c = 0; c < 3; c++) recs[size_t(j)].acc[c] = acc[3 * j + c];
+        RVS_CUDA(h, cudaMemcpy(h->d_env, recs.data(), size_t(h->M) * sizeof(EnvRec), cudaMemcpyHostToDevice));
+    }
+    if (ground_included >= 0) h->env_ground_included = ground_included;
+    RVS_TRY(env_rand_ready(h, 1));
+    if (seed >= 0) {
+        LibcRand g;
+        g.seed(uint32_t(seed));
+        RVS_CUDA(h, cudaMemcpy(h->d_rand, &g, sizeof(LibcRand), cudaMemcpyHostToDevice));
+    }
+    return RVS_OK;
+}
+int rvs_env_get_random_directions(rvs_handle h, float *acc, uint32_t *draws) {
+    RVS_TRY(enter(h));
+    if (!h->env_on) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no dynamic environment: call rvs_env_set first");
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (acc && h->M > 0) {
+        std::vector<EnvRec> recs(static_cast<size_t>(h->M), EnvRec{});
+        RVS_CUDA(h, cudaMemcpy(recs.data(), h->d_env, size_t(h->M) * sizeof(EnvRec), cudaMemcpyDeviceToHost));
+        for (int j = 0; j < h->M; j++)
+            for (int c = 0; c < 3; c++) acc[3 * j + c] = recs[size_t(j)].acc[c];
+    }
+    if (draws) {
+        *draws = 0;
+        if (h->d_rand) {
+            LibcRand g;
+            RVS_CUDA(h, cudaMemcpy(&g, h->d_rand, sizeof(LibcRand), cudaMemcpyDeviceToHost));
+            *draws = g.draws;
+        }
+    }
     return RVS_OK;
 }
 

@@ -14,7 +14,11 @@
 // Arithmetic: FP32, no FMA contraction, IEEE division / square root (this header is compiled in the EXACT translation unit), same
 // operation order as the reference's Eigen expressions -> bit-identical to oracle/rvs_oracle_env.hpp for the straight, two_tunnels
 // and light_directions laws; the circular law calls atan2f / sinf / cosf, whose CUDA and glibc implementations differ in the
-// last ulp (tests use 1e-5 m there).  random_directions draws from libc rand() in the reference and is not supported.
+// last ulp (tests use 1e-5 m there).
+// random_directions (:289-333) draws from Eigen::Vector3f::Random = libc rand(), ONE stream shared by all obstacles in index order: the
+// device keeps its own copy of that stream (LibcRand, rvs_types.h: glibc's additive feedback generator, seeded like srand) and
+// env_advance_random_kernel (one warp) steps 32 obstacles at a time in parallel — an obstacle only touches the stream when its move is
+// rejected — and serialises the rejected ones in index order, so the draws land on the same obstacles as in the reference's loop.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -76,6 +80,44 @@ __device__ __forceinline__ void env_step(EnvRec &o, const EnvArgs &a) {
     }
 }
 
+// ---- random_directions (:289-333) -----------------------------------------------------------------------------------------------------
+// Environment::isValid(pos, vel) (:169-190)
+__device__ __forceinline__ bool env_pos_valid(const EnvArgs &a, float x, float y, float z, float vel) {
+    const float tol_radius = fmaxf(vel / a.robot_max_vel, a.base_radius);
+    const float rc = env_norm3(x - a.ws_center[0], y - a.ws_center[1], z - a.ws_center[2]);
+    const float rxy = sqrtf(x * x + y * y);
+    if (a.env_ground_included > 0) return !(rc > a.ws_radius || z < 0 || (rxy < tol_radius && z < a.ws_center[2]) || rc < tol_radius);
+    return !(rc > a.ws_radius || (rxy < tol_radius && z < a.ws_center[2] && z > -a.base_radius) || rc < tol_radius);
+}
+// one attempt of the loop body: 0 = moved, 1 = velocity above max_vel (wants a new acceleration), 2 = position invalid (wants a new velocity)
+__device__ __forceinline__ int env_random_try(EnvRec &o, const EnvArgs &a, float &vel_intensity) {
+    const float dt = a.dt;
+    const float vx = o.vel[0] + dt * o.acc[0], vy = o.vel[1] + dt * o.acc[1], vz = o.vel[2] + dt * o.acc[2];
+    const float px = o.pos[0] + dt * vx, py = o.pos[1] + dt * vy, pz = o.pos[2] + dt * vz;
+    vel_intensity = env_norm3(vx, vy, vz);
+    if (vel_intensity > o.max_vel) return 1;
+    if (!env_pos_valid(a, px, py, pz, vel_intensity)) return 2;
+    o.vel[0] = vx; o.vel[1] = vy; o.vel[2] = vz;
+    o.pos[0] = px; o.pos[1] = py; o.pos[2] = pz;
+    return 0;
+}
+// the reference's `i--` retries of ONE obstacle, drawing from the shared stream until the move is accepted (bounded: the reference
+// would spin forever on an obstacle that cannot be placed, e.g. zero acceleration above max_vel)
+__device__ __forceinline__ void env_random_retry(EnvRec &o, const EnvArgs &a, LibcRand &g, int why, float vel_intensity) {
+    for (int tries = 0; tries < 100000 && why != 0; tries++) {
+        const float rx = g.uniform(), ry = g.uniform(), rz = g.uniform();
+        const float nr = env_norm3(rx, ry, rz);
+        const float ux = rx / nr, uy = ry / nr, uz = rz / nr;                              // normalize(): *this /= norm()
+        if (why == 1) {
+            const float keep = env_norm3(o.acc[0], o.acc[1], o.acc[2]);
+            o.acc[0] = keep * ux; o.acc[1] = keep * uy; o.acc[2] = keep * uz;
+        } else {
+            o.vel[0] = vel_intensity * ux; o.vel[1] = vel_intensity * uy; o.vel[2] = vel_intensity * uz;
+        }
+        why = env_random_try(o, a, vel_intensity);
+    }
+}
+
 // AABB after setPosition (Object.cpp:21-26; FCL computeAABB of a box: centre -/+ half extents)
 __device__ __forceinline__ ObstacleRec env_aabb(const EnvRec &o) {
     ObstacleRec r;
@@ -92,6 +134,40 @@ __global__ void __launch_bounds__(128) env_advance_kernel(const EnvArgs a) {
     for (int k = 0; k < a.K; k++) {
         env_step(o, a);
         a.timeline[size_t(k) * a.M + j] = o;
+    }
+}
+
+// random_directions: ONE warp.  Per update and chunk of 32 obstacles: every lane tries its obstacle's move; the rejected ones are
+// completed one after the other in index order with the shared libc stream (kept in shared memory); the stream state after every
+// update is recorded next to the obstacle timeline.
+__global__ void __launch_bounds__(32) env_advance_random_kernel(const EnvArgs a) {
+    __shared__ LibcRand g;
+    const int lane = threadIdx.x;
+    for (int w = lane; w < kLibcRandWords; w += 32) reinterpret_cast<uint32_t *>(&g)[w] = reinterpret_cast<const uint32_t *>(a.rand_state)[w];
+    __syncwarp();
+    for (int k = 0; k < a.K; k++) {
+        const EnvRec *__restrict__ from = k == 0 ? a.state : a.timeline + size_t(k - 1) * a.M;
+        for (int c0 = 0; c0 < a.M; c0 += 32) {
+            const int j = c0 + lane;
+            EnvRec o{};
+            int why = 0;
+            float vel_intensity = 0.f;
+            if (j < a.M) {
+                o = from[j];
+                if (o.dynamic) why = env_random_try(o, a, vel_intensity);
+            }
+            unsigned pending = __ballot_sync(0xffffffffu, why != 0);
+            while (pending) {
+                const int l = __ffs(int(pending)) - 1;
+                pending &= pending - 1u;
+                if (lane == l) env_random_retry(o, a, g, why, vel_intensity);
+                __syncwarp();
+            }
+            if (j < a.M) a.timeline[size_t(k) * a.M + j] = o;
+        }
+        __syncwarp();
+        for (int w = lane; w < kLibcRandWords; w += 32) reinterpret_cast<uint32_t *>(a.rand_timeline + k)[w] = reinterpret_cast<const uint32_t *>(&g)[w];
+        __syncwarp();
     }
 }
 #endif
@@ -166,6 +242,7 @@ __global__ void __launch_bounds__(128) env_commit_kernel(const EnvArgs a) {
     if (a.commit_edge >= 0) { const int fi = a.first_invalid[a.commit_edge]; if (fi <= a.K) kc = fi; }
     const EnvRec o = a.timeline[size_t(kc - 1) * a.M + j];
     a.state[j] = o;
+    if (a.motion_type == RVS_MOTION_RANDOM_DIRECTIONS && j == 0) *a.rand_state = a.rand_timeline[kc - 1];    // the stream as the adopted updates left it
     const ObstacleRec r = env_aabb(o);
     a.obstacles[j] = r;
     a.scan_key[j] = env_base_distance(r, a.robot);

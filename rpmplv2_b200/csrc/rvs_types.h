@@ -4,6 +4,12 @@
 
 #include "../../include/rvs_cuda.h"
 
+#if defined(__CUDACC__)
+#define RVS_HD __host__ __device__
+#else
+#define RVS_HD
+#endif
+
 namespace rvs {
 
 constexpr int kMaxDofs = RVS_MAX_DOFS;
@@ -157,9 +163,42 @@ struct EnvRec {
     uint32_t dynamic;     // label == "dynamic_obstacle"
     float tol;            // min_dist_tol
     uint32_t flags;       // bit0: label == "ground"
-    uint32_t pad;
+    float acc[3];         // env::Object::acceleration (random_directions)
+    uint32_t pad[2];
 };
-static_assert(sizeof(EnvRec) == 64, "EnvRec must be 64 bytes");
+static_assert(sizeof(EnvRec) == 80, "EnvRec must be 80 bytes (a multiple of 16)");
+
+// glibc rand() after srand(seed) (random_r TYPE_3: r[i] = r[i-3] + r[i-31] over a 34-word table, output r[i] >> 1), the stream
+// Eigen::Vector3f::Random draws from in Environment::moveRandomDirections (Environment.cpp:309, :318).  36 words: table, position, draws.
+constexpr int kLibcRandWords = 36;
+struct LibcRand {
+    uint32_t r[34];
+    uint32_t pos, draws;
+    RVS_HD uint32_t next() {
+        const uint32_t v = r[(pos + 3) % 34] + r[(pos + 31) % 34];
+        r[pos] = v;
+        pos = (pos + 1) % 34;
+        draws++;
+        return v >> 1;
+    }
+    RVS_HD float uniform() { return 2.0f * float(next()) / float(2147483647) - 1.0f; }      // Eigen's random<float>(): [-1, 1]
+    void seed(uint32_t s) {
+        if (s == 0) s = 1;
+        int32_t word = int32_t(s);
+        r[0] = uint32_t(word);
+        for (int i = 1; i < 31; i++) {
+            const int32_t hi = word / 127773, lo = word % 127773;         // 16807 * word mod (2^31 - 1), Schrage's split
+            word = 16807 * lo - 2836 * hi;
+            if (word < 0) word += 2147483647;
+            r[i] = uint32_t(word);
+        }
+        for (int i = 31; i < 34; i++) r[i] = r[i - 31];
+        pos = 0; draws = 0;
+        for (int i = 0; i < 310; i++) next();
+        draws = 0;
+    }
+};
+static_assert(sizeof(LibcRand) == kLibcRandWords * 4, "LibcRand layout");
 
 struct EnvArgs {
     const RobotDev *robot;
@@ -178,6 +217,10 @@ struct EnvArgs {
     ObstacleRec *obstacles, *obstacles_scan;
     float *scan_dist, *scan_key;
     void *obstacles_pack;        // fp16 copy of the scan-order table (re-packed after every re-ranking)
+    // random_directions
+    int32_t env_ground_included; // Environment::ground_included (read by Environment::isValid only)
+    LibcRand *rand_state;        // the libc stream the law draws from
+    LibcRand *rand_timeline;     // [K] its state after k = 1..K updates (commit adopts the one that matches the adopted obstacles)
 };
 
 }  // namespace rvs

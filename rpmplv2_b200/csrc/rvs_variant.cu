@@ -179,7 +179,8 @@ cudaError_t launch_generate_configs(const KArgs &a, float *out, cudaStream_t st)
 }
 cudaError_t launch_env_advance(const EnvArgs &a, cudaStream_t st) {
     if (a.M <= 0 || a.K <= 0) return cudaSuccess;
-    env_advance_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
+    if (a.motion_type == RVS_MOTION_RANDOM_DIRECTIONS) env_advance_random_kernel<<<1, 32, 0, st>>>(a);
+    else env_advance_kernel<<<grid_for(a.M, 128), 128, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st) {

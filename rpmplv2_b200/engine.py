@@ -98,6 +98,8 @@ SYMBOLS = {
     "rvs_generate_configs_dev": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
     "rvs_set_culling": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_env_set": (ctypes.c_int, [_H, ctypes.POINTER(RvsEnvParams), c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_u8p, c_u8p, c_f32p, ctypes.c_int32]),
+    "rvs_env_set_random_directions": (ctypes.c_int, [_H, c_f32p, ctypes.c_int32, ctypes.c_int64]),
+    "rvs_env_get_random_directions": (ctypes.c_int, [_H, c_f32p, ctypes.POINTER(ctypes.c_uint32)]),
     "rvs_env_step": (ctypes.c_int, [_H, ctypes.c_float, ctypes.c_int32]),
     "rvs_env_get": (ctypes.c_int, [_H, c_f32p, c_f32p]),
     "rvs_motion_validity": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_int32, c_u8p, c_i32p]),
@@ -342,6 +344,17 @@ class Engine:
 
     def env_step(self, delta_time: float, steps: int = 1):
         self._check(self._lib.rvs_env_step(self._h, float(delta_time), int(steps)))
+
+    def env_set_random_directions(self, acc=None, ground_included: int = -1, seed: int = -1):
+        """Extra state of Environment::moveRandomDirections: accelerations [M, 3], Environment::ground_included, srand(seed)."""
+        acc = None if acc is None else _f32(acc, (self.M, 3))
+        self._check(self._lib.rvs_env_set_random_directions(self._h, _p(acc, c_f32p), int(ground_included), int(seed)))
+
+    def env_get_random_directions(self):
+        """-> (accelerations [M, 3], rand() calls consumed since the last seed)."""
+        acc, draws = np.empty((self.M, 3), np.float32), ctypes.c_uint32(0)
+        self._check(self._lib.rvs_env_get_random_directions(self._h, _p(acc, c_f32p), ctypes.byref(draws)))
+        return acc, int(draws.value)
 
     def env_get(self):
         pos, vel = np.empty((self.M, 3), np.float32), np.empty((self.M, 3), np.float32)

@@ -97,7 +97,7 @@ class Scenario:
         hands the objects to rvs_env_set, otherwise the AABBs go to rvs_set_obstacles."""
         eng = Engine(self.robot, params or robots.default_params(), device=device)
         if dynamic is None:
-            dynamic = self.motion_type is not None and self.motion_type != "random_directions" and bool(self.is_dynamic.any())
+            dynamic = self.motion_type is not None and bool(self.is_dynamic.any())
         if dynamic:
             eng.env_set(self.env_params(), self.dim, self.pos, vel=self.vel, max_vel=self.max_vel, is_dynamic=self.is_dynamic,
                         is_ground=self.is_ground, min_dist_tol=self.min_dist_tol, rotated=self.rotated)

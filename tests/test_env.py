@@ -214,9 +214,8 @@ def test_gpu_env_argument_errors(ob):
     eng = Engine(rb)
     with pytest.raises(RvsError):
         eng.env_step(0.01, 1)                                               # no environment yet
-    with pytest.raises(RvsError) as ei:
-        eng.env_set(params_for("random_directions"), **sc)                  # libc rand() in the reference: unsupported
-    assert ei.value.code == 5
+    with pytest.raises(RvsError):
+        eng.env_set_random_directions(seed=3)                               # no environment yet
     eng.env_set(params_for("straight"), **sc)
     with pytest.raises(RvsError):
         eng.update_obstacle_aabbs(sc["pos"], sc["pos"])                     # the table is driven by the environment now
@@ -261,6 +260,116 @@ def test_gpu_env_edge_cases(ob):
     with pytest.raises(RvsError):
         eng.env_step(0.01, 1)
     eng.update_obstacle_aabbs(sc["pos"] - half, sc["pos"] + half)            # allowed again
+    eng.close()
+
+
+# ------------------------------------------------------------------- random_directions (Environment.cpp:289-333): libc rand() replayed
+def test_oracle_libc_rand_replay_is_the_c_librarys_rand(ob):
+    """oracle/rvs_oracle_env.hpp LibcRand against the C library this interpreter runs on: srand(seed), then the same outputs."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    lib = ob.lib()
+    lib.orc_libc_rand.restype = ctypes.c_uint32
+    for seed in (0, 1, 7, 1005, 2 ** 31 + 5, 2 ** 32 - 1):
+        st = np.zeros(36, np.uint32)
+        lib.orc_libc_srand(ctypes.c_uint32(seed), st.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        libc.srand(ctypes.c_uint(seed))
+        assert [lib.orc_libc_rand(st.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) for _ in range(3000)] == [libc.rand() for _ in range(3000)]
+        assert st[35] == 3000
+
+
+def _random_oracle(ob, case):
+    prm, sc, acc, gi, dt, steps, seed = case
+    rb = robots.xarm6()
+    o = ob.Oracle(rb)
+    o.env_set(env_params("random_directions", ws_center=prm[:3], ws_radius=prm[3], base_radius=prm[4], robot_max_vel=prm[5]), **sc)
+    o.env_set_random_directions(acc, gi, seed)
+    return o
+
+
+def test_oracle_random_directions_matches_the_reference_environment_golden(ob):
+    """Environment::moveRandomDirections compiled unmodified, run after srand(seed) (tests/golden/make_env_golden.py: envref_update_random):
+    positions, velocities and accelerations of every object bit for bit along the whole run, and the stream ends where libc's does."""
+    import ctypes
+    mod = _golden_cases()
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "env_golden.npz")))
+    for k, case in enumerate(mod.random_cases()):
+        o = _random_oracle(ob, case)
+        dt, steps = float(case[4]), case[5]
+        keep = list(gold[f"r{k}_keep"])
+        for step in range(steps):
+            o.env_step(dt, 1)
+            if step in keep:
+                i = keep.index(step)
+                (pos, vel), (acc, _) = o.env_get(), o.env_get_random_directions()
+                assert np.array_equal(pos, gold[f"r{k}_pos"][i]) and np.array_equal(vel, gold[f"r{k}_vel"][i]) and np.array_equal(acc, gold[f"r{k}_acc"][i]), (k, step)
+        st = o._env["rand"]
+        ob.lib().orc_libc_rand.restype = ctypes.c_uint32
+        assert st[35] > 0 and ob.lib().orc_libc_rand(st.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) == gold[f"r{k}_next"][0]
+        # invariants of the law: speed never above max_vel, every object inside the workspace shell and above the ground
+        pos, vel = o.env_get()
+        dyn = case[1]["is_dynamic"].astype(bool)
+        assert (np.linalg.norm(vel[dyn], axis=1) <= case[1]["max_vel"][dyn] * (1 + 1e-6)).all()
+        assert (np.linalg.norm(pos[dyn] - case[0][:3], axis=1) <= case[0][3] * (1 + 1e-6)).all()
+
+
+@pytest.mark.gpu
+def test_gpu_random_directions_matches_the_oracle_and_the_reference_golden(ob):
+    """rvs_env_step under RVS_MOTION_RANDOM_DIRECTIONS: the device's replay of the libc stream moves every object exactly as the
+    reference's loop does (golden vectors of the compiled Environment.cpp), one update per call and many updates per call."""
+    from rpmplv2_b200.engine import Engine
+    mod = _golden_cases()
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "env_golden.npz")))
+    for k, case in enumerate(mod.random_cases()):
+        prm, sc, acc, gi, dt, steps, seed = case
+        ep = env_params("random_directions", ws_center=prm[:3], ws_radius=prm[3], base_radius=prm[4], robot_max_vel=prm[5])
+        for chunk in (1, 10):
+            eng = Engine(robots.xarm6())
+            eng.env_set(ep, **sc)
+            eng.env_set_random_directions(acc, gi, seed)
+            keep = list(gold[f"r{k}_keep"])
+            for step in range(chunk - 1, steps, chunk):
+                eng.env_step(float(dt), chunk)
+                if step in keep:
+                    i = keep.index(step)
+                    (pos, vel), (a_dev, draws) = eng.env_get(), eng.env_get_random_directions()
+                    assert np.array_equal(pos, gold[f"r{k}_pos"][i]) and np.array_equal(vel, gold[f"r{k}_vel"][i]) and np.array_equal(a_dev, gold[f"r{k}_acc"][i]), (k, chunk, step)
+            o = _random_oracle(ob, case)
+            o.env_step(float(dt), (steps // chunk) * chunk)
+            assert eng.env_get_random_directions()[1] == o.env_get_random_directions()[1] > 0           # same number of rand() calls consumed
+            q = synthetic.configs(robots.xarm6(), 512, seed=0xE5)
+            assert np.array_equal(eng.distance(q)[0], o.distance(q)[0])                                  # the resident table followed
+            eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_motion_validity_under_random_directions(ob):
+    """MotionValidity::check with obstacles moving by the random law: what-if queries leave objects AND stream untouched; a committed
+    motion leaves both as after first_invalid (or K) updates."""
+    from rpmplv2_b200.engine import Engine
+    rb = robots.xarm6()
+    sc = dynamic_scene(rb, 30, 77, speed=0.5, size=0.25)
+    ep = env_params("random_directions", ws_center=WS_CENTER, ws_radius=1.0, base_radius=0.15, robot_max_vel=3.0)
+    acc = np.zeros((31, 3), np.float32)
+    acc[2::2] = [0.3, -0.2, 0.1]
+    eng, o = Engine(rb), ob.Oracle(rb)
+    for x in (eng, o):
+        x.env_set(ep, **sc)
+        x.env_set_random_directions(acc, 2, 99)
+    q1, q2 = random_motions(rb, 256, 0x77)
+    K, dt = 10, 0.01
+    v_e, f_e = eng.motion_validity(q1, q2, K, dt)
+    v_o, f_o = o.motion_validity(q1, q2, K, dt)
+    assert np.array_equal(f_e, f_o) and 0 < v_o.sum() < len(v_o)
+    assert np.array_equal(eng.env_get()[0], sc["pos"]) and eng.env_get_random_directions()[1] == 0
+    for it in range(40):
+        e = it * 37 % 256
+        v_e, f_e = eng.motion_validity(q1, q2, K, dt, commit_edge=e)
+        v_o, f_o = o.motion_validity(q1, q2, K, dt, commit_edge=e)
+        assert np.array_equal(f_e, f_o), it
+        assert np.array_equal(eng.env_get()[0], o.env_get()[0]) and np.array_equal(eng.env_get()[1], o.env_get()[1])
+        assert eng.env_get_random_directions()[1] == o.env_get_random_directions()[1]
+    assert o.env_get_random_directions()[1] > 0
     eng.close()
 
 
