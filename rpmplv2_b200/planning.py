@@ -120,7 +120,8 @@ def rrtx_config(**overrides) -> RrtxConfig:
 
 
 def rrtx_call(fn, handle, cfg: RrtxConfig, n: int, q_root, samples, path_start: int = -1, max_states: Optional[int] = None):
-    """Shared by rrtx_grow and the CPU-oracle twin (oracle_binding.plan_rrtx_grow): same signature after the handle."""
+    """Marshalling of rvsplan_rrtx_grow; `fn` / `handle` are parameters so that the tests can drive their CPU checker, which exports a
+    function of the same signature, through the same code."""
     q_root = np.ascontiguousarray(q_root, np.float32).reshape(n)
     samples = np.ascontiguousarray(samples, np.float32).reshape(-1, n)
     S = samples.shape[0]
