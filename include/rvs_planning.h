@@ -60,6 +60,14 @@ void rvsplan_default_config(int32_t kind, rvsplan_config *out);
  * Returns an rvs_status; the message of a failure is available through rvs_last_error(h) or rvsplan_last_error(). */
 int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
                         int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats);
+/* The same call, also returning both trees of every run the way RBTConnect::outputPlannerData dumps them (`output_file << *trees[0]`,
+ * `*trees[1]`; src/planners/rbt/RBTConnect.cpp:203-253, base::Tree's operator<<, src/state_spaces/Tree.cpp:155-162): for run p and tree t
+ * (0 = from q_start, 1 = from q_goal) tree_sizes[2p + t] states in tree order, coordinates at tree_coord[(2p + t) * max_tree_states ...]
+ * (x num_dofs) and the parent's index inside the same tree (-1 for the root) at tree_parent[(2p + t) * max_tree_states ...]; a tree
+ * larger than max_tree_states is truncated (its size is still reported). */
+int rvsplan_solve_batch_trees(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
+                              int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats,
+                              float *tree_coord, int32_t *tree_parent, int32_t *tree_sizes, int32_t max_tree_states);
 const char *rvsplan_last_error(void);
 
 /* ---- RRTx's edge-batch consumers ----------------------------------------------------------------------------

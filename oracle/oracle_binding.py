@@ -381,6 +381,9 @@ def plan_lib():
                                                   ctypes.c_int32, ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.POINTER(ctypes.c_int64)]
         _plan_lib.orcplan_last_error.restype = ctypes.c_char_p
+        _plan_lib.orcplan_solve_batch_trees.restype = ctypes.c_int
+        _plan_lib.orcplan_solve_batch_trees.argtypes = [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64),
+                                                        ctypes.c_int32, ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, c_f32p, c_i32p, c_i32p, ctypes.c_int32]
         from rpmplv2_b200.planning import SYMBOLS as _PS
         _plan_lib.orcplan_rrtx_grow.restype, _plan_lib.orcplan_rrtx_grow.argtypes = _PS["rvsplan_rrtx_grow"]
     return _plan_lib
@@ -406,6 +409,24 @@ def plan_solve_batch(orc: "Oracle", cfg, q_start, q_goal, seeds=None, max_path: 
     if rc != 0:
         raise RuntimeError((lib_.orcplan_last_error() or b"").decode())
     return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1])}
+
+
+def plan_solve_batch_trees(orc: "Oracle", cfg, q_start, q_goal, seeds, max_path: int = 512, trees: int = 4096):
+    """plan_solve_batch (one pool) that also returns both trees of every run: the CPU twin of planning.solve_batch(..., trees=T)."""
+    from rpmplv2_b200.planning import PlanResult, attach_trees, unpack_results
+    n, P = orc.n, len(seeds)
+    qs = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(q_start, np.float32)), (P, n)))
+    qg = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(q_goal, np.float32)), (P, n)))
+    sd = np.ascontiguousarray(seeds, np.uint64)
+    results, paths = (PlanResult * P)(), np.zeros((P, max_path, n), np.float32)
+    tc, tp, ts = np.zeros((2 * P, trees, n), np.float32), np.zeros((2 * P, trees), np.int32), np.zeros(2 * P, np.int32)
+    rc = plan_lib().orcplan_solve_batch_trees(orc._h, ctypes.byref(cfg), _p(qs, c_f32p), _p(qg, c_f32p), sd.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), P,
+                                              results, _p(paths, c_f32p), max_path, _p(tc, c_f32p), _p(tp, c_i32p), _p(ts, c_i32p), trees)
+    if rc != 0:
+        raise RuntimeError((plan_lib().orcplan_last_error() or b"").decode())
+    out = unpack_results(results, paths, n)
+    attach_trees(out, tc, tp, ts)
+    return out
 
 
 def plan_rrtx_grow(orc: "Oracle", cfg, q_root, samples, path_start: int = -1, max_states=None) -> dict:

@@ -139,6 +139,28 @@ int orcplan_solve_batch(void *orc_handle, const rvsplan_config *cfg, const float
 }
 
 
+// one run (P = 1 per pool, single thread) with both trees returned: the CPU twin of rvsplan_solve_batch_trees
+int orcplan_solve_batch_trees(void *orc_handle, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds, int32_t P,
+                              rvsplan_result *results, float *paths, int32_t max_path, float *tree_coord, int32_t *tree_parent, int32_t *tree_sizes,
+                              int32_t max_tree_states) {
+    if (!orc_handle || !cfg || !q_start || !q_goal || !results || P < 0 || !tree_coord || !tree_parent || !tree_sizes) { g_error = "orcplan_solve_batch_trees: bad argument"; return 1; }
+    auto &eng = *static_cast<orc_capi::Engine *>(orc_handle);
+    const int n = eng.robot.n;
+    rvsplan::PlannerConfig pc = rvsplan::config_from_c(*cfg);
+    pc.keep_trees = true;
+    try {
+        OracleBackend backend(eng);
+        rvsplan::PlannerPool pool(backend, pc);
+        const auto res = pool.solve(q_start, q_goal, seeds, P, true);
+        rvsplan::results_to_c(res, n, results, paths, max_path);
+        rvsplan::trees_to_c(res, n, tree_coord, tree_parent, tree_sizes, max_tree_states);
+    } catch (const std::exception &ex) {
+        g_error = ex.what();
+        return 2;
+    }
+    return 0;
+}
+
 // RRTx's tree growth (rpmplv2_b200/cpp/planning/Rrtx.cpp) over the oracle: the CPU twin of rvsplan_rrtx_grow
 int orcplan_rrtx_grow(void *orc_handle, const rvsplan_rrtx_config *cfg, const float *q_root, const float *samples, int32_t S, int32_t max_states, float *coord,
                       int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path, int32_t *path_len, int32_t *path_invalid,

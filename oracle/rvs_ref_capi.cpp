@@ -439,6 +439,11 @@ int rvsref_motion_points_run(void *p, const float *env_params, int32_t motion_ty
 // only source of randomness, so a planner that draws from the same stream can be compared state by state.  base::Tree's kd-tree is the
 // exhaustive stand-in of env_shim/nanoflann.hpp (exact nearest neighbour, like nanoflann).
 // Returns 0, or 2 when the constructor throws (start / goal invalid).  path: path_len x n (truncated to max_path rows).
+// rvsref_set_plan_log(path): the next rvsref_plan calls also write the planner's own log (outputPlannerData: header, both trees, the path;
+// RBTConnect.cpp:203-253 / RRTConnect.cpp) to that file; NULL or "" switches it off again.
+static std::string g_plan_log;
+void rvsref_set_plan_log(const char *path) { g_plan_log = path ? path : ""; }
+
 int rvsref_plan(void *p, int32_t kind, const float *q_start, const float *q_goal, uint32_t seed, int64_t max_num_iter, int64_t max_num_states,
                 float max_planning_time, float eps_step, int32_t max_extension_steps, float delta, int32_t num_spines, int32_t num_layers,
                 int32_t num_iter_spine, int32_t use_expanded_bubble, float d_crit, int32_t *success, int64_t *iterations, int64_t *states,
@@ -472,6 +477,7 @@ int rvsref_plan(void *p, int32_t kind, const float *q_start, const float *q_goal
     *path_len = *success ? int32_t(pth.size()) : 0;
     for (int32_t k = 0; k < *path_len && k < max_path; k++)
         for (int i = 0; i < h->n; i++) path[size_t(k) * size_t(h->n) + size_t(i)] = pth[size_t(k)]->getCoord(i);
+    if (!g_plan_log.empty()) planner->outputPlannerData(g_plan_log);
     tree_sizes[0] = int64_t(planner->trees[0]->getNumStates());      // (getTree() returns a copy whose destructor clears the shared state list)
     tree_sizes[1] = int64_t(planner->trees[1]->getNumStates());
     return 0;

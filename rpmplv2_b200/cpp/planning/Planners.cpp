@@ -181,7 +181,17 @@ namespace rvsplan
 
 	private:
 		float elapsed() const { return std::chrono::duration<float>(Clock::now() - t0).count(); }
-		void finish(bool ok) { res.success = ok; res.planning_time = elapsed(); finished = true; req.kind = Request::NONE; }
+		void finish(bool ok)
+		{
+			res.success = ok; res.planning_time = elapsed(); finished = true; req.kind = Request::NONE;
+			if (cfg.keep_trees)
+				for (int t = 0; t < 2; t++)
+				{
+					res.tree_coord[t] = trees[t].coords();
+					res.tree_parent[t].clear();
+					for (const Node &nd : trees[t].nodes) res.tree_parent[t].push_back(nd.parent);
+				}
+		}
 
 		// RealVectorSpace::getRandomState (RealVectorSpace.cpp:27-41)
 		void randomState(const float *center, float *out)

@@ -17,10 +17,10 @@
 // threads (tree growth and the linear nearest-neighbour scans are the host-side cost of a round).
 //
 // Differences from the reference, all outside the collision/distance path: nearest neighbours are found by a linear scan
-// instead of nanoflann's kd-tree (both exact); random numbers come from a counter-based generator instead of
-// Eigen::VectorXf::Random (std::rand), so trees are not comparable run by run with the reference, only statistically;
-// robot self-collision is the constant `false` (true for every robot but xArm6, whose check ends in an FCL mesh test,
-// SURVEY.md 8c).
+// instead of nanoflann's kd-tree (both exact); random numbers come from a counter-based generator per run (independent of P and of
+// the thread schedule) unless RVS_PLAN_RNG=libc, which makes a single run draw from std::rand() exactly like Eigen::VectorXf::Random —
+// that run then reproduces the reference planner's own run state by state (tests/test_planners.py against the compiled solve()).
+// Robot self-collision (xArm6's capsule pre-filter and edge marching, xArm6.cpp:284-424) is part of the backend's isValid / isValidEdges.
 #ifndef RVS_PLANNING_PLANNERS_H
 #define RVS_PLANNING_PLANNERS_H
 
@@ -50,6 +50,7 @@ namespace rvsplan
 		float delta = 3.14159f;              // RBTConnectConfig::DELTA
 		int num_spines = 7;                  // RBTConnectConfig::NUM_SPINES
 		SpineParams spine;                   // D_CRIT, NUM_ITER_SPINE, USE_EXPANDED_BUBBLE, NUM_LAYERS (1 for RBT-Connect)
+		bool keep_trees = false;             // return both trees with the result (RBTConnect::outputPlannerData's `*trees[0]`, `*trees[1]`)
 	};
 
 	struct PlannerResult
@@ -61,6 +62,8 @@ namespace rvsplan
 		int64_t rounds = 0;                  // backend rounds this run took part in
 		int64_t num_valid = 0, num_edges = 0, num_distances = 0, num_spines = 0;   // queries it issued
 		std::vector<float> path;             // path_len x n
+		std::vector<float> tree_coord[2];    // the two trees as outputPlannerData dumps them (only when PlannerConfig::keep_trees): states in tree order
+		std::vector<int32_t> tree_parent[2]; // parent index inside the same tree, -1 for the root
 	};
 
 	// ---- coroutine plumbing --------------------------------------------------------------------------------------------
@@ -140,6 +143,7 @@ namespace rvsplan
 		int nearest(const float *q) const;                   // getNearestState (exact, linear scan)
 		const float *coord(int idx) const { return &q[size_t(idx) * n]; }
 		int size() const { return int(nodes.size()); }
+		const std::vector<float> &coords() const { return q; }
 		std::vector<Node> nodes;
 	private:
 		int n;

@@ -26,19 +26,24 @@ void rvsplan_default_config(int32_t kind, rvsplan_config *out)
 
 const char *rvsplan_last_error(void) { return g_error.c_str(); }
 
-int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
-						int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats)
+static int solve_batch_impl(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds, int32_t P,
+							rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats, float *tree_coord, int32_t *tree_parent,
+							int32_t *tree_sizes, int32_t max_tree_states)
 {
 	if (!h || !cfg || !q_start || !q_goal || !results || P < 0) { g_error = "rvsplan_solve_batch: NULL argument or P < 0"; return RVS_ERR_INVALID_ARGUMENT; }
 	if (cfg->kind < RVSPLAN_RRT_CONNECT || cfg->kind > RVSPLAN_RGBT_CONNECT || cfg->num_spines < 1 || cfg->spine.num_layers < 1 ||
 		cfg->max_extension_steps < 1 || !(cfg->eps_step > 0)) { g_error = "rvsplan_solve_batch: bad planner configuration"; return RVS_ERR_INVALID_ARGUMENT; }
+	const bool want_trees = tree_coord && tree_parent && tree_sizes && max_tree_states > 0;
 	try
 	{
 		rvsplan::CudaBackend backend(h);
-		rvsplan::PlannerPool pool(backend, rvsplan::config_from_c(*cfg));
+		rvsplan::PlannerConfig pc = rvsplan::config_from_c(*cfg);
+		pc.keep_trees = want_trees;
+		rvsplan::PlannerPool pool(backend, pc);
 		const int64_t launches0 = rvs_launch_count(h);
 		const std::vector<rvsplan::PlannerResult> res = pool.solve(q_start, q_goal, seeds, P, true);
 		rvsplan::results_to_c(res, backend.numDofs(), results, paths, max_path);
+		if (want_trees) rvsplan::trees_to_c(res, backend.numDofs(), tree_coord, tree_parent, tree_sizes, max_tree_states);
 		if (pool_stats) { pool_stats[0] = pool.rounds(); pool_stats[1] = pool.backendCalls(); pool_stats[2] = rvs_launch_count(h) - launches0; }
 	}
 	catch (const std::exception &e)
@@ -49,6 +54,19 @@ int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_
 	return RVS_OK;
 }
 
+int rvsplan_solve_batch(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
+						int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats)
+{
+	return solve_batch_impl(h, cfg, q_start, q_goal, seeds, P, results, paths, max_path, pool_stats, nullptr, nullptr, nullptr, 0);
+}
+
+int rvsplan_solve_batch_trees(rvs_handle h, const rvsplan_config *cfg, const float *q_start, const float *q_goal, const uint64_t *seeds,
+							  int32_t P, rvsplan_result *results, float *paths, int32_t max_path, int64_t *pool_stats,
+							  float *tree_coord, int32_t *tree_parent, int32_t *tree_sizes, int32_t max_tree_states)
+{
+	if (!tree_coord || !tree_parent || !tree_sizes || max_tree_states < 1) { g_error = "rvsplan_solve_batch_trees: NULL tree buffers"; return RVS_ERR_INVALID_ARGUMENT; }
+	return solve_batch_impl(h, cfg, q_start, q_goal, seeds, P, results, paths, max_path, pool_stats, tree_coord, tree_parent, tree_sizes, max_tree_states);
+}
 
 void rvsplan_rrtx_default_config(rvsplan_rrtx_config *out)
 {

@@ -42,6 +42,19 @@ namespace rvsplan
 		}
 	}
 
+	inline void trees_to_c(const std::vector<PlannerResult> &res, int n, float *tree_coord, int32_t *tree_parent, int32_t *tree_sizes, int32_t max_tree_states)
+	{
+		for (size_t p = 0; p < res.size(); p++)
+			for (int t = 0; t < 2; t++)
+			{
+				const size_t slot = 2 * p + size_t(t);
+				const size_t count = res[p].tree_parent[t].size(), keep = std::min<size_t>(count, size_t(max_tree_states));
+				tree_sizes[slot] = int32_t(count);
+				std::copy_n(res[p].tree_coord[t].begin(), keep * size_t(n), tree_coord + slot * size_t(max_tree_states) * size_t(n));
+				std::copy_n(res[p].tree_parent[t].begin(), keep, tree_parent + slot * size_t(max_tree_states));
+			}
+	}
+
 	// the body of rvsplan_rrtx_grow / its CPU-oracle twin: 0, or 1 when the tree outgrows max_states
 	inline int rrtx_grow(SpaceBackend &backend, NeighborIndex &index, const rvsplan_rrtx_config &c, const float *q_root, const float *samples, int32_t S,
 						 int32_t max_states, float *coord, int32_t *parent, float *cost, int32_t *new_index, int32_t path_start, int32_t *path,

@@ -45,6 +45,8 @@ SYMBOLS = {
     "rvsplan_default_config": (None, [ctypes.c_int32, ctypes.POINTER(PlanConfig)]),
     "rvsplan_solve_batch": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
                                            ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64)]),
+    "rvsplan_solve_batch_trees": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(PlanConfig), c_f32p, c_f32p, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32,
+                                                 ctypes.POINTER(PlanResult), c_f32p, ctypes.c_int32, ctypes.POINTER(ctypes.c_int64), c_f32p, c_i32p, c_i32p, ctypes.c_int32]),
     "rvsplan_last_error": (ctypes.c_char_p, []),
     "rvsplan_rrtx_default_config": (None, [ctypes.POINTER(RrtxConfig)]),
     "rvsplan_rrtx_grow": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(RrtxConfig), c_f32p, c_f32p, ctypes.c_int32, ctypes.c_int32, c_f32p, c_i32p, c_f32p,
@@ -90,9 +92,20 @@ def unpack_results(results, paths, n):
     return out
 
 
-def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_path: int = 512):
+def attach_trees(results, tree_coord, tree_parent, tree_sizes):
+    """results[p]['trees'] = [(coord [k, n], parent [k]) for the start tree and the goal tree]."""
+    for p, r in enumerate(results):
+        r["trees"] = []
+        for t in range(2):
+            k = min(int(tree_sizes[2 * p + t]), tree_coord.shape[1])
+            r["trees"].append((tree_coord[2 * p + t, :k].copy(), tree_parent[2 * p + t, :k].copy()))
+            r.setdefault("tree_sizes", []).append(int(tree_sizes[2 * p + t]))
+
+
+def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_path: int = 512, trees: int = 0):
     """P planner runs on the engine's resident scene. q_start / q_goal: [P, n] (or [n], broadcast over the seeds).
-    Returns (list of result dicts incl. 'path' [len, n], pool stats dict)."""
+    Returns (list of result dicts incl. 'path' [len, n], pool stats dict).  trees = T > 0: every result also carries both trees
+    (result['trees'], up to T states each) as RBTConnect::outputPlannerData dumps them."""
     lib = load_library()
     n = eng.n
     qs, qg = np.atleast_2d(np.asarray(q_start, np.float32)), np.atleast_2d(np.asarray(q_goal, np.float32))
@@ -103,11 +116,19 @@ def solve_batch(eng: Engine, cfg: PlanConfig, q_start, q_goal, seeds=None, max_p
     results = (PlanResult * P)()
     paths = np.zeros((P, max_path, n), np.float32)
     stats = (ctypes.c_int64 * 3)()
-    rc = lib.rvsplan_solve_batch(eng._h, ctypes.byref(cfg), qs.ctypes.data_as(c_f32p), qg.ctypes.data_as(c_f32p),
-                                 sd.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), P, results, paths.ctypes.data_as(c_f32p), max_path, stats)
+    head = (eng._h, ctypes.byref(cfg), qs.ctypes.data_as(c_f32p), qg.ctypes.data_as(c_f32p), sd.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), P, results,
+            paths.ctypes.data_as(c_f32p), max_path, stats)
+    if trees > 0:
+        tc, tp, ts = np.zeros((2 * P, trees, n), np.float32), np.zeros((2 * P, trees), np.int32), np.zeros(2 * P, np.int32)
+        rc = lib.rvsplan_solve_batch_trees(*head, tc.ctypes.data_as(c_f32p), tp.ctypes.data_as(c_i32p), ts.ctypes.data_as(c_i32p), trees)
+    else:
+        rc = lib.rvsplan_solve_batch(*head)
     if rc != 0:
         raise RvsError(rc, (lib.rvsplan_last_error() or b"").decode())
-    return unpack_results(results, paths, n), {"rounds": int(stats[0]), "backend_calls": int(stats[1]), "kernel_launches": int(stats[2])}
+    out = unpack_results(results, paths, n)
+    if trees > 0:
+        attach_trees(out, tc, tp, ts)
+    return out, {"rounds": int(stats[0]), "backend_calls": int(stats[1]), "kernel_launches": int(stats[2])}
 
 
 def rrtx_config(**overrides) -> RrtxConfig:
@@ -161,9 +182,10 @@ def write_planner_log(filename: str, result: dict, kind: int, num_dimensions: in
                       append: bool = False) -> None:
     """The planner `.log` the reference's visualizer reads (RBTConnect::outputPlannerData, /root/reference/src/planners/rbt/RBTConnect.cpp:203-253;
     /root/reference/visualizer/log_parser.py:33-67 parses the `Path:` block): header, planner info, the path as
-    `q: (...); parent q: (...)` lines (State's operator<<, src/state_spaces/State.cpp:58-65), the 25-dash terminator. The two tree
-    dumps the reference writes between the info and the path are omitted: the batched planners return paths, not trees, and the
-    parser does not read them."""
+    `q: (...); parent q: (...)` lines (State's operator<<, src/state_spaces/State.cpp:58-65), the 25-dash terminator. When the result
+    carries trees (solve_batch(..., trees=T)) the two dumps the reference writes between the info and the path are written too:
+    `Tree: <name>` and one state line per node in tree order (base::Tree's operator<<, src/state_spaces/Tree.cpp:155-162; the trees are
+    named "q_start" / "q_goal" by RRTConnect's constructor, RRTConnect.cpp:21-22)."""
     path = result.get("path")
     with open(filename, "a" if append else "w") as f:
         f.write(f"Space Type:      {space_type}\n")
@@ -174,9 +196,27 @@ def write_planner_log(filename: str, result: dict, kind: int, num_dimensions: in
         f.write(f"\t Number of iterations: {int(result['iterations'])}\n")
         f.write(f"\t Number of states:     {int(result['states'])}\n")
         f.write(f"\t Planning time [s]:    {float(result['planning_time']):.6g}\n")
+        for name, (coord, parent) in zip(("q_start", "q_goal"), result.get("trees") or []):
+            f.write(f"Tree: {name}\n")
+            for k in range(len(parent)):
+                par = "NONE" if parent[k] < 0 else f"({_eigen_row(coord[parent[k]])})"
+                f.write(f"q: ({_eigen_row(coord[k])}); parent q: {par}\n")
         if path is not None and len(path) > 0:
             f.write("Path:\n")
+            # every state is printed with ITS parent (State's operator<<): the previous path state on the start-tree side, the next one
+            # on the goal-tree side (RRTConnect::computePath walks the goal tree towards its root).  Without trees: the previous state.
+            goal_side = {}
+            if result.get("trees"):
+                coord, par = result["trees"][1]
+                goal_side = {coord[k].tobytes(): (None if par[k] < 0 else coord[par[k]]) for k in range(len(par))}
+            on_goal_side = False
             for i, q in enumerate(path):
-                parent = "NONE" if i == 0 else f"({_eigen_row(path[i - 1])})"
+                key = np.ascontiguousarray(q, np.float32).tobytes()
+                if not on_goal_side and key in goal_side and (i + 1 == len(path) or (goal_side[key] is not None and np.array_equal(goal_side[key], path[i + 1]))):
+                    on_goal_side = True
+                if on_goal_side:
+                    parent = "NONE" if goal_side[key] is None else f"({_eigen_row(goal_side[key])})"
+                else:
+                    parent = "NONE" if i == 0 else f"({_eigen_row(path[i - 1])})"
                 f.write(f"q: ({_eigen_row(q)}); parent q: {parent}\n")
         f.write("-" * 25 + "\n")

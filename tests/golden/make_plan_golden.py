@@ -61,6 +61,32 @@ def run_reference(lib, h, n, cfg, qs, qg, seed):
     return dict(invalid_ends=False, success=bool(suc.value), iterations=it.value, states=st.value, path=path[:pl.value].copy(), tree_sizes=(ts[0], ts[1]))
 
 
+LOG_RUNS = (("xarm6", planning.RGBT_CONNECT, 1), ("planar2", planning.RRT_CONNECT, 2))     # planner logs kept as text fixtures
+
+
+def log_fixture(name, kind, seed):
+    return os.path.join(ROOT, "tests", "golden", f"plan_log_{name}_k{kind}_s{seed}.log")
+
+
+def parse_log(text):
+    """-> ({tree name: [(q, parent q or None), ...]}, path [(q, parent q or None), ...]) from a planner log (RBTConnect::outputPlannerData's format)."""
+    def state(line):
+        a, b = line.split("; parent q: ")
+        q = [float(x) for x in a[len("q: ("):-1].split()]
+        return q, None if b.strip() == "NONE" else [float(x) for x in b.strip()[1:-1].split()]
+    trees, path, cur = {}, [], None
+    for line in text.splitlines():
+        if line.startswith("Tree: "):
+            cur = trees.setdefault(line[len("Tree: "):].strip(), [])
+        elif line.startswith("Path:"):
+            cur = path
+        elif line.startswith("q: (") and cur is not None:
+            cur.append(state(line))
+        elif line.startswith("-----"):
+            break
+    return trees, path
+
+
 if __name__ == "__main__":
     lib = refharness.load()
     data = {}
@@ -72,5 +98,13 @@ if __name__ == "__main__":
                 print(name, kind, seed, r["success"], r["iterations"], r["states"], len(r["path"]))
                 data[f"{name}_k{kind}_s{seed}_counts"] = np.array([r["success"], r["iterations"], r["states"], r["tree_sizes"][0], r["tree_sizes"][1]], np.int64)
                 data[f"{name}_k{kind}_s{seed}_path"] = r["path"]
+        for lname, lkind, lseed in LOG_RUNS:
+            if lname == name:                                            # the reference's own log of that run (outputPlannerData)
+                lib.rvsref_set_plan_log(log_fixture(lname, lkind, lseed).encode())
+                run_reference(lib, h, rb.num_dofs, config(lkind), qs, qg, lseed)
+                lib.rvsref_set_plan_log(None)
+                import re
+                text = open(log_fixture(lname, lkind, lseed)).read()                # the wall-clock line is the only run-dependent one
+                open(log_fixture(lname, lkind, lseed), "w").write(re.sub(r"Planning time \[s\]:    .*", "Planning time [s]:    0", text))
         lib.rvsref_destroy(h)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "plan_golden.npz"), **data)

@@ -195,6 +195,62 @@ def test_oracle_backed_planners_reproduce_the_compiled_reference_on_fresh_runs(o
         lib.rvsref_destroy(h)
 
 
+def _same_log_states(ours, theirs):
+    if len(ours) != len(theirs):
+        return False
+    for (q, par), (q_r, par_r) in zip(ours, theirs):
+        if (par is None) != (par_r is None) or not np.allclose(q, q_r, rtol=2e-5, atol=2e-6):
+            return False
+        if par is not None and not np.allclose(par, par_r, rtol=2e-5, atol=2e-6):
+            return False
+    return True
+
+
+def test_planner_log_with_trees_matches_the_reference_planners_own_log(ob, monkeypatch, tmp_path):
+    """RBTConnect / RRTConnect::outputPlannerData (RBTConnect.cpp:203-253) of the compiled reference wrote tests/golden/plan_log_*.log for
+    two golden runs; the same runs here (RVS_PLAN_RNG=libc), written by planning.write_planner_log with their trees, hold the same
+    `Tree: q_start` / `Tree: q_goal` / `Path:` blocks state by state (6 significant digits, the precision of the text)."""
+    mod, _ = _plan_golden()
+    monkeypatch.setenv("RVS_PLAN_RNG", "libc")
+    for name, kind, seed in mod.LOG_RUNS:
+        ref_text = open(mod.log_fixture(name, kind, seed)).read()
+        o, scene, qs, qg = _oracle(ob, name)
+        rb = scene[0]
+        res = ob.plan_solve_batch_trees(o, mod.config(kind), qs, qg, [seed], max_path=mod.MAX_PATH, trees=8192)[0]
+        assert res["success"] and res["tree_sizes"][0] + res["tree_sizes"][1] == res["states"]
+        f = tmp_path / f"{name}.log"
+        planning.write_planner_log(str(f), res, kind, rb.num_dofs)
+        text = f.read_text()
+        ours, ours_path = mod.parse_log(text)
+        theirs, theirs_path = mod.parse_log(ref_text)
+        assert list(ours) == list(theirs) == ["q_start", "q_goal"]
+        for t in theirs:
+            assert len(theirs[t]) > 5 and _same_log_states(ours[t], theirs[t]), (name, t)
+        assert _same_log_states(ours_path, theirs_path)
+        # everything but the space name and the wall clock is the same text up to number formatting
+        head = lambda s: [l for l in s.splitlines()[:8] if not l.startswith(("Space Type", "\t Planning time"))]
+        assert head(text) == head(ref_text)
+
+
+@pytest.mark.gpu
+def test_gpu_planner_returns_the_trees_of_a_run():
+    fn, qs, qg = SCENARIOS["xarm6"]
+    rb, mn, mx, g, tol = fn()
+    eng = engine.Engine(rb)
+    eng.set_obstacles(mn, mx, g, tol)
+    res, _ = planning.solve_batch(eng, planning.default_config(planning.RGBT_CONNECT), np.asarray(qs, np.float32), np.asarray(qg, np.float32), seeds=[3, 4], trees=4096)
+    for r in res:
+        assert r["success"] and sum(r["tree_sizes"]) == r["states"]
+        for t, root in zip(r["trees"], (qs, qg)):
+            coord, parent = t
+            assert parent[0] == -1 and (parent[1:] >= 0).all() and (parent[1:] < np.arange(1, len(parent))).all()      # parents precede children
+            assert np.allclose(coord[0], root, atol=1e-6)
+        # the path runs through states of the two trees
+        both = np.vstack([r["trees"][0][0], r["trees"][1][0]])
+        assert all((np.abs(both - p).max(axis=1) < 1e-6).any() for p in r["path"])
+    eng.close()
+
+
 @pytest.mark.gpu
 def test_gpu_backed_planners_reproduce_the_reference_planner_runs(monkeypatch):
     """The planners on the CUDA backend against the compiled reference's runs.  A device FK that differs from the host's in the last
