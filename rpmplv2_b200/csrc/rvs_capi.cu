@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 #include <string>
@@ -41,6 +42,11 @@ struct rvs_engine {
     RobotDev h_robot{};
     RobotDev *d_robot = nullptr;
     void *d_obs_pack = nullptr;               // fp16 boxes of the scan-order table, two obstacles per 32-byte record
+    // coarse distance field of the table (first thresholds of the work-queue distance kernel): built lazily, rebuilt when the table changed
+    void *d_df = nullptr;
+    bool df_dirty = true;
+    int df_on = 1;
+    float df_origin[3] = {0.f, 0.f, 0.f}, df_cell = 0.f;
     ObstacleRec *d_obs = nullptr;
     int M = 0, obs_cap = 0;
     std::vector<ObstacleRec> h_obs, h_obs_scan;
@@ -177,8 +183,10 @@ KArgs base_args(rvs_engine *h, const float *d_q, int64_t N) {
     a.num_ground = h->num_ground;
     a.pair_count = h->d_pair_count;
     a.slices = 1;
+    a.df = nullptr;                             // switched on by distance_dev_impl for the work-queue kernel
     return a;
 }
+
 
 // validity work-queue kernel: how many slices of the obstacle table per batch of `items` configurations (1 = every warp walks the
 // whole table).  Worth it when the batch alone cannot fill the GPU and the table is long.
@@ -201,6 +209,30 @@ int launched(rvs_engine *h, cudaError_t e, const char *what) {
     if (e != cudaSuccess) return cuda_fail(h, e, what);
     h->launches++;
     return RVS_OK;
+}
+
+// Distance field for the work-queue distance kernel: 64^3 cells centred on the robot base, wide enough for every point of the chain
+// (sum of the link offsets + the gripper) plus a margin.  (Re)built on the handle's stream when the table changed since the last build.
+constexpr int kDfDim = 64;
+constexpr int64_t kDfMinConfigs = 32768;        // below this the build (~0.1 ms) is not worth it
+constexpr int kDfMinObstacles = 32;
+int df_ready(rvs_engine *h) {
+    if (!h->df_dirty && h->d_df) return RVS_OK;
+    if (!h->d_df) RVS_CUDA(h, cudaMalloc(&h->d_df, size_t(kDfDim) * kDfDim * kDfDim * 2));
+    double reach = double(h->h_robot.gripper_length) + 0.3;
+    for (int i = 1; i <= h->h_robot.n; i++)
+        reach += std::sqrt(h->h_robot.xyz[i][0] * h->h_robot.xyz[i][0] + h->h_robot.xyz[i][1] * h->h_robot.xyz[i][1] + h->h_robot.xyz[i][2] * h->h_robot.xyz[i][2]);
+    h->df_cell = float(2.0 * reach / kDfDim);
+    for (int c = 0; c < 3; c++) h->df_origin[c] = float(h->h_robot.xyz[0][c] - reach);
+    RVS_TRY(launched(h, launch_df_build(h->d_obs, h->M, h->prm.max_distance, h->d_df, kDfDim, h->df_origin, h->df_cell, h->stream), "distance field build"));
+    h->df_dirty = false;
+    return RVS_OK;
+}
+void df_args(rvs_engine *h, KArgs &a) {
+    a.df = h->d_df; a.df_dim = kDfDim;
+    for (int c = 0; c < 3; c++) a.df_origin[c] = h->df_origin[c];
+    a.df_inv_cell = 1.0f / h->df_cell;
+    a.df_slack = h->df_cell * 0.8660255f * 1.0001f + 1e-6f;                 // half a cell diagonal
 }
 
 int h2d(rvs_engine *h, int which, const void *src, size_t bytes) {
@@ -228,6 +260,10 @@ int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, 
         return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer for the requested distance mode");
     KArgs a = base_args(h, d_q, N);
     a.mode = mode; a.d_c = d_dc; a.profile = d_prof; a.nearest = d_near;
+    if (h->df_on && h->cull && mode != RVS_DIST_FULL && h->M >= kDfMinObstacles && h->M < (1 << 16) && (N >= kDfMinConfigs || on)) {
+        if (!on) RVS_TRY(df_ready(h));           // (the pipelined host path builds it before it forks its streams)
+        if (h->d_df && !h->df_dirty) df_args(h, a);
+    }
     return launched(h, h->lt.distance(a, on ? on : h->stream), "distance kernel launch");
 }
 
@@ -276,6 +312,7 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     }
     if (mode >= RVS_DIST_PROFILE && !profile) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL profile buffer");
     RVS_TRY(pipeline_ready(h));
+    if (h->df_on && h->cull && h->M >= kDfMinObstacles && h->M < (1 << 16)) RVS_TRY(df_ready(h));
     RVS_CUDA(h, cudaEventRecord(h->ev_done, h->stream));                 // order the copy streams after earlier work on the handle
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_k2, h->ev_done, 0));
@@ -351,6 +388,7 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     }
     if (device < 0 || device >= count) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "device index out of range");
     rvs_engine *h = new rvs_engine();
+    if (const char *e_df = std::getenv("RVS_DISTANCE_FIELD")) h->df_on = std::atoi(e_df) ? 1 : 0;      // A/B switch (results are identical either way)
     h->device = device;
     h->prm = *params;
     int rc = build_robot(h, robot);
@@ -369,8 +407,8 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     h->own_stream = true;
     if ((e = cudaMalloc(&h->d_robot, sizeof(RobotDev))) != cudaSuccess) return bail(e, "cudaMalloc(robot)");
     if ((e = cudaMemcpy(h->d_robot, &h->h_robot, sizeof(RobotDev), cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(robot)");
-    if ((e = cudaMalloc(&h->d_pair_count, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
-    if ((e = cudaMemset(h->d_pair_count, 0, 4 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
+    if ((e = cudaMalloc(&h->d_pair_count, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc(pair counter)");
+    if ((e = cudaMemset(h->d_pair_count, 0, 8 * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMemset(pair counter)");
     void *arena = nullptr;
     if (cudaHostAlloc(&arena, kArenaBytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) h->arena = static_cast<char *>(arena);
     else cudaGetLastError();                 // no pinned memory to spare: small calls simply take the DMA path
@@ -386,6 +424,7 @@ int rvs_destroy(rvs_handle h) {
     if (h->arena) cudaFreeHost(h->arena);
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_obs_pack) cudaFree(h->d_obs_pack);
+    if (h->d_df) cudaFree(h->d_df);
     for (auto &t : h->trees) if (t.d) cudaFree(t.d);
     if (h->d_tree_ptr) cudaFree(h->d_tree_ptr);
     if (h->d_tree_cnt) cudaFree(h->d_tree_cnt);
@@ -484,7 +523,7 @@ int rvs_pair_count(rvs_handle h, int32_t reset, uint64_t *out) {
     unsigned long long v = 0;
     RVS_CUDA(h, cudaMemcpy(&v, h->d_pair_count, sizeof(v), cudaMemcpyDeviceToHost));
     if (out) *out = uint64_t(v);
-    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, 4 * sizeof(v)));
+    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, 8 * sizeof(v)));
     return RVS_OK;
 }
 
@@ -494,7 +533,22 @@ int rvs_work_stats(rvs_handle h, int32_t reset, uint64_t *out4) {
     unsigned long long v[4] = {0, 0, 0, 0};
     RVS_CUDA(h, cudaMemcpy(v, h->d_pair_count, sizeof(v), cudaMemcpyDeviceToHost));
     if (out4) for (int k = 0; k < 4; k++) out4[k] = uint64_t(v[k]);
-    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, sizeof(v)));
+    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count, 0, 8 * sizeof(unsigned long long)));
+    return RVS_OK;
+}
+
+int rvs_set_distance_field(rvs_handle h, int32_t on) {
+    if (!h) return RVS_ERR_INVALID_ARGUMENT;
+    h->df_on = on ? 1 : 0;
+    return RVS_OK;
+}
+int rvs_second_pass_warps(rvs_handle h, int32_t reset, uint64_t *out) {
+    RVS_TRY(enter(h));
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    unsigned long long v = 0;
+    RVS_CUDA(h, cudaMemcpy(&v, h->d_pair_count + 4, sizeof(v), cudaMemcpyDeviceToHost));
+    if (out) *out = uint64_t(v);
+    if (reset) RVS_CUDA(h, cudaMemset(h->d_pair_count + 4, 0, sizeof(v)));
     return RVS_OK;
 }
 
@@ -535,6 +589,7 @@ int upload_obstacles(rvs_engine *h) {
     RVS_CUDA(h, cudaMemcpyAsync(h->d_obs + 2 * size_t(h->obs_cap), h->h_scan_dist.data(), size_t(M) * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     RVS_CUDA(h, launch_pack_scan(h->d_obs + h->obs_cap, M, h->d_obs_pack, h->stream));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->df_dirty = true;
     return RVS_OK;
 }
 }  // namespace
@@ -1120,6 +1175,7 @@ int rvs_env_step(rvs_handle h, float delta_time, int32_t steps) {
     EnvArgs a = env_args(h, steps, delta_time);
     RVS_TRY(launched(h, launch_env_advance(a, h->stream), "environment advance launch"));
     RVS_TRY(launched(h, launch_env_commit(a, h->stream), "environment commit launch"));
+    h->df_dirty = true;
     h->launches++;                                                          // commit = two grids
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
     return RVS_OK;
@@ -1170,6 +1226,7 @@ static int motion_validity_impl(rvs_handle h, const float *q_prev, const float *
     RVS_TRY(launched(h, h->lt.motion_valid(a, h->stream), "motion validity launch"));
     if (commit_edge >= 0 && h->M > 0) {
         RVS_TRY(launched(h, launch_env_commit(a, h->stream), "environment commit launch"));
+    h->df_dirty = true;
         h->launches++;
     }
     std::vector<int32_t> fi(static_cast<size_t>(E), 0);

@@ -17,6 +17,10 @@
 //                      The link of the current first collision only searches for EARLIER collisions (threshold =
 //                      radius): its minimum is not an output, and without this a colliding configuration would push
 //                      every obstacle of that link through the queues.
+//   phase 0  bootstrap the running minimum of every link starts at an UPPER BOUND read from a coarse distance field of the obstacle table
+//                      (df_build_kernel: 64^3 cells around the robot, fp16, distance from the cell centre to the nearest obstacle,
+//                      rounded up): min over three points of the link axis of (field + half a cell diagonal) - radius.  Without it the
+//                      first thresholds are infinite and the first obstacles of the table go through the narrow phase for every link.
 //   phase A' unpack    Q0 >= 32: every lane turns one hit word into pair entries of Q1 (warp prefix sum).
 //   phase B1 re-cull   Q1 >= 32: every lane pops ONE pair (of any configuration of the warp) and re-tests it with the
 //                      Euclidean box gap against the now tighter minimum; survivors are ballot-compacted into Q1b.
@@ -36,6 +40,11 @@
 //     inequality dist(x, box) >= dist(base, box) - |x - base| with dist(base, box) rounded DOWN on the host;
 //   * min(c_k) - r == min(c_k - r) and the min_dist_tol filter d > tol is monotone, so candidates can be merged one
 //     by one instead of per pair;
+//   * the bootstrap bound is only a THRESHOLD: it is >= the exact distance to the obstacle that defines it (a point of the axis against
+//     that box), so that obstacle survives every cull and its candidate replaces the bound.  Should the reference's routine return MORE
+//     than the geometric distance for it (its case tree has slips) and nothing else come below the bound, the minimum still
+//     equals the bound at the end: such a link is re-scanned without bounds (second pass of the scan loop), so outputs never depend on
+//     the field.  Obstacles with a min_dist_tol or the ground label are left out of the field (they do not count for every link);
 //   * first-collision semantics (RealVectorSpace.cpp:370-378) are order dependent in the reference: we keep the
 //     minimum of key = link * M + obstacle over ALL colliding pairs (links below the current hit are never
 //     dropped), then replay exactly that one pair sequentially to obtain the value the reference stores in
@@ -203,7 +212,48 @@ __device__ __forceinline__ unsigned wq_dup_up(float x) { const __half v = __floa
 __device__ __forceinline__ unsigned wq_le2(unsigned a, unsigned b) { return __hle2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b)); }
 __device__ __forceinline__ unsigned wq_ge2(unsigned a, unsigned b) { return __hge2_mask(*reinterpret_cast<const __half2 *>(&a), *reinterpret_cast<const __half2 *>(&b)); }
 
+// ---- coarse distance field (phase 0) ---------------------------------------------------------------------------------------------------
+// upper bound of dist(p, nearest eligible obstacle): field value of p's cell + half a cell diagonal; +inf outside the grid
+__device__ __forceinline__ float wq_df_point(const KArgs &a, float x, float y, float z) {
+    const float fx = (x - a.df_origin[0]) * a.df_inv_cell, fy = (y - a.df_origin[1]) * a.df_inv_cell, fz = (z - a.df_origin[2]) * a.df_inv_cell;
+    const float lim = float(a.df_dim);
+    if (!(fx >= 0.f && fx < lim && fy >= 0.f && fy < lim && fz >= 0.f && fz < lim)) return __int_as_float(0x7f800000);
+    const int idx = (int(fz) * a.df_dim + int(fy)) * a.df_dim + int(fx);
+    return __half2float(__ldg(static_cast<const __half *>(a.df) + idx)) + a.df_slack;
+}
+// bound for the capsule (A, B, radius): a value >= the exact distance of the link to the obstacle that defines it, widened so that it
+// stays above that distance through the roundings of the narrow phase
+template <class R>
+__device__ __forceinline__ R wq_df_bound(const KArgs &a, R ax, R ay, R az, R bx, R by, R bz, R radius, R max_dist) {
+    const float x0 = float(ax), y0 = float(ay), z0 = float(az), x1 = float(bx), y1 = float(by), z1 = float(bz);
+    float u = wq_df_point(a, x0, y0, z0);
+    u = fminf(u, wq_df_point(a, x1, y1, z1));
+    u = fminf(u, wq_df_point(a, 0.5f * (x0 + x1), 0.5f * (y0 + y1), 0.5f * (z0 + z1)));
+    const float b = fmaxf(u - float(radius), 0.f) * 1.001f + 1e-4f;
+    return b < float(max_dist) ? R(b) : max_dist;
+}
+
 #ifdef RVS_VARIANT_EXACT
+// one thread per cell: distance from the cell centre to the nearest obstacle that counts for EVERY link of every configuration (no
+// ground label, no min_dist_tol below MAX_DISTANCE), rounded up to fp16
+__global__ void __launch_bounds__(128) df_build_kernel(const ObstacleRec *__restrict__ obs, int M, float max_dist, __half *__restrict__ df, int dim,
+                                                       float ox, float oy, float oz, float cell) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= dim * dim * dim) return;
+    const int ix = idx % dim, iy = (idx / dim) % dim, iz = idx / (dim * dim);
+    const float cx = ox + (float(ix) + 0.5f) * cell, cy = oy + (float(iy) + 0.5f) * cell, cz = oz + (float(iz) + 0.5f) * cell;
+    float best = __int_as_float(0x7f800000);
+#pragma unroll 4
+    for (int j = 0; j < M; j++) {
+        const float4 w0 = __ldg(reinterpret_cast<const float4 *>(obs + j)), w1 = __ldg(reinterpret_cast<const float4 *>(obs + j) + 1);
+        if ((__float_as_uint(w1.w) & 1u) || !(w1.z >= max_dist)) continue;
+        const float gx = fmaxf(fmaxf(w0.x - cx, cx - w0.w), 0.f), gy = fmaxf(fmaxf(w0.y - cy, cy - w1.x), 0.f), gz = fmaxf(fmaxf(w0.z - cz, cz - w1.y), 0.f);
+        const float d2 = gx * gx + gy * gy + gz * gz;
+        best = fminf(best, d2);
+    }
+    df[idx] = __float2half_ru(sqrtf(best) * 1.00001f + 1e-6f);
+}
+
 // one thread per obstacle pair: scan-ordered ObstacleRec table -> packed half2 table (launched after every upload / re-ranking of the table)
 __global__ void __launch_bounds__(128) pack_scan_kernel(const ObstacleRec *__restrict__ scan, int M, uint4 *__restrict__ pack) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,13 +463,26 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
             prev = nrm;
         }
     }
-    for (int i = 0; i < L; i++) c.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist);
+    // phase 0: every link's running minimum starts at the distance-field bound (an upper bound of the answer), or at MAX_DISTANCE
+    for (int i = 0; i < L; i++) {
+        R b0 = c.max_dist;
+        if (a.df && live) {
+            const R *sk = c.skel + (3 * i) * kWqStride + t;
+            b0 = wq_df_bound<R>(a, sk[0], sk[kWqStride], sk[2 * kWqStride], sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride], RobotScalars<R>::radius(rb, i), c.max_dist);
+        }
+        c.best[i * kWqStride + t] = WqBits<R>::to(b0);
+    }
     c.hit[t] = kNoHit;
     if (t < L) c.radius[t] = RobotScalars<R>::radius(rb, t);
     if (lane < 8) c.tails[lane] = 0;
     const int ground_included = rb->ground_included;
     __syncthreads();                                                       // radius[] is shared by the block; everything else is per warp
 
+    // pass 0 scans with the bootstrap bounds in place; pass 1 (normally never entered) re-scans the links whose minimum still EQUALS its
+    // bound, i.e. for which no candidate came below it, without bounds — see "Exactness" in the header
+    bool scanning = live;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
     for (int base = 0; base < a.M; base += kWqSegment) {
         const int count = min(kWqSegment, a.M - base);
         c.seg_base = base;
@@ -437,7 +500,7 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
                 // obstacle j0 nor any later one can lower its minimum.  Links at or above a known collision are dead as well.
                 const unsigned hk = c.hit[t];
                 const int hit_link = hk == kNoHit ? -1 : int(hk / unsigned(a.M));
-                const int limit = !live ? 0 : (hk == kNoHit ? L : hit_link + 1);
+                const int limit = !scanning ? 0 : (hk == kNoHit ? L : hit_link + 1);
                 const R dnext = R(__ldg(sd + j0));
                 unsigned mine = 0;
 #pragma unroll
@@ -568,6 +631,22 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
         }
     }
     __syncwarp();
+    if (pass == 1 || !a.df) break;
+    bool redo = false;
+    if (live) {
+        const unsigned hk0 = c.hit[t];
+        const int outputs = hk0 == kNoHit ? L : int(hk0 / unsigned(a.M));     // links below the first collision: their minima are outputs
+        for (int i = 0; i < outputs; i++) {
+            const R *sk = c.skel + (3 * i) * kWqStride + t;
+            const R b0 = wq_df_bound<R>(a, sk[0], sk[kWqStride], sk[2 * kWqStride], sk[3 * kWqStride], sk[4 * kWqStride], sk[5 * kWqStride], RobotScalars<R>::radius(rb, i), c.max_dist);
+            if (b0 < c.max_dist && WqBits<R>::from(c.best[i * kWqStride + t]) == b0) { c.best[i * kWqStride + t] = WqBits<R>::to(c.max_dist); redo = true; }
+        }
+    }
+    if (!__any_sync(0xffffffffu, redo)) break;
+    if (a.pair_count && lane == 0) atomicAdd(a.pair_count + 4, 1ull);            // (work statistics: warps that took the second pass)
+    scanning = redo;
+    __syncwarp();
+    }
 
     // ---- per-configuration epilogue (lane = configuration again) ---------------------------------------------------
     const unsigned hk = c.hit[t];

@@ -82,6 +82,12 @@ struct KArgs {
     int32_t robot_n_hint;    // num_dofs as known by the host (grid sizing)
     int32_t num_ground;      // obstacles flagged ground
     unsigned long long *pair_count;   // += pair queries the reference's loop would have visited (early exit respected)
+    // coarse distance field of the obstacle table (rvs_distance_wq.cuh: df_build_kernel): upper bounds for the first thresholds; nullptr = off
+    const void *df;          // [df_dim^3] __half, distance from the cell centre to the nearest eligible obstacle, rounded up
+    float df_origin[3];      // lower corner of the grid
+    float df_inv_cell;       // cells per metre
+    float df_slack;          // half a cell diagonal (+ rounding): |p - centre| for any p of the cell
+    int32_t df_dim;
 };
 
 // Arguments of the batched generalized-bur spine kernel (rvs_extend_spines).

@@ -202,6 +202,10 @@ cudaError_t launch_nn_radius(const NnArgs &a, cudaStream_t st) {
     nn_radius_kernel<<<1, kNnBlock, 0, st>>>(a);
     return cudaGetLastError();
 }
+cudaError_t launch_df_build(const ObstacleRec *obs, int M, float max_dist, void *df, int dim, const float *origin, float cell, cudaStream_t st) {
+    df_build_kernel<<<grid_for(int64_t(dim) * dim * dim, 128), 128, 0, st>>>(obs, M, max_dist, static_cast<__half *>(df), dim, origin[0], origin[1], origin[2], cell);
+    return cudaGetLastError();
+}
 cudaError_t launch_pack_scan(const ObstacleRec *scan, int M, void *pack, cudaStream_t st) {
     if (M <= 0) return cudaSuccess;
     pack_scan_kernel<<<grid_for((M + 1) / 2, 128), 128, 0, st>>>(scan, M, static_cast<uint4 *>(pack));

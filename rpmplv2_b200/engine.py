@@ -96,6 +96,8 @@ SYMBOLS = {
     "rvs_underestimation_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rvs_generate_configs_dev": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "rvs_set_distance_field": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_second_pass_warps": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]),
     "rvs_set_culling": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_env_set": (ctypes.c_int, [_H, ctypes.POINTER(RvsEnvParams), c_f32p, c_f32p, c_u8p, c_f32p, c_f32p, c_u8p, c_u8p, c_f32p, ctypes.c_int32]),
     "rvs_env_set_random_directions": (ctypes.c_int, [_H, c_f32p, ctypes.c_int32, ctypes.c_int64]),
@@ -214,6 +216,15 @@ class Engine:
 
     def set_culling(self, on: bool):
         self._check(self._lib.rvs_set_culling(self._h, 1 if on else 0))
+
+    def set_distance_field(self, on: bool):
+        """Bootstrap thresholds of large distance batches from a coarse distance field (results identical on / off)."""
+        self._check(self._lib.rvs_set_distance_field(self._h, 1 if on else 0))
+
+    def second_pass_warps(self, reset: bool = False) -> int:
+        out = ctypes.c_uint64(0)
+        self._check(self._lib.rvs_second_pass_warps(self._h, 1 if reset else 0, ctypes.byref(out)))
+        return int(out.value)
 
     def set_params(self, params: RvsParams):
         self._check(self._lib.rvs_set_params(self._h, ctypes.byref(params)))
