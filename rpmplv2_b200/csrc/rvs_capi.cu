@@ -13,6 +13,7 @@
 
 #include "rvs_launch.h"
 #include "rvs_robot_host.h"
+#include "rvs_sort.cuh"
 #include "rvs_types.h"
 
 using namespace rvs;
@@ -46,6 +47,11 @@ struct rvs_engine {
     void *d_df = nullptr;
     bool df_dirty = true;
     int df_on = 1;
+    // permutation that makes the warps of a large distance batch geometrically coherent (rvs_sort.cuh)
+    int sort_on = 1;
+    int32_t *d_perm = nullptr;
+    size_t perm_cap = 0;
+    uint32_t *d_hist[2] = {nullptr, nullptr};    // one per compute stream of the pipelined host path
     float df_origin[3] = {0.f, 0.f, 0.f}, df_cell = 0.f;
     ObstacleRec *d_obs = nullptr;
     int M = 0, obs_cap = 0;
@@ -235,6 +241,40 @@ void df_args(rvs_engine *h, KArgs &a) {
     a.df_slack = h->df_cell * 0.8660255f * 1.0001f + 1e-6f;                 // half a cell diagonal
 }
 
+// Coherent warps for the work-queue distance kernel: counting sort of the batch d_q[0, N) on its leading joints, written to
+// d_perm[perm_offset, perm_offset + N) (as indices relative to d_q) on stream `st`.
+constexpr int64_t kSortMinConfigs = 65536;
+constexpr int kSortMaxBits = 18;
+int sort_ready(rvs_engine *h, size_t total) {
+    if (total > h->perm_cap) {
+        if (h->d_perm) RVS_CUDA(h, cudaFree(h->d_perm));
+        h->d_perm = nullptr; h->perm_cap = 0;
+        RVS_CUDA(h, cudaMalloc(&h->d_perm, total * sizeof(int32_t)));
+        h->perm_cap = total;
+    }
+    for (auto &p : h->d_hist)
+        if (!p) RVS_CUDA(h, cudaMalloc(&p, (size_t(1) << kSortMaxBits) * sizeof(uint32_t)));
+    return RVS_OK;
+}
+int sort_configs(rvs_engine *h, const float *d_q, int64_t N, int64_t perm_offset, int which, cudaStream_t st) {
+    SortArgs a{};
+    a.q = d_q; a.N = N; a.n = h->h_robot.n; a.joints = std::min(3, h->h_robot.n);
+    int total = 0;
+    while (total < kSortMaxBits && (int64_t(48) << (total + 1)) <= N) total++;           // ~48 configurations per bin or more
+    for (int j = 0; j < 3; j++) a.bits[j] = 0;
+    for (int b = 0; b < total; b++) a.bits[b % a.joints]++;
+    for (int j = 0; j < a.joints; j++) {
+        a.lo[j] = h->h_robot.limit_lo[j];
+        const float span = h->h_robot.limit_hi[j] - h->h_robot.limit_lo[j];
+        a.inv[j] = span > 0.f ? 1.0f / span : 0.f;
+    }
+    a.nbins = 1 << total; a.hist = h->d_hist[which]; a.perm = h->d_perm + perm_offset;
+    RVS_CUDA(h, cudaMemsetAsync(a.hist, 0, size_t(a.nbins) * sizeof(uint32_t), st));
+    RVS_TRY(launched(h, launch_sort_configs(a, st), "configuration sort"));
+    h->launches += 2;                                                                     // three grids
+    return RVS_OK;
+}
+
 int h2d(rvs_engine *h, int which, const void *src, size_t bytes) {
     RVS_TRY(reserve(h, which, bytes));
     if (!bytes) return RVS_OK;
@@ -251,7 +291,7 @@ int d2h_from(rvs_engine *h, void *dst, const void *src, size_t bytes) {
 int d2h(rvs_engine *h, void *dst, int which, size_t bytes) { return d2h_from(h, dst, h->buf[which].p, bytes); }
 
 int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, void *d_dc, void *d_prof, void *d_near, bool want_f64,
-                      cudaStream_t on = nullptr) {
+                      cudaStream_t on = nullptr, int64_t perm_offset = 0, int which = 0) {
     if ((h->prm.precision == RVS_PREC_F64) != want_f64)
         return fail(h, RVS_ERR_INVALID_ARGUMENT, want_f64 ? "handle was not created with RVS_PREC_F64" : "RVS_PREC_F64 handles use the *_f64 entry points");
     if (N < 0 || mode < RVS_DIST_MIN || mode > RVS_DIST_FULL) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad N or mode");
@@ -263,6 +303,11 @@ int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, 
     if (h->df_on && h->cull && mode != RVS_DIST_FULL && h->M >= kDfMinObstacles && h->M < (1 << 16) && (N >= kDfMinConfigs || on)) {
         if (!on) RVS_TRY(df_ready(h));           // (the pipelined host path builds it before it forks its streams)
         if (h->d_df && !h->df_dirty) df_args(h, a);
+    }
+    if (h->sort_on && h->cull && mode != RVS_DIST_FULL && h->M > 0 && N >= kSortMinConfigs && N < (int64_t(1) << 31)) {
+        if (!on) RVS_TRY(sort_ready(h, size_t(N)));   // (the pipelined host path sizes the buffers before it forks its streams)
+        RVS_TRY(sort_configs(h, d_q, N, perm_offset, which, on ? on : h->stream));
+        a.perm = h->d_perm + perm_offset;
     }
     return launched(h, h->lt.distance(a, on ? on : h->stream), "distance kernel launch");
 }
@@ -313,6 +358,7 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     if (mode >= RVS_DIST_PROFILE && !profile) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL profile buffer");
     RVS_TRY(pipeline_ready(h));
     if (h->df_on && h->cull && h->M >= kDfMinObstacles && h->M < (1 << 16)) RVS_TRY(df_ready(h));
+    if (h->sort_on && h->cull && h->M > 0) RVS_TRY(sort_ready(h, size_t(N)));
     RVS_CUDA(h, cudaEventRecord(h->ev_done, h->stream));                 // order the copy streams after earlier work on the handle
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_k2, h->ev_done, 0));
@@ -324,7 +370,7 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
         RVS_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
         cudaStream_t sk = (c & 1) ? h->s_k2 : h->stream;
         RVS_CUDA(h, cudaStreamWaitEvent(sk, h->ev_in[c], 0));
-        RVS_TRY(distance_dev_impl(h, dq + first * n, cnt, mode, ddc + first * rs, dprof + first * L * rs, nullptr, want_f64, sk));
+        RVS_TRY(distance_dev_impl(h, dq + first * n, cnt, mode, ddc + first * rs, dprof + first * L * rs, nullptr, want_f64, sk, first, c & 1));
         RVS_CUDA(h, cudaEventRecord(h->ev_k[c], sk));
         RVS_CUDA(h, cudaStreamWaitEvent(h->s_out, h->ev_k[c], 0));
         RVS_CUDA(h, cudaMemcpyAsync(static_cast<char *>(d_c) + first * rs, ddc + first * rs, size_t(cnt) * rs, cudaMemcpyDeviceToHost, h->s_out));
@@ -388,6 +434,7 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     }
     if (device < 0 || device >= count) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "device index out of range");
     rvs_engine *h = new rvs_engine();
+    if (const char *e_so = std::getenv("RVS_SORT_CONFIGS")) h->sort_on = std::atoi(e_so) ? 1 : 0;
     if (const char *e_df = std::getenv("RVS_DISTANCE_FIELD")) h->df_on = std::atoi(e_df) ? 1 : 0;      // A/B switch (results are identical either way)
     h->device = device;
     h->prm = *params;
@@ -425,6 +472,8 @@ int rvs_destroy(rvs_handle h) {
     if (h->d_obs) cudaFree(h->d_obs);
     if (h->d_obs_pack) cudaFree(h->d_obs_pack);
     if (h->d_df) cudaFree(h->d_df);
+    if (h->d_perm) cudaFree(h->d_perm);
+    for (auto *p : h->d_hist) if (p) cudaFree(p);
     for (auto &t : h->trees) if (t.d) cudaFree(t.d);
     if (h->d_tree_ptr) cudaFree(h->d_tree_ptr);
     if (h->d_tree_cnt) cudaFree(h->d_tree_cnt);

@@ -446,8 +446,9 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
 
     WqCtx<R> c = wq_make_ctx<R, G>(wq_smem, reinterpret_cast<const float4 *>(a.obstacles_scan), L, a.M, 0, R(a.eq_thr), R(a.max_dist));
 
-    const int64_t cfg = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
-    const bool live = cfg < a.N;
+    const int64_t slot_k = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
+    const bool live = slot_k < a.N;
+    const int64_t cfg = live && a.perm ? int64_t(__ldg(a.perm + slot_k)) : slot_k;     // coherent warps: see rvs_sort.cuh
     const int t = threadIdx.x;
     if (live) fk_skeleton<F, R>(rb, a.q + cfg * L, c.skel + t, kWqStride);
     else for (int k = 0; k < 3 * (L + 1); k++) c.skel[k * kWqStride + t] = R(0);

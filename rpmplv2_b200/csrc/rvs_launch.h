@@ -32,6 +32,8 @@ cudaError_t launch_env_advance(const EnvArgs &a, cudaStream_t st);          // K
 cudaError_t launch_env_commit(const EnvArgs &a, cudaStream_t st);           // adopt timeline[kc], rewrite both copies of the obstacle table
 cudaError_t launch_nn_nearest(const NnArgs &a, cudaStream_t st);
 cudaError_t launch_nn_radius(const NnArgs &a, cudaStream_t st);
+struct SortArgs;
+cudaError_t launch_sort_configs(const SortArgs &a, cudaStream_t st);   // histogram (zeroed by the caller) -> scan -> scatter: a.perm
 cudaError_t launch_df_build(const ObstacleRec *obs, int M, float max_dist, void *df, int dim, const float *origin, float cell, cudaStream_t st);   // coarse distance field
 cudaError_t launch_pack_scan(const ObstacleRec *scan, int M, void *pack, cudaStream_t st);   // fp16 copy of the scan-order obstacle table
 cudaError_t launch_fma_peak(int fp64, void *sink, int blocks, int iters, cudaStream_t st);

@@ -8,6 +8,7 @@
 #include "rvs_store.cuh"
 #include "rvs_env.cuh"
 #include "rvs_nn.cuh"
+#include "rvs_sort.cuh"
 #include "rvs_launch.h"
 
 #include <map>
@@ -200,6 +201,13 @@ cudaError_t launch_nn_nearest(const NnArgs &a, cudaStream_t st) {
 }
 cudaError_t launch_nn_radius(const NnArgs &a, cudaStream_t st) {
     nn_radius_kernel<<<1, kNnBlock, 0, st>>>(a);
+    return cudaGetLastError();
+}
+cudaError_t launch_sort_configs(const SortArgs &a, cudaStream_t st) {
+    if (a.N <= 0) return cudaSuccess;
+    sort_hist_kernel<<<grid_for(a.N, 256), 256, 0, st>>>(a);
+    sort_scan_kernel<<<1, 1024, 0, st>>>(a);
+    sort_scatter_kernel<<<grid_for(a.N, 256), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 cudaError_t launch_df_build(const ObstacleRec *obs, int M, float max_dist, void *df, int dim, const float *origin, float cell, cudaStream_t st) {
