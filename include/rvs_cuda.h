@@ -356,6 +356,10 @@ int  rvs_set_culling(rvs_handle h, int32_t cull);
  * for which no candidate came below its bound is re-scanned without bounds, so results are identical with the switch on or off.
  * rvs_second_pass_warps: how many warps (of 32 configurations) needed that second pass since the last reset. */
 int  rvs_set_distance_field(rvs_handle h, int32_t on);
+/* on != 0 (default): batches of >= 65536 configurations (distance MIN / PROFILE, isValid, edges) are processed in an order that puts
+ * similar configurations into the same warp (a counting sort on the leading joints, on the device; results are written back in the
+ * caller's order).  Per-configuration results do not depend on it. */
+int  rvs_set_config_sort(rvs_handle h, int32_t on);
 int  rvs_second_pass_warps(rvs_handle h, int32_t reset, uint64_t *out);
 
 #ifdef __cplusplus

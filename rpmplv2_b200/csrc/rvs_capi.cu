@@ -275,6 +275,15 @@ int sort_configs(rvs_engine *h, const float *d_q, int64_t N, int64_t perm_offset
     return RVS_OK;
 }
 
+// large validity batches take the work-queue kernel too: same permutation (edges are ordered by their first end)
+int sort_for_validity(rvs_engine *h, KArgs &a, int64_t N) {
+    if (!h->sort_on || !h->cull || h->M <= 0 || h->M >= (1 << 22) || N < kSortMinConfigs || N >= (int64_t(1) << 31)) return RVS_OK;
+    RVS_TRY(sort_ready(h, size_t(N)));
+    RVS_TRY(sort_configs(h, a.q, N, 0, 0, h->stream));
+    a.perm = h->d_perm;
+    return RVS_OK;
+}
+
 int h2d(rvs_engine *h, int which, const void *src, size_t bytes) {
     RVS_TRY(reserve(h, which, bytes));
     if (!bytes) return RVS_OK;
@@ -402,6 +411,7 @@ int run_simple(rvs_engine *h, const float *q, int64_t N, LaunchFn fn, void *out,
             else RVS_CUDA(h, cudaMemsetAsync(h->buf[which].p, 1, out_bytes, h->stream));
         }
     }
+    if (verdict_out && fn == h->lt.is_valid) RVS_TRY(sort_for_validity(h, a, N));
     RVS_TRY(launched(h, fn(a, h->stream), what));
     RVS_TRY(d2h(h, out, which, out_bytes));
     return finish(h);
@@ -591,6 +601,11 @@ int rvs_set_distance_field(rvs_handle h, int32_t on) {
     h->df_on = on ? 1 : 0;
     return RVS_OK;
 }
+int rvs_set_config_sort(rvs_handle h, int32_t on) {
+    if (!h) return RVS_ERR_INVALID_ARGUMENT;
+    h->sort_on = on ? 1 : 0;
+    return RVS_OK;
+}
 int rvs_second_pass_warps(rvs_handle h, int32_t reset, uint64_t *out) {
     RVS_TRY(enter(h));
     RVS_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -707,6 +722,7 @@ int rvs_is_valid_dev(rvs_handle h, const float *d_q, int64_t N, uint8_t *d_valid
         if (h->zc) std::memset(d_valid, 1, size_t(N));
         else RVS_CUDA(h, cudaMemsetAsync(d_valid, 1, size_t(N), h->stream));
     }
+    RVS_TRY(sort_for_validity(h, a, N));
     return launched(h, h->lt.is_valid(a, h->stream), "is_valid kernel launch");
 }
 int rvs_is_valid_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_valid) {
@@ -725,6 +741,7 @@ int edges_dev_impl(rvs_engine *h, const float *d_q1, const float *d_q2, int64_t 
     KArgs a = base_args(h, d_q1, E);
     a.q2 = d_q2; a.verdict = d_valid;
     a.slices = valid_slices(h, E * int64_t(h->prm.num_interpolation_validity_checks));
+    RVS_TRY(sort_for_validity(h, a, E));
     return launched(h, h->lt.edge_valid(a, h->stream), "edge kernel launch");
 }
 int underestimation_dev_impl(rvs_engine *h, const float *d_q, int64_t N, const float *d_planes, const int32_t *d_plane_idx, int32_t R,

@@ -42,22 +42,38 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(const SortArgs a) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < a.N) atomicAdd(a.hist + sort_key(a, i), 1u);
 }
-// exclusive scan of the histogram by ONE block of 1024 threads (<= 2^18 bins: 256 per thread)
+// exclusive scan of the histogram by ONE block of 1024 threads (<= 2^18 bins): every thread owns a contiguous run of bins and walks it
+// with 16-byte loads; the 1024 partial sums are scanned by warp shuffles
 __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortArgs a) {
-    __shared__ uint32_t part[1024];
-    const int per = (a.nbins + 1023) / 1024, b0 = threadIdx.x * per, b1 = min(b0 + per, a.nbins);
+    __shared__ uint32_t warp_sum[32];
+    const int per = ((a.nbins + 1023) / 1024 + 3) & ~3, b0 = threadIdx.x * per, b1 = min(b0 + per, a.nbins);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t sum = 0;
-    for (int b = b0; b < b1; b++) sum += a.hist[b];
-    part[threadIdx.x] = sum;
+    if (a.nbins >= 4096) {
+        for (int b = b0; b < b1; b += 4) { const uint4 v = *reinterpret_cast<const uint4 *>(a.hist + b); sum += v.x + v.y + v.z + v.w; }
+    } else
+        for (int b = b0; b < b1; b++) sum += a.hist[b];
+    uint32_t incl = sum;
+    for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+    if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    for (int off = 1; off < 1024; off <<= 1) {
-        const uint32_t v = threadIdx.x >= off ? part[threadIdx.x - off] : 0u;
-        __syncthreads();
-        part[threadIdx.x] += v;
-        __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_sum[lane];
+        for (int off = 1; off < 32; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+        warp_sum[lane] = w;
     }
-    uint32_t run = part[threadIdx.x] - sum;
-    for (int b = b0; b < b1; b++) { const uint32_t c = a.hist[b]; a.hist[b] = run; run += c; }
+    __syncthreads();
+    uint32_t run = incl - sum + (warp > 0 ? warp_sum[warp - 1] : 0u);
+    if (a.nbins >= 4096) {
+        for (int b = b0; b < b1; b += 4) {
+            uint4 v = *reinterpret_cast<const uint4 *>(a.hist + b);
+            const uint32_t c0 = v.x, c1 = v.y, c2 = v.z, c3 = v.w;
+            v.x = run; v.y = run + c0; v.z = v.y + c1; v.w = v.z + c2;
+            run = v.w + c3;
+            *reinterpret_cast<uint4 *>(a.hist + b) = v;
+        }
+    } else
+        for (int b = b0; b < b1; b++) { const uint32_t c = a.hist[b]; a.hist[b] = run; run += c; }
 }
 __global__ void __launch_bounds__(256) sort_scatter_kernel(const SortArgs a) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;

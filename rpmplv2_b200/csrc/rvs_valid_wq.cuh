@@ -49,16 +49,19 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_ker
     const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
     int seg_base = 0;
 
-    const int64_t item = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
-    int64_t edge = 0;
+    // a.perm (rvs_sort.cuh): thread k works on configuration / edge perm[k], so that the configurations of a warp are alike
+    const int64_t slot_k = int64_t(blockIdx.x) * kWqBlock + threadIdx.x;
+    int64_t item = slot_k, edge = 0;
     bool live;
     if (!EDGE) {
-        live = item < a.N;
+        live = slot_k < a.N;
+        if (live && a.perm) item = int64_t(__ldg(a.perm + slot_k));
         if (live) fk_skeleton<F, R>(rb, a.q + item * n, skel + t, kWqStride);
     } else {
-        edge = item / a.num_checks;
-        const int kidx = int(item - edge * a.num_checks);
+        edge = slot_k / a.num_checks;
+        const int kidx = int(slot_k - edge * a.num_checks);
         live = edge < a.N;
+        if (live && a.perm) edge = int64_t(__ldg(a.perm + edge));
         if (live) {
             const float *q1p = a.q + edge * n, *q2p = a.q2 + edge * n;
             const float dist = coord_norm(q1p, q2p, n);

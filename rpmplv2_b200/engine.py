@@ -96,6 +96,7 @@ SYMBOLS = {
     "rvs_underestimation_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
                                                ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
     "rvs_generate_configs_dev": (ctypes.c_int, [_H, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p]),
+    "rvs_set_config_sort": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_set_distance_field": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_second_pass_warps": (ctypes.c_int, [_H, ctypes.c_int32, ctypes.POINTER(ctypes.c_uint64)]),
     "rvs_set_culling": (ctypes.c_int, [_H, ctypes.c_int32]),
@@ -220,6 +221,10 @@ class Engine:
     def set_distance_field(self, on: bool):
         """Bootstrap thresholds of large distance batches from a coarse distance field (results identical on / off)."""
         self._check(self._lib.rvs_set_distance_field(self._h, 1 if on else 0))
+
+    def set_config_sort(self, on: bool):
+        """Coherent-warp ordering of large batches (results identical on / off)."""
+        self._check(self._lib.rvs_set_config_sort(self._h, 1 if on else 0))
 
     def second_pass_warps(self, reset: bool = False) -> int:
         out = ctypes.c_uint64(0)

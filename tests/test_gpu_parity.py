@@ -367,6 +367,45 @@ def test_device_pointer_api_and_generator(ob):
     assert (d_val.cpu().numpy() == o.is_valid(q, threads=8)).all()
 
 
+@pytest.mark.parametrize("robot,M,dist,r_min", [("xarm6", 1000, "D2", 0.9), ("xarm6", 300, "D1", 0.0), ("spatial10", 120, "D2", 0.3), ("planar2", 40, "D2", 0.0)])
+def test_large_batch_switches_do_not_change_any_result(ob, robot, M, dist, r_min):
+    """The two result-neutral devices of the large-batch path — thresholds bootstrapped from the coarse distance field
+    (rvs_set_distance_field) and the coherent-warp ordering of the batch (rvs_set_config_sort) — against the same kernels with both
+    switched off, bit for bit, and against the oracle on a sample: distances (MIN / PROFILE), isValid and edge validity."""
+    rb = {"xarm6": robots.xarm6, "spatial10": lambda: robots.spatial(10), "planar2": lambda: robots.planar(2)}[robot]()
+    if robot == "xarm6":
+        mn, mx, g, tol = synthetic.sweep_obstacles(M, dist, r_min=r_min)
+    else:
+        reach = float(np.abs(rb.xyz).sum())
+        mn, mx, g, tol = synthetic.sweep_obstacles(M, dist, r_min=r_min * reach, ws_center=(0.0, 0.0, 0.0), ws_radius=1.2 * reach)
+        if rb.ground_included == 0:
+            g = np.zeros_like(g)
+    tol = tol.copy()
+    tol[1::7] = 0.08                                                       # some obstacles with a min_dist_tol: they must stay out of the field
+    N = 200_000
+    q = synthetic.configs(rb, N, seed=0xC0FE)
+    q1, q2 = synthetic.edges(rb, 70_000, 0.3, seed=0xC0FF)
+    out = {}
+    for df, srt in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        eng = make(rb, mn, mx, g, tol)
+        eng.set_distance_field(bool(df)); eng.set_config_sort(bool(srt))
+        out[(df, srt)] = (eng.distance(q, robots.DIST_MIN)[0], *eng.distance(q, robots.DIST_PROFILE)[:2], eng.is_valid(q), eng.is_valid_edges(q1, q2))
+        if df:
+            out[(df, srt, "second")] = eng.second_pass_warps()
+        eng.close()
+    base = out[(0, 0)]
+    for key in ((1, 1), (1, 0), (0, 1)):
+        for a, b in zip(out[key], base):
+            assert same(a, b).all(), key
+    assert out[(1, 1, "second")] < 0.01 * N / 32                            # the second pass is the exception
+    o = make_oracle(ob, rb, mn, mx, g, tol)
+    sample = slice(0, 4000)
+    d_o, p_o, _ = o.distance(q[sample], robots.DIST_PROFILE)
+    assert np.abs(base[1][sample] - d_o).max() <= TOL32 and np.abs(base[2][sample] - p_o).max() <= TOL32
+    assert (base[3][sample] != o.is_valid(q[sample])).sum() == 0
+    assert 0 < base[3].mean() < 1 or robot != "xarm6"
+
+
 def test_full_size_properties():
     """BASELINE sweep size (2^20 configurations x 1000 boxes): size-independent properties instead of an oracle run."""
     torch = pytest.importorskip("torch")
