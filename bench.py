@@ -290,9 +290,10 @@ def roofline(eng, rb, prec, precision_name, N, avg_launch_s, pairs_per_launch, w
         sms = 148
     issue_peak = sms * 4 * sm_mhz * 1e6 / 1e9                    # G warp-inst / s
     out = {"bound": "issue", "unit": "Ginst/s", "peak": issue_peak, "peak_source": f"{sms} SMs x 4 schedulers x 1 warp instruction / cycle x {sm_mhz} MHz (SM clock sampled in the timed region)",
-           "kernel": ("rvs::distance_kernel<%s,PROFILE>" if no_cull else "rvs::distance_wq_kernel<%s,PROFILE,6> (broad-phase scan + warp work queues)") %
+           "kernel": ("rvs::distance_kernel<%s,PROFILE>" if no_cull else "rvs::distance_wq_kernel<%s,PROFILE,3> (coherent warps from a counting sort of the batch, distance-field bootstrap, broad-phase scan + warp work queues)") %
                      {"ref32": "double,float", "fast32": "float,float", "f64": "double,double"}[precision_name],
-           "avg_launch_ms": 1e3 * avg_launch_s, "configs_per_launch": N}
+           "avg_launch_ms": 1e3 * avg_launch_s, "configs_per_launch": N,
+           "avg_launch_covers": "one rvs_distance_dev call = the three grids of the counting sort (rvs_sort.cuh, ~4 % of the time) + the distance kernel, CUDA events on the engine's stream"}
     prof = None
     if os.path.exists(NCU_PROFILE) and not no_cull and precision_name == "ref32":
         prof = json.load(open(NCU_PROFILE))
@@ -302,6 +303,9 @@ def roofline(eng, rb, prec, precision_name, N, avg_launch_s, pairs_per_launch, w
         flop32 = prof["thread_inst_fp32"]["flop"] * scale
         out.update(achieved=inst / avg_launch_s / 1e9, frac=inst / avg_launch_s / 1e9 / issue_peak,
                    traffic=(prof["dram_bytes_read"] + prof["dram_bytes_write"]) * scale,
+                   traffic_note="dram__bytes_read + dram__bytes_write of the distance kernel in the ncu capture quoted below (not measured in this run), scaled to this "
+                                "launch; above the algorithmic bytes because the coherent-warp order gathers 24-byte configurations and scatters 4- / 24-byte "
+                                "results through 32-byte sectors - under 3 % of the HBM peak either way, the kernel is issue-bound",
                    counters={"source": "profiles/r2/" + os.path.basename(NCU_PROFILE) + " (ncu --set full capture of this kernel on this workload; counts scaled by configurations per launch, "
                                        "time measured live by CUDA events)",
                              "capture": prof["capture"], "capture_configs": prof["configs"], "capture_duration_ms": prof["duration_ms"],

@@ -49,6 +49,8 @@ struct rvs_engine {
     int df_on = 1;
     // permutation that makes the warps of a large distance batch geometrically coherent (rvs_sort.cuh)
     int sort_on = 1;
+    int sort_per_bin = 128;                      // configurations per bin aimed at (RVS_SORT_PER_BIN overrides)
+    int sort_joints = 3;                         // leading joints in the sort key (RVS_SORT_JOINTS overrides, for experiments)
     int32_t *d_perm = nullptr;
     size_t perm_cap = 0;
     uint32_t *d_hist[2] = {nullptr, nullptr};    // one per compute stream of the pipelined host path
@@ -244,7 +246,7 @@ void df_args(rvs_engine *h, KArgs &a) {
 // Coherent warps for the work-queue distance kernel: counting sort of the batch d_q[0, N) on its leading joints, written to
 // d_perm[perm_offset, perm_offset + N) (as indices relative to d_q) on stream `st`.
 constexpr int64_t kSortMinConfigs = 65536;
-constexpr int kSortMaxBits = 18;
+constexpr int kSortMaxBits = 21;
 int sort_ready(rvs_engine *h, size_t total) {
     if (total > h->perm_cap) {
         if (h->d_perm) RVS_CUDA(h, cudaFree(h->d_perm));
@@ -258,10 +260,10 @@ int sort_ready(rvs_engine *h, size_t total) {
 }
 int sort_configs(rvs_engine *h, const float *d_q, int64_t N, int64_t perm_offset, int which, cudaStream_t st) {
     SortArgs a{};
-    a.q = d_q; a.N = N; a.n = h->h_robot.n; a.joints = std::min(3, h->h_robot.n);
+    a.q = d_q; a.N = N; a.n = h->h_robot.n; a.joints = std::min(h->sort_joints, h->h_robot.n);
     int total = 0;
-    while (total < kSortMaxBits && (int64_t(48) << (total + 1)) <= N) total++;           // ~48 configurations per bin or more
-    for (int j = 0; j < 3; j++) a.bits[j] = 0;
+    while (total < kSortMaxBits && (int64_t(h->sort_per_bin) << (total + 1)) <= N) total++;   // that many configurations per bin, or more
+    for (int j = 0; j < 6; j++) a.bits[j] = 0;
     for (int b = 0; b < total; b++) a.bits[b % a.joints]++;
     for (int j = 0; j < a.joints; j++) {
         a.lo[j] = h->h_robot.limit_lo[j];
@@ -445,6 +447,8 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     if (device < 0 || device >= count) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "device index out of range");
     rvs_engine *h = new rvs_engine();
     if (const char *e_so = std::getenv("RVS_SORT_CONFIGS")) h->sort_on = std::atoi(e_so) ? 1 : 0;
+    if (const char *e_sb = std::getenv("RVS_SORT_PER_BIN")) h->sort_per_bin = std::max(1, std::atoi(e_sb));
+    if (const char *e_sj = std::getenv("RVS_SORT_JOINTS")) h->sort_joints = std::max(1, std::min(6, std::atoi(e_sj)));
     if (const char *e_df = std::getenv("RVS_DISTANCE_FIELD")) h->df_on = std::atoi(e_df) ? 1 : 0;      // A/B switch (results are identical either way)
     h->device = device;
     h->prm = *params;

@@ -3,8 +3,9 @@
 // The work-queue distance kernel (rvs_distance_wq.cuh) gives one warp 32 configurations; everything it decides per warp — which links
 // are still open, where the sorted obstacle table can be cut off, when the queues hold a full warp of one kind of work — is as good as
 // those 32 arms are similar.  A batch arrives in the caller's order (random for sweeps and dataset generation), so the kernel is given
-// a permutation: a counting sort on a key made of the leading joints (they place most of the chain), quantised to as many bits as the
-// batch has warps.  Three small kernels (histogram, scan of <= 2^18 bins, scatter); results are written back through the same
+// a permutation: a counting sort on a key made of the three leading joints (they place most of the chain; two joints or four measured
+// slower), quantised so that a bin holds ~128 configurations (measured optimum: finer bins cost more in the sort than they return in
+// the kernel; profiles/r2).  Three small kernels (histogram, scan of <= 2^21 bins, scatter); results are written back through the same
 // permutation, so the caller sees its own order and per-configuration results do not depend on it.
 #pragma once
 #include <cuda_runtime.h>
@@ -17,9 +18,9 @@ struct SortArgs {
     const float *q;          // [N][n]
     int64_t N;
     int32_t n;
-    int32_t joints;          // leading joints in the key (<= 3)
-    int32_t bits[3];         // bits per joint, most significant joint first
-    float lo[3], inv[3];     // joint range: u = (q - lo) * inv in [0, 1)
+    int32_t joints;          // leading joints in the key (<= 6)
+    int32_t bits[6];         // bits per joint, most significant joint first
+    float lo[6], inv[6];     // joint range: u = (q - lo) * inv in [0, 1)
     uint32_t *hist;          // [1 << total bits] zeroed by the caller; becomes the write cursor of the scatter
     int32_t nbins;
     int32_t *perm;           // [N] out: perm[k] = index of the configuration processed k-th
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) sort_hist_kernel(const SortArgs a) {
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i < a.N) atomicAdd(a.hist + sort_key(a, i), 1u);
 }
-// exclusive scan of the histogram by ONE block of 1024 threads (<= 2^18 bins): every thread owns a contiguous run of bins and walks it
+// exclusive scan of the histogram by ONE block of 1024 threads (<= 2^21 bins): every thread owns a contiguous run of bins and walks it
 // with 16-byte loads; the 1024 partial sums are scanned by warp shuffles
 __global__ void __launch_bounds__(1024) sort_scan_kernel(const SortArgs a) {
     __shared__ uint32_t warp_sum[32];
