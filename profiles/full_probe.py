@@ -9,14 +9,15 @@ from rpmplv2_b200 import engine, robots, synthetic
 rb = robots.xarm6()
 eng = engine.Engine(rb, robots.default_params(), device=0)
 stream = torch.cuda.current_stream(); eng.set_stream(stream.cuda_stream)
-for N, M in ((131072, 51), (16384, 51), (2048, 51), (131072, 6)):
+for N, M in ((131072, 51), (1048576, 51), (16384, 51), (2048, 51), (131072, 6)):
     mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1", r_min=0.3)
     eng.set_obstacles(mn, mx, g, tol)
     d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
     eng.generate_configs_dev(synthetic.SEED_CONFIGS, 0, N, d_q.data_ptr())
     d_dc = torch.empty(N, dtype=torch.float32, device="cuda"); d_p = torch.empty((N, 6), dtype=torch.float32, device="cuda")
     d_n = torch.empty((N, M, 6, 6), dtype=torch.float32, device="cuda")
-    for mode, name in ((robots.DIST_FULL, "FULL"), (robots.DIST_PROFILE, "PROFILE")):
+    for mode, name, srt in ((robots.DIST_FULL, "FULL", 1), (robots.DIST_FULL, "FULL unsorted", 0), (robots.DIST_PROFILE, "PROFILE", 1)):
+        eng.set_config_sort(bool(srt))
         ms = []
         for _ in range(4):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

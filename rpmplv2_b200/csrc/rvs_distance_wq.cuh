@@ -83,6 +83,9 @@ constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bi
 #ifndef RVS_WQ_HALF
 #define RVS_WQ_HALF 1
 #endif
+#ifndef RVS_WQ_FIRST
+#define RVS_WQ_FIRST 4                            // first refresh interval when the minima start from the distance-field bounds (without them: 4)
+#endif
 constexpr int kWqExpand = RVS_WQ_EXPAND;          // hit words unpacked per expansion round (bounds the pair queue: kWqExpand * 2G + 32 entries)
 constexpr int kWqG = RVS_WQ_G;                    // links scanned per pass over the obstacle table (slots of the scan loop)
 constexpr int kWqInterval = RVS_WQ_INTERVAL;      // obstacles between two threshold refreshes (after the first doublings 4, 8, 16, ...)
@@ -567,7 +570,8 @@ __global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_WQ_MINBLOCKS : 
 #endif
                 }
                 // the minima settle quickly (the table is sorted nearest-first): refresh after 4, 8, 16, 32, 64, 128, 256, 384, ... obstacles
-                const int jend = alive ? min(j0 + (j0 < 4 ? 4 : min(j0, kWqInterval)), count) : count;
+                const int first = a.df ? RVS_WQ_FIRST : 4;
+                const int jend = alive ? min(j0 + (j0 < first ? first : min(j0, kWqInterval)), count) : count;
                 const bool seg_end = jend == count && g0 + G >= L;         // queue entries index this segment: empty every queue before moving on
 #pragma unroll 1
                 for (int j = j0; j < jend; j += kWqUnroll) {

@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(kBlock) distance_kernel(const KArgs a) {
     __shared__ ObstacleRec tile[kTileObstacles];
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n;
-    const int64_t cfg = int64_t(blockIdx.x) * kBlock + threadIdx.x;
-    const bool live = cfg < a.N;
+    const int64_t slot_k = int64_t(blockIdx.x) * kBlock + threadIdx.x;
+    const bool live = slot_k < a.N;
+    // a.perm (rvs_sort.cuh): the lanes of a warp walk the same (link, obstacle) pairs in lockstep, so arms that are alike take the same
+    // branches of the reference's case tree
+    const int64_t cfg = live && a.perm ? int64_t(__ldg(a.perm + slot_k)) : slot_k;
     const R eq_thr = R(a.eq_thr), max_dist = R(a.max_dist);
 
     R sk[3 * (kMaxDofs + 1)];
