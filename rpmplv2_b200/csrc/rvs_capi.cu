@@ -38,7 +38,7 @@ struct rvs_engine {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t s_in = nullptr, s_out = nullptr, s_k2 = nullptr;   // copy streams + second compute stream of the pipelined host-pointer distance path (lazy)
-    cudaEvent_t ev_in[8] = {}, ev_k[8] = {}, ev_done = nullptr;
+    cudaEvent_t ev_in[32] = {}, ev_k[32] = {}, ev_done = nullptr;
     rvs_params prm{};
     RobotDev h_robot{};
     RobotDev *d_robot = nullptr;
@@ -328,7 +328,7 @@ int pipeline_ready(rvs_engine *h) {
     RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
     RVS_CUDA(h, cudaStreamCreateWithFlags(&h->s_k2, cudaStreamNonBlocking));
-    for (int k = 0; k < 8; k++) {
+    for (int k = 0; k < 32; k++) {
         RVS_CUDA(h, cudaEventCreateWithFlags(&h->ev_in[k], cudaEventDisableTiming));
         RVS_CUDA(h, cudaEventCreateWithFlags(&h->ev_k[k], cudaEventDisableTiming));
     }
@@ -356,7 +356,8 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     float *dq = static_cast<float *>(h->buf[B_Q].p);
     char *ddc = static_cast<char *>(h->buf[B_DC].p), *dprof = static_cast<char *>(h->buf[B_PROF].p);
     constexpr int64_t kMinChunk = 1 << 16;
-    const int chunks = mode == RVS_DIST_FULL ? 1 : int(std::min<int64_t>(8, N / kMinChunk));
+    static const int max_chunks = [] { const char *e = std::getenv("RVS_PIPE_CHUNKS"); return e ? std::max(1, std::min(32, std::atoi(e))) : 12; }();
+    const int chunks = mode == RVS_DIST_FULL ? 1 : int(std::min<int64_t>(max_chunks, N / kMinChunk));
     if (chunks < 2) {
         if (h->zc) std::memcpy(dq, q, size_t(N) * n * sizeof(float));
         else RVS_CUDA(h, cudaMemcpyAsync(dq, q, size_t(N) * n * sizeof(float), cudaMemcpyHostToDevice, h->stream));
