@@ -31,9 +31,27 @@ for rb, (mn, mx, g, tol) in ((robots.xarm6(), synthetic.sweep_obstacles(300, "D2
     eng.env_step(0.01, 7)
     eng.motion_validity(q1[:50], q2[:50], 10, 0.005, commit_edge=3)
     eng.distance(q[:5000], robots.DIST_PROFILE)
+    # round 2: random_directions (libc stream on the device), self-collision edges, device-resident trees
+    eng.env_set(env_params("random_directions", ws_center=scenes.WS_CENTER, ws_radius=1.0, base_radius=0.15, robot_max_vel=3.0), **sc)
+    eng.env_set_random_directions(np.full((len(sc["max_vel"]), 3), 0.2, np.float32), 2, 5)
+    eng.env_step(0.02, 40)
+    eng.motion_validity(q1[:50], q2[:50], 6, 0.01, commit_edge=1)
+    eng.self_collision_edges(q1[:300], q2[:300]); eng.check_edges(q1[:300], q2[:300]); eng.check_states(q[:300])
+    t = eng.tree_create(); eng.tree_append(t, q[:3000]); eng.tree_nearest(q[3000:3100]); eng.tree_radius(t, q[5], 2.0, 5, capacity=64)
     eng.close()
+# round 2: the large-batch path (coherent-warp sort, distance-field bootstrap, second pass) on a batch above both thresholds
+rb = robots.xarm6()
+mn, mx, g, tol = synthetic.sweep_obstacles(200, "D2", r_min=0.6)
+eng = engine.Engine(rb); eng.set_obstacles(mn, mx, g, tol)
+qq = synthetic.configs(rb, 70000)
+eng.distance(qq, robots.DIST_PROFILE); eng.distance(qq, robots.DIST_MIN); eng.is_valid(qq)
+e1, e2 = synthetic.edges(rb, 66000, 0.2)
+eng.is_valid_edges(e1, e2)
+eng.close()
 rb, mn, mx, g, tol = scenes.xarm6_scenario1()
 eng = engine.Engine(rb); eng.set_obstacles(mn, mx, g, tol)
 cfg = planning.default_config(planning.RGBT_CONNECT, max_planning_time=5.0)
 res, st = planning.solve_batch(eng, cfg, np.array([0, 0.7854, -2.3562, 0, 0, 0], np.float32), np.array([3.14159, 0.7854, -2.3562, 3.14159, 0, 3.14159], np.float32), seeds=np.arange(4))
-print("sanitize probe done; planner success", [r["success"] for r in res])
+out = planning.rrtx_grow(eng, planning.rrtx_config(eps_step=0.5, r_rewire=2.0, max_neighbors=50, device_index=1), np.array([3.14159, 0.7854, -2.3562, 3.14159, 0, 3.14159], np.float32),
+                         synthetic.configs(rb, 150, seed=77))
+print("sanitize probe done; planner success", [r["success"] for r in res], "rrtx states", out["stats"]["states"])
