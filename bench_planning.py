@@ -49,7 +49,7 @@ def scenarios():
     for M in (51, 1000):
         mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1" if M == 51 else "D2", r_min=0.0 if M == 51 else 0.55)
         out.append(dict(name=f"xarm6 random obstacles M={M}", planner=planning.RGBT_CONNECT, robot=robots.xarm6(), obstacles=(mn, mx, g, tol),
-                        q_start=[0, 0, 0, 3.1415, 1.5708, 0], q_goal=[3.1415, 0, -1.5708, 0, 0, 3.1415], prune_ends=True))
+                        q_start=[0, 0.7854, -2.3562, 0, 0, 0], q_goal=[3.14159, 0.7854, -2.3562, 3.14159, 0, 3.14159], prune_ends=True))   # scenario1's ends: free of self-collision
     return out
 
 

@@ -260,6 +260,15 @@ int  rvs_store_distance(rvs_handle h, const float *q, int32_t N, const int32_t *
 int  rvs_store_extend_spines(rvs_handle h, const int32_t *root_slots, const float *q_targets, int32_t S,
                              const rvs_spine_params *sp, int32_t gen2, float *q_layers, int32_t *n_layers,
                              float *d_c_last, uint8_t *status);
+/* connectGenSpine's loop (src/planners/rbt/RGBTConnect.cpp:120-150; RBTConnect::connectSpine :152-180 with one layer) for R requests in
+ * ONE call: request r starts from the cached state root_slots[r] and repeats, at most `steps` times,
+ *     { extendGenSpine2 towards q_targets[r]; computeDistance of the state it reached, cached in new_slots[r][k] }
+ * while the spine Advanced and the current state's d_c is above d_crit (below it the reference marches in RRT mode: the caller's
+ * business).  new_slots is R x steps (-1 = this request makes fewer steps).  Outputs, R x steps each: q_layers (x num_layers x num_dofs),
+ * n_layers (-1: the step was not executed — the loop had ended), d_c_new (real distance of the reached state), status
+ * (base::State::Status of the spine).  The 2 x steps kernels gate themselves on device state: one synchronisation per loop. */
+int  rvs_store_connect(rvs_handle h, const int32_t *root_slots, const float *q_targets, const int32_t *new_slots, int32_t R, int32_t steps,
+                       const rvs_spine_params *sp, float *q_layers, int32_t *n_layers, float *d_c_new, uint8_t *status);
 /* copy one slot back to the host (any of the outputs may be NULL); planes[M x L x 6] */
 int  rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *profile, float *planes);
 

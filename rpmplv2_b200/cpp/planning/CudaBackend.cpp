@@ -55,6 +55,15 @@ namespace rvsplan
 		check(rvs_store_extend_spines(engine, root_slots, q_targets, S, &p, gen2 ? 1 : 0, q_layers, n_layers, d_c_last, status), "rvs_store_extend_spines");
 	}
 
+	// the whole loop in ONE engine call: its 2 x steps kernels gate themselves on device state (rvs_store_connect)
+	void CudaBackend::connectGenSpines(const int32_t *root_slots, const float *, const float *q_targets, const int32_t *new_slots, int R, int steps,
+									   const SpineParams &sp, float *q_layers, int32_t *n_layers, float *d_c_new, uint8_t *status)
+	{
+		rvs_spine_params p;
+		p.num_layers = sp.num_layers; p.num_iter_spine = sp.num_iter_spine; p.use_expanded_bubble = sp.use_expanded_bubble ? 1 : 0; p.d_crit = sp.d_crit;
+		check(rvs_store_connect(engine, root_slots, q_targets, new_slots, R, steps, &p, q_layers, n_layers, d_c_new, status), "rvs_store_connect");
+	}
+
 	CudaNeighborIndex::CudaNeighborIndex(rvs_handle h) : engine(h)
 	{
 		if (!h) throw std::runtime_error("CudaNeighborIndex: NULL engine handle");

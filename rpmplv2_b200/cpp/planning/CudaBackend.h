@@ -28,6 +28,8 @@ namespace rvsplan
 		void distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c) override;
 		void extendGenSpines(const int32_t *root_slots, const float *q_targets, int S, const SpineParams &sp, bool gen2,
 							 float *q_layers, int32_t *n_layers, float *d_c_last, uint8_t *status) override;
+		void connectGenSpines(const int32_t *root_slots, const float *root_d_c, const float *q_targets, const int32_t *new_slots, int R, int steps,
+							  const SpineParams &sp, float *q_layers, int32_t *n_layers, float *d_c_new, uint8_t *status) override;
 	private:
 		void check(int status, const char *what) const;
 		rvs_handle engine;

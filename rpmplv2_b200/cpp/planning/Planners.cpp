@@ -88,6 +88,7 @@ namespace rvsplan
 			rng.seed = splitmix64(seed);
 			if (libcStream()) { rng.libc = true; std::srand(unsigned(seed)); }
 			if (cfg.kind == PlannerKind::RBTConnect) cfg.spine.num_layers = 1;     // a bur spine is a one-layer generalized spine
+			if (const char *e = std::getenv("RVS_PLAN_CONNECT_CHUNK")) cfg.connect_chunk = std::max(0, std::min(64, std::atoi(e)));   // A/B knob (0: a query per step)
 		}
 
 		Task<int> solve()
@@ -325,32 +326,65 @@ namespace rvsplan
 		}
 
 		// RBTConnect::connectSpine (RBTConnect.cpp:152-180) / RGBTConnect::connectGenSpine (RGBTConnect.cpp:120-150)
+		// The loop { spine from q_new; computeDistance(q_new) } depends on nothing but the state space, so up to cfg.connect_chunk of
+		// its steps go out as ONE query (Request::CONNECT; on the CUDA backend one engine call whose kernels gate themselves on device
+		// state) and the tree is grown from the answer.
 		Task<Status> connectGenSpine(int t, int idx, Coord q_e)
 		{
 			float d_c = co_await computeDistance(t, idx);
 			int q_new = idx;
 			Status status = Status::Advanced;
-			int num_ext = 0;
-			while (status == Status::Advanced && num_ext++ < cfg.max_extension_steps)
+			int num_ext = 0;                                   // extension steps made so far (the reference's num_ext after its increment)
+			while (status == Status::Advanced && num_ext < cfg.max_extension_steps)
 			{
-				const int q_temp = q_new;
-				if (d_c > cfg.spine.d_crit)
+				if (!(d_c > cfg.spine.d_crit))
 				{
+					// below D_CRIT the loop stays in RRT mode until it ends (d_c is not refreshed, :141-146): march the rest at once
+					status = co_await connect(t, q_new, q_e, cfg.max_extension_steps - num_ext);
+					co_return status;
+				}
+				if (cfg.connect_chunk <= 0)
+				{
+					const int q_temp = q_new;
 					req.kind = Request::SPINES; req.count = 1; req.gen2 = true;
 					req.q1 = q_e;
 					req.slots.assign(1, trees[t].nodes[q_temp].slot);
 					co_await Query{*this};
 					res.num_spines++;
+					num_ext++;
 					status = Status(req.flags[0]);
 					q_new = addLayers(t, 0, q_temp);
 					d_c = co_await computeDistance(t, q_new);
+					continue;
 				}
-				else
+				const int steps = std::min(cfg.connect_chunk, cfg.max_extension_steps - num_ext);
+				req.kind = Request::CONNECT; req.count = 1; req.steps = steps;
+				req.q1 = q_e;
+				req.d.assign(1, d_c);
+				req.slots.assign(1, trees[t].nodes[q_new].slot);
+				for (int k = 0; k < steps; k++)
 				{
-					// below D_CRIT the loop stays in RRT mode until it ends (d_c is not refreshed, :141-146): march the rest at once
-					status = co_await connect(t, q_temp, q_e, cfg.max_extension_steps - num_ext + 1);
-					co_return status;
+					if (spare_slots.empty()) req.slots.push_back(slots.next());
+					else { req.slots.push_back(spare_slots.back()); spare_slots.pop_back(); }
 				}
+				co_await Query{*this};
+				const size_t stride = size_t(cfg.spine.num_layers) * n;
+				int used = 0;
+				for (int k = 0; k < steps; k++)
+				{
+					if (req.n_layers[k] < 0) break;              // the loop had ended before this step
+					used++; num_ext++;
+					res.num_spines++; res.num_distances++;
+					status = Status(req.flags[k]);
+					const int layers = std::max(1, int(req.n_layers[k]));
+					for (int l = 0; l < layers; l++) q_new = trees[t].add(&req.q_layers[size_t(k) * stride + size_t(l) * n], q_new);
+					Node &nd = trees[t].nodes[q_new];
+					nd.slot = req.slots[size_t(1 + k)]; nd.d_c = req.d[size_t(k)]; nd.is_real = true;
+					d_c = nd.d_c;
+					if (status != Status::Advanced) break;
+				}
+				for (int k = steps; k > used; k--) spare_slots.push_back(req.slots[size_t(k)]);     // slots the loop did not get to
+				if (used == 0) break;                            // (cannot happen: d_c > D_CRIT was checked above)
 			}
 			co_return status;
 		}
@@ -371,6 +405,7 @@ namespace rvsplan
 		float eq_thr;
 		SlotAllocator &slots;
 		Rng rng;
+		std::vector<int32_t> spare_slots;      // State slots a connect query was given but did not use
 		Tree trees[2];
 		Coord q_start, q_goal;
 		Clock::time_point t0;
@@ -487,7 +522,7 @@ namespace rvsplan
 		while (true)
 		{
 			bool any = false;
-			for (int kind = Request::VALID; kind <= Request::SPINES; kind++)
+			for (int kind = Request::VALID; kind <= Request::CONNECT; kind++)
 			{
 				who.clear(); q1.clear(); q2.clear(); sl.clear();
 				int total = 0;
@@ -502,6 +537,43 @@ namespace rvsplan
 					if (kind == Request::DISTANCE || kind == Request::SPINES) sl.insert(sl.end(), r.slots.begin(), r.slots.begin() + r.count);
 				}
 				if (who.empty()) continue;
+				if (kind == Request::CONNECT)
+				{
+					// every run's chain in one backend call: R requests x the longest chain asked for (shorter ones are padded with -1)
+					any = true;
+					num_calls++;
+					if (slots.used() > slot_cap)
+					{
+						slot_cap = std::max(256, 2 * slots.used());
+						backend.reserveSlots(slot_cap);
+					}
+					const int R = int(who.size());
+					int steps = 0;
+					for (int p : who) steps = std::max(steps, runs[p]->req.steps);
+					std::vector<int32_t> roots(static_cast<size_t>(R)), fresh(size_t(R) * steps, -1), nl(size_t(R) * steps);
+					std::vector<float> root_d(static_cast<size_t>(R)), d_new(size_t(R) * steps), layers(size_t(R) * steps * layer_stride);
+					std::vector<uint8_t> st(size_t(R) * steps);
+					for (int i = 0; i < R; i++)
+					{
+						const Request &r = runs[size_t(who[size_t(i)])]->req;
+						roots[size_t(i)] = r.slots[0]; root_d[size_t(i)] = r.d[0];
+						for (int k = 0; k < r.steps; k++) fresh[size_t(i) * steps + k] = r.slots[size_t(1 + k)];
+					}
+					backend.connectGenSpines(roots.data(), root_d.data(), q1.data(), fresh.data(), R, steps, sp, layers.data(), nl.data(), d_new.data(), st.data());
+					for (int i = 0; i < R; i++)
+					{
+						Request &r = runs[size_t(who[size_t(i)])]->req;
+						const size_t o = size_t(i) * steps;
+						r.n_layers.assign(nl.begin() + o, nl.begin() + o + r.steps);
+						r.d.assign(d_new.begin() + o, d_new.begin() + o + r.steps);
+						r.flags.assign(st.begin() + o, st.begin() + o + r.steps);
+						r.q_layers.assign(layers.begin() + o * layer_stride, layers.begin() + (o + r.steps) * layer_stride);
+						r.kind = Request::NONE;
+						runs[size_t(who[size_t(i)])]->res.rounds++;
+					}
+					crew.run(R, [&](int i) { runs[size_t(who[size_t(i)])]->resume_at.resume(); });
+					continue;
+				}
 				any = true;
 				num_calls++;
 				if (slots.used() > slot_cap)

@@ -50,6 +50,8 @@ namespace rvsplan
 		float delta = 3.14159f;              // RBTConnectConfig::DELTA
 		int num_spines = 7;                  // RBTConnectConfig::NUM_SPINES
 		SpineParams spine;                   // D_CRIT, NUM_ITER_SPINE, USE_EXPANDED_BUBBLE, NUM_LAYERS (1 for RBT-Connect)
+		int connect_chunk = 2;               // steps of connectSpine / connectGenSpine's loop per backend query (0: one spine + one distance query per step).
+		                                     // Measured (profiles/r2): the loop rarely runs more than two steps on the shipped scenes, so longer chains only add idle launches
 		bool keep_trees = false;             // return both trees with the result (RBTConnect::outputPlannerData's `*trees[0]`, `*trees[1]`)
 	};
 
@@ -115,14 +117,15 @@ namespace rvsplan
 	// ---- one pending state-space query of one run -----------------------------------------------------------------------
 	struct Request
 	{
-		enum Kind { NONE, VALID, EDGES, DISTANCE, SPINES } kind = NONE;
+		enum Kind { NONE, VALID, EDGES, DISTANCE, SPINES, CONNECT } kind = NONE;
 		std::vector<float> q1, q2;           // VALID/DISTANCE: q1 = N x n;  EDGES: q1, q2 = E x n;  SPINES: q1 = targets S x n
-		std::vector<int32_t> slots;          // DISTANCE: destination slots;  SPINES: root slots
+		std::vector<int32_t> slots;          // DISTANCE: destination slots;  SPINES: root slots;  CONNECT: root slot, then one slot per step
+		int steps = 0;                       // CONNECT: steps of connectGenSpine's loop asked for in this query (q1 = the target, d[0] = root d_c)
 		bool gen2 = true;
 		int count = 0;
 		// answers
 		std::vector<uint8_t> flags;          // VALID / EDGES verdicts; SPINES status
-		std::vector<float> d;                // DISTANCE d_c; SPINES d_c_last
+		std::vector<float> d;                // DISTANCE d_c; SPINES d_c_last; CONNECT: real d_c of the state every step reached
 		std::vector<float> q_layers;         // SPINES: S x num_layers x n
 		std::vector<int32_t> n_layers;       // SPINES
 	};

@@ -1088,6 +1088,67 @@ int rvs_store_extend_spines(rvs_handle h, const int32_t *root_slots, const float
     return finish(h);
 }
 
+// connectGenSpine's loop (RGBTConnect.cpp:120-150) for R requests at once: up to `steps` times { generalized spine from the current
+// state's slot towards the target; computeDistance of the state it reached into the next slot }, the 2 * steps kernels launched back to
+// back and gating themselves on device state — one synchronisation per loop instead of two per step.
+int rvs_store_connect(rvs_handle h, const int32_t *root_slots, const float *q_targets, const int32_t *new_slots, int32_t R, int32_t steps,
+                      const rvs_spine_params *sp, float *q_layers, int32_t *n_layers, float *d_c_new, uint8_t *status) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "spines run in FP32: use a REF32/FAST32 handle");
+    if (R < 0 || steps < 1 || steps > 64 || !sp || sp->num_layers < 1 || sp->num_iter_spine < 1) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad R, steps (1..64) or spine parameters");
+    if (R == 0) return RVS_OK;
+    if (!root_slots || !q_targets || !new_slots || !q_layers || !n_layers || !d_c_new || !status) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    RVS_TRY(check_slots(h, root_slots, R));
+    const size_t n = size_t(h->h_robot.n), layers = size_t(sp->num_layers), Rs = size_t(R), K = size_t(steps);
+    // per-step tables in [step][request] order: root slot of the step, slot of its result (-1: this request makes fewer steps)
+    std::vector<int32_t> tab(2 * K * Rs + Rs, 1);                            // ... followed by the chain states (all alive)
+    for (size_t r = 0; r < Rs; r++)
+        for (size_t k = 0; k < K; k++) {
+            const int32_t fresh = new_slots[r * K + k];
+            if (fresh >= 0) RVS_TRY(check_slots(h, &fresh, 1));
+            tab[K * Rs + k * Rs + r] = fresh;
+            tab[k * Rs + r] = k == 0 ? root_slots[r] : new_slots[r * K + k - 1];
+            if (tab[k * Rs + r] < 0) { tab[k * Rs + r] = root_slots[r]; tab[K * Rs + k * Rs + r] = -1; }     // (a gap ends the chain)
+        }
+    begin_call(h, kSmallCall + 1);                                          // device staging: the kernels of a chain read each other's results
+    RVS_TRY(h2d(h, B_Q, q_targets, Rs * n * sizeof(float)));
+    RVS_TRY(h2d(h, B_IDX, tab.data(), tab.size() * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_NEAR, K * Rs * layers * n * sizeof(float)));
+    RVS_TRY(reserve(h, B_DC, 2 * K * Rs * sizeof(float)));
+    RVS_TRY(reserve(h, B_PROF, K * Rs * sizeof(int32_t)));
+    RVS_TRY(reserve(h, B_VERD, K * Rs));
+    const int32_t *d_tab = static_cast<const int32_t *>(h->buf[B_IDX].p);
+    float *d_layers = static_cast<float *>(h->buf[B_NEAR].p), *d_dc = static_cast<float *>(h->buf[B_DC].p);
+    int32_t *d_nl = static_cast<int32_t *>(h->buf[B_PROF].p);
+    uint8_t *d_st = static_cast<uint8_t *>(h->buf[B_VERD].p);
+    for (size_t k = 0; k < K; k++) {
+        StoreArgs a = store_args(h);
+        a.S = R; a.N = R;
+        a.root_slot = d_tab + k * Rs; a.slots = d_tab + K * Rs + k * Rs; a.chain_state = const_cast<int32_t *>(d_tab) + 2 * K * Rs;
+        a.q_targets = static_cast<const float *>(h->buf[B_Q].p);
+        a.num_layers = sp->num_layers; a.num_iter_spine = sp->num_iter_spine; a.use_expanded_bubble = sp->use_expanded_bubble; a.gen2 = 1;
+        a.d_crit = sp->d_crit;
+        a.q_layers = d_layers + k * Rs * layers * n; a.n_layers = d_nl + k * Rs; a.d_c_last = d_dc + K * Rs + k * Rs; a.status = d_st + k * Rs;
+        RVS_TRY(launched(h, h->lt.store_spines(a, h->stream), "connect chain: spine kernel launch"));
+        a.q = a.q_layers; a.layers_n = a.n_layers; a.d_c = d_dc + k * Rs; a.profile = nullptr;
+        RVS_TRY(launched(h, h->lt.store_distance(a, h->stream), "connect chain: distance kernel launch"));
+    }
+    std::vector<float> layers_t(K * Rs * layers * n), dc_t(K * Rs);
+    std::vector<int32_t> nl_t(K * Rs);
+    std::vector<uint8_t> st_t(K * Rs);
+    RVS_TRY(d2h(h, layers_t.data(), B_NEAR, layers_t.size() * sizeof(float)));
+    RVS_TRY(d2h(h, dc_t.data(), B_DC, dc_t.size() * sizeof(float)));
+    RVS_TRY(d2h(h, nl_t.data(), B_PROF, nl_t.size() * sizeof(int32_t)));
+    RVS_TRY(d2h(h, st_t.data(), B_VERD, st_t.size()));
+    RVS_TRY(finish(h));
+    for (size_t r = 0; r < Rs; r++)                                         // [step][request] -> the caller's [request][step]
+        for (size_t k = 0; k < K; k++) {
+            std::copy_n(layers_t.begin() + (k * Rs + r) * layers * n, layers * n, q_layers + (r * K + k) * layers * n);
+            n_layers[r * K + k] = nl_t[k * Rs + r]; d_c_new[r * K + k] = dc_t[k * Rs + r]; status[r * K + k] = st_t[k * Rs + r];
+        }
+    return RVS_OK;
+}
+
 int rvs_store_read(rvs_handle h, int32_t slot, float *q, float *d_c, float *profile, float *planes) {
     RVS_TRY(enter(h));
     RVS_TRY(check_slots(h, &slot, 1));

@@ -34,6 +34,12 @@ __global__ void __launch_bounds__(32 * kStoreWarps) store_distance_kernel(const 
     const int cfg = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *q = a.q + size_t(cfg) * L;
+    if (a.layers_n) {
+        // step of a connect chain: the configuration is the last layer the spine kernel of this step wrote (a.q = its q_layers)
+        const int nl = a.layers_n[cfg];
+        if (nl < 0) { if (threadIdx.x == 0) a.d_c[cfg] = -1.f; return; }                   // (the whole CTA leaves: nothing to do)
+        q = a.q + (size_t(cfg) * a.num_layers + size_t(nl > 1 ? nl - 1 : 0)) * L;
+    }
     float *slot = a.store + size_t(a.slots[cfg]) * store_slot_floats(L, M);
     float *planes = slot + store_header_floats(L);
     if (threadIdx.x == 0) {
@@ -89,6 +95,7 @@ __global__ void __launch_bounds__(32 * kStoreWarps) store_distance_kernel(const 
             slot[L + 1 + i] = p;
             if (a.profile) a.profile[size_t(cfg) * L + i] = p;
         }
+        if (a.chain_state && a.status[cfg] != 1) a.chain_state[cfg] = 0;                    // the loop ends unless the spine Advanced
     }
 }
 
@@ -376,6 +383,16 @@ __global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const Sto
     if (s >= a.S) return;                                              // (whole warps leave together; no block-level barrier below)
     float *sk = spine_smem + size_t(warp) * (2 * 3 * W + n * W + n), *sk_new = sk + 3 * W, *Rm = sk_new + 3 * W, *delta = Rm + n * W;
     const float *slot = a.store + size_t(a.root_slot[s]) * store_slot_floats(n, M);
+    if (a.chain_state) {
+        // step of a connect chain (connectGenSpine's loop, RGBTConnect.cpp:120-150): it runs while the chain is alive, the caller left
+        // room for its result (a.slots[s] >= 0) and the root still has clearance above D_CRIT (below it the caller marches in RRT mode)
+        const int alive = a.chain_state[s];
+        if (!alive || a.slots[s] < 0 || !(slot[n] > a.d_crit)) {
+            __syncwarp();
+            if (lane == 0) { a.n_layers[s] = -1; a.status[s] = 0; a.d_c_last[s] = slot[n]; a.chain_state[s] = 0; }
+            return;
+        }
+    }
     const float *root_planes = slot + store_header_floats(n);
     float *q_out = a.q_layers + size_t(s) * a.num_layers * n;
     const bool own = lane < n;

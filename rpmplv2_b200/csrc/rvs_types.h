@@ -135,6 +135,10 @@ struct StoreArgs {
     int32_t *n_layers;         // [S]
     float *d_c_last;           // [S]
     uint8_t *status;           // [S]
+    // connect chains (rvs_store_connect): the spine and distance kernels of step k are launched back to back on one stream and gate
+    // themselves on device state, so a whole connectGenSpine loop costs one synchronisation
+    int32_t *chain_state;      // [S] 1 = the chain of request s is still running; nullptr = plain call
+    const int32_t *layers_n;   // distance kernel: [N] layers the spine of this step produced (< 0: step not executed); q = its last layer
 };
 
 // ---- nearest-neighbour / radius queries over device-resident planner trees (rvs_nn.cuh) ----------------------------------------------

@@ -84,6 +84,7 @@ SYMBOLS = {
     "rvs_store_distance": (ctypes.c_int, [_H, c_f32p, ctypes.c_int32, c_i32p, c_f32p, c_f32p]),
     "rvs_store_extend_spines": (ctypes.c_int, [_H, c_i32p, c_f32p, ctypes.c_int32, ctypes.POINTER(RvsSpineParams), ctypes.c_int32,
                                                c_f32p, c_i32p, c_f32p, c_u8p]),
+    "rvs_store_connect": (ctypes.c_int, [_H, c_i32p, c_f32p, c_i32p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(RvsSpineParams), c_f32p, c_i32p, c_f32p, c_u8p]),
     "rvs_store_read": (ctypes.c_int, [_H, ctypes.c_int32, c_f32p, c_f32p, c_f32p, c_f32p]),
     "rvs_capsule_box_distance": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_f32p]),
     "rvs_capsule_box_collision": (ctypes.c_int, [_H, c_f32p, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
@@ -336,6 +337,20 @@ class Engine:
         self._check(self._lib.rvs_store_extend_spines(self._h, _p(root_slots, c_i32p), _p(q_targets, c_f32p), S, ctypes.byref(sp), 1 if gen2 else 0,
                                                       _p(q_layers, c_f32p), _p(n_layers, c_i32p), _p(d_last, c_f32p), _p(status, c_u8p)))
         return q_layers, n_layers, d_last, status
+
+    def store_connect(self, root_slots, q_targets, new_slots, spine_params: Optional[RvsSpineParams] = None):
+        """connectGenSpine's loop for R requests in one call (rvs_store_connect). new_slots: [R, steps] (-1 = fewer steps).
+        Returns (q_layers[R,steps,layers,n], n_layers[R,steps] (-1: step not executed), d_c_new[R,steps], status[R,steps])."""
+        sp = spine_params or RvsSpineParams(5, 1, 1, 0.05)
+        root_slots = np.ascontiguousarray(root_slots, np.int32)
+        new_slots = np.ascontiguousarray(new_slots, np.int32).reshape(len(root_slots), -1)
+        q_targets = _f32(q_targets, (len(root_slots), self.n))
+        R, steps = new_slots.shape
+        q_layers = np.zeros((R, steps, sp.num_layers, self.n), np.float32)
+        n_layers, d_new, status = np.empty((R, steps), np.int32), np.empty((R, steps), np.float32), np.empty((R, steps), np.uint8)
+        self._check(self._lib.rvs_store_connect(self._h, _p(root_slots, c_i32p), _p(q_targets, c_f32p), _p(new_slots, c_i32p), R, steps, ctypes.byref(sp),
+                                                _p(q_layers, c_f32p), _p(n_layers, c_i32p), _p(d_new, c_f32p), _p(status, c_u8p)))
+        return q_layers, n_layers, d_new, status
 
     def store_read(self, slot: int):
         """(q[n], d_c, profile[L], planes[M,L,6]) of one cached state."""

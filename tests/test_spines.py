@@ -263,6 +263,63 @@ def _compare_spines(got, d_root, want, mode, exact=True, tag=""):
         assert np.array_equal(dl[live], want_d[live]) if exact else np.abs(dl[live] - want_d[live]).max() <= 1e-4, tag
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,layers,steps", [("xarm6", 5, 6), ("xarm6", 1, 12), ("spatial22", 5, 4)])
+def test_gpu_connect_chain_equals_the_step_by_step_loop(case, layers, steps):
+    """rvs_store_connect (connectGenSpine's loop, RGBTConnect.cpp:120-150, as ONE call whose kernels gate themselves on device state)
+    against the same loop made of rvs_store_extend_spines + rvs_store_distance calls, bit for bit: layers, statuses, distances, where
+    every chain stops (D_CRIT, Reached / Trapped, the slots it was given) and what the State cache holds afterwards."""
+    if case == "xarm6":
+        rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D2", 0.45)
+    else:
+        rb, mn, mx, g, tol = scenes.chain_scene(robots.spatial(22), 6)
+    sp = robots.RvsSpineParams(layers, 1, 1, 0.05)
+    R = 64
+    q = synthetic.configs(rb, R, seed=0xC4A1)
+    rng = np.random.default_rng(11)
+    targets = (q + rng.normal(0, 2.5, q.shape)).astype(np.float32)
+    lo, hi = np.asarray(rb.limits)[:, 0], np.asarray(rb.limits)[:, 1]
+    targets = np.clip(targets, lo, hi).astype(np.float32)
+    new_slots = (R + np.arange(R * steps, dtype=np.int32)).reshape(R, steps)
+    new_slots[5, 2:] = -1                                              # a request that was given room for two steps only
+    out = {}
+    for fused in (True, False):
+        eng = engine.Engine(rb)
+        eng.set_obstacles(mn, mx, g, tol)
+        eng.store_reserve(R * (steps + 1))
+        d_root, _ = eng.store_distance(q, np.arange(R, dtype=np.int32))
+        if fused:
+            calls = eng.launch_count()
+            ql, nl, dn, st = eng.store_connect(np.arange(R, dtype=np.int32), targets, new_slots, sp)
+            assert eng.launch_count() - calls == 2 * steps
+        else:
+            ql = np.zeros((R, steps, layers, rb.num_dofs), np.float32)
+            nl, dn, st = np.full((R, steps), -1, np.int32), np.full((R, steps), -1, np.float32), np.zeros((R, steps), np.uint8)
+            cur, d_cur, alive = np.arange(R, dtype=np.int32), d_root.copy(), np.ones(R, bool)
+            for k in range(steps):
+                alive &= (new_slots[:, k] >= 0) & (d_cur > sp.d_crit)
+                who = np.nonzero(alive)[0]
+                if len(who) == 0:
+                    break
+                l, n_, _, s_ = eng.store_extend_spines(cur[who], targets[who], sp, gen2=True)
+                q_new = l[np.arange(len(who)), np.maximum(n_, 1) - 1]
+                d_, _ = eng.store_distance(q_new, new_slots[who, k])
+                ql[who, k], nl[who, k], dn[who, k], st[who, k] = l, n_, d_, s_
+                cur[who], d_cur[who] = new_slots[who, k], d_
+                alive[who[s_ != 1]] = False
+        cache = [eng.store_read(int(s)) for s in new_slots[nl >= 0][:40]]
+        out[fused] = (ql, nl, dn, st, cache)
+        eng.close()
+    (ql, nl, dn, st, cache), (ql0, nl0, dn0, st0, cache0) = out[True], out[False]
+    assert np.array_equal(nl, nl0) and np.array_equal(st[nl >= 0], st0[nl0 >= 0]) and np.array_equal(dn[nl >= 0], dn0[nl0 >= 0])
+    for r, k in zip(*np.nonzero(nl >= 0)):                              # (layers a spine did not write are undefined)
+        assert np.array_equal(ql[r, k, :max(1, nl[r, k])], ql0[r, k, :max(1, nl[r, k])]), (r, k)
+    assert (nl[5, 2:] == -1).all()
+    assert ((nl >= 0).sum(axis=1) >= 2).sum() >= 3 and (nl[:, 0] == -1).any()          # chains of several steps, and roots that never start
+    for a, b in zip(cache, cache0):
+        assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
 def test_oracle_spines_match_the_reference_planner_golden(ob):
     import os
     from conftest import ROOT
