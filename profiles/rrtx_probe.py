@@ -6,14 +6,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import scenes
+import bench_planning
 from rpmplv2_b200 import engine, planning, robots, synthetic
 from oracle import oracle_binding as ob            # CPU baseline leg only
 
 Q_GOAL = np.array([3.14159, 0.7854, -2.3562, 3.14159, 0, 3.14159], np.float32)
 for name, (rb, mn, mx, g, tol), S in (("xarm6 scenario1 (5 boxes)", scenes.xarm6_scenario1(), 3000), ("xarm6 200 boxes", (robots.xarm6(),) + tuple(synthetic.sweep_obstacles(200, "D2", r_min=0.55)), 3000)):
     smp = synthetic.configs(rb, S, seed=0x7272)
-    eng = engine.Engine(rb); eng.set_obstacles(mn, mx, g, tol)
-    row = dict(scene=name, samples=S)
+    eng = engine.Engine(rb)
+    sc = dict(obstacles=(mn, mx, g, tol), q_start=Q_GOAL, q_goal=Q_GOAL)
+    bench_planning._prune(eng, sc)                      # the reference re-draws random obstacles that hit the start / goal (apps/CommonFunctions.h:102-110)
+    mn, mx, g, tol = sc["obstacles"]
+    eng.set_obstacles(mn, mx, g, tol)
+    row = dict(scene=name, samples=S, obstacles=int(len(g)))
     base = None
     for mode, kw in (("one call per iteration, host neighbours", dict(one_call_per_iteration=1, device_index=0)),
                      ("three calls per iteration, host neighbours", dict(one_call_per_iteration=0, device_index=0)),
