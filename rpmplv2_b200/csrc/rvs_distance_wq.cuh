@@ -69,7 +69,7 @@ constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bi
 #define RVS_WQ_INTERVAL 128
 #endif
 #ifndef RVS_WQ_MINBLOCKS
-#define RVS_WQ_MINBLOCKS 7
+#define RVS_WQ_MINBLOCKS 6                        // 80 registers: with coherent warps 6 CTAs/SM without the spills of 72 registers beat 7 (profiles/r2)
 #endif
 #ifndef RVS_WQ_FLUSH
 #define RVS_WQ_FLUSH 2
