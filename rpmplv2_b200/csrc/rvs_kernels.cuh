@@ -553,6 +553,105 @@ __global__ void __launch_bounds__(kBlock) self_collision_edge_kernel(const KArgs
     for (int i = 0; i < n; i++) out[i] = q2[i];
 }
 
+// The same routine for a PLANNER-SIZED batch: one WARP per edge.  A lone thread walks up to five bubble iterations and then the EPS_STEP
+// marching, one FP64 forward kinematics each — 30 to 150 us of dependent instructions for a single edge.  Here the bubble iterations use
+// the warp-cooperative FK (lane k evaluates sincos(q_k)), rows of the enclosing-radii matrix and the four capsule distances are spread
+// over lanes, and the marching points — which do not depend on the verdicts — are laid out by lane 0 and tested 32 at a time, one per
+// lane; the first hit in marching order decides.  Every value is computed by the same instruction sequence as in
+// self_collision_edge_of(), so verdicts and truncated configurations are bit-identical (tests/test_gpu_parity.py).
+constexpr int kScWarps = 4;
+template <class F, class R>
+__global__ void __launch_bounds__(32 * kScWarps) self_collision_edge_warp_kernel(const KArgs a) {
+    constexpr int n = 6, W = 7;
+    __shared__ float s_sk[kScWarps][3 * W], s_Rm[kScWarps][n * W], s_delta[kScWarps][n], s_pts[kScWarps][33][n], s_dist[kScWarps][32];
+    const RobotDev *__restrict__ rb = a.robot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t e = int64_t(blockIdx.x) * kScWarps + warp;
+    if (e >= a.N) return;                                                       // (whole warps leave together)
+    float *sk = s_sk[warp], *Rm = s_Rm[warp], *delta = s_delta[warp];
+    float q1t[n], q2[n];
+    for (int i = 0; i < n; i++) { q1t[i] = a.q[e * n + i]; q2[i] = a.q2[e * n + i]; }
+    bool hit = false;
+    const bool active = rb->kind == RVS_ROBOT_XARM6 && rb->self_collision && rb->n == 6;
+    float step04 = 0.f, step05 = 0.f, step14 = 0.f, step15 = 0.f;
+    bool surely_free = !active;
+    if (active) {
+        for (int num_iter = 0;;) {                                              // xArm6.cpp:297-325
+            __syncwarp();
+            float mine[3 * W];
+            fk_skeleton_warp<F, float>(rb, q1t, mine);
+            if (lane == 0) for (int k = 0; k < 3 * W; k++) sk[k] = mine[k];
+            __syncwarp();
+            if (lane < n) { enclosing_radii_row<float>(rb, sk, lane, Rm + lane * W); delta[lane] = fabsf(q2[lane] - q1t[lane]); }
+            __syncwarp();
+            // lanes 0-3: one capsule distance each; lanes 4-7: phi2, phi4, phi5, phi6
+            float v = 0.f;
+            if (lane < 4) v = capsules_distance(rb, sk, lane >> 1, 4 + (lane & 1), a.eq_thr, a.max_dist);          // 0-4, 0-5, 1-4, 1-5
+            else if (lane < 8) v = dot_dyn(Rm + (lane == 4 ? 2 : lane - 1), W, delta, n);
+            const float d04 = __shfl_sync(0xffffffffu, v, 0), d05 = __shfl_sync(0xffffffffu, v, 1), d14 = __shfl_sync(0xffffffffu, v, 2), d15 = __shfl_sync(0xffffffffu, v, 3);
+            const float phi2 = __shfl_sync(0xffffffffu, v, 4), phi4 = __shfl_sync(0xffffffffu, v, 5), phi5 = __shfl_sync(0xffffffffu, v, 6), phi6 = __shfl_sync(0xffffffffu, v, 7);
+            const float m45 = phi4 < phi5 ? phi5 : phi4, m56 = phi5 < phi6 ? phi6 : phi5;
+            step04 = d04 / m45; step05 = d05 / m56; step14 = d14 / (phi2 + m45); step15 = d15 / (phi2 + m56);
+            const float sa = step05 < step04 ? step05 : step04, sb = step15 < step14 ? step15 : step14;
+            const float step = sb < sa ? sb : sa;
+            if (step > 1.f) { surely_free = true; break; }
+            if (++num_iter == 5 || step <= 0.f) break;
+            if (step > 0.f)
+                for (int i = 0; i < n; i++) q1t[i] = q1t[i] + step * (q2[i] - q1t[i]);
+        }
+    }
+    if (!surely_free) {
+        // marching (xArm6.cpp:327-362): q_m = q_{m-1} + (q2 - q_{m-1}) / dist * EPS_STEP until q2 is reached; pts[0] = q1_temp
+        const float D = coord_norm(q2, q1t, n), eps = rb->eps_step;
+        float (*pts)[n] = s_pts[warp];
+        float dist = D;
+        bool advanced = true;
+        if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = q1t[i];
+        while (advanced && !hit) {
+            int count = 0;
+            __syncwarp();
+            if (lane == 0) {
+                for (; count < 32 && advanced; count++) {
+                    const float *prev = pts[count];
+                    float *qn = pts[count + 1];
+                    if (dist > eps) { for (int i = 0; i < n; i++) qn[i] = prev[i] + (q2[i] - prev[i]) / dist * eps; }
+                    else { for (int i = 0; i < n; i++) qn[i] = q2[i]; advanced = false; }
+                    dist = coord_norm(q2, qn, n);
+                    s_dist[warp][count] = dist;
+                }
+            }
+            count = __shfl_sync(0xffffffffu, count, 0);
+            advanced = __shfl_sync(0xffffffffu, int(advanced), 0) != 0;
+            dist = __shfl_sync(0xffffffffu, dist, 0);
+            __syncwarp();
+            bool mine_hit = false;
+            if (lane < count) {
+                const float step_crit = 1.f - s_dist[warp][lane] / D;
+                float skm[3 * W];
+                fk_skeleton<F, float>(rb, pts[lane + 1], skm);
+                mine_hit = (!(step05 > step_crit) && capsules_distance(rb, skm, 0, 5, a.eq_thr, a.max_dist) < 0.f) ||
+                           (!(step15 > step_crit) && capsules_distance(rb, skm, 1, 5, a.eq_thr, a.max_dist) < 0.f) ||
+                           (!(step04 > step_crit) && capsules_distance(rb, skm, 0, 4, a.eq_thr, a.max_dist) < 0.f) ||
+                           (!(step14 > step_crit) && capsules_distance(rb, skm, 1, 4, a.eq_thr, a.max_dist) < 0.f);
+            }
+            const unsigned hb = __ballot_sync(0xffffffffu, mine_hit);
+            if (hb) {
+                const int f = __ffs(int(hb)) - 1;                               // first colliding point: q2 := the point before it
+                for (int i = 0; i < n; i++) q2[i] = pts[f][i];
+                hit = true;
+            } else if (advanced) {
+                __syncwarp();
+                if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = pts[count][i];      // next round starts where this one ended
+            }
+        }
+    }
+    if (lane != 0) return;
+    if (!a.d_c) { if (hit) a.verdict[e] = 0; return; }
+    a.verdict[e] = hit ? 1 : 0;
+    float *out = static_cast<float *>(a.d_c) + e * n;
+    for (int i = 0; i < n; i++) out[i] = q2[i];
+}
+
 template <class F>
 __global__ void __launch_bounds__(64) spine_kernel(const SpineArgs a) {
     const RobotDev *__restrict__ rb = a.robot;

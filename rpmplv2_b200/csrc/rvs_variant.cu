@@ -134,7 +134,9 @@ struct Variant {
     }
     static cudaError_t self_collision_edges(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
-        self_collision_edge_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
+        // planner-sized batches of xArm6 edges: one warp per edge (latency); sweeps: one thread per edge (throughput)
+        if (a.robot_n_hint == 6 && a.N <= 8192) self_collision_edge_warp_kernel<F, R><<<grid_for(a.N, kScWarps), 32 * kScWarps, 0, st>>>(a);
+        else self_collision_edge_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, 0, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t primitive(const KArgs &a, cudaStream_t st) {

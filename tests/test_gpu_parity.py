@@ -406,6 +406,34 @@ def test_large_batch_switches_do_not_change_any_result(ob, robot, M, dist, r_min
     assert 0 < base[3].mean() < 1 or robot != "xarm6"
 
 
+@pytest.mark.parametrize("eps,length", [(0.1, 0.3), (1.0, 3.0), (0.05, 6.0), (0.1, 0.0)])
+def test_warp_per_edge_self_collision_equals_the_thread_per_edge_kernel(ob, eps, length):
+    """xArm6::checkSelfCollision(q1, q2&) for planner-sized batches (one warp per edge: cooperative FK in the bubble iterations, the
+    marching points tested 32 at a time) against the one-thread-per-edge kernel that larger batches take, bit for bit — verdicts and
+    truncated configurations — and both against the oracle."""
+    rb = robots.xarm6()
+    eng = engine.Engine(rb)
+    eng.set_self_collision(True, eps)
+    E = 3000
+    q1, q2 = synthetic.edges(rb, 9000, max(length, 1e-3), seed=0x5E1F)
+    if length == 0.0:
+        q2 = q1.copy()                                                 # zero-length motions: the bubble steps are inf / NaN as in the reference
+    hit_w, out_w = eng.self_collision_edges(q1[:E], q2[:E])            # <= 8192 edges: warp kernel
+    hit_t, out_t = eng.self_collision_edges(q1, q2)                    # 9000 edges: thread kernel
+    assert np.array_equal(hit_w, hit_t[:E]) and same(out_w, out_t[:E]).all()
+    one_h, one_q = eng.self_collision_edges(q1[7:8], q2[7:8])
+    assert one_h[0] == hit_t[7] and same(one_q[0], out_t[7]).all()
+    o = ob.Oracle(rb)
+    o.set_self_collision(True, eps)
+    hit_o, out_o = o.self_collision_edges(q1[:E], q2[:E])
+    assert (hit_w != hit_o).mean() <= 0.005                            # FK last-ulp band, as in tests/test_robot_golden.py
+    agree = hit_w == hit_o
+    assert (np.abs(out_w[agree] - out_o[agree]).max(axis=1) <= 1e-5).mean() >= 0.995
+    if length >= 3.0:
+        assert 0 < hit_w.sum() < E
+    eng.close()
+
+
 def test_full_size_properties():
     """BASELINE sweep size (2^20 configurations x 1000 boxes): size-independent properties instead of an oracle run."""
     torch = pytest.importorskip("torch")
