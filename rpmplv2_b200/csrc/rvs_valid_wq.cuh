@@ -29,8 +29,11 @@ __host__ __device__ inline size_t vq_smem_bytes(int L) {
     return b;
 }
 
+#ifndef RVS_VQ_MINBLOCKS
+#define RVS_VQ_MINBLOCKS 5
+#endif
 template <class F, class R, int G, bool EDGE>
-__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? 5 : 3) valid_wq_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kWqBlock, sizeof(R) == 4 ? RVS_VQ_MINBLOCKS : 3) valid_wq_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char vq_smem[];
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n, n = L;
