@@ -52,8 +52,11 @@ template <> struct RobotScalars<double> {
 
 // ---- computeDistance (RealVectorSpace.cpp:318-392) ----------------------------------------------------------------
 // MODE: 0 MIN, 1 PROFILE, 2 FULL.  F = FK scalar, R = geometry scalar.
+#ifndef RVS_SEQ_MINBLOCKS
+#define RVS_SEQ_MINBLOCKS 1
+#endif
 template <class F, class R, int MODE>
-__global__ void __launch_bounds__(kBlock) distance_kernel(const KArgs a) {
+__global__ void __launch_bounds__(kBlock, sizeof(R) == 4 ? RVS_SEQ_MINBLOCKS : 1) distance_kernel(const KArgs a) {
     __shared__ ObstacleRec tile[kTileObstacles];
     const RobotDev *__restrict__ rb = a.robot;
     const int L = rb->n;
