@@ -216,8 +216,9 @@ int  rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *
  *   rvs_tree_radius   <- planning::rrtx::RRTx::findNeighbors (src/planners/rrtx/RRTx.cpp:424-452): every state within `radius` of the
  *                        query in ss->getNorm, in TREE ORDER, except index `exclude`; *count = number of hits (when it exceeds `capacity`
  *                        only the first `capacity` are written: call again with more room)
- * Trees are append-only arrays (rvs_tree_clear empties one); ids are dense from 0 per handle. */
+ * Trees are append-only arrays (rvs_tree_clear empties one, rvs_tree_release frees its memory and lets rvs_tree_create hand the id out again). */
 int  rvs_tree_create(rvs_handle h, int32_t *tree);
+int  rvs_tree_release(rvs_handle h, int32_t tree);
 int  rvs_tree_clear(rvs_handle h, int32_t tree);
 int  rvs_tree_size(rvs_handle h, int32_t tree);
 int  rvs_tree_append(rvs_handle h, int32_t tree, const float *q, int32_t count);

@@ -69,7 +69,7 @@ namespace rvsplan
 		if (!h) throw std::runtime_error("CudaNeighborIndex: NULL engine handle");
 		check(rvs_tree_create(h, &tree), "rvs_tree_create");
 	}
-	CudaNeighborIndex::~CudaNeighborIndex() { if (tree >= 0) rvs_tree_clear(engine, tree); }
+	CudaNeighborIndex::~CudaNeighborIndex() { if (tree >= 0) rvs_tree_release(engine, tree); }
 	void CudaNeighborIndex::check(int status, const char *what) const
 	{
 		if (status != RVS_OK) throw std::runtime_error(std::string(what) + ": " + rvs_last_error(engine));

@@ -89,7 +89,7 @@ struct rvs_engine {
     std::string err;
     // device-resident planner trees (rvs_tree_*): states of tree t at trees[t].d [cap][n]; the pointer / count tables the kernels read
     // are mirrored in d_tree_ptr / d_tree_cnt and refreshed lazily
-    struct DevTree { float *d = nullptr; int count = 0, cap = 0; };
+    struct DevTree { float *d = nullptr; int count = 0, cap = 0; bool released = false; };
     std::vector<DevTree> trees;
     const float **d_tree_ptr = nullptr;
     int32_t *d_tree_cnt = nullptr;
@@ -1416,14 +1416,26 @@ extern "C" {
 int rvs_tree_create(rvs_handle h, int32_t *tree) {
     RVS_TRY(enter(h));
     if (!tree) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL tree id");
+    for (size_t t = 0; t < h->trees.size(); t++)
+        if (h->trees[t].released) { h->trees[t].released = false; h->trees[t].count = 0; *tree = int32_t(t); return RVS_OK; }     // reuse a released id
     h->trees.emplace_back();
     h->tree_tab_dirty = true;
     *tree = int32_t(h->trees.size() - 1);
     return RVS_OK;
 }
+int rvs_tree_release(rvs_handle h, int32_t tree) {
+    RVS_TRY(enter(h));
+    if (tree < 0 || size_t(tree) >= h->trees.size() || h->trees[size_t(tree)].released) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
+    auto &t = h->trees[size_t(tree)];
+    RVS_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (t.d) RVS_CUDA(h, cudaFree(t.d));
+    t.d = nullptr; t.count = 0; t.cap = 0; t.released = true;
+    h->tree_tab_dirty = true;
+    return RVS_OK;
+}
 int rvs_tree_clear(rvs_handle h, int32_t tree) {
     RVS_TRY(enter(h));
-    if (tree < 0 || size_t(tree) >= h->trees.size()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
+    if (tree < 0 || size_t(tree) >= h->trees.size() || h->trees[size_t(tree)].released) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
     h->trees[size_t(tree)].count = 0;
     h->tree_tab_dirty = true;
     return RVS_OK;
@@ -1434,7 +1446,7 @@ int rvs_tree_size(rvs_handle h, int32_t tree) {
 }
 int rvs_tree_append(rvs_handle h, int32_t tree, const float *q, int32_t count) {
     RVS_TRY(enter(h));
-    if (tree < 0 || size_t(tree) >= h->trees.size() || count < 0 || (count > 0 && !q)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad tree append");
+    if (tree < 0 || size_t(tree) >= h->trees.size() || h->trees[size_t(tree)].released || count < 0 || (count > 0 && !q)) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad tree append");
     if (count == 0) return RVS_OK;
     auto &t = h->trees[size_t(tree)];
     const size_t row = size_t(h->h_robot.n) * sizeof(float);
@@ -1461,7 +1473,7 @@ int rvs_tree_nearest(rvs_handle h, const int32_t *trees, const float *queries, i
     if (h->trees.empty()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "no tree");
     if (trees)
         for (int k = 0; k < Q; k++)
-            if (trees[k] < 0 || size_t(trees[k]) >= h->trees.size()) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
+            if (trees[k] < 0 || size_t(trees[k]) >= h->trees.size() || h->trees[size_t(trees[k])].released) return fail(h, RVS_ERR_INVALID_ARGUMENT, "unknown tree");
     RVS_TRY(tree_tables(h));
     const size_t n = size_t(h->h_robot.n);
     begin_call(h, size_t(Q) * (n * 4 + 12) + 64);
@@ -1482,7 +1494,7 @@ int rvs_tree_nearest(rvs_handle h, const int32_t *trees, const float *queries, i
 int rvs_tree_radius(rvs_handle h, int32_t tree, const float *query, float radius, int32_t exclude, int32_t capacity, int32_t *idx, float *dist,
                     int32_t *count) {
     RVS_TRY(enter(h));
-    if (tree < 0 || size_t(tree) >= h->trees.size() || !query || !idx || !dist || !count || capacity < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad radius query");
+    if (tree < 0 || size_t(tree) >= h->trees.size() || h->trees[size_t(tree)].released || !query || !idx || !dist || !count || capacity < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "bad radius query");
     RVS_TRY(tree_tables(h));
     const size_t n = size_t(h->h_robot.n);
     begin_call(h, n * 4 + size_t(capacity) * 8 + 64);

@@ -69,6 +69,7 @@ SYMBOLS = {
     "rvs_get_self_collision": (ctypes.c_int, [_H, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_float)]),
     "rvs_tree_create": (ctypes.c_int, [_H, c_i32p]),
     "rvs_tree_clear": (ctypes.c_int, [_H, ctypes.c_int32]),
+    "rvs_tree_release": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_tree_size": (ctypes.c_int, [_H, ctypes.c_int32]),
     "rvs_tree_append": (ctypes.c_int, [_H, ctypes.c_int32, c_f32p, ctypes.c_int32]),
     "rvs_tree_nearest": (ctypes.c_int, [_H, c_i32p, c_f32p, ctypes.c_int32, c_i32p, c_f32p]),
@@ -444,6 +445,9 @@ class Engine:
 
     def tree_clear(self, tree: int) -> None:
         self._check(self._lib.rvs_tree_clear(self._h, tree))
+
+    def tree_release(self, tree: int) -> None:
+        self._check(self._lib.rvs_tree_release(self._h, tree))
 
     def tree_size(self, tree: int) -> int:
         return int(self._lib.rvs_tree_size(self._h, tree))

@@ -102,4 +102,10 @@ def test_tree_errors():
         eng.tree_append(t + 1, synthetic.configs(rb, 2))
     with pytest.raises(engine.RvsError):
         eng.tree_nearest(synthetic.configs(rb, 2), np.array([0, 5], np.int32))
+    # a released id is handed out again, empty; using it in between is an error
+    eng.tree_append(t, synthetic.configs(rb, 10))
+    eng.tree_release(t)
+    with pytest.raises(engine.RvsError):
+        eng.tree_append(t, synthetic.configs(rb, 2))
+    assert eng.tree_create() == t and eng.tree_size(t) == 0
     eng.close()
