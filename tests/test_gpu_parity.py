@@ -404,6 +404,16 @@ def test_large_batch_switches_do_not_change_any_result(ob, robot, M, dist, r_min
     assert np.abs(base[1][sample] - d_o).max() <= TOL32 and np.abs(base[2][sample] - p_o).max() <= TOL32
     assert (base[3][sample] != o.is_valid(q[sample])).sum() == 0
     assert 0 < base[3].mean() < 1 or robot != "xarm6"
+    # the other two arithmetic variants go through the same switches (F64: its own kernel instantiation, minima kept as doubles)
+    for prec in (robots.PREC_FAST32, robots.PREC_F64):
+        res = {}
+        for df, srt in ((1, 1), (0, 0)):
+            eng = make(rb, mn, mx, g, tol, prec)
+            eng.set_distance_field(bool(df)); eng.set_config_sort(bool(srt))
+            res[(df, srt)] = (*eng.distance(q[:120_000], robots.DIST_PROFILE)[:2], eng.is_valid(q[:120_000]))
+            eng.close()
+        for a, b in zip(res[(1, 1)], res[(0, 0)]):
+            assert same(a, b).all(), prec
 
 
 @pytest.mark.parametrize("eps,length", [(0.1, 0.3), (1.0, 3.0), (0.05, 6.0), (0.1, 0.0)])
