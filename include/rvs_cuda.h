@@ -40,6 +40,16 @@
  *   rvs_extend_spines                 <- RBTConnect::extendSpine + RGBTConnect::extendGenSpine over a set of
  *                                        targets (src/planners/rbt/RBTConnect.cpp:85-150,
  *                                        src/planners/rbt/RGBTConnect.cpp:73-118)
+ *   rvs_check_states / rvs_check_edges <- the two composite tests the planners write by hand: isValid && !robot->checkSelfCollision
+ *                                        (src/planners/rrt/RRTConnect.cpp:13-15, :100; trajectory/MotionValidity.cpp:42)
+ *   rvs_store_connect                 <- RGBTConnect::connectGenSpine's loop / RBTConnect::connectSpine
+ *                                        (src/planners/rbt/RGBTConnect.cpp:120-150, RBTConnect.cpp:152-180) as one call
+ *   rvs_env_set_random_directions     <- Environment::moveRandomDirections' state: accelerations, ground_included, srand(seed)
+ *                                        (src/environments/Environment.cpp:169-190, 289-333)
+ *   rvs_tree_create / append /        <- base::Tree's states and getNearestState (src/state_spaces/Tree.cpp:35-50, :90-103),
+ *   nearest / radius / release           RRTx::findNeighbors (src/planners/rrtx/RRTx.cpp:424-452), resident in HBM
+ *   rvs_set_distance_field /          <- (no reference counterpart) result-neutral switches of the large-batch path
+ *   rvs_set_config_sort / rvs_set_culling
  *
  * Conventions
  *  - plain pointers and sizes only; no C++ / torch types; all functions return an rvs_status (0 = ok);
