@@ -219,6 +219,9 @@ int  rvs_get_self_collision(rvs_handle h, int32_t *enabled, float *eps_step);
  * (conservative).  hit = 0 / q2_out = q2 when the check is off or the robot is not an xArm6. */
 int  rvs_self_collision_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *hit, float *q2_out);
 int  rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_hit, float *d_q2_out);
+/* isValid(q1, q2) and robot->checkSelfCollision(q1, q2) in ONE call, reported apart: a caller whose control flow depends on WHICH test failed
+ * (RRTx::chooseParent re-seats q_new on a self hit, src/planners/rrtx/RRTx.cpp:466-468) gets both verdicts with one synchronisation. */
+int  rvs_check_edges_detailed(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *obstacle_ok, uint8_t *self_hit, float *q2_out);
 /* Device-resident planner trees: the states of base::Tree kept as a [count][n] array in HBM, answering
  *   rvs_tree_nearest  <- base::Tree::getNearestState (src/state_spaces/Tree.cpp:35-50; nanoflann kd-tree, exact 1-NN in the squared
  *                        L2 metric): Q queries in ONE launch, query k against tree trees[k] (NULL = tree 0) -> idx[k] (-1 for an empty

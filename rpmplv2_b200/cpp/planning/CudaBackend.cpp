@@ -38,8 +38,7 @@ namespace rvsplan
 
 	void CudaBackend::isValidEdgesDetailed(const float *q1, const float *q2, int E, uint8_t *obstacle_ok, uint8_t *self_hit, float *q2_out)
 	{
-		check(rvs_is_valid_edges(engine, q1, q2, E, obstacle_ok), "rvs_is_valid_edges");
-		check(rvs_self_collision_edges(engine, q1, q2, E, self_hit, q2_out), "rvs_self_collision_edges");
+		check(rvs_check_edges_detailed(engine, q1, q2, E, obstacle_ok, self_hit, q2_out), "rvs_check_edges_detailed");
 	}
 
 	void CudaBackend::distanceToSlots(const float *q, int N, const int32_t *slots, float *d_c)

@@ -143,7 +143,7 @@ namespace rvsplan
 			if (self)
 			{
 				backend.isValidEdgesDetailed(e1.data(), e2.data(), K - first, &up_ok[size_t(first)], &up_self[size_t(first)], &up_q2[size_t(first) * size_t(n)]);
-				stats.backend_calls += 2; stats.edges_checked += K - first;
+				stats.backend_calls++; stats.edges_checked += K - first;
 				e1.clear(); e2.clear();
 			}
 			else

@@ -907,6 +907,31 @@ int rvs_check_edges(rvs_handle h, const float *q1, const float *q2, int64_t E, u
     RVS_TRY(d2h(h, valid, B_VERD, size_t(E)));
     return finish(h);
 }
+// Both halves of the edge test in ONE call, reported apart (RRTx::chooseParent needs to know WHICH one failed, RRTx.cpp:466-468):
+// obstacle_ok[e] = isValid(q1_e, q2_e); self_hit[e] / q2_out[e] as rvs_self_collision_edges.
+int rvs_check_edges_detailed(rvs_handle h, const float *q1, const float *q2, int64_t E, uint8_t *obstacle_ok, uint8_t *self_hit, float *q2_out) {
+    RVS_TRY(enter(h));
+    if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "self-collision runs on REF32 / FAST32 handles");
+    if (E < 0) return fail(h, RVS_ERR_INVALID_ARGUMENT, "E < 0");
+    if (E == 0) return RVS_OK;
+    if (!q1 || !q2 || !obstacle_ok || !self_hit || !q2_out) return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer");
+    const size_t bytes = size_t(E) * size_t(h->h_robot.n) * sizeof(float);
+    begin_call(h, 3 * bytes + 2 * size_t(E) + 64);
+    RVS_TRY(h2d(h, B_Q, q1, bytes));
+    RVS_TRY(h2d(h, B_Q2, q2, bytes));
+    RVS_TRY(reserve(h, B_VERD, 2 * size_t(E)));
+    RVS_TRY(reserve(h, B_DC, bytes));
+    const float *d_q1 = static_cast<const float *>(h->buf[B_Q].p), *d_q2 = static_cast<const float *>(h->buf[B_Q2].p);
+    uint8_t *d_ok = static_cast<uint8_t *>(h->buf[B_VERD].p), *d_hit = d_ok + E;
+    RVS_TRY(edges_dev_impl(h, d_q1, d_q2, E, d_ok));
+    KArgs a = base_args(h, d_q1, E);
+    a.q2 = d_q2; a.verdict = d_hit; a.d_c = h->buf[B_DC].p;
+    RVS_TRY(launched(h, h->lt.self_collision_edges(a, h->stream), "self collision edge kernel launch"));
+    RVS_TRY(d2h(h, obstacle_ok, B_VERD, size_t(E)));
+    RVS_TRY(d2h_from(h, self_hit, d_hit, size_t(E)));
+    RVS_TRY(d2h(h, q2_out, B_DC, bytes));
+    return finish(h);
+}
 int rvs_self_collision_edges_dev(rvs_handle h, const float *d_q1, const float *d_q2, int64_t E, uint8_t *d_hit, float *d_q2_out) {
     RVS_TRY(enter(h));
     if (h->prm.precision == RVS_PREC_F64) return fail(h, RVS_ERR_UNSUPPORTED, "self-collision runs on REF32 / FAST32 handles");

@@ -77,6 +77,7 @@ SYMBOLS = {
     "rvs_check_states": (ctypes.c_int, [_H, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_check_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p]),
     "rvs_self_collision_edges": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p, c_f32p]),
+    "rvs_check_edges_detailed": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_int64, c_u8p, c_u8p, c_f32p]),
     "rvs_self_collision_edges_dev": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p]),
     "rvs_extend_spines": (ctypes.c_int, [_H, c_f32p, c_f32p, ctypes.c_float, c_f32p, c_f32p, ctypes.c_int32,
                                          ctypes.POINTER(RvsSpineParams), c_f32p, c_f32p, c_u8p]),
@@ -470,6 +471,13 @@ class Engine:
             if cnt.value <= capacity:
                 return idx[:cnt.value].copy(), dist[:cnt.value].copy()
             capacity = int(cnt.value)
+
+    def check_edges_detailed(self, q1, q2):
+        """isValid(q1,q2) and checkSelfCollision(q1,q2) in one call, reported apart -> (obstacle_ok[E] bool, self_hit[E] bool, q2 after the call)."""
+        q1, q2 = _f32(q1, (-1, self.n)), _f32(q2, (-1, self.n))
+        ok, hit, out = np.empty(q1.shape[0], np.uint8), np.empty(q1.shape[0], np.uint8), np.empty_like(q2)
+        self._check(self._lib.rvs_check_edges_detailed(self._h, _p(q1, c_f32p), _p(q2, c_f32p), q1.shape[0], _p(ok, c_u8p), _p(hit, c_u8p), _p(out, c_f32p)))
+        return ok.astype(bool), hit.astype(bool), out
 
     def check_states(self, q) -> np.ndarray:
         """isValid(q) && !robot->checkSelfCollision(q) in one call (RRTConnect.cpp:13-15, MotionValidity.cpp:42)."""

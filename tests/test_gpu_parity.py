@@ -431,6 +431,12 @@ def test_warp_per_edge_self_collision_equals_the_thread_per_edge_kernel(ob, eps,
     hit_w, out_w = eng.self_collision_edges(q1[:E], q2[:E])            # <= 8192 edges: warp kernel
     hit_t, out_t = eng.self_collision_edges(q1, q2)                    # 9000 edges: thread kernel
     assert np.array_equal(hit_w, hit_t[:E]) and same(out_w, out_t[:E]).all()
+    # rvs_check_edges_detailed = the two separate calls in one
+    mn, mx, g, tol = synthetic.sweep_obstacles(40, "D2")
+    eng.set_obstacles(mn, mx, g, tol)
+    ok_d, hit_d, out_d = eng.check_edges_detailed(q1[:E], q2[:E])
+    assert np.array_equal(ok_d, eng.is_valid_edges(q1[:E], q2[:E]).astype(bool)) and np.array_equal(hit_d, hit_w.astype(bool)) and same(out_d, out_w).all()
+    assert np.array_equal(eng.check_edges(q1[:E], q2[:E]).astype(bool), ok_d & ~hit_d)
     one_h, one_q = eng.self_collision_edges(q1[7:8], q2[7:8])
     assert one_h[0] == hit_t[7] and same(one_q[0], out_t[7]).all()
     o = ob.Oracle(rb)
