@@ -270,6 +270,38 @@ def run_reference(args, rank, world):
                       "gpu_launches": 0}))
 
 
+# ---- BASELINE.json's second metric: planning time next to the CPU arm, same run -------------------------------------------------------
+def planning_summary(device: int):
+    """`planning time vs CPU` for BASELINE configs 1-4, bounded to ~1 minute: 64 planner runs per shipped scene (bench_planning.py: all 64 in one
+    lockstep pool on the GPU, single runs on the GPU, single runs on ONE host thread — the reference's execution model —, the 64 runs over all
+    host threads; the CPU arm is the same planner code over the oracle port: cpu_baseline leg) and the DRGBT-shaped replanning loop of
+    bench_drgbt.py per 50 ms iteration.  Config 2's RGBMT* and DRGBT's own bookkeeping are not restated: RGBT-Connect / the iteration's
+    state-space calls stand in.  A reported baseline, not the target."""
+    import bench_drgbt
+    import bench_planning
+    rows = []
+    try:
+        for r in bench_planning.run(64, device=device, cpu=True, max_time=10.0, skip="random obstacles"):
+            rows.append({"config": r["scenario"], "planner": r["planner"], "runs": r["runs"], "success": r["success"],
+                         "gpu_lockstep_ms_per_run": r["gpu_lockstep"]["per_run_ms"], "gpu_single_run_ms": r["gpu_single"]["per_run_ms"],
+                         "cpu_1thread_ms_per_run": r["cpu_1thread"]["per_run_ms"], "cpu_all_threads_ms_per_run": r["cpu_all"]["per_run_ms"],
+                         "cpu_cores": r["cpu_all"]["cores"], "cpu_kind": "port (same planner code over the oracle)",
+                         "identical_runs_gpu_vs_cpu": r["identical_runs_gpu_vs_cpu"]})
+        # the same scenes with 1024 runs per pool: the batch size at which the lockstep pool is meant to be used
+        for row, r in zip(rows, bench_planning.run(1024, device=device, cpu=True, max_time=10.0, skip="random obstacles")):
+            row["p1024"] = {"gpu_lockstep_ms_per_run": r["gpu_lockstep"]["per_run_ms"], "cpu_all_threads_ms_per_run": r["cpu_all"]["per_run_ms"],
+                            "success": r["success"], "identical_runs_gpu_vs_cpu": r["identical_runs_gpu_vs_cpu"]}
+        d = bench_drgbt.run(iters=200, obstacles=5, cpu=True, gpu=True, device=device)
+        g_arm, c_arm = d["arms"][0], d["arms"][1]
+        rows.append({"config": "spatial_22dof DRGBT-shaped replanning loop, 5 moving obstacles (bench_drgbt.py)", "iterations": g_arm["iterations"],
+                     "gpu_iteration_ms_median": g_arm["iter_ms"]["median"], "gpu_iteration_ms_p95": g_arm["iter_ms"]["p95"],
+                     "cpu_1thread_iteration_ms_median": c_arm["iter_ms"]["median"], "cpu_1thread_iteration_ms_p95": c_arm["iter_ms"]["p95"],
+                     "iterations_within_50ms": {"gpu": g_arm["within_50ms"], "cpu": c_arm["within_50ms"]}, "same_run": d.get("same_run")})
+    except Exception as e:                                   # the summary must never cost the headline line
+        rows.append({"error": repr(e)})
+    return rows
+
+
 # ---- GPU arm -------------------------------------------------------------------------------------------------------------------------
 def roofline(eng, rb, prec, precision_name, N, avg_launch_s, pairs_per_launch, work_per_launch, peak32, peak64, clocks, no_cull):
     """Hardware fraction of the dominant kernel.  The kernel is bound by instruction ISSUE (predicated FP32 compares / selects on the ALU
@@ -341,7 +373,7 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--precision", default="ref32", choices=["ref32", "fast32", "f64"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the `workloads` points and the isValid figure")
+    ap.add_argument("--no-extras", action="store_true", help="skip the `workloads` points, the isValid figure and the planning-time summary")
     ap.add_argument("--no-cull", action="store_true", help="sequential one-thread-per-configuration kernel (no broad phase)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -507,6 +539,9 @@ def main():
         del d_v
         extra = extra_workloads(eng, torch, dev, stream, rb, odt)
         eng.set_obstacles(mn, mx, g, tol)
+    planning_rows = None
+    if world == 1 and not args.no_extras and not args.no_cpu_baseline and args.precision == "ref32" and not args.no_cull:
+        planning_rows = planning_summary(local)
 
     # ---- reductions across ranks: time = max, pairs = sum ----
     red = torch.tensor([t_rank, t_e2e, sum(ms_compute) * 1e-3, sum(ms_gather) * 1e-3], dtype=torch.float64, device=dev)
@@ -538,6 +573,8 @@ def main():
             "fma_peak_tflops": {"fp32": peak32, "fp64": peak64, "source": "FFMA / DFMA register microbenchmark measured in this run (rvs_measure_fma_peak)"},
             "clocks": clocks,
         }
+        if planning_rows is not None:
+            out["planning_time_vs_cpu"] = planning_rows
         if strong:
             gb = float(N_STRONG) * esz * (1 + L) * (world - 1) / max(world, 1) / 1e9
             out["strong_scaling"] = {"configs_total": N_STRONG, "compute_ms_per_step": 1e3 * t_compute_all / K, "gather_ms_per_step": 1e3 * t_gather_all / K,

@@ -127,6 +127,41 @@ def run_loop(arm: Arm, rb, iters: int, seed: int):
                 final_obstacle_checksum=float(np.asarray(arm.env_get()[0], np.float64).sum()))
 
 
+def run(iters: int = 300, obstacles: int = 5, seed: int = 4, cpu: bool = True, gpu: bool = True, device: int = 0) -> dict:
+    rb = robots.spatial(22)
+    sc = scene(obstacles, seed)
+    ep = env_params("light_directions", ws_center=WS_CENTER, ws_radius=WS_RADIUS, base_radius=0.3, robot_max_vel=ROBOT_MAX_VEL)
+    cfg = planning.default_config(planning.RGBT_CONNECT, max_planning_time=MAX_ITER_TIME * 20)
+    rows = []
+    if gpu:
+        from rpmplv2_b200.engine import Engine
+        eng = Engine(rb, device=device)
+        eng.env_set(ep, **sc)
+        arm = Arm("RealVectorSpaceCUDA (B200)", eng, lambda a, b, K, dt: eng.motion_validity(a, b, K, dt, commit_edge=0),
+                  lambda qs, qg, s: planning.solve_batch(eng, cfg, qs, qg, seeds=[s])[0][0], eng.env_get)
+        run_loop(arm, rb, 20, seed)                                                               # warm-up: allocations, module load
+        eng.env_set(ep, **sc)
+        launches = eng.launch_count()
+        row = run_loop(arm, rb, iters, seed)
+        row["kernel_launches_per_iteration"] = (eng.launch_count() - launches) / row["iterations"]
+        rows.append(row)
+        eng.close()
+    if cpu:
+        from oracle import oracle_binding as ob                                                   # CPU baseline leg only
+        from oracle.oracle_space import OracleSpace
+        o = ob.Oracle(rb, robots.default_params())
+        o.env_set(ep, **sc)
+        arm = Arm("RealVectorSpace (CPU oracle port, 1 thread)", OracleSpace(o), lambda a, b, K, dt: o.motion_validity(a, b, K, dt, commit_edge=0),
+                  lambda qs, qg, s: ob.plan_solve_batch(o, cfg, qs, qg, seeds=[s])[0][0], o.env_get)
+        rows.append(run_loop(arm, rb, iters, seed))
+    out = dict(bench="drgbt_iteration", config="spatial_22dof scenario_random_obstacles, light_directions, %d obstacles + ground" % obstacles,
+               max_iter_time_ms=1e3 * MAX_ITER_TIME, arms=rows)
+    if len(rows) == 2:
+        out["iteration_speedup_median"] = rows[1]["iter_ms"]["median"] / rows[0]["iter_ms"]["median"]
+        out["same_run"] = rows[0]["final_obstacle_checksum"] == rows[1]["final_obstacle_checksum"] and rows[0]["iterations"] == rows[1]["iterations"]
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=300)
@@ -135,38 +170,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-gpu", action="store_true")
     args = ap.parse_args()
-    rb = robots.spatial(22)
-    sc = scene(args.obstacles, args.seed)
-    ep = env_params("light_directions", ws_center=WS_CENTER, ws_radius=WS_RADIUS, base_radius=0.3, robot_max_vel=ROBOT_MAX_VEL)
-    cfg = planning.default_config(planning.RGBT_CONNECT, max_planning_time=MAX_ITER_TIME * 20)
-    rows = []
-    if not args.no_gpu:
-        from rpmplv2_b200.engine import Engine
-        eng = Engine(rb)
-        eng.env_set(ep, **sc)
-        arm = Arm("RealVectorSpaceCUDA (B200)", eng, lambda a, b, K, dt: eng.motion_validity(a, b, K, dt, commit_edge=0),
-                  lambda qs, qg, s: planning.solve_batch(eng, cfg, qs, qg, seeds=[s])[0][0], eng.env_get)
-        run_loop(arm, rb, 20, args.seed)                                                          # warm-up: allocations, module load
-        eng.env_set(ep, **sc)
-        launches = eng.launch_count()
-        row = run_loop(arm, rb, args.iters, args.seed)
-        row["kernel_launches_per_iteration"] = (eng.launch_count() - launches) / row["iterations"]
-        rows.append(row)
-        eng.close()
-    if not args.no_cpu:
-        from oracle import oracle_binding as ob                                                   # CPU baseline leg only
-        from oracle.oracle_space import OracleSpace
-        o = ob.Oracle(rb, robots.default_params())
-        o.env_set(ep, **sc)
-        arm = Arm("RealVectorSpace (CPU oracle port, 1 thread)", OracleSpace(o), lambda a, b, K, dt: o.motion_validity(a, b, K, dt, commit_edge=0),
-                  lambda qs, qg, s: ob.plan_solve_batch(o, cfg, qs, qg, seeds=[s])[0][0], o.env_get)
-        rows.append(run_loop(arm, rb, args.iters, args.seed))
-    out = dict(bench="drgbt_iteration", config="spatial_22dof scenario_random_obstacles, light_directions, %d obstacles + ground" % args.obstacles,
-               max_iter_time_ms=1e3 * MAX_ITER_TIME, arms=rows)
-    if len(rows) == 2:
-        out["iteration_speedup_median"] = rows[1]["iter_ms"]["median"] / rows[0]["iter_ms"]["median"]
-        out["same_run"] = rows[0]["final_obstacle_checksum"] == rows[1]["final_obstacle_checksum"] and rows[0]["iterations"] == rows[1]["iterations"]
-    print(json.dumps(out))
+    print(json.dumps(run(args.iters, args.obstacles, args.seed, cpu=not args.no_cpu, gpu=not args.no_gpu)))
 
 
 if __name__ == "__main__":
