@@ -11,8 +11,9 @@
  * Plain C: pointers and sizes only, status ints, no exception crosses the boundary.
  *
  * Environment switches (read per call): RVS_PLAN_THREADS = host threads that resume the runs between backend calls;
- * RVS_PLAN_CONNECT_CHUNK = steps of connectSpine / connectGenSpine's loop sent to the engine as one rvs_store_connect call (default 2;
- * 0 = one spine call and one distance call per step, the round-1 behaviour; runs are identical either way);
+ * RVS_PLAN_CONNECT_CHUNK = K > 0: K steps of connectSpine / connectGenSpine's loop go to the engine as one rvs_store_connect call (default 0 =
+ * one spine call and one distance call per step; runs are identical either way, and on the shipped scenes the chain does not pay);
+ * RVS_PLAN_PROFILE = print the pool's time split (gather / backend / scatter + resume) to stderr;
  * RVS_PLAN_RNG=libc = draw random states from std::rand() after srand(seed), one call per coordinate like Eigen::VectorXf::Random —
  * a SINGLE run (P = 1) then follows the reference planner's own random stream and reproduces its run state by state
  * (tests/test_planners.py checks exactly that against the reference's compiled solve() loops). Default: a counter-based stream

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <functional>
 #include <stdexcept>
@@ -519,11 +520,16 @@ namespace rvsplan
 		const size_t layer_stride = size_t(cfg.kind == PlannerKind::RBTConnect ? 1 : cfg.spine.num_layers) * n;
 		SpineParams sp = cfg.spine;
 		if (cfg.kind == PlannerKind::RBTConnect) sp.num_layers = 1;
+		double t_gather = 0, t_backend = 0, t_resume = 0, t_connect = 0;
+		const bool profile = std::getenv("RVS_PLAN_PROFILE") != nullptr;
+		auto now = [] { return Clock::now(); };
+		auto secs = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
 		while (true)
 		{
 			bool any = false;
 			for (int kind = Request::VALID; kind <= Request::CONNECT; kind++)
 			{
+				const auto tg0 = now();
 				who.clear(); q1.clear(); q2.clear(); sl.clear();
 				int total = 0;
 				for (int p = 0; p < P; p++)
@@ -537,6 +543,7 @@ namespace rvsplan
 					if (kind == Request::DISTANCE || kind == Request::SPINES) sl.insert(sl.end(), r.slots.begin(), r.slots.begin() + r.count);
 				}
 				if (who.empty()) continue;
+				t_gather += secs(tg0, now());
 				if (kind == Request::CONNECT)
 				{
 					// every run's chain in one backend call: R requests x the longest chain asked for (shorter ones are padded with -1)
@@ -559,7 +566,10 @@ namespace rvsplan
 						roots[size_t(i)] = r.slots[0]; root_d[size_t(i)] = r.d[0];
 						for (int k = 0; k < r.steps; k++) fresh[size_t(i) * steps + k] = r.slots[size_t(1 + k)];
 					}
+					const auto tc0 = now();
 					backend.connectGenSpines(roots.data(), root_d.data(), q1.data(), fresh.data(), R, steps, sp, layers.data(), nl.data(), d_new.data(), st.data());
+					const auto tc1 = now();
+					t_backend += secs(tc0, tc1); t_connect += secs(tc0, tc1);
 					for (int i = 0; i < R; i++)
 					{
 						Request &r = runs[size_t(who[size_t(i)])]->req;
@@ -572,6 +582,7 @@ namespace rvsplan
 						runs[size_t(who[size_t(i)])]->res.rounds++;
 					}
 					crew.run(R, [&](int i) { runs[size_t(who[size_t(i)])]->resume_at.resume(); });
+					t_resume += secs(tc1, now());
 					continue;
 				}
 				any = true;
@@ -581,6 +592,7 @@ namespace rvsplan
 					slot_cap = std::max(256, 2 * slots.used());
 					backend.reserveSlots(slot_cap);
 				}
+				const auto tb0 = now();
 				switch (kind)
 				{
 					case Request::VALID:
@@ -601,6 +613,8 @@ namespace rvsplan
 						backend.extendGenSpines(sl.data(), q1.data(), total, sp, true, q_layers.data(), n_layers.data(), d.data(), flags.data());
 						break;
 				}
+				const auto tr0 = now();
+				t_backend += secs(tb0, tr0);
 				size_t off = 0;
 				for (int p : who)
 				{
@@ -619,10 +633,12 @@ namespace rvsplan
 				}
 				// resume after the scatter: a resumed run overwrites its request with the next one (possibly of a kind served later in this round)
 				crew.run(int(who.size()), [&](int i) { runs[size_t(who[size_t(i)])]->resume_at.resume(); });
+				t_resume += secs(tr0, now());
 			}
 			if (!any) break;
 			num_rounds++;
 		}
+		if (profile) std::fprintf(stderr, "[rvsplan] P=%d rounds=%lld calls=%lld gather %.1f ms backend %.1f ms (connect chains %.1f ms) scatter+resume %.1f ms total %.1f ms\n", P, (long long)num_rounds, (long long)num_calls, 1e3 * t_gather, 1e3 * t_backend, 1e3 * t_connect, 1e3 * t_resume, 1e3 * secs(t0, now()));
 		std::vector<PlannerResult> out;
 		out.reserve(size_t(P));
 		for (int p = 0; p < P; p++)

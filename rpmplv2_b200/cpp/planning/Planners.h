@@ -50,8 +50,10 @@ namespace rvsplan
 		float delta = 3.14159f;              // RBTConnectConfig::DELTA
 		int num_spines = 7;                  // RBTConnectConfig::NUM_SPINES
 		SpineParams spine;                   // D_CRIT, NUM_ITER_SPINE, USE_EXPANDED_BUBBLE, NUM_LAYERS (1 for RBT-Connect)
-		int connect_chunk = 2;               // steps of connectSpine / connectGenSpine's loop per backend query (0: one spine + one distance query per step).
-		                                     // Measured (profiles/r2): the loop rarely runs more than two steps on the shipped scenes, so longer chains only add idle launches
+		int connect_chunk = 0;               // > 0: that many steps of connectSpine / connectGenSpine's loop per backend query (Request::CONNECT, one
+		                                     // rvs_store_connect call on the CUDA backend); 0: one spine query + one distance query per step.
+		                                     // Off by default: on the shipped scenes the loop seldom makes a second step, so a chain saves no round
+		                                     // and its idle launches cost (measured, profiles/r2: 1024 lockstep xArm6 runs 0.65 -> 1.14 s with 2)
 		bool keep_trees = false;             // return both trees with the result (RBTConnect::outputPlannerData's `*trees[0]`, `*trees[1]`)
 	};
 

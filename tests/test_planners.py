@@ -160,6 +160,20 @@ def test_oracle_backed_planners_reproduce_the_reference_planner_runs(ob, monkeyp
     assert res[0]["success"] and not _same_run(res[0], gold["xarm6_k2_s1_counts"], gold["xarm6_k2_s1_path"])
 
 
+@pytest.mark.parametrize("chunk", [1, 4])
+def test_connect_chains_do_not_change_a_run(ob, monkeypatch, chunk):
+    """Request::CONNECT (RVS_PLAN_CONNECT_CHUNK steps of connectSpine / connectGenSpine's loop per query) against the golden runs of the
+    reference's own planners: same iterations, states and paths as with one query per step."""
+    mod, gold = _plan_golden()
+    monkeypatch.setenv("RVS_PLAN_RNG", "libc")
+    monkeypatch.setenv("RVS_PLAN_CONNECT_CHUNK", str(chunk))
+    for name in mod.SCENARIOS:
+        o, _, qs, qg = _oracle(ob, name)
+        for kind in (planning.RBT_CONNECT, planning.RGBT_CONNECT):
+            res, _ = ob.plan_solve_batch(o, mod.config(kind), qs, qg, seeds=[2], max_path=mod.MAX_PATH)
+            assert _same_run(res[0], gold[f"{name}_k{kind}_s2_counts"], gold[f"{name}_k{kind}_s2_path"]), (name, kind, chunk)
+
+
 def test_oracle_backed_planners_reproduce_the_compiled_reference_on_fresh_runs(ob, monkeypatch):
     """Same comparison against oracle/_ref/librvs_ref.so itself: other seeds and non-default parameters (plain bubble, 3 spine
     iterations, 3 layers, a coarser EPS_STEP), and the invalid-start rule."""
@@ -230,6 +244,23 @@ def test_planner_log_with_trees_matches_the_reference_planners_own_log(ob, monke
         # everything but the space name and the wall clock is the same text up to number formatting
         head = lambda s: [l for l in s.splitlines()[:8] if not l.startswith(("Space Type", "\t Planning time"))]
         assert head(text) == head(ref_text)
+
+
+@pytest.mark.gpu
+def test_gpu_connect_chains_give_the_same_runs(monkeypatch):
+    """The same planner batch with and without rvs_store_connect chains (RVS_PLAN_CONNECT_CHUNK): identical runs."""
+    fn, qs, qg = SCENARIOS["xarm6"]
+    rb, mn, mx, g, tol = fn()
+    eng = engine.Engine(rb)
+    eng.set_obstacles(mn, mx, g, tol)
+    out = {}
+    for chunk in (0, 3):
+        monkeypatch.setenv("RVS_PLAN_CONNECT_CHUNK", str(chunk))
+        res, st = planning.solve_batch(eng, planning.default_config(planning.RGBT_CONNECT), np.asarray(qs, np.float32), np.asarray(qg, np.float32), seeds=np.arange(24))
+        out[chunk] = res
+    for a, b in zip(out[0], out[3]):
+        assert a["success"] and a["iterations"] == b["iterations"] and a["states"] == b["states"] and np.array_equal(a["path"], b["path"])
+    eng.close()
 
 
 @pytest.mark.gpu
