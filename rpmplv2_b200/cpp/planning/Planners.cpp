@@ -520,7 +520,8 @@ namespace rvsplan
 		const size_t layer_stride = size_t(cfg.kind == PlannerKind::RBTConnect ? 1 : cfg.spine.num_layers) * n;
 		SpineParams sp = cfg.spine;
 		if (cfg.kind == PlannerKind::RBTConnect) sp.num_layers = 1;
-		double t_gather = 0, t_backend = 0, t_resume = 0, t_connect = 0;
+		double t_gather = 0, t_backend = 0, t_resume = 0, t_connect = 0, t_kind[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+		long long n_kind[8] = {0, 0, 0, 0, 0, 0, 0, 0}, items_kind[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 		const bool profile = std::getenv("RVS_PLAN_PROFILE") != nullptr;
 		auto now = [] { return Clock::now(); };
 		auto secs = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
@@ -614,7 +615,7 @@ namespace rvsplan
 						break;
 				}
 				const auto tr0 = now();
-				t_backend += secs(tb0, tr0);
+				t_backend += secs(tb0, tr0); t_kind[kind] += secs(tb0, tr0); n_kind[kind]++; items_kind[kind] += total;
 				size_t off = 0;
 				for (int p : who)
 				{
@@ -639,6 +640,9 @@ namespace rvsplan
 			num_rounds++;
 		}
 		if (profile) std::fprintf(stderr, "[rvsplan] P=%d rounds=%lld calls=%lld gather %.1f ms backend %.1f ms (connect chains %.1f ms) scatter+resume %.1f ms total %.1f ms\n", P, (long long)num_rounds, (long long)num_calls, 1e3 * t_gather, 1e3 * t_backend, 1e3 * t_connect, 1e3 * t_resume, 1e3 * secs(t0, now()));
+		if (profile)
+			for (int k = Request::VALID; k <= Request::SPINES; k++)
+				std::fprintf(stderr, "[rvsplan]   kind %d (1 valid, 2 edges, 3 distance, 4 spines): %lld calls, %lld items, %.1f ms (%.1f us per call)\n", k, n_kind[k], items_kind[k], 1e3 * t_kind[k], n_kind[k] ? 1e6 * t_kind[k] / double(n_kind[k]) : 0.0);
 		std::vector<PlannerResult> out;
 		out.reserve(size_t(P));
 		for (int p = 0; p < P; p++)

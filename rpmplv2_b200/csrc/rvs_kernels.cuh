@@ -563,91 +563,109 @@ __global__ void __launch_bounds__(kBlock) self_collision_edge_kernel(const KArgs
 // lane; the first hit in marching order decides.  Every value is computed by the same instruction sequence as in
 // self_collision_edge_of(), so verdicts and truncated configurations are bit-identical (tests/test_gpu_parity.py).
 constexpr int kScWarps = 4;
-template <class F, class R>
-__global__ void __launch_bounds__(32 * kScWarps) self_collision_edge_warp_kernel(const KArgs a) {
+// self_collision_steps() by a whole warp: lanes 0-3 take one capsule distance each, lanes 4-7 one phi each; same arithmetic per value,
+// so the four steps and their minimum are those of the one-thread version.  sk / Rm / delta may live in shared memory (every lane reads them).
+__device__ __forceinline__ float self_collision_steps_warp(const RobotDev *__restrict__ rb, const float *sk, const float *Rm, const float *delta, float eq_thr,
+                                                           float max_dist, float &step04, float &step05, float &step14, float &step15) {
+    constexpr int n = 6, W = 7;
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+    if (lane < 4) v = capsules_distance(rb, sk, lane >> 1, 4 + (lane & 1), eq_thr, max_dist);          // 0-4, 0-5, 1-4, 1-5
+    else if (lane < 8) v = dot_dyn(Rm + (lane == 4 ? 2 : lane - 1), W, delta, n);                      // phi2, phi4, phi5, phi6
+    const float d04 = __shfl_sync(0xffffffffu, v, 0), d05 = __shfl_sync(0xffffffffu, v, 1), d14 = __shfl_sync(0xffffffffu, v, 2), d15 = __shfl_sync(0xffffffffu, v, 3);
+    const float phi2 = __shfl_sync(0xffffffffu, v, 4), phi4 = __shfl_sync(0xffffffffu, v, 5), phi5 = __shfl_sync(0xffffffffu, v, 6), phi6 = __shfl_sync(0xffffffffu, v, 7);
+    const float m45 = phi4 < phi5 ? phi5 : phi4, m56 = phi5 < phi6 ? phi6 : phi5;
+    step04 = d04 / m45; step05 = d05 / m56; step14 = d14 / (phi2 + m45); step15 = d15 / (phi2 + m56);
+    const float sa = step05 < step04 ? step05 : step04, sb = step15 < step14 ? step15 : step14;
+    return sb < sa ? sb : sa;
+}
+
+// The routine itself, executed by ALL 32 lanes of a warp with identical q1 / q2 in their registers (at most kScWarps warps per CTA: the
+// scratch is static shared memory indexed by the warp's number in the CTA).  Returns the verdict (warp-uniform); on a hit q2 holds the
+// last collision-free configuration in every lane.
+template <class F>
+__device__ __noinline__ bool self_collision_edge_warp(const RobotDev *__restrict__ rb, const float *q1, float *q2, float eq_thr, float max_dist) {
     constexpr int n = 6, W = 7;
     __shared__ float s_sk[kScWarps][3 * W], s_Rm[kScWarps][n * W], s_delta[kScWarps][n], s_pts[kScWarps][33][n], s_dist[kScWarps][32];
+    if (rb->kind != RVS_ROBOT_XARM6 || !rb->self_collision || rb->n != 6) return false;
+    const int warp = (threadIdx.x >> 5) % kScWarps, lane = threadIdx.x & 31;
+    float *sk = s_sk[warp], *Rm = s_Rm[warp], *delta = s_delta[warp];
+    float q1t[n];
+    for (int i = 0; i < n; i++) q1t[i] = q1[i];
+    float step04 = 0.f, step05 = 0.f, step14 = 0.f, step15 = 0.f;
+    for (int num_iter = 0;;) {                                                  // xArm6.cpp:297-325
+        __syncwarp();
+        float mine[3 * W];
+        fk_skeleton_warp<F, float>(rb, q1t, mine);
+        if (lane == 0) for (int k = 0; k < 3 * W; k++) sk[k] = mine[k];
+        __syncwarp();
+        if (lane < n) { enclosing_radii_row<float>(rb, sk, lane, Rm + lane * W); delta[lane] = fabsf(q2[lane] - q1t[lane]); }
+        __syncwarp();
+        const float step = self_collision_steps_warp(rb, sk, Rm, delta, eq_thr, max_dist, step04, step05, step14, step15);
+        if (step > 1.f) return false;
+        if (++num_iter == 5 || step <= 0.f) break;
+        if (step > 0.f)
+            for (int i = 0; i < n; i++) q1t[i] = q1t[i] + step * (q2[i] - q1t[i]);
+    }
+    // marching (xArm6.cpp:327-362): q_m = q_{m-1} + (q2 - q_{m-1}) / dist * EPS_STEP until q2 is reached; pts[0] = q1_temp
+    const float D = coord_norm(q2, q1t, n), eps = rb->eps_step;
+    float (*pts)[n] = s_pts[warp];
+    float dist = D;
+    bool advanced = true;
+    __syncwarp();
+    if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = q1t[i];
+    while (advanced) {
+        int count = 0;
+        __syncwarp();
+        if (lane == 0) {
+            for (; count < 32 && advanced; count++) {
+                const float *prev = pts[count];
+                float *qn = pts[count + 1];
+                if (dist > eps) { for (int i = 0; i < n; i++) qn[i] = prev[i] + (q2[i] - prev[i]) / dist * eps; }
+                else { for (int i = 0; i < n; i++) qn[i] = q2[i]; advanced = false; }
+                dist = coord_norm(q2, qn, n);
+                s_dist[warp][count] = dist;
+            }
+        }
+        count = __shfl_sync(0xffffffffu, count, 0);
+        advanced = __shfl_sync(0xffffffffu, int(advanced), 0) != 0;
+        dist = __shfl_sync(0xffffffffu, dist, 0);
+        __syncwarp();
+        bool mine_hit = false;
+        if (lane < count) {
+            const float step_crit = 1.f - s_dist[warp][lane] / D;
+            float skm[3 * W];
+            fk_skeleton<F, float>(rb, pts[lane + 1], skm);
+            mine_hit = (!(step05 > step_crit) && capsules_distance(rb, skm, 0, 5, eq_thr, max_dist) < 0.f) ||
+                       (!(step15 > step_crit) && capsules_distance(rb, skm, 1, 5, eq_thr, max_dist) < 0.f) ||
+                       (!(step04 > step_crit) && capsules_distance(rb, skm, 0, 4, eq_thr, max_dist) < 0.f) ||
+                       (!(step14 > step_crit) && capsules_distance(rb, skm, 1, 4, eq_thr, max_dist) < 0.f);
+        }
+        const unsigned hb = __ballot_sync(0xffffffffu, mine_hit);
+        if (hb) {
+            const int f = __ffs(int(hb)) - 1;                                   // first colliding point: q2 := the point before it
+            for (int i = 0; i < n; i++) q2[i] = pts[f][i];
+            __syncwarp();
+            return true;
+        }
+        if (advanced) {
+            __syncwarp();
+            if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = pts[count][i];          // next round starts where this one ended
+        }
+    }
+    return false;
+}
+
+template <class F, class R>
+__global__ void __launch_bounds__(32 * kScWarps) self_collision_edge_warp_kernel(const KArgs a) {
+    constexpr int n = 6;
     const RobotDev *__restrict__ rb = a.robot;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t e = int64_t(blockIdx.x) * kScWarps + warp;
     if (e >= a.N) return;                                                       // (whole warps leave together)
-    float *sk = s_sk[warp], *Rm = s_Rm[warp], *delta = s_delta[warp];
-    float q1t[n], q2[n];
-    for (int i = 0; i < n; i++) { q1t[i] = a.q[e * n + i]; q2[i] = a.q2[e * n + i]; }
-    bool hit = false;
-    const bool active = rb->kind == RVS_ROBOT_XARM6 && rb->self_collision && rb->n == 6;
-    float step04 = 0.f, step05 = 0.f, step14 = 0.f, step15 = 0.f;
-    bool surely_free = !active;
-    if (active) {
-        for (int num_iter = 0;;) {                                              // xArm6.cpp:297-325
-            __syncwarp();
-            float mine[3 * W];
-            fk_skeleton_warp<F, float>(rb, q1t, mine);
-            if (lane == 0) for (int k = 0; k < 3 * W; k++) sk[k] = mine[k];
-            __syncwarp();
-            if (lane < n) { enclosing_radii_row<float>(rb, sk, lane, Rm + lane * W); delta[lane] = fabsf(q2[lane] - q1t[lane]); }
-            __syncwarp();
-            // lanes 0-3: one capsule distance each; lanes 4-7: phi2, phi4, phi5, phi6
-            float v = 0.f;
-            if (lane < 4) v = capsules_distance(rb, sk, lane >> 1, 4 + (lane & 1), a.eq_thr, a.max_dist);          // 0-4, 0-5, 1-4, 1-5
-            else if (lane < 8) v = dot_dyn(Rm + (lane == 4 ? 2 : lane - 1), W, delta, n);
-            const float d04 = __shfl_sync(0xffffffffu, v, 0), d05 = __shfl_sync(0xffffffffu, v, 1), d14 = __shfl_sync(0xffffffffu, v, 2), d15 = __shfl_sync(0xffffffffu, v, 3);
-            const float phi2 = __shfl_sync(0xffffffffu, v, 4), phi4 = __shfl_sync(0xffffffffu, v, 5), phi5 = __shfl_sync(0xffffffffu, v, 6), phi6 = __shfl_sync(0xffffffffu, v, 7);
-            const float m45 = phi4 < phi5 ? phi5 : phi4, m56 = phi5 < phi6 ? phi6 : phi5;
-            step04 = d04 / m45; step05 = d05 / m56; step14 = d14 / (phi2 + m45); step15 = d15 / (phi2 + m56);
-            const float sa = step05 < step04 ? step05 : step04, sb = step15 < step14 ? step15 : step14;
-            const float step = sb < sa ? sb : sa;
-            if (step > 1.f) { surely_free = true; break; }
-            if (++num_iter == 5 || step <= 0.f) break;
-            if (step > 0.f)
-                for (int i = 0; i < n; i++) q1t[i] = q1t[i] + step * (q2[i] - q1t[i]);
-        }
-    }
-    if (!surely_free) {
-        // marching (xArm6.cpp:327-362): q_m = q_{m-1} + (q2 - q_{m-1}) / dist * EPS_STEP until q2 is reached; pts[0] = q1_temp
-        const float D = coord_norm(q2, q1t, n), eps = rb->eps_step;
-        float (*pts)[n] = s_pts[warp];
-        float dist = D;
-        bool advanced = true;
-        if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = q1t[i];
-        while (advanced && !hit) {
-            int count = 0;
-            __syncwarp();
-            if (lane == 0) {
-                for (; count < 32 && advanced; count++) {
-                    const float *prev = pts[count];
-                    float *qn = pts[count + 1];
-                    if (dist > eps) { for (int i = 0; i < n; i++) qn[i] = prev[i] + (q2[i] - prev[i]) / dist * eps; }
-                    else { for (int i = 0; i < n; i++) qn[i] = q2[i]; advanced = false; }
-                    dist = coord_norm(q2, qn, n);
-                    s_dist[warp][count] = dist;
-                }
-            }
-            count = __shfl_sync(0xffffffffu, count, 0);
-            advanced = __shfl_sync(0xffffffffu, int(advanced), 0) != 0;
-            dist = __shfl_sync(0xffffffffu, dist, 0);
-            __syncwarp();
-            bool mine_hit = false;
-            if (lane < count) {
-                const float step_crit = 1.f - s_dist[warp][lane] / D;
-                float skm[3 * W];
-                fk_skeleton<F, float>(rb, pts[lane + 1], skm);
-                mine_hit = (!(step05 > step_crit) && capsules_distance(rb, skm, 0, 5, a.eq_thr, a.max_dist) < 0.f) ||
-                           (!(step15 > step_crit) && capsules_distance(rb, skm, 1, 5, a.eq_thr, a.max_dist) < 0.f) ||
-                           (!(step04 > step_crit) && capsules_distance(rb, skm, 0, 4, a.eq_thr, a.max_dist) < 0.f) ||
-                           (!(step14 > step_crit) && capsules_distance(rb, skm, 1, 4, a.eq_thr, a.max_dist) < 0.f);
-            }
-            const unsigned hb = __ballot_sync(0xffffffffu, mine_hit);
-            if (hb) {
-                const int f = __ffs(int(hb)) - 1;                               // first colliding point: q2 := the point before it
-                for (int i = 0; i < n; i++) q2[i] = pts[f][i];
-                hit = true;
-            } else if (advanced) {
-                __syncwarp();
-                if (lane == 0) for (int i = 0; i < n; i++) pts[0][i] = pts[count][i];      // next round starts where this one ended
-            }
-        }
-    }
+    float q1[n], q2[n];
+    for (int i = 0; i < n; i++) { q1[i] = a.q[e * n + i]; q2[i] = a.q2[e * n + i]; }
+    const bool hit = self_collision_edge_warp<F>(rb, q1, q2, a.eq_thr, a.max_dist);
     if (lane != 0) return;
     if (!a.d_c) { if (hit) a.verdict[e] = 0; return; }
     a.verdict[e] = hit ? 1 : 0;

@@ -443,13 +443,11 @@ __global__ void __launch_bounds__(32 * kSpineWarps) store_spine_kernel(const Sto
                     float q1v[6], q2v[6];
 #pragma unroll
                     for (int k = 0; k < 6; k++) { q1v[k] = __shfl_sync(0xffffffffu, q_temp, k); q2v[k] = __shfl_sync(0xffffffffu, q_new, k); }
-                    int hit = 0;
-                    if (lane == 0) {
-                        float s04, s05, s14, s15;
-                        const float sc_step = self_collision_steps(rb, sk_use, Rm, delta, a.eq_thr, a.max_dist, s04, s05, s14, s15);
-                        if (!(sc_step > 1.f)) hit = self_collision_edge_of<F>(rb, q1v, q2v, a.eq_thr, a.max_dist) ? 1 : 0;
-                    }
-                    hit = __shfl_sync(0xffffffffu, hit, 0);
+                    // the four bubble steps spread over eight lanes; the rare path (`step > 1` fails): the whole routine, by the whole warp
+                    // (cooperative FK in its bubble iterations, marching points 32 at a time)
+                    float s04, s05, s14, s15;
+                    const bool need = !(self_collision_steps_warp(rb, sk_use, Rm, delta, a.eq_thr, a.max_dist, s04, s05, s14, s15) > 1.f);
+                    const int hit = need && self_collision_edge_warp<F>(rb, q1v, q2v, a.eq_thr, a.max_dist) ? 1 : 0;
                     if (hit) {
                         self_collision = true;
                         float mine = q_new;
