@@ -42,11 +42,7 @@ __global__ void __launch_bounds__(32 * kStoreWarps) store_distance_kernel(const 
     }
     float *slot = a.store + size_t(a.slots[cfg]) * store_slot_floats(L, M);
     float *planes = slot + store_header_floats(L);
-    if (threadIdx.x == 0) {
-        float sk[3 * (kMaxDofs + 1)];
-        fk_skeleton<F, float>(rb, q, sk);
-        for (int k = 0; k < 3 * (L + 1); k++) s_sk[k] = sk[k];
-    }
+    if (warp == 0) fk_skeleton_warp<F, float>(rb, q, s_sk);            // lane k evaluates sincos(q_k); every lane stores the same skeleton (as distance_cta_kernel)
     if (threadIdx.x < L) slot[threadIdx.x] = q[threadIdx.x];
     __syncthreads();
     const int ground_included = rb->ground_included;
