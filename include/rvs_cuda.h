@@ -374,7 +374,7 @@ int  rvs_generate_configs_dev(rvs_handle h, uint64_t seed, int64_t first, int64_
  * lower bound cannot beat the running per-link minimum skips the exact narrow phase. Results are identical. */
 int  rvs_set_culling(rvs_handle h, int32_t cull);
 /* on != 0 (default): large MIN/PROFILE distance batches (>= 32768 configurations, 32 <= M < 65536) start every link's running minimum at
- * an upper bound read from a coarse distance field of the obstacle table (64^3 fp16 cells around the robot, rebuilt on the device when
+ * an upper bound read from a coarse distance field of the obstacle table (128^3 fp16 cells around the robot, rebuilt on the device when
  * the table changed), instead of at MAX_DISTANCE: the first obstacles of the table no longer pass the broad phase for every link.  A link
  * for which no candidate came below its bound is re-scanned without bounds, so results are identical with the switch on or off.
  * rvs_second_pass_warps: how many warps (of 32 configurations) needed that second pass since the last reset. */

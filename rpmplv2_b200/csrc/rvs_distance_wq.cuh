@@ -18,7 +18,7 @@
 //                      radius): its minimum is not an output, and without this a colliding configuration would push
 //                      every obstacle of that link through the queues.
 //   phase 0  bootstrap the running minimum of every link starts at an UPPER BOUND read from a coarse distance field of the obstacle table
-//                      (df_build_kernel: 64^3 cells around the robot, fp16, distance from the cell centre to the nearest obstacle,
+//                      (df_build_kernel: 128^3 cells around the robot, fp16, distance from the cell centre to the nearest obstacle,
 //                      rounded up): min over three points of the link axis of (field + half a cell diagonal) - radius.  Without it the
 //                      first thresholds are infinite and the first obstacles of the table go through the narrow phase for every link.
 //   phase A' unpack    Q0 >= 32: every lane turns one hit word into pair entries of Q1 (warp prefix sum).
@@ -82,6 +82,9 @@ constexpr int kWqSegment = 1 << 16;               // queue entries carry a 16-bi
 #endif
 #ifndef RVS_WQ_HALF
 #define RVS_WQ_HALF 1
+#endif
+#ifndef RVS_WQ_DFPTS
+#define RVS_WQ_DFPTS 3                            // points of every link axis looked up in the distance field (ends + evenly spaced interior points)
 #endif
 #ifndef RVS_WQ_FIRST
 #define RVS_WQ_FIRST 4                            // first refresh interval when the minima start from the distance-field bounds (without them: 4)
@@ -231,7 +234,11 @@ __device__ __forceinline__ R wq_df_bound(const KArgs &a, R ax, R ay, R az, R bx,
     const float x0 = float(ax), y0 = float(ay), z0 = float(az), x1 = float(bx), y1 = float(by), z1 = float(bz);
     float u = wq_df_point(a, x0, y0, z0);
     u = fminf(u, wq_df_point(a, x1, y1, z1));
-    u = fminf(u, wq_df_point(a, 0.5f * (x0 + x1), 0.5f * (y0 + y1), 0.5f * (z0 + z1)));
+#pragma unroll
+    for (int k = 1; k < RVS_WQ_DFPTS - 1; k++) {                                   // interior points of the axis, evenly spaced
+        const float w = float(k) / float(RVS_WQ_DFPTS - 1);
+        u = fminf(u, wq_df_point(a, x0 + w * (x1 - x0), y0 + w * (y1 - y0), z0 + w * (z1 - z0)));
+    }
     const float b = fmaxf(u - float(radius), 0.f) * 1.001f + 1e-4f;
     return b < float(max_dist) ? R(b) : max_dist;
 }
