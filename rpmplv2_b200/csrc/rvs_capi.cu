@@ -377,10 +377,23 @@ int distance_host_impl(rvs_engine *h, const float *q, int64_t N, int32_t mode, v
     RVS_CUDA(h, cudaEventRecord(h->ev_done, h->stream));                 // order the copy streams after earlier work on the handle
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_in, h->ev_done, 0));
     RVS_CUDA(h, cudaStreamWaitEvent(h->s_k2, h->ev_done, 0));
-    const int64_t per = ((N + chunks - 1) / chunks + 127) & ~int64_t(127);
+    // Chunk sizes ramp up and down (weights 1, 2, 4, 4, ..., 4, 2, 1): the pipeline's fill (first H2D) and drain (last D2H) are the part of
+    // the transfers that compute cannot hide, so the first and last chunks are small.  RVS_PIPE_RAMP=0: equal chunks.
+    static const bool ramp = [] { const char *e = std::getenv("RVS_PIPE_RAMP"); return !e || std::atoi(e) != 0; }();
+    int64_t bounds[33];
+    {
+        double wsum = 0, acc = 0;
+        auto weight = [&](int c) { const int edge = std::min(c, chunks - 1 - c); return (!ramp || chunks < 6) ? 4.0 : (edge == 0 ? 1.0 : (edge == 1 ? 2.0 : 4.0)); };
+        for (int c = 0; c < chunks; c++) wsum += weight(c);
+        bounds[0] = 0;
+        for (int c = 0; c < chunks; c++) {
+            acc += weight(c);
+            bounds[c + 1] = c + 1 == chunks ? N : std::min<int64_t>(N, (int64_t(double(N) * acc / wsum) + 127) & ~int64_t(127));
+        }
+    }
     for (int c = 0; c < chunks; c++) {
-        const int64_t first = int64_t(c) * per, cnt = std::min(per, N - first);
-        if (cnt <= 0) break;
+        const int64_t first = bounds[c], cnt = bounds[c + 1] - first;
+        if (cnt <= 0) continue;
         RVS_CUDA(h, cudaMemcpyAsync(dq + first * n, q + first * n, size_t(cnt) * n * sizeof(float), cudaMemcpyHostToDevice, h->s_in));
         RVS_CUDA(h, cudaEventRecord(h->ev_in[c], h->s_in));
         cudaStream_t sk = (c & 1) ? h->s_k2 : h->stream;
