@@ -9,8 +9,8 @@ from rpmplv2_b200 import engine, robots, synthetic
 rb = robots.xarm6()
 eng = engine.Engine(rb, robots.default_params(), device=0)
 stream = torch.cuda.current_stream(); eng.set_stream(stream.cuda_stream)
-for N, M in ((131072, 51), (1048576, 51), (16384, 51), (2048, 51), (131072, 6)):
-    mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1", r_min=0.3)
+for N, M, dist, rmin in ((131072, 51, "D1", 0.3), (1048576, 51, "D1", 0.3), (16384, 51, "D1", 0.3), (2048, 51, "D1", 0.3), (131072, 6, "D1", 0.3), (131072, 51, "D2", 0.9), (32768, 300, "D2", 0.9)):
+    mn, mx, g, tol = synthetic.sweep_obstacles(M, dist, r_min=rmin)
     eng.set_obstacles(mn, mx, g, tol)
     d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
     eng.generate_configs_dev(synthetic.SEED_CONFIGS, 0, N, d_q.data_ptr())
@@ -23,4 +23,5 @@ for N, M in ((131072, 51), (1048576, 51), (16384, 51), (2048, 51), (131072, 6)):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream); eng.distance_dev(d_q.data_ptr(), N, mode, d_dc.data_ptr(), d_p.data_ptr(), d_n.data_ptr()); b.record(stream); torch.cuda.synchronize(); ms.append(a.elapsed_time(b))
         t = float(np.median(ms[1:]))
-        print("N", N, "M", M, name, "ms %.3f" % t, "configs/s %.3g" % (N / t * 1e3), "GB/s written %.0f" % (N * M * 6 * 24 / t / 1e6) if mode == robots.DIST_FULL else "", flush=True)
+        if name == "FULL" and N == 131072: print("   collision-free fraction %.3f" % float((d_dc > 0).float().mean()), "RVS_FULL_SPLIT", os.environ.get("RVS_FULL_SPLIT", "1"), flush=True)
+        print("N", N, "M", M, dist, rmin, name, "ms %.3f" % t, "configs/s %.3g" % (N / t * 1e3), "GB/s written %.0f" % (N * M * 6 * 24 / t / 1e6) if mode == robots.DIST_FULL else "", flush=True)

@@ -53,6 +53,9 @@ struct rvs_engine {
     int sort_joints = 3;                         // leading joints in the sort key (RVS_SORT_JOINTS overrides, for experiments)
     int32_t *d_perm = nullptr;
     size_t perm_cap = 0;
+    int32_t *d_list = nullptr;               // FULL mode of a large batch: collision-free configurations (rvs_distance_full.cuh)
+    size_t list_cap = 0;
+    bool full_split_on = true;               // RVS_FULL_SPLIT=0: distance_kernel<FULL> as before (A/B)
     uint32_t *d_hist[2] = {nullptr, nullptr};    // one per compute stream of the pipelined host path
     float df_origin[3] = {0.f, 0.f, 0.f}, df_cell = 0.f;
     ObstacleRec *d_obs = nullptr;
@@ -261,6 +264,15 @@ int sort_ready(rvs_engine *h, size_t total) {
         if (!p) RVS_CUDA(h, cudaMalloc(&p, (size_t(1) << kSortMaxBits) * sizeof(uint32_t)));
     return RVS_OK;
 }
+constexpr int kFullSplitMinObstacles = 16;      // shorter tables: the PROFILE pass in front costs more than the idle lanes it removes (131072 x 6: 0.21 -> 0.27 ms)
+int list_ready(rvs_engine *h, size_t N) {
+    if (N + 4 <= h->list_cap) return RVS_OK;
+    if (h->d_list) RVS_CUDA(h, cudaFree(h->d_list));
+    h->d_list = nullptr; h->list_cap = 0;
+    RVS_CUDA(h, cudaMalloc(&h->d_list, (N + 4) * sizeof(int32_t)));
+    h->list_cap = N + 4;
+    return RVS_OK;
+}
 int sort_configs(rvs_engine *h, const float *d_q, int64_t N, int64_t perm_offset, int which, cudaStream_t st) {
     SortArgs a{};
     a.q = d_q; a.N = N; a.n = h->h_robot.n; a.joints = std::min(h->sort_joints, h->h_robot.n);
@@ -314,11 +326,18 @@ int distance_dev_impl(rvs_engine *h, const float *d_q, int64_t N, int32_t mode, 
         return fail(h, RVS_ERR_INVALID_ARGUMENT, "NULL buffer for the requested distance mode");
     KArgs a = base_args(h, d_q, N);
     a.mode = mode; a.d_c = d_dc; a.profile = d_prof; a.nearest = d_near;
-    if (h->df_on && h->cull && mode != RVS_DIST_FULL && h->M >= kDfMinObstacles && h->M < (1 << 16) && (N >= kDfMinConfigs || on)) {
+    // FULL for a large batch: PROFILE through the work-queue kernel + the nearest points of the collision-free configurations (rvs_distance_full.cuh)
+    const bool split = mode == RVS_DIST_FULL && h->full_split_on && h->cull && h->M >= kFullSplitMinObstacles && N > distance_small_batch(mode, h->M) && N < (int64_t(1) << 31);
+    if (split) {
+        RVS_TRY(list_ready(h, size_t(N)));
+        a.list = h->d_list;
+        h->launches += 2;
+    }
+    if (h->df_on && h->cull && (mode != RVS_DIST_FULL || split) && h->M >= kDfMinObstacles && h->M < (1 << 16) && (N >= kDfMinConfigs || on)) {
         if (!on) RVS_TRY(df_ready(h));           // (the pipelined host path builds it before it forks its streams)
         if (h->d_df && !h->df_dirty) df_args(h, a);
     }
-    if (h->sort_on && h->cull && mode != RVS_DIST_FULL && h->M > 0 && N >= kSortMinConfigs && N < (int64_t(1) << 31)) {      // (FULL: measured slower with the permutation, 2.10 -> 2.91 ms for 131072 x 51: its scattered result rows lose their locality)
+    if (h->sort_on && h->cull && (mode != RVS_DIST_FULL || split) && h->M > 0 && N >= kSortMinConfigs && N < (int64_t(1) << 31)) {      // (distance_kernel<FULL>: measured slower with the permutation, 2.10 -> 2.91 ms for 131072 x 51: its scattered result rows lose their locality)
         if (!on) RVS_TRY(sort_ready(h, size_t(N)));   // (the pipelined host path sizes the buffers before it forks its streams)
         RVS_TRY(sort_configs(h, d_q, N, perm_offset, which, on ? on : h->stream));
         a.perm = h->d_perm + perm_offset;
@@ -464,6 +483,7 @@ int rvs_create(const rvs_robot_desc *robot, const rvs_params *params, int device
     if (device < 0 || device >= count) return fail(nullptr, RVS_ERR_INVALID_ARGUMENT, "device index out of range");
     rvs_engine *h = new rvs_engine();
     if (const char *e_so = std::getenv("RVS_SORT_CONFIGS")) h->sort_on = std::atoi(e_so) ? 1 : 0;
+    if (const char *e_fs = std::getenv("RVS_FULL_SPLIT")) h->full_split_on = std::atoi(e_fs) != 0;
     if (const char *e_sb = std::getenv("RVS_SORT_PER_BIN")) h->sort_per_bin = std::max(1, std::atoi(e_sb));
     if (const char *e_sj = std::getenv("RVS_SORT_JOINTS")) h->sort_joints = std::max(1, std::min(6, std::atoi(e_sj)));
     if (const char *e_df = std::getenv("RVS_DISTANCE_FIELD")) h->df_on = std::atoi(e_df) ? 1 : 0;      // A/B switch (results are identical either way)
@@ -504,6 +524,7 @@ int rvs_destroy(rvs_handle h) {
     if (h->d_obs_pack) cudaFree(h->d_obs_pack);
     if (h->d_df) cudaFree(h->d_df);
     if (h->d_perm) cudaFree(h->d_perm);
+    if (h->d_list) cudaFree(h->d_list);
     for (auto *p : h->d_hist) if (p) cudaFree(p);
     for (auto &t : h->trees) if (t.d) cudaFree(t.d);
     if (h->d_tree_ptr) cudaFree(h->d_tree_ptr);

@@ -182,6 +182,8 @@ struct PairPlan {
     int count;        // edges to evaluate
     bool twelve;      // all 12 edges in the reference's order (:746-751)
     bool done;
+    unsigned cand;    // PTS only: where the candidate points behind `d` come from: bits 0-2 = face (x_min, y_min, z_min, x_max, y_max, z_max) the
+                      // endpoint projects onto, 7 = no candidate yet (P1 = P2 = 0); bit 3 = the endpoint is B
 };
 
 // k-th edge code of a plan
@@ -199,7 +201,7 @@ template <class R, bool PTS>
 __device__ __forceinline__ PairPlan<R> classify_pair(const Capsule<R> &cp, const Box<R> &bx, R eq_thr, R max_dist, V3<R> &P1, V3<R> &P2) {
     const V3<R> &A = cp.A, &B = cp.B;
     PairPlan<R> pl;
-    pl.list = 0; pl.count = 0; pl.twelve = false; pl.done = true; pl.d = R(0);
+    pl.list = 0; pl.count = 0; pl.twelve = false; pl.done = true; pl.d = R(0); pl.cand = 7u;
     // --- stage 1: endpoint classification (projectionLineSegOnSide x3, :451-475)
     const bool ainx = A.x >= bx.lo.x && A.x <= bx.hi.x, ainy = A.y >= bx.lo.y && A.y <= bx.hi.y, ainz = A.z >= bx.lo.z && A.z <= bx.hi.z;
     const bool binx = B.x >= bx.lo.x && B.x <= bx.hi.x, biny = B.y >= bx.lo.y && B.y <= bx.hi.y, binz = B.z >= bx.lo.z && B.z <= bx.hi.z;
@@ -234,6 +236,7 @@ __device__ __forceinline__ PairPlan<R> classify_pair(const Capsule<R> &cp, const
             const int c = face > 2 ? face - 3 : face;
             P1 = Pn; P2 = Pn;
             put3(P2, c, face > 2 ? sel3(bx.hi, c) : sel3(bx.lo, c));
+            pl.cand = unsigned(face) | (useB ? 8u : 0u);
         }
         if ((mA & mB) == 0u) {
             // checkEdges (:477-574): first face in the order x_min, x_max, y_min, y_max, z_min, z_max

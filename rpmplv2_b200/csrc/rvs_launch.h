@@ -8,6 +8,16 @@ namespace rvs {
 
 typedef cudaError_t (*LaunchFn)(const KArgs &, cudaStream_t);
 
+#ifndef RVS_SMALL_BATCH
+#define RVS_SMALL_BATCH 4096
+#endif
+// rvs_distance* calls up to this many configurations take the one-CTA-per-configuration kernel (rvs_store.cuh): measured cross-overs
+// (profiles/README.md), ~4k configurations for MIN / PROFILE, ~16k for FULL, a quarter of that against long obstacle tables
+inline int64_t distance_small_batch(int32_t mode, int32_t M) {
+    const int64_t b = RVS_SMALL_BATCH;
+    return M > 256 ? b / 4 : (mode == RVS_DIST_FULL ? 4 * b : b);
+}
+
 struct LaunchTable {
     LaunchFn distance;
     LaunchFn is_valid;

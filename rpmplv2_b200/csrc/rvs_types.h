@@ -84,6 +84,7 @@ struct KArgs {
     unsigned long long *pair_count;   // += pair queries the reference's loop would have visited (early exit respected)
     // coarse distance field of the obstacle table (rvs_distance_wq.cuh: df_build_kernel): upper bounds for the first thresholds; nullptr = off
     const int32_t *perm;     // work-queue distance kernel: thread k works on configuration perm[k] (rvs_sort.cuh); nullptr = identity
+    int32_t *list;           // FULL mode of a large batch (rvs_distance_full.cuh): [0] = number of collision-free configurations, their indices from [4]; nullptr = one kernel
     const void *df;          // [df_dim^3] __half, distance from the cell centre to the nearest eligible obstacle, rounded up
     float df_origin[3];      // lower corner of the grid
     float df_inv_cell;       // cells per metre

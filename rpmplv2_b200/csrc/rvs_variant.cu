@@ -4,6 +4,7 @@
 //   -DRVS_VARIANT_FAST   -fmad=true                                             -> FAST32 launch table
 #include "rvs_kernels.cuh"
 #include "rvs_distance_wq.cuh"
+#include "rvs_distance_full.cuh"
 #include "rvs_valid_wq.cuh"
 #include "rvs_store.cuh"
 #include "rvs_env.cuh"
@@ -19,11 +20,7 @@ namespace rvs {
 namespace {
 
 inline unsigned grid_for(int64_t n, int block) { return unsigned((n + block - 1) / block); }
-#ifndef RVS_SMALL_BATCH
-#define RVS_SMALL_BATCH 4096
-#endif
 constexpr int64_t kSmallValid = 2048;       // validity items (configurations, or edges x checks) up to which one CTA per item is used
-constexpr int64_t kSmallBatch = RVS_SMALL_BATCH;      // rvs_distance* calls up to this many configurations (4x for FULL) take the one-CTA-per-configuration kernel
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device).  One table per process: (function, device) -> bytes already
 // granted; looked up under a mutex because handles on different devices may be driven from different host threads.
@@ -62,13 +59,34 @@ struct Variant {
         distance_cta_kernel<F, MODE><<<unsigned(a.N), 32 * kStoreWarps, 0, st>>>(a);
         return cudaGetLastError();
     }
+    // FULL mode of a large batch (rvs_distance_full.cuh): PROFILE through the work-queue kernel, then the nearest points of the
+    // collision-free configurations only
+    static cudaError_t distance_full_split(const KArgs &a, cudaStream_t st) {
+        KArgs p = a;
+        p.mode = RVS_DIST_PROFILE;
+        cudaError_t e = a.robot_n_hint <= 2 ? distance_wq<RVS_DIST_PROFILE, 2>(p, st) : distance_wq<RVS_DIST_PROFILE, kWqG>(p, st);
+        if (e != cudaSuccess) return e;
+        e = cudaMemsetAsync(a.list, 0, 4 * sizeof(int32_t), st);
+        if (e != cudaSuccess) return e;
+        full_list_kernel<R><<<grid_for(a.N, kListBlock), kListBlock, 0, st>>>(a);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        const size_t smem = full_smem_bytes(a.robot_n_hint, sizeof(R));
+        if (smem > 48u * 1024u) {
+            e = raise_smem_limit(reinterpret_cast<const void *>(nearest_points_kernel<F, R>), smem);
+            if (e != cudaSuccess) return e;
+        }
+        nearest_points_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, smem, st>>>(a);
+        return cudaGetLastError();
+    }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
         if (a.N <= 0) return cudaSuccess;
-        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= (a.M > 256 ? kSmallBatch / 4 : (a.mode == RVS_DIST_FULL ? 4 * kSmallBatch : kSmallBatch))) {     // measured cross-overs (profiles/README.md): ~4k configurations for MIN / PROFILE, ~16k for FULL
+        if (sizeof(R) == 4 && a.cull && a.M > 0 && a.N <= distance_small_batch(a.mode, a.M)) {
             if (a.mode == RVS_DIST_MIN) return distance_cta<RVS_DIST_MIN>(a, st);
             if (a.mode == RVS_DIST_PROFILE) return distance_cta<RVS_DIST_PROFILE>(a, st);
             return distance_cta<RVS_DIST_FULL>(a, st);
         }
+        if (a.cull && a.mode == RVS_DIST_FULL && a.M > 0 && a.list) return distance_full_split(a, st);
         if (a.cull && a.mode != RVS_DIST_FULL && a.M > 0) {
             // work-queue kernel (rvs_distance_wq.cuh): results identical to the sequential kernel below
             const bool narrow = a.robot_n_hint <= 2;

@@ -172,6 +172,66 @@ def test_small_batch_kernel_is_bit_identical_to_sequential_kernel(case, prec):
 
 
 @pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32, robots.PREC_F64])
+@pytest.mark.parametrize("case", ["xarm6_16_sorted", "xarm6_51", "xarm6_300", "spatial10", "planar2"])
+def test_full_mode_of_a_large_batch_equals_sequential_kernel(case, prec):
+    """FULL beyond the small-batch cross-over is three launches (rvs_distance_full.cuh): PROFILE through the work-queue kernel, the list of
+    collision-free configurations, their nearest points. d_c, the profile with its early-exit fill, the reference-order pair count and the
+    nearest points of every collision-free configuration must equal distance_kernel<FULL> (rvs_set_culling(0)) bit for bit; the block of a
+    configuration in collision is unspecified (include/rvs_cuda.h) and stays as the caller passed it."""
+    if case == "xarm6_16_sorted":
+        (rb, mn, mx, g, tol), N = scenes.xarm6_scene(16, "D2", 0.45), 70000        # >= 65536: coherent-warp permutation in front
+    elif case == "xarm6_51":
+        (rb, mn, mx, g, tol), N = scenes.xarm6_scene(51, "D1", 0.3), 20000
+    elif case == "xarm6_300":
+        (rb, mn, mx, g, tol), N = scenes.xarm6_scene(300, "D2", 0.8), 3000         # long table: the cross-over is 1024, two obstacle tiles
+    elif case == "spatial10":
+        (rb, mn, mx, g, tol), N = scenes.chain_scene(robots.spatial(10), 20), 20000
+    else:
+        (rb, mn, mx, g, tol), N = scenes.chain_scene(robots.planar(2), 17), 20000          # two links: 48-byte rows, odd pair count
+    eng = make(rb, mn, mx, g, tol, prec, 1e-4)
+    q = synthetic.configs(rb, N, seed=0xF011)
+    eng.set_culling(True)
+    eng.pair_count(reset=True)
+    k0 = eng.launch_count()
+    d1, p1, n1 = eng.distance(q, robots.DIST_FULL)
+    assert eng.launch_count() - k0 >= 3
+    c1 = eng.pair_count(reset=True)
+    eng.set_culling(False)
+    d0, p0, n0 = eng.distance(q, robots.DIST_FULL)
+    c0 = eng.pair_count(reset=True)
+    eq = (lambda x, y: (x.view(np.uint8) == y.view(np.uint8)).all()) if prec != robots.PREC_FAST32 else \
+         (lambda x, y: np.abs(x - y).max(initial=0.0) <= 1e-5)
+    free = d0 > 0
+    assert 0.02 < free.mean() < 0.999
+    assert eq(d1, d0) and ((d1 > 0) == free).all() and eq(p1, p0)
+    assert c1 == c0 or prec == robots.PREC_FAST32
+    if prec != robots.PREC_FAST32:
+        assert eq(n1[free], n0[free])
+    elif free.any():
+        assert (np.abs(n1[free] - n0[free]) <= 1e-5).mean() > 0.98
+    assert (n1[~free] == 0).all()                                         # untouched (the binding passes a zeroed block)
+    eng.close()
+
+
+def test_full_mode_large_batch_with_a_misaligned_result_block():
+    """A caller's nearest-point block that is only 4-byte aligned takes scalar stores instead of 8-byte ones: same bytes."""
+    import torch
+    rb, mn, mx, g, tol = scenes.xarm6_scene(20, "D2", 0.45)
+    eng = make(rb, mn, mx, g, tol)
+    N, M, L = 18000, 20, 6
+    d_q = torch.from_numpy(synthetic.configs(rb, N, seed=0xA11)).cuda()
+    d_dc, d_p = torch.empty(N, dtype=torch.float32, device="cuda"), torch.empty((N, L), dtype=torch.float32, device="cuda")
+    out = []
+    for off in (0, 1):
+        buf = torch.zeros(N * M * L * 6 + 4, dtype=torch.float32, device="cuda")
+        eng.distance_dev(d_q.data_ptr(), N, robots.DIST_FULL, d_dc.data_ptr(), d_p.data_ptr(), buf.data_ptr() + 4 * off)
+        torch.cuda.synchronize()
+        out.append(buf[off:off + N * M * L * 6].cpu().numpy())
+    assert (out[0].view(np.uint8) == out[1].view(np.uint8)).all() and (out[0] != 0).any()
+    eng.close()
+
+
+@pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32, robots.PREC_F64])
 @pytest.mark.parametrize("case", ["xarm6_1000", "xarm6_2500_dense", "spatial22", "planar2"])
 def test_work_queue_validity_kernels_equal_sequential_kernels(case, prec):
     """isValid(q) / isValid(q1,q2) through the scan + queue kernel (rvs_valid_wq.cuh) vs the one-thread-per-configuration kernels."""
