@@ -15,6 +15,8 @@
 // stores.  Same per-pair routine (capsule_box_distance<R, true>), so the points are those of distance_kernel<FULL> bit for bit
 // (tests/test_gpu_parity.py compares the two on every precision).
 #pragma once
+#include <algorithm>
+
 #include "rvs_kernels.cuh"
 
 namespace rvs {
@@ -41,6 +43,17 @@ __global__ void __launch_bounds__(kListBlock) full_list_kernel(const KArgs a) {
     }
     __syncthreads();
     if (keep) a.list[4 + warp_base[kListBlock / 32] + warp_base[warp] + __popc(mask & ((1u << lane) - 1u))] = cfg;
+}
+
+// ranges of the obstacle table per batch of kBlock configurations: enough blocks for ~6 waves of 5 CTAs on 148 SMs if every configuration
+// were listed (2220 / 4440 measured, profiles/r2), at least 8 obstacles per range
+#ifndef RVS_FULL_PARTS_TARGET
+#define RVS_FULL_PARTS_TARGET 4440
+#endif
+inline int full_parts(int64_t N, int M) {
+    const int64_t blocks = (N + kBlock - 1) / kBlock;
+    const int64_t want = (RVS_FULL_PARTS_TARGET + blocks - 1) / blocks;
+    return int(std::max<int64_t>(1, std::min<int64_t>(want, M / 8)));
 }
 
 template <class R> struct Pair2;
@@ -125,8 +138,11 @@ __global__ void __launch_bounds__(kBlock, sizeof(R) == 4 ? RVS_FULL_MINBLOCKS : 
         return cp;
     };
 
-    for (int base = 0; base < a.M; base += kFullTile) {
-        const int count = min(kFullTile, a.M - base);
+    // gridDim.y blocks share a batch of configurations, each walking its own range of the obstacle table: batches that would not fill the
+    // GPU with one thread per configuration (full_parts below) get that many times the warps
+    const int m_lo = int(int64_t(a.M) * blockIdx.y / gridDim.y), m_hi = int(int64_t(a.M) * (blockIdx.y + 1) / gridDim.y);
+    for (int base = m_lo; base < m_hi; base += kFullTile) {
+        const int count = min(kFullTile, m_hi - base);
         __syncthreads();
         stage_tile(tile, a.obstacles + base, count);
         __syncthreads();

@@ -76,7 +76,7 @@ struct Variant {
             e = raise_smem_limit(reinterpret_cast<const void *>(nearest_points_kernel<F, R>), smem);
             if (e != cudaSuccess) return e;
         }
-        nearest_points_kernel<F, R><<<grid_for(a.N, kBlock), kBlock, smem, st>>>(a);
+        nearest_points_kernel<F, R><<<dim3(grid_for(a.N, kBlock), unsigned(full_parts(a.N, a.M))), kBlock, smem, st>>>(a);
         return cudaGetLastError();
     }
     static cudaError_t distance(const KArgs &a, cudaStream_t st) {
