@@ -12,10 +12,14 @@ typedef cudaError_t (*LaunchFn)(const KArgs &, cudaStream_t);
 #define RVS_SMALL_BATCH 4096
 #endif
 // rvs_distance* calls up to this many configurations take the one-CTA-per-configuration kernel (rvs_store.cuh): measured cross-overs
-// (profiles/README.md), ~4k configurations for MIN / PROFILE, ~16k for FULL, a quarter of that against long obstacle tables
+// (profiles/README.md; profiles/r2/full_small_probe*.txt for FULL against the three-launch split), ~4k configurations for MIN / PROFILE,
+// ~8k for FULL, ~1k against long obstacle tables
+#ifndef RVS_SMALL_BATCH_FULL
+#define RVS_SMALL_BATCH_FULL (2 * RVS_SMALL_BATCH)
+#endif
 inline int64_t distance_small_batch(int32_t mode, int32_t M) {
-    const int64_t b = RVS_SMALL_BATCH;
-    return M > 256 ? b / 4 : (mode == RVS_DIST_FULL ? 4 * b : b);
+    const int64_t b = mode == RVS_DIST_FULL ? RVS_SMALL_BATCH_FULL : RVS_SMALL_BATCH;
+    return M > 256 ? RVS_SMALL_BATCH / 4 : b;
 }
 
 struct LaunchTable {

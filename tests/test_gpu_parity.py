@@ -131,7 +131,7 @@ def test_work_queue_kernel_is_bit_identical_to_sequential_kernel(case, prec):
 @pytest.mark.parametrize("prec", [robots.PREC_REF32, robots.PREC_FAST32])
 @pytest.mark.parametrize("case", ["xarm6_51", "xarm6_1000", "xarm6_dense", "spatial22", "planar2"])
 def test_small_batch_kernel_is_bit_identical_to_sequential_kernel(case, prec):
-    """rvs_distance* calls of up to 4096 configurations (16384 for FULL) take distance_cta_kernel (one CTA per configuration, rvs_store.cuh): every
+    """rvs_distance* calls of up to 4096 configurations (8192 for FULL) take distance_cta_kernel (one CTA per configuration, rvs_store.cuh): every
     output of every mode — d_c, the profile with its early-exit fill, the nearest points of collision-free configurations and the
     reference-order pair count — must equal the one-thread-per-configuration kernel (rvs_set_culling(0)) bit for bit."""
     if case == "xarm6_51":
