@@ -20,6 +20,7 @@ for rb, (mn, mx, g, tol) in ((robots.xarm6(), synthetic.sweep_obstacles(300, "D2
     eng.is_valid(q); eng.is_valid(q[:40]); eng.is_valid(q[:3000])
     q1, q2 = synthetic.edges(rb, 800, 0.1)
     eng.is_valid_edges(q1, q2); eng.is_valid_edges(q1[:20], q2[:20])
+    eng.distance(synthetic.configs(rb, 8300 if rb.num_dofs > 6 else 2500, seed=9), robots.DIST_FULL)     # three-launch split (rvs_distance_full.cuh): rings, obstacle ranges, two tiles / > 48 KB of shared memory
     d, p, near = eng.distance(q[:64], robots.DIST_FULL)
     k = int(np.argmax(d))
     eng.underestimation(q[:64], near[k:k + 1], np.zeros(64, np.int32))
