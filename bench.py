@@ -45,6 +45,7 @@ from rpmplv2_b200.sharding import shard_range  # noqa: E402
 
 N_CONFIGS = int(os.environ.get("RVS_BENCH_CONFIGS", 10_000_000))           # configurations per step and rank (weak scaling)
 N_STRONG = int(os.environ.get("RVS_BENCH_STRONG_CONFIGS", 100_000_000))    # ONE batch over all ranks (--scaling strong)
+N_FULL = int(os.environ.get("RVS_BENCH_FULL_CONFIGS", 1 << 20))                # configurations per launch of the `full_mode` point (7.7 GB of nearest points)
 N_EXTRA = int(os.environ.get("RVS_BENCH_EXTRA_CONFIGS", 1 << 22))          # configurations per launch of the `workloads` points
 MAX_RESIDENT_BATCHES = 24
 FLOP_PER_PAIR, FLOP_FK = 150.0, 630.0          # counting convention C1
@@ -523,7 +524,7 @@ def main():
     del h_q, h_dc, h_prof
 
     # ---- supplementary points (rank 0 of a single-GPU run only; not part of the metric) ----
-    verdict, extra = None, None
+    verdict, extra, full_mode = None, None, None
     if world == 1 and not args.no_extras and prec != robots.PREC_F64:
         d_v = torch.empty(N, dtype=torch.uint8, device=dev)
         vms = []
@@ -539,6 +540,7 @@ def main():
         del d_v
         extra = extra_workloads(eng, torch, dev, stream, rb, odt)
         eng.set_obstacles(mn, mx, g, tol)
+        full_mode = full_mode_point(torch, dev, stream, rb, prec, local)
     planning_rows = None
     if world == 1 and not args.no_extras and not args.no_cpu_baseline and args.precision == "ref32" and not args.no_cull:
         planning_rows = planning_summary(local)
@@ -584,12 +586,56 @@ def main():
             out["is_valid"] = verdict
         if extra:
             out["workloads"] = extra
+        if full_mode:
+            out["full_mode"] = full_mode
         if not args.no_cpu_baseline and world == 1:
             out.update(cpu_baseline())
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+def full_mode_point(torch, dev, stream, rb, prec, device):
+    """computeDistance with the nearest points of every (link, obstacle) pair (RVS_DIST_FULL, State::nearest_points): N_FULL configurations
+    against 51 boxes, device-resident, median of 3 launches after one warm-up; the 24 L M bytes per configuration written per launch
+    exceed the L2. Timed twice: the shipped three-launch path (csrc/rvs_distance_full.cuh) and distance_kernel<FULL> (RVS_FULL_SPLIT=0)."""
+    from rpmplv2_b200 import engine
+    n, L, M = rb.num_dofs, rb.num_links, 51
+    mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1", r_min=0.3)
+    odt = torch.float32
+    d_q = torch.empty((N_FULL, n), dtype=torch.float32, device=dev)
+    d_dc = torch.empty(N_FULL, dtype=odt, device=dev)
+    d_prof = torch.empty((N_FULL, L), dtype=odt, device=dev)
+    d_near = torch.zeros((N_FULL, M, L, 6), dtype=odt, device=dev)
+    out = {"configs": N_FULL, "obstacles": M, "result_bytes_per_config": 24 * L * M,
+           "note": "nearest points are an output of every pair: nothing is culled; the block of a configuration in collision is unspecified and is not computed by the split path"}
+    keep = os.environ.get("RVS_FULL_SPLIT")
+    for key, env in (("split", "1"), ("one_kernel", "0")):
+        os.environ["RVS_FULL_SPLIT"] = env
+        e2 = engine.Engine(rb, robots.default_params(prec), device=device)
+        e2.set_stream(stream.cuda_stream)
+        e2.set_obstacles(mn, mx, g, tol)
+        e2.generate_configs_dev(synthetic.SEED_CONFIGS, 1 << 41, N_FULL, d_q.data_ptr())
+        ms = []
+        for _ in range(4):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0 = e2.launch_count()
+            a.record(stream); e2.distance_dev(d_q.data_ptr(), N_FULL, robots.DIST_FULL, d_dc.data_ptr(), d_prof.data_ptr(), d_near.data_ptr()); b.record(stream)
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+            launches = e2.launch_count() - k0
+        med = sorted(ms[1:])[1]
+        free = float((d_dc > 0).float().mean().item())
+        out[key] = {"ms_per_launch": med, "configs_per_s": N_FULL / med * 1e3, "launches": launches,
+                    "nearest_points_written_gbs": N_FULL * free * 24 * L * M / med / 1e6}
+        out["collision_free_fraction"] = round(free, 4)
+        e2.close()
+    if keep is None:
+        os.environ.pop("RVS_FULL_SPLIT", None)
+    else:
+        os.environ["RVS_FULL_SPLIT"] = keep
+    return out
 
 
 def extra_workloads(eng, torch, dev, stream, rb, odt):

@@ -31,6 +31,8 @@ def test_headline_line_carries_every_contract_key():
     rows = d["planning_time_vs_cpu"]
     assert len(rows) == 4 and all("error" not in row for row in rows)                       # BASELINE configs 1-4
     assert all(row["identical_runs_gpu_vs_cpu"] == row["runs"] for row in rows[:3]) and rows[3]["same_run"] is True
+    f = d["full_mode"]                                                                      # nearest points of every pair: shipped path vs the one-kernel path, same run
+    assert f["split"]["launches"] > f["one_kernel"]["launches"] == 1 and f["split"]["ms_per_launch"] < 0.5 * f["one_kernel"]["ms_per_launch"]
 
 
 def test_reference_arm_is_the_same_metric_on_the_same_configuration():
