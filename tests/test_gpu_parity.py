@@ -548,6 +548,50 @@ def test_full_size_properties():
     assert ((val == 1) != free).float().mean().item() < 1e-3
 
 
+def test_full_mode_at_scale_nearest_points_reproduce_the_profile(ob):
+    """300 000 configurations x 51 boxes with nearest points (2.2 GB of results, the three-launch path with a sorted PROFILE pass, rings
+    and two obstacle ranges per block): for every collision-free configuration the profile is recovered from the nearest points alone —
+    min over the obstacles of |P_robot - P_obstacle| - radius, with the min_dist_tol rule — and a sample of 2000 configurations equals
+    the CPU oracle's points."""
+    torch = pytest.importorskip("torch")
+    rb, mn, mx, g, tol = scenes.xarm6_scene(51, "D1", 0.3)
+    eng = make(rb, mn, mx, g, tol)
+    N, M, L = 300000, 51, 6
+    eng.set_stream(torch.cuda.current_stream().cuda_stream)
+    d_q = torch.empty((N, L), dtype=torch.float32, device="cuda")
+    eng.generate_configs_dev(synthetic.SEED_CONFIGS, 0, N, d_q.data_ptr())
+    d_dc, d_p = torch.empty(N, dtype=torch.float32, device="cuda"), torch.empty((N, L), dtype=torch.float32, device="cuda")
+    near = torch.zeros((N, M, L, 6), dtype=torch.float32, device="cuda")
+    k0 = eng.launch_count()
+    eng.distance_dev(d_q.data_ptr(), N, robots.DIST_FULL, d_dc.data_ptr(), d_p.data_ptr(), near.data_ptr())
+    torch.cuda.synchronize()
+    assert eng.launch_count() - k0 >= 3
+    free = d_dc > 0
+    assert 0.3 < free.float().mean().item() < 0.5
+    assert (near[~free] == 0).all()                                                              # blocks of colliding configurations: untouched
+    radius = torch.tensor(rb.radius[:L], dtype=torch.float32, device="cuda")
+    t_tol = torch.tensor(tol, dtype=torch.float32, device="cuda")
+    worst = 0.0
+    idx = torch.nonzero(free).flatten()
+    for chunk in torch.split(idx, 20000):
+        nb = near[chunk]
+        d = (nb[..., :3] - nb[..., 3:]).norm(dim=-1) - radius[None, None, :]                     # [n, M, L]
+        clear = ((d - t_tol[None, :, None]).abs() > 1e-4).all(dim=2).all(dim=1)                  # (not within rounding of a min_dist_tol)
+        d = torch.where(d > t_tol[None, :, None], torch.full_like(d, 1000.0), d)                 # min_dist_tol (:367-368)
+        worst = max(worst, (d.min(dim=1).values - d_p[chunk])[clear].abs().max().item())
+    assert worst <= 1e-5
+    # a sample against the oracle
+    o = make_oracle(ob, rb, mn, mx, g, tol)
+    sel = torch.arange(0, N, 150, device="cuda")
+    q_s = d_q[sel].cpu().numpy()
+    d_o, p_o, n_o = o.distance(q_s, robots.DIST_FULL)
+    f_o = d_o > 0
+    assert ((d_dc[sel].cpu().numpy() > 0) == f_o).all()
+    n_g = near[sel].cpu().numpy()
+    assert np.abs(n_g[f_o] - n_o[f_o]).max() <= TOL32 and (n_g[f_o] != n_o[f_o]).mean() < 1e-3
+    eng.close()
+
+
 def test_headline_step_of_1e7_configurations_sampled_against_the_oracle(ob):
     """bench.py's step as it is timed — 10^7 device-generated configurations against the headline scene in ONE launch of the work-queue
     kernel — with 40 000 configurations sampled out of it (stride 250) and re-computed by the CPU oracle: bit-identical up to rare
