@@ -93,6 +93,7 @@ template <class R> __device__ __forceinline__ void store_points(R *dst, bool vec
 #ifndef RVS_FULL_STORE16
 #define RVS_FULL_STORE16 1
 #endif
+
 template <> __device__ __forceinline__ void store_points<float>(float *dst, bool vec, const V3<float> &P1, const V3<float> &P2) {
     if (vec && RVS_FULL_STORE16) {
         if ((reinterpret_cast<size_t>(dst) & 15) == 0) {
