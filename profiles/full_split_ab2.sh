@@ -1,5 +1,8 @@
 #!/bin/bash
 # profiles/full_split_ab2.sh <tag> — nearest_points_kernel with deferred-edge rings of 16 / 8 / 32 entries, then one ncu --set full capture of it
+# The variants/*.so it loads through RVS_CUDA_LIB are builds of the same tree with one macro changed, made beforehand with e.g.
+#   make -C rpmplv2_b200/csrc BUILD=_build_x OUT=../../variants/librvs_full_ring32.so EXTRA=-DRVS_FULL_RING=32
+# (RVS_FULL_MINBLOCKS, RVS_FULL_RING, RVS_FULL_STORE16, RVS_FULL_PARTS_TARGET, RVS_SMALL_BATCH_FULL); variants/ is scratch and not committed.
 tag=${1:-x}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "full" > gpurun_out/${tag}_full_tests.log 2>&1; echo "tests rc=$?" >> gpurun_out/${tag}_full_tests.log

@@ -1,5 +1,8 @@
 #!/bin/bash
 # profiles/full_split_ab3.sh <tag> — whole GPU suite on the tree with the FULL-mode split, the obstacle-range split of
+# The variants/*.so it loads through RVS_CUDA_LIB are builds of the same tree with one macro changed, made beforehand with e.g.
+#   make -C rpmplv2_b200/csrc BUILD=_build_x OUT=../../variants/librvs_full_ring32.so EXTRA=-DRVS_FULL_RING=32
+# (RVS_FULL_MINBLOCKS, RVS_FULL_RING, RVS_FULL_STORE16, RVS_FULL_PARTS_TARGET, RVS_SMALL_BATCH_FULL); variants/ is scratch and not committed.
 # nearest_points_kernel (RVS_FULL_PARTS_TARGET 2220 / 1 = off / 4440), a default bench line
 tag=${1:-x}
 mkdir -p gpurun_out

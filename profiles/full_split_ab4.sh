@@ -1,5 +1,8 @@
 #!/bin/bash
 # profiles/full_split_ab4.sh <tag> — nearest_points_kernel: streaming stores (st.global.cs), rings of 4 entries
+# The variants/*.so it loads through RVS_CUDA_LIB are builds of the same tree with one macro changed, made beforehand with e.g.
+#   make -C rpmplv2_b200/csrc BUILD=_build_x OUT=../../variants/librvs_full_ring32.so EXTRA=-DRVS_FULL_RING=32
+# (RVS_FULL_MINBLOCKS, RVS_FULL_RING, RVS_FULL_STORE16, RVS_FULL_PARTS_TARGET, RVS_SMALL_BATCH_FULL); variants/ is scratch and not committed.
 tag=${1:-x}
 mkdir -p gpurun_out
 for lib in rpmplv2_b200/librvs_cuda.so variants/librvs_full_stcs.so variants/librvs_full_ring4.so; do
