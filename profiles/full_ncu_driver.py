@@ -6,7 +6,7 @@ from rpmplv2_b200 import engine, robots, synthetic
 rb = robots.xarm6()
 eng = engine.Engine(rb, robots.default_params(), device=0)
 stream = torch.cuda.current_stream(); eng.set_stream(stream.cuda_stream)
-N, M = 131072, 51
+N, M = int(os.environ.get("RVS_FULL_NCU_CONFIGS", 131072)), 51
 mn, mx, g, tol = synthetic.sweep_obstacles(M, "D1", r_min=0.3)
 eng.set_obstacles(mn, mx, g, tol)
 d_q = torch.empty((N, 6), dtype=torch.float32, device="cuda")
