@@ -11,9 +11,10 @@
 // With the list every lane of step 3 is a free configuration and does the same L x M trips; nothing is culled, nothing exits early.
 // Step 3 also differs from distance_kernel<FULL> in its memory behaviour: the skeleton sits in a shared-memory column instead of a
 // dynamically indexed local array, the loop is obstacle-major / link-minor so that the L pieces of one obstacle (24 L contiguous bytes
-// of the [M][L][6] block) are written back to back and meet in L2 before they are evicted, and a piece goes out as three 8-byte
-// stores.  Same per-pair routine (capsule_box_distance<R, true>), so the points are those of distance_kernel<FULL> bit for bit
-// (tests/test_gpu_parity.py compares the two on every precision).
+// of the [M][L][6] block) are written back to back and meet in L2 before they are evicted, a piece goes out as one 16-byte and one
+// 8-byte store, and the edge evaluations are deferred onto per-thread rings (below).  Same per-pair routines in the same order per
+// pair (classify_pair, then plan_edge_distance over the planned edges = capsule_box_distance<R, true>), so the points are those of
+// distance_kernel<FULL> bit for bit (tests/test_gpu_parity.py compares the two on every precision).
 #pragma once
 #include <algorithm>
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kListBlock) full_list_kernel(const KArgs a) {
     if (keep) a.list[4 + warp_base[kListBlock / 32] + warp_base[warp] + __popc(mask & ((1u << lane) - 1u))] = cfg;
 }
 
-// ranges of the obstacle table per batch of kBlock configurations: enough blocks for ~6 waves of 5 CTAs on 148 SMs if every configuration
+// ranges of the obstacle table per batch of kBlock configurations: enough blocks for ~7 waves of 4 CTAs on 148 SMs if every configuration
 // were listed (2220 / 4440 measured, profiles/r2), at least 8 obstacles per range
 #ifndef RVS_FULL_PARTS_TARGET
 #define RVS_FULL_PARTS_TARGET 4440
@@ -60,13 +61,15 @@ template <class R> struct Pair2;
 template <> struct Pair2<float> { typedef float2 type; static __device__ __forceinline__ float2 make(float x, float y) { return make_float2(x, y); } };
 template <> struct Pair2<double> { typedef double2 type; static __device__ __forceinline__ double2 make(double x, double y) { return make_double2(x, y); } };
 
+// (101 registers -> 4 CTAs per SM; 5 / 6 CTAs measured slower: the store path is the limit, profiles/r2/ncu_details_nearest_points_1m.txt)
 #ifndef RVS_FULL_MINBLOCKS
 #define RVS_FULL_MINBLOCKS 4
 #endif
 // The case analysis of a pair (classify_pair, rvs_geom.cuh) ends most pairs on the spot; the others leave 1, 2, 4 or 12 box edges for
 // distanceLineSegToLineSeg.  Run pair by pair, that edge loop is where the warp falls apart (ncu, profiles/r2: seg_edge and its helpers
 // are two thirds of the instructions at 5 of 32 lanes, classify_pair runs at 29).  So the edge work is DEFERRED: a thread pushes the
-// pairs that need edges onto its own ring in shared memory (kFullRing entries — 8 / 16 / 32 measured, profiles/r2 — each the plan, the pair, the face candidate) and goes on
+// pairs that need edges onto its own ring in shared memory (kFullRing entries — 4 / 8 / 16 / 32 measured, profiles/r2 — each the plan,
+// the pair and the face candidate) and goes on
 // classifying; when some lane's ring is full, every lane with work evaluates ONE edge per trip — one converged seg_edge per lane
 // whatever pair or edge count it belongs to — until all rings are at most half full.  A pair's edges are still evaluated in the
 // reference's order by the one thread that owns the pair, so the nearest points are those of the sequential loop bit for bit.
