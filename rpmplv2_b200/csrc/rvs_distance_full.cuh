@@ -165,13 +165,7 @@ __global__ void __launch_bounds__(kBlock, sizeof(R) == 4 ? RVS_FULL_MINBLOCKS : 
                 const int edges = int((plan >> 24) & 15u);
                 if (edge_k == 0) {                                      // the candidate classify_pair left (face projection, or none)
                     best = ring_d[head * kBlock];
-                    const unsigned cand = plan >> 28;
-                    B1 = {0, 0, 0}; B2 = {0, 0, 0};
-                    if ((cand & 7u) != 7u) {
-                        const int face = int(cand & 7u), c = face > 2 ? face - 3 : face;
-                        B1 = (cand & 8u) ? cp.B : cp.A; B2 = B1;
-                        put3(B2, c, face > 2 ? sel3(bx.hi, c) : sel3(bx.lo, c));
-                    }
+                    plan_candidate_points(cp, bx, plan >> 28, B1, B2);
                 }
                 PairPlan<R> pl;
                 pl.list = plan & 0xffffffu; pl.count = edges; pl.twelve = edges == 12;

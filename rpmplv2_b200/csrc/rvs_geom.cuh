@@ -292,6 +292,18 @@ __device__ __forceinline__ R plan_edge_distance(const Capsule<R> &cp, const Box<
     return seg_edge<R, PTS>(cp, C, e, De, eq_thr, max_dist, q1, q2);
 }
 
+// The candidate points classify_pair<R, true> leaves behind an UNDECIDED pair, rebuilt from PairPlan::cand — for callers that evaluate the
+// planned edges later (rvs_distance_full.cuh defers them): the endpoint that projects onto a face and its projection, or no points yet.
+template <class R>
+__device__ __forceinline__ void plan_candidate_points(const Capsule<R> &cp, const Box<R> &bx, unsigned cand, V3<R> &P1, V3<R> &P2) {
+    P1 = {0, 0, 0}; P2 = {0, 0, 0};
+    if ((cand & 7u) != 7u) {
+        const int face = int(cand & 7u), c = face > 2 ? face - 3 : face;
+        P1 = (cand & 8u) ? cp.B : cp.A; P2 = P1;
+        put3(P2, c, face > 2 ? sel3(bx.hi, c) : sel3(bx.lo, c));
+    }
+}
+
 // distance from the capsule to the box, radius already subtracted; exactly 0 when an endpoint lies inside the box
 // (Q11); -radius on the snap/crossing paths (Q14).
 template <class R, bool PTS>

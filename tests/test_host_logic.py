@@ -84,6 +84,26 @@ def test_device_geometry_headers_compiled_for_host_match_golden(golden, host_sim
         assert (hit == golden[f"{tag}_coll"]).all()
 
 
+def test_deferred_edge_evaluation_of_the_full_mode_kernel_matches_golden(golden, host_sim):
+    """nearest_points_kernel (rvs_distance_full.cuh) parks an undecided pair as a plan word + candidate distance and evaluates its box edges
+    later; the candidate points are rebuilt from PairPlan::cand. The same steps on the host (tests/host_sim) give the reference's golden
+    distances and nearest points bit for bit, and a fair share of the golden pairs does go through the parked path."""
+    f32p = ctypes.POINTER(ctypes.c_float)
+    for tag, thr in (("t4", 1e-4), ("t6", 1e-6)):
+        AB, r, obs, g = (np.ascontiguousarray(golden[f"{tag}_{k}"]) for k in ("AB", "r", "obs", "dist"))
+        K = AB.shape[0]
+        out, seq = np.empty((K, 8), np.float32), np.empty((K, 8), np.float32)
+        host_sim.hs_capsule_box_points_deferred_f32(ctypes.c_int64(K), AB.ctypes.data_as(f32p), r.ctypes.data_as(f32p), obs.ctypes.data_as(f32p),
+                                                    ctypes.c_float(thr), ctypes.c_float(1000.0), out.ctypes.data_as(f32p))
+        host_sim.hs_capsule_box_distance_f32(ctypes.c_int64(K), AB.ctypes.data_as(f32p), r.ctypes.data_as(f32p), obs.ctypes.data_as(f32p),
+                                             ctypes.c_float(thr), ctypes.c_float(1000.0), ctypes.c_int(1), seq.ctypes.data_as(f32p))
+        assert same(out[:, 0], g[:, 0]).all()
+        live = (g[:, 1] == 1) & (g[:, 0] > 0)
+        assert same(out[live, 2:], g[live, 2:]).all() and same(out[live, 2:], seq[live, 2:]).all()
+        parked = out[:, 1] == 0
+        assert parked.mean() > 0.1 and (parked & live).sum() > 100
+
+
 def test_device_fk_header_compiled_for_host_matches_oracle(ob, host_sim):
     f32p, f64p = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
     for rb in (robots.xarm6(), robots.planar(10), robots.spatial(22)):
