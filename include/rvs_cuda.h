@@ -191,7 +191,8 @@ int  rvs_is_valid_edges(rvs_handle h, const float *q1, const float *q2, int64_t 
  * After a collision (d_c == 0) the profile follows the reference's early-exit fill
  * (RealVectorSpace.cpp:370-378) and the nearest-point block of that configuration is unspecified
  * (large FULL batches do not touch it at all: csrc/rvs_distance_full.cuh computes the nearest points of the collision-free
- * configurations only; RVS_FULL_SPLIT=0 in the environment at rvs_create time selects the one-kernel path for A/B runs). */
+ * configurations only; RVS_FULL_SPLIT=0 in the environment at rvs_create time selects the one-kernel path for A/B runs;
+ * RVS_FULL_PARTS_TARGET=<blocks>, read per call, overrides how many obstacle ranges share a block of configurations — results do not depend on either). */
 int  rvs_distance(rvs_handle h, const float *q, int64_t N, int32_t mode,
                   float *d_c, float *profile, float *nearest);
 /* planes: R x M x L x 6 nearest-point sets of R root configurations; plane_idx[N] selects the root

@@ -17,6 +17,7 @@
 // distance_kernel<FULL> bit for bit (tests/test_gpu_parity.py compares the two on every precision).
 #pragma once
 #include <algorithm>
+#include <cstdlib>
 
 #include "rvs_kernels.cuh"
 
@@ -52,8 +53,10 @@ __global__ void __launch_bounds__(kListBlock) full_list_kernel(const KArgs a) {
 #define RVS_FULL_PARTS_TARGET 4440
 #endif
 inline int full_parts(int64_t N, int M) {
+    const char *e = std::getenv("RVS_FULL_PARTS_TARGET");              // (read per launch: tests use 1 to walk a long table in one range, tile after tile)
+    const int64_t target = e ? std::max(1, std::atoi(e)) : RVS_FULL_PARTS_TARGET;
     const int64_t blocks = (N + kBlock - 1) / kBlock;
-    const int64_t want = (RVS_FULL_PARTS_TARGET + blocks - 1) / blocks;
+    const int64_t want = (target + blocks - 1) / blocks;
     return int(std::max<int64_t>(1, std::min<int64_t>(want, M / 8)));
 }
 

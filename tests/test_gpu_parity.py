@@ -213,6 +213,27 @@ def test_full_mode_of_a_large_batch_equals_sequential_kernel(case, prec):
     eng.close()
 
 
+def test_full_mode_large_batch_one_range_over_two_obstacle_tiles(monkeypatch):
+    """RVS_FULL_PARTS_TARGET=1: every block of configurations walks the whole table itself — 300 obstacles = two shared-memory tiles, the
+    rings drained in between — instead of one short range per block; same bytes as the default split and as distance_kernel<FULL>."""
+    rb, mn, mx, g, tol = scenes.xarm6_scene(300, "D2", 0.8)
+    eng = make(rb, mn, mx, g, tol)
+    q = synthetic.configs(rb, 2500, seed=0x7117)
+    d1, p1, n1 = eng.distance(q, robots.DIST_FULL)
+    monkeypatch.setenv("RVS_FULL_PARTS_TARGET", "1")
+    k0 = eng.launch_count()
+    d2, p2, n2 = eng.distance(q, robots.DIST_FULL)
+    assert eng.launch_count() - k0 >= 3
+    monkeypatch.delenv("RVS_FULL_PARTS_TARGET")
+    eng.set_culling(False)
+    d0, p0, n0 = eng.distance(q, robots.DIST_FULL)
+    free = d0 > 0
+    assert 0.3 < free.mean() < 0.9
+    for d, p, n in ((d1, p1, n1), (d2, p2, n2)):
+        assert same(d, d0).all() and same(p, p0).all() and same(n[free], n0[free]).all()
+    eng.close()
+
+
 def test_full_mode_large_batch_with_a_misaligned_result_block():
     """A caller's nearest-point block that is only 4-byte aligned takes scalar stores instead of 8-byte ones: same bytes."""
     import torch
