@@ -214,3 +214,35 @@ def test_gpu_engine_matches_the_reference_realvectorspace_golden():
     mod, gold = _rvs_golden_module()
     for name, case in mod.cases().items():
         _check_space_against(lambda rb, prm: engine.Engine(rb, prm), name, case, gold, exact=False)
+
+
+@pytest.mark.gpu
+def test_gpu_full_mode_split_matches_the_reference_realvectorspace_golden():
+    """The golden configurations of the compiled reference, repeated until the batch is past the small-batch cross-over, so that FULL goes
+    through the three-launch path (csrc/rvs_distance_full.cuh): every replica reproduces the reference's d_c, profile and nearest points
+    (same tolerances as the test above) and is bit-identical to the small-batch kernel's answer for the same configuration."""
+    from rpmplv2_b200 import engine, robots
+    mod, gold = _rvs_golden_module()
+    checked = 0
+    for name, case in mod.cases().items():
+        rb, mn, mx, g, tol, thr, N = case
+        if len(mn) < 16:
+            continue                                                                         # short tables keep the one-kernel path
+        q, _, _ = mod.inputs(rb, N)
+        reps = -(-8300 // N)
+        eng = engine.Engine(rb, robots.default_params(equality_threshold=thr))
+        eng.set_obstacles(mn, mx, g, tol)
+        d_s, p_s, n_s = eng.distance(q, robots.DIST_FULL)                                    # one CTA per configuration
+        k0 = eng.launch_count()
+        d, p, near = eng.distance(np.tile(q, (reps, 1)), robots.DIST_FULL)
+        assert eng.launch_count() - k0 >= 3, name
+        G = lambda k: gold[f"{name}__{k}"]
+        free = G("d") > 0
+        for r in range(reps):
+            sl = slice(r * N, (r + 1) * N)
+            assert np.array_equal(d[sl], d_s) and np.array_equal(p[sl], p_s) and np.array_equal(near[sl][free], n_s[free]), name
+        assert ((d[:N] == 0) == (G("d") == 0)).all() and np.abs(d[:N] - G("d")).max() <= 1e-4 and np.abs(p[:N] - G("prof")).max() <= 1e-4
+        assert np.abs(near[:N][free] - G("near")[free]).max() <= 1e-4 and (near[:N][free] != G("near")[free]).mean() < 5e-3
+        eng.close()
+        checked += 1
+    assert checked >= 3
